@@ -1,0 +1,66 @@
+"""ctypes binding of libhiarch_b200.so (the C ABI declared in include/hiarch_b200.h).
+
+There is no CPU fallback: if the library is missing or an entry point is absent the import of
+an op fails loudly. torch tensors are only the buffer type -- every call passes raw device
+pointers, sizes and the current CUDA stream.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhiarch_b200.so")
+
+c_i32, c_i64, c_f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+c_int, c_vp = ctypes.c_int, ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/hiarch_b200.h declares
+PROTOTYPES = {
+    "hia_version": (c_int, []),
+    "hia_status_string": (ctypes.c_char_p, [c_int]),
+    "hia_last_cuda_error": (ctypes.c_char_p, []),
+    "hia_scatter_workspace_bytes": (c_i64, [c_i32]),
+    "hia_scatter_coo_sym": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_int, c_int,
+                                    c_vp, c_i32, c_vp, c_vp]),
+    "hia_oe_expected_pass": (c_int, [c_vp, c_i32, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp,
+                                     c_vp, c_vp, c_vp]),
+    "hia_oe_finalize": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_int,
+                                c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hia_oe_apply": (c_int, [c_vp, c_vp, c_i32, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_int,
+                             c_vp]),
+    "hia_similarity_workspace_bytes": (c_i64, [c_i32, c_i32, c_int]),
+    "hia_similarity": (c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_int, c_int, c_i32, c_i32,
+                               c_i32, c_vp, c_i64, c_vp]),
+}
+
+_lib = None
+
+
+class HiaError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library and bind every prototype. Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HiaError(
+            f"{LIB_PATH} not found: build it with `python -m hiarch_b200.build` "
+            "(hiarch_b200 has no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        lib = load()
+        msg = lib.hia_status_string(status).decode()
+        if status == -3:
+            msg += ": " + lib.hia_last_cuda_error().decode()
+        raise HiaError(f"{what} failed: {msg} ({status})")

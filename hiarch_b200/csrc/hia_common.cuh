@@ -1,0 +1,88 @@
+// Shared device/host helpers for the hiarch_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+#include "../../include/hiarch_b200.h"
+
+#define HIA_API extern "C" __attribute__((visibility("default")))
+
+namespace hia {
+
+void set_last_cuda_error(cudaError_t e);
+
+inline int cuda_ok(cudaError_t e) {
+  if (e == cudaSuccess) return HIA_OK;
+  set_last_cuda_error(e);
+  return HIA_ERR_CUDA;
+}
+
+#define HIA_CUDA(call)                                   \
+  do {                                                   \
+    int _s = ::hia::cuda_ok((call));                     \
+    if (_s != HIA_OK) return _s;                         \
+  } while (0)
+
+#define HIA_LAUNCH_CHECK() HIA_CUDA(cudaGetLastError())
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kNumSMs = 148;   // B200
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Positive floats (and +inf) order like their bit patterns.
+__device__ __forceinline__ void atomic_min_pos_float(float* addr, float v) {
+  atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+// Order-preserving float <-> uint32 key (any sign): smaller float <=> smaller key.
+__host__ __device__ __forceinline__ unsigned int float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+  unsigned int b = __float_as_uint(f);
+#else
+  unsigned int b; memcpy(&b, &f, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(unsigned int k) {
+  unsigned int b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+// streaming 128-bit accesses (no L1 allocation)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+}  // namespace hia

@@ -1,0 +1,29 @@
+// Library-level entry points: version, status strings, last CUDA error.
+#include "hia_common.cuh"
+
+namespace hia {
+static thread_local char g_last_err[256] = "";
+void set_last_cuda_error(cudaError_t e) {
+  const char* s = cudaGetErrorString(e);
+  strncpy(g_last_err, s ? s : "unknown", sizeof(g_last_err) - 1);
+  g_last_err[sizeof(g_last_err) - 1] = 0;
+  cudaGetLastError();  // clear the sticky-free error state
+}
+}  // namespace hia
+
+HIA_API int hia_version(void) { return 100; }
+
+HIA_API const char* hia_last_cuda_error(void) { return hia::g_last_err; }
+
+HIA_API const char* hia_status_string(int s) {
+  switch (s) {
+    case HIA_OK: return "ok";
+    case HIA_ERR_BAD_ARG: return "bad argument";
+    case HIA_ERR_ALIGN: return "alignment requirement not met";
+    case HIA_ERR_CUDA: return "CUDA error";
+    case HIA_ERR_UNSUPPORTED: return "unsupported size";
+    case HIA_ERR_WORKSPACE: return "workspace too small";
+    case HIA_ERR_ARCH: return "device is not sm_100";
+    default: return "unknown status";
+  }
+}

@@ -1,0 +1,448 @@
+// a4/a5: expected contacts per diagonal, O/E distance normalisation, log.
+//
+// Replaces HiCMtx.obs_d_exp(mode='sgd_mean') -- publish/new_hic_class.py:1121-1290
+// (_sgd_mean :1182-1216, monotone clamp :1251-1261, per-diagonal divide :1263-1268, inter
+// blocks :1272-1282) -- and ArrayHiCMtx.log (:2076-2094).
+//
+// All three kernels are HBM-bound streaming passes over an fp32 map:
+//   intra_diag_kernel  reads the upper triangle of every intra block once   (4 B/cell read)
+//   inter_block_kernel reads every upper inter block once                   (4 B/cell read)
+//   oe_apply_kernel    reads + writes the full map once                     (8 B/cell)
+// i.e. 2 B/cell + 8 B/cell = 10 B/cell of the full symmetric map.
+// Reductions accumulate in fp64 (the reference is fp64 throughout).
+#include "hia_common.cuh"
+
+namespace hia {
+namespace {
+
+constexpr int kDiagThreads = 256;             // one float4 column group per thread
+constexpr int kDiagWindow = kDiagThreads * 4; // diagonals covered by one CTA
+constexpr int kDiagRowGroups = 32;            // 4-row groups per CTA  (128 rows)
+
+// ---------------------------------------------------------------------------------------
+// Per-diagonal sums of one intra block.
+//
+// Work item = (diagonal window w, row chunk). Thread L owns the 7 diagonals
+// D + [-3, 3], D = 4 (L + 256 w).  For the 4-row group rho (global rows 4 rho .. 4 rho + 3) it
+// loads the 16-byte aligned float4 at global column 4 (L + 256 w + rho) of each row: the load
+// address advances by one float4 per row group, so the diagonals a thread sees stay fixed --
+// coalesced 128-bit loads (a warp reads 512 contiguous bytes per row), no shared memory, no
+// shuffles in the loop; the 3-diagonal overlap between neighbouring lanes is merged by the
+// fp64 atomics at the end.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDiagThreads)
+intra_diag_kernel(const float* __restrict__ map, long long ld, const int* __restrict__ chr_start,
+                  double* __restrict__ diag_sum, float* __restrict__ diag_minpos, int row_chunks) {
+  const int c = blockIdx.y;
+  const int s = chr_start[c], e = chr_start[c + 1] - 1;   // inclusive bin range
+  const int n = e - s + 1;
+  if (n <= 0) return;
+  const int w = blockIdx.x / row_chunks;
+  const int chunk = blockIdx.x % row_chunks;
+  // global 4-row groups covering [s, e]
+  const int rho_first = s >> 2;
+  const int rho_lo = rho_first + chunk * kDiagRowGroups;
+  const int rho_hi = min(rho_lo + kDiagRowGroups, (e >> 2) + 1);
+  if (rho_lo >= rho_hi) return;
+  const int D = 4 * (threadIdx.x + kDiagThreads * w);     // centre diagonal of this thread
+  if (D - 3 > n - 1) {
+    // whole warp beyond the last diagonal? (D grows with threadIdx) -> nothing to do
+    if (4 * ((threadIdx.x & ~31) + kDiagThreads * w) - 3 > n - 1) return;
+  }
+  double acc[7];
+  float mn[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { acc[k] = 0.0; mn[k] = INFINITY; }
+
+  for (int rho = rho_lo; rho < rho_hi; ++rho) {
+    const int gc0 = 4 * rho + D;                           // aligned global column of the float4
+    if (gc0 > e) break;                                    // later row groups are further right
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int gr = 4 * rho + rr;
+      if (gr < s || gr > e) continue;
+      if (gc0 + 3 < gr) continue;                          // float4 entirely below the diagonal
+      const float4 v = *reinterpret_cast<const float4*>(map + (long long)gr * ld + gc0);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int gc = gc0 + cc;
+        if (gc >= gr && gc <= e) {
+          const int k = cc - rr + 3;                       // diagonal D + (cc - rr)
+          acc[k] += (double)vv[cc];
+          if (vv[cc] > 0.f) mn[k] = fminf(mn[k], vv[cc]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int d = D + k - 3;
+    if (d >= 0 && d < n) {
+      if (acc[k] != 0.0) atomicAdd(&diag_sum[s + d], acc[k]);
+      if (mn[k] != INFINITY) atomic_min_pos_float(&diag_minpos[s + d], mn[k]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Upper inter blocks (a < b): sum, non-zero count, min positive per block.
+// CTA = (row, column chunk); columns right of the row's chromosome only.
+// ---------------------------------------------------------------------------------------
+constexpr int kInterThreads = 256;
+constexpr int kInterCols = kInterThreads * 4 * 4;   // 4 float4 per thread per row
+
+__global__ void __launch_bounds__(kInterThreads)
+inter_block_kernel(const float* __restrict__ map, int n, long long ld,
+                   const int* __restrict__ chr_start, int n_chr,
+                   const short* __restrict__ bin_chr, double* __restrict__ inter_sum,
+                   unsigned long long* __restrict__ inter_nnz, float* __restrict__ inter_minpos,
+                   int rows_per_cta) {
+  extern __shared__ unsigned char smem_raw[];
+  double* s_sum = reinterpret_cast<double*>(smem_raw);
+  unsigned long long* s_nnz = reinterpret_cast<unsigned long long*>(s_sum + n_chr);
+  float* s_min = reinterpret_cast<float*>(s_nnz + n_chr);
+
+  const int r0 = blockIdx.y * rows_per_cta;
+  if (r0 >= n) return;
+  const int r1 = min(r0 + rows_per_cta, n);
+  const int cbase = blockIdx.x * kInterCols;
+  int a_prev = -1;
+  for (int r = r0; r < r1; ++r) {
+    const int a = bin_chr[r];
+    const int col_lo = chr_start[a + 1];                  // first column of the next chromosome
+    if (cbase + kInterCols <= col_lo) continue;           // chunk entirely left of the inter part
+    if (a != a_prev) {
+      if (a_prev >= 0) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < n_chr; b += blockDim.x) {
+          if (s_nnz[b] | (s_sum[b] != 0.0)) {
+            atomicAdd(&inter_sum[a_prev * n_chr + b], s_sum[b]);
+            atomicAdd(&inter_nnz[a_prev * n_chr + b], s_nnz[b]);
+          }
+          if (s_min[b] != INFINITY) atomic_min_pos_float(&inter_minpos[a_prev * n_chr + b], s_min[b]);
+        }
+      }
+      __syncthreads();
+      for (int b = threadIdx.x; b < n_chr; b += blockDim.x) { s_sum[b] = 0.0; s_nnz[b] = 0ull; s_min[b] = INFINITY; }
+      __syncthreads();
+      a_prev = a;
+    }
+    const float* row = map + (long long)r * ld;
+    int cur_b = -1;
+    double sum = 0.0;
+    unsigned long long cnt = 0;
+    float mn = INFINITY;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int c0 = cbase + (it * kInterThreads + threadIdx.x) * 4;
+      if (c0 + 3 < col_lo || c0 >= n) continue;
+      const float4 v = *reinterpret_cast<const float4*>(row + c0);   // ld % 4 == 0, ld >= n
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int gc = c0 + cc;
+        if (gc < col_lo || gc >= n) continue;
+        const int b = bin_chr[gc];
+        if (b != cur_b) {
+          if (cur_b >= 0) {
+            atomicAdd(&s_sum[cur_b], sum);
+            atomicAdd(&s_nnz[cur_b], cnt);
+            if (mn != INFINITY) atomic_min_pos_float(&s_min[cur_b], mn);
+          }
+          cur_b = b; sum = 0.0; cnt = 0; mn = INFINITY;
+        }
+        sum += (double)vv[cc];
+        cnt += (vv[cc] != 0.f);
+        if (vv[cc] > 0.f) mn = fminf(mn, vv[cc]);
+      }
+    }
+    if (cur_b >= 0) {
+      atomicAdd(&s_sum[cur_b], sum);
+      atomicAdd(&s_nnz[cur_b], cnt);
+      if (mn != INFINITY) atomic_min_pos_float(&s_min[cur_b], mn);
+    }
+  }
+  if (a_prev >= 0) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < n_chr; b += blockDim.x) {
+      if (s_nnz[b] | (s_sum[b] != 0.0)) {
+        atomicAdd(&inter_sum[a_prev * n_chr + b], s_sum[b]);
+        atomicAdd(&inter_nnz[a_prev * n_chr + b], s_nnz[b]);
+      }
+      if (s_min[b] != INFINITY) atomic_min_pos_float(&inter_minpos[a_prev * n_chr + b], s_min[b]);
+    }
+  }
+}
+
+__global__ void init_expected_kernel(double* diag_sum, float* diag_minpos, int n, double* inter_sum,
+                                     unsigned long long* inter_nnz, float* inter_minpos, int cc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { diag_sum[i] = 0.0; diag_minpos[i] = INFINITY; }
+  if (i < cc) { inter_sum[i] = 0.0; inter_nnz[i] = 0ull; inter_minpos[i] = INFINITY; }
+}
+
+// ---------------------------------------------------------------------------------------
+// Finalize: one CTA per chromosome. SGD pooling, un-flushed last group, monotone clamp.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxGroups = 512;
+constexpr int kFinThreads = 1024;
+
+__global__ void __launch_bounds__(kFinThreads)
+finalize_intra_kernel(const double* __restrict__ diag_sum, const float* __restrict__ diag_minpos,
+                      const int* __restrict__ chr_start, const int* __restrict__ pool_gid,
+                      const int* __restrict__ use_code, int clamp, double* __restrict__ expected,
+                      float* __restrict__ inv_expected, float* __restrict__ min_pos_oe) {
+  __shared__ double g_sum[kMaxGroups];
+  __shared__ double g_cnt[kMaxGroups];
+  __shared__ double s_scan[kFinThreads];
+  __shared__ double s_carry;
+  __shared__ int s_has_carry;
+  __shared__ float s_min[32];
+
+  const int c = blockIdx.x;
+  const int s = chr_start[c];
+  const int n = chr_start[c + 1] - s;
+  if (n <= 0) return;
+  const int tid = threadIdx.x;
+  for (int g = tid; g < kMaxGroups; g += blockDim.x) { g_sum[g] = 0.0; g_cnt[g] = 0.0; }
+  __syncthreads();
+  // pooled sums: an 'all'-type diagonal d>0 holds both +-d: sum = 2 * upper sum, 2 (n-d) cells
+  for (int d = tid; d < n; d += blockDim.x) {
+    const int g = pool_gid[s + d];
+    if (g >= 0) {
+      const double mult = (d == 0) ? 1.0 : 2.0;
+      atomicAdd(&g_sum[g], mult * diag_sum[s + d]);
+      atomicAdd(&g_cnt[g], mult * (double)(n - d));
+    }
+  }
+  __syncthreads();
+  const double diag0_mean = diag_sum[s] / (double)n;
+  // n <= 1: M / mean(M); all-zero block: unchanged  (new_hic_class.py:1229-1236)
+  // -> both fall out of the generic path: exp[0] = mean(diag) and exp <= 0 is skipped.
+
+  if (tid == 0) { s_carry = 0.0; s_has_carry = 0; }
+  __syncthreads();
+  float my_min = INFINITY;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int d = base + tid;
+    double x = 0.0;
+    bool valid = d < n;
+    if (valid) {
+      const int code = use_code[s + d];
+      if (code < 0) {
+        x = diag0_mean;
+      } else {
+        const int g = code >> 1;
+        x = g_sum[g] / g_cnt[g];
+        if ((code & 1) && x == 0.0) x = 1.0;
+      }
+    }
+    double ex = x;
+    if (clamp) {
+      // exp'[d] = x > pmin ? pmin : x, pmin = min over the non-zero x before d (carry included)
+      // exclusive prefix-min over non-zero values: Hillis-Steele in shared memory
+      const double big = INFINITY;
+      s_scan[tid] = (valid && x != 0.0) ? x : big;
+      __syncthreads();
+      for (int off = 1; off < blockDim.x; off <<= 1) {
+        double other = (tid >= off) ? s_scan[tid - off] : big;
+        __syncthreads();
+        s_scan[tid] = fmin(s_scan[tid], other);
+        __syncthreads();
+      }
+      double pmin = (tid > 0) ? s_scan[tid - 1] : big;     // exclusive
+      if (s_has_carry) pmin = fmin(pmin, s_carry);
+      if (valid && pmin != big && x > pmin) ex = pmin;
+      __syncthreads();
+      if (tid == blockDim.x - 1) {
+        double incl = s_scan[tid];
+        if (incl != big) {
+          s_carry = s_has_carry ? fmin(s_carry, incl) : incl;
+          s_has_carry = 1;
+        }
+      }
+      __syncthreads();
+    }
+    if (valid) {
+      expected[s + d] = ex;
+      const float inv = (ex > 0.0) ? (float)(1.0 / ex) : 1.0f;   // exp <= 0 -> skipped (:1264)
+      inv_expected[s + d] = inv;
+      const float mp = diag_minpos[s + d];
+      if (mp != INFINITY) my_min = fminf(my_min, mp * inv);
+    }
+  }
+  my_min = warp_min(my_min);
+  if ((tid & 31) == 0) s_min[tid >> 5] = my_min;
+  __syncthreads();
+  if (tid < 32) {
+    float v = (tid < (blockDim.x >> 5)) ? s_min[tid] : INFINITY;
+    v = warp_min(v);
+    if (tid == 0 && v != INFINITY && v > 0.f) atomic_min_pos_float(min_pos_oe, v);
+  }
+}
+
+__global__ void finalize_inter_kernel(const double* __restrict__ inter_sum,
+                                      const unsigned long long* __restrict__ inter_nnz,
+                                      const float* __restrict__ inter_minpos, int n_chr,
+                                      float* __restrict__ inter_inv, float* __restrict__ min_pos_oe) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_chr * n_chr) return;
+  const int a = i / n_chr, b = i % n_chr;
+  if (a == b) { inter_inv[i] = 1.f; return; }
+  const int u = (a < b) ? i : (b * n_chr + a);                  // stats live in the upper block
+  const unsigned long long cnt = inter_nnz[u];
+  float inv = 1.f;
+  if (cnt > 0) {
+    const double mean = inter_sum[u] / (double)cnt;             // mean of non-zero cells (:1278-1280)
+    inv = (float)(1.0 / mean);
+    const float mp = inter_minpos[u];
+    if (a < b && mp != INFINITY) {
+      const float x = mp * inv;
+      if (x > 0.f) atomic_min_pos_float(min_pos_oe, x);
+    }
+  }
+  inter_inv[i] = inv;
+}
+
+__global__ void init_min_kernel(float* p) { *p = INFINITY; }
+
+// ---------------------------------------------------------------------------------------
+// Apply: out = map * inv; optional log. One thread per float4, rows over blockIdx.y.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+oe_apply_kernel(const float* __restrict__ map, float* __restrict__ out, int n, long long ld,
+                const int* __restrict__ chr_start, int n_chr, const short* __restrict__ bin_chr,
+                const float* __restrict__ inv_expected, const float* __restrict__ inter_inv,
+                const float* __restrict__ min_pos_oe, int flags) {
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c0 >= n) return;
+  const bool do_log = flags & HIA_OE_LOG;
+  const bool only_intra = flags & HIA_OE_ONLY_INTRA;
+  float fill = 0.f;
+  if (do_log) {
+    const float m = *min_pos_oe;
+    fill = (m == INFINITY) ? 0.f : log1pf(m);
+  }
+  int cb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cb[j] = bin_chr[min(c0 + j, n - 1)];
+  for (int r = blockIdx.y; r < n; r += gridDim.y) {
+    const int a = bin_chr[r];
+    const int s = chr_start[a];
+    const float* src = map + (long long)r * ld + c0;
+    float v[4];
+    if (c0 + 3 < n) {
+      const float4 t = ld_stream4(src);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (c0 + j < n) ? src[j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gc = c0 + j;
+      float x;
+      if (cb[j] == a) {
+        const int d = abs(gc - r);
+        x = v[j] * inv_expected[s + d];
+      } else if (only_intra) {
+        x = 0.f;
+      } else {
+        x = v[j] * inter_inv[a * n_chr + cb[j]];
+      }
+      if (do_log) x = (x > 0.f) ? log1pf(x) : fill;
+      v[j] = x;
+    }
+    float* dst = out + (long long)r * ld + c0;
+    if (c0 + 3 < n) {
+      st_stream4(dst, make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+      for (int j = 0; j < 4 && c0 + j < n; ++j) dst[j] = v[j];
+    }
+  }
+}
+
+}  // namespace
+}  // namespace hia
+
+HIA_API int hia_oe_expected_pass(const float* map, int32_t n, int64_t ld, const int32_t* chr_start,
+                                 const int32_t* chr_start_host, int32_t n_chr, double* diag_sum,
+                                 float* diag_minpos, double* inter_sum,
+                                 unsigned long long* inter_nnz, float* inter_minpos,
+                                 const int16_t* bin_chr, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!map || !chr_start || !chr_start_host || !diag_sum || !diag_minpos || !inter_sum ||
+      !inter_nnz || !inter_minpos || !bin_chr || n <= 0 || n_chr <= 0 || ld < n)
+    return HIA_ERR_BAD_ARG;
+  if (!aligned16(map) || (ld & 3)) return HIA_ERR_ALIGN;
+  if (n_chr > 1024) return HIA_ERR_UNSUPPORTED;
+  const int cc = n_chr * n_chr;
+  const int cnt = max(n, cc);
+  init_expected_kernel<<<(cnt + 255) / 256, 256, 0, stream>>>(diag_sum, diag_minpos, n, inter_sum,
+                                                             inter_nnz, inter_minpos, cc);
+  HIA_LAUNCH_CHECK();
+  int max_len = 0;
+  for (int c = 0; c < n_chr; ++c) max_len = max(max_len, chr_start_host[c + 1] - chr_start_host[c]);
+  if (max_len <= 0) return HIA_ERR_BAD_ARG;
+  // +1 chunk: chromosome starts are not 4-row aligned
+  const int row_chunks = (max_len + 3) / 4 / kDiagRowGroups + 2;
+  const int windows = (max_len + 3 + kDiagWindow - 1) / kDiagWindow;
+  dim3 grid_d(windows * row_chunks, n_chr);
+  intra_diag_kernel<<<grid_d, kDiagThreads, 0, stream>>>(map, ld, chr_start, diag_sum, diag_minpos,
+                                                         row_chunks);
+  HIA_LAUNCH_CHECK();
+  if (n_chr > 1) {
+    const int rows_per_cta = 8;
+    dim3 grid_i((n + kInterCols - 1) / kInterCols, (n + rows_per_cta - 1) / rows_per_cta);
+    const size_t sh = (size_t)n_chr * (8 + 8 + 4);
+    inter_block_kernel<<<grid_i, kInterThreads, sh, stream>>>(map, n, ld, chr_start, n_chr, bin_chr,
+                                                              inter_sum, inter_nnz, inter_minpos,
+                                                              rows_per_cta);
+    HIA_LAUNCH_CHECK();
+  }
+  return HIA_OK;
+}
+
+HIA_API int hia_oe_finalize(const double* diag_sum, const float* diag_minpos, const double* inter_sum,
+                            const unsigned long long* inter_nnz, const float* inter_minpos,
+                            const int32_t* chr_start, int32_t n_chr, int32_t n,
+                            const int32_t* pool_gid, const int32_t* use_code, int counts_must_decrese,
+                            double* expected, float* inv_expected, float* inter_inv,
+                            float* min_pos_oe, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!diag_sum || !diag_minpos || !inter_sum || !inter_nnz || !inter_minpos || !chr_start ||
+      !pool_gid || !use_code || !expected || !inv_expected || !inter_inv || !min_pos_oe ||
+      n <= 0 || n_chr <= 0)
+    return HIA_ERR_BAD_ARG;
+  init_min_kernel<<<1, 1, 0, stream>>>(min_pos_oe);
+  HIA_LAUNCH_CHECK();
+  finalize_intra_kernel<<<n_chr, kFinThreads, 0, stream>>>(diag_sum, diag_minpos, chr_start, pool_gid,
+                                                           use_code, counts_must_decrese ? 1 : 0,
+                                                           expected, inv_expected, min_pos_oe);
+  HIA_LAUNCH_CHECK();
+  const int cc = n_chr * n_chr;
+  finalize_inter_kernel<<<(cc + 255) / 256, 256, 0, stream>>>(inter_sum, inter_nnz, inter_minpos, n_chr,
+                                                              inter_inv, min_pos_oe);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
+HIA_API int hia_oe_apply(const float* map, float* out, int32_t n, int64_t ld, const int32_t* chr_start,
+                         int32_t n_chr, const int16_t* bin_chr, const float* inv_expected,
+                         const float* inter_inv, const float* min_pos_oe, int flags, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!map || !out || !chr_start || !bin_chr || !inv_expected || !inter_inv || !min_pos_oe ||
+      n <= 0 || n_chr <= 0 || ld < n)
+    return HIA_ERR_BAD_ARG;
+  if (!aligned16(map) || !aligned16(out) || (ld & 3)) return HIA_ERR_ALIGN;
+  const int threads = 256;
+  dim3 grid((n + threads * 4 - 1) / (threads * 4), min(n, 2048));
+  oe_apply_kernel<<<grid, threads, 0, stream>>>(map, out, n, ld, chr_start, n_chr, bin_chr,
+                                                inv_expected, inter_inv, min_pos_oe, flags);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}

@@ -1,0 +1,189 @@
+// a1/a2: sparse (i, j, v) -> dense symmetric fp32 map.
+//
+// Replaces read_sps_file -> coo_matrix -> tocsr (duplicates summed), SpsHiCMtx.to_all
+// (triu(M,0).T + triu(M,1)) and SpsHiCMtx.to_dense (absent cells 0, or min(data) when
+// has_neg; explicit zero entries stay 0) -- publish/new_hic_class.py:2576-2602, :2229-2246,
+// :2209-2224. Per-block min fill follows yield_by_chro(triu=True)+to_dense as used by
+// complex/src/main_local.py:112-115.
+//
+// HBM-bound: 12 B/nnz read + 4 B/cell written (fill) + 4..8 B/nnz scattered.
+// Pipeline: [block-min reduce] -> fill -> [zero the present cells] -> RED.ADD scatter.
+// Duplicates are summed with fp32 RED atomics; with no duplicates the result is bit-exact
+// (0 + v == v), which is the case for every file the pipeline writes.
+#include "hia_common.cuh"
+
+namespace hia {
+namespace {
+
+constexpr int kMaxChr = 1024;
+
+__device__ __forceinline__ int find_chr(const int* s_start, int n_chr, int bin) {
+  // largest c with s_start[c] <= bin
+  int lo = 0, hi = n_chr - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (s_start[mid] <= bin) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void init_keys_kernel(unsigned int* keys, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) keys[i] = 0xffffffffu;
+}
+
+// min over valid entries, per chromosome-pair block (BLOCK_MIN) and overall (slot C*C).
+__global__ void __launch_bounds__(256)
+block_min_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
+                 const float* __restrict__ vals, long long nnz, int n, int mtx_type,
+                 const int* __restrict__ chr_start, int n_chr, int per_block,
+                 unsigned int* __restrict__ keys) {
+  extern __shared__ int s_start[];
+  for (int i = threadIdx.x; i <= n_chr; i += blockDim.x) s_start[i] = chr_start[i];
+  __syncthreads();
+  const int slot_all = n_chr * n_chr;
+  int cur_slot = -1;
+  unsigned int cur_key = 0xffffffffu;
+  unsigned int all_key = 0xffffffffu;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+    int r = rows[e], c = cols[e];
+    if (r < 0 || c < 0 || r >= n || c >= n) continue;
+    if (mtx_type == HIA_MTX_TRIU && c < r) continue;
+    unsigned int k = float_to_ordered(vals[e]);
+    all_key = min(all_key, k);
+    if (per_block) {
+      int slot = find_chr(s_start, n_chr, r) * n_chr + find_chr(s_start, n_chr, c);
+      if (slot != cur_slot) {
+        if (cur_slot >= 0) atomicMin(&keys[cur_slot], cur_key);
+        cur_slot = slot;
+        cur_key = k;
+      } else {
+        cur_key = min(cur_key, k);
+      }
+    }
+  }
+  if (per_block && cur_slot >= 0) atomicMin(&keys[cur_slot], cur_key);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) all_key = min(all_key, __shfl_xor_sync(0xffffffffu, all_key, o));
+  if ((threadIdx.x & 31) == 0 && all_key != 0xffffffffu) atomicMin(&keys[slot_all], all_key);
+}
+
+// out[r][c] = fill(r, c). One thread per 4 columns (128-bit stores), rows over blockIdx.y.
+__global__ void __launch_bounds__(256)
+fill_kernel(float* __restrict__ out, int n, long long ld, int fill_mode, int mtx_type,
+            const int* __restrict__ chr_start, int n_chr, const unsigned int* __restrict__ keys) {
+  extern __shared__ int s_start[];
+  for (int i = threadIdx.x; i <= n_chr; i += blockDim.x) s_start[i] = chr_start[i];
+  __syncthreads();
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c0 >= n) return;
+  float gfill = 0.f;
+  if (fill_mode == HIA_FILL_MIN) {
+    unsigned int k = keys[n_chr * n_chr];
+    gfill = (k == 0xffffffffu) ? 0.f : ordered_to_float(k);
+  }
+  int cb[4];
+  if (fill_mode == HIA_FILL_BLOCK_MIN) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cb[j] = find_chr(s_start, n_chr, min(c0 + j, n - 1));
+  }
+  for (int r = blockIdx.y; r < n; r += gridDim.y) {
+    float v[4] = {gfill, gfill, gfill, gfill};
+    if (fill_mode == HIA_FILL_BLOCK_MIN) {
+      int a = find_chr(s_start, n_chr, r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int b = cb[j];
+        // triu input: only upper blocks hold entries; the lower block mirrors the upper one
+        int slot = (mtx_type == HIA_MTX_TRIU && b < a) ? (b * n_chr + a) : (a * n_chr + b);
+        unsigned int k = keys[slot];
+        v[j] = (k == 0xffffffffu) ? 0.f : ordered_to_float(k);
+      }
+    }
+    float* p = out + (long long)r * ld + c0;
+    if (c0 + 3 < n) {
+      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      for (int j = 0; j < 4 && c0 + j < n; ++j) p[j] = v[j];
+    }
+  }
+}
+
+template <bool kAdd>
+__global__ void __launch_bounds__(256)
+scatter_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
+               const float* __restrict__ vals, long long nnz, int n, int mtx_type,
+               float* __restrict__ out, long long ld) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+    int r = rows[e], c = cols[e];
+    if (r < 0 || c < 0 || r >= n || c >= n) continue;
+    if (mtx_type == HIA_MTX_TRIU && c < r) continue;
+    if (kAdd) {
+      float v = vals[e];
+      atomicAdd(out + (long long)r * ld + c, v);
+      if (mtx_type == HIA_MTX_TRIU && r != c) atomicAdd(out + (long long)c * ld + r, v);
+    } else {
+      out[(long long)r * ld + c] = 0.f;
+      if (mtx_type == HIA_MTX_TRIU && r != c) out[(long long)c * ld + r] = 0.f;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace hia
+
+HIA_API int64_t hia_scatter_workspace_bytes(int32_t n_chr) {
+  if (n_chr < 1) n_chr = 1;
+  return (int64_t)((int64_t)n_chr * n_chr + 1) * 4;
+}
+
+HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const float* vals,
+                                int64_t nnz, int32_t n, float* out, int64_t ld, int mtx_type,
+                                int fill_mode, const int32_t* chr_start, int32_t n_chr,
+                                void* workspace, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!out || n <= 0 || ld < n || nnz < 0) return HIA_ERR_BAD_ARG;
+  if (nnz > 0 && (!rows || !cols || !vals)) return HIA_ERR_BAD_ARG;
+  if (mtx_type != HIA_MTX_TRIU && mtx_type != HIA_MTX_ALL) return HIA_ERR_BAD_ARG;
+  if (fill_mode < HIA_FILL_ZERO || fill_mode > HIA_FILL_BLOCK_MIN) return HIA_ERR_BAD_ARG;
+  if (!aligned16(out) || (ld & 3)) return HIA_ERR_ALIGN;
+  if (fill_mode != HIA_FILL_ZERO && (!workspace || !chr_start || n_chr < 1)) return HIA_ERR_BAD_ARG;
+  if (n_chr > kMaxChr) return HIA_ERR_UNSUPPORTED;
+
+  const int threads = 256;
+  const int grid_e = (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (nnz + threads - 1) / threads));
+  if (fill_mode == HIA_FILL_ZERO) {
+    if (ld == n) {
+      HIA_CUDA(cudaMemsetAsync(out, 0, (size_t)n * n * sizeof(float), stream));
+    } else {
+      HIA_CUDA(cudaMemset2DAsync(out, (size_t)ld * 4, 0, (size_t)n * 4, n, stream));
+    }
+  } else {
+    unsigned int* keys = static_cast<unsigned int*>(workspace);
+    const int nk = n_chr * n_chr + 1;
+    init_keys_kernel<<<(nk + 255) / 256, 256, 0, stream>>>(keys, nk);
+    HIA_LAUNCH_CHECK();
+    const size_t sh = (size_t)(n_chr + 1) * sizeof(int);
+    if (nnz > 0) {
+      block_min_kernel<<<grid_e, threads, sh, stream>>>(rows, cols, vals, nnz, n, mtx_type,
+                                                          chr_start, n_chr,
+                                                          fill_mode == HIA_FILL_BLOCK_MIN, keys);
+      HIA_LAUNCH_CHECK();
+    }
+    dim3 grid((n + threads * 4 - 1) / (threads * 4), min(n, 4096));
+    fill_kernel<<<grid, threads, sh, stream>>>(out, n, ld, fill_mode, mtx_type, chr_start, n_chr, keys);
+    HIA_LAUNCH_CHECK();
+    if (nnz > 0) {
+      scatter_kernel<false><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld);
+      HIA_LAUNCH_CHECK();
+    }
+  }
+  if (nnz > 0) {
+    scatter_kernel<true><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld);
+    HIA_LAUNCH_CHECK();
+  }
+  return HIA_OK;
+}

@@ -1,0 +1,498 @@
+// a8: row x row similarity of an m x k map block -- cosine distance (get_adj_mtx ==
+// squareform(pdist(M,'cosine')), publish/complex/src/S1_get_adj_mtx.py:8-14) and Pearson
+// correlation (the same contraction on row-centred rows; north-star flavour).
+//
+// out[i][j] = f( sum_k xn[i][k] * xn[j][k] ),  xn = unit-norm (optionally centred) rows.
+//
+// Design (sm_100a):
+//   row_prep_kernel   fp64 row mean / norm, writes xn split into two TF32-exact fp32 planes
+//                     hi = rna_tf32(xn), lo = rna_tf32(xn - hi)           (12 B/cell, HBM-bound)
+//   syrk_tf32x3_kernel  persistent, warp-specialised tcgen05 kernel:
+//       warp 0   TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, 128 B = 32 fp32 per row)
+//       warp 1   MMA issuer     (tcgen05.mma.cta_group::1.kind::tf32, M=128, N=256, K=8 per
+//                                instruction; 3 MMAs per k-step: hi.hi + hi.lo + lo.hi)
+//       warps 2-5 epilogue      (tcgen05.ld 32x32b.x32 -> fp32 running tile -> 1-c / c ->
+//                                coalesced direct + mirrored stores)
+//     Accumulators live in tensor memory (2 x 256 columns, double buffered). To bound the
+//     rounding of long fp32 accumulation chains the K loop is cut into chunks (k_chunk
+//     elements): each chunk accumulates in TMEM, the epilogue folds it into a per-CTA fp32
+//     running tile (L2 resident, coalesced) while the next chunk's MMAs run.
+//   Only tiles touching the upper triangle (and the requested |i-j| band) are computed; the
+//   lower triangle is written as the exact mirror, the diagonal as the exact constant.
+//
+// 3xTF32 error budget: |hi.hi + hi.lo + lo.hi - x.y| <= ~2^-21 |x||y| per product; fp32
+// accumulation over <= k_chunk/8 MMA steps, then RN fp32 adds of <= k/k_chunk partials.
+#include <cuda.h>
+#include "hia_common.cuh"
+
+namespace hia {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 32;                         // fp32 elements per k-block = 128 B (one SW128 atom)
+constexpr int UMMA_K = 8;                      // tf32
+constexpr int STAGES = 2;
+constexpr int A_BYTES = BM * BK * 4;           // 16 KB
+constexpr int B_BYTES = BN * BK * 4;           // 32 KB
+constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // hi + lo planes: 96 KB
+constexpr int EPI_WARPS = 4;
+constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
+constexpr int TRANS_PAD = 33;
+constexpr int SMEM_TILES = STAGES * STAGE_BYTES;                      // 196608
+constexpr int SMEM_TRANS = EPI_WARPS * 32 * TRANS_PAD * 4;            // 16896
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + SMEM_TILES + SMEM_TRANS + 256 /*barriers*/;
+constexpr int TMEM_COLS = 512;
+constexpr unsigned long long kSpinLimit = 1ull << 31;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  unsigned long long spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, set 1) |
+//   [32,46) SBO >> 4 = 1024 B (8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a/b=TF32 [7,10),[10,13)=2,
+// K-major both, N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                            ((uint32_t)(BM >> 4) << 24);
+
+struct TileCoord { int m_blk; int n_blk; };
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                   const TileCoord* __restrict__ tiles, int num_tiles, int m, int num_k_blocks,
+                   int kb_per_chunk, float* __restrict__ out, long long ld_out,
+                   float* __restrict__ running, int flavour) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* s_trans = reinterpret_cast<float*>(smem + SMEM_TILES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_TILES + SMEM_TRANS);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_lo) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int chunks_per_tile = (num_k_blocks + kb_per_chunk - 1) / kb_per_chunk;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = tiles[t].m_blk * BM, n0 = tiles[t].n_blk * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          unsigned char* st = smem + s * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          const int k0 = kb * BK;
+          tma_load_2d(st, &map_hi, &full_bar[s], k0, m0);                               // A hi
+          tma_load_2d(st + A_BYTES, &map_lo, &full_bar[s], k0, m0);                     // A lo
+          tma_load_2d(st + 2 * A_BYTES, &map_hi, &full_bar[s], k0, n0);                 // B hi [0,128)
+          tma_load_2d(st + 2 * A_BYTES + A_BYTES, &map_hi, &full_bar[s], k0, n0 + BM);  // B hi [128,256)
+          tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_lo, &full_bar[s], k0, n0);       // B lo
+          tma_load_2d(st + 2 * A_BYTES + B_BYTES + A_BYTES, &map_lo, &full_bar[s], k0, n0 + BM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t it = 0, chunk_it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int ch = 0; ch < chunks_per_tile; ++ch, ++chunk_it) {
+          const uint32_t buf = chunk_it & 1, tph = (chunk_it >> 1) & 1;
+          mbar_wait(&tempty_bar[buf], tph ^ 1);           // epilogue drained this accumulator
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          const int kb_end = min(num_k_blocks, (ch + 1) * kb_per_chunk);
+          for (int kb = ch * kb_per_chunk; kb < kb_end; ++kb, ++it) {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tcgen05_fence_after();
+            const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+            const uint64_t a_hi = make_kmajor_sw128_desc(st);
+            const uint64_t a_lo = make_kmajor_sw128_desc(st + A_BYTES);
+            const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * A_BYTES);
+            const uint64_t b_lo = make_kmajor_sw128_desc(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+            for (int j = 0; j < BK / UMMA_K; ++j) {
+              const uint64_t adv = (uint64_t)((j * UMMA_K * 4) >> 4);   // +32 B per k-step
+              const uint32_t first = (kb == ch * kb_per_chunk && j == 0) ? 0u : 1u;
+              // small cross terms first, the dominant hi.hi term last
+              umma_tf32(d_tmem, a_lo + adv, b_hi + adv, kIdesc, first);
+              umma_tf32(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+              umma_tf32(d_tmem, a_hi + adv, b_hi + adv, kIdesc, 1u);
+            }
+            umma_commit(&empty_bar[s]);                   // frees the smem stage when MMAs retire
+          }
+          umma_commit(&tfull_bar[buf]);                   // accumulator chunk complete
+        }
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps (TMEM lane quarter = warp % 4)
+    const int q = warp & 3;
+    float* trans = s_trans + (warp - 2) * 32 * TRANS_PAD;
+    float* run = running + (long long)blockIdx.x * (BM * BN);
+    uint32_t chunk_it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = tiles[t].m_blk * BM, n0 = tiles[t].n_blk * BN;
+      const int row_l = q * 32 + lane;                    // row within the tile == TMEM lane
+      for (int ch = 0; ch < chunks_per_tile; ++ch, ++chunk_it) {
+        const uint32_t buf = chunk_it & 1, tph = (chunk_it >> 1) & 1;
+        mbar_wait(&tfull_bar[buf], tph);
+        tcgen05_fence_after();
+        const bool last = (ch == chunks_per_tile - 1);
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+        for (int cg = 0; cg < BN / 32; ++cg) {
+          // skip column groups that lie entirely below the diagonal band of this warp's rows
+          uint32_t v[32];
+          tmem_ld32(taddr0 + cg * 32, v);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          // running tile layout [col][row]: lanes hit consecutive addresses
+          float* rp = run + (long long)(cg * 32) * BM + row_l;
+          if (ch > 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += rp[j * BM];
+          }
+          if (!last) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rp[j * BM] = f[j];
+          } else {
+            const int gr_base = m0 + q * 32;              // first global row of this warp
+            const int gc_base = n0 + cg * 32;
+            if (gc_base + 31 >= gr_base && gr_base < m && gc_base < m) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float c = f[j];
+                c = fminf(1.f, fmaxf(-1.f, c));           // NaN stays NaN (fminf/fmaxf would drop it)
+                if (f[j] != f[j]) c = f[j];
+                f[j] = (flavour == HIA_SIM_COSINE_DISTANCE) ? (1.f - c) : c;
+              }
+              const float diag_val = (flavour == HIA_SIM_COSINE_DISTANCE) ? 0.f : 1.f;
+              const int gr = gr_base + lane;
+              // mirrored store out[gc][gr] (lanes = consecutive gr -> coalesced)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int gc = gc_base + j;
+                if (gr < m && gc < m && gc > gr) out[(long long)gc * ld_out + gr] = f[j];
+              }
+              // direct store out[gr][gc] through a 32x32 shared transpose (coalesced rows)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) trans[lane * TRANS_PAD + j] = f[j];
+              __syncwarp();
+#pragma unroll 4
+              for (int i = 0; i < 32; ++i) {
+                const int r = gr_base + i, gc = gc_base + lane;
+                if (r < m && gc < m && gc >= r) {
+                  out[(long long)r * ld_out + gc] = (gc == r) ? diag_val : trans[i * TRANS_PAD + lane];
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ row prologue
+// One CTA per row: fp64 mean (Pearson) and norm, then the TF32 hi/lo planes of the unit row.
+__global__ void __launch_bounds__(256)
+row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int kpad, int center,
+                float* __restrict__ hi, float* __restrict__ lo) {
+  __shared__ double s_red[8];
+  __shared__ double s_val;
+  const int r = blockIdx.x;
+  if (r >= m) return;
+  const float* row = x + (long long)r * ld_x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  double mean = 0.0;
+  if (center) {
+    double sum = 0.0;
+    for (int j = tid; j < k; j += blockDim.x) sum += (double)row[j];
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[w] = sum;
+    __syncthreads();
+    if (tid == 0) { double t = 0; for (int i = 0; i < 8; ++i) t += s_red[i]; s_val = t / (double)k; }
+    __syncthreads();
+    mean = s_val;
+    __syncthreads();
+  }
+  double ss = 0.0;
+  for (int j = tid; j < k; j += blockDim.x) { const double d = (double)row[j] - mean; ss += d * d; }
+  ss = warp_sum(ss);
+  if (lane == 0) s_red[w] = ss;
+  __syncthreads();
+  if (tid == 0) { double t = 0; for (int i = 0; i < 8; ++i) t += s_red[i]; s_val = 1.0 / sqrt(t); }
+  __syncthreads();
+  const double inv = s_val;                               // inf for an all-zero row -> NaN, like pdist
+  float* ph = hi + (long long)r * kpad;
+  float* pl = lo + (long long)r * kpad;
+  for (int j = tid; j < kpad; j += blockDim.x) {
+    float h = 0.f, l = 0.f;
+    if (j < k) {
+      const float xn = (float)(((double)row[j] - mean) * inv);
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(xn));
+      h = __uint_as_float(hb);
+      const float rem = xn - h;                           // exact in fp32
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+      l = __uint_as_float(lb);
+    }
+    ph[j] = h;
+    pl[j] = l;
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_plane_map(CUtensorMap* map, float* base, int rows, int kpad) {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !p) { set_last_cuda_error(e); return HIA_ERR_CUDA; }
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kpad * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_cuda_error(cudaErrorInvalidValue); return HIA_ERR_CUDA; }
+  return HIA_OK;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Tiles touching the upper triangle and the band, in super-blocks for L2 reuse.
+int build_tiles(int m, int band_lo, int band_hi, TileCoord* dst) {
+  const int mt = (m + BM - 1) / BM, nt = (m + BN - 1) / BN;
+  const int SBM = 16, SBN = 8;        // super-block = 2048 x 2048 cells
+  int cnt = 0;
+  for (int sm = 0; sm < mt; sm += SBM)
+    for (int sn = 0; sn < nt; sn += SBN)
+      for (int mi = sm; mi < min(sm + SBM, mt); ++mi)
+        for (int nj = sn; nj < min(sn + SBN, nt); ++nj) {
+          const long long r0 = (long long)mi * BM, r1 = min((long long)m, r0 + BM) - 1;
+          const long long c0 = (long long)nj * BN, c1 = min((long long)m, c0 + BN) - 1;
+          if (c1 < r0) continue;                         // entirely below the diagonal
+          // distance range of upper cells in the tile: [max(0, c0 - r1), c1 - r0]
+          const long long dmin = max(0ll, c0 - r1), dmax = c1 - r0;
+          if (band_hi >= 0 && (dmin > band_hi || dmax < band_lo)) continue;
+          if (dst) { dst[cnt].m_blk = mi; dst[cnt].n_blk = nj; }
+          ++cnt;
+        }
+  return cnt;
+}
+
+}  // namespace
+
+int similarity_fp64(const float* x, int m, int k, long long ld_x, float* out, long long ld_out,
+                    int flavour, void* workspace, long long workspace_bytes, cudaStream_t stream);
+long long similarity_fp64_workspace(int m, int k);
+
+}  // namespace hia
+
+// workspace layout (3xTF32): [hi plane][lo plane][running tiles: 148 x 128 x 256 fp32][tile list]
+static int64_t tf32_ws_layout(int m, int k, int64_t* off_lo, int64_t* off_run, int64_t* off_tiles) {
+  using namespace hia;
+  const int64_t kpad = round_up(k, BK);
+  const int64_t plane = (int64_t)m * kpad * 4;
+  const int64_t plane_al = (plane + 1023) / 1024 * 1024;
+  const int64_t run = (int64_t)kNumSMs * BM * BN * 4;
+  const int64_t ntiles = (int64_t)((m + BM - 1) / BM) * ((m + BN - 1) / BN);
+  if (off_lo) *off_lo = plane_al;
+  if (off_run) *off_run = 2 * plane_al;
+  if (off_tiles) *off_tiles = 2 * plane_al + run;
+  return 2 * plane_al + run + ntiles * (int64_t)sizeof(TileCoord) + 1024;
+}
+
+HIA_API int64_t hia_similarity_workspace_bytes(int32_t m, int32_t k, int precision) {
+  if (m <= 0 || k <= 0) return 0;
+  if (precision == HIA_PREC_FP64) return hia::similarity_fp64_workspace(m, k);
+  return tf32_ws_layout(m, k, nullptr, nullptr, nullptr);
+}
+
+HIA_API int hia_similarity(const float* x, int32_t m, int32_t k, int64_t ld_x, float* out,
+                           int64_t ld_out, int flavour, int precision, int32_t band_lo,
+                           int32_t band_hi, int32_t k_chunk, void* workspace,
+                           int64_t workspace_bytes, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !out || !workspace || m <= 0 || k <= 0 || ld_x < k || ld_out < m) return HIA_ERR_BAD_ARG;
+  if (flavour != HIA_SIM_COSINE_DISTANCE && flavour != HIA_SIM_PEARSON) return HIA_ERR_BAD_ARG;
+  if (workspace_bytes < hia_similarity_workspace_bytes(m, k, precision)) return HIA_ERR_WORKSPACE;
+  if (precision == HIA_PREC_FP64)
+    return similarity_fp64(x, m, k, ld_x, out, ld_out, flavour, workspace, workspace_bytes, stream);
+  if (precision != HIA_PREC_3XTF32) return HIA_ERR_BAD_ARG;
+  if (!aligned16(workspace)) return HIA_ERR_ALIGN;
+  if (band_hi >= 0 && band_lo > band_hi) return HIA_ERR_BAD_ARG;
+  if (band_lo < 0) band_lo = 0;
+
+  int dev = 0, major = 0;
+  HIA_CUDA(cudaGetDevice(&dev));
+  HIA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return HIA_ERR_ARCH;
+
+  int64_t off_lo, off_run, off_tiles;
+  tf32_ws_layout(m, k, &off_lo, &off_run, &off_tiles);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  float* hi = reinterpret_cast<float*>(ws);
+  float* lo = reinterpret_cast<float*>(ws + off_lo);
+  float* running = reinterpret_cast<float*>(ws + off_run);
+  TileCoord* d_tiles = reinterpret_cast<TileCoord*>(ws + off_tiles);
+  const int kpad = round_up(k, BK);
+
+  row_prep_kernel<<<m, 256, 0, stream>>>(x, m, k, ld_x, kpad, flavour == HIA_SIM_PEARSON ? 1 : 0, hi, lo);
+  HIA_LAUNCH_CHECK();
+
+  const int max_tiles = ((m + BM - 1) / BM) * ((m + BN - 1) / BN);
+  TileCoord* h_tiles = static_cast<TileCoord*>(malloc((size_t)max_tiles * sizeof(TileCoord)));
+  if (!h_tiles) return HIA_ERR_BAD_ARG;
+  const int num_tiles = build_tiles(m, band_lo, band_hi, h_tiles);
+  if (num_tiles == 0) { free(h_tiles); return HIA_OK; }
+  // pageable H2D: the runtime stages the data before returning, so freeing right after is safe
+  cudaError_t ce = cudaMemcpyAsync(d_tiles, h_tiles, (size_t)num_tiles * sizeof(TileCoord),
+                                   cudaMemcpyHostToDevice, stream);
+  free(h_tiles);
+  HIA_CUDA(ce);
+
+  CUtensorMap map_hi, map_lo;
+  int st = make_plane_map(&map_hi, hi, m, kpad);
+  if (st != HIA_OK) return st;
+  st = make_plane_map(&map_lo, lo, m, kpad);
+  if (st != HIA_OK) return st;
+
+  const int num_k_blocks = kpad / BK;
+  if (k_chunk <= 0) k_chunk = 1024;
+  int kb_per_chunk = max(1, k_chunk / BK);
+  HIA_CUDA(cudaFuncSetAttribute(syrk_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int grid = min(num_tiles, kNumSMs);
+  syrk_tf32x3_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_hi, map_lo, d_tiles, num_tiles, m,
+                                                                num_k_blocks, kb_per_chunk, out, ld_out,
+                                                                running, flavour);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}

@@ -1,0 +1,126 @@
+/*
+ * hiarch_b200.h -- C ABI of the B200-native (sm_100a) HiArch matrix hot path.
+ *
+ * The reference (xjtu-omics/HiArch) has no FFI: its operator boundary is the set of Python
+ * methods/functions listed in SURVEY.md section 8(a/b). Each entry point below names the
+ * reference interface it replaces (file:line relative to /root/reference/publish/).
+ * `INTEGRATION.md` shows the ctypes stub a reference maintainer would add per call site.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns all memory (inputs, outputs, workspaces) and keeps it alive until the
+ *     stream is synchronised; the library allocates nothing persistent;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, re-entrant,
+ *     no global state;
+ *   - return value: 0 (HIA_OK) or a negative hia_status; nothing is thrown across the ABI;
+ *   - dense maps are row-major fp32 with leading dimension `ld` (elements); `ld % 4 == 0`
+ *     and 16-byte aligned bases are required where stated (128-bit loads / TMA);
+ *   - chromosome layout is `chr_start[C+1]` (int32, device): chromosome c owns bins
+ *     [chr_start[c], chr_start[c+1]) -- GenomeIndex.chr_seps (new_hic_class.py:92-102).
+ */
+#ifndef HIARCH_B200_H
+#define HIARCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  HIA_OK = 0,
+  HIA_ERR_BAD_ARG = -1,       /* null pointer, negative size, bad flag            */
+  HIA_ERR_ALIGN = -2,         /* pointer / ld alignment requirement not met       */
+  HIA_ERR_CUDA = -3,          /* a CUDA runtime call or launch failed             */
+  HIA_ERR_UNSUPPORTED = -4,   /* size beyond what this build supports             */
+  HIA_ERR_WORKSPACE = -5,     /* workspace too small                              */
+  HIA_ERR_ARCH = -6           /* device is not sm_100                             */
+} hia_status;
+
+int hia_version(void);
+const char* hia_status_string(int status);
+/* last CUDA error text seen by this thread inside the library (for HIA_ERR_CUDA) */
+const char* hia_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* a1/a2  sparse (i, j, v) -> dense symmetric                                            */
+/* replaces read_sps_file -> SpsHiCMtx (new_hic_class.py:2576-2602, 2152-2198),          */
+/*          SpsHiCMtx.to_all (:2229-2246), SpsHiCMtx.to_dense (:2209-2224),              */
+/*          ArrayHiCMtx.to_all (:1991-2008)                                              */
+/* ------------------------------------------------------------------------------------ */
+#define HIA_MTX_TRIU 0   /* entries with col < row are ignored; result mirrored */
+#define HIA_MTX_ALL  1   /* entries stored as given                             */
+#define HIA_FILL_ZERO      0  /* absent cells = 0                (has_neg == False)          */
+#define HIA_FILL_MIN       1  /* absent cells = min(all entries) (has_neg, whole matrix)     */
+#define HIA_FILL_BLOCK_MIN 2  /* absent cells = min(entries of that chromosome-pair block)   */
+                              /* (yield_by_chro(triu=True) + to_dense, main_local.py:112-115) */
+/* workspace: (C*C + 1) floats. Duplicate (i,j) are summed (coo->csr). Explicit zero
+ * entries are stored as 0 (they are not "absent"). out is n x n, ld >= n. */
+int64_t hia_scatter_workspace_bytes(int32_t n_chr);
+int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz,
+                        int32_t n, float* out, int64_t ld, int mtx_type, int fill_mode,
+                        const int32_t* chr_start, int32_t n_chr, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* a4/a5  expected contacts per diagonal, O/E, log                                       */
+/* replaces HiCMtx.obs_d_exp(mode='sgd_mean') (new_hic_class.py:1121-1290) and           */
+/*          ArrayHiCMtx.log (:2076-2094); oe_map_core (oe_map/S2_oe.py:10-15)            */
+/* ------------------------------------------------------------------------------------ */
+/* Pass 1 (reads the upper triangle once): per intra block, per diagonal d: sum of the
+ * upper-diagonal cells (fp64) and min positive cell; per inter block (a<b): sum, non-zero
+ * count and min positive. The map must be symmetric ('all' type from the scatter).
+ * diag_sum[N] fp64, diag_minpos[N] fp32 (indexed chr_start[c] + d), inter_sum[C*C] fp64,
+ * inter_nnz[C*C] u64, inter_minpos[C*C] fp32 -- all zero/inf-initialised by the call.
+ * bin_chr[N] (int16) = chromosome index of every bin; chr_start_host = host copy (grid sizing). */
+int hia_oe_expected_pass(const float* map, int32_t n, int64_t ld, const int32_t* chr_start,
+                         const int32_t* chr_start_host, int32_t n_chr, double* diag_sum,
+                         float* diag_minpos, double* inter_sum, unsigned long long* inter_nnz,
+                         float* inter_minpos, const int16_t* bin_chr, void* stream);
+
+/* Pass 1b (tiny): SGD pooling + un-flushed-last-group rule + monotone clamp.
+ * pool_gid[N], use_code[N] are the data-independent tables the host derives from
+ * ScaledGenomicDistance (new_hic_class.py:788-1003, scalar lookup quirk :865-875):
+ *   pool_gid[s+d]  = stored-group index diagonal d is pooled into, or -1;
+ *   use_code[s+d]  = -1 -> mean of the main diagonal (d == 0);
+ *                    2*g   -> stored mean of group g as is (fallback to the largest key);
+ *                    2*g+1 -> stored mean of group g, 0 replaced by 1 (:1213).
+ * Outputs: expected[N] fp64 (the reference's exp_counts), inv_expected[N] fp32 (1/exp, or 1
+ * where exp <= 0 -> "skip", :1264-1267), inter_inv[C*C] fp32 (1/mean of non-zero cells, both
+ * (a,b) and (b,a)), min_pos_oe[1] fp32 = smallest positive O/E value (for the log fill). */
+int hia_oe_finalize(const double* diag_sum, const float* diag_minpos, const double* inter_sum,
+                    const unsigned long long* inter_nnz, const float* inter_minpos,
+                    const int32_t* chr_start, int32_t n_chr, int32_t n, const int32_t* pool_gid,
+                    const int32_t* use_code, int counts_must_decrese, double* expected,
+                    float* inv_expected, float* inter_inv, float* min_pos_oe, void* stream);
+
+/* Pass 2 (streaming, 8 B/cell): out = map * inv (intra: per diagonal; inter: per block);
+ * flags: HIA_OE_LOG -> x>0 ? ln(x+1) : min over positives of ln(x+1)   (ArrayHiCMtx.log)
+ *        HIA_OE_ONLY_INTRA -> inter blocks are written as 0            (only_intra=True) */
+#define HIA_OE_LOG 1
+#define HIA_OE_ONLY_INTRA 2
+int hia_oe_apply(const float* map, float* out, int32_t n, int64_t ld, const int32_t* chr_start,
+                 int32_t n_chr, const int16_t* bin_chr, const float* inv_expected,
+                 const float* inter_inv, const float* min_pos_oe, int flags, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* a8  row x row similarity: cosine distance (get_adj_mtx, complex/src/S1_get_adj_mtx.py  */
+/*     :8-14 == squareform(pdist(M,'cosine'))) and Pearson correlation (north-star)       */
+/* ------------------------------------------------------------------------------------ */
+#define HIA_SIM_COSINE_DISTANCE 0   /* out = 1 - cos, exact 0 diagonal (pdist/squareform) */
+#define HIA_SIM_PEARSON 1           /* out = corr,     exact 1 diagonal                    */
+#define HIA_PREC_3XTF32 0           /* tcgen05 kind::tf32, hi/lo split, fp32 accumulate    */
+#define HIA_PREC_FP64 1             /* FP64 DMMA (mma.sync m8n8k4), fp64 accumulate        */
+/* X is m x k (ld_x), out is m x m (ld_out). band_lo/band_hi (in bins, band_hi < 0 = all):
+ * only tiles intersecting band_lo <= |i-j| <= band_hi are computed (checkerboard needs
+ * 5%..15% of the chromosome length only); other cells of `out` are left untouched.
+ * k_chunk: K elements accumulated inside tensor memory before the partial sum is folded
+ * into an fp32 running tile (0 = default). */
+int64_t hia_similarity_workspace_bytes(int32_t m, int32_t k, int precision);
+int hia_similarity(const float* x, int32_t m, int32_t k, int64_t ld_x, float* out, int64_t ld_out,
+                   int flavour, int precision, int32_t band_lo, int32_t band_hi, int32_t k_chunk,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIARCH_B200_H */

@@ -1,0 +1,226 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs and against the reference's golden vectors. Run on the B200 box: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): scattered non-zeros bit-exact; O/E (logged) and
+similarity entries within 1e-5 absolute; raw O/E additionally 2e-7 relative (fp32 map storage).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hia_oracle as O
+from hiarch_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ATOL = 1e-5
+
+
+def _dev(a, dtype):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device="cuda", dtype=dtype)
+
+
+def _coo(g, prefix):
+    return (_dev(g[f"{prefix}.rows"], torch.int32), _dev(g[f"{prefix}.cols"], torch.int32),
+            _dev(g[f"{prefix}.vals"], torch.float32))
+
+
+def _seps(g):
+    return synth.chr_seps_from_lens([int(x) for x in g["in.lens"]])
+
+
+# --------------------------------------------------------------------------------- scatter
+@pytest.mark.parametrize("case", ["g3chr", "g1chr", "gquirk"])
+def test_scatter_zero_fill_bit_exact(golden, case):
+    from hiarch_b200 import ops
+    g = golden(case)
+    n = int(g["in.lens"].sum())
+    r, c, v = _coo(g, "in")
+    dense = ops.scatter_coo_sym(r, c, v, n)
+    ref = O.scatter_coo_sym(g["in.rows"], g["in.cols"], g["in.vals"], n).astype(np.float32)
+    assert np.array_equal(dense.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("case", ["g3chr", "g1chr"])
+def test_scatter_min_fill_bit_exact(golden, case):
+    from hiarch_b200 import ops
+    g = golden(case)
+    n = int(g["in.lens"].sum())
+    seps = _seps(g)
+    layout = ops.GenomeLayout(seps)
+    r, c, v = _coo(g, "de_file")
+    ref_g = O.scatter_coo_sym(g["de_file.rows"], g["de_file.cols"], g["de_file.vals"], n, has_neg=True)
+    ref_b = O.scatter_coo_sym(g["de_file.rows"], g["de_file.cols"], g["de_file.vals"], n, has_neg=True,
+                              seps=seps)
+    d_g = ops.scatter_coo_sym(r, c, v, n, fill_mode=ops.FILL_MIN, layout=layout)
+    d_b = ops.scatter_coo_sym(r, c, v, n, fill_mode=ops.FILL_BLOCK_MIN, layout=layout)
+    assert np.array_equal(d_g.cpu().numpy(), ref_g.astype(np.float32))
+    assert np.array_equal(d_b.cpu().numpy(), ref_b.astype(np.float32))
+    # the block the reference densified itself (explicit 0.00 entries stay 0)
+    s0, e0 = seps[0]
+    assert np.array_equal(d_b[s0:e0 + 1, s0:e0 + 1].cpu().numpy(), g["checker.block0"].astype(np.float32))
+
+
+def test_scatter_duplicates_lower_entries_and_empty():
+    from hiarch_b200 import ops
+    rng = np.random.default_rng(5)
+    n = 257
+    rows = rng.integers(0, n, 5000).astype(np.int32)
+    cols = rng.integers(0, n, 5000).astype(np.int32)
+    vals = rng.integers(-8, 9, 5000).astype(np.float32)       # small ints: any sum order is exact
+    for has_neg, mode in ((False, ops.FILL_ZERO), (True, ops.FILL_MIN)):
+        ref = O.scatter_coo_sym(rows, cols, vals, n, has_neg=has_neg)
+        got = ops.scatter_coo_sym(_dev(rows, torch.int32), _dev(cols, torch.int32),
+                                  _dev(vals, torch.float32), n, fill_mode=mode)
+        assert np.array_equal(got.cpu().numpy(), ref.astype(np.float32))
+    ref = O.scatter_coo_sym(rows, cols, vals, n, mtx_type="all")
+    got = ops.scatter_coo_sym(_dev(rows, torch.int32), _dev(cols, torch.int32), _dev(vals, torch.float32),
+                              n, mtx_type=ops.MTX_ALL)
+    assert np.array_equal(got.cpu().numpy(), ref.astype(np.float32))
+    empty = ops.scatter_coo_sym(torch.empty(0, dtype=torch.int32, device="cuda"),
+                                torch.empty(0, dtype=torch.int32, device="cuda"),
+                                torch.empty(0, dtype=torch.float32, device="cuda"), 5)
+    assert float(empty.abs().sum()) == 0.0
+
+
+# --------------------------------------------------------------------------------- O/E + log
+def _check_oe(dense64, seps, bs):
+    from hiarch_b200 import ops
+    n = dense64.shape[0]
+    layout = ops.GenomeLayout(seps)
+    dmap = ops.alloc_map(n)
+    dmap.copy_(_dev(dense64, torch.float32))
+    ref_oe, ref_exp = O.obs_d_exp(dense64, seps, bs, return_expected=True)
+    ref_log = O.log_map(ref_oe)
+    got_oe, state = ops.obs_d_exp(dmap, layout, bs)
+    got_log, _ = ops.obs_d_exp(dmap, layout, bs, log=True)
+    exp = state.expected.cpu().numpy()
+    for (s, e), rexp in zip(seps, ref_exp):
+        if rexp is not None:
+            assert np.allclose(exp[s:e + 1], rexp, rtol=1e-6, atol=0)
+    go = got_oe.cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(go - ref_oe) <= ATOL + 2e-7 * np.abs(ref_oe))
+    assert np.abs(got_log.cpu().numpy().astype(np.float64) - ref_log).max() <= ATOL
+    # no clamp, only_intra
+    got_nc, _ = ops.obs_d_exp(dmap, layout, bs, counts_must_decrese=False, log=True)
+    ref_nc = O.log_map(O.obs_d_exp(dense64, seps, bs, counts_must_decrese=False))
+    assert np.abs(got_nc.cpu().numpy().astype(np.float64) - ref_nc).max() <= ATOL
+    got_oi, _ = ops.obs_d_exp(dmap, layout, bs, only_intra=True)
+    ref_oi = O.obs_d_exp(dense64, seps, bs, only_intra=True)
+    goi = got_oi.cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(goi - ref_oi) <= ATOL + 2e-7 * np.abs(ref_oi))
+    # in place
+    work = ops.alloc_map(n)
+    work.copy_(dmap)
+    ops.obs_d_exp(work, layout, bs, log=True, out=work)
+    assert torch.equal(work, got_log)
+
+
+@pytest.mark.parametrize("case", ["g3chr", "g1chr", "gquirk"])
+def test_oe_against_reference_golden(golden, case):
+    from hiarch_b200 import ops
+    g = golden(case)
+    n = int(g["in.lens"].sum())
+    bs = int(g["in.bin_size"])
+    seps = _seps(g)
+    r, c, v = _coo(g, "in")
+    dense = ops.scatter_coo_sym(r, c, v, n)
+    layout = ops.GenomeLayout(seps)
+    got, state = ops.obs_d_exp(dense, layout, bs)
+    got_log, _ = ops.obs_d_exp(dense, layout, bs, log=True)
+    ref = g["oe"]
+    assert np.all(np.abs(got.cpu().numpy() - ref) <= ATOL + 2e-7 * np.abs(ref))
+    assert np.abs(got_log.cpu().numpy() - g["oe_log"]).max() <= ATOL
+    s, e = seps[-1]
+    assert np.allclose(state.expected.cpu().numpy()[s:e + 1], g["expected_last_block"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("lens,bs,seed", [([700, 333, 129, 50], 100000, 11), ([1500], 50000, 12),
+                                          ([37, 1030, 64], 25000, 13)])
+def test_oe_against_oracle_synthetic(lens, bs, seed):
+    lam, seps = synth.rate_matrix(lens, seed)
+    up = synth.sample_counts(lam, seed)
+    dense = up + np.triu(up, 1).T
+    _check_oe(dense, seps, bs)
+
+
+def test_oe_degenerate_blocks():
+    """all-zero chromosome, zero rows, an inter block with no contacts."""
+    lens = [60, 40, 30]
+    lam, seps = synth.rate_matrix(lens, 3)
+    up = synth.sample_counts(lam, 3)
+    dense = up + np.triu(up, 1).T
+    s, e = seps[1]
+    dense[s:e + 1, s:e + 1] = 0.0            # all-zero intra block (np.sum == 0 -> unchanged)
+    s2, e2 = seps[2]
+    dense[s:e + 1, s2:e2 + 1] = 0.0          # empty inter block
+    dense[s2:e2 + 1, s:e + 1] = 0.0
+    dense[5, :] = 0.0
+    dense[:, 5] = 0.0
+    _check_oe(dense, seps, 100000)
+
+
+# --------------------------------------------------------------------------------- similarity
+def _sim_ref(x64, flavour):
+    return O.cosine_distance(x64) if flavour == 0 else O.pearson(x64)
+
+
+@pytest.mark.parametrize("m,k", [(50, 50), (130, 77), (257, 300), (640, 1000), (1000, 33)])
+@pytest.mark.parametrize("flavour", [0, 1])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_similarity_small(m, k, flavour, precision):
+    from hiarch_b200 import ops
+    rng = np.random.default_rng(m * 1000 + k)
+    x = rng.standard_normal((m, k)).astype(np.float32)
+    x[:, : k // 3] += 0.7                                 # non-zero means, correlated rows
+    x[: m // 2] += rng.standard_normal(k).astype(np.float32)
+    xd = ops.alloc_map(m, cols=k)
+    xd.copy_(_dev(x, torch.float32))
+    got = ops.similarity(xd, flavour=flavour, precision=precision).cpu().numpy().astype(np.float64)
+    ref = _sim_ref(x.astype(np.float64), flavour)
+    assert np.abs(got - ref).max() <= (ATOL if precision == 0 else 5e-7)
+    assert np.array_equal(got, got.T)
+    assert np.all(np.diag(got) == (0.0 if flavour == 0 else 1.0))
+
+
+def test_similarity_long_k_chunked_accumulation():
+    """K = 20 000: many MMA steps per output; 1e-5 must hold for both chunk settings."""
+    from hiarch_b200 import ops
+    rng = np.random.default_rng(77)
+    m, k = 512, 20000
+    base = rng.standard_normal(k)
+    x = (0.8 * base[None, :] + 0.6 * rng.standard_normal((m, k)) + 0.3).astype(np.float32)
+    xd = ops.alloc_map(m, cols=k)
+    xd.copy_(_dev(x, torch.float32))
+    ref = O.pearson(x.astype(np.float64))
+    refc = O.cosine_distance(x.astype(np.float64))
+    for k_chunk in (256, 1024, 1 << 20):
+        got = ops.similarity(xd, flavour=1, k_chunk=k_chunk).cpu().numpy().astype(np.float64)
+        err = np.abs(got - ref).max()
+        print(f"pearson k_chunk={k_chunk}: max abs err {err:.3e}")
+        if k_chunk <= 1024:
+            assert err <= ATOL
+    got = ops.similarity(xd, flavour=0).cpu().numpy().astype(np.float64)
+    assert np.abs(got - refc).max() <= ATOL
+
+
+def test_similarity_golden_adj_and_band(golden):
+    from hiarch_b200 import ops
+    g = golden("g3chr")
+    blk = g["checker.block0"]
+    xd = ops.alloc_map(blk.shape[0], cols=blk.shape[1])
+    xd.copy_(_dev(blk, torch.float32))
+    got = ops.similarity(xd).cpu().numpy().astype(np.float64)
+    assert np.abs(got - g["checker.adj0"]).max() <= ATOL          # vs the reference's pdist
+    # band-limited: cells inside the band equal the full result
+    rng = np.random.default_rng(1)
+    m = 900
+    x = rng.standard_normal((m, 400)).astype(np.float32)
+    xd = ops.alloc_map(m, cols=400)
+    xd.copy_(_dev(x, torch.float32))
+    full = ops.similarity(xd).cpu().numpy()
+    lo, hi = 45, 135
+    band = ops.similarity(xd, band=(lo, hi)).cpu().numpy()
+    i, j = np.indices((m, m))
+    inb = (np.abs(i - j) >= lo) & (np.abs(i - j) <= hi)
+    assert np.array_equal(band[inb], full[inb])

@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- the HiArch matrix hot path on B200: scatter -> O/E+log -> Pearson -> top-3 eigvec.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N=1: plain python;
+    python -m torch.distributed.run ... bench.py --gpus N    #  N>1: one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the CPU reference arm (oracle port)
+
+Metric (BASELINE.json): "O/E+Pearson+eigen cells/s". A cell = one entry of the dense N x N map.
+Workload at N GPUs (weak scaling, no data-path collective): every rank processes its own
+synthetic genome-wide human map at 100 kb (configs[1]: 30 894 bins, 9.54e8 cells, 24 hg38
+chromosomes), i.e. samples are sharded by rank like the reference's ParallelFunc
+(publish/run_hic_dataset.py:573-603).
+
+One step = sparse (i,j,v) upper triangle resident in HBM -> dense symmetric scatter -> expected /
+O-E / log (sgd_mean, k=.2) -> row x row Pearson on tcgen05 (3xTF32) -> top-3 eigenvectors (block
+Lanczos). `value` = cells of all ranks / max-over-ranks device time. `e2e` = the same through
+HotPath.run_host: COO in pinned host memory, H2D inside the timed region, eigenpairs read back.
+Inputs (0.9 GB COO / 3.8 GB maps) are far larger than the 126 MB L2, so no explicit L2 flush.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "O/E+Pearson+eigen cells/s"
+UNIT = "cells/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--res", type=int, default=100000, help="bin size (bp)")
+    ap.add_argument("--chroms", type=int, default=24, help="first C hg38 chromosomes")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-chroms", default="chr16,chr17,chr18,chr19,chr20,chr21,chr22")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (numpy/BLAS restatement of the reference, oracle/hia_oracle.py)
+# --------------------------------------------------------------------------------------------
+def cpu_sample(args):
+    from hiarch_b200 import synth
+    chroms = args.cpu_sample_chroms.split(",")
+    bins = synth.hg38_bins(args.res, chroms)
+    lens = [n for _, n in bins]
+    lam, seps = synth.rate_matrix(lens, seed=0)
+    up = synth.sample_counts(lam, seed=0, jitter=False)
+    dense = up + np.triu(up, 1).T
+    return dense, seps, chroms
+
+
+def cpu_step(dense, seps, res):
+    """One pass of the hot path on the host: O/E+log -> Pearson -> top-3 eigenpairs."""
+    from oracle import hia_oracle as O
+    oe = O.oe_map_core(dense, seps, res)
+    c = O.pearson(oe)
+    return O.topk_eig(c, 3)
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        t = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        return max(t) if t else os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dense, seps, chroms = cpu_sample(args)
+    n = dense.shape[0]
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_step(dense, seps, args.res)
+    t0 = time.perf_counter()
+    steps = max(1, args.steps)
+    for _ in range(steps):
+        cpu_step(dense, seps, args.res)
+    dt = (time.perf_counter() - t0) / steps
+    value = n * n / dt
+    sample = (f"{'+'.join(chroms)} at {args.res // 1000} kb = {n} bins ({n * n:.3g} cells) per step; "
+              "O/E+log python loops 1 thread, Pearson GEMM + eigh on all BLAS threads")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": "genome-wide human 100 kb O/E+log -> Pearson -> top-3 eigvec "
+                               "(bounded CPU sample of the same workload)", "bins": n, "res": args.res},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hiarch_b200 import _lib, ops, synth
+    from hiarch_b200.pipeline import HotPath, dense_to_coo
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    pk, pk_src = peaks()
+
+    bins = synth.hg38_bins(args.res)[: args.chroms]
+    lens = [n for _, n in bins]
+    dense, seps = synth.device_dense_map(lens, seed=rank)        # one sample per rank
+    n = dense.shape[0]
+    rows, cols, vals = dense_to_coo(dense)
+    del dense
+    torch.cuda.empty_cache()
+    nnz = rows.numel()
+    hp = HotPath(seps, args.res, k_eig=3, max_nnz=nnz)
+    rows_h = torch.empty(nnz, dtype=torch.int32).pin_memory().copy_(rows)
+    cols_h = torch.empty(nnz, dtype=torch.int32).pin_memory().copy_(cols)
+    vals_h = torch.empty(nnz, dtype=torch.float32).pin_memory().copy_(vals)
+    cells = n * n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        hp.run_device(rows, cols, vals)
+    barrier()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.hia_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    gemm_ms, prep_ms = [], []
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        hp.scatter(rows, cols, vals)
+        hp.normalise()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        hp.similarity_prep()
+        e1.record()
+        hp.similarity_gemm()                       # the dominant kernel, timed on its own stream
+        e2.record()
+        w, vecs = hp.eigen()
+        gemm_ms.append((e1, e2))
+        prep_ms.append((e0, e1))
+    t_end.record()
+    barrier()
+    launches = lib.hia_launch_count() - launches0
+    ms_total = max_over_ranks(t_start.elapsed_time(t_end))
+    ms_step = ms_total / args.steps
+    gemm = float(np.mean([a.elapsed_time(b) for a, b in gemm_ms]))
+    prep = float(np.mean([a.elapsed_time(b) for a, b in prep_ms]))
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- end-to-end arm (pinned host COO -> eigenpairs on host) --------------------------------
+    for _ in range(min(args.warmup, 2)):
+        hp.run_host(rows_h, cols_h, vals_h)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        w_h, v_h = hp.run_host(rows_h, cols_h, vals_h)
+    t1.record()
+    barrier()
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (syrk_tf32x3_kernel) ----------------------------------
+    # algorithmic flops per launch: N^2 * K multiply-adds counted as the symmetric half,
+    # i.e. 2 * N^2 * K / 2 = N^3 logical flops; each logical flop costs 3 TF32 MMAs.
+    logical = float(n) ** 3
+    achieved = logical / (gemm * 1e-3) / 1e12
+    tf32_peak = pk["bf16_tflops_sustained"] / 2.0           # TF32 dense = bf16 / 2 on Blackwell
+    peak_logical = tf32_peak / 3.0
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_logical, "unit": "TFLOP/s",
+                "frac": achieved / peak_logical, "traffic": None,
+                "kernel": "syrk_tf32x3_kernel", "ms_per_launch": gemm,
+                "note": ("achieved = N^3 logical flops (upper-triangle SYRK) / CUDA-event time of the "
+                         "kernel; peak = bf16_tflops_sustained/2 (TF32) /3 (3xTF32 split), "
+                         f"{pk_src}; executed TF32 rate = {3 * achieved:.1f} TFLOP/s")}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        d_cpu, seps_cpu, chroms_cpu = cpu_sample(args)
+        t0c = time.perf_counter()
+        cpu_step(d_cpu, seps_cpu, args.res)
+        dtc = time.perf_counter() - t0c
+        nc = d_cpu.shape[0]
+        cpu_baseline = {"value": nc * nc / dtc, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                        "sample": (f"{'+'.join(chroms_cpu)} at {args.res // 1000} kb = {nc} bins, "
+                                   f"{dtc:.1f} s: oracle port (numpy restatement of the reference; "
+                                   "O/E loops 1 thread, Pearson GEMM + eigh on all BLAS threads)")}
+
+    line = {
+        "metric": METRIC, "value": world * cells / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 storage, fp64 reductions)",
+        "data": "synthetic",
+        "config": {"workload": f"genome-wide human {args.res // 1000} kb ({n} bins, {cells:.3g} cells) "
+                               "scatter -> O/E+log -> Pearson -> top-3 eigvec, one sample per GPU",
+                   "bins": n, "nnz_upper": nnz, "chromosomes": len(lens),
+                   "l2": "inputs (>=0.9 GB) exceed the 126 MB L2; no explicit flush",
+                   "sharding": "samples by rank, no collective"},
+        "clocks": clk, "gpu_launches": int(launches),
+        "e2e": {"value": world * cells / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 12 * nnz, "d2h_bytes_per_step": 3 * 8 + 3 * n * 4},
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "breakdown_ms": {"similarity_prep": prep, "similarity_gemm": gemm},
+        "eigvals": [float(x) for x in w_h],
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,7 @@ PROTOTYPES = {
     "hia_version": (c_int, []),
     "hia_status_string": (ctypes.c_char_p, [c_int]),
     "hia_last_cuda_error": (ctypes.c_char_p, []),
+    "hia_launch_count": (ctypes.c_uint64, []),
     "hia_scatter_workspace_bytes": (c_i64, [c_i32]),
     "hia_scatter_coo_sym": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_int, c_int,
                                     c_vp, c_i32, c_vp, c_vp]),
@@ -30,6 +31,12 @@ PROTOTYPES = {
     "hia_similarity_workspace_bytes": (c_i64, [c_i32, c_i32, c_int]),
     "hia_similarity": (c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_int, c_int, c_i32, c_i32,
                                c_i32, c_vp, c_i64, c_vp]),
+    "hia_similarity_prep": (c_int, [c_vp, c_i32, c_i32, c_i64, c_int, c_vp, c_i64, c_vp]),
+    "hia_similarity_gemm": (c_int, [c_i32, c_i32, c_vp, c_i64, c_int, c_i32, c_i32, c_i32, c_vp, c_i64,
+                                    c_vp]),
+    "hia_topk_eig_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),
+    "hia_topk_eig": (c_int, [c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_i32,
+                             c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
 }
 
 _lib = None

@@ -11,6 +11,7 @@
 namespace hia {
 
 void set_last_cuda_error(cudaError_t e);
+void count_launch();          // per-process counter of kernels launched by this library
 
 inline int cuda_ok(cudaError_t e) {
   if (e == cudaSuccess) return HIA_OK;
@@ -24,7 +25,11 @@ inline int cuda_ok(cudaError_t e) {
     if (_s != HIA_OK) return _s;                         \
   } while (0)
 
-#define HIA_LAUNCH_CHECK() HIA_CUDA(cudaGetLastError())
+#define HIA_LAUNCH_CHECK()                 \
+  do {                                     \
+    ::hia::count_launch();                 \
+    HIA_CUDA(cudaGetLastError());          \
+  } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

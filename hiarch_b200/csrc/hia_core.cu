@@ -9,7 +9,11 @@ void set_last_cuda_error(cudaError_t e) {
   g_last_err[sizeof(g_last_err) - 1] = 0;
   cudaGetLastError();  // clear the sticky-free error state
 }
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 }  // namespace hia
+
+HIA_API uint64_t hia_launch_count(void) { return __atomic_load_n(&hia::g_launches, __ATOMIC_RELAXED); }
 
 HIA_API int hia_version(void) { return 100; }
 

@@ -1,0 +1,514 @@
+// a9: top-k eigenvectors of a dense symmetric fp32 matrix (the Pearson map) -- the
+// compartment / checkerboard-sign extraction of the north-star. There is NO eigen-decomposition
+// in the reference: parity is against numpy.linalg.eigh on the
+// identical matrix ("parity unpinned by the reference").
+//
+// Method: block Lanczos (block Krylov subspace with full re-orthogonalisation, CGS2 + CholQR2),
+// Rayleigh-Ritz on the projected block-tridiagonal matrix with a one-sided Jacobi solver that
+// runs in a single CTA -- everything stays on the device, no host round trip.
+//   Y = C * Q_j          symm_panel_kernel: the only pass over C (4 B/cell, HBM-bound);
+//                        fp32 C x fp32 panel, fp32 per-lane partials folded in fp64
+//   H[:,j] = Q^T Y ; Y -= Q H[:,j]   (twice)      gram_kernel / panel_sub_kernel   (fp64)
+//   Q_{j+1} R = Y        CholQR twice                                               (fp64)
+//   T = sym(H) -> Jacobi -> Ritz vectors U = Q Z[:, top k]; residuals ||C u - lambda u||
+// Panels are stored column-major (each vector contiguous, ld = n).
+#include "hia_common.cuh"
+
+namespace hia {
+namespace {
+
+constexpr int kMaxBlock = 16;
+constexpr int kSymmCols = 1024;       // columns of C per shared-memory V chunk
+constexpr int kSymmRowsPerWarp = 4;
+constexpr int kSymmWarps = 8;
+constexpr int kSymmRows = kSymmRowsPerWarp * kSymmWarps;   // 32 rows per CTA
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+
+__global__ void random_panel_kernel(double* __restrict__ q, int n, int b, unsigned long long seed) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * b) return;
+  const uint32_t h = hash32((uint32_t)i * 2654435761u + (uint32_t)seed) ^ hash32((uint32_t)(i >> 32) + (uint32_t)(seed >> 32) + 0x9e3779b9u);
+  q[i] = (double)hash32(h) * (2.0 / 4294967296.0) - 1.0;
+}
+
+__global__ void float_to_double_panel_kernel(const float* __restrict__ src, double* __restrict__ dst, long long count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = (double)src[i];
+}
+
+__global__ void double_to_float_panel_kernel(const double* __restrict__ src, float* __restrict__ dst, long long count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = (float)src[i];
+}
+
+// Y[n x B] (fp64, col-major) = C[n x n] (fp32 row-major, ld) * V[n x B] (fp32, col-major)
+template <int B>
+__global__ void __launch_bounds__(kSymmWarps * 32)
+symm_panel_kernel(const float* __restrict__ c, int n, long long ld, const float* __restrict__ v,
+                  double* __restrict__ y) {
+  __shared__ __align__(16) float s_v[B][kSymmCols];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * kSymmRows + warp * kSymmRowsPerWarp;
+  double tot[kSymmRowsPerWarp][B];
+#pragma unroll
+  for (int r = 0; r < kSymmRowsPerWarp; ++r)
+#pragma unroll
+    for (int j = 0; j < B; ++j) tot[r][j] = 0.0;
+
+  for (int k0 = 0; k0 < n; k0 += kSymmCols) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < B * kSymmCols; idx += blockDim.x) {
+      const int j = idx / kSymmCols, col = idx % kSymmCols;
+      s_v[j][col] = (k0 + col < n) ? v[(long long)j * n + k0 + col] : 0.f;
+    }
+    __syncthreads();
+    float acc[kSymmRowsPerWarp][B];
+#pragma unroll
+    for (int r = 0; r < kSymmRowsPerWarp; ++r)
+#pragma unroll
+      for (int j = 0; j < B; ++j) acc[r][j] = 0.f;
+#pragma unroll 2
+    for (int cc = lane * 4; cc < kSymmCols; cc += 128) {
+      const int gc = k0 + cc;
+      if (gc >= n) break;
+      float4 a[kSymmRowsPerWarp];
+#pragma unroll
+      for (int r = 0; r < kSymmRowsPerWarp; ++r) {
+        const int gr = r0 + r;
+        if (gr < n) {
+          if (gc + 3 < n) a[r] = ld_stream4(c + (long long)gr * ld + gc);
+          else {
+            const float* p = c + (long long)gr * ld + gc;
+            a[r].x = p[0];
+            a[r].y = (gc + 1 < n) ? p[1] : 0.f;
+            a[r].z = (gc + 2 < n) ? p[2] : 0.f;
+            a[r].w = 0.f;
+          }
+        } else a[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const float4 vv = *reinterpret_cast<const float4*>(&s_v[j][cc]);
+#pragma unroll
+        for (int r = 0; r < kSymmRowsPerWarp; ++r) {
+          acc[r][j] = fmaf(a[r].x, vv.x, acc[r][j]);
+          acc[r][j] = fmaf(a[r].y, vv.y, acc[r][j]);
+          acc[r][j] = fmaf(a[r].z, vv.z, acc[r][j]);
+          acc[r][j] = fmaf(a[r].w, vv.w, acc[r][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kSymmRowsPerWarp; ++r)
+#pragma unroll
+      for (int j = 0; j < B; ++j) tot[r][j] += (double)acc[r][j];
+  }
+#pragma unroll
+  for (int r = 0; r < kSymmRowsPerWarp; ++r)
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const double s = warp_sum(tot[r][j]);
+      if (lane == 0 && r0 + r < n) y[(long long)j * n + r0 + r] = s;
+    }
+}
+
+// G[p x b] (row-major, += ) = A[:, 0:p]^T B[:, 0:b]; A, B col-major fp64 with ld = n.
+__global__ void __launch_bounds__(256)
+gram_kernel(const double* __restrict__ a, int p, const double* __restrict__ bm, int b, int n,
+            int rows_per_cta, double* __restrict__ g) {
+  __shared__ double s_red[8][kMaxBlock];
+  const int i = blockIdx.x;                  // column of A
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(n, r0 + rows_per_cta);
+  double acc[kMaxBlock];
+#pragma unroll
+  for (int j = 0; j < kMaxBlock; ++j) acc[j] = 0.0;
+  const double* ai = a + (long long)i * n;
+  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    const double x = ai[r];
+#pragma unroll
+    for (int j = 0; j < kMaxBlock; ++j)
+      if (j < b) acc[j] += x * bm[(long long)j * n + r];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < kMaxBlock; ++j) {
+    if (j < b) {
+      const double s = warp_sum(acc[j]);
+      if (lane == 0) s_red[warp][j] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < b) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
+    atomicAdd(&g[i * b + threadIdx.x], s);
+  }
+}
+
+// Y[:, j] -= sum_i A[:, i] G[i][j]   (thread per row)
+__global__ void __launch_bounds__(256)
+panel_sub_kernel(const double* __restrict__ a, int p, const double* __restrict__ g, int b, int n,
+                 double* __restrict__ y) {
+  extern __shared__ double s_g[];
+  for (int idx = threadIdx.x; idx < p * b; idx += blockDim.x) s_g[idx] = g[idx];
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double acc[kMaxBlock];
+#pragma unroll
+  for (int j = 0; j < kMaxBlock; ++j) acc[j] = 0.0;
+  for (int i = 0; i < p; ++i) {
+    const double x = a[(long long)i * n + r];
+#pragma unroll
+    for (int j = 0; j < kMaxBlock; ++j)
+      if (j < b) acc[j] += x * s_g[i * b + j];
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxBlock; ++j)
+    if (j < b) y[(long long)j * n + r] -= acc[j];
+}
+
+// Cholesky of G (b x b, row-major) = R^T R; writes R (upper) and Rinv (upper). One thread.
+// A pivot below eps * max diagonal deflates the column (Rinv column = 0).
+__global__ void chol_kernel(const double* __restrict__ g, int b, double* __restrict__ r_out,
+                            double* __restrict__ rinv_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double R[kMaxBlock][kMaxBlock], Ri[kMaxBlock][kMaxBlock];
+  double dmax = 0.0;
+  for (int i = 0; i < b; ++i) dmax = fmax(dmax, g[i * b + i]);
+  bool dead[kMaxBlock];
+  for (int i = 0; i < b; ++i)
+    for (int j = 0; j < b; ++j) { R[i][j] = 0.0; Ri[i][j] = 0.0; }
+  for (int j = 0; j < b; ++j) {
+    double d = g[j * b + j];
+    for (int t = 0; t < j; ++t) d -= R[t][j] * R[t][j];
+    dead[j] = !(d > 1e-24 * dmax) || !(dmax > 0.0);
+    if (dead[j]) { R[j][j] = 0.0; continue; }
+    R[j][j] = sqrt(d);
+    for (int c = j + 1; c < b; ++c) {
+      double s = 0.5 * (g[j * b + c] + g[c * b + j]);
+      for (int t = 0; t < j; ++t) s -= R[t][j] * R[t][c];
+      R[j][c] = s / R[j][j];
+    }
+  }
+  // Rinv by back substitution on the live columns
+  for (int j = 0; j < b; ++j) {
+    if (dead[j]) continue;
+    Ri[j][j] = 1.0 / R[j][j];
+    for (int i = j - 1; i >= 0; --i) {
+      if (dead[i]) continue;
+      double s = 0.0;
+      for (int t = i + 1; t <= j; ++t) s += R[i][t] * Ri[t][j];
+      Ri[i][j] = -s / R[i][i];
+    }
+  }
+  for (int i = 0; i < b; ++i)
+    for (int j = 0; j < b; ++j) { r_out[i * b + j] = R[i][j]; rinv_out[i * b + j] = Ri[i][j]; }
+}
+
+// Y <- Y * M (M b x b row-major), thread per row; optionally also writes an fp32 copy.
+__global__ void __launch_bounds__(256)
+panel_mul_kernel(double* __restrict__ y, const double* __restrict__ mtx, int b, int n,
+                 float* __restrict__ yf) {
+  __shared__ double s_m[kMaxBlock * kMaxBlock];
+  for (int idx = threadIdx.x; idx < b * b; idx += blockDim.x) s_m[idx] = mtx[idx];
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double in[kMaxBlock], out[kMaxBlock];
+#pragma unroll
+  for (int j = 0; j < kMaxBlock; ++j) in[j] = (j < b) ? y[(long long)j * n + r] : 0.0;
+#pragma unroll
+  for (int j = 0; j < kMaxBlock; ++j) {
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < kMaxBlock; ++t)
+      if (t < b && j < b) s += in[t] * s_m[t * b + j];
+    out[j] = s;
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxBlock; ++j)
+    if (j < b) {
+      y[(long long)j * n + r] = out[j];
+      if (yf) yf[(long long)j * n + r] = (float)out[j];
+    }
+}
+
+// dst (b x b) = A * B  (tiny, one thread): R_total = R2 * R1
+__global__ void small_matmul_kernel(const double* a, const double* bb, int b, double* dst) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double tmp[kMaxBlock * kMaxBlock];
+  for (int i = 0; i < b; ++i)
+    for (int j = 0; j < b; ++j) {
+      double s = 0.0;
+      for (int t = 0; t < b; ++t) s += a[i * b + t] * bb[t * b + j];
+      tmp[i * b + j] = s;
+    }
+  for (int i = 0; i < b * b; ++i) dst[i] = tmp[i];
+}
+
+// H[(row0 + i) * D + col0 + j] (+)= src[i * b + j]
+__global__ void place_block_kernel(const double* __restrict__ src, int rows, int b, double* __restrict__ h,
+                                   int D, int row0, int col0, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * b) return;
+  const int i = idx / b, j = idx % b;
+  double* dst = &h[(long long)(row0 + i) * D + col0 + j];
+  *dst = accumulate ? (*dst + src[idx]) : src[idx];
+}
+
+// One-sided (Hestenes) Jacobi on the symmetric D x D matrix built from the lower triangle of H.
+// Single CTA, warp per column pair, round-robin pairing. A and V are col-major in global memory.
+__global__ void __launch_bounds__(1024)
+jacobi_kernel(const double* __restrict__ h, int D, int dim, double* __restrict__ A, double* __restrict__ V,
+              double* __restrict__ lam, int* __restrict__ order, int max_sweeps) {
+  __shared__ int s_rot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int m = (dim + 1) & ~1;                      // padded to even (phantom index dim)
+  for (int idx = tid; idx < dim * dim; idx += blockDim.x) {
+    const int col = idx / dim, row = idx % dim;
+    const double v = (row >= col) ? h[(long long)row * D + col] : h[(long long)col * D + row];
+    A[(long long)col * dim + row] = v;
+    V[(long long)col * dim + row] = (row == col) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    for (int step = 0; step < m - 1; ++step) {
+      for (int pi = warp; pi < m / 2; pi += nwarps) {
+        int p, q;
+        if (pi == 0) { p = m - 1; q = step; }
+        else { p = (step + pi) % (m - 1); q = (step - pi + (m - 1)) % (m - 1); }
+        if (p >= dim || q >= dim) continue;
+        double* ap = A + (long long)p * dim; double* aq = A + (long long)q * dim;
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+        for (int r = lane; r < dim; r += 32) {
+          const double x = ap[r], y = aq[r];
+          alpha += x * x; beta += y * y; gamma += x * y;
+        }
+        alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
+        if (fabs(gamma) <= 1e-15 * sqrt(alpha * beta) || gamma == 0.0) continue;
+        if (lane == 0) s_rot = 1;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+        double* vp = V + (long long)p * dim; double* vq = V + (long long)q * dim;
+        for (int r = lane; r < dim; r += 32) {
+          const double x = ap[r], y = aq[r];
+          ap[r] = cs * x - sn * y; aq[r] = sn * x + cs * y;
+          const double vx = vp[r], vy = vq[r];
+          vp[r] = cs * vx - sn * vy; vq[r] = sn * vx + cs * vy;
+        }
+      }
+      __syncthreads();
+    }
+    const int rotated = s_rot;
+    __syncthreads();
+    if (!rotated) break;
+  }
+  // eigenvalue_p = v_p . (T v_p) = v_p . a_p   (a_p = T v_p is maintained by the rotations)
+  for (int p = warp; p < dim; p += nwarps) {
+    double s = 0.0;
+    for (int r = lane; r < dim; r += 32) s += V[(long long)p * dim + r] * A[(long long)p * dim + r];
+    s = warp_sum(s);
+    if (lane == 0) lam[p] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {                                    // descending order (selection sort, dim <= 272)
+    for (int i = 0; i < dim; ++i) order[i] = i;
+    for (int i = 0; i < dim; ++i) {
+      int best = i;
+      for (int j = i + 1; j < dim; ++j) if (lam[order[j]] > lam[order[best]]) best = j;
+      const int t = order[i]; order[i] = order[best]; order[best] = t;
+    }
+  }
+}
+
+// U[:, j] = Q[:, 0:dim] * Z[:, order[j]], j < k  (thread per row); fp64 + fp32 copies, eigenvalues out
+__global__ void __launch_bounds__(256)
+ritz_kernel(const double* __restrict__ q, int n, int dim, const double* __restrict__ Z,
+            const int* __restrict__ order, const double* __restrict__ lam, int k,
+            double* __restrict__ u, float* __restrict__ uf, double* __restrict__ eigvals) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x < k) eigvals[threadIdx.x] = lam[order[threadIdx.x]];
+  if (r >= n) return;
+  double acc[kMaxBlock];
+#pragma unroll
+  for (int j = 0; j < kMaxBlock; ++j) acc[j] = 0.0;
+  for (int i = 0; i < dim; ++i) {
+    const double x = q[(long long)i * n + r];
+#pragma unroll
+    for (int j = 0; j < kMaxBlock; ++j)
+      if (j < k) acc[j] += x * Z[(long long)order[j] * dim + i];
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxBlock; ++j)
+    if (j < k) { u[(long long)j * n + r] = acc[j]; uf[(long long)j * n + r] = (float)acc[j]; }
+}
+
+// resid[j] = || W[:, j] - lambda_j U[:, j] ||   (sum of squares via atomics, sqrt later)
+__global__ void __launch_bounds__(256)
+resid_kernel(const double* __restrict__ w, const double* __restrict__ u, const double* __restrict__ eigvals,
+             int n, int k, double* __restrict__ resid2) {
+  const int j = blockIdx.y;
+  double s = 0.0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const double d = w[(long long)j * n + r] - eigvals[j] * u[(long long)j * n + r];
+    s += d * d;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&resid2[j], s);
+}
+__global__ void sqrt_kernel(double* x, int k) { if (threadIdx.x < k) x[threadIdx.x] = sqrt(x[threadIdx.x]); }
+
+struct EigWs {
+  double *Q, *Y, *U, *H, *G, *G2, *R1, *Rinv, *R2, *Rt, *JA, *JV, *lam, *resid2;
+  float *Vf;
+  int* order;
+};
+
+long long carve(unsigned char* base, int n, int b, int steps, EigWs* w) {
+  const long long D = (long long)b * (steps + 1);
+  long long off = 0;
+  auto take = [&](long long bytes) { long long o = off; off += (bytes + 255) / 256 * 256; return base ? base + o : nullptr; };
+  unsigned char* p;
+  p = take((long long)n * D * 8); if (w) w->Q = (double*)p;
+  p = take((long long)n * b * 8); if (w) w->Y = (double*)p;
+  p = take((long long)n * b * 8); if (w) w->U = (double*)p;
+  p = take((long long)n * b * 4); if (w) w->Vf = (float*)p;
+  p = take(D * D * 8); if (w) w->H = (double*)p;
+  p = take(D * b * 8); if (w) w->G = (double*)p;
+  p = take(D * b * 8); if (w) w->G2 = (double*)p;
+  p = take(b * b * 8); if (w) w->R1 = (double*)p;
+  p = take(b * b * 8); if (w) w->Rinv = (double*)p;
+  p = take(b * b * 8); if (w) w->R2 = (double*)p;
+  p = take(b * b * 8); if (w) w->Rt = (double*)p;
+  p = take(D * D * 8); if (w) w->JA = (double*)p;
+  p = take(D * D * 8); if (w) w->JV = (double*)p;
+  p = take(D * 8); if (w) w->lam = (double*)p;
+  p = take(b * 8); if (w) w->resid2 = (double*)p;
+  p = take(D * 4); if (w) w->order = (int*)p;
+  return off + 256;
+}
+
+template <int B>
+int launch_symm(const float* c, int n, long long ld, const float* v, double* y, cudaStream_t s) {
+  symm_panel_kernel<B><<<(n + kSymmRows - 1) / kSymmRows, kSymmWarps * 32, 0, s>>>(c, n, ld, v, y);
+  count_launch();
+  return cuda_ok(cudaGetLastError());
+}
+int symm(const float* c, int n, long long ld, const float* v, double* y, int b, cudaStream_t s) {
+  switch (b) {
+    case 4: return launch_symm<4>(c, n, ld, v, y, s);
+    case 8: return launch_symm<8>(c, n, ld, v, y, s);
+    default: return HIA_ERR_UNSUPPORTED;
+  }
+}
+
+// Orthonormalise Y (n x b) in place by CholQR; returns R in r_out (b x b), fp32 copy in yf.
+int cholqr(double* Y, int n, int b, EigWs& w, double* r_out, float* yf, cudaStream_t s) {
+  const int rows_per_cta = 8192;
+  HIA_CUDA(cudaMemsetAsync(w.G2, 0, (size_t)b * b * 8, s));
+  dim3 grid(b, (n + rows_per_cta - 1) / rows_per_cta);
+  gram_kernel<<<grid, 256, 0, s>>>(Y, b, Y, b, n, rows_per_cta, w.G2);
+  HIA_LAUNCH_CHECK();
+  chol_kernel<<<1, 32, 0, s>>>(w.G2, b, r_out, w.Rinv);
+  HIA_LAUNCH_CHECK();
+  panel_mul_kernel<<<(n + 255) / 256, 256, 0, s>>>(Y, w.Rinv, b, n, yf);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
+}  // namespace
+}  // namespace hia
+
+HIA_API int64_t hia_topk_eig_workspace_bytes(int32_t n, int32_t block, int32_t steps) {
+  if (n <= 0 || block <= 0 || steps <= 0) return 0;
+  return hia::carve(nullptr, n, block, steps, nullptr);
+}
+
+HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block, int32_t steps,
+                         uint64_t seed, const float* init_vecs, int32_t n_init, double* eigvals,
+                         float* eigvecs, double* resid, void* workspace, int64_t workspace_bytes,
+                         void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (!c || !eigvals || !eigvecs || !resid || !workspace || n <= 0 || ld < n || k <= 0 || steps <= 0)
+    return HIA_ERR_BAD_ARG;
+  if (block != 4 && block != 8) return HIA_ERR_UNSUPPORTED;
+  if (k > block || n_init < 0 || n_init > block) return HIA_ERR_BAD_ARG;
+  if ((long long)block * (steps + 1) > n) return HIA_ERR_BAD_ARG;       // Krylov space larger than n
+  if ((long long)block * (steps + 1) > 272) return HIA_ERR_UNSUPPORTED;
+  if (!aligned16(c) || (ld & 3)) return HIA_ERR_ALIGN;
+  if (workspace_bytes < hia_topk_eig_workspace_bytes(n, block, steps)) return HIA_ERR_WORKSPACE;
+  const int b = block, D = b * (steps + 1);
+  EigWs w;
+  carve(static_cast<unsigned char*>(workspace), n, b, steps, &w);
+
+  // ---- start block: caller-provided vectors (restart) + random columns, orthonormalised
+  random_panel_kernel<<<(int)(((long long)n * b + 255) / 256), 256, 0, s>>>(w.Q, n, b, seed);
+  HIA_LAUNCH_CHECK();
+  if (n_init > 0) {
+    if (!init_vecs) return HIA_ERR_BAD_ARG;
+    float_to_double_panel_kernel<<<(int)(((long long)n * n_init + 255) / 256), 256, 0, s>>>(init_vecs, w.Q, (long long)n * n_init);
+    HIA_LAUNCH_CHECK();
+  }
+  int st = cholqr(w.Q, n, b, w, w.R1, nullptr, s);
+  if (st != HIA_OK) return st;
+  st = cholqr(w.Q, n, b, w, w.R1, w.Vf, s);
+  if (st != HIA_OK) return st;
+  HIA_CUDA(cudaMemsetAsync(w.H, 0, (size_t)D * D * 8, s));
+
+  const int rows_per_cta = 8192;
+  for (int j = 0; j < steps; ++j) {
+    double* Qj = w.Q + (long long)j * b * n;
+    double* Qn = w.Q + (long long)(j + 1) * b * n;
+    const int p = (j + 1) * b;                       // columns of Q so far
+    st = symm(c, n, ld, w.Vf, Qn, b, s);             // Y = C Q_j, written where Q_{j+1} will live
+    if (st != HIA_OK) return st;
+    (void)Qj;
+    for (int pass = 0; pass < 2; ++pass) {           // CGS2 against all previous blocks
+      HIA_CUDA(cudaMemsetAsync(w.G, 0, (size_t)p * b * 8, s));
+      dim3 grid(p, (n + rows_per_cta - 1) / rows_per_cta);
+      gram_kernel<<<grid, 256, 0, s>>>(w.Q, p, Qn, b, n, rows_per_cta, w.G);
+      HIA_LAUNCH_CHECK();
+      panel_sub_kernel<<<(n + 255) / 256, 256, (size_t)p * b * 8, s>>>(w.Q, p, w.G, b, n, Qn);
+      HIA_LAUNCH_CHECK();
+      place_block_kernel<<<(p * b + 255) / 256, 256, 0, s>>>(w.G, p, b, w.H, D, 0, j * b, pass);
+      HIA_LAUNCH_CHECK();
+    }
+    // CholQR2: Y = Q_{j+1} (R2 R1)
+    st = cholqr(Qn, n, b, w, w.R1, nullptr, s);
+    if (st != HIA_OK) return st;
+    st = cholqr(Qn, n, b, w, w.R2, w.Vf, s);
+    if (st != HIA_OK) return st;
+    small_matmul_kernel<<<1, 32, 0, s>>>(w.R2, w.R1, b, w.Rt);
+    HIA_LAUNCH_CHECK();
+    place_block_kernel<<<(b * b + 255) / 256, 256, 0, s>>>(w.Rt, b, b, w.H, D, (j + 1) * b, j * b, 0);
+    HIA_LAUNCH_CHECK();
+  }
+  // ---- Rayleigh-Ritz on the leading dim x dim part (the last block has no column in H)
+  const int dim = steps * b;
+  jacobi_kernel<<<1, 1024, 0, s>>>(w.H, D, dim, w.JA, w.JV, w.lam, w.order, 30);
+  HIA_LAUNCH_CHECK();
+  ritz_kernel<<<(n + 255) / 256, 256, 0, s>>>(w.Q, n, dim, w.JV, w.order, w.lam, k, w.U, w.Vf, eigvals);
+  HIA_LAUNCH_CHECK();
+  HIA_CUDA(cudaMemcpyAsync(eigvecs, w.Vf, (size_t)n * k * 4, cudaMemcpyDeviceToDevice, s));
+  // ---- true residuals ||C u - lambda u||
+  if (k < b) HIA_CUDA(cudaMemsetAsync(w.Vf + (long long)k * n, 0, (size_t)(b - k) * n * 4, s));
+  st = symm(c, n, ld, w.Vf, w.Y, b, s);
+  if (st != HIA_OK) return st;
+  HIA_CUDA(cudaMemsetAsync(w.resid2, 0, (size_t)b * 8, s));
+  resid_kernel<<<dim3(64, k), 256, 0, s>>>(w.Y, w.U, eigvals, n, k, w.resid2);
+  HIA_LAUNCH_CHECK();
+  sqrt_kernel<<<1, 32, 0, s>>>(w.resid2, k);
+  HIA_LAUNCH_CHECK();
+  HIA_CUDA(cudaMemcpyAsync(resid, w.resid2, (size_t)k * 8, cudaMemcpyDeviceToDevice, s));
+  return HIA_OK;
+}

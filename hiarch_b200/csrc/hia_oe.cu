@@ -87,92 +87,92 @@ intra_diag_kernel(const float* __restrict__ map, long long ld, const int* __rest
 
 // ---------------------------------------------------------------------------------------
 // Upper inter blocks (a < b): sum, non-zero count, min positive per block.
-// CTA = (row, column chunk); columns right of the row's chromosome only.
+// CTA = 64 rows x 1024 columns; a thread owns one float4 column group, so the chromosome of its
+// 4 columns is fixed; per-tile partials are fp32 (<= 64 addends), folded into fp64 shared
+// tables with warp-aggregated atomics, then one global atomic per (tile, chromosome).
 // ---------------------------------------------------------------------------------------
 constexpr int kInterThreads = 256;
-constexpr int kInterCols = kInterThreads * 4 * 4;   // 4 float4 per thread per row
+constexpr int kInterCols = kInterThreads * 4;
+constexpr int kInterRows = 64;
 
 __global__ void __launch_bounds__(kInterThreads)
 inter_block_kernel(const float* __restrict__ map, int n, long long ld,
                    const int* __restrict__ chr_start, int n_chr,
                    const short* __restrict__ bin_chr, double* __restrict__ inter_sum,
-                   unsigned long long* __restrict__ inter_nnz, float* __restrict__ inter_minpos,
-                   int rows_per_cta) {
+                   unsigned long long* __restrict__ inter_nnz, float* __restrict__ inter_minpos) {
   extern __shared__ unsigned char smem_raw[];
   double* s_sum = reinterpret_cast<double*>(smem_raw);
   unsigned long long* s_nnz = reinterpret_cast<unsigned long long*>(s_sum + n_chr);
   float* s_min = reinterpret_cast<float*>(s_nnz + n_chr);
 
-  const int r0 = blockIdx.y * rows_per_cta;
+  const int r0 = blockIdx.y * kInterRows;
   if (r0 >= n) return;
-  const int r1 = min(r0 + rows_per_cta, n);
-  const int cbase = blockIdx.x * kInterCols;
-  int a_prev = -1;
-  for (int r = r0; r < r1; ++r) {
-    const int a = bin_chr[r];
-    const int col_lo = chr_start[a + 1];                  // first column of the next chromosome
-    if (cbase + kInterCols <= col_lo) continue;           // chunk entirely left of the inter part
-    if (a != a_prev) {
-      if (a_prev >= 0) {
-        __syncthreads();
-        for (int b = threadIdx.x; b < n_chr; b += blockDim.x) {
-          if (s_nnz[b] | (s_sum[b] != 0.0)) {
-            atomicAdd(&inter_sum[a_prev * n_chr + b], s_sum[b]);
-            atomicAdd(&inter_nnz[a_prev * n_chr + b], s_nnz[b]);
-          }
-          if (s_min[b] != INFINITY) atomic_min_pos_float(&inter_minpos[a_prev * n_chr + b], s_min[b]);
-        }
-      }
-      __syncthreads();
-      for (int b = threadIdx.x; b < n_chr; b += blockDim.x) { s_sum[b] = 0.0; s_nnz[b] = 0ull; s_min[b] = INFINITY; }
-      __syncthreads();
-      a_prev = a;
-    }
-    const float* row = map + (long long)r * ld;
-    int cur_b = -1;
-    double sum = 0.0;
-    unsigned long long cnt = 0;
-    float mn = INFINITY;
+  const int r1 = min(r0 + kInterRows, n);
+  const int cta_c1 = min(n, (int)(blockIdx.x + 1) * kInterCols);      // exclusive
+  int a_prev = bin_chr[r0];
+  // the inter part of a row starts at chr_start[a + 1], which only grows with the row index
+  if (cta_c1 <= chr_start[a_prev + 1]) return;
+  const int c0 = (blockIdx.x * kInterThreads + threadIdx.x) * 4;
+  const bool active = c0 < n;
+  int b[4];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int c0 = cbase + (it * kInterThreads + threadIdx.x) * 4;
-      if (c0 + 3 < col_lo || c0 >= n) continue;
-      const float4 v = *reinterpret_cast<const float4*>(row + c0);   // ld % 4 == 0, ld >= n
+  for (int j = 0; j < 4; ++j) b[j] = active ? (int)bin_chr[min(c0 + j, n - 1)] : 0;
+  for (int i = threadIdx.x; i < n_chr; i += blockDim.x) { s_sum[i] = 0.0; s_nnz[i] = 0ull; s_min[i] = INFINITY; }
+  __syncthreads();
+
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+  unsigned int cnt[4] = {0u, 0u, 0u, 0u};
+  float mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+
+  auto flush = [&](int a) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b0 = __shfl_sync(0xffffffffu, b[j], 0);
+      if (__all_sync(0xffffffffu, b[j] == b0)) {
+        const double ws = warp_sum((double)sum[j]);
+        const unsigned long long wc = warp_sum((unsigned long long)cnt[j]);
+        const float wm = warp_min(mn[j]);
+        if ((threadIdx.x & 31) == 0) {
+          if (wc | (ws != 0.0)) { atomicAdd(&s_sum[b0], ws); atomicAdd(&s_nnz[b0], wc); }
+          if (wm != INFINITY) atomic_min_pos_float(&s_min[b0], wm);
+        }
+      } else {
+        if (cnt[j] | (sum[j] != 0.f)) { atomicAdd(&s_sum[b[j]], (double)sum[j]); atomicAdd(&s_nnz[b[j]], (unsigned long long)cnt[j]); }
+        if (mn[j] != INFINITY) atomic_min_pos_float(&s_min[b[j]], mn[j]);
+      }
+      sum[j] = 0.f; cnt[j] = 0u; mn[j] = INFINITY;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_chr; i += blockDim.x) {
+      if (s_nnz[i] | (s_sum[i] != 0.0)) {
+        atomicAdd(&inter_sum[a * n_chr + i], s_sum[i]);
+        atomicAdd(&inter_nnz[a * n_chr + i], s_nnz[i]);
+      }
+      if (s_min[i] != INFINITY) atomic_min_pos_float(&inter_minpos[a * n_chr + i], s_min[i]);
+      s_sum[i] = 0.0; s_nnz[i] = 0ull; s_min[i] = INFINITY;
+    }
+    __syncthreads();
+  };
+
+  for (int r = r0; r < r1; ++r) {
+    const int a = bin_chr[r];                              // uniform
+    if (a != a_prev) { flush(a_prev); a_prev = a; }
+    const int col_lo = chr_start[a + 1];
+    if (active && c0 + 3 >= col_lo) {
+      const float4 v = ld_stream4(map + (long long)r * ld + c0);   // ld % 4 == 0, ld >= n
       const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int gc = c0 + cc;
-        if (gc < col_lo || gc >= n) continue;
-        const int b = bin_chr[gc];
-        if (b != cur_b) {
-          if (cur_b >= 0) {
-            atomicAdd(&s_sum[cur_b], sum);
-            atomicAdd(&s_nnz[cur_b], cnt);
-            if (mn != INFINITY) atomic_min_pos_float(&s_min[cur_b], mn);
-          }
-          cur_b = b; sum = 0.0; cnt = 0; mn = INFINITY;
+      for (int j = 0; j < 4; ++j) {
+        const int gc = c0 + j;
+        if (gc >= col_lo && gc < n) {
+          sum[j] += vv[j];
+          cnt[j] += (vv[j] != 0.f);
+          if (vv[j] > 0.f) mn[j] = fminf(mn[j], vv[j]);
         }
-        sum += (double)vv[cc];
-        cnt += (vv[cc] != 0.f);
-        if (vv[cc] > 0.f) mn = fminf(mn, vv[cc]);
       }
     }
-    if (cur_b >= 0) {
-      atomicAdd(&s_sum[cur_b], sum);
-      atomicAdd(&s_nnz[cur_b], cnt);
-      if (mn != INFINITY) atomic_min_pos_float(&s_min[cur_b], mn);
-    }
   }
-  if (a_prev >= 0) {
-    __syncthreads();
-    for (int b = threadIdx.x; b < n_chr; b += blockDim.x) {
-      if (s_nnz[b] | (s_sum[b] != 0.0)) {
-        atomicAdd(&inter_sum[a_prev * n_chr + b], s_sum[b]);
-        atomicAdd(&inter_nnz[a_prev * n_chr + b], s_nnz[b]);
-      }
-      if (s_min[b] != INFINITY) atomic_min_pos_float(&inter_minpos[a_prev * n_chr + b], s_min[b]);
-    }
-  }
+  flush(a_prev);
 }
 
 __global__ void init_expected_kernel(double* diag_sum, float* diag_minpos, int n, double* inter_sum,
@@ -394,12 +394,10 @@ HIA_API int hia_oe_expected_pass(const float* map, int32_t n, int64_t ld, const 
                                                          row_chunks);
   HIA_LAUNCH_CHECK();
   if (n_chr > 1) {
-    const int rows_per_cta = 8;
-    dim3 grid_i((n + kInterCols - 1) / kInterCols, (n + rows_per_cta - 1) / rows_per_cta);
+    dim3 grid_i((n + kInterCols - 1) / kInterCols, (n + kInterRows - 1) / kInterRows);
     const size_t sh = (size_t)n_chr * (8 + 8 + 4);
     inter_block_kernel<<<grid_i, kInterThreads, sh, stream>>>(map, n, ld, chr_start, n_chr, bin_chr,
-                                                              inter_sum, inter_nnz, inter_minpos,
-                                                              rows_per_cta);
+                                                              inter_sum, inter_nnz, inter_minpos);
     HIA_LAUNCH_CHECK();
   }
   return HIA_OK;

@@ -7,7 +7,10 @@
 // complex/src/main_local.py:112-115.
 //
 // HBM-bound: 12 B/nnz read + 4 B/cell written (fill) + 4..8 B/nnz scattered.
-// Pipeline: [block-min reduce] -> fill -> [zero the present cells] -> RED.ADD scatter.
+// Zero fill:  memset -> RED.ADD scatter.
+// Min fill:   NaN sentinel fill -> store 0 at present cells -> RED.ADD scatter -> min over the
+//             *scattered* cells (so duplicates are summed before the min, like coo->csr then
+//             np.min(data)) -> replace the remaining sentinels by the (per-block) min.
 // Duplicates are summed with fp32 RED atomics; with no duplicates the result is bit-exact
 // (0 + v == v), which is the case for every file the pipeline writes.
 #include "hia_common.cuh"
@@ -35,7 +38,7 @@ __global__ void init_keys_kernel(unsigned int* keys, int count) {
 // min over valid entries, per chromosome-pair block (BLOCK_MIN) and overall (slot C*C).
 __global__ void __launch_bounds__(256)
 block_min_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
-                 const float* __restrict__ vals, long long nnz, int n, int mtx_type,
+                 const float* __restrict__ dense, long long ld, long long nnz, int n, int mtx_type,
                  const int* __restrict__ chr_start, int n_chr, int per_block,
                  unsigned int* __restrict__ keys) {
   extern __shared__ int s_start[];
@@ -50,7 +53,7 @@ block_min_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
     int r = rows[e], c = cols[e];
     if (r < 0 || c < 0 || r >= n || c >= n) continue;
     if (mtx_type == HIA_MTX_TRIU && c < r) continue;
-    unsigned int k = float_to_ordered(vals[e]);
+    unsigned int k = float_to_ordered(dense[(long long)r * ld + c]);   // summed value
     all_key = min(all_key, k);
     if (per_block) {
       int slot = find_chr(s_start, n_chr, r) * n_chr + find_chr(s_start, n_chr, c);
@@ -69,10 +72,24 @@ block_min_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
   if ((threadIdx.x & 31) == 0 && all_key != 0xffffffffu) atomicMin(&keys[slot_all], all_key);
 }
 
-// out[r][c] = fill(r, c). One thread per 4 columns (128-bit stores), rows over blockIdx.y.
 __global__ void __launch_bounds__(256)
-fill_kernel(float* __restrict__ out, int n, long long ld, int fill_mode, int mtx_type,
-            const int* __restrict__ chr_start, int n_chr, const unsigned int* __restrict__ keys) {
+fill_const_kernel(float* __restrict__ out, int n, long long ld, float value) {
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c0 >= n) return;
+  for (int r = blockIdx.y; r < n; r += gridDim.y) {
+    float* p = out + (long long)r * ld + c0;
+    if (c0 + 3 < n) {
+      *reinterpret_cast<float4*>(p) = make_float4(value, value, value, value);
+    } else {
+      for (int j = 0; j < 4 && c0 + j < n; ++j) p[j] = value;
+    }
+  }
+}
+
+// Replace the NaN sentinels (absent cells) by fill(r, c). One thread per 4 columns.
+__global__ void __launch_bounds__(256)
+fixup_kernel(float* __restrict__ out, int n, long long ld, int fill_mode, int mtx_type,
+             const int* __restrict__ chr_start, int n_chr, const unsigned int* __restrict__ keys) {
   extern __shared__ int s_start[];
   for (int i = threadIdx.x; i <= n_chr; i += blockDim.x) s_start[i] = chr_start[i];
   __syncthreads();
@@ -89,20 +106,31 @@ fill_kernel(float* __restrict__ out, int n, long long ld, int fill_mode, int mtx
     for (int j = 0; j < 4; ++j) cb[j] = find_chr(s_start, n_chr, min(c0 + j, n - 1));
   }
   for (int r = blockIdx.y; r < n; r += gridDim.y) {
-    float v[4] = {gfill, gfill, gfill, gfill};
-    if (fill_mode == HIA_FILL_BLOCK_MIN) {
-      int a = find_chr(s_start, n_chr, r);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int b = cb[j];
-        // triu input: only upper blocks hold entries; the lower block mirrors the upper one
-        int slot = (mtx_type == HIA_MTX_TRIU && b < a) ? (b * n_chr + a) : (a * n_chr + b);
-        unsigned int k = keys[slot];
-        v[j] = (k == 0xffffffffu) ? 0.f : ordered_to_float(k);
-      }
-    }
     float* p = out + (long long)r * ld + c0;
-    if (c0 + 3 < n) {
+    float v[4];
+    const bool full = c0 + 3 < n;
+    if (full) {
+      const float4 t = *reinterpret_cast<const float4*>(p);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+      for (int j = 0; j < 4; ++j) v[j] = (c0 + j < n) ? p[j] : 0.f;
+    }
+    if (!(v[0] != v[0] || v[1] != v[1] || v[2] != v[2] || v[3] != v[3])) continue;
+    const int a = (fill_mode == HIA_FILL_BLOCK_MIN) ? find_chr(s_start, n_chr, r) : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (v[j] == v[j]) continue;
+      float f = gfill;
+      if (fill_mode == HIA_FILL_BLOCK_MIN) {
+        const int b = cb[j];
+        // triu input: only upper blocks hold entries; the lower block mirrors the upper one
+        const int slot = (mtx_type == HIA_MTX_TRIU && b < a) ? (b * n_chr + a) : (a * n_chr + b);
+        const unsigned int k = keys[slot];
+        f = (k == 0xffffffffu) ? 0.f : ordered_to_float(k);
+      }
+      v[j] = f;
+    }
+    if (full) {
       *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     } else {
       for (int j = 0; j < 4 && c0 + j < n; ++j) p[j] = v[j];
@@ -161,28 +189,29 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
     } else {
       HIA_CUDA(cudaMemset2DAsync(out, (size_t)ld * 4, 0, (size_t)n * 4, n, stream));
     }
+    if (nnz > 0) {
+      scatter_kernel<true><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld);
+      HIA_LAUNCH_CHECK();
+    }
   } else {
     unsigned int* keys = static_cast<unsigned int*>(workspace);
     const int nk = n_chr * n_chr + 1;
     init_keys_kernel<<<(nk + 255) / 256, 256, 0, stream>>>(keys, nk);
     HIA_LAUNCH_CHECK();
     const size_t sh = (size_t)(n_chr + 1) * sizeof(int);
-    if (nnz > 0) {
-      block_min_kernel<<<grid_e, threads, sh, stream>>>(rows, cols, vals, nnz, n, mtx_type,
-                                                          chr_start, n_chr,
-                                                          fill_mode == HIA_FILL_BLOCK_MIN, keys);
-      HIA_LAUNCH_CHECK();
-    }
     dim3 grid((n + threads * 4 - 1) / (threads * 4), min(n, 4096));
-    fill_kernel<<<grid, threads, sh, stream>>>(out, n, ld, fill_mode, mtx_type, chr_start, n_chr, keys);
+    fill_const_kernel<<<grid, threads, 0, stream>>>(out, n, ld, nanf(""));
     HIA_LAUNCH_CHECK();
     if (nnz > 0) {
       scatter_kernel<false><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld);
       HIA_LAUNCH_CHECK();
+      scatter_kernel<true><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld);
+      HIA_LAUNCH_CHECK();
+      block_min_kernel<<<grid_e, threads, sh, stream>>>(rows, cols, out, ld, nnz, n, mtx_type, chr_start,
+                                                          n_chr, fill_mode == HIA_FILL_BLOCK_MIN, keys);
+      HIA_LAUNCH_CHECK();
     }
-  }
-  if (nnz > 0) {
-    scatter_kernel<true><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld);
+    fixup_kernel<<<grid, threads, sh, stream>>>(out, n, ld, fill_mode, mtx_type, chr_start, n_chr, keys);
     HIA_LAUNCH_CHECK();
   }
   return HIA_OK;

@@ -184,3 +184,41 @@ def similarity(x, flavour=SIM_COSINE_DISTANCE, precision=PREC_3XTF32, band=None,
                             band_lo, band_hi, k_chunk, _ptr(workspace), workspace.numel(), _stream())
     _lib.check(st, "hia_similarity")
     return out
+
+
+# ------------------------------------------------------------------------------- a9 eigen
+def topk_eig(c, k=3, block=8, steps=None, tol=1e-6, max_restarts=8, seed=0, return_info=False):
+    """Largest-algebraic k eigenpairs of a dense symmetric fp32 matrix (e.g. the Pearson map).
+    No reference implementation exists (oracle: numpy.linalg.eigh) -- north-star item.
+    Block Lanczos on the device; restarted from the current Ritz vectors until every residual
+    ||C u - lambda u|| <= tol * |lambda_1|. Returns (eigvals[k] fp64, eigvecs[n, k] fp32)."""
+    lib = _lib.load()
+    _need_cuda(c)
+    n = c.shape[0]
+    assert c.shape == (n, n) and c.dtype == torch.float32 and c.stride(1) == 1
+    if n < 2 * block:
+        block = 4
+    if steps is None:
+        steps = 12
+    steps = max(1, min(steps, n // block - 1, 272 // block - 1))
+    if block * (steps + 1) > n or k > block:
+        raise _lib.HiaError(f"matrix of {n} bins is too small for k={k}")
+    dev = c.device
+    ws = torch.empty(lib.hia_topk_eig_workspace_bytes(n, block, steps), dtype=torch.uint8, device=dev)
+    eigvals = torch.empty(k, dtype=torch.float64, device=dev)
+    eigvecs = torch.empty((k, n), dtype=torch.float32, device=dev)
+    resid = torch.empty(k, dtype=torch.float64, device=dev)
+    init, n_init, info = None, 0, []
+    for it in range(max_restarts):
+        st = lib.hia_topk_eig(_ptr(c), n, c.stride(0), k, block, steps, seed + it, _ptr(init), n_init,
+                              _ptr(eigvals), _ptr(eigvecs), _ptr(resid), _ptr(ws), ws.numel(),
+                              _stream())
+        _lib.check(st, "hia_topk_eig")
+        r = resid.cpu().numpy()
+        lam = eigvals.cpu().numpy()
+        info.append((float(r.max()), float(abs(lam[0]))))
+        if np.all(r <= tol * max(abs(lam[0]), 1e-300)):
+            break
+        init, n_init = eigvecs.clone(), k
+    out = (eigvals, eigvecs.t())
+    return out + (info,) if return_info else out

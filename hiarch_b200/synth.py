@@ -108,10 +108,18 @@ def write_sample(prefix, names, lens, bin_size, seed=0, lam_inter=0.6, x_shape=0
     return f"{prefix}_normalized.mtx", f"{prefix}.window.bed"
 
 
-def device_dense_map(lens, seed=0, lam_inter=0.6, device="cuda", dtype=None):
+COMPONENT_BETAS = (0.5, 0.3, 0.2)       # A/B compartments + two weaker sub-compartment tracks
+
+
+def device_dense_map(lens, seed=0, lam_inter=0.6, device="cuda", dtype=None,
+                     betas=COMPONENT_BETAS):
     """Large maps: symmetric dense fp32 Poisson map built directly in HBM (torch RNG stream,
     `torch.Generator(device).manual_seed(seed)`), one chromosome-pair block at a time so the
-    peak footprint stays ~2x the map. Returns (dense [N,N] fp32 'all'-type, seps)."""
+    peak footprint stays ~2x the map. The rate is
+        lambda = base(d) * (1 + sum_m beta_m c_m[i] c_m[j])
+    with three compartment-like tracks of decreasing strength and smoothing scale, so that the
+    top-3 eigenvectors of the correlation map are well separated (like sub-compartments in
+    real maps). Returns (dense [N,N] fp32 'all'-type, seps)."""
     import torch
     dtype = dtype or torch.float32
     gen = torch.Generator(device=device)
@@ -119,8 +127,11 @@ def device_dense_map(lens, seed=0, lam_inter=0.6, device="cuda", dtype=None):
     n = int(sum(lens))
     seps = chr_seps_from_lens(lens)
     rng = np.random.default_rng(seed)
-    comp = torch.from_numpy(np.concatenate(
-        [compartment_track(L, rng, max(3, L // 40)) for L in lens])).to(device=device, dtype=dtype)
+    comps = []
+    for m, beta in enumerate(betas):
+        track = np.concatenate([compartment_track(L, rng, max(3, L // (40 * (m + 1)))) for L in lens])
+        comps.append(np.sqrt(beta) * track)
+    comp = torch.from_numpy(np.stack(comps, axis=1)).to(device=device, dtype=dtype)   # [N, M]
     out = torch.empty((n, n), device=device, dtype=dtype)
     for a, (s1, e1) in enumerate(seps):
         ca = comp[s1:e1 + 1]
@@ -128,7 +139,7 @@ def device_dense_map(lens, seed=0, lam_inter=0.6, device="cuda", dtype=None):
             if b < a:
                 continue
             cb = comp[s2:e2 + 1]
-            cc = 1.0 + BETA * torch.outer(ca, cb)
+            cc = 1.0 + ca @ cb.T
             if a == b:
                 L = e1 - s1 + 1
                 i = torch.arange(L, device=device, dtype=dtype)

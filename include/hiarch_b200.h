@@ -41,6 +41,8 @@ int hia_version(void);
 const char* hia_status_string(int status);
 /* last CUDA error text seen by this thread inside the library (for HIA_ERR_CUDA) */
 const char* hia_last_cuda_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t hia_launch_count(void);
 
 /* ------------------------------------------------------------------------------------ */
 /* a1/a2  sparse (i, j, v) -> dense symmetric                                            */
@@ -119,6 +121,33 @@ int64_t hia_similarity_workspace_bytes(int32_t m, int32_t k, int precision);
 int hia_similarity(const float* x, int32_t m, int32_t k, int64_t ld_x, float* out, int64_t ld_out,
                    int flavour, int precision, int32_t band_lo, int32_t band_hi, int32_t k_chunk,
                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The two phases of hia_similarity(precision = 3xTF32) as separate calls, so that a caller
+ * can time (or overlap) them: prep = fp64 row statistics + TF32 hi/lo planes into the workspace
+ * (12 B/cell, HBM-bound); gemm = the tcgen05 contraction + epilogue (tensor-bound). */
+int hia_similarity_prep(const float* x, int32_t m, int32_t k, int64_t ld_x, int flavour,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+int hia_similarity_gemm(int32_t m, int32_t k, float* out, int64_t ld_out, int flavour,
+                        int32_t band_lo, int32_t band_hi, int32_t k_chunk, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* a9  top-k eigenvectors of a dense symmetric fp32 matrix (largest algebraic).          */
+/* No reference implementation exists (the reference never decomposes anything); the     */
+/* north-star asks for compartment eigenvectors: oracle = numpy.linalg.eigh.             */
+/* Block Lanczos (block in {4, 8}, `steps` Krylov steps, full re-orthogonalisation),      */
+/* Rayleigh-Ritz by an on-device Jacobi solver. block * (steps + 1) <= min(n, 272).       */
+/* init_vecs: optional n_init <= block start vectors (fp32, each contiguous, length n)    */
+/* for restarts. Outputs (device): eigvals[k] fp64 descending, eigvecs[k][n] fp32 (each   */
+/* vector contiguous, unit norm, sign arbitrary), resid[k] = ||C u - lambda u||_2 fp64.   */
+/* Exact for positive semi-definite input (Pearson maps); for indefinite input pairs      */
+/* +lambda/-lambda of equal magnitude may mix.                                            */
+/* ------------------------------------------------------------------------------------ */
+int64_t hia_topk_eig_workspace_bytes(int32_t n, int32_t block, int32_t steps);
+int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block, int32_t steps,
+                 uint64_t seed, const float* init_vecs, int32_t n_init, double* eigvals,
+                 float* eigvecs, double* resid, void* workspace, int64_t workspace_bytes,
+                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -224,3 +224,41 @@ def test_similarity_golden_adj_and_band(golden):
     i, j = np.indices((m, m))
     inb = (np.abs(i - j) >= lo) & (np.abs(i - j) <= hi)
     assert np.array_equal(band[inb], full[inb])
+
+
+# --------------------------------------------------------------------------------- top-k eigen
+def _check_eig(C64, k=3, tol=1e-6):
+    from hiarch_b200 import ops
+    n = C64.shape[0]
+    cd = ops.alloc_map(n)
+    cd.copy_(_dev(C64, torch.float32))
+    c32 = cd.cpu().numpy().astype(np.float64)             # the identical matrix the GPU sees
+    w_ref, v_ref = O.topk_eig(c32, k)
+    w, v, info = ops.topk_eig(cd, k=k, tol=tol, return_info=True)
+    w, v = w.cpu().numpy(), v.cpu().numpy().astype(np.float64)
+    print("eig restarts/residuals:", info)
+    assert np.allclose(w, w_ref, rtol=1e-5)
+    for j in range(k):
+        cos = abs(v[:, j] @ v_ref[:, j]) / np.linalg.norm(v[:, j])
+        assert cos >= 0.9999, (j, cos)                    # north-star: |cos| >= 0.9999
+    assert np.allclose(np.linalg.norm(v, axis=0), 1.0, atol=1e-4)
+
+
+def test_topk_eig_planted_spectrum():
+    rng = np.random.default_rng(3)
+    n = 700
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.concatenate([[50.0, 31.0, 17.0, 9.0], rng.uniform(0.0, 4.0, n - 4)])
+    _check_eig((q * lam) @ q.T)
+
+
+def test_topk_eig_of_pearson_map(golden):
+    g = golden("g3chr")
+    _check_eig(O.pearson(g["norm_de"]))
+
+
+def test_topk_eig_small_and_k1():
+    rng = np.random.default_rng(4)
+    a = rng.standard_normal((64, 20))
+    _check_eig(a @ a.T + np.diag(np.linspace(0, 30, 64)), k=1)
+    _check_eig(a @ a.T + np.diag(np.linspace(0, 30, 64)), k=3)

@@ -95,6 +95,13 @@ def main():
     err = (simout[:sub, :sub].double() - ref).abs()
     err.fill_diagonal_(0)
     print("similarity max abs err vs fp64 (256x256 corner):", float(err.max()), flush=True)
+    t0 = time.time()
+    w, v, info = ops.topk_eig(simout, k=3, return_info=True)
+    torch.cuda.synchronize()
+    print("topk_eig wall", time.time() - t0, "s; eigvals", w.cpu().numpy(), "info", info, flush=True)
+    best, _ = timeit(lambda: ops.topk_eig(simout, k=3, max_restarts=1), reps=2)
+    res["topk_eig_one_cycle_12steps"] = dict(ms=best)
+    print(json.dumps(res), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/perf_probe.json", "w"), indent=1)
 

@@ -11,18 +11,19 @@
 //       warp 0   TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, 128 B = 32 fp32 per row)
 //       warp 1   MMA issuer     (tcgen05.mma.cta_group::1.kind::tf32, M=128, N=256, K=8 per
 //                                instruction; 3 MMAs per k-step: hi.hi + hi.lo + lo.hi)
-//       warps 2-5 epilogue      (tcgen05.ld 32x32b.x32 -> fp32 running tile -> 1-c / c ->
-//                                coalesced direct + mirrored stores)
+//       warps 2-9 epilogue      (tcgen05.ld 32x32b.x32 -> fp32 running sums in registers ->
+//                                1-c / c -> coalesced direct + mirrored stores)
 //     Accumulators live in tensor memory (2 x 256 columns, double buffered). To bound the
 //     rounding of long fp32 accumulation chains the K loop is cut into chunks (k_chunk
-//     elements): each chunk accumulates in TMEM, the epilogue folds it into a per-CTA fp32
-//     running tile (L2 resident, coalesced) while the next chunk's MMAs run.
+//     elements): each chunk accumulates in TMEM, the 8 epilogue warps fold it into fp32
+//     running sums held in registers (128 per thread) while the next chunk's MMAs run.
 //   Only tiles touching the upper triangle (and the requested |i-j| band) are computed; the
 //   lower triangle is written as the exact mirror, the diagonal as the exact constant.
 //
 // 3xTF32 error budget: |hi.hi + hi.lo + lo.hi - x.y| <= ~2^-21 |x||y| per product; fp32
 // accumulation over <= k_chunk/8 MMA steps, then RN fp32 adds of <= k/k_chunk partials.
 #include <cuda.h>
+#include <stdlib.h>
 #include "hia_common.cuh"
 
 namespace hia {
@@ -36,7 +37,7 @@ constexpr int STAGES = 2;
 constexpr int A_BYTES = BM * BK * 4;           // 16 KB
 constexpr int B_BYTES = BN * BK * 4;           // 32 KB
 constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // hi + lo planes: 96 KB
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;                   // 2 per TMEM lane quarter x 128 columns each
 constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr int TRANS_PAD = 33;
 constexpr int SMEM_TILES = STAGES * STAGE_BYTES;                      // 196608
@@ -137,8 +138,8 @@ struct TileCoord { int m_blk; int n_blk; };
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                    const TileCoord* __restrict__ tiles, int num_tiles, int m, int num_k_blocks,
-                   int kb_per_chunk, float* __restrict__ out, long long ld_out,
-                   float* __restrict__ running, int flavour) {
+                   int kb_per_chunk, float* __restrict__ out, long long ld_out, int flavour,
+                   unsigned int* __restrict__ sync_ctr, int sync_every) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -180,6 +181,20 @@ syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         const int m0 = tiles[t].m_blk * BM, n0 = tiles[t].n_blk * BN;
         for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          if (sync_every > 0 && (it % sync_every) == 0) {
+            // Soft rendezvous of all TMA producers: keeps the CTAs that share operand tiles
+            // within the L2 residency window of each other (measured: without it they drift
+            // apart over a 1.4 ms tile and every operand tile is re-read from HBM).
+            // Timing only -- bounded wait, then proceed: cannot deadlock, carries no data.
+            const uint32_t step = it / sync_every;
+            const int seq = (t - (int)blockIdx.x) / (int)gridDim.x;
+            const uint32_t expected = (uint32_t)min((int)gridDim.x, num_tiles - seq * (int)gridDim.x);
+            atomicAdd(&sync_ctr[step], 1u);
+            for (int spin = 0; spin < 256; ++spin) {
+              if (*reinterpret_cast<volatile unsigned int*>(&sync_ctr[step]) >= expected) break;
+              __nanosleep(64);
+            }
+          }
           mbar_wait(&empty_bar[s], ph ^ 1);
           unsigned char* st = smem + s * STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
@@ -229,74 +244,70 @@ syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       }
     }
   } else {
-    // ===================================================== epilogue warps (TMEM lane quarter = warp % 4)
+    // ===================================================== epilogue warps
+    // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter split the 256
+    // accumulator columns. The fp32 running sums of the K chunks live in REGISTERS (128 per
+    // thread): a chunk costs 4 x (tcgen05.ld + 32 FADD) per warp, no memory traffic.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     float* trans = s_trans + (warp - 2) * 32 * TRANS_PAD;
-    float* run = running + (long long)blockIdx.x * (BM * BN);
     uint32_t chunk_it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = tiles[t].m_blk * BM, n0 = tiles[t].n_blk * BN;
-      const int row_l = q * 32 + lane;                    // row within the tile == TMEM lane
+      const int m0 = tiles[t].m_blk * BM, n0 = tiles[t].n_blk * BN + half * (BN / 2);
+      float accr[BN / 2];
+#pragma unroll
+      for (int j = 0; j < BN / 2; ++j) accr[j] = 0.f;
       for (int ch = 0; ch < chunks_per_tile; ++ch, ++chunk_it) {
         const uint32_t buf = chunk_it & 1, tph = (chunk_it >> 1) & 1;
         mbar_wait(&tfull_bar[buf], tph);
         tcgen05_fence_after();
-        const bool last = (ch == chunks_per_tile - 1);
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
-#pragma unroll 1
-        for (int cg = 0; cg < BN / 32; ++cg) {
-          // skip column groups that lie entirely below the diagonal band of this warp's rows
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * (BN / 2);
+#pragma unroll
+        for (int cg = 0; cg < BN / 64; ++cg) {
           uint32_t v[32];
           tmem_ld32(taddr0 + cg * 32, v);
-          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          // running tile layout [col][row]: lanes hit consecutive addresses
-          float* rp = run + (long long)(cg * 32) * BM + row_l;
-          if (ch > 0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += rp[j * BM];
-          }
-          if (!last) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) rp[j * BM] = f[j];
-          } else {
-            const int gr_base = m0 + q * 32;              // first global row of this warp
-            const int gc_base = n0 + cg * 32;
-            if (gc_base + 31 >= gr_base && gr_base < m && gc_base < m) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float c = f[j];
-                c = fminf(1.f, fmaxf(-1.f, c));           // NaN stays NaN (fminf/fmaxf would drop it)
-                if (f[j] != f[j]) c = f[j];
-                f[j] = (flavour == HIA_SIM_COSINE_DISTANCE) ? (1.f - c) : c;
-              }
-              const float diag_val = (flavour == HIA_SIM_COSINE_DISTANCE) ? 0.f : 1.f;
-              const int gr = gr_base + lane;
-              // mirrored store out[gc][gr] (lanes = consecutive gr -> coalesced)
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int gc = gc_base + j;
-                if (gr < m && gc < m && gc > gr) out[(long long)gc * ld_out + gr] = f[j];
-              }
-              // direct store out[gr][gc] through a 32x32 shared transpose (coalesced rows)
-#pragma unroll
-              for (int j = 0; j < 32; ++j) trans[lane * TRANS_PAD + j] = f[j];
-              __syncwarp();
-#pragma unroll 4
-              for (int i = 0; i < 32; ++i) {
-                const int r = gr_base + i, gc = gc_base + lane;
-                if (r < m && gc < m && gc >= r) {
-                  out[(long long)r * ld_out + gc] = (gc == r) ? diag_val : trans[i * TRANS_PAD + lane];
-                }
-              }
-              __syncwarp();
-            }
-          }
+          for (int j = 0; j < 32; ++j) accr[cg * 32 + j] += __uint_as_float(v[j]);
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);       // accumulator buffer is free again
+      }
+      // ---- finalize + store (overlaps the next tile's MMAs)
+      const int gr_base = m0 + q * 32;                      // first global row of this warp
+      const float diag_val = (flavour == HIA_SIM_COSINE_DISTANCE) ? 0.f : 1.f;
+#pragma unroll
+      for (int cg = 0; cg < BN / 64; ++cg) {
+        const int gc_base = n0 + cg * 32;
+        // skip column groups entirely below the diagonal for this warp's rows / out of range
+        if (gc_base + 31 >= gr_base && gr_base < m && gc_base < m) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float raw = accr[cg * 32 + j];
+            float c = fminf(1.f, fmaxf(-1.f, raw));         // |cos| clipped to 1 like scipy
+            if (raw != raw) c = raw;                        // NaN stays NaN
+            f[j] = (flavour == HIA_SIM_COSINE_DISTANCE) ? (1.f - c) : c;
+          }
+          const int gr = gr_base + lane;
+          // mirrored store out[gc][gr] (lanes = consecutive gr -> coalesced)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gc = gc_base + j;
+            if (gr < m && gc < m && gc > gr) out[(long long)gc * ld_out + gr] = f[j];
+          }
+          // direct store out[gr][gc] through a 32x32 shared transpose (coalesced rows)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) trans[lane * TRANS_PAD + j] = f[j];
+          __syncwarp();
+#pragma unroll 4
+          for (int i = 0; i < 32; ++i) {
+            const int r = gr_base + i, gc = gc_base + lane;
+            if (r < m && gc < m && gc >= r)
+              out[(long long)r * ld_out + gc] = (gc == r) ? diag_val : trans[i * TRANS_PAD + lane];
+          }
+          __syncwarp();
+        }
       }
     }
   }
@@ -416,17 +427,27 @@ long long similarity_fp64_workspace(int m, int k);
 }  // namespace hia
 
 // workspace layout (3xTF32): [hi plane][lo plane][running tiles: 148 x 128 x 256 fp32][tile list]
-static int64_t tf32_ws_layout(int m, int k, int64_t* off_lo, int64_t* off_run, int64_t* off_tiles) {
+constexpr int kSyncEvery = 32;          // k-blocks between producer rendezvous
+static int64_t sync_counters(int m, int k) {
+  using namespace hia;
+  const int64_t ntiles = (int64_t)((m + BM - 1) / BM) * ((m + BN - 1) / BN);
+  const int64_t per_cta = ntiles / kNumSMs + 2;
+  return per_cta * (round_up(k, BK) / BK) / kSyncEvery + 64;
+}
+static int64_t tf32_ws_layout(int m, int k, int64_t* off_lo, int64_t* off_run, int64_t* off_tiles,
+                              int64_t* off_sync = nullptr) {
   using namespace hia;
   const int64_t kpad = round_up(k, BK);
   const int64_t plane = (int64_t)m * kpad * 4;
   const int64_t plane_al = (plane + 1023) / 1024 * 1024;
-  const int64_t run = (int64_t)kNumSMs * BM * BN * 4;
+  const int64_t run = 0;   // (round 1 kept the chunk running sums here; they live in registers now)
   const int64_t ntiles = (int64_t)((m + BM - 1) / BM) * ((m + BN - 1) / BN);
   if (off_lo) *off_lo = plane_al;
   if (off_run) *off_run = 2 * plane_al;
   if (off_tiles) *off_tiles = 2 * plane_al + run;
-  return 2 * plane_al + run + ntiles * (int64_t)sizeof(TileCoord) + 1024;
+  const int64_t tiles_al = (ntiles * (int64_t)sizeof(TileCoord) + 1023) / 1024 * 1024;
+  if (off_sync) *off_sync = 2 * plane_al + run + tiles_al;
+  return 2 * plane_al + run + tiles_al + sync_counters(m, k) * 4 + 1024;
 }
 
 HIA_API int64_t hia_similarity_workspace_bytes(int32_t m, int32_t k, int precision) {
@@ -480,12 +501,11 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
   HIA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   if (major != 10) return HIA_ERR_ARCH;
 
-  int64_t off_lo, off_run, off_tiles;
-  tf32_ws_layout(m, k, &off_lo, &off_run, &off_tiles);
+  int64_t off_lo, off_run, off_tiles, off_sync;
+  tf32_ws_layout(m, k, &off_lo, &off_run, &off_tiles, &off_sync);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   float* hi = reinterpret_cast<float*>(ws);
   float* lo = reinterpret_cast<float*>(ws + off_lo);
-  float* running = reinterpret_cast<float*>(ws + off_run);
   TileCoord* d_tiles = reinterpret_cast<TileCoord*>(ws + off_tiles);
   const int kpad = round_up(k, BK);
 
@@ -517,9 +537,13 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
   int kb_per_chunk = max(1, k_chunk / BK);
   HIA_CUDA(cudaFuncSetAttribute(syrk_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int grid = min(num_tiles, kNumSMs);
+  unsigned int* sync_ctr = reinterpret_cast<unsigned int*>(ws + off_sync);
+  static const int sync_every = getenv("HIA_SYRK_SYNC") ? atoi(getenv("HIA_SYRK_SYNC")) : kSyncEvery;
+  HIA_CUDA(cudaMemsetAsync(sync_ctr, 0, (size_t)sync_counters(m, k) * 4, stream));
   syrk_tf32x3_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_hi, map_lo, d_tiles, num_tiles, m,
                                                                 num_k_blocks, kb_per_chunk, out, ld_out,
-                                                                running, flavour);
+                                                                flavour, sync_ctr,
+                                                                (sync_every >= kSyncEvery) ? sync_every : 0);
   HIA_LAUNCH_CHECK();
   return HIA_OK;
 }

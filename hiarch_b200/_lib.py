@@ -34,6 +34,19 @@ PROTOTYPES = {
     "hia_similarity_prep": (c_int, [c_vp, c_i32, c_i32, c_i64, c_int, c_vp, c_i64, c_vp]),
     "hia_similarity_gemm": (c_int, [c_i32, c_i32, c_vp, c_i64, c_int, c_i32, c_i32, c_i32, c_vp, c_i64,
                                     c_vp]),
+    "hia_percentiles_workspace_bytes": (c_i64, []),
+    "hia_percentiles": (c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_i64, c_vp]),
+    "hia_clip": (c_int, [c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp]),
+    "hia_core_moments": (c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hia_zscore": (c_int, [c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp]),
+    "hia_sym_clip_bounds": (c_int, [c_vp, c_vp, c_vp]),
+    "hia_band_entropy_workspace_bytes": (c_i64, [c_i32]),
+    "hia_band_entropy": (c_int, [c_vp, c_i32, c_i64, c_i32, c_i32, c_vp, c_i32, ctypes.c_double, c_vp,
+                                 c_vp, c_i64, c_vp]),
+    "hia_row_profiles": (c_int, [c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp,
+                                 c_vp]),
+    "hia_smooth1d_reflect": (c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, ctypes.c_double, c_i32, c_vp]),
+    "hia_gf_pool_scores": (c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hia_topk_eig_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),
     "hia_topk_eig": (c_int, [c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_i32,
                              c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),

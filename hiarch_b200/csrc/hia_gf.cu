@@ -1,0 +1,258 @@
+// a11 / a14 / a15: global-folding reductions.
+//
+//  row_profile: keep_high_cons (publish/confor/src/S1_preprocess/S1_2_find_anchors/
+//      U2_keep_top_cons.py:20-41) fused with get_inter_rowsum (S2_1_find_by_inter_rowsum.py:26-37)
+//      and get_intra_rowsum (S2_3_find_by_intra_low.py:18-27): one 4 B/cell pass produces, per row,
+//      sum_{inter cols} f(x) and sum_{intra cols} f(x), f(x) = max(x - t, 0) (reverse: max(t - x, 0)),
+//      plus the global sum / count of the positive f values (the `new_data /= mean(positives)`
+//      normalisation) -- the thresholded map is never materialised.
+//  smooth1d: smooth_rowsum (S2_1:42-55): per-chromosome odd box filter, scipy 'reflect'.
+//  pool + finish: pool_mtx / norm_mtx / symmetry (publish/confor/src/S2_to_train_mtx/
+//      preprocess.py:8-48) and the template scores of to_confor
+//      (publish/confor/src/S5_sim_to_pat/to_confor.py:35-47).
+#include "hia_common.cuh"
+
+namespace hia {
+namespace {
+
+// ------------------------------------------------------------------------------ row profiles
+__global__ void __launch_bounds__(256)
+row_profile_kernel(const float* __restrict__ x, int n, long long ld, const int* __restrict__ chr_start,
+                   const short* __restrict__ bin_chr, const double* __restrict__ thr, int reverse,
+                   double* __restrict__ inter_sum, double* __restrict__ intra_sum,
+                   double* __restrict__ pos_stats /* [sum, count] */) {
+  __shared__ double s_red[8][4];
+  const int r = blockIdx.x;
+  const int a = bin_chr[r];
+  const int s = chr_start[a], e = chr_start[a + 1];      // [s, e)
+  const double t = *thr;
+  const float* row = x + (long long)r * ld;
+  double acc_inter = 0.0, acc_intra = 0.0, acc_pos = 0.0, cnt_pos = 0.0;
+  for (int c0 = threadIdx.x * 4; c0 < n; c0 += blockDim.x * 4) {
+    float v[4];
+    const int nv = min(4, n - c0);
+    if (nv == 4) { const float4 q = ld_stream4(row + c0); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+    else for (int j = 0; j < 4; ++j) v[j] = (j < nv) ? row[c0 + j] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= nv) break;
+      const double d = reverse ? (t - (double)v[j]) : ((double)v[j] - t);
+      const double f = d > 0.0 ? d : 0.0;
+      const int c = c0 + j;
+      if (c >= s && c < e) acc_intra += f; else acc_inter += f;
+      if (f > 0.0) { acc_pos += f; cnt_pos += 1.0; }
+    }
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double vals[4] = {acc_inter, acc_intra, acc_pos, cnt_pos};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const double q = warp_sum(vals[k]); if (lane == 0) s_red[w][k] = q; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double q = 0; for (int i = 0; i < 8; ++i) q += s_red[i][threadIdx.x];
+    if (threadIdx.x == 0) inter_sum[r] = q;
+    else if (threadIdx.x == 1) intra_sum[r] = q;
+    else atomicAdd(&pos_stats[threadIdx.x - 2], q);
+  }
+}
+
+// profile = rowsum / n_cols / mean(positives)
+__global__ void profile_finish_kernel(const double* __restrict__ inter_sum, const double* __restrict__ intra_sum,
+                                      const double* __restrict__ pos_stats, int n,
+                                      const int* __restrict__ chr_start, const short* __restrict__ bin_chr,
+                                      int norm, double* __restrict__ inter_prof, double* __restrict__ intra_prof) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int a = bin_chr[r];
+  const int len = chr_start[a + 1] - chr_start[a];
+  const double mean_pos = norm ? pos_stats[0] / pos_stats[1] : 1.0;
+  const int other = n - len;
+  inter_prof[r] = other > 0 ? inter_sum[r] / mean_pos / (double)other : 0.0;
+  intra_prof[r] = intra_sum[r] / mean_pos / (double)len;
+}
+
+// scipy.ndimage 'reflect' (d c b a | a b c d | d c b a), any distance
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (n == 1) return 0;
+  const int p = 2 * n;
+  i %= p;
+  if (i < 0) i += p;
+  return i < n ? i : p - 1 - i;
+}
+
+__global__ void smooth1d_kernel(const double* __restrict__ in, double* __restrict__ out, int n,
+                                const int* __restrict__ chr_start, const short* __restrict__ bin_chr,
+                                double kernal_per, int min_kernal_len) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int a = bin_chr[r];
+  const int s = chr_start[a], len = chr_start[a + 1] - s;
+  int kl = (int)((double)len * kernal_per);              // get_kernal_len (S2_1:15-20)
+  if (kl < min_kernal_len) kl = min_kernal_len;
+  kl = (kl / 2) * 2 + 1;
+  const double w = 1.0 / (double)kl;
+  const int h = kl / 2;
+  double acc = 0.0;
+  for (int o = -h; o <= h; ++o) acc += w * in[s + reflect_idx(r - s + o, len)];
+  out[r] = acc;
+}
+
+// ------------------------------------------------------------------------------ GF_S2 pooling
+struct PairDesc { int r0, n1, c0, n2, cen1, cen2, intra, pad; };
+
+// adaptive-average-pool cell range: [floor(i*n/k), ceil((i+1)*n/k))
+__device__ __forceinline__ void pool_range(int i, int n, int k, int& lo, int& hi) {
+  lo = (int)(((long long)i * n) / k);
+  hi = (int)(((long long)(i + 1) * n + k - 1) / k);
+}
+
+__global__ void __launch_bounds__(256)
+pool_kernel(const float* __restrict__ x, long long ld, const PairDesc* __restrict__ pairs,
+            double* __restrict__ pooled /* [P][256] */) {
+  __shared__ double s_red[8];
+  const PairDesc p = pairs[blockIdx.y];
+  const int cell = blockIdx.x, i = cell >> 4, j = cell & 15;
+  // pool_mtx: whole-block 16x16 unless a 'used' anchor lies strictly inside on both axes
+  const bool split = p.cen1 > 0 && p.cen1 < p.n1 - 1 && p.cen2 > 0 && p.cen2 < p.n2 - 1;
+  int r_lo, r_hi, c_lo, c_hi;
+  if (!split) {
+    pool_range(i, p.n1, 16, r_lo, r_hi);
+    pool_range(j, p.n2, 16, c_lo, c_hi);
+  } else {
+    const int qi = i >> 3, ii = i & 7, qj = j >> 3, jj = j & 7;
+    const int rb = qi ? p.cen1 : 0, rl = qi ? p.n1 - p.cen1 : p.cen1;
+    const int cb = qj ? p.cen2 : 0, cl = qj ? p.n2 - p.cen2 : p.cen2;
+    pool_range(ii, rl, 8, r_lo, r_hi); r_lo += rb; r_hi += rb;
+    pool_range(jj, cl, 8, c_lo, c_hi); c_lo += cb; c_hi += cb;
+  }
+  const int w = c_hi - c_lo, hgt = r_hi - r_lo;
+  double acc = 0.0;
+  for (long long idx = threadIdx.x; idx < (long long)w * hgt; idx += blockDim.x) {
+    const int rr = (int)(idx / w), cc = (int)(idx % w);
+    acc += (double)x[(long long)(p.r0 + r_lo + rr) * ld + p.c0 + c_lo + cc];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double q = 0; for (int k = 0; k < 8; ++k) q += s_red[k];
+    pooled[(long long)blockIdx.y * 256 + cell] = q / ((double)w * (double)hgt);
+  }
+}
+
+// norm_mtx (population std) -> symmetry -> template scores; one CTA (256 threads) per pair.
+__global__ void __launch_bounds__(256)
+gf_finish_kernel(const double* __restrict__ pooled, const PairDesc* __restrict__ pairs,
+                 const double* __restrict__ tmpl_intra, const double* __restrict__ tmpl_inter,
+                 double* __restrict__ isym /* [P][256] */, double* __restrict__ xs /* [P][256] */,
+                 double* __restrict__ scores /* [P][5] */) {
+  __shared__ double s_img[256];
+  __shared__ double s_sym[256];
+  __shared__ double s_red[8];
+  __shared__ double s_stat[2];
+  const int pidx = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const PairDesc p = pairs[pidx];
+  const double v = pooled[(long long)pidx * 256 + t];
+  double q = warp_sum(v);
+  if (lane == 0) s_red[w] = q;
+  __syncthreads();
+  if (t == 0) { double a = 0; for (int k = 0; k < 8; ++k) a += s_red[k]; s_stat[0] = a / 256.0; }
+  __syncthreads();
+  const double mean = s_stat[0];
+  const double d = v - mean;
+  q = warp_sum(d * d);
+  __syncthreads();
+  if (lane == 0) s_red[w] = q;
+  __syncthreads();
+  if (t == 0) { double a = 0; for (int k = 0; k < 8; ++k) a += s_red[k]; s_stat[1] = sqrt(a / 256.0); }
+  __syncthreads();
+  const double sd = s_stat[1];
+  const double z = sd > 0.0 ? d / sd : d;
+  s_img[t] = z;
+  isym[(long long)pidx * 256 + t] = z;
+  __syncthreads();
+  const int i = t >> 4, j = t & 15;
+  double sym;
+  if (p.intra) {
+    sym = (z + s_img[(15 - i) * 16 + (15 - j)]) / 2.0;
+  } else {
+    sym = z;                                             // x + flipud + fliplr + flipud(fliplr), / 4
+    sym += s_img[(15 - i) * 16 + j];
+    sym += s_img[i * 16 + (15 - j)];
+    sym += s_img[(15 - i) * 16 + (15 - j)];
+    sym /= 4.0;
+  }
+  s_sym[t] = sym;
+  xs[(long long)pidx * 256 + t] = sym;
+  __syncthreads();
+  const double* tm = p.intra ? tmpl_intra : tmpl_inter;
+  for (int k = 0; k < 5; ++k) {
+    double a = warp_sum(sym * tm[k * 256 + t]);
+    double b = p.intra ? 0.0 : warp_sum(s_sym[j * 16 + i] * tm[k * 256 + t]);   // transposed image
+    __syncthreads();
+    if (lane == 0) { s_red[w] = a; }
+    __syncthreads();
+    double sa = 0;
+    if (t == 0) for (int kk = 0; kk < 8; ++kk) sa += s_red[kk];
+    __syncthreads();
+    if (lane == 0) { s_red[w] = b; }
+    __syncthreads();
+    if (t == 0) {
+      double sb = 0; for (int kk = 0; kk < 8; ++kk) sb += s_red[kk];
+      scores[(long long)pidx * 5 + k] = (!p.intra && sa < sb) ? sb : sa;       // max with transposed
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+}  // namespace hia
+
+HIA_API int hia_row_profiles(const float* x, int32_t n, int64_t ld, const int32_t* chr_start,
+                             const int16_t* bin_chr, const double* threshold, int reverse, int norm,
+                             double* inter_profile, double* intra_profile, double* workspace,
+                             void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (!x || !chr_start || !bin_chr || !threshold || !inter_profile || !intra_profile || !workspace ||
+      n <= 0 || ld < n)
+    return HIA_ERR_BAD_ARG;
+  if (!aligned16(x) || (ld & 3)) return HIA_ERR_ALIGN;
+  double* inter_sum = workspace;             // [n]
+  double* intra_sum = workspace + n;         // [n]
+  double* pos_stats = workspace + 2 * (int64_t)n;   // [2]
+  HIA_CUDA(cudaMemsetAsync(pos_stats, 0, 2 * sizeof(double), s));
+  row_profile_kernel<<<n, 256, 0, s>>>(x, n, ld, chr_start, bin_chr, threshold, reverse, inter_sum,
+                                       intra_sum, pos_stats);
+  HIA_LAUNCH_CHECK();
+  profile_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(inter_sum, intra_sum, pos_stats, n, chr_start,
+                                                        bin_chr, norm, inter_profile, intra_profile);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
+HIA_API int hia_smooth1d_reflect(const double* in, double* out, int32_t n, const int32_t* chr_start,
+                                 const int16_t* bin_chr, double kernal_per, int32_t min_kernal_len,
+                                 void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (!in || !out || in == out || !chr_start || !bin_chr || n <= 0) return HIA_ERR_BAD_ARG;
+  smooth1d_kernel<<<(n + 255) / 256, 256, 0, s>>>(in, out, n, chr_start, bin_chr, kernal_per, min_kernal_len);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
+HIA_API int hia_gf_pool_scores(const float* x, int64_t ld, const int32_t* pairs8, int32_t n_pairs,
+                               const double* tmpl_intra, const double* tmpl_inter, double* pooled,
+                               double* isym, double* xs, double* scores, void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (!x || !pairs8 || !tmpl_intra || !tmpl_inter || !pooled || !isym || !xs || !scores || n_pairs <= 0)
+    return HIA_ERR_BAD_ARG;
+  const PairDesc* pairs = reinterpret_cast<const PairDesc*>(pairs8);
+  pool_kernel<<<dim3(256, n_pairs), 256, 0, s>>>(x, ld, pairs, pooled);
+  HIA_LAUNCH_CHECK();
+  gf_finish_kernel<<<n_pairs, 256, 0, s>>>(pooled, pairs, tmpl_intra, tmpl_inter, isym, xs, scores);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}

@@ -222,3 +222,255 @@ def topk_eig(c, k=3, block=8, steps=None, tol=1e-6, max_restarts=8, seed=0, retu
         init, n_init = eigvecs.clone(), k
     out = (eigvals, eigvecs.t())
     return out + (info,) if return_info else out
+
+
+# ------------------------------------------------------------------------------- a6 selection
+PCT_ALL, PCT_POS, PCT_NEG = 0, 1, 2
+
+
+def percentiles(x, qs, modes=None):
+    """np.percentile(x[, subset], q) for up to 4 (q, mode) pairs -> fp64 device tensor [nq].
+    q in percent like numpy; the quantile q/100 is formed on the host in fp64 exactly like
+    numpy does (true_divide(q, 100))."""
+    lib = _lib.load()
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    qs = list(qs)
+    modes = [PCT_ALL] * len(qs) if modes is None else list(modes)
+    quant = np.true_divide(np.asarray(qs, dtype=np.float64), 100)
+    d_quant = torch.from_numpy(quant).to(x.device)
+    d_modes = torch.tensor(modes, dtype=torch.int32, device=x.device)
+    out = torch.empty(len(qs), dtype=torch.float64, device=x.device)
+    ws = torch.empty(lib.hia_percentiles_workspace_bytes(), dtype=torch.uint8, device=x.device)
+    st = lib.hia_percentiles(_ptr(x), x.shape[0], x.shape[1], x.stride(0), _ptr(d_modes), _ptr(d_quant),
+                             len(qs), _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _lib.check(st, "hia_percentiles")
+    return out
+
+
+def _like(x, out):
+    if out is None:
+        out = alloc_map(x.shape[0], x.device, cols=x.shape[1])
+    assert out.stride(0) == x.stride(0) and out.shape == x.shape
+    return out
+
+
+def clip(x, lo=None, hi=None, out=None):
+    """x clipped to [lo, hi]; lo / hi are 1-element fp64 device tensors (or None)."""
+    lib = _lib.load()
+    _need_cuda(x)
+    out = _like(x, out)
+    st = lib.hia_clip(_ptr(x), _ptr(out), x.shape[0], x.shape[1], x.stride(0), _ptr(lo), _ptr(hi), _stream())
+    _lib.check(st, "hia_clip")
+    return out
+
+
+def tid_off_outliers(x, vmax_per=98, out=None):
+    """publish/oe_map/S3_denoise.py:85-92."""
+    p = percentiles(x, [vmax_per, 100 - vmax_per])
+    return clip(x, lo=p[1:2], hi=p[0:1], out=out)
+
+
+def norm_to_zero_mean(x, mid_vmax_per=66, out=None):
+    """publish/oe_map/S4_norm_value.py:10-27."""
+    lib = _lib.load()
+    _need_cuda(x)
+    out = _like(x, out)
+    p = percentiles(x, [mid_vmax_per, 100 - mid_vmax_per])         # vmax, vmin
+    ms = torch.empty(2, dtype=torch.float64, device=x.device)
+    ws6 = torch.empty(6, dtype=torch.float64, device=x.device)
+    st = lib.hia_core_moments(_ptr(x), x.shape[0], x.shape[1], x.stride(0), _ptr(p[1:2]), _ptr(p[0:1]),
+                              _ptr(ms), _ptr(ws6), _stream())
+    _lib.check(st, "hia_core_moments")
+    st = lib.hia_zscore(_ptr(x), _ptr(out), x.shape[0], x.shape[1], x.stride(0), _ptr(ms), _stream())
+    _lib.check(st, "hia_zscore")
+    return out
+
+
+def remove_outliers(x, default_vmax_per=98, out=None):
+    """publish/oe_map/S4_norm_value.py:30-40."""
+    lib = _lib.load()
+    p = percentiles(x, [default_vmax_per, 100 - default_vmax_per], [PCT_POS, PCT_NEG])
+    b = torch.empty(2, dtype=torch.float64, device=x.device)
+    _lib.check(lib.hia_sym_clip_bounds(_ptr(p), _ptr(b), _stream()), "hia_sym_clip_bounds")
+    return clip(x, lo=b[0:1], hi=b[1:2], out=out)
+
+
+def norm_de_mtx(x, out=None):
+    """publish/oe_map/S4_norm_value.py:43-46."""
+    z = norm_to_zero_mean(x, out=out)
+    return remove_outliers(z, out=z)
+
+
+# ------------------------------------------------------------------------------- a10 checkerboard
+MIN_CHRO_LEN = 50            # publish/complex/src/main_local.py:16
+MIN_N_SHORT_SIMS = 200       # publish/complex/src/main_local.py:17
+_edges_cache = {}
+
+
+def _hist_edges(device):
+    key = str(device)
+    if key not in _edges_cache:
+        _edges_cache[key] = torch.from_numpy(np.linspace(0, 1.6, 30)).to(device)   # S2_get_entro.py:61
+    return _edges_cache[key]
+
+
+def band_entropy(adj, d_lo, d_hi, per=2):
+    """The diagonal/entropy loop of get_local on a symmetric distance matrix.
+    Returns a 2-element fp64 device tensor [score or NaN, number of entropy chunks]."""
+    lib = _lib.load()
+    _need_cuda(adj)
+    n = adj.shape[0]
+    out = torch.empty(2, dtype=torch.float64, device=adj.device)
+    nd = max(0, d_hi - d_lo)
+    ws = torch.empty(lib.hia_band_entropy_workspace_bytes(nd), dtype=torch.uint8, device=adj.device)
+    st = lib.hia_band_entropy(_ptr(adj), n, adj.stride(0), d_lo, d_hi, _ptr(_hist_edges(adj.device)),
+                              MIN_N_SHORT_SIMS, float(per), _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _lib.check(st, "hia_band_entropy")
+    return out
+
+
+def get_local(block, L=None, short_dis_max_per=.15, precision=PREC_3XTF32):
+    """Checkerboard score of one dense block (rows x cols view of a min-filled symmetric map).
+    publish/complex/src/main_local.py:19-55. L = mean chromosome length of the block's row
+    window (S2_get_entro.py:6-10); defaults to the number of rows. Returns float or None."""
+    if min(block.shape) < MIN_CHRO_LEN:
+        return None
+    L = block.shape[0] if L is None else L
+    smax = int(L * short_dis_max_per)
+    smin = int(L * .05)
+    if smax <= smin:
+        return None
+    if block.stride(1) != 1 or block.stride(0) % 4 or block.data_ptr() % 16:
+        tmp = alloc_map(block.shape[0], block.device, cols=block.shape[1])
+        tmp.copy_(block)
+        block = tmp
+    n = block.shape[0]
+    # only the tiles of the distance matrix that touch the band are computed
+    adj = similarity(block, flavour=SIM_COSINE_DISTANCE, precision=precision,
+                     band=(smin, min(smax - 1, n - 1)) if precision == PREC_3XTF32 else None,
+                     out=alloc_map(n, block.device))
+    res = band_entropy(adj, smin, smax).cpu().numpy()
+    return None if res[1] == 0 else float(res[0])
+
+
+def main_local(dense, layout, chros, short_dis_max_per=.15):
+    """publish/complex/src/main_local.py:108-141 on a dense (per-block min-filled) 'all' map:
+    intra + upper inter blocks, then the transposed inter block (skipped when the first
+    orientation gave None; its L stays the first chromosome's length).
+    Returns [(accord_chro, other_chro, accord)]."""
+    out = []
+    for a, (s1, e1) in enumerate(layout.seps):
+        for b, (s2, e2) in enumerate(layout.seps):
+            if s1 > s2:
+                continue
+            blk = dense[s1:e1 + 1, s2:e2 + 1]
+            L = e1 - s1 + 1
+            acc = get_local(blk, L, short_dis_max_per)
+            if acc is None:
+                continue
+            out.append((chros[a], chros[b], acc))
+            if a != b:
+                acc = get_local(blk.t(), L, short_dis_max_per)
+                if acc is None:
+                    continue
+                out.append((chros[b], chros[a], acc))
+    return out
+
+
+# ------------------------------------------------------------------------------- a11 GF_S1 profiles
+def row_profiles(x, layout, threshold, reverse=False, norm=True):
+    """(inter_profile, intra_profile) fp64 [N]: keep_high_cons fused with get_inter_rowsum /
+    get_intra_rowsum. `threshold`: 1-element fp64 device tensor (the 66.7 / 33.3 percentile)."""
+    lib = _lib.load()
+    _need_cuda(x)
+    n = layout.n
+    inter = torch.empty(n, dtype=torch.float64, device=x.device)
+    intra = torch.empty(n, dtype=torch.float64, device=x.device)
+    ws = torch.empty(2 * n + 2, dtype=torch.float64, device=x.device)
+    st = lib.hia_row_profiles(_ptr(x), n, x.stride(0), _ptr(layout.chr_start), _ptr(layout.bin_chr),
+                              _ptr(threshold), 1 if reverse else 0, 1 if norm else 0, _ptr(inter),
+                              _ptr(intra), _ptr(ws), _stream())
+    _lib.check(st, "hia_row_profiles")
+    return inter, intra
+
+
+def smooth_rowsum(profile, layout, kernal_per=.1, min_kernal_len=5):
+    """smooth_rowsum (S2_1_find_by_inter_rowsum.py:42-55)."""
+    lib = _lib.load()
+    out = torch.empty_like(profile)
+    st = lib.hia_smooth1d_reflect(_ptr(profile), _ptr(out), layout.n, _ptr(layout.chr_start),
+                                  _ptr(layout.bin_chr), float(kernal_per), int(min_kernal_len), _stream())
+    _lib.check(st, "hia_smooth1d_reflect")
+    return out
+
+
+def inter_rowsum_profile(x, layout, per=100 / 3):
+    """keep_high_cons -> get_inter_rowsum -> smooth_rowsum (main_find_anchors_by_inter_rowsum,
+    S2_1:374-396). Returns (raw, smoothed) fp64 device tensors."""
+    t = percentiles(x, [100 - per])
+    inter, _ = row_profiles(x, layout, t[0:1], reverse=False)
+    return inter, smooth_rowsum(inter, layout)
+
+
+def intra_low_profile(x, layout, per=100 / 3):
+    """keep_high_cons(reverse) -> get_intra_rowsum -> smooth_rowsum (S2_3:32-56)."""
+    t = percentiles(x, [per])
+    _, intra = row_profiles(x, layout, t[0:1], reverse=True)
+    return intra, smooth_rowsum(intra, layout)
+
+
+# ------------------------------------------------------------------------------- a14/a15 GF_S2
+_tmpl_cache = {}
+
+
+def _templates(device):
+    """The shipped template maps (publish/confor/{intra,inter}_ave_maps.mat, keys sorted
+    numerically), L1-normalised in float32 exactly like get_n_norm_ave_maps
+    (to_confor.py:12-25), promoted to fp64."""
+    import os
+    key = str(device)
+    if key not in _tmpl_cache:
+        data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "ave_maps.npz"))
+        out = []
+        for tag in ("intra", "inter"):
+            t = data[tag]                                            # float32 [5, 256]
+            norm = np.vstack([row / np.sum(np.abs(row)) for row in t])
+            out.append(torch.from_numpy(norm.astype(np.float64)).to(device))
+        _tmpl_cache[key] = out
+    return _tmpl_cache[key]
+
+
+INTRA_AVE_NAMES = ['End-whole', 'Large-center', 'Center', 'Center-end-axis', 'Center-whole']
+INTER_AVE_NAMES = ['Center-center', 'Center-end-axis', 'Center-whole', 'End-whole', 'End-end']
+
+
+def gf_scores(dense, layout, centers=None):
+    """GF_S2 on a dense zero-filled 'all' map: every ordered chromosome pair -> pooled 16x16
+    image -> z-score -> symmetrise -> 5 template scores. `centers[c]` = chromosome-relative
+    index of the 'used' anchor or None. Returns dict of host arrays:
+    pairs [(a, b)], xs / isym [P, 256], scores [P, 5] (fp64)."""
+    lib = _lib.load()
+    _need_cuda(dense)
+    C = layout.n_chr
+    centers = [None] * C if centers is None else centers
+    desc, pairs = [], []
+    for a, (s1, e1) in enumerate(layout.seps):
+        for b, (s2, e2) in enumerate(layout.seps):
+            c1 = -1 if centers[a] is None else int(centers[a])
+            c2 = -1 if centers[b] is None else int(centers[b])
+            desc.append([s1, e1 - s1 + 1, s2, e2 - s2 + 1, c1, c2, 1 if a == b else 0, 0])
+            pairs.append((a, b))
+    P = len(desc)
+    d_desc = torch.tensor(desc, dtype=torch.int32, device=dense.device)
+    t_intra, t_inter = _templates(dense.device)
+    pooled = torch.empty((P, 256), dtype=torch.float64, device=dense.device)
+    isym = torch.empty_like(pooled)
+    xs = torch.empty_like(pooled)
+    scores = torch.empty((P, 5), dtype=torch.float64, device=dense.device)
+    st = lib.hia_gf_pool_scores(_ptr(dense), dense.stride(0), _ptr(d_desc), P, _ptr(t_intra),
+                                _ptr(t_inter), _ptr(pooled), _ptr(isym), _ptr(xs), _ptr(scores),
+                                _stream())
+    _lib.check(st, "hia_gf_pool_scores")
+    return {"pairs": pairs, "pooled": pooled.cpu().numpy(), "isym": isym.cpu().numpy(),
+            "xs": xs.cpu().numpy(), "scores": scores.cpu().numpy()}

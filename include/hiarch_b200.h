@@ -132,6 +132,81 @@ int hia_similarity_gemm(int32_t m, int32_t k, float* out, int64_t ld_out, int fl
                         int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
+/* a6  whole-matrix percentiles (numpy 'linear'), clip, core mean/std, z-score           */
+/* replaces tid_off_outliers (oe_map/S3_denoise.py:85-92), norm_to_zero_mean /            */
+/*          remove_outliers / norm_de_mtx (oe_map/S4_norm_value.py:10-46), the percentile */
+/*          of keep_high_cons (confor/.../U2_keep_top_cons.py:20-41)                      */
+/* ------------------------------------------------------------------------------------ */
+#define HIA_PCT_ALL 0   /* np.percentile(a, q)          */
+#define HIA_PCT_POS 1   /* np.percentile(a[a > 0], q)   */
+#define HIA_PCT_NEG 2   /* np.percentile(a[a < 0], q)   */
+/* Up to 4 percentiles of a rows x cols fp32 matrix in one call (3 streaming passes, exact
+ * order statistics by radix select, numpy _lerp interpolation). modes[nq] (int32) and
+ * quantiles[nq] (fp64, = q/100 computed by the caller) are DEVICE arrays; out[nq] fp64 on the
+ * device (NaN for an empty subset). */
+int64_t hia_percentiles_workspace_bytes(void);
+int hia_percentiles(const float* x, int32_t rows, int32_t cols, int64_t ld, const int32_t* modes,
+                    const double* quantiles, int32_t nq, double* out, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+/* out = x with x > *hi -> *hi, x < *lo -> *lo (either bound may be NULL). lo/hi device fp64. */
+int hia_clip(const float* x, float* out, int32_t rows, int32_t cols, int64_t ld, const double* lo,
+             const double* hi, void* stream);
+/* mean_std[2] (device fp64) = mean and population std of the values strictly inside
+ * (*vmin, *vmax) -- or of all values when vmin >= vmax or the core is empty
+ * (S4_norm_value.py:14-22). workspace6: 6 doubles. */
+int hia_core_moments(const float* x, int32_t rows, int32_t cols, int64_t ld, const double* vmin,
+                     const double* vmax, double* mean_std, double* workspace6, void* stream);
+/* out = (x - mean_std[0]) / mean_std[1] */
+int hia_zscore(const float* x, float* out, int32_t rows, int32_t cols, int64_t ld,
+               const double* mean_std, void* stream);
+/* bounds2 = (-v, v), v = min(pcts2[0], -pcts2[1])   (remove_outliers, S4_norm_value.py:34-37) */
+int hia_sym_clip_bounds(const double* pcts2, double* bounds2, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* a10  checkerboard strength: the diagonal / entropy loop of get_local                   */
+/* replaces get_short_sims / get_accordance (complex/src/S2_get_entro.py:40-65) and the   */
+/*          loop of get_local (complex/src/main_local.py:30-55)                           */
+/* ------------------------------------------------------------------------------------ */
+/* adj: symmetric n x n distance matrix (only the diagonals d_lo <= d < d_hi are read).
+ * edges30: the 30 histogram edges (device fp64; np.linspace(0, 1.6, 30)). per = 2 (percent).
+ * out2 (device fp64): [mean entropy or NaN, number of entropy chunks]. */
+int64_t hia_band_entropy_workspace_bytes(int32_t n_diag);
+int hia_band_entropy(const float* adj, int32_t n, int64_t ld, int32_t d_lo, int32_t d_hi,
+                     const double* edges30, int32_t min_count, double per, double* out2,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* a11  GF_S1 row profiles: keep_high_cons fused with get_inter_rowsum / get_intra_rowsum */
+/* (confor/.../U2_keep_top_cons.py:20-41, S2_1_find_by_inter_rowsum.py:26-37,             */
+/*  S2_3_find_by_intra_low.py:18-27) and smooth_rowsum (S2_1:42-55)                       */
+/* ------------------------------------------------------------------------------------ */
+/* f(x) = max(x - *threshold, 0)  (reverse: max(*threshold - x, 0)); profiles[N] fp64:
+ *   inter[i] = sum_{j not in chr(i)} f / (#such j) / mean(f > 0)   (0 for a single chromosome)
+ *   intra[i] = sum_{j in chr(i)} f / len(chr(i)) / mean(f > 0)     (norm = 0 skips the mean)
+ * workspace: (2 N + 2) doubles. */
+int hia_row_profiles(const float* x, int32_t n, int64_t ld, const int32_t* chr_start,
+                     const int16_t* bin_chr, const double* threshold, int reverse, int norm,
+                     double* inter_profile, double* intra_profile, double* workspace, void* stream);
+/* per-chromosome box smoothing, odd length max(min_kernal_len, int(len * kernal_per)) | 1,
+ * scipy 'reflect' boundary. in != out. */
+int hia_smooth1d_reflect(const double* in, double* out, int32_t n, const int32_t* chr_start,
+                         const int16_t* bin_chr, double kernal_per, int32_t min_kernal_len,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* a14/a15  GF_S2: adaptive pool 16x16 (4 quadrants of 8x8 around a 'used' anchor),        */
+/* z-score, flip-symmetrise, 5 template scores (inter: max with the transposed image)      */
+/* replaces pool_mtx / norm_mtx / symmetry (confor/src/S2_to_train_mtx/preprocess.py:8-48) */
+/*          and to_confor (confor/src/S5_sim_to_pat/to_confor.py:35-47)                    */
+/* ------------------------------------------------------------------------------------ */
+/* pairs8[P][8] int32 (device): {row0, n_rows, col0, n_cols, cen1 (-1 = none), cen2, intra, 0}.
+ * tmpl_*: 5 x 256 fp64, already L1-normalised. Outputs (device fp64): pooled/isym/xs [P][256],
+ * scores [P][5]. */
+int hia_gf_pool_scores(const float* x, int64_t ld, const int32_t* pairs8, int32_t n_pairs,
+                       const double* tmpl_intra, const double* tmpl_inter, double* pooled,
+                       double* isym, double* xs, double* scores, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
 /* a9  top-k eigenvectors of a dense symmetric fp32 matrix (largest algebraic).          */
 /* No reference implementation exists (the reference never decomposes anything); the     */
 /* north-star asks for compartment eigenvectors: oracle = numpy.linalg.eigh.             */

@@ -262,3 +262,140 @@ def test_topk_eig_small_and_k1():
     a = rng.standard_normal((64, 20))
     _check_eig(a @ a.T + np.diag(np.linspace(0, 30, 64)), k=1)
     _check_eig(a @ a.T + np.diag(np.linspace(0, 30, 64)), k=3)
+
+
+# --------------------------------------------------------------------------------- a6 selection
+def _mapdev(a):
+    from hiarch_b200 import ops
+    d = ops.alloc_map(a.shape[0], cols=a.shape[1])
+    d.copy_(_dev(a, torch.float32))
+    return d
+
+
+def test_percentiles_exact_numpy_semantics():
+    from hiarch_b200 import ops
+    rng = np.random.default_rng(9)
+    cases = [rng.standard_normal((301, 257)), np.round(rng.standard_normal((64, 1000)), 1),
+             rng.integers(-3, 4, (129, 130)).astype(np.float64), np.abs(rng.standard_normal((50, 51))),
+             np.full((40, 44), 2.5)]
+    for a in cases:
+        a32 = a.astype(np.float32)
+        d = _mapdev(a32)
+        a64 = a32.astype(np.float64)
+        got = ops.percentiles(d, [2, 98, 66, 100 / 3]).cpu().numpy()
+        ref = np.array([np.percentile(a64, q) for q in (2, 98, 66, 100 / 3)])
+        assert np.array_equal(got, ref), (got, ref)
+        got = ops.percentiles(d, [98, 2, 0, 100], [ops.PCT_POS, ops.PCT_NEG, ops.PCT_ALL, ops.PCT_ALL]).cpu().numpy()
+        pos, neg = a64[a64 > 0], a64[a64 < 0]
+        ref = [np.percentile(pos, 98) if pos.size else np.nan, np.percentile(neg, 2) if neg.size else np.nan,
+               a64.min(), a64.max()]
+        assert np.array_equal(got, np.array(ref), equal_nan=True), (got, ref)
+
+
+def test_clip_zscore_chain_against_golden(golden):
+    from hiarch_b200 import ops
+    g = golden("g3chr")
+    d = _mapdev(g["oe_log"])
+    x64 = d.cpu().numpy().astype(np.float64)                       # what the GPU starts from
+    t = ops.tid_off_outliers(d)
+    assert np.abs(t.cpu().numpy() - O.tid_off_outliers(x64)).max() <= 1e-6
+    assert np.abs(t.cpu().numpy() - g["tid_off"]).max() <= ATOL
+    z = ops.norm_to_zero_mean(t)
+    assert np.abs(z.cpu().numpy() - g["zscore"]).max() <= ATOL
+    nd = ops.norm_de_mtx(t)
+    assert np.abs(nd.cpu().numpy() - g["norm_de"]).max() <= ATOL
+    # in place
+    w = _mapdev(g["oe_log"])
+    ops.tid_off_outliers(w, out=w)
+    assert torch.equal(w, t)
+
+
+def test_norm_to_zero_mean_degenerate_core():
+    """vmin >= vmax (constant matrix region) -> falls back to all values."""
+    from hiarch_b200 import ops
+    a = np.zeros((60, 64))
+    a[:3] = 5.0                                                    # p34 == p66 == 0
+    got = ops.norm_to_zero_mean(_mapdev(a)).cpu().numpy()
+    assert np.abs(got - O.norm_to_zero_mean(a)).max() <= ATOL
+
+
+# --------------------------------------------------------------------------------- a10 checkerboard
+@pytest.mark.parametrize("case", ["g3chr", "g1chr"])
+def test_checkerboard_table_against_reference(golden, case):
+    """.mtx (%.2f) -> per-block min fill -> cosine distance band -> entropy, vs main_local."""
+    from hiarch_b200 import ops
+    g = golden(case)
+    n = int(g["in.lens"].sum())
+    seps = _seps(g)
+    names = [str(x) for x in g["in.names"]]
+    layout = ops.GenomeLayout(seps)
+    r, c, v = _coo(g, "de_file")
+    dense = ops.scatter_coo_sym(r, c, v, n, fill_mode=ops.FILL_BLOCK_MIN, layout=layout)
+    table = ops.main_local(dense, layout, names)
+    assert [t[0] for t in table] == list(g["checker.accord_chro"])
+    assert [t[1] for t in table] == list(g["checker.other_chro"])
+    got = np.array([t[2] for t in table])
+    assert np.all(np.abs(got - g["checker.accord"]) <= 1e-4 * np.abs(g["checker.accord"])), \
+        (got, g["checker.accord"])                          # north-star: 1e-4 relative
+
+
+def test_band_entropy_against_oracle_on_exact_adj():
+    """Same fp32 distance matrix on both sides: the reduction itself must match to 1e-12."""
+    from hiarch_b200 import ops
+    rng = np.random.default_rng(21)
+    for n, L in ((180, 180), (60, 60), (400, 333)):
+        x = rng.standard_normal((n, 90)) + rng.standard_normal(90)
+        adj = O.cosine_distance(x).astype(np.float32)
+        d = _mapdev(adj)
+        smin, smax = int(L * .05), int(L * .15)
+        res = ops.band_entropy(d, smin, smax).cpu().numpy()
+        ref = O.checkerboard_from_adj(adj.astype(np.float64), L)
+        if ref is None:
+            assert res[1] == 0
+        else:
+            assert abs(res[0] - ref) <= 1e-12 * abs(ref), (res, ref)
+    assert ops.get_local(_mapdev(rng.standard_normal((40, 200)))) is None      # < 50 rows
+
+
+# --------------------------------------------------------------------------------- a11 GF_S1 profiles
+@pytest.mark.parametrize("case", ["g3chr", "g1chr"])
+def test_gf_s1_profiles(golden, case):
+    from hiarch_b200 import ops
+    g = golden(case)
+    seps = _seps(g)
+    layout = ops.GenomeLayout(seps)
+    d = _mapdev(g["filt"])
+    raw, sm = ops.inter_rowsum_profile(d, layout)
+    assert np.abs(raw.cpu().numpy() - g["inter_rowsum"]).max() <= 1e-6
+    assert np.abs(sm.cpu().numpy() - g["inter_rowsum_smooth"]).max() <= 1e-6
+    if "intra_rowsum" in g:
+        raw, sm = ops.intra_low_profile(d, layout)
+        assert np.abs(raw.cpu().numpy() - g["intra_rowsum"]).max() <= 1e-6
+        assert np.abs(sm.cpu().numpy() - g["intra_rowsum_smooth"]).max() <= 1e-6
+
+
+# --------------------------------------------------------------------------------- a14/a15 GF_S2
+def test_gf_s2_images_and_scores(golden):
+    from hiarch_b200 import ops
+    g = golden("g3chr")
+    n = int(g["in.lens"].sum())
+    seps = _seps(g)
+    names = [str(x) for x in g["in.names"]]
+    layout = ops.GenomeLayout(seps)
+    r, c, v = _coo(g, "filt_file")
+    dense = ops.scatter_coo_sym(r, c, v, n)                 # scipy .todense(): absent = 0
+    for method in ("inter_rowsum", "no_anchor"):
+        used = {}
+        for ch, ty, cen in zip(g[f"anchors.{method}.chr"], g[f"anchors.{method}.type"], g[f"anchors.{method}.cen"]):
+            if ty == "used" and str(ch) not in used:
+                used[str(ch)] = int(cen) - seps[names.index(str(ch))][0]
+        res = ops.gf_scores(dense, layout, [used.get(nm) for nm in names])
+        intra = [i for i, (a, b) in enumerate(res["pairs"]) if a == b]
+        inter = [i for i, (a, b) in enumerate(res["pairs"]) if a != b]
+        assert np.abs(res["xs"][intra] - g[f"gf.{method}.intra_xs"]).max() <= 1e-6
+        assert np.abs(res["xs"][inter] - g[f"gf.{method}.inter_xs"]).max() <= 1e-6
+        si = res["scores"][intra].T.reshape(-1)             # golden is melted column-major
+        so = res["scores"][inter].T.reshape(-1)
+        ri, ro = g[f"gf.{method}.intra_score"], g[f"gf.{method}.inter_score"]
+        assert np.all(np.abs(si - ri) <= 1e-4 * np.abs(ri) + 1e-9)      # north-star: 1e-4 relative
+        assert np.all(np.abs(so - ro) <= 1e-4 * np.abs(ro) + 1e-9)

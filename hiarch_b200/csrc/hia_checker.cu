@@ -64,7 +64,7 @@ __device__ unsigned int block_select(const float* s_vals, int cnt, unsigned int 
 
 __device__ __forceinline__ double np_lerp(double a, double b, double t) {
   const double d = b - a;
-  return (t >= 0.5) ? (b - d * (1.0 - t)) : (a + d * t);
+  return (t >= 0.5) ? __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, t))) : __dadd_rn(a, __dmul_rn(d, t));   // no FMA
 }
 
 __global__ void __launch_bounds__(kBandThreads)

@@ -1,0 +1,270 @@
+// GF_S1 used_filter (publish/confor/src/S1_preprocess/S1_1_filtering.py:13-16) as ONE op on a
+// block: box filter (size x size, reflect) followed by norm_to_zero_mean
+// (publish/oe_map/S4_norm_value.py:10-27), computed internally in fp64 with scipy's exact
+// operation order.
+//
+// Why a bit-replica: Hi-C values are discrete (count levels, or %.2f-quantised files), so the
+// box-filtered values are massively TIED around the p34 / p66 percentiles that select the
+// "core" of norm_to_zero_mean; which tied cells pass the strict `vmin < x < vmax` test is decided
+// by the last-bit rounding of scipy's running sums (NI_UniformFilter1D: tmp = sum of the first
+// window in order; tmp += new - old; out = tmp / size; axis 0 then axis 1, fp64 intermediate).
+// Any other summation order flips those cells and moves the block's mean/std by ~1e-2. So this
+// path reproduces that order exactly (verified bit-for-bit against scipy in
+// tests/test_host_tables.py::test_uniform_filter_replica), selects the percentiles exactly on
+// 64-bit order-preserving keys, and only rounds to fp32 at the very end.
+//
+// The fp32 input is promoted to the reference's fp64 values: when `decimals >= 0` every value is
+// re-quantised as nearbyint(x * 10^decimals) / 10^decimals in fp64, i.e. the double a "%.2f"
+// text field parses to (the pipeline hands maps over as %.2f text, new_hic_class.py:2298).
+#include "hia_common.cuh"
+
+namespace hia {
+namespace {
+
+__device__ __forceinline__ int reflect_idx64(int i, int n) {
+  if (n == 1) return 0;
+  const int p = 2 * n;
+  i %= p;
+  if (i < 0) i += p;
+  return i < n ? i : p - 1 - i;
+}
+
+__device__ __forceinline__ unsigned long long double_to_ordered(double d) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_to_double(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+__global__ void load_f64_kernel(const float* __restrict__ x, long long ld, int rows, int cols,
+                                double scale, double* __restrict__ a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  double v = (double)x[(long long)r * ld + c];
+  if (scale > 0.0) v = nearbyint(v * scale) / scale;     // the double the decimal text parses to
+  a[i] = v;
+}
+
+// uniform_filter1d along axis 0: thread per column, the whole column sequentially (scipy order)
+__global__ void box64_axis0_kernel(const double* __restrict__ in, double* __restrict__ out, int rows,
+                                   int cols, int size) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int s1 = size / 2;
+  double tmp = 0.0;
+  for (int ll = 0; ll < size; ++ll) tmp += in[(long long)reflect_idx64(ll - s1, rows) * cols + c];
+  const double fs = (double)size;
+  out[c] = tmp / fs;
+  for (int ll = 1; ll < rows; ++ll) {
+    const double nw = in[(long long)reflect_idx64(ll + size - 1 - s1, rows) * cols + c];
+    const double od = in[(long long)reflect_idx64(ll - 1 - s1, rows) * cols + c];
+    tmp += nw - od;
+    out[(long long)ll * cols + c] = tmp / fs;
+  }
+}
+
+// uniform_filter1d along axis 1: thread per row, the whole row sequentially
+__global__ void box64_axis1_kernel(const double* __restrict__ in, double* __restrict__ out, int rows,
+                                   int cols, int size) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const double* line = in + (long long)r * cols;
+  double* oline = out + (long long)r * cols;
+  const int s1 = size / 2;
+  double tmp = 0.0;
+  for (int ll = 0; ll < size; ++ll) tmp += line[reflect_idx64(ll - s1, cols)];
+  const double fs = (double)size;
+  oline[0] = tmp / fs;
+  for (int ll = 1; ll < cols; ++ll) {
+    const double nw = line[reflect_idx64(ll + size - 1 - s1, cols)];
+    const double od = line[reflect_idx64(ll - 1 - s1, cols)];
+    tmp += nw - od;
+    oline[ll] = tmp / fs;
+  }
+}
+
+// ---- exact order statistics on 64-bit keys: 8 passes of 8 bits, up to 4 ranks
+struct Sel64 {
+  unsigned long long hist[4][256];
+  unsigned long long prefix[4];
+  unsigned long long rank[4];
+  double gamma[2];
+  double pct[2];       // p_hi (66), p_lo (34)
+  double sums[6];
+  double mean_std[2];
+};
+
+__global__ void sel64_init_kernel(Sel64* st, long long n, double q_hi, double q_lo) {
+  const int t = threadIdx.x;
+  for (int i = t; i < 4 * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
+  if (t < 6) st->sums[t] = 0.0;
+  if (t == 0) {
+    const double qs[2] = {q_hi, q_lo};
+    for (int q = 0; q < 2; ++q) {
+      const double h = (double)(n - 1) * qs[q];            // numpy 'linear': (n - 1) * q/100
+      double lo = floor(h);
+      long long lo_i = (long long)lo;
+      if (lo_i < 0) lo_i = 0;
+      if (lo_i > n - 1) lo_i = n - 1;
+      const long long hi_i = (lo_i + 1 <= n - 1) ? lo_i + 1 : n - 1;
+      st->gamma[q] = h - lo;
+      st->rank[2 * q] = (unsigned long long)lo_i;
+      st->rank[2 * q + 1] = (unsigned long long)hi_i;
+    }
+    for (int r = 0; r < 4; ++r) st->prefix[r] = 0ull;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sel64_pass_kernel(const double* __restrict__ a, long long n, int pass, Sel64* st) {
+  __shared__ unsigned int s_hist[4][256];
+  __shared__ unsigned long long s_prefix[4];
+  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0u;
+  if (threadIdx.x < 4) s_prefix[threadIdx.x] = st->prefix[threadIdx.x];
+  __syncthreads();
+  const int shift = 56 - 8 * pass;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long key = double_to_ordered(a[i]);
+    const unsigned long long hi = (pass == 0) ? 0ull : (key >> (shift + 8));
+    const unsigned int dig = (unsigned int)((key >> shift) & 0xffull);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (hi == s_prefix[r]) atomicAdd(&s_hist[r][dig], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
+    const unsigned int v = (&s_hist[0][0])[i];
+    if (v) atomicAdd(&(&st->hist[0][0])[i], (unsigned long long)v);
+  }
+}
+
+__global__ void sel64_scan_kernel(Sel64* st) {
+  const int r = threadIdx.x;
+  if (r < 4) {
+    unsigned long long cum = 0, target = st->rank[r];
+    int bin = 255;
+    for (int i = 0; i < 256; ++i) {
+      const unsigned long long c = st->hist[r][i];
+      if (target < cum + c) { bin = i; break; }
+      cum += c;
+    }
+    st->rank[r] = target - cum;
+    st->prefix[r] = (st->prefix[r] << 8) | (unsigned long long)bin;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
+}
+
+__global__ void sel64_finish_kernel(Sel64* st) {
+  const int q = threadIdx.x;
+  if (q >= 2) return;
+  const double a = ordered_to_double(st->prefix[2 * q]);
+  const double b = ordered_to_double(st->prefix[2 * q + 1]);
+  const double t = st->gamma[q], d = b - a;
+  st->pct[q] = (t >= 0.5) ? __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, t))) : __dadd_rn(a, __dmul_rn(d, t));  // numpy _lerp, no FMA
+}
+
+__global__ void __launch_bounds__(256)
+moments64_kernel(const double* __restrict__ a, long long n, Sel64* st) {
+  __shared__ double s_red[8][6];
+  const double hi = st->pct[0], lo = st->pct[1];
+  const double c = 0.5 * (lo + hi);
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double v = a[i], d = v - c;
+    acc[3] += 1.0; acc[4] += d; acc[5] += d * d;
+    if (v < hi && v > lo) { acc[0] += 1.0; acc[1] += d; acc[2] += d * d; }
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { const double s = warp_sum(acc[k]); if (lane == 0) s_red[w][k] = s; }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double s = 0; for (int i = 0; i < 8; ++i) s += s_red[i][threadIdx.x];
+    atomicAdd(&st->sums[threadIdx.x], s);
+  }
+}
+
+__global__ void moments64_finish_kernel(Sel64* st) {
+  if (threadIdx.x != 0) return;
+  const double hi = st->pct[0], lo = st->pct[1], c = 0.5 * (lo + hi);
+  const bool use_core = (lo < hi) && (st->sums[0] > 0.0);            // S4_norm_value.py:16-22
+  const double cnt = use_core ? st->sums[0] : st->sums[3];
+  const double s1 = use_core ? st->sums[1] : st->sums[4];
+  const double s2 = use_core ? st->sums[2] : st->sums[5];
+  const double m = s1 / cnt;
+  double var = s2 / cnt - m * m;
+  if (var < 0) var = 0;
+  st->mean_std[0] = m + c;
+  st->mean_std[1] = sqrt(var);
+}
+
+__global__ void zscore64_kernel(const double* __restrict__ a, int rows, int cols, const Sel64* st,
+                                float* __restrict__ out, long long ld_out, int normalise) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  double v = a[i];
+  if (normalise) v = (v - st->mean_std[0]) / st->mean_std[1];
+  out[(long long)r * ld_out + c] = (float)v;
+}
+
+}  // namespace
+}  // namespace hia
+
+HIA_API int64_t hia_used_filter_f64_workspace_bytes(int32_t rows, int32_t cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  return 2 * (int64_t)rows * cols * 8 + (int64_t)sizeof(hia::Sel64) + 512;
+}
+
+HIA_API int hia_used_filter_f64(const float* x, int32_t rows, int32_t cols, int64_t ld_in, int32_t size,
+                                int32_t decimals, int normalise, double mid_vmax_per, float* out,
+                                int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (!x || !out || !workspace || rows <= 0 || cols <= 0 || ld_in < cols || ld_out < cols || size < 0)
+    return HIA_ERR_BAD_ARG;
+  if (workspace_bytes < hia_used_filter_f64_workspace_bytes(rows, cols)) return HIA_ERR_WORKSPACE;
+  unsigned char* ws = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  const long long n = (long long)rows * cols;
+  double* A = reinterpret_cast<double*>(ws);
+  double* B = A + n;
+  Sel64* st = reinterpret_cast<Sel64*>(B + n);
+  const int blocks = (int)((n + 255) / 256);
+  double scale = 0.0;
+  if (decimals >= 0) { scale = 1.0; for (int i = 0; i < decimals; ++i) scale *= 10.0; }
+  load_f64_kernel<<<blocks, 256, 0, s>>>(x, ld_in, rows, cols, scale, A);
+  HIA_LAUNCH_CHECK();
+  if (size > 1) {                                        // scipy: size 1 (and 0) leave the block as is
+    box64_axis0_kernel<<<(cols + 127) / 128, 128, 0, s>>>(A, B, rows, cols, size);
+    HIA_LAUNCH_CHECK();
+    box64_axis1_kernel<<<(rows + 127) / 128, 128, 0, s>>>(B, A, rows, cols, size);
+    HIA_LAUNCH_CHECK();
+  }
+  if (normalise) {
+    const double q_hi = mid_vmax_per / 100.0, q_lo = (100.0 - mid_vmax_per) / 100.0;
+    sel64_init_kernel<<<1, 256, 0, s>>>(st, n, q_hi, q_lo);
+    HIA_LAUNCH_CHECK();
+    const int grid = (int)std::min<long long>(blocks, (long long)kNumSMs * 8);
+    for (int pass = 0; pass < 8; ++pass) {
+      sel64_pass_kernel<<<grid, 256, 0, s>>>(A, n, pass, st);
+      HIA_LAUNCH_CHECK();
+      sel64_scan_kernel<<<1, 256, 0, s>>>(st);
+      HIA_LAUNCH_CHECK();
+    }
+    sel64_finish_kernel<<<1, 32, 0, s>>>(st);
+    HIA_LAUNCH_CHECK();
+    moments64_kernel<<<grid, 256, 0, s>>>(A, n, st);
+    HIA_LAUNCH_CHECK();
+    moments64_finish_kernel<<<1, 32, 0, s>>>(st);
+    HIA_LAUNCH_CHECK();
+  }
+  zscore64_kernel<<<blocks, 256, 0, s>>>(A, rows, cols, st, out, ld_out, normalise);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}

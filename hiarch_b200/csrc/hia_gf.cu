@@ -205,8 +205,76 @@ gf_finish_kernel(const double* __restrict__ pooled, const PairDesc* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------ a13 intra-x
+// get_intra_x (publish/confor/src/S1_preprocess/S1_2_find_anchors/S2_2_find_by_intra_x.py:25-50,
+// :116-126): for every candidate centre c the response sum(M * K_c) / sum(K_c), with
+//   K_c[y][x] = max(0, (k_len - dist((x, y), line through (0, n) and (c, c))) / k_len)
+// evaluated on the lower triangle (y >= x) and mirrored (np.tril(K).T + np.tril(K, -1)).
+// The reference builds the dense n x n kernel per centre (O(n^3)); here each centre only
+// visits the band of width 2 k_len around its line: CTA per centre, warp per row, lanes over
+// the (conservative) column interval, exact per-cell weight in fp64.
+__global__ void __launch_bounds__(256)
+intra_x_kernel(const float* __restrict__ m, int n, long long ld, int k_len, double* __restrict__ out) {
+  __shared__ double s_red[8][2];
+  const int c = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vertical = (c == 0);                        // cen_point[0] == telo_point[0]
+  double k = 0.0, nrm = 1.0;
+  if (!vertical) { k = ((double)c - (double)n) / ((double)c - 0.0); nrm = sqrt(1.0 + k * k); }
+  const double b0 = (double)n;
+  const double inv_klen = 1.0 / (double)k_len;
+  double num = 0.0, den = 0.0;
+  for (int y = warp; y < n; y += 8) {
+    int x_lo, x_hi;                                      // conservative inclusive column interval
+    if (vertical) { x_lo = 0; x_hi = min(y, k_len); }
+    else {
+      // |k x - y + n| < k_len * nrm  <=>  x between (y - n -+ W) / k ; k < 0 for c < n
+      const double W = (double)k_len * nrm;
+      if (k == 0.0) { x_lo = 0; x_hi = y; }
+      else {
+        double xa = ((double)y - b0 - W) / k, xb = ((double)y - b0 + W) / k;
+        if (xa > xb) { const double t = xa; xa = xb; xb = t; }
+        x_lo = max(0, (int)floor(xa) - 1);
+        x_hi = min(y, (int)ceil(xb) + 1);
+      }
+    }
+    for (int x = x_lo + lane; x <= x_hi; x += 32) {
+      const double dis = vertical ? fabs((double)x - (double)c)
+                                  : fabs(k * (double)x - (double)y + b0) / nrm;
+      double w = inv_klen * ((double)k_len - dis);
+      if (w <= 0.0) continue;
+      const double lower = (double)m[(long long)y * ld + x];
+      if (x == y) { num += lower * w; den += w; }
+      else {
+        const double upper = (double)m[(long long)x * ld + y];   // mirrored kernel cell
+        num += (lower + upper) * w;
+        den += 2.0 * w;
+      }
+    }
+  }
+  num = warp_sum(num);
+  den = warp_sum(den);
+  if (lane == 0) { s_red[warp][0] = num; s_red[warp][1] = den; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, d = 0;
+    for (int i = 0; i < 8; ++i) { a += s_red[i][0]; d += s_red[i][1]; }
+    out[c] = a / d;
+  }
+}
+
 }  // namespace
 }  // namespace hia
+
+HIA_API int hia_intra_x_response(const float* block, int32_t n, int64_t ld, int32_t k_len, double* out,
+                                 void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (!block || !out || n <= 0 || ld < n || k_len <= 0) return HIA_ERR_BAD_ARG;
+  intra_x_kernel<<<n, 256, 0, s>>>(block, n, ld, k_len, out);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
 
 HIA_API int hia_row_profiles(const float* x, int32_t n, int64_t ld, const int32_t* chr_start,
                              const int16_t* bin_chr, const double* threshold, int reverse, int norm,

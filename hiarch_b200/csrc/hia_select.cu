@@ -190,7 +190,8 @@ __global__ void sel_finish_kernel(const SelState* st, int nq, double* __restrict
   const double b = (double)ordered_to_float(st->prefix[2 * q + 1]);
   const double t = st->gamma[q];
   const double d = b - a;
-  out[q] = (t >= 0.5) ? (b - d * (1.0 - t)) : (a + d * t);
+  // numpy rounds the product and the sum separately: no FMA contraction here
+  out[q] = (t >= 0.5) ? __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, t))) : __dadd_rn(a, __dmul_rn(d, t));
 }
 
 // ---------------------------------------------------------------------------------------

@@ -474,3 +474,98 @@ def gf_scores(dense, layout, centers=None):
     _lib.check(st, "hia_gf_pool_scores")
     return {"pairs": pairs, "pooled": pooled.cpu().numpy(), "isym": isym.cpu().numpy(),
             "xs": xs.cpu().numpy(), "scores": scores.cpu().numpy()}
+
+
+# ------------------------------------------------------------------------------- a7 filters
+def box_filter_reflect(block, size, out=None, scratch=None):
+    """scipy.ndimage.uniform_filter(block, size, mode='reflect') on a rows x cols view
+    (denoise_one_method 'mean', publish/oe_map/S3_denoise.py:53-57)."""
+    lib = _lib.load()
+    _need_cuda(block)
+    assert block.dtype == torch.float32 and block.stride(1) == 1
+    rows, cols = block.shape
+    out = block if out is None else out
+    if scratch is None:
+        scratch = torch.empty((rows, block.stride(0)), dtype=torch.float32, device=block.device)[:, :cols]
+    assert out.stride(0) == block.stride(0) == scratch.stride(0)
+    st = lib.hia_box_filter_reflect(_ptr(block), _ptr(out), _ptr(scratch), rows, cols, block.stride(0),
+                                    int(size), _stream())
+    _lib.check(st, "hia_box_filter_reflect")
+    return out
+
+
+def median_filter_reflect(block, size, out=None):
+    """scipy.ndimage.median_filter(block, size, mode='reflect') (denoise_one_method 'median',
+    publish/oe_map/S3_denoise.py:48-52)."""
+    lib = _lib.load()
+    _need_cuda(block)
+    assert block.dtype == torch.float32 and block.stride(1) == 1
+    rows, cols = block.shape
+    if out is None:
+        out = torch.empty((rows, block.stride(0)), dtype=torch.float32, device=block.device)[:, :cols]
+    assert out.stride(0) == block.stride(0)
+    st = lib.hia_median_filter_reflect(_ptr(block), _ptr(out), rows, cols, block.stride(0), int(size),
+                                       _stream())
+    _lib.check(st, "hia_median_filter_reflect")
+    return out
+
+
+def used_filter(block, size, out, decimals=2, normalise=True, workspace=None):
+    """used_filter of GF_S1 on one block: box filter + norm_to_zero_mean, fp64 inside with
+    scipy's exact summation order (see csrc/hia_filter64.cu for why)."""
+    lib = _lib.load()
+    _need_cuda(block)
+    rows, cols = block.shape
+    need = lib.hia_used_filter_f64_workspace_bytes(rows, cols)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=block.device)
+    st = lib.hia_used_filter_f64(_ptr(block), rows, cols, block.stride(0), int(size), int(decimals),
+                                 1 if normalise else 0, 66.0, _ptr(out), out.stride(0), _ptr(workspace),
+                                 workspace.numel(), _stream())
+    _lib.check(st, "hia_used_filter_f64")
+    return out
+
+
+def main_filter(dense, layout, out=None, decimals=2):
+    """GF_S1 main_filter (publish/confor/src/S1_preprocess/S1_1_filtering.py:21-32): per block
+    box filter (size = int(len(row chromosome) * .1)) + norm_to_zero_mean, then one global
+    remove_outliers. `dense` is the globally min-filled 'all' map; `decimals` = the decimal
+    quantisation of its values (2 for a map read from a %.2f .mtx; -1 = not quantised)."""
+    lib = _lib.load()
+    n = layout.n
+    out = alloc_map(n, dense.device) if out is None else out
+    assert out.data_ptr() != dense.data_ptr()
+    max_len = max(e - s + 1 for s, e in layout.seps)
+    ws = torch.empty(lib.hia_used_filter_f64_workspace_bytes(max_len, max_len), dtype=torch.uint8,
+                     device=dense.device)
+    for (s1, e1) in layout.seps:
+        size = int(np.mean(np.array([e1 - s1 + 1]) * .1))
+        for (s2, e2) in layout.seps:
+            used_filter(dense[s1:e1 + 1, s2:e2 + 1], size, out[s1:e1 + 1, s2:e2 + 1], decimals,
+                        workspace=ws)
+    return remove_outliers(out, out=out)
+
+
+def norm_to_zero_mean_block(block, mid_vmax_per=66):
+    """norm_to_zero_mean in place on an arbitrary (possibly unaligned) block view."""
+    if block.data_ptr() % 16 == 0 and block.stride(0) % 4 == 0:
+        return norm_to_zero_mean(block, mid_vmax_per, out=block)
+    tmp = alloc_map(block.shape[0], block.device, cols=block.shape[1])
+    tmp.copy_(block)
+    norm_to_zero_mean(tmp, mid_vmax_per, out=tmp)
+    block.copy_(tmp)
+    return block
+
+
+# ------------------------------------------------------------------------------- a13 intra-x
+def intra_x_response(block):
+    """get_intra_x (S2_2_find_by_intra_x.py:116-126) of one intra block -> fp64 device [n]."""
+    lib = _lib.load()
+    _need_cuda(block)
+    n = block.shape[0]
+    assert block.shape == (n, n) and block.dtype == torch.float32 and block.stride(1) == 1
+    k_len = max(3, int(n * .05))
+    out = torch.empty(n, dtype=torch.float64, device=block.device)
+    st = lib.hia_intra_x_response(_ptr(block), n, block.stride(0), k_len, _ptr(out), _stream())
+    _lib.check(st, "hia_intra_x_response")
+    return out

@@ -193,6 +193,36 @@ int hia_smooth1d_reflect(const double* in, double* out, int32_t n, const int32_t
                          const int16_t* bin_chr, double kernal_per, int32_t min_kernal_len,
                          void* stream);
 
+/* a13  intra-x response (confor/.../S2_2_find_by_intra_x.py:25-50, :116-126): for every     */
+/* candidate centre c of an n x n intra block: sum(M * K_c) / sum(K_c), K_c = the X-shaped    */
+/* line-distance kernel of half-width k_len = max(3, int(.05 n)). out[n] fp64 (device).       */
+int hia_intra_x_response(const float* block, int32_t n, int64_t ld, int32_t k_len, double* out,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* a7  box (uniform) and median filters, scipy.ndimage 'reflect' boundary                 */
+/* replaces denoise_one_method(mode='mean'|'median') (oe_map/S3_denoise.py:48-57), used by  */
+/* used_denoise (:76-79) and used_filter (confor/src/S1_preprocess/S1_1_filtering.py:13-16) */
+/* ------------------------------------------------------------------------------------ */
+/* x / out / scratch: rows x cols views sharing the leading dimension ld; out may alias x for
+ * the box filter (scratch must not); size <= 1 is the identity (like scipy). */
+int hia_box_filter_reflect(const float* x, float* out, float* scratch, int32_t rows, int32_t cols,
+                           int64_t ld, int32_t size, void* stream);
+/* out != x. element of rank size*size/2 of each size x size window. */
+int hia_median_filter_reflect(const float* x, float* out, int32_t rows, int32_t cols, int64_t ld,
+                              int32_t size, void* stream);
+
+/* GF_S1 used_filter (confor/src/S1_preprocess/S1_1_filtering.py:13-16) on one block as a single
+ * op: box filter (size) + norm_to_zero_mean (mid_vmax_per = 66), fp64 inside with scipy's exact
+ * running-sum order, because the core selection of norm_to_zero_mean is decided by ties (see
+ * hia_filter64.cu). decimals >= 0: the fp32 input is first re-quantised to that many decimals in
+ * fp64 (= the double a "%.2f" field parses to); -1: plain promotion. normalise = 0: box filter
+ * only. x / out: rows x cols views (any alignment). */
+int64_t hia_used_filter_f64_workspace_bytes(int32_t rows, int32_t cols);
+int hia_used_filter_f64(const float* x, int32_t rows, int32_t cols, int64_t ld_in, int32_t size,
+                        int32_t decimals, int normalise, double mid_vmax_per, float* out,
+                        int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------ */
 /* a14/a15  GF_S2: adaptive pool 16x16 (4 quadrants of 8x8 around a 'used' anchor),        */
 /* z-score, flip-symmetrise, 5 template scores (inter: max with the transposed image)      */

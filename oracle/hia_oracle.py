@@ -314,6 +314,37 @@ def box_filter_reflect(M, size):
     return uniform_filter(np.asarray(M, dtype=np.float64), size=size, mode="reflect")
 
 
+def _reflect(i, n):
+    p = 2 * n
+    i %= p
+    return i if i < n else p - 1 - i
+
+
+def box_filter_replica(M, size):
+    """Bit-for-bit restatement of scipy.ndimage.uniform_filter(mode='reflect') = two passes of
+    NI_UniformFilter1D (axis 0 then axis 1): tmp = sum of the first window in order;
+    tmp += new - old; out = tmp / size. The GPU fp64 path (csrc/hia_filter64.cu) follows this
+    order; `tests/test_host_tables.py::test_uniform_filter_replica` pins it against scipy."""
+    def one_axis(a, axis):
+        a = np.moveaxis(np.asarray(a, dtype=np.float64), axis, 0).copy()
+        n = a.shape[0]
+        out = np.empty_like(a)
+        s1 = size // 2
+        s2 = size - s1 - 1
+        ext = a[[_reflect(i, n) for i in range(-s1, n + s2)]]
+        tmp = np.zeros(a.shape[1:])
+        for ll in range(size):
+            tmp = tmp + ext[ll]
+        out[0] = tmp / float(size)
+        for ll in range(1, n):
+            tmp = tmp + (ext[ll + size - 1] - ext[ll - 1])
+            out[ll] = tmp / float(size)
+        return np.moveaxis(out, 0, axis)
+    if size <= 1:
+        return np.array(M, dtype=np.float64)
+    return one_axis(one_axis(M, 0), 1)
+
+
 def median_filter_reflect(M, size):
     """denoise_one_method(mode='median'): median_filter(size, mode='reflect'). S3_denoise.py:48-52."""
     from scipy.ndimage import median_filter

@@ -399,3 +399,77 @@ def test_gf_s2_images_and_scores(golden):
         ri, ro = g[f"gf.{method}.intra_score"], g[f"gf.{method}.inter_score"]
         assert np.all(np.abs(si - ri) <= 1e-4 * np.abs(ri) + 1e-9)      # north-star: 1e-4 relative
         assert np.all(np.abs(so - ro) <= 1e-4 * np.abs(ro) + 1e-9)
+
+
+# --------------------------------------------------------------------------------- a7 filters
+@pytest.mark.parametrize("shape,size", [((120, 120), 12), ((100, 80), 10), ((80, 120), 8), ((64, 33), 5),
+                                        ((30, 30), 2), ((12, 300), 30), ((50, 50), 1), ((2500, 300), 250)])
+def test_box_filter_vs_scipy(shape, size):
+    from hiarch_b200 import ops
+    rng = np.random.default_rng(size)
+    a = rng.standard_normal(shape).astype(np.float32)
+    d = _mapdev(a)
+    got = ops.box_filter_reflect(d, size, out=_mapdev(np.zeros(shape))).cpu().numpy()
+    ref = O.box_filter_reflect(a.astype(np.float64), size)
+    assert np.abs(got - ref).max() <= 2e-6
+
+
+@pytest.mark.parametrize("shape,size", [((120, 120), 2), ((100, 80), 5), ((64, 33), 3), ((40, 40), 8),
+                                        ((300, 200), 24)])
+def test_median_filter_vs_scipy(shape, size):
+    from hiarch_b200 import ops
+    rng = np.random.default_rng(size)
+    a = np.round(rng.standard_normal(shape), 2).astype(np.float32)
+    got = ops.median_filter_reflect(_mapdev(a), size).cpu().numpy()
+    ref = O.median_filter_reflect(a.astype(np.float64), size)
+    assert np.array_equal(got, ref.astype(np.float32))          # a selection: bit-exact
+
+
+@pytest.mark.parametrize("case", ["g3chr", "g1chr"])
+def test_main_filter_against_reference(golden, case):
+    """GF_S1 main_filter through the fp64 scipy-order replica (csrc/hia_filter64.cu): the core
+    selection of norm_to_zero_mean sits on massive ties, so only the exact summation order
+    reproduces the reference."""
+    from hiarch_b200 import ops
+    g = golden(case)
+    n = int(g["in.lens"].sum())
+    seps = _seps(g)
+    layout = ops.GenomeLayout(seps)
+    # (1) un-quantised input (fp32 values promoted as they are)
+    x32 = g["norm_de"].astype(np.float32)
+    ref = O.main_filter(x32.astype(np.float64), seps)
+    got = ops.main_filter(_mapdev(x32), layout, decimals=-1).cpu().numpy()
+    assert np.all(np.abs(got - ref) <= 2e-6 + 2e-7 * np.abs(ref)), np.abs(got - ref).max()
+    # (2) the pipeline's %.2f file -> the reference's own output
+    r, c, v = _coo(g, "de_file")
+    dense = ops.scatter_coo_sym(r, c, v, n, fill_mode=ops.FILL_MIN, layout=layout)
+    filt = ops.main_filter(dense, layout, decimals=2).cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(filt - g["filt"]) <= 2e-6 + 2e-7 * np.abs(g["filt"])), np.abs(filt - g["filt"]).max()
+
+
+def test_used_filter_box_only_is_bit_exact_vs_scipy():
+    from hiarch_b200 import ops
+    rng = np.random.default_rng(8)
+    for shape, size in (((120, 100), 12), ((37, 53), 5), ((12, 40), 30), ((64, 64), 1)):
+        a = np.round(rng.standard_normal(shape) * 3, 2)
+        d = _mapdev(a)
+        out = _mapdev(np.zeros(shape))
+        ops.used_filter(d, size, out, decimals=2, normalise=False)
+        ref = O.box_filter_reflect(a, size) if size > 1 else a
+        assert np.array_equal(out.cpu().numpy(), ref.astype(np.float32))
+
+
+# --------------------------------------------------------------------------------- a13 intra-x
+def test_intra_x_response(golden):
+    from hiarch_b200 import ops
+    g = golden("g1chr")
+    got = ops.intra_x_response(_mapdev(g["filt"])).cpu().numpy()
+    ref = g["intra_x"]
+    assert np.all(np.abs(got - ref) <= 1e-4 * np.abs(ref) + 1e-7)
+    rng = np.random.default_rng(2)
+    for n in (61, 150):
+        a = rng.standard_normal((n, n))
+        a = (a + a.T) / 2
+        got = ops.intra_x_response(_mapdev(a)).cpu().numpy()
+        ref = O.intra_x(a.astype(np.float32).astype(np.float64))
+        assert np.all(np.abs(got - ref) <= 1e-9 + 1e-9 * np.abs(ref))

@@ -87,3 +87,12 @@ def test_tiny_chromosome_raises_like_reference():
     with pytest.raises(ValueError):
         oe_tables(100000, 2)
     oe_tables(100000, 1)
+
+
+def test_uniform_filter_replica():
+    """The summation order the GPU fp64 filter path follows is scipy's, bit for bit."""
+    rng = np.random.default_rng(0)
+    for shape, size in [((120, 100), 12), ((100, 80), 10), ((80, 80), 8), ((37, 53), 5),
+                        ((30, 30), 2), ((12, 40), 30), ((50, 64), 7)]:
+        a = np.round(rng.standard_normal(shape) * 3, 2)
+        assert np.array_equal(O.box_filter_replica(a, size), O.box_filter_reflect(a, size))

@@ -363,8 +363,55 @@ oe_apply_kernel(const float* __restrict__ map, float* __restrict__ out, int n, l
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Stand-alone ArrayHiCMtx.log (new_hic_class.py:2076-2094) for maps that did not come out of
+// hia_oe_apply: pass 1 = min positive value, pass 2 = x>0 ? ln(x+1) : ln(min_pos + 1).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+min_pos_kernel(const float* __restrict__ x, int rows, int cols, long long ld, float* __restrict__ min_pos) {
+  float mn = INFINITY;
+  const long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[(i / cols) * ld + (i % cols)];
+    if (v > 0.f) mn = fminf(mn, v);
+  }
+  mn = warp_min(mn);
+  if ((threadIdx.x & 31) == 0 && mn != INFINITY) atomic_min_pos_float(min_pos, mn);
+}
+
+__global__ void __launch_bounds__(256)
+log_apply_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int cols, long long ld,
+                 const float* __restrict__ min_pos) {
+  const float m = *min_pos;
+  const float fill = (m == INFINITY) ? 0.f : log1pf(m);
+  const long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long off = (i / cols) * ld + (i % cols);
+    const float v = x[off];
+    out[off] = (v > 0.f) ? log1pf(v) : fill;
+  }
+}
+
 }  // namespace
 }  // namespace hia
+
+HIA_API int hia_log_map(const float* x, float* out, int32_t rows, int32_t cols, int64_t ld,
+                        float* min_pos_ws, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !out || !min_pos_ws || rows <= 0 || cols <= 0 || ld < cols) return HIA_ERR_BAD_ARG;
+  init_min_kernel<<<1, 1, 0, stream>>>(min_pos_ws);
+  HIA_LAUNCH_CHECK();
+  const long long total = (long long)rows * cols;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+  min_pos_kernel<<<grid, 256, 0, stream>>>(x, rows, cols, ld, min_pos_ws);
+  HIA_LAUNCH_CHECK();
+  log_apply_kernel<<<grid, 256, 0, stream>>>(x, out, rows, cols, ld, min_pos_ws);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
 
 HIA_API int hia_oe_expected_pass(const float* map, int32_t n, int64_t ld, const int32_t* chr_start,
                                  const int32_t* chr_start_host, int32_t n_chr, double* diag_sum,

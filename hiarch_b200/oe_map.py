@@ -1,0 +1,93 @@
+"""Mirror of publish/oe_map (the O/E normalisation package) on the CUDA ops.
+
+oe_map_core    publish/oe_map/S2_oe.py:10-15            obs_d_exp(sgd_mean, k=.2) -> log, fused
+tid_off_outliers / main_denoise   publish/oe_map/S3_denoise.py:85-107
+norm_to_zero_mean / remove_outliers / norm_de_mtx       publish/oe_map/S4_norm_value.py:10-46
+"""
+import numpy as np
+
+from . import ops
+from .new_hic_class import ArrayHiCMtx, SpsHiCMtx
+
+mode = 'sgd_mean'
+k = .2
+counts_must_decrese = True
+mid_vmax_per = 66
+default_vmax_per = 98
+
+
+def _dense_all(m):
+    d = m.to_dense() if isinstance(m, SpsHiCMtx) else m
+    if d.mtx_type != 'all':
+        d = d.to_all(inplace=False)
+    return d
+
+
+def oe_map_core(sps_mtx, counts_must_decrese=True):
+    """S2_oe.py:10-15: one fused call (expected pass + finalize + apply+log)."""
+    d = _dense_all(sps_mtx)
+    layout = d.row_window.layout(d.dmatrix.device)
+    out, state = ops.obs_d_exp(d.dmatrix, layout, d.row_window.bin_size, k=k,
+                               counts_must_decrese=counts_must_decrese, log=True)
+    res = ArrayHiCMtx(out, copy_mtx_paras=d, mtx_type='all', has_neg=False)
+    res._oe_state = state
+    return res
+
+
+def tid_off_outliers(sps_map, vamx_per=default_vmax_per):
+    d = _dense_all(sps_map)
+    return ArrayHiCMtx(ops.tid_off_outliers(d.dmatrix, vamx_per), copy_mtx_paras=d)
+
+
+def norm_to_zero_mean(input_mtx):
+    d = _dense_all(input_mtx)
+    return ArrayHiCMtx(ops.norm_to_zero_mean(d.dmatrix, mid_vmax_per), copy_mtx_paras=d, has_neg=True)
+
+
+def remove_outliers(input_mtx):
+    d = _dense_all(input_mtx)
+    return ArrayHiCMtx(ops.remove_outliers(d.dmatrix, default_vmax_per), copy_mtx_paras=d)
+
+
+def norm_de_mtx(input_mtx):
+    return remove_outliers(norm_to_zero_mean(input_mtx))
+
+
+def denoise_one_method(sps_mtx, mode='wavelet', sigma=None, spatial_sigma_ratio=None):
+    """S3_denoise.py:38-73, modes 'median' and 'mean'. 'wavelet' (skimage db3 VisuShrink) is
+    third-party, unversioned arithmetic that is absent here: parity unpinned, not implemented."""
+    d = sps_mtx.to_dense() if isinstance(sps_mtx, SpsHiCMtx) else sps_mtx
+    ratio = .1 if spatial_sigma_ratio is None else spatial_sigma_ratio
+    size = int(np.mean(np.array(list(sps_mtx.row_window.chr_lens.values())) * ratio))
+    if mode == 'median':
+        size = 2 if size < 2 else size
+        src = d.dmatrix
+        if src.data_ptr() % 16 or src.stride(0) % 4:
+            tmp = ops.alloc_map(src.shape[0], src.device, cols=src.shape[1])
+            tmp.copy_(src)
+            src = tmp
+        out = ops.median_filter_reflect(src, size)
+    elif mode == 'mean':
+        out = ops.alloc_map(d.shape[0], d.dmatrix.device, cols=d.shape[1])
+        ops.used_filter(d.dmatrix, size, out, decimals=-1, normalise=False)
+    else:
+        raise NotImplementedError(f"denoise mode {mode!r}: parity unpinned / not on the hot path")
+    return ArrayHiCMtx(out, copy_mtx_paras=d)
+
+
+def main_denoise(sps_map, wavelet=None):
+    """S3_denoise.py:95-107: clip to [p2, p98], then per block wavelet -> median. The wavelet is
+    NOT available (see denoise_one_method); `wavelet` may be a callable applied per block to
+    keep both sides of a comparison identical; default = skip it (identity)."""
+    d = _dense_all(sps_map)
+    clipped = tid_off_outliers(d)
+    out = ops.alloc_map(d.shape[0], d.dmatrix.device)
+    res = ArrayHiCMtx(out, copy_mtx_paras=clipped)
+    for c1, c2, blk in clipped.yield_by_chro():
+        if wavelet is not None:
+            blk = wavelet(blk)
+        den = denoise_one_method(blk, 'median', None, .01)
+        s1, e1 = d.row_window.chr_seps[c1]
+        s2, e2 = d.col_window.chr_seps[c2]
+        out[s1:e1 + 1, s2:e2 + 1].copy_(den.dmatrix)
+    return res

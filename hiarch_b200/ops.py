@@ -160,6 +160,19 @@ def obs_d_exp(dense, layout, bin_size, k=.2, counts_must_decrese=True, only_intr
     return out, state
 
 
+def log_map(x, out=None):
+    """ArrayHiCMtx.log (publish/new_hic_class.py:2076-2094) on an arbitrary rows x cols view."""
+    lib = _lib.load()
+    _need_cuda(x)
+    if out is None:
+        out = alloc_map(x.shape[0], x.device, cols=x.shape[1])
+    assert out.stride(0) == x.stride(0)
+    ws = torch.empty(1, dtype=torch.float32, device=x.device)
+    st = lib.hia_log_map(_ptr(x), _ptr(out), x.shape[0], x.shape[1], x.stride(0), _ptr(ws), _stream())
+    _lib.check(st, "hia_log_map")
+    return out
+
+
 # ------------------------------------------------------------------------------- a8 similarity
 _ws_cache = {}
 

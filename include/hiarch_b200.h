@@ -104,6 +104,11 @@ int hia_oe_apply(const float* map, float* out, int32_t n, int64_t ld, const int3
                  int32_t n_chr, const int16_t* bin_chr, const float* inv_expected,
                  const float* inter_inv, const float* min_pos_oe, int flags, void* stream);
 
+/* Stand-alone ArrayHiCMtx.log (new_hic_class.py:2076-2094) for a map that did not come out of
+ * hia_oe_apply: x>0 -> ln(x+1); x<=0 -> min over positives of ln(x+1). min_pos_ws: 1 float. */
+int hia_log_map(const float* x, float* out, int32_t rows, int32_t cols, int64_t ld, float* min_pos_ws,
+                void* stream);
+
 /* ------------------------------------------------------------------------------------ */
 /* a8  row x row similarity: cosine distance (get_adj_mtx, complex/src/S1_get_adj_mtx.py  */
 /*     :8-14 == squareform(pdist(M,'cosine'))) and Pearson correlation (north-star)       */

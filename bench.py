@@ -271,8 +271,14 @@ def run_ours(args):
     achieved = logical / (gemm * 1e-3) / 1e12
     tf32_peak = pk["bf16_tflops_sustained"] / 2.0           # TF32 dense = bf16 / 2 on Blackwell
     peak_logical = tf32_peak / 3.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "syrk_traffic.json")
+    if os.path.exists(tpath) and n == 30894:            # the capture was taken on this workload
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_logical, "unit": "TFLOP/s",
-                "frac": achieved / peak_logical, "traffic": None,
+                "frac": achieved / peak_logical, "traffic": traffic,
+                "frac_of_burst_peak": achieved / (pk["bf16_tflops"] / 6.0),
                 "kernel": "syrk_tf32x3_kernel", "ms_per_launch": gemm,
                 "note": ("achieved = N^3 logical flops (upper-triangle SYRK) / CUDA-event time of the "
                          "kernel; peak = bf16_tflops_sustained/2 (TF32) /3 (3xTF32 split), "

@@ -45,27 +45,28 @@ __global__ void double_to_float_panel_kernel(const double* __restrict__ src, flo
   if (i < count) dst[i] = (float)src[i];
 }
 
-// Y[n x B] (fp64, col-major) = C[n x n] (fp32 row-major, ld) * V[n x B] (fp32, col-major)
+// Y[n x B] (fp64, col-major, += into a zeroed panel) = C[n x n] (fp32 row-major) * V[n x B] (fp32).
+// CTA = 1024-column chunk x 256 rows: the V chunk (B x 1024 fp32) is staged in shared memory ONCE
+// per CTA and reused by 256 rows; every warp streams its 32 rows in groups of 4 with 128-bit
+// loads, fp32 partials over the chunk, butterfly reduce, one fp64 atomicAdd per (row, vector).
+constexpr int kSymmRowsPerCta = 256;
 template <int B>
 __global__ void __launch_bounds__(kSymmWarps * 32)
 symm_panel_kernel(const float* __restrict__ c, int n, long long ld, const float* __restrict__ v,
                   double* __restrict__ y) {
   __shared__ __align__(16) float s_v[B][kSymmCols];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = blockIdx.x * kSymmRows + warp * kSymmRowsPerWarp;
-  double tot[kSymmRowsPerWarp][B];
-#pragma unroll
-  for (int r = 0; r < kSymmRowsPerWarp; ++r)
-#pragma unroll
-    for (int j = 0; j < B; ++j) tot[r][j] = 0.0;
-
-  for (int k0 = 0; k0 < n; k0 += kSymmCols) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < B * kSymmCols; idx += blockDim.x) {
-      const int j = idx / kSymmCols, col = idx % kSymmCols;
-      s_v[j][col] = (k0 + col < n) ? v[(long long)j * n + k0 + col] : 0.f;
-    }
-    __syncthreads();
+  const int k0 = blockIdx.x * kSymmCols;
+  for (int idx = threadIdx.x; idx < B * kSymmCols; idx += blockDim.x) {
+    const int j = idx / kSymmCols, col = idx % kSymmCols;
+    s_v[j][col] = (k0 + col < n) ? v[(long long)j * n + k0 + col] : 0.f;
+  }
+  __syncthreads();
+  const int rbase = blockIdx.y * kSymmRowsPerCta + warp * (kSymmRowsPerCta / kSymmWarps);
+#pragma unroll 1
+  for (int g = 0; g < kSymmRowsPerCta / kSymmWarps / kSymmRowsPerWarp; ++g) {
+    const int r0 = rbase + g * kSymmRowsPerWarp;
+    if (r0 >= n) break;
     float acc[kSymmRowsPerWarp][B];
 #pragma unroll
     for (int r = 0; r < kSymmRowsPerWarp; ++r)
@@ -105,15 +106,11 @@ symm_panel_kernel(const float* __restrict__ c, int n, long long ld, const float*
 #pragma unroll
     for (int r = 0; r < kSymmRowsPerWarp; ++r)
 #pragma unroll
-      for (int j = 0; j < B; ++j) tot[r][j] += (double)acc[r][j];
+      for (int j = 0; j < B; ++j) {
+        const float s = warp_sum(acc[r][j]);
+        if (lane == ((r * B + j) & 31) && r0 + r < n) atomicAdd(&y[(long long)j * n + r0 + r], (double)s);
+      }
   }
-#pragma unroll
-  for (int r = 0; r < kSymmRowsPerWarp; ++r)
-#pragma unroll
-    for (int j = 0; j < B; ++j) {
-      const double s = warp_sum(tot[r][j]);
-      if (lane == 0 && r0 + r < n) y[(long long)j * n + r0 + r] = s;
-    }
 }
 
 // G[p x b] (row-major, += ) = A[:, 0:p]^T B[:, 0:b]; A, B col-major fp64 with ld = n.
@@ -293,7 +290,7 @@ jacobi_kernel(const double* __restrict__ h, int D, int dim, double* __restrict__
           alpha += x * x; beta += y * y; gamma += x * y;
         }
         alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
-        if (fabs(gamma) <= 1e-15 * sqrt(alpha * beta) || gamma == 0.0) continue;
+        if (fabs(gamma) <= 1e-13 * sqrt(alpha * beta) || gamma == 0.0) continue;
         if (lane == 0) s_rot = 1;
         const double zeta = (beta - alpha) / (2.0 * gamma);
         const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -399,7 +396,9 @@ long long carve(unsigned char* base, int n, int b, int steps, EigWs* w) {
 
 template <int B>
 int launch_symm(const float* c, int n, long long ld, const float* v, double* y, cudaStream_t s) {
-  symm_panel_kernel<B><<<(n + kSymmRows - 1) / kSymmRows, kSymmWarps * 32, 0, s>>>(c, n, ld, v, y);
+  HIA_CUDA(cudaMemsetAsync(y, 0, (size_t)n * B * sizeof(double), s));
+  dim3 grid((n + kSymmCols - 1) / kSymmCols, (n + kSymmRowsPerCta - 1) / kSymmRowsPerCta);
+  symm_panel_kernel<B><<<grid, kSymmWarps * 32, 0, s>>>(c, n, ld, v, y);
   count_launch();
   return cuda_ok(cudaGetLastError());
 }
@@ -495,7 +494,7 @@ HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32
   }
   // ---- Rayleigh-Ritz on the leading dim x dim part (the last block has no column in H)
   const int dim = steps * b;
-  jacobi_kernel<<<1, 1024, 0, s>>>(w.H, D, dim, w.JA, w.JV, w.lam, w.order, 30);
+  jacobi_kernel<<<1, 1024, 0, s>>>(w.H, D, dim, w.JA, w.JV, w.lam, w.order, 15);
   HIA_LAUNCH_CHECK();
   ritz_kernel<<<(n + 255) / 256, 256, 0, s>>>(w.Q, n, dim, w.JV, w.order, w.lam, k, w.U, w.Vf, eigvals);
   HIA_LAUNCH_CHECK();

@@ -322,36 +322,48 @@ syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 }
 
 // ------------------------------------------------------------------ row prologue
-// One CTA per row: fp64 mean (Pearson) and norm, then the TF32 hi/lo planes of the unit row.
+// One CTA per row: fp64 sum and sum of squares in ONE pass (128-bit loads; the row then sits in
+// L1/L2), mean / norm, then the TF32 hi/lo planes of the unit row in a second pass.
 __global__ void __launch_bounds__(256)
 row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int kpad, int center,
                 float* __restrict__ hi, float* __restrict__ lo) {
-  __shared__ double s_red[8];
-  __shared__ double s_val;
+  __shared__ double s_red[8][2];
+  __shared__ double s_val[2];
   const int r = blockIdx.x;
   if (r >= m) return;
   const float* row = x + (long long)r * ld_x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  double mean = 0.0;
-  if (center) {
-    double sum = 0.0;
-    for (int j = tid; j < k; j += blockDim.x) sum += (double)row[j];
-    sum = warp_sum(sum);
-    if (lane == 0) s_red[w] = sum;
-    __syncthreads();
-    if (tid == 0) { double t = 0; for (int i = 0; i < 8; ++i) t += s_red[i]; s_val = t / (double)k; }
-    __syncthreads();
-    mean = s_val;
-    __syncthreads();
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
+  // shift by the first element: keeps sum((x - s)^2) - n (mean - s)^2 well conditioned
+  const double shift = (double)row[0];
+  double s1 = 0.0, s2 = 0.0;
+  if (vec_ok) {
+    const int k4 = k >> 2;
+    for (int j = tid; j < k4; j += blockDim.x) {
+      const float4 v = *reinterpret_cast<const float4*>(row + 4 * j);
+      const double a = (double)v.x - shift, b = (double)v.y - shift, c = (double)v.z - shift, d = (double)v.w - shift;
+      s1 += (a + b) + (c + d);
+      s2 += (a * a + b * b) + (c * c + d * d);
+    }
+    for (int j = (k4 << 2) + tid; j < k; j += blockDim.x) { const double a = (double)row[j] - shift; s1 += a; s2 += a * a; }
+  } else {
+    for (int j = tid; j < k; j += blockDim.x) { const double a = (double)row[j] - shift; s1 += a; s2 += a * a; }
   }
-  double ss = 0.0;
-  for (int j = tid; j < k; j += blockDim.x) { const double d = (double)row[j] - mean; ss += d * d; }
-  ss = warp_sum(ss);
-  if (lane == 0) s_red[w] = ss;
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) { s_red[w][0] = s1; s_red[w][1] = s2; }
   __syncthreads();
-  if (tid == 0) { double t = 0; for (int i = 0; i < 8; ++i) t += s_red[i]; s_val = 1.0 / sqrt(t); }
+  if (tid == 0) {
+    double t1 = 0, t2 = 0;
+    for (int i = 0; i < 8; ++i) { t1 += s_red[i][0]; t2 += s_red[i][1]; }
+    // Pearson: centre on the mean; cosine: centre on 0 (= shift back)
+    const double mean_s = center ? t1 / (double)k : -shift;      // mean of (x - shift)
+    const double ss = t2 - 2.0 * mean_s * t1 + (double)k * mean_s * mean_s;   // sum (x - shift - mean_s)^2
+    s_val[0] = mean_s + shift;
+    s_val[1] = 1.0 / sqrt(ss > 0.0 ? ss : 0.0);          // inf for an all-zero row -> NaN, like pdist
+  }
   __syncthreads();
-  const double inv = s_val;                               // inf for an all-zero row -> NaN, like pdist
+  const double mean = s_val[0], inv = s_val[1];
   float* ph = hi + (long long)r * kpad;
   float* pl = lo + (long long)r * kpad;
   for (int j = tid; j < kpad; j += blockDim.x) {

@@ -57,6 +57,16 @@ PROTOTYPES = {
     "hia_topk_eig_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),
     "hia_topk_eig": (c_int, [c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_i32,
                              c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "hia_sim_kpad": (c_i32, [c_i32]),
+    "hia_sim_prep_rows": (c_int, [c_vp, c_i32, c_i32, c_i64, c_int, c_vp, c_vp, c_vp]),
+    "hia_sim_gemm_rows_workspace_bytes": (c_i64, [c_i32, c_i32]),
+    "hia_sim_gemm_rows": (c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_int, c_i32,
+                                  c_vp, c_i64, c_vp]),
+    "hia_eig_begin": (c_int, [c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_i32, c_vp, c_i64, c_vp]),
+    "hia_eig_symm_rows": (c_int, [c_vp, c_i32, c_i32, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "hia_eig_absorb": (c_int, [c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "hia_eig_ritz": (c_int, [c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "hia_eig_resid": (c_int, [c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

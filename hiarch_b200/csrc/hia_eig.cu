@@ -52,8 +52,10 @@ __global__ void double_to_float_panel_kernel(const double* __restrict__ src, flo
 constexpr int kSymmRowsPerCta = 256;
 template <int B>
 __global__ void __launch_bounds__(kSymmWarps * 32)
-symm_panel_kernel(const float* __restrict__ c, int n, long long ld, const float* __restrict__ v,
-                  double* __restrict__ y) {
+symm_panel_kernel(const float* __restrict__ c, int rows, int n, long long ld, const float* __restrict__ v,
+                  double* __restrict__ y, int row_major) {
+  // c: rows x n block of the matrix (rows <= n); v: n x B panel (col-major, ld n);
+  // y: rows x B, row-major (row_major != 0) or col-major with ld = rows
   __shared__ __align__(16) float s_v[B][kSymmCols];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * kSymmCols;
@@ -66,7 +68,7 @@ symm_panel_kernel(const float* __restrict__ c, int n, long long ld, const float*
 #pragma unroll 1
   for (int g = 0; g < kSymmRowsPerCta / kSymmWarps / kSymmRowsPerWarp; ++g) {
     const int r0 = rbase + g * kSymmRowsPerWarp;
-    if (r0 >= n) break;
+    if (r0 >= rows) break;
     float acc[kSymmRowsPerWarp][B];
 #pragma unroll
     for (int r = 0; r < kSymmRowsPerWarp; ++r)
@@ -80,7 +82,7 @@ symm_panel_kernel(const float* __restrict__ c, int n, long long ld, const float*
 #pragma unroll
       for (int r = 0; r < kSymmRowsPerWarp; ++r) {
         const int gr = r0 + r;
-        if (gr < n) {
+        if (gr < rows) {
           if (gc + 3 < n) a[r] = ld_stream4(c + (long long)gr * ld + gc);
           else {
             const float* p = c + (long long)gr * ld + gc;
@@ -108,7 +110,10 @@ symm_panel_kernel(const float* __restrict__ c, int n, long long ld, const float*
 #pragma unroll
       for (int j = 0; j < B; ++j) {
         const float s = warp_sum(acc[r][j]);
-        if (lane == ((r * B + j) & 31) && r0 + r < n) atomicAdd(&y[(long long)j * n + r0 + r], (double)s);
+        if (lane == ((r * B + j) & 31) && r0 + r < rows) {
+          double* dst = row_major ? &y[(long long)(r0 + r) * B + j] : &y[(long long)j * rows + r0 + r];
+          atomicAdd(dst, (double)s);
+        }
       }
   }
 }
@@ -395,19 +400,29 @@ long long carve(unsigned char* base, int n, int b, int steps, EigWs* w) {
 }
 
 template <int B>
-int launch_symm(const float* c, int n, long long ld, const float* v, double* y, cudaStream_t s) {
-  HIA_CUDA(cudaMemsetAsync(y, 0, (size_t)n * B * sizeof(double), s));
-  dim3 grid((n + kSymmCols - 1) / kSymmCols, (n + kSymmRowsPerCta - 1) / kSymmRowsPerCta);
-  symm_panel_kernel<B><<<grid, kSymmWarps * 32, 0, s>>>(c, n, ld, v, y);
+int launch_symm(const float* c, int rows, int n, long long ld, const float* v, double* y, int row_major,
+                cudaStream_t s) {
+  HIA_CUDA(cudaMemsetAsync(y, 0, (size_t)rows * B * sizeof(double), s));
+  dim3 grid((n + kSymmCols - 1) / kSymmCols, (rows + kSymmRowsPerCta - 1) / kSymmRowsPerCta);
+  symm_panel_kernel<B><<<grid, kSymmWarps * 32, 0, s>>>(c, rows, n, ld, v, y, row_major);
   count_launch();
   return cuda_ok(cudaGetLastError());
 }
-int symm(const float* c, int n, long long ld, const float* v, double* y, int b, cudaStream_t s) {
+int symm(const float* c, int rows, int n, long long ld, const float* v, double* y, int b, int row_major,
+         cudaStream_t s) {
   switch (b) {
-    case 4: return launch_symm<4>(c, n, ld, v, y, s);
-    case 8: return launch_symm<8>(c, n, ld, v, y, s);
+    case 4: return launch_symm<4>(c, rows, n, ld, v, y, row_major, s);
+    case 8: return launch_symm<8>(c, rows, n, ld, v, y, row_major, s);
     default: return HIA_ERR_UNSUPPORTED;
   }
+}
+
+// dst (col-major n x b) <- src (row-major n x b)
+__global__ void rowmajor_to_colmajor_kernel(const double* __restrict__ src, double* __restrict__ dst, int n, int b) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * b) return;
+  const int j = (int)(i / n), r = (int)(i % n);
+  dst[i] = src[(long long)r * b + j];
 }
 
 // Orthonormalise Y (n x b) in place by CholQR; returns R in r_out (b x b), fp32 copy in yf.
@@ -424,6 +439,14 @@ int cholqr(double* Y, int n, int b, EigWs& w, double* r_out, float* yf, cudaStre
   return HIA_OK;
 }
 
+int check_shape(int n, int block, int steps) {
+  if (n <= 0 || steps <= 0) return HIA_ERR_BAD_ARG;
+  if (block != 4 && block != 8) return HIA_ERR_UNSUPPORTED;
+  if ((long long)block * (steps + 1) > n) return HIA_ERR_BAD_ARG;       // Krylov space larger than n
+  if ((long long)block * (steps + 1) > 272) return HIA_ERR_UNSUPPORTED;
+  return HIA_OK;
+}
+
 }  // namespace
 }  // namespace hia
 
@@ -432,82 +455,149 @@ HIA_API int64_t hia_topk_eig_workspace_bytes(int32_t n, int32_t block, int32_t s
   return hia::carve(nullptr, n, block, steps, nullptr);
 }
 
-HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block, int32_t steps,
-                         uint64_t seed, const float* init_vecs, int32_t n_init, double* eigvals,
-                         float* eigvecs, double* resid, void* workspace, int64_t workspace_bytes,
-                         void* stream_) {
+// ---- phase 0: start block (caller-provided vectors for a restart + random columns), orthonormal
+HIA_API int hia_eig_begin(int32_t n, int32_t block, int32_t steps, uint64_t seed, const float* init_vecs,
+                          int32_t n_init, void* workspace, int64_t workspace_bytes, void* stream_) {
   using namespace hia;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
-  if (!c || !eigvals || !eigvecs || !resid || !workspace || n <= 0 || ld < n || k <= 0 || steps <= 0)
-    return HIA_ERR_BAD_ARG;
-  if (block != 4 && block != 8) return HIA_ERR_UNSUPPORTED;
-  if (k > block || n_init < 0 || n_init > block) return HIA_ERR_BAD_ARG;
-  if ((long long)block * (steps + 1) > n) return HIA_ERR_BAD_ARG;       // Krylov space larger than n
-  if ((long long)block * (steps + 1) > 272) return HIA_ERR_UNSUPPORTED;
-  if (!aligned16(c) || (ld & 3)) return HIA_ERR_ALIGN;
+  int st = check_shape(n, block, steps);
+  if (st != HIA_OK) return st;
+  if (!workspace || n_init < 0 || n_init > block || (n_init > 0 && !init_vecs)) return HIA_ERR_BAD_ARG;
   if (workspace_bytes < hia_topk_eig_workspace_bytes(n, block, steps)) return HIA_ERR_WORKSPACE;
   const int b = block, D = b * (steps + 1);
   EigWs w;
   carve(static_cast<unsigned char*>(workspace), n, b, steps, &w);
-
-  // ---- start block: caller-provided vectors (restart) + random columns, orthonormalised
   random_panel_kernel<<<(int)(((long long)n * b + 255) / 256), 256, 0, s>>>(w.Q, n, b, seed);
   HIA_LAUNCH_CHECK();
   if (n_init > 0) {
-    if (!init_vecs) return HIA_ERR_BAD_ARG;
     float_to_double_panel_kernel<<<(int)(((long long)n * n_init + 255) / 256), 256, 0, s>>>(init_vecs, w.Q, (long long)n * n_init);
     HIA_LAUNCH_CHECK();
   }
-  int st = cholqr(w.Q, n, b, w, w.R1, nullptr, s);
+  st = cholqr(w.Q, n, b, w, w.R1, nullptr, s);
   if (st != HIA_OK) return st;
   st = cholqr(w.Q, n, b, w, w.R1, w.Vf, s);
   if (st != HIA_OK) return st;
   HIA_CUDA(cudaMemsetAsync(w.H, 0, (size_t)D * D * 8, s));
+  return HIA_OK;
+}
 
+// ---- the only pass over the matrix: y_rows (rows x block, row-major fp64) = C[rows, :] * panel,
+// where the panel is the current fp32 block held in the workspace (Q_j, or the Ritz vectors).
+HIA_API int hia_eig_symm_rows(const float* c_rows, int32_t rows, int32_t n, int64_t ld, int32_t block,
+                              int32_t steps, void* workspace, double* y_rows, void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (!c_rows || !workspace || !y_rows || rows <= 0 || rows > n || ld < n) return HIA_ERR_BAD_ARG;
+  if (!aligned16(c_rows) || (ld & 3)) return HIA_ERR_ALIGN;
+  int st = check_shape(n, block, steps);
+  if (st != HIA_OK) return st;
+  EigWs w;
+  carve(static_cast<unsigned char*>(workspace), n, block, steps, &w);
+  return symm(c_rows, rows, n, ld, w.Vf, y_rows, block, 1, s);
+}
+
+// ---- step j: Y (n x block, row-major: all rows gathered) -> H[:, j], Q_{j+1}, next fp32 panel
+HIA_API int hia_eig_absorb(int32_t n, int32_t block, int32_t steps, int32_t j, const double* y_full,
+                           void* workspace, void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  int st = check_shape(n, block, steps);
+  if (st != HIA_OK) return st;
+  if (!y_full || !workspace || j < 0 || j >= steps) return HIA_ERR_BAD_ARG;
+  const int b = block, D = b * (steps + 1);
+  EigWs w;
+  carve(static_cast<unsigned char*>(workspace), n, b, steps, &w);
+  double* Qn = w.Q + (long long)(j + 1) * b * n;
+  const int p = (j + 1) * b;                         // columns of Q so far
+  rowmajor_to_colmajor_kernel<<<(int)(((long long)n * b + 255) / 256), 256, 0, s>>>(y_full, Qn, n, b);
+  HIA_LAUNCH_CHECK();
   const int rows_per_cta = 8192;
-  for (int j = 0; j < steps; ++j) {
-    double* Qj = w.Q + (long long)j * b * n;
-    double* Qn = w.Q + (long long)(j + 1) * b * n;
-    const int p = (j + 1) * b;                       // columns of Q so far
-    st = symm(c, n, ld, w.Vf, Qn, b, s);             // Y = C Q_j, written where Q_{j+1} will live
-    if (st != HIA_OK) return st;
-    (void)Qj;
-    for (int pass = 0; pass < 2; ++pass) {           // CGS2 against all previous blocks
-      HIA_CUDA(cudaMemsetAsync(w.G, 0, (size_t)p * b * 8, s));
-      dim3 grid(p, (n + rows_per_cta - 1) / rows_per_cta);
-      gram_kernel<<<grid, 256, 0, s>>>(w.Q, p, Qn, b, n, rows_per_cta, w.G);
-      HIA_LAUNCH_CHECK();
-      panel_sub_kernel<<<(n + 255) / 256, 256, (size_t)p * b * 8, s>>>(w.Q, p, w.G, b, n, Qn);
-      HIA_LAUNCH_CHECK();
-      place_block_kernel<<<(p * b + 255) / 256, 256, 0, s>>>(w.G, p, b, w.H, D, 0, j * b, pass);
-      HIA_LAUNCH_CHECK();
-    }
-    // CholQR2: Y = Q_{j+1} (R2 R1)
-    st = cholqr(Qn, n, b, w, w.R1, nullptr, s);
-    if (st != HIA_OK) return st;
-    st = cholqr(Qn, n, b, w, w.R2, w.Vf, s);
-    if (st != HIA_OK) return st;
-    small_matmul_kernel<<<1, 32, 0, s>>>(w.R2, w.R1, b, w.Rt);
+  for (int pass = 0; pass < 2; ++pass) {             // CGS2 against all previous blocks
+    HIA_CUDA(cudaMemsetAsync(w.G, 0, (size_t)p * b * 8, s));
+    dim3 grid(p, (n + rows_per_cta - 1) / rows_per_cta);
+    gram_kernel<<<grid, 256, 0, s>>>(w.Q, p, Qn, b, n, rows_per_cta, w.G);
     HIA_LAUNCH_CHECK();
-    place_block_kernel<<<(b * b + 255) / 256, 256, 0, s>>>(w.Rt, b, b, w.H, D, (j + 1) * b, j * b, 0);
+    panel_sub_kernel<<<(n + 255) / 256, 256, (size_t)p * b * 8, s>>>(w.Q, p, w.G, b, n, Qn);
+    HIA_LAUNCH_CHECK();
+    place_block_kernel<<<(p * b + 255) / 256, 256, 0, s>>>(w.G, p, b, w.H, D, 0, j * b, pass);
     HIA_LAUNCH_CHECK();
   }
-  // ---- Rayleigh-Ritz on the leading dim x dim part (the last block has no column in H)
-  const int dim = steps * b;
+  st = cholqr(Qn, n, b, w, w.R1, nullptr, s);        // CholQR2: Y = Q_{j+1} (R2 R1)
+  if (st != HIA_OK) return st;
+  st = cholqr(Qn, n, b, w, w.R2, w.Vf, s);
+  if (st != HIA_OK) return st;
+  small_matmul_kernel<<<1, 32, 0, s>>>(w.R2, w.R1, b, w.Rt);
+  HIA_LAUNCH_CHECK();
+  place_block_kernel<<<(b * b + 255) / 256, 256, 0, s>>>(w.Rt, b, b, w.H, D, (j + 1) * b, j * b, 0);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
+// ---- Rayleigh-Ritz: eigvals[k], eigvecs[k][n]; the fp32 panel becomes [U, 0] for the residual pass
+HIA_API int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t k, double* eigvals, float* eigvecs,
+                         void* workspace, void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  int st = check_shape(n, block, steps);
+  if (st != HIA_OK) return st;
+  if (!eigvals || !eigvecs || !workspace || k <= 0 || k > block) return HIA_ERR_BAD_ARG;
+  const int b = block, D = b * (steps + 1), dim = steps * b;
+  EigWs w;
+  carve(static_cast<unsigned char*>(workspace), n, b, steps, &w);
   jacobi_kernel<<<1, 1024, 0, s>>>(w.H, D, dim, w.JA, w.JV, w.lam, w.order, 15);
   HIA_LAUNCH_CHECK();
   ritz_kernel<<<(n + 255) / 256, 256, 0, s>>>(w.Q, n, dim, w.JV, w.order, w.lam, k, w.U, w.Vf, eigvals);
   HIA_LAUNCH_CHECK();
   HIA_CUDA(cudaMemcpyAsync(eigvecs, w.Vf, (size_t)n * k * 4, cudaMemcpyDeviceToDevice, s));
-  // ---- true residuals ||C u - lambda u||
   if (k < b) HIA_CUDA(cudaMemsetAsync(w.Vf + (long long)k * n, 0, (size_t)(b - k) * n * 4, s));
-  st = symm(c, n, ld, w.Vf, w.Y, b, s);
+  return HIA_OK;
+}
+
+// ---- residuals ||C u - lambda u|| from y_full = C * [U, 0] (n x block, row-major)
+HIA_API int hia_eig_resid(int32_t n, int32_t block, int32_t steps, int32_t k, const double* y_full,
+                          const double* eigvals, double* resid, void* workspace, void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  int st = check_shape(n, block, steps);
   if (st != HIA_OK) return st;
-  HIA_CUDA(cudaMemsetAsync(w.resid2, 0, (size_t)b * 8, s));
+  if (!y_full || !eigvals || !resid || !workspace || k <= 0 || k > block) return HIA_ERR_BAD_ARG;
+  EigWs w;
+  carve(static_cast<unsigned char*>(workspace), n, block, steps, &w);
+  rowmajor_to_colmajor_kernel<<<(int)(((long long)n * block + 255) / 256), 256, 0, s>>>(y_full, w.Y, n, block);
+  HIA_LAUNCH_CHECK();
+  HIA_CUDA(cudaMemsetAsync(w.resid2, 0, (size_t)block * 8, s));
   resid_kernel<<<dim3(64, k), 256, 0, s>>>(w.Y, w.U, eigvals, n, k, w.resid2);
   HIA_LAUNCH_CHECK();
   sqrt_kernel<<<1, 32, 0, s>>>(w.resid2, k);
   HIA_LAUNCH_CHECK();
   HIA_CUDA(cudaMemcpyAsync(resid, w.resid2, (size_t)k * 8, cudaMemcpyDeviceToDevice, s));
   return HIA_OK;
+}
+
+// ---- single-device driver: all phases on one stream, no host round trip
+HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block, int32_t steps,
+                         uint64_t seed, const float* init_vecs, int32_t n_init, double* eigvals,
+                         float* eigvecs, double* resid, void* workspace, int64_t workspace_bytes,
+                         void* stream) {
+  using namespace hia;
+  if (!c || !eigvals || !eigvecs || !resid || !workspace || ld < n || k <= 0) return HIA_ERR_BAD_ARG;
+  if (k > block) return HIA_ERR_BAD_ARG;
+  int st = hia_eig_begin(n, block, steps, seed, init_vecs, n_init, workspace, workspace_bytes, stream);
+  if (st != HIA_OK) return st;
+  EigWs w;
+  carve(static_cast<unsigned char*>(workspace), n, block, steps, &w);
+  double* ystage = w.Y;                               // n x block staging (row-major)
+  for (int j = 0; j < steps; ++j) {
+    st = hia_eig_symm_rows(c, n, n, ld, block, steps, workspace, ystage, stream);
+    if (st != HIA_OK) return st;
+    st = hia_eig_absorb(n, block, steps, j, ystage, workspace, stream);
+    if (st != HIA_OK) return st;
+  }
+  st = hia_eig_ritz(n, block, steps, k, eigvals, eigvecs, workspace, stream);
+  if (st != HIA_OK) return st;
+  // the residual pass needs a second staging buffer: w.Y is the transposed target of hia_eig_resid
+  double* ystage2 = w.Q + (long long)steps * block * n;   // Q_{steps} is no longer needed
+  st = hia_eig_symm_rows(c, n, n, ld, block, steps, workspace, ystage2, stream);
+  if (st != HIA_OK) return st;
+  return hia_eig_resid(n, block, steps, k, ystage2, eigvals, resid, workspace, stream);
 }

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                    const TileCoord* __restrict__ tiles, int num_tiles, int m, int num_k_blocks,
                    int kb_per_chunk, float* __restrict__ out, long long ld_out, int flavour,
-                   unsigned int* __restrict__ sync_ctr, int sync_every) {
+                   unsigned int* __restrict__ sync_ctr, int sync_every, int row0, int row_end,
+                   int symmetric) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -279,8 +280,9 @@ syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 #pragma unroll
       for (int cg = 0; cg < BN / 64; ++cg) {
         const int gc_base = n0 + cg * 32;
-        // skip column groups entirely below the diagonal for this warp's rows / out of range
-        if (gc_base + 31 >= gr_base && gr_base < m && gc_base < m) {
+        // symmetric: skip column groups entirely below the diagonal for this warp's rows
+        const bool needed = symmetric ? (gc_base + 31 >= gr_base) : true;
+        if (needed && gr_base < m && gc_base < m) {
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -290,21 +292,24 @@ syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             f[j] = (flavour == HIA_SIM_COSINE_DISTANCE) ? (1.f - c) : c;
           }
           const int gr = gr_base + lane;
-          // mirrored store out[gc][gr] (lanes = consecutive gr -> coalesced)
+          if (symmetric) {
+            // mirrored store out[gc][gr] (lanes = consecutive gr -> coalesced)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int gc = gc_base + j;
-            if (gr < m && gc < m && gc > gr) out[(long long)gc * ld_out + gr] = f[j];
+            for (int j = 0; j < 32; ++j) {
+              const int gc = gc_base + j;
+              if (gr < m && gc < m && gc > gr) out[(long long)gc * ld_out + gr] = f[j];
+            }
           }
-          // direct store out[gr][gc] through a 32x32 shared transpose (coalesced rows)
+          // direct store out[gr][gc] through a 32x32 shared transpose (coalesced rows);
+          // row-block mode: every column, rows relative to the block's first row
 #pragma unroll
           for (int j = 0; j < 32; ++j) trans[lane * TRANS_PAD + j] = f[j];
           __syncwarp();
 #pragma unroll 4
           for (int i = 0; i < 32; ++i) {
             const int r = gr_base + i, gc = gc_base + lane;
-            if (r < m && gc < m && gc >= r)
-              out[(long long)r * ld_out + gc] = (gc == r) ? diag_val : trans[i * TRANS_PAD + lane];
+            if (r < row_end && gc < m && (gc >= r || !symmetric))
+              out[(long long)(r - row0) * ld_out + gc] = (gc == r) ? diag_val : trans[i * TRANS_PAD + lane];
           }
           __syncwarp();
         }
@@ -472,6 +477,10 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
                            int64_t ld_out, int flavour, int precision, int32_t band_lo,
                            int32_t band_hi, int32_t k_chunk, void* workspace,
                            int64_t workspace_bytes, void* stream_, int phases);
+static int launch_gemm(float* hi, float* lo, int plane_rows, int n_valid, int kpad, int row0, int rows,
+                       int symmetric, int band_lo, int band_hi, float* out, int64_t ld_out, int flavour,
+                       int k_chunk, hia::TileCoord* d_tiles, unsigned int* sync_ctr, int64_t n_sync,
+                       cudaStream_t stream);
 
 HIA_API int hia_similarity(const float* x, int32_t m, int32_t k, int64_t ld_x, float* out,
                            int64_t ld_out, int flavour, int precision, int32_t band_lo,
@@ -527,10 +536,30 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
   }
   if (!(phases & 2)) return HIA_OK;
 
+  return launch_gemm(hi, lo, m, m, kpad, 0, m, 1, band_lo, band_hi, out, ld_out, flavour, k_chunk,
+                     d_tiles, reinterpret_cast<unsigned int*>(ws + off_sync), sync_counters(m, k), stream);
+}
+
+// Tiles + tensor maps + launch. plane_rows = rows the planes hold (>= n_valid; extra rows must be
+// zero), n_valid = true matrix size, [row0, row0 + rows) = the output rows to compute.
+static int launch_gemm(float* hi, float* lo, int plane_rows, int n_valid, int kpad, int row0, int rows,
+                       int symmetric, int band_lo, int band_hi, float* out, int64_t ld_out, int flavour,
+                       int k_chunk, hia::TileCoord* d_tiles, unsigned int* sync_ctr, int64_t n_sync,
+                       cudaStream_t stream) {
+  using namespace hia;
+  const int m = n_valid;
   const int max_tiles = ((m + BM - 1) / BM) * ((m + BN - 1) / BN);
   TileCoord* h_tiles = static_cast<TileCoord*>(malloc((size_t)max_tiles * sizeof(TileCoord)));
   if (!h_tiles) return HIA_ERR_BAD_ARG;
-  const int num_tiles = build_tiles(m, band_lo, band_hi, h_tiles);
+  int num_tiles = 0;
+  if (symmetric) {
+    num_tiles = build_tiles(m, band_lo, band_hi, h_tiles);
+  } else {
+    const int mi0 = row0 / BM, mi1 = (min(row0 + rows, m) + BM - 1) / BM, nt = (m + BN - 1) / BN;
+    for (int sn = 0; sn < nt; sn += 8)                     // 8-column-tile super blocks for L2 reuse
+      for (int mi = mi0; mi < mi1; ++mi)
+        for (int nj = sn; nj < min(sn + 8, nt); ++nj) { h_tiles[num_tiles].m_blk = mi; h_tiles[num_tiles].n_blk = nj; ++num_tiles; }
+  }
   if (num_tiles == 0) { free(h_tiles); return HIA_OK; }
   // pageable H2D: the runtime stages the data before returning, so freeing right after is safe
   cudaError_t ce = cudaMemcpyAsync(d_tiles, h_tiles, (size_t)num_tiles * sizeof(TileCoord),
@@ -539,9 +568,9 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
   HIA_CUDA(ce);
 
   CUtensorMap map_hi, map_lo;
-  int st = make_plane_map(&map_hi, hi, m, kpad);
+  int st = make_plane_map(&map_hi, hi, plane_rows, kpad);
   if (st != HIA_OK) return st;
-  st = make_plane_map(&map_lo, lo, m, kpad);
+  st = make_plane_map(&map_lo, lo, plane_rows, kpad);
   if (st != HIA_OK) return st;
 
   const int num_k_blocks = kpad / BK;
@@ -549,13 +578,55 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
   int kb_per_chunk = max(1, k_chunk / BK);
   HIA_CUDA(cudaFuncSetAttribute(syrk_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int grid = min(num_tiles, kNumSMs);
-  unsigned int* sync_ctr = reinterpret_cast<unsigned int*>(ws + off_sync);
   static const int sync_every = getenv("HIA_SYRK_SYNC") ? atoi(getenv("HIA_SYRK_SYNC")) : kSyncEvery;
-  HIA_CUDA(cudaMemsetAsync(sync_ctr, 0, (size_t)sync_counters(m, k) * 4, stream));
+  HIA_CUDA(cudaMemsetAsync(sync_ctr, 0, (size_t)n_sync * 4, stream));
   syrk_tf32x3_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_hi, map_lo, d_tiles, num_tiles, m,
                                                                 num_k_blocks, kb_per_chunk, out, ld_out,
                                                                 flavour, sync_ctr,
-                                                                (sync_every >= kSyncEvery) ? sync_every : 0);
+                                                                (sync_every >= kSyncEvery) ? sync_every : 0,
+                                                                row0, min(row0 + rows, m), symmetric);
   HIA_LAUNCH_CHECK();
   return HIA_OK;
+}
+
+// ------------------------------------------------------------------ row-sharded entry points
+// (the genome-wide high-resolution similarity is the one step with an
+//  exchange: every rank prepares the TF32 planes of ITS rows, the planes are all-gathered by the
+//  caller (NCCL), then every rank contracts its row block against all rows.)
+HIA_API int32_t hia_sim_kpad(int32_t k) { return hia::round_up(k, hia::BK); }
+
+HIA_API int hia_sim_prep_rows(const float* x_rows, int32_t rows, int32_t k, int64_t ld_x, int flavour,
+                              float* hi_rows, float* lo_rows, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x_rows || !hi_rows || !lo_rows || rows <= 0 || k <= 0 || ld_x < k) return HIA_ERR_BAD_ARG;
+  row_prep_kernel<<<rows, 256, 0, stream>>>(x_rows, rows, k, ld_x, round_up(k, BK),
+                                            flavour == HIA_SIM_PEARSON ? 1 : 0, hi_rows, lo_rows);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
+HIA_API int64_t hia_sim_gemm_rows_workspace_bytes(int32_t n, int32_t k) {
+  if (n <= 0 || k <= 0) return 0;
+  const int64_t ntiles = (int64_t)((n + hia::BM - 1) / hia::BM) * ((n + hia::BN - 1) / hia::BN);
+  return (ntiles * (int64_t)sizeof(hia::TileCoord) + 1023) / 1024 * 1024 + sync_counters(n, k) * 4 + 1024;
+}
+
+HIA_API int hia_sim_gemm_rows(float* hi, float* lo, int32_t plane_rows, int32_t n, int32_t k, int32_t row0,
+                              int32_t rows, float* out_rows, int64_t ld_out, int flavour, int32_t k_chunk,
+                              void* workspace, int64_t workspace_bytes, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!hi || !lo || !out_rows || !workspace || n <= 0 || k <= 0 || plane_rows < n || rows <= 0 ||
+      row0 < 0 || ld_out < n)
+    return HIA_ERR_BAD_ARG;
+  if (row0 % BM) return HIA_ERR_ALIGN;                    // row blocks start on a 128-row tile boundary
+  if (!aligned16(hi) || !aligned16(lo) || !aligned16(workspace)) return HIA_ERR_ALIGN;
+  if (workspace_bytes < hia_sim_gemm_rows_workspace_bytes(n, k)) return HIA_ERR_WORKSPACE;
+  const int64_t ntiles = (int64_t)((n + BM - 1) / BM) * ((n + BN - 1) / BN);
+  const int64_t tiles_al = (ntiles * (int64_t)sizeof(TileCoord) + 1023) / 1024 * 1024;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  return launch_gemm(hi, lo, plane_rows, n, round_up(k, BK), row0, rows, 0, 0, -1, out_rows, ld_out, flavour,
+                     k_chunk, reinterpret_cast<TileCoord*>(ws), reinterpret_cast<unsigned int*>(ws + tiles_al),
+                     sync_counters(n, k), stream);
 }

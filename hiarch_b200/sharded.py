@@ -1,0 +1,125 @@
+"""Row-sharded genome-wide similarity + top-k eigenvectors across the GPUs of one box.
+
+The single exchange step of the hot path (BASELINE.json config C5:
+123 541 bins = 61 GB per fp32 map, too large for one pass on one GPU). Rank r owns the rows
+[r * per, (r + 1) * per) of the normalised map, `per` a multiple of the 128-row MMA tile:
+
+  1. every rank builds the unit-norm TF32 hi/lo planes of ITS rows            (hia_sim_prep_rows)
+  2. NCCL all-gather of the planes over NVLink (torch.distributed)            -> full planes
+  3. every rank contracts its row block against all rows on tcgen05           (hia_sim_gemm_rows)
+  4. eigenvectors: block Lanczos where the only pass over the matrix,
+     Y[rows] = C[rows, :] V, is local and the n x 8 fp64 panel is all-gathered per step;
+     the tiny orthogonalisation / Rayleigh-Ritz is replicated (bit-identical on all ranks).
+
+Round-1 version: each rank computes its FULL row block (no symmetry saving -> balanced without a
+row permutation); the planes are gathered whole before the contraction (not chunk-pipelined).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+
+
+def rows_per_rank(n, world):
+    per = (n + world - 1) // world
+    return (per + 127) // 128 * 128
+
+
+class ShardedSimilarity:
+    def __init__(self, n, k, flavour=ops.SIM_PEARSON, group=None, device=None):
+        self.lib = _lib.load()
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n, self.k, self.flavour = n, k, flavour
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.per = rows_per_rank(n, self.world)
+        self.n_pad = self.per * self.world
+        self.row0 = self.rank * self.per
+        self.rows = max(0, min(n, self.row0 + self.per) - self.row0)
+        self.kpad = self.lib.hia_sim_kpad(k)
+        # full planes (all-gather targets); rows >= n stay zero
+        self.hi = torch.zeros((self.n_pad, self.kpad), dtype=torch.float32, device=self.device)
+        self.lo = torch.zeros((self.n_pad, self.kpad), dtype=torch.float32, device=self.device)
+        self.own_hi = torch.zeros((self.per, self.kpad), dtype=torch.float32, device=self.device)
+        self.own_lo = torch.zeros((self.per, self.kpad), dtype=torch.float32, device=self.device)
+        self.ws = torch.empty(self.lib.hia_sim_gemm_rows_workspace_bytes(n, k), dtype=torch.uint8,
+                              device=self.device)
+
+    def run(self, x_rows, out_rows=None, k_chunk=0):
+        """x_rows: this rank's rows of the map [rows, k] (fp32, stride(1) == 1).
+        Returns out_rows [rows, n] = similarity of the own rows against all rows."""
+        lib = self.lib
+        assert x_rows.shape == (self.rows, self.k) and x_rows.dtype == torch.float32
+        if self.rows > 0:
+            st = lib.hia_sim_prep_rows(x_rows.data_ptr(), self.rows, self.k, x_rows.stride(0), self.flavour,
+                                       self.own_hi.data_ptr(), self.own_lo.data_ptr(), ops._stream())
+            _lib.check(st, "hia_sim_prep_rows")
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.hi.view(-1), self.own_hi.view(-1), group=self.group)
+            dist.all_gather_into_tensor(self.lo.view(-1), self.own_lo.view(-1), group=self.group)
+        else:
+            self.hi.copy_(self.own_hi)
+            self.lo.copy_(self.own_lo)
+        if out_rows is None:
+            out_rows = torch.empty((max(self.rows, 1), ops.padded_ld(self.n)), dtype=torch.float32,
+                                   device=self.device)[:self.rows, :self.n]
+        if self.rows > 0:
+            st = lib.hia_sim_gemm_rows(self.hi.data_ptr(), self.lo.data_ptr(), self.n_pad, self.n, self.k,
+                                       self.row0, self.rows, out_rows.data_ptr(), out_rows.stride(0),
+                                       self.flavour, k_chunk, self.ws.data_ptr(), self.ws.numel(),
+                                       ops._stream())
+            _lib.check(st, "hia_sim_gemm_rows")
+        return out_rows
+
+
+def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, max_restarts=8, seed=0, group=None):
+    """Top-k eigenpairs of the symmetric n x n matrix whose rows [row0, row0 + rows) this rank
+    holds in `c_rows` (row layout of ShardedSimilarity). Returns (eigvals [k] fp64 device,
+    eigvecs [n, k] fp32 device, info) -- identical on every rank."""
+    lib = _lib.load()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    per = rows_per_rank(n, world)
+    row0 = rank * per
+    rows = max(0, min(n, row0 + per) - row0)
+    assert c_rows.shape[0] == rows and c_rows.shape[1] == n
+    dev = c_rows.device
+    steps = max(1, min(steps, n // block - 1, 272 // block - 1))
+    ws = torch.empty(lib.hia_topk_eig_workspace_bytes(n, block, steps), dtype=torch.uint8, device=dev)
+    y_rows = torch.zeros((per, block), dtype=torch.float64, device=dev)
+    y_full = torch.zeros((per * world, block), dtype=torch.float64, device=dev)
+    eigvals = torch.empty(k, dtype=torch.float64, device=dev)
+    eigvecs = torch.empty((k, n), dtype=torch.float32, device=dev)
+    resid = torch.empty(k, dtype=torch.float64, device=dev)
+    s = ops._stream
+
+    def matvec():
+        if rows > 0:
+            _lib.check(lib.hia_eig_symm_rows(c_rows.data_ptr(), rows, n, c_rows.stride(0), block, steps,
+                                             ws.data_ptr(), y_rows.data_ptr(), s()), "hia_eig_symm_rows")
+        if world > 1:
+            dist.all_gather_into_tensor(y_full.view(-1), y_rows.view(-1), group=group)
+        else:
+            y_full.copy_(y_rows)
+
+    init, n_init, info = None, 0, []
+    for it in range(max_restarts):
+        _lib.check(lib.hia_eig_begin(n, block, steps, seed + it, ops._ptr(init), n_init, ws.data_ptr(),
+                                     ws.numel(), s()), "hia_eig_begin")
+        for j in range(steps):
+            matvec()
+            _lib.check(lib.hia_eig_absorb(n, block, steps, j, y_full.data_ptr(), ws.data_ptr(), s()),
+                       "hia_eig_absorb")
+        _lib.check(lib.hia_eig_ritz(n, block, steps, k, eigvals.data_ptr(), eigvecs.data_ptr(),
+                                    ws.data_ptr(), s()), "hia_eig_ritz")
+        matvec()
+        _lib.check(lib.hia_eig_resid(n, block, steps, k, y_full.data_ptr(), eigvals.data_ptr(),
+                                     resid.data_ptr(), ws.data_ptr(), s()), "hia_eig_resid")
+        r, lam = resid.cpu().numpy(), eigvals.cpu().numpy()
+        info.append((float(r.max()), float(abs(lam[0]))))
+        if np.all(r <= tol * max(abs(lam[0]), 1e-300)):
+            break
+        init, n_init = eigvecs.clone(), k
+    return eigvals, eigvecs.t(), info

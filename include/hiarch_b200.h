@@ -241,6 +241,19 @@ int hia_gf_pool_scores(const float* x, int64_t ld, const int32_t* pairs8, int32_
                        const double* tmpl_intra, const double* tmpl_inter, double* pooled,
                        double* isym, double* xs, double* scores, void* stream);
 
+/* Row-sharded similarity (the one exchange step of the path): every rank
+ * prepares the TF32 hi/lo planes of ITS rows (hia_sim_prep_rows; planes are row-major with
+ * hia_sim_kpad(k) columns), the caller all-gathers the planes (NCCL), then every rank contracts
+ * its row block [row0, row0 + rows) against all rows (hia_sim_gemm_rows; row0 % 128 == 0).
+ * plane_rows >= n rows are addressable in hi/lo (rows >= n must be zero). out_rows: rows x n. */
+int32_t hia_sim_kpad(int32_t k);
+int hia_sim_prep_rows(const float* x_rows, int32_t rows, int32_t k, int64_t ld_x, int flavour,
+                      float* hi_rows, float* lo_rows, void* stream);
+int64_t hia_sim_gemm_rows_workspace_bytes(int32_t n, int32_t k);
+int hia_sim_gemm_rows(float* hi, float* lo, int32_t plane_rows, int32_t n, int32_t k, int32_t row0,
+                      int32_t rows, float* out_rows, int64_t ld_out, int flavour, int32_t k_chunk,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------ */
 /* a9  top-k eigenvectors of a dense symmetric fp32 matrix (largest algebraic).          */
 /* No reference implementation exists (the reference never decomposes anything); the     */
@@ -258,6 +271,25 @@ int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block
                  uint64_t seed, const float* init_vecs, int32_t n_init, double* eigvals,
                  float* eigvecs, double* resid, void* workspace, int64_t workspace_bytes,
                  void* stream);
+
+/* The phases of hia_topk_eig as separate calls, so that a row-sharded caller can all-gather the
+ * panel between the pass over the matrix and the (replicated, tiny) orthogonalisation:
+ *   hia_eig_begin      start block (restart vectors + random), orthonormalised
+ *   hia_eig_symm_rows  y_rows[rows x block] (row-major fp64) = C[rows, :] * current fp32 panel
+ *   hia_eig_absorb     step j: y_full[n x block] (row-major, all rows) -> H[:, j], Q_{j+1}
+ *   hia_eig_ritz       Jacobi on the projected matrix -> eigvals[k], eigvecs[k][n]; panel = [U, 0]
+ *   hia_eig_resid      y_full = C [U, 0] -> resid[k] = ||C u - lambda u||
+ * All take the same (n, block, steps) and the workspace of hia_topk_eig_workspace_bytes. */
+int hia_eig_begin(int32_t n, int32_t block, int32_t steps, uint64_t seed, const float* init_vecs,
+                  int32_t n_init, void* workspace, int64_t workspace_bytes, void* stream);
+int hia_eig_symm_rows(const float* c_rows, int32_t rows, int32_t n, int64_t ld, int32_t block,
+                      int32_t steps, void* workspace, double* y_rows, void* stream);
+int hia_eig_absorb(int32_t n, int32_t block, int32_t steps, int32_t j, const double* y_full,
+                   void* workspace, void* stream);
+int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t k, double* eigvals, float* eigvecs,
+                 void* workspace, void* stream);
+int hia_eig_resid(int32_t n, int32_t block, int32_t steps, int32_t k, const double* y_full,
+                  const double* eigvals, double* resid, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

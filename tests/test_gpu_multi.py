@@ -1,0 +1,34 @@
+"""GPU, needs >= 2 devices (gpurun --gpus 2): the row-sharded similarity + eigen path against the
+single-GPU result. Skipped on a 1-GPU box."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.mark.parametrize("n", [1500, 3333])
+def test_row_sharded_similarity_and_eigen_match_single_gpu(n):
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2 if ngpu < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29631",
+           os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(n)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    recs = [json.loads(m) for m in re.findall(r"REC (\{.*\})", out.stdout)]
+    assert len(recs) == world
+    for r in recs:
+        assert r["sim_err"] <= 2e-6, r                  # same kernel, same planes: tiny differences
+        assert r["eig_rel"] <= 1e-6, r
+        assert min(r["cos"]) >= 0.9999, r
+    covered = sorted((r["rows"][0], r["rows"][1]) for r in recs)
+    assert sum(c[1] for c in covered) == n

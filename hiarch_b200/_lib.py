@@ -28,6 +28,10 @@ PROTOTYPES = {
                                 c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hia_oe_apply": (c_int, [c_vp, c_vp, c_i32, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_int,
                              c_vp]),
+    "hia_oe_expected_pass_rows": (c_int, [c_vp, c_i32, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp,
+                                          c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hia_oe_apply_rows": (c_int, [c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp,
+                                  c_vp, c_int, c_vp]),
     "hia_log_map": (c_int, [c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp]),
     "hia_similarity_workspace_bytes": (c_i64, [c_i32, c_i32, c_int]),
     "hia_similarity": (c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_int, c_int, c_i32, c_i32,

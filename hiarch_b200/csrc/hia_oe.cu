@@ -32,7 +32,9 @@ constexpr int kDiagRowGroups = 32;            // 4-row groups per CTA  (128 rows
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kDiagThreads)
 intra_diag_kernel(const float* __restrict__ map, long long ld, const int* __restrict__ chr_start,
-                  double* __restrict__ diag_sum, float* __restrict__ diag_minpos, int row_chunks) {
+                  double* __restrict__ diag_sum, float* __restrict__ diag_minpos, int row_chunks,
+                  int row0, int row_end) {
+  // `map` points at global row `row0`; only rows [row0, row_end) are visited (row sharding)
   const int c = blockIdx.y;
   const int s = chr_start[c], e = chr_start[c + 1] - 1;   // inclusive bin range
   const int n = e - s + 1;
@@ -60,9 +62,9 @@ intra_diag_kernel(const float* __restrict__ map, long long ld, const int* __rest
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
       const int gr = 4 * rho + rr;
-      if (gr < s || gr > e) continue;
+      if (gr < s || gr > e || gr < row0 || gr >= row_end) continue;
       if (gc0 + 3 < gr) continue;                          // float4 entirely below the diagonal
-      const float4 v = *reinterpret_cast<const float4*>(map + (long long)gr * ld + gc0);
+      const float4 v = *reinterpret_cast<const float4*>(map + (long long)(gr - row0) * ld + gc0);
       const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
@@ -99,15 +101,16 @@ __global__ void __launch_bounds__(kInterThreads)
 inter_block_kernel(const float* __restrict__ map, int n, long long ld,
                    const int* __restrict__ chr_start, int n_chr,
                    const short* __restrict__ bin_chr, double* __restrict__ inter_sum,
-                   unsigned long long* __restrict__ inter_nnz, float* __restrict__ inter_minpos) {
+                   unsigned long long* __restrict__ inter_nnz, float* __restrict__ inter_minpos,
+                   int row0, int row_end) {
   extern __shared__ unsigned char smem_raw[];
   double* s_sum = reinterpret_cast<double*>(smem_raw);
   unsigned long long* s_nnz = reinterpret_cast<unsigned long long*>(s_sum + n_chr);
   float* s_min = reinterpret_cast<float*>(s_nnz + n_chr);
 
-  const int r0 = blockIdx.y * kInterRows;
-  if (r0 >= n) return;
-  const int r1 = min(r0 + kInterRows, n);
+  const int r0 = row0 + blockIdx.y * kInterRows;           // global rows; `map` points at row0
+  if (r0 >= row_end) return;
+  const int r1 = min(r0 + kInterRows, row_end);
   const int cta_c1 = min(n, (int)(blockIdx.x + 1) * kInterCols);      // exclusive
   int a_prev = bin_chr[r0];
   // the inter part of a row starts at chr_start[a + 1], which only grows with the row index
@@ -159,7 +162,7 @@ inter_block_kernel(const float* __restrict__ map, int n, long long ld,
     if (a != a_prev) { flush(a_prev); a_prev = a; }
     const int col_lo = chr_start[a + 1];
     if (active && c0 + 3 >= col_lo) {
-      const float4 v = ld_stream4(map + (long long)r * ld + c0);   // ld % 4 == 0, ld >= n
+      const float4 v = ld_stream4(map + (long long)(r - row0) * ld + c0);   // ld % 4 == 0, ld >= n
       const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -314,7 +317,8 @@ __global__ void __launch_bounds__(256)
 oe_apply_kernel(const float* __restrict__ map, float* __restrict__ out, int n, long long ld,
                 const int* __restrict__ chr_start, int n_chr, const short* __restrict__ bin_chr,
                 const float* __restrict__ inv_expected, const float* __restrict__ inter_inv,
-                const float* __restrict__ min_pos_oe, int flags) {
+                const float* __restrict__ min_pos_oe, int flags, int row0, int row_end) {
+  // map / out point at global row `row0`
   const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c0 >= n) return;
   const bool do_log = flags & HIA_OE_LOG;
@@ -327,10 +331,10 @@ oe_apply_kernel(const float* __restrict__ map, float* __restrict__ out, int n, l
   int cb[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) cb[j] = bin_chr[min(c0 + j, n - 1)];
-  for (int r = blockIdx.y; r < n; r += gridDim.y) {
+  for (int r = row0 + blockIdx.y; r < row_end; r += gridDim.y) {
     const int a = bin_chr[r];
     const int s = chr_start[a];
-    const float* src = map + (long long)r * ld + c0;
+    const float* src = map + (long long)(r - row0) * ld + c0;
     float v[4];
     if (c0 + 3 < n) {
       const float4 t = ld_stream4(src);
@@ -354,7 +358,7 @@ oe_apply_kernel(const float* __restrict__ map, float* __restrict__ out, int n, l
       if (do_log) x = (x > 0.f) ? log1pf(x) : fill;
       v[j] = x;
     }
-    float* dst = out + (long long)r * ld + c0;
+    float* dst = out + (long long)(r - row0) * ld + c0;
     if (c0 + 3 < n) {
       st_stream4(dst, make_float4(v[0], v[1], v[2], v[3]));
     } else {
@@ -413,15 +417,16 @@ HIA_API int hia_log_map(const float* x, float* out, int32_t rows, int32_t cols, 
   return HIA_OK;
 }
 
-HIA_API int hia_oe_expected_pass(const float* map, int32_t n, int64_t ld, const int32_t* chr_start,
-                                 const int32_t* chr_start_host, int32_t n_chr, double* diag_sum,
-                                 float* diag_minpos, double* inter_sum,
-                                 unsigned long long* inter_nnz, float* inter_minpos,
-                                 const int16_t* bin_chr, void* stream_) {
+static int expected_pass_impl(const float* map, int32_t n, int64_t ld, const int32_t* chr_start,
+                              const int32_t* chr_start_host, int32_t n_chr, double* diag_sum,
+                              float* diag_minpos, double* inter_sum, unsigned long long* inter_nnz,
+                              float* inter_minpos, const int16_t* bin_chr, int row0, int rows,
+                              void* stream_) {
   using namespace hia;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!map || !chr_start || !chr_start_host || !diag_sum || !diag_minpos || !inter_sum ||
-      !inter_nnz || !inter_minpos || !bin_chr || n <= 0 || n_chr <= 0 || ld < n)
+      !inter_nnz || !inter_minpos || !bin_chr || n <= 0 || n_chr <= 0 || ld < n || row0 < 0 ||
+      rows < 0 || row0 + rows > n)
     return HIA_ERR_BAD_ARG;
   if (!aligned16(map) || (ld & 3)) return HIA_ERR_ALIGN;
   if (n_chr > 1024) return HIA_ERR_UNSUPPORTED;
@@ -430,6 +435,7 @@ HIA_API int hia_oe_expected_pass(const float* map, int32_t n, int64_t ld, const 
   init_expected_kernel<<<(cnt + 255) / 256, 256, 0, stream>>>(diag_sum, diag_minpos, n, inter_sum,
                                                              inter_nnz, inter_minpos, cc);
   HIA_LAUNCH_CHECK();
+  if (rows == 0) return HIA_OK;
   int max_len = 0;
   for (int c = 0; c < n_chr; ++c) max_len = max(max_len, chr_start_host[c + 1] - chr_start_host[c]);
   if (max_len <= 0) return HIA_ERR_BAD_ARG;
@@ -438,16 +444,40 @@ HIA_API int hia_oe_expected_pass(const float* map, int32_t n, int64_t ld, const 
   const int windows = (max_len + 3 + kDiagWindow - 1) / kDiagWindow;
   dim3 grid_d(windows * row_chunks, n_chr);
   intra_diag_kernel<<<grid_d, kDiagThreads, 0, stream>>>(map, ld, chr_start, diag_sum, diag_minpos,
-                                                         row_chunks);
+                                                         row_chunks, row0, row0 + rows);
   HIA_LAUNCH_CHECK();
   if (n_chr > 1) {
-    dim3 grid_i((n + kInterCols - 1) / kInterCols, (n + kInterRows - 1) / kInterRows);
+    dim3 grid_i((n + kInterCols - 1) / kInterCols, (rows + kInterRows - 1) / kInterRows);
     const size_t sh = (size_t)n_chr * (8 + 8 + 4);
     inter_block_kernel<<<grid_i, kInterThreads, sh, stream>>>(map, n, ld, chr_start, n_chr, bin_chr,
-                                                              inter_sum, inter_nnz, inter_minpos);
+                                                              inter_sum, inter_nnz, inter_minpos,
+                                                              row0, row0 + rows);
     HIA_LAUNCH_CHECK();
   }
   return HIA_OK;
+}
+
+HIA_API int hia_oe_expected_pass(const float* map, int32_t n, int64_t ld, const int32_t* chr_start,
+                                 const int32_t* chr_start_host, int32_t n_chr, double* diag_sum,
+                                 float* diag_minpos, double* inter_sum,
+                                 unsigned long long* inter_nnz, float* inter_minpos,
+                                 const int16_t* bin_chr, void* stream) {
+  return expected_pass_impl(map, n, ld, chr_start, chr_start_host, n_chr, diag_sum, diag_minpos,
+                            inter_sum, inter_nnz, inter_minpos, bin_chr, 0, n, stream);
+}
+
+// Row-sharded variant: `map_rows` holds global rows [row0, row0 + rows) of the n x n map. The
+// outputs are this rank's PARTIAL statistics: the caller sums diag_sum / inter_sum / inter_nnz and
+// takes the min of diag_minpos / inter_minpos over the ranks (two small all-reduces), then runs
+// hia_oe_finalize (replicated) and hia_oe_apply_rows.
+HIA_API int hia_oe_expected_pass_rows(const float* map_rows, int32_t n, int64_t ld, int32_t row0,
+                                      int32_t rows, const int32_t* chr_start,
+                                      const int32_t* chr_start_host, int32_t n_chr, double* diag_sum,
+                                      float* diag_minpos, double* inter_sum,
+                                      unsigned long long* inter_nnz, float* inter_minpos,
+                                      const int16_t* bin_chr, void* stream) {
+  return expected_pass_impl(map_rows, n, ld, chr_start, chr_start_host, n_chr, diag_sum, diag_minpos,
+                            inter_sum, inter_nnz, inter_minpos, bin_chr, row0, rows, stream);
 }
 
 HIA_API int hia_oe_finalize(const double* diag_sum, const float* diag_minpos, const double* inter_sum,
@@ -475,19 +505,37 @@ HIA_API int hia_oe_finalize(const double* diag_sum, const float* diag_minpos, co
   return HIA_OK;
 }
 
-HIA_API int hia_oe_apply(const float* map, float* out, int32_t n, int64_t ld, const int32_t* chr_start,
-                         int32_t n_chr, const int16_t* bin_chr, const float* inv_expected,
-                         const float* inter_inv, const float* min_pos_oe, int flags, void* stream_) {
+static int apply_impl(const float* map, float* out, int32_t n, int64_t ld, const int32_t* chr_start,
+                      int32_t n_chr, const int16_t* bin_chr, const float* inv_expected,
+                      const float* inter_inv, const float* min_pos_oe, int flags, int row0, int rows,
+                      void* stream_) {
   using namespace hia;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!map || !out || !chr_start || !bin_chr || !inv_expected || !inter_inv || !min_pos_oe ||
-      n <= 0 || n_chr <= 0 || ld < n)
+      n <= 0 || n_chr <= 0 || ld < n || row0 < 0 || rows < 0 || row0 + rows > n)
     return HIA_ERR_BAD_ARG;
   if (!aligned16(map) || !aligned16(out) || (ld & 3)) return HIA_ERR_ALIGN;
+  if (rows == 0) return HIA_OK;
   const int threads = 256;
-  dim3 grid((n + threads * 4 - 1) / (threads * 4), min(n, 2048));
+  dim3 grid((n + threads * 4 - 1) / (threads * 4), min(rows, 2048));
   oe_apply_kernel<<<grid, threads, 0, stream>>>(map, out, n, ld, chr_start, n_chr, bin_chr,
-                                                inv_expected, inter_inv, min_pos_oe, flags);
+                                                inv_expected, inter_inv, min_pos_oe, flags, row0,
+                                                row0 + rows);
   HIA_LAUNCH_CHECK();
   return HIA_OK;
+}
+
+HIA_API int hia_oe_apply(const float* map, float* out, int32_t n, int64_t ld, const int32_t* chr_start,
+                         int32_t n_chr, const int16_t* bin_chr, const float* inv_expected,
+                         const float* inter_inv, const float* min_pos_oe, int flags, void* stream) {
+  return apply_impl(map, out, n, ld, chr_start, n_chr, bin_chr, inv_expected, inter_inv, min_pos_oe,
+                    flags, 0, n, stream);
+}
+
+HIA_API int hia_oe_apply_rows(const float* map_rows, float* out_rows, int32_t n, int64_t ld, int32_t row0,
+                              int32_t rows, const int32_t* chr_start, int32_t n_chr,
+                              const int16_t* bin_chr, const float* inv_expected, const float* inter_inv,
+                              const float* min_pos_oe, int flags, void* stream) {
+  return apply_impl(map_rows, out_rows, n, ld, chr_start, n_chr, bin_chr, inv_expected, inter_inv,
+                    min_pos_oe, flags, row0, rows, stream);
 }

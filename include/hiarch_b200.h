@@ -104,6 +104,21 @@ int hia_oe_apply(const float* map, float* out, int32_t n, int64_t ld, const int3
                  int32_t n_chr, const int16_t* bin_chr, const float* inv_expected,
                  const float* inter_inv, const float* min_pos_oe, int flags, void* stream);
 
+/* Row-sharded O/E: a rank that holds global rows [row0, row0 + rows) of the map computes PARTIAL
+ * statistics (sum the diag_sum / inter_sum / inter_nnz arrays and take the element-wise min of
+ * diag_minpos / inter_minpos over the ranks -- two small all-reduces), runs hia_oe_finalize on the
+ * reduced arrays (replicated) and applies to its own rows. The upper-triangle rule (column >=
+ * row) makes the partial sums disjoint. */
+int hia_oe_expected_pass_rows(const float* map_rows, int32_t n, int64_t ld, int32_t row0, int32_t rows,
+                              const int32_t* chr_start, const int32_t* chr_start_host, int32_t n_chr,
+                              double* diag_sum, float* diag_minpos, double* inter_sum,
+                              unsigned long long* inter_nnz, float* inter_minpos,
+                              const int16_t* bin_chr, void* stream);
+int hia_oe_apply_rows(const float* map_rows, float* out_rows, int32_t n, int64_t ld, int32_t row0,
+                      int32_t rows, const int32_t* chr_start, int32_t n_chr, const int16_t* bin_chr,
+                      const float* inv_expected, const float* inter_inv, const float* min_pos_oe,
+                      int flags, void* stream);
+
 /* Stand-alone ArrayHiCMtx.log (new_hic_class.py:2076-2094) for a map that did not come out of
  * hia_oe_apply: x>0 -> ln(x+1); x<=0 -> min over positives of ln(x+1). min_pos_ws: 1 float. */
 int hia_log_map(const float* x, float* out, int32_t rows, int32_t cols, int64_t ld, float* min_pos_ws,

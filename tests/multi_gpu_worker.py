@@ -11,7 +11,8 @@ import torch.distributed as dist
 
 from hiarch_b200 import dist as D
 from hiarch_b200 import ops
-from hiarch_b200.sharded import ShardedSimilarity, topk_eig_rows
+from hiarch_b200.sharded import ShardedSimilarity, topk_eig_rows, obs_d_exp_rows, rows_per_rank
+from hiarch_b200 import synth
 
 
 def main():
@@ -33,7 +34,20 @@ def main():
     w2, v2, info = topk_eig_rows(mine, n, k=3)
     cos = [float(abs((v1[:, j].double() @ v2[:, j].double())) / (v1[:, j].double().norm() * v2[:, j].double().norm()))
            for j in range(3)]
-    rec = {"rank": rank, "world": world, "rows": [sh.row0, sh.rows], "sim_err": sim_err,
+    # row-sharded O/E + log against the single-GPU passes, on a multi-chromosome count map
+    lens = [n // 2, n // 3, n - n // 2 - n // 3]
+    lam, seps = synth.rate_matrix(lens, seed=3)
+    up = synth.sample_counts(lam, seed=3)
+    counts = ops.alloc_map(n)
+    counts.copy_(torch.from_numpy(up + np.triu(up, 1).T).to("cuda", torch.float32))
+    layout = ops.GenomeLayout(seps)
+    ref_oe, _ = ops.obs_d_exp(counts, layout, 100000, log=True)
+    per = rows_per_rank(n, world)
+    r0 = rank * per
+    nr = max(0, min(n, r0 + per) - r0)
+    got_oe, _ = obs_d_exp_rows(counts[r0:r0 + nr], layout, 100000, r0)
+    oe_err = float((got_oe - ref_oe[r0:r0 + nr]).abs().max()) if nr else 0.0
+    rec = {"rank": rank, "world": world, "rows": [sh.row0, sh.rows], "sim_err": sim_err, "oe_err": oe_err,
            "eig_rel": float(((w1 - w2).abs() / w1.abs()).max()), "cos": cos, "info": info}
     D.barrier()
     sys.stdout.write("REC " + json.dumps(rec) + "\n")

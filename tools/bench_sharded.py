@@ -41,19 +41,104 @@ def make_rows(n, row0, rows, seed, device, chunk=2048):
     return x
 
 
+def _hash_uniform(key, salt):
+    """Counter-based uniform in (0, 1) from an int64 key (splitmix-like; wraps mod 2^64)."""
+    z = key + salt
+    z = (z ^ (z >> 30)) * -4658895280553007687          # 0xBF58476D1CE4E5B9 as int64
+    z = (z ^ (z >> 27)) * -7723592293110705685          # 0x94D049BB133111EB
+    z = z ^ (z >> 31)
+    return ((z >> 11) & ((1 << 53) - 1)).double() * (1.0 / (1 << 53)) * (1 - 2e-16) + 1e-16
+
+
+def make_count_rows(lens, row0, rows, seed, device, lam_inter=0.6, chunk=1024):
+    """rows x n block of a SYMMETRIC synthetic count map (SURVEY 8d generator): the sample of cell
+    (i, j) is a deterministic function of (min(i,j), max(i,j), seed), so every rank generates a
+    consistent slice without any rank holding the whole map. Poisson by inverse CDF (lambda <= 12)
+    or the rounded normal approximation (lambda > 12)."""
+    n = int(sum(lens))
+    seps = synth.chr_seps_from_lens(lens)
+    rng = np.random.default_rng(seed)
+    comps = np.stack([np.sqrt(b) * np.concatenate([synth.compartment_track(L, rng, max(3, L // (40 * (m + 1))))
+                                                   for L in lens]) for m, b in enumerate(synth.COMPONENT_BETAS)], axis=1)
+    comp = torch.from_numpy(comps).to(device=device, dtype=torch.float32)
+    bin_chr = torch.from_numpy(np.concatenate([np.full(L, c, dtype=np.int64) for c, L in enumerate(lens)])).to(device)
+    x = torch.empty((rows, ops.padded_ld(n)), dtype=torch.float32, device=device)[:, :n]
+    jj = torch.arange(n, device=device, dtype=torch.int64)
+    for r in range(0, rows, chunk):
+        r1 = min(rows, r + chunk)
+        ii = torch.arange(row0 + r, row0 + r1, device=device, dtype=torch.int64)
+        lo_ = torch.minimum(ii[:, None], jj[None, :])
+        hi_ = torch.maximum(ii[:, None], jj[None, :])
+        key = lo_ * n + hi_
+        cc = 1.0 + comp[row0 + r:row0 + r1] @ comp.T
+        same = bin_chr[row0 + r:row0 + r1, None] == bin_chr[None, :]
+        d = (hi_ - lo_).float()
+        lam = torch.where(same, synth.A_INTRA * (d + 1.0) ** (-synth.ALPHA) * cc, lam_inter * cc).double()
+        u = _hash_uniform(key, seed * 7919 + 1)
+        # small lambda: inverse CDF
+        k = torch.zeros_like(lam)
+        p = torch.exp(-lam)
+        cdf = p.clone()
+        for t in range(1, 40):
+            k += (u > cdf).double()
+            p = p * lam / t
+            cdf += p
+        # large lambda: normal approximation with a second hashed uniform (Box-Muller)
+        u2 = _hash_uniform(key, seed * 7919 + 2)
+        z = torch.sqrt(-2.0 * torch.log(u)) * torch.cos(2 * np.pi * u2)
+        big = torch.clamp(torch.round(lam + torch.sqrt(lam) * z), min=0.0)
+        x[r:r1] = torch.where(lam > 12.0, big, k).float()
+    return x, seps
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--from-counts", action="store_true",
+                    help="start from synthetic COUNT rows and run the row-sharded O/E+log first")
     ap.add_argument("--res", type=int, default=25000)
     ap.add_argument("--bins", type=int, default=0, help="override the bin count")
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--no-eig", action="store_true")
     args = ap.parse_args()
-    rank, local, world = D.init("nccl")
+    # a rank that dies must not leave the others in a 10-minute NCCL watchdog wait
+    os.environ.setdefault("TORCH_NCCL_HEARTBEAT_TIMEOUT_SEC", "120")
+    import datetime
+    rank, local, world = D.env_world()
     torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local),
+                                timeout=datetime.timedelta(seconds=120))
     dev = torch.device("cuda", local)
-    n = args.bins or sum(nb for _, nb in synth.hg38_bins(args.res))
+    lens = [nb for _, nb in synth.hg38_bins(args.res)]
+    n = args.bins or sum(lens)
+    oe_ms = []
+    from hiarch_b200.sharded import rows_per_rank
+    per = rows_per_rank(n, world)
+    my_row0 = rank * per
+    my_rows = max(0, min(n, my_row0 + per) - my_row0)
+    if args.from_counts:
+        from hiarch_b200.sharded import obs_d_exp_rows
+        assert not args.bins
+        # generate + normalise BEFORE the 2 x (n_pad x kpad) plane buffers exist (memory headroom)
+        counts, seps = make_count_rows(lens, my_row0, my_rows, 5, dev)
+        torch.cuda.empty_cache()
+        layout = ops.GenomeLayout(seps, dev)
+        layout.oe_tables(args.res)
+        x = torch.empty((max(my_rows, 1), counts.stride(0)), dtype=torch.float32, device=dev)[:my_rows, :n]
+        for it in range(2):
+            D.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            obs_d_exp_rows(counts, layout, args.res, my_row0, log=True, out_rows=x)
+            b.record()
+            D.barrier()
+            oe_ms.append(D.max_over_ranks(a.elapsed_time(b)))
+        # symmetry spot check of the generator + O/E across ranks: O/E[i, j] on this rank vs [j, i]
+        del counts
+        torch.cuda.empty_cache()
+    else:
+        x = make_rows(n, my_row0, my_rows, 5, dev)
     sh = ShardedSimilarity(n, n, flavour=ops.SIM_PEARSON)
-    x = make_rows(n, sh.row0, sh.rows, 5, dev)
     out = torch.empty((max(sh.rows, 1), ops.padded_ld(n)), dtype=torch.float32, device=dev)[:sh.rows, :n]
     D.barrier()
     times = {"similarity": [], "eig": []}
@@ -88,8 +173,9 @@ def main():
         cells = float(n) * n
         rec = {"workload": f"row-sharded Pearson + top-3 eigvec, {n} bins ({cells:.3g} cells), {world} GPUs",
                "n_gpus": world, "bins": n, "rows_per_rank": sh.per,
+               "oe_log_ms": (oe_ms[-1] if oe_ms else None),
                "similarity_ms": sim, "eig_ms": eig,
-               "cells_per_s": cells / ((sim + eig) * 1e-3),
+               "cells_per_s": cells / ((sim + eig + (oe_ms[-1] if oe_ms else 0.0)) * 1e-3),
                "executed_tf32_tflops_per_gpu": 3 * 2 * float(sh.per) * n * n / (sim * 1e-3) / 1e12,
                "allgather_bytes_per_rank": 2 * (world - 1) * sh.per * sh.kpad * 4,
                "max_abs_err_vs_fp64_spotcheck": err}
@@ -98,7 +184,8 @@ def main():
             rec["eig_info"] = info
         print(json.dumps(rec), flush=True)
         os.makedirs("gpurun_out", exist_ok=True)
-        with open(f"gpurun_out/sharded_{world}gpu_{n}.json", "w") as fh:
+        tag = "counts_" if args.from_counts else ""
+        with open(f"gpurun_out/sharded_{tag}{world}gpu_{n}.json", "w") as fh:
             json.dump(rec, fh, indent=1)
     dist.destroy_process_group()
 

@@ -175,8 +175,160 @@ mirror_kernel(float* __restrict__ out, int n, long long ld) {
   }
 }
 
+// ------------------------------------------------------------------ f1: condense / trim as a remap
+// out[map[r]][map[c]] += v (and the mirrored cell for a 'triu' input, at the FINE level: a fine
+// off-diagonal entry whose two bins fall into one coarse bin is counted twice on the coarse
+// diagonal, exactly like condensing the symmetrised matrix, new_hic_class.py:2426-2465).
+__global__ void __launch_bounds__(256)
+scatter_remap_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
+                     const float* __restrict__ vals, long long nnz, int n_fine,
+                     const int* __restrict__ index_map, int mtx_type, float* __restrict__ out,
+                     long long ld) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+    const int r = rows[e], c = cols[e];
+    if (r < 0 || c < 0 || r >= n_fine || c >= n_fine) continue;
+    if (mtx_type == HIA_MTX_TRIU && c < r) continue;
+    const int rr = index_map[r], cc = index_map[c];
+    if (rr < 0 || cc < 0) continue;
+    const float v = vals[e];
+    atomicAdd(out + (long long)rr * ld + cc, v);
+    if (mtx_type == HIA_MTX_TRIU && r != c) atomicAdd(out + (long long)cc * ld + rr, v);
+  }
+}
+
+// non-zero stored entries per chromosome pair of the symmetrised ('all') matrix
+__global__ void __launch_bounds__(256)
+coo_block_nnz_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
+                     const float* __restrict__ vals, long long nnz, int n, int mtx_type,
+                     const short* __restrict__ bin_chr, int n_chr,
+                     unsigned long long* __restrict__ counts) {
+  int cur = -1;
+  unsigned long long acc = 0;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+    const int r = rows[e], c = cols[e];
+    if (r < 0 || c < 0 || r >= n || c >= n) continue;
+    if (mtx_type == HIA_MTX_TRIU && c < r) continue;
+    if (vals[e] == 0.f) continue;
+    const int a = bin_chr[r], b = bin_chr[c];
+    const bool twice = (mtx_type == HIA_MTX_TRIU && r != c);
+    if (a == b) {
+      const int slot = a * n_chr + a;
+      if (slot != cur) { if (cur >= 0) atomicAdd(&counts[cur], acc); cur = slot; acc = 0; }
+      acc += twice ? 2 : 1;
+    } else {
+      atomicAdd(&counts[a * n_chr + b], 1ull);
+      if (twice) atomicAdd(&counts[b * n_chr + a], 1ull);
+    }
+  }
+  if (cur >= 0) atomicAdd(&counts[cur], acc);
+}
+
+// fp64 row sums of the symmetrised, remapped matrix straight from the fine COO (no dense map):
+// decides which bins tid_off_low_bins keeps, so it must not depend on fp32 rounding of the map.
+__global__ void __launch_bounds__(256)
+coo_bin_sums_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
+                    const float* __restrict__ vals, long long nnz, int n_fine,
+                    const int* __restrict__ index_map, int mtx_type, double* __restrict__ bin_sum) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+    const int r = rows[e], c = cols[e];
+    if (r < 0 || c < 0 || r >= n_fine || c >= n_fine) continue;
+    if (mtx_type == HIA_MTX_TRIU && c < r) continue;
+    const int rr = index_map[r], cc = index_map[c];
+    if (rr < 0 || cc < 0) continue;
+    const double v = (double)vals[e];
+    atomicAdd(bin_sum + rr, v);
+    if (mtx_type == HIA_MTX_TRIU && r != c) atomicAdd(bin_sum + cc, v);
+  }
+}
+
+// per-row sum (fp64) and non-zero count of a dense map; CTA per row
+__global__ void __launch_bounds__(256)
+bin_stats_kernel(const float* __restrict__ x, int n, long long ld, double* __restrict__ row_sum,
+                 long long* __restrict__ row_nnz) {
+  __shared__ double s_sum[8];
+  __shared__ unsigned long long s_cnt[8];
+  const int r = blockIdx.x;
+  const float* row = x + (long long)r * ld;
+  double acc = 0.0;
+  unsigned long long cnt = 0;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) { const float v = row[c]; acc += (double)v; cnt += (v != 0.f); }
+  acc = warp_sum(acc);
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = acc; s_cnt[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0; unsigned long long k = 0;
+    for (int i = 0; i < 8; ++i) { a += s_sum[i]; k += s_cnt[i]; }
+    row_sum[r] = a;
+    row_nnz[r] = (long long)k;
+  }
+}
+
 }  // namespace
 }  // namespace hia
+
+HIA_API int hia_scatter_coo_remap(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz,
+                                  int32_t n_fine, const int32_t* index_map, int32_t n_out, float* out,
+                                  int64_t ld, int mtx_type, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!out || !index_map || n_fine <= 0 || n_out <= 0 || ld < n_out || nnz < 0) return HIA_ERR_BAD_ARG;
+  if (nnz > 0 && (!rows || !cols || !vals)) return HIA_ERR_BAD_ARG;
+  if (mtx_type != HIA_MTX_TRIU && mtx_type != HIA_MTX_ALL) return HIA_ERR_BAD_ARG;
+  HIA_CUDA(cudaMemset2DAsync(out, (size_t)ld * 4, 0, (size_t)n_out * 4, n_out, stream));
+  if (nnz > 0) {
+    const int grid = (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (nnz + 255) / 256));
+    scatter_remap_kernel<<<grid, 256, 0, stream>>>(rows, cols, vals, nnz, n_fine, index_map, mtx_type, out, ld);
+    HIA_LAUNCH_CHECK();
+  }
+  return HIA_OK;
+}
+
+HIA_API int hia_coo_block_nnz(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz,
+                              int32_t n, int mtx_type, const int16_t* bin_chr, int32_t n_chr,
+                              unsigned long long* counts, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!bin_chr || !counts || n <= 0 || n_chr <= 0 || nnz < 0) return HIA_ERR_BAD_ARG;
+  if (nnz > 0 && (!rows || !cols || !vals)) return HIA_ERR_BAD_ARG;
+  HIA_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_chr * n_chr * 8, stream));
+  if (nnz > 0) {
+    const int grid = (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (nnz + 255) / 256));
+    coo_block_nnz_kernel<<<grid, 256, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, bin_chr, n_chr, counts);
+    HIA_LAUNCH_CHECK();
+  }
+  return HIA_OK;
+}
+
+HIA_API int hia_coo_bin_sums(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz,
+                             int32_t n_fine, const int32_t* index_map, int32_t n_out, int mtx_type,
+                             double* bin_sum, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!bin_sum || !index_map || n_fine <= 0 || n_out <= 0 || nnz < 0) return HIA_ERR_BAD_ARG;
+  if (nnz > 0 && (!rows || !cols || !vals)) return HIA_ERR_BAD_ARG;
+  if (mtx_type != HIA_MTX_TRIU && mtx_type != HIA_MTX_ALL) return HIA_ERR_BAD_ARG;
+  HIA_CUDA(cudaMemsetAsync(bin_sum, 0, (size_t)n_out * 8, stream));
+  if (nnz > 0) {
+    const int grid = (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (nnz + 255) / 256));
+    coo_bin_sums_kernel<<<grid, 256, 0, stream>>>(rows, cols, vals, nnz, n_fine, index_map, mtx_type, bin_sum);
+    HIA_LAUNCH_CHECK();
+  }
+  return HIA_OK;
+}
+
+HIA_API int hia_bin_stats(const float* x, int32_t n, int64_t ld, double* row_sum, long long* row_nnz,
+                          void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !row_sum || !row_nnz || n <= 0 || ld < n) return HIA_ERR_BAD_ARG;
+  bin_stats_kernel<<<n, 256, 0, stream>>>(x, n, ld, row_sum, row_nnz);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
 
 HIA_API int64_t hia_scatter_workspace_bytes(int32_t n_chr) {
   if (n_chr < 1) n_chr = 1;

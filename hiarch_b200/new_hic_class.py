@@ -111,6 +111,61 @@ class GenomeIndex:
         """4-column .window.bed (:419-421)."""
         self.window_df[['chr', 'start', 'end', 'index']].to_csv(out_file, sep="\t", header=False, index=False)
 
+    # ---- index surgery used by preprocess_mtx / CorrectMap (host, integer, bit-exact) ----------
+    def condense(self, condense_fold):
+        """:423-458. Returns (new GenomeIndex, index_trans: old index -> new index, int64 array)."""
+        df = self.window_df
+        idx = df['index'].values
+        chrs = df['chr'].values
+        new_index = np.zeros(len(df), dtype=np.int64)
+        current = 0
+        for chro in self.chros:
+            lo = self.chr_seps[chro][0]
+            m = chrs == chro
+            ni = (idx[m] - lo) // condense_fold + current
+            new_index[m] = ni
+            current = int(ni.max()) + 1
+        tmp = pd.DataFrame({'chr': chrs, 'start': df['start'].values, 'end': df['end'].values,
+                            'new_index': new_index})
+        grp = tmp.groupby('new_index')
+        new_df = pd.DataFrame({'chr': grp['chr'].min(), 'start': grp['start'].min(), 'end': grp['end'].max()})
+        new_df['index'] = new_df.index
+        trans = np.full(int(idx.max()) + 1, -1, dtype=np.int64)
+        trans[idx] = new_index
+        return GenomeIndex(new_df.reset_index(drop=True)), trans
+
+    def keep_chros(self, chros, return_old_index=False):
+        """:256-278: chromosomes re-packed in the given order; returns the old index per new bin."""
+        if len(chros) == 0:
+            return (None, None) if return_old_index else None
+        parts = [self.window_df[self.window_df['chr'] == c] for c in chros]
+        new_df = pd.concat(parts, axis=0).reset_index(drop=True)
+        old_index = np.array(new_df['index'])
+        new_df = new_df.drop(['index'], axis=1)
+        new_df['index'] = np.arange(len(new_df))
+        g = GenomeIndex(new_df[['chr', 'start', 'end', 'index']])
+        return (g, old_index) if return_old_index else g
+
+    def keep_long_chros(self, min_chro_len=5, return_old_index=False, verbose=True):
+        """:306-327: chromosomes with MORE than min_chro_len bins."""
+        keep = [c for c in self.chros if self.chr_lens[c] > min_chro_len]
+        drop = [c for c in self.chros if self.chr_lens[c] <= min_chro_len]
+        if verbose and drop:
+            print(f'{" ".join(drop)} is too short.')
+        return self.keep_chros(keep, return_old_index)
+
+    def get_sub_gen_index(self, start=None, end=None, idxes=None, reset_index=True):
+        """:229-249 for a list of kept indexes."""
+        if idxes is None:
+            raise NotImplementedError
+        sub = self.window_df.loc[idxes, :].copy()
+        sub.loc[:, 'ori_index'] = sub['index'].copy()
+        sub.reset_index(inplace=True, drop=True)
+        sub.loc[:, 'index'] = sub.index
+        g = GenomeIndex(sub)
+        g.ori_start_idx = int(np.min(idxes)) if len(idxes) else None
+        return g
+
 
 # ------------------------------------------------------------------------------------------
 class HiCMtx:

@@ -48,7 +48,7 @@ def compartment_track(n, rng, smooth=25):
     return np.sign(sm + 1e-12) * np.minimum(1.0, np.abs(sm) * 3)
 
 
-def rate_matrix(lens, seed=0, lam_inter=0.6, smooth=None, x_shape=0.0):
+def rate_matrix(lens, seed=0, lam_inter=0.6, smooth=None, x_shape=0.0, depth=1.0):
     """Dense fp64 rate matrix lambda for chromosomes of `lens` bins (host, small sizes).
     x_shape > 0 adds a Rabl-like X pattern (anti-diagonal band through the chromosome centre)
     so that the `intra_x` anchor method has something to find."""
@@ -67,7 +67,7 @@ def rate_matrix(lens, seed=0, lam_inter=0.6, smooth=None, x_shape=0.0):
             anti = np.abs(np.add.outer(i, i) - (L - 1))
             blk = blk + x_shape * np.exp(-(anti / max(2.0, 0.03 * L)) ** 2)
         lam[s:e + 1, s:e + 1] = blk
-    return lam, seps
+    return lam * depth, seps
 
 
 def sample_counts(lam, seed=0, jitter=True):
@@ -80,9 +80,9 @@ def sample_counts(lam, seed=0, jitter=True):
     return up                                  # upper triangle incl. diagonal
 
 
-def synth_coo(lens, seed=0, lam_inter=0.6, jitter=True, x_shape=0.0):
+def synth_coo(lens, seed=0, lam_inter=0.6, jitter=True, x_shape=0.0, depth=1.0):
     """(rows, cols, vals, seps): upper-triangle non-zeros of a seeded synthetic map."""
-    lam, seps = rate_matrix(lens, seed, lam_inter, x_shape=x_shape)
+    lam, seps = rate_matrix(lens, seed, lam_inter, x_shape=x_shape, depth=depth)
     up = sample_counts(lam, seed, jitter)
     r, c = np.nonzero(up)
     return r.astype(np.int32), c.astype(np.int32), up[r, c], seps
@@ -98,9 +98,9 @@ def window_table(names, lens, bin_size):
     return rows
 
 
-def write_sample(prefix, names, lens, bin_size, seed=0, lam_inter=0.6, x_shape=0.0):
+def write_sample(prefix, names, lens, bin_size, seed=0, lam_inter=0.6, x_shape=0.0, depth=1.0):
     """Write `<prefix>_normalized.mtx` + `<prefix>.window.bed` in the reference's format."""
-    r, c, v, seps = synth_coo(lens, seed, lam_inter, x_shape=x_shape)
+    r, c, v, seps = synth_coo(lens, seed, lam_inter, x_shape=x_shape, depth=depth)
     np.savetxt(f"{prefix}_normalized.mtx", np.vstack([r, c, v]).T, fmt="%d\t%d\t%.2f")
     with open(f"{prefix}.window.bed", "w") as fh:
         for (name, s, e, i) in window_table(names, lens, bin_size):

@@ -64,6 +64,33 @@ int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const float* v
                         const int32_t* chr_start, int32_t n_chr, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
+/* f1  coarse-graining / trimming as an index remap fused into the scatter                 */
+/* replaces SpsHiCMtx.condense (new_hic_class.py:2426-2465), tid_off_low_bins (:1671-1702), */
+/*          tid_off_zero_chros / keep_long_chros / get_multi_chros_mtx (row+column           */
+/*          selection), as composed by preprocess_mtx (oe_map/S1_preprocess.py:48-83)        */
+/* ------------------------------------------------------------------------------------ */
+/* out[map[r]][map[c]] += v for every entry (index_map[n_fine] int32, -1 = bin dropped); a
+ * 'triu' input is mirrored at the fine level. out (n_out x n_out) is zero-filled first. */
+int hia_scatter_coo_remap(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz,
+                          int32_t n_fine, const int32_t* index_map, int32_t n_out, float* out,
+                          int64_t ld, int mtx_type, void* stream);
+/* counts[C*C] (u64): non-zero stored entries per chromosome pair of the symmetrised matrix
+ * (HiCMtx.get_nonzero_ratio on the blocks of yield_by_chro, :1040-1065). */
+int hia_coo_block_nnz(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz,
+                      int32_t n, int mtx_type, const int16_t* bin_chr, int32_t n_chr,
+                      unsigned long long* counts, void* stream);
+/* bin_sum[n_out] (fp64): row sums of the symmetrised, remapped matrix straight from the fine COO
+ * (the statistic get_high_coverage_bins :1658-1669 thresholds; fp64 so that the kept-bin set
+ * does not depend on the fp32 storage of the map). */
+int hia_coo_bin_sums(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz,
+                     int32_t n_fine, const int32_t* index_map, int32_t n_out, int mtx_type,
+                     double* bin_sum, void* stream);
+/* row_sum[n] (fp64) and row_nnz[n] (i64) of a dense map (get_high_coverage_bins :1658-1669,
+ * get_nonzero_ratio). */
+int hia_bin_stats(const float* x, int32_t n, int64_t ld, double* row_sum, long long* row_nnz,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------ */
 /* a4/a5  expected contacts per diagonal, O/E, log                                       */
 /* replaces HiCMtx.obs_d_exp(mode='sgd_mean') (new_hic_class.py:1121-1290) and           */
 /*          ArrayHiCMtx.log (:2076-2094); oe_map_core (oe_map/S2_oe.py:10-15)            */

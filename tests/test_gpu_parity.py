@@ -473,3 +473,63 @@ def test_intra_x_response(golden):
         got = ops.intra_x_response(_mapdev(a)).cpu().numpy()
         ref = O.intra_x(a.astype(np.float32).astype(np.float64))
         assert np.all(np.abs(got - ref) <= 1e-9 + 1e-9 * np.abs(ref))
+
+
+# --------------------------------------------------------------------------------- f1 preprocess
+@pytest.mark.parametrize("case", ["gpre_fold", "gpre_sparse", "gpre_none"])
+def test_preprocess_mtx_matches_reference(golden, case, tmp_path):
+    """S1_preprocess.py:48-83 through the remap-scatter / COO statistics kernels: the log (every
+    fold / trim / gate decision), the bin table (bit-exact) and the coarse map."""
+    from hiarch_b200.preprocess import preprocess_mtx
+    from test_host_preprocess import check_preprocess_case
+    check_preprocess_case(case, golden, tmp_path, preprocess_mtx)
+
+
+def test_remap_scatter_and_coo_statistics_vs_numpy():
+    from hiarch_b200 import _lib, ops
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    n_fine, nnz = 700, 60000
+    r = rng.integers(0, n_fine, nnz); c = rng.integers(0, n_fine, nnz)
+    r, c = np.minimum(r, c), np.maximum(r, c)
+    lin = np.unique(r * n_fine + c)                     # duplicate-free, like the host's coo -> csr
+    r, c, nnz = lin // n_fine, lin % n_fine, len(lin)
+    v = np.round(rng.gamma(2.0, 3.0, nnz), 2)
+    v[rng.random(nnz) < .02] = 0.0
+    fmap = (np.arange(n_fine) // 3).astype(np.int32)
+    fmap[rng.random(n_fine) < .1] = -1
+    kept = np.unique(fmap[fmap >= 0]); rel = np.full(fmap.max() + 1, -1); rel[kept] = np.arange(len(kept))
+    fmap = np.where(fmap >= 0, rel[np.maximum(fmap, 0)], -1).astype(np.int32)
+    n_out = int(fmap.max()) + 1
+    off = r != c
+    rr = np.concatenate([fmap[r], fmap[c[off]]]); cc = np.concatenate([fmap[c], fmap[r[off]]])
+    vv = np.concatenate([v, v[off]]).astype(np.float32).astype(np.float64)
+    ok = (rr >= 0) & (cc >= 0)
+    ref = np.zeros((n_out, n_out)); np.add.at(ref, (rr[ok], cc[ok]), vv[ok])
+    dr, dc, dv, dm = _dev(r, torch.int32), _dev(c, torch.int32), _dev(v, torch.float32), _dev(fmap, torch.int32)
+    out = ops.alloc_map(n_out, "cuda")
+    _lib.check(lib.hia_scatter_coo_remap(dr.data_ptr(), dc.data_ptr(), dv.data_ptr(), nnz, n_fine, dm.data_ptr(),
+                                         n_out, out.data_ptr(), out.stride(0), ops.MTX_TRIU, ops._stream()), "remap")
+    got = out.cpu().numpy().astype(np.float64)
+    assert np.abs(got - ref).max() <= 2e-6 * ref.max()
+    assert np.array_equal(got, got.T)                                   # symmetric cell by cell? (same addends)
+    bs = torch.empty(n_out, dtype=torch.float64, device="cuda")
+    _lib.check(lib.hia_coo_bin_sums(dr.data_ptr(), dc.data_ptr(), dv.data_ptr(), nnz, n_fine, dm.data_ptr(), n_out,
+                                    ops.MTX_TRIU, bs.data_ptr(), ops._stream()), "bin_sums")
+    assert np.allclose(bs.cpu().numpy(), ref.sum(axis=1), rtol=1e-12, atol=0)
+    rs = torch.empty(n_out, dtype=torch.float64, device="cuda"); rn = torch.empty(n_out, dtype=torch.int64, device="cuda")
+    _lib.check(lib.hia_bin_stats(out.data_ptr(), n_out, out.stride(0), rs.data_ptr(), rn.data_ptr(), ops._stream()), "stats")
+    assert np.array_equal(rn.cpu().numpy(), (got != 0).sum(axis=1))
+    assert np.allclose(rs.cpu().numpy(), got.sum(axis=1), rtol=1e-12)
+    # per-chromosome-pair stored non-zeros of the symmetrised fine matrix
+    lens = [300, 250, 150]
+    layout = ops.GenomeLayout(synth.chr_seps_from_lens(lens))
+    cnt = torch.empty(9, dtype=torch.int64, device="cuda")
+    _lib.check(lib.hia_coo_block_nnz(dr.data_ptr(), dc.data_ptr(), dv.data_ptr(), nnz, n_fine, ops.MTX_TRIU,
+                                     layout.bin_chr.data_ptr(), 3, cnt.data_ptr(), ops._stream()), "block_nnz")
+    chr_of = np.repeat(np.arange(3), lens)
+    nz = v != 0
+    ref_cnt = np.zeros((3, 3), dtype=np.int64)
+    np.add.at(ref_cnt, (chr_of[r[nz]], chr_of[c[nz]]), 1)
+    np.add.at(ref_cnt, (chr_of[c[nz & off]], chr_of[r[nz & off]]), 1)
+    assert np.array_equal(cnt.cpu().numpy().reshape(3, 3), ref_cnt)

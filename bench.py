@@ -12,7 +12,8 @@ chromosomes), i.e. samples are sharded by rank like the reference's ParallelFunc
 (publish/run_hic_dataset.py:573-603).
 
 One step = sparse (i,j,v) upper triangle resident in HBM -> dense symmetric scatter -> expected /
-O-E / log (sgd_mean, k=.2) -> row x row Pearson on tcgen05 (3xTF32) -> top-3 eigenvectors (block
+O-E / log (sgd_mean, k=.2) -> row x row Pearson on tcgen05 (3-term fp16 hi/lo split by default,
+--precision tf32x3 for the TF32 split) -> top-3 eigenvectors (block
 Lanczos). `value` = cells of all ranks / max-over-ranks device time. `e2e` = the same through
 HotPath.run_host: COO in pinned host memory, H2D inside the timed region, eigenpairs read back.
 Inputs (0.9 GB COO / 3.8 GB maps) are far larger than the 126 MB L2, so no explicit L2 flush.
@@ -42,6 +43,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--res", type=int, default=100000, help="bin size (bp)")
     ap.add_argument("--chroms", type=int, default=24, help="first C hg38 chromosomes")
+    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "tf32x3"],
+                    help="operand split of the Pearson contraction (both carry 22 significant bits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-chroms", default="chr16,chr17,chr18,chr19,chr20,chr21,chr22")
     return ap.parse_args()
@@ -193,7 +196,8 @@ def run_ours(args):
     del dense
     torch.cuda.empty_cache()
     nnz = rows.numel()
-    hp = HotPath(seps, args.res, k_eig=3, max_nnz=nnz)
+    prec = ops.PREC_3XF16 if args.precision == "f16x3" else ops.PREC_3XTF32
+    hp = HotPath(seps, args.res, k_eig=3, max_nnz=nnz, precision=prec)
     rows_h = torch.empty(nnz, dtype=torch.int32).pin_memory().copy_(rows)
     cols_h = torch.empty(nnz, dtype=torch.int32).pin_memory().copy_(cols)
     vals_h = torch.empty(nnz, dtype=torch.float32).pin_memory().copy_(vals)
@@ -264,25 +268,27 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (syrk_tf32x3_kernel) ----------------------------------
+    # ---- roofline of the dominant kernel (syrk_split3_kernel) ----------------------------------
     # algorithmic flops per launch: N^2 * K multiply-adds counted as the symmetric half,
-    # i.e. 2 * N^2 * K / 2 = N^3 logical flops; each logical flop costs 3 TF32 MMAs.
+    # i.e. 2 * N^2 * K / 2 = N^3 logical flops; each logical flop costs 3 MMAs
+    # (hi.hi + hi.lo + lo.hi) at the fp16 (= measured bf16) or TF32 (= bf16 / 2) dense rate.
     logical = float(n) ** 3
     achieved = logical / (gemm * 1e-3) / 1e12
-    tf32_peak = pk["bf16_tflops_sustained"] / 2.0           # TF32 dense = bf16 / 2 on Blackwell
-    peak_logical = tf32_peak / 3.0
+    rate_div = 1.0 if args.precision == "f16x3" else 2.0
+    peak_logical = pk["bf16_tflops_sustained"] / rate_div / 3.0
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "syrk_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", f"syrk_traffic_{args.precision}.json")
     if os.path.exists(tpath) and n == 30894:            # the capture was taken on this workload
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    kind = "fp16" if args.precision == "f16x3" else "TF32"
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_logical, "unit": "TFLOP/s",
                 "frac": achieved / peak_logical, "traffic": traffic,
-                "frac_of_burst_peak": achieved / (pk["bf16_tflops"] / 6.0),
-                "kernel": "syrk_tf32x3_kernel", "ms_per_launch": gemm,
+                "frac_of_burst_peak": achieved / (pk["bf16_tflops"] / rate_div / 3.0),
+                "kernel": f"syrk_split3_kernel<{args.precision}>", "ms_per_launch": gemm,
                 "note": ("achieved = N^3 logical flops (upper-triangle SYRK) / CUDA-event time of the "
-                         "kernel; peak = bf16_tflops_sustained/2 (TF32) /3 (3xTF32 split), "
-                         f"{pk_src}; executed TF32 rate = {3 * achieved:.1f} TFLOP/s")}
+                         f"kernel; peak = bf16_tflops_sustained{'' if rate_div == 1 else '/2'} ({kind} dense) "
+                         f"/3 (3-term split), {pk_src}; executed {kind} rate = {3 * achieved:.1f} TFLOP/s")}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -299,7 +305,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": world * cells / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 storage, fp64 reductions)",
+        "scaling": "weak", "vs_baseline": None, "dtype": f"{args.precision} (fp32 storage, fp64 reductions)",
         "data": "synthetic",
         "config": {"workload": f"genome-wide human {args.res // 1000} kb ({n} bins, {cells:.3g} cells) "
                                "scatter -> O/E+log -> Pearson -> top-3 eigvec, one sample per GPU",

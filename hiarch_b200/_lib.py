@@ -40,8 +40,8 @@ PROTOTYPES = {
     "hia_similarity_workspace_bytes": (c_i64, [c_i32, c_i32, c_int]),
     "hia_similarity": (c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_int, c_int, c_i32, c_i32,
                                c_i32, c_vp, c_i64, c_vp]),
-    "hia_similarity_prep": (c_int, [c_vp, c_i32, c_i32, c_i64, c_int, c_vp, c_i64, c_vp]),
-    "hia_similarity_gemm": (c_int, [c_i32, c_i32, c_vp, c_i64, c_int, c_i32, c_i32, c_i32, c_vp, c_i64,
+    "hia_similarity_prep": (c_int, [c_vp, c_i32, c_i32, c_i64, c_int, c_int, c_vp, c_i64, c_vp]),
+    "hia_similarity_gemm": (c_int, [c_i32, c_i32, c_vp, c_i64, c_int, c_int, c_i32, c_i32, c_i32, c_vp, c_i64,
                                     c_vp]),
     "hia_percentiles_workspace_bytes": (c_i64, []),
     "hia_percentiles": (c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_i64, c_vp]),
@@ -65,11 +65,12 @@ PROTOTYPES = {
     "hia_topk_eig_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),
     "hia_topk_eig": (c_int, [c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_i32,
                              c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
-    "hia_sim_kpad": (c_i32, [c_i32]),
-    "hia_sim_prep_rows": (c_int, [c_vp, c_i32, c_i32, c_i64, c_int, c_vp, c_vp, c_vp]),
+    "hia_sim_kpad": (c_i32, [c_i32, c_int]),
+    "hia_sim_plane_elem_bytes": (c_i32, [c_int]),
+    "hia_sim_prep_rows": (c_int, [c_vp, c_i32, c_i32, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     "hia_sim_gemm_rows_workspace_bytes": (c_i64, [c_i32, c_i32]),
-    "hia_sim_gemm_rows": (c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_int, c_i32,
-                                  c_vp, c_i64, c_vp]),
+    "hia_sim_gemm_rows": (c_int, [c_vp, c_vp, c_int, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_int,
+                                  c_i32, c_vp, c_i64, c_vp]),
     "hia_eig_begin": (c_int, [c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_i32, c_vp, c_i64, c_vp]),
     "hia_eig_symm_rows": (c_int, [c_vp, c_i32, c_i32, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "hia_eig_absorb": (c_int, [c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),

@@ -20,9 +20,16 @@
 //   Only tiles touching the upper triangle (and the requested |i-j| band) are computed; the
 //   lower triangle is written as the exact mirror, the diagonal as the exact constant.
 //
+// HIA_PREC_3XF16: the same split on kind::f16 -- fp16 has the SAME 11-bit significand as TF32, so
+// hi = fp16(S xn), lo = fp16(S xn - hi) (S = 2^14, exact; |xn| <= 1 keeps hi finite) carry the same
+// 22 bits, the products are exact in fp32, and one MMA instruction covers K = 16 instead of 8 in
+// the same 128 cycles and the same 12 KB of shared-memory operands: half the MMA time, half the
+// plane bytes. The epilogue rescales by 2^-28 (exact).
+//
 // 3xTF32 error budget: |hi.hi + hi.lo + lo.hi - x.y| <= ~2^-21 |x||y| per product; fp32
 // accumulation over <= k_chunk/8 MMA steps, then RN fp32 adds of <= k/k_chunk partials.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "hia_common.cuh"
 
@@ -31,11 +38,16 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BN = 256;
-constexpr int BK = 32;                         // fp32 elements per k-block = 128 B (one SW128 atom)
-constexpr int UMMA_K = 8;                      // tf32
+constexpr int ROW_BYTES = 128;                 // one SW128 atom of K per row and k-block
+constexpr int UMMA_K_BYTES = 32;               // K extent of one MMA instruction, all kinds
 constexpr int STAGES = 2;
-constexpr int A_BYTES = BM * BK * 4;           // 16 KB
-constexpr int B_BYTES = BN * BK * 4;           // 32 KB
+constexpr int A_BYTES = BM * ROW_BYTES;        // 16 KB
+constexpr int B_BYTES = BN * ROW_BYTES;        // 32 KB
+// elements per k-block: 32 (tf32 planes, fp32 storage) or 64 (fp16 planes)
+__host__ __device__ constexpr int bk_of(int prec) { return prec == HIA_PREC_3XF16 ? 64 : 32; }
+__host__ __device__ constexpr int elem_bytes(int prec) { return prec == HIA_PREC_3XF16 ? 2 : 4; }
+constexpr float kF16Scale = 16384.f;                         // 2^14
+constexpr float kF16Unscale = 1.f / (16384.f * 16384.f);     // 2^-28
 constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // hi + lo planes: 96 KB
 constexpr int EPI_WARPS = 8;                   // 2 per TMEM lane quarter x 128 columns each
 constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
@@ -89,13 +101,22 @@ __device__ __forceinline__ void tcgen05_fence_before() {
 __device__ __forceinline__ void tcgen05_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+template <int PREC>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                     uint32_t idesc, uint32_t accumulate) {
+  if constexpr (PREC == HIA_PREC_3XF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
@@ -127,16 +148,19 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a/b=TF32 [7,10),[10,13)=2,
-// K-major both, N>>3 at [17,23), M>>4 at [24,29).
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                            ((uint32_t)(BM >> 4) << 24);
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a/b format [7,10),[10,13)
+// (F16 = 0, TF32 = 2), K-major both, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t idesc_of(int prec) {
+  const uint32_t fmt = prec == HIA_PREC_3XF16 ? 0u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 
 struct TileCoord { int m_blk; int n_blk; };
 
 // ------------------------------------------------------------------ the kernel
+template <int PREC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                    const TileCoord* __restrict__ tiles, int num_tiles, int m, int num_k_blocks,
                    int kb_per_chunk, float* __restrict__ out, long long ld_out, int flavour,
                    unsigned int* __restrict__ sync_ctr, int sync_every, int row0, int row_end,
@@ -199,7 +223,7 @@ syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
           mbar_wait(&empty_bar[s], ph ^ 1);
           unsigned char* st = smem + s * STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-          const int k0 = kb * BK;
+          const int k0 = kb * bk_of(PREC);
           tma_load_2d(st, &map_hi, &full_bar[s], k0, m0);                               // A hi
           tma_load_2d(st + A_BYTES, &map_lo, &full_bar[s], k0, m0);                     // A lo
           tma_load_2d(st + 2 * A_BYTES, &map_hi, &full_bar[s], k0, n0);                 // B hi [0,128)
@@ -229,14 +253,15 @@ syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             const uint64_t a_lo = make_kmajor_sw128_desc(st + A_BYTES);
             const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * A_BYTES);
             const uint64_t b_lo = make_kmajor_sw128_desc(st + 2 * A_BYTES + B_BYTES);
+            constexpr uint32_t kIdesc = idesc_of(PREC);
 #pragma unroll
-            for (int j = 0; j < BK / UMMA_K; ++j) {
-              const uint64_t adv = (uint64_t)((j * UMMA_K * 4) >> 4);   // +32 B per k-step
+            for (int j = 0; j < ROW_BYTES / UMMA_K_BYTES; ++j) {
+              const uint64_t adv = (uint64_t)((j * UMMA_K_BYTES) >> 4);   // +32 B per k-step
               const uint32_t first = (kb == ch * kb_per_chunk && j == 0) ? 0u : 1u;
               // small cross terms first, the dominant hi.hi term last
-              umma_tf32(d_tmem, a_lo + adv, b_hi + adv, kIdesc, first);
-              umma_tf32(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
-              umma_tf32(d_tmem, a_hi + adv, b_hi + adv, kIdesc, 1u);
+              umma<PREC>(d_tmem, a_lo + adv, b_hi + adv, kIdesc, first);
+              umma<PREC>(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+              umma<PREC>(d_tmem, a_hi + adv, b_hi + adv, kIdesc, 1u);
             }
             umma_commit(&empty_bar[s]);                   // frees the smem stage when MMAs retire
           }
@@ -286,7 +311,7 @@ syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float raw = accr[cg * 32 + j];
+            const float raw = (PREC == HIA_PREC_3XF16) ? accr[cg * 32 + j] * kF16Unscale : accr[cg * 32 + j];
             float c = fminf(1.f, fmaxf(-1.f, raw));         // |cos| clipped to 1 like scipy
             if (raw != raw) c = raw;                        // NaN stays NaN
             f[j] = (flavour == HIA_SIM_COSINE_DISTANCE) ? (1.f - c) : c;
@@ -328,10 +353,32 @@ syrk_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 
 // ------------------------------------------------------------------ row prologue
 // One CTA per row: fp64 sum and sum of squares in ONE pass (128-bit loads; the row then sits in
-// L1/L2), mean / norm, then the TF32 hi/lo planes of the unit row in a second pass.
+// L1/L2), mean / norm, then the hi/lo planes of the unit row in a second pass
+// (TF32-exact fp32 planes, or fp16 planes of the row scaled by 2^14).
+template <int PREC> struct PlaneT { typedef float type; };
+template <> struct PlaneT<HIA_PREC_3XF16> { typedef __half type; };
+
+template <int PREC>
+__device__ __forceinline__ void split_hi_lo(float xn, typename PlaneT<PREC>::type& h, typename PlaneT<PREC>::type& l) {
+  if constexpr (PREC == HIA_PREC_3XF16) {
+    const float xs = xn * kF16Scale;                      // exact (power of two)
+    h = __float2half_rn(xs);
+    l = __float2half_rn(xs - __half2float(h));            // the difference is exact in fp32
+  } else {
+    uint32_t hb, lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(xn));
+    h = __uint_as_float(hb);
+    const float rem = xn - h;                             // exact in fp32
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+    l = __uint_as_float(lb);
+  }
+}
+
+template <int PREC>
 __global__ void __launch_bounds__(256)
 row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int kpad, int center,
-                float* __restrict__ hi, float* __restrict__ lo) {
+                typename PlaneT<PREC>::type* __restrict__ hi, typename PlaneT<PREC>::type* __restrict__ lo) {
+  typedef typename PlaneT<PREC>::type P;
   __shared__ double s_red[8][2];
   __shared__ double s_val[2];
   const int r = blockIdx.x;
@@ -369,21 +416,44 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
   }
   __syncthreads();
   const double mean = s_val[0], inv = s_val[1];
-  float* ph = hi + (long long)r * kpad;
-  float* pl = lo + (long long)r * kpad;
-  for (int j = tid; j < kpad; j += blockDim.x) {
-    float h = 0.f, l = 0.f;
-    if (j < k) {
-      const float xn = (float)(((double)row[j] - mean) * inv);
-      uint32_t hb, lb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(xn));
-      h = __uint_as_float(hb);
-      const float rem = xn - h;                           // exact in fp32
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
-      l = __uint_as_float(lb);
+  P* ph = hi + (long long)r * kpad;
+  P* pl = lo + (long long)r * kpad;
+  // second pass: 4 cells per thread (128-bit loads; 128-/64-bit plane stores; kpad % 4 == 0 and the
+  // plane rows are 16-byte aligned by construction)
+  if (vec_ok) {
+    for (int j4 = tid; j4 < (kpad >> 2); j4 += blockDim.x) {
+      const int j = j4 << 2;
+      float xv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j + 3 < k) {
+        const float4 v = *reinterpret_cast<const float4*>(row + j);
+        xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
+      } else {
+        for (int e = 0; e < 4; ++e) if (j + e < k) xv[e] = row[j + e];
+      }
+      P h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (j + e < k) {
+          split_hi_lo<PREC>((float)(((double)xv[e] - mean) * inv), h[e], l[e]);
+        } else {
+          h[e] = P(0.f); l[e] = P(0.f);
+        }
+      }
+      if constexpr (PREC == HIA_PREC_3XF16) {
+        *reinterpret_cast<uint2*>(ph + j) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(pl + j) = *reinterpret_cast<const uint2*>(l);
+      } else {
+        *reinterpret_cast<float4*>(ph + j) = *reinterpret_cast<const float4*>(h);
+        *reinterpret_cast<float4*>(pl + j) = *reinterpret_cast<const float4*>(l);
+      }
     }
-    ph[j] = h;
-    pl[j] = l;
+  } else {
+    for (int j = tid; j < kpad; j += blockDim.x) {
+      P h = P(0.f), l = P(0.f);
+      if (j < k) split_hi_lo<PREC>((float)(((double)row[j] - mean) * inv), h, l);
+      ph[j] = h;
+      pl[j] = l;
+    }
   }
 }
 
@@ -392,7 +462,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_plane_map(CUtensorMap* map, float* base, int rows, int kpad) {
+int make_plane_map(CUtensorMap* map, void* base, int rows, int kpad, int prec) {
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -402,10 +472,11 @@ int make_plane_map(CUtensorMap* map, float* base, int rows, int kpad) {
     fn = reinterpret_cast<PFN_encodeTiled>(p);
   }
   cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)kpad * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint64_t strides[1] = {(cuuint64_t)kpad * elem_bytes(prec)};
+  cuuint32_t box[2] = {(cuuint32_t)bk_of(prec), (cuuint32_t)BM};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+  CUresult r = fn(map, prec == HIA_PREC_3XF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                  2, base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_cuda_error(cudaErrorInvalidValue); return HIA_ERR_CUDA; }
@@ -413,6 +484,7 @@ int make_plane_map(CUtensorMap* map, float* base, int rows, int kpad) {
 }
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline bool split_prec(int p) { return p == HIA_PREC_3XTF32 || p == HIA_PREC_3XF16; }
 
 // Tiles touching the upper triangle and the band, in super-blocks for L2 reuse.
 int build_tiles(int m, int band_lo, int band_hi, TileCoord* dst) {
@@ -435,6 +507,19 @@ int build_tiles(int m, int band_lo, int band_hi, TileCoord* dst) {
   return cnt;
 }
 
+int launch_prep(const float* x, int rows, int k, long long ld_x, int center, void* hi, void* lo, int prec,
+                cudaStream_t stream) {
+  const int kpad = round_up(k, bk_of(prec));
+  if (prec == HIA_PREC_3XF16)
+    row_prep_kernel<HIA_PREC_3XF16><<<rows, 256, 0, stream>>>(x, rows, k, ld_x, kpad, center,
+                                                             static_cast<__half*>(hi), static_cast<__half*>(lo));
+  else
+    row_prep_kernel<HIA_PREC_3XTF32><<<rows, 256, 0, stream>>>(x, rows, k, ld_x, kpad, center,
+                                                              static_cast<float*>(hi), static_cast<float*>(lo));
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
 }  // namespace
 
 int similarity_fp64(const float* x, int m, int k, long long ld_x, float* out, long long ld_out,
@@ -443,41 +528,40 @@ long long similarity_fp64_workspace(int m, int k);
 
 }  // namespace hia
 
-// workspace layout (3xTF32): [hi plane][lo plane][running tiles: 148 x 128 x 256 fp32][tile list]
+// workspace layout (split precisions): [hi plane][lo plane][tile list][rendezvous counters]
 constexpr int kSyncEvery = 32;          // k-blocks between producer rendezvous
 static int64_t sync_counters(int m, int k) {
   using namespace hia;
   const int64_t ntiles = (int64_t)((m + BM - 1) / BM) * ((m + BN - 1) / BN);
   const int64_t per_cta = ntiles / kNumSMs + 2;
-  return per_cta * (round_up(k, BK) / BK) / kSyncEvery + 64;
+  return per_cta * (round_up(k, 32) / 32) / kSyncEvery + 64;      // sized for the smaller k-block
 }
-static int64_t tf32_ws_layout(int m, int k, int64_t* off_lo, int64_t* off_run, int64_t* off_tiles,
-                              int64_t* off_sync = nullptr) {
+static int64_t split_ws_layout(int m, int k, int prec, int64_t* off_lo, int64_t* off_tiles,
+                               int64_t* off_sync = nullptr) {
   using namespace hia;
-  const int64_t kpad = round_up(k, BK);
-  const int64_t plane = (int64_t)m * kpad * 4;
+  const int64_t kpad = round_up(k, bk_of(prec));
+  const int64_t plane = (int64_t)m * kpad * elem_bytes(prec);
   const int64_t plane_al = (plane + 1023) / 1024 * 1024;
-  const int64_t run = 0;   // (round 1 kept the chunk running sums here; they live in registers now)
   const int64_t ntiles = (int64_t)((m + BM - 1) / BM) * ((m + BN - 1) / BN);
   if (off_lo) *off_lo = plane_al;
-  if (off_run) *off_run = 2 * plane_al;
-  if (off_tiles) *off_tiles = 2 * plane_al + run;
+  if (off_tiles) *off_tiles = 2 * plane_al;
   const int64_t tiles_al = (ntiles * (int64_t)sizeof(TileCoord) + 1023) / 1024 * 1024;
-  if (off_sync) *off_sync = 2 * plane_al + run + tiles_al;
-  return 2 * plane_al + run + tiles_al + sync_counters(m, k) * 4 + 1024;
+  if (off_sync) *off_sync = 2 * plane_al + tiles_al;
+  return 2 * plane_al + tiles_al + sync_counters(m, k) * 4 + 1024;
 }
 
 HIA_API int64_t hia_similarity_workspace_bytes(int32_t m, int32_t k, int precision) {
   if (m <= 0 || k <= 0) return 0;
   if (precision == HIA_PREC_FP64) return hia::similarity_fp64_workspace(m, k);
-  return tf32_ws_layout(m, k, nullptr, nullptr, nullptr);
+  if (!hia::split_prec(precision)) return 0;
+  return split_ws_layout(m, k, precision, nullptr, nullptr);
 }
 
 static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, float* out,
                            int64_t ld_out, int flavour, int precision, int32_t band_lo,
                            int32_t band_hi, int32_t k_chunk, void* workspace,
                            int64_t workspace_bytes, void* stream_, int phases);
-static int launch_gemm(float* hi, float* lo, int plane_rows, int n_valid, int kpad, int row0, int rows,
+static int launch_gemm(void* hi, void* lo, int prec, int plane_rows, int n_valid, int kpad, int row0, int rows,
                        int symmetric, int band_lo, int band_hi, float* out, int64_t ld_out, int flavour,
                        int k_chunk, hia::TileCoord* d_tiles, unsigned int* sync_ctr, int64_t n_sync,
                        cudaStream_t stream);
@@ -490,15 +574,17 @@ HIA_API int hia_similarity(const float* x, int32_t m, int32_t k, int64_t ld_x, f
                          workspace, workspace_bytes, stream, 3);
 }
 HIA_API int hia_similarity_prep(const float* x, int32_t m, int32_t k, int64_t ld_x, int flavour,
-                                void* workspace, int64_t workspace_bytes, void* stream) {
-  return similarity_impl(x, m, k, ld_x, reinterpret_cast<float*>(workspace), m, flavour, HIA_PREC_3XTF32,
+                                int precision, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!hia::split_prec(precision)) return HIA_ERR_BAD_ARG;
+  return similarity_impl(x, m, k, ld_x, reinterpret_cast<float*>(workspace), m, flavour, precision,
                          0, -1, 0, workspace, workspace_bytes, stream, 1);
 }
 HIA_API int hia_similarity_gemm(int32_t m, int32_t k, float* out, int64_t ld_out, int flavour,
-                                int32_t band_lo, int32_t band_hi, int32_t k_chunk, void* workspace,
-                                int64_t workspace_bytes, void* stream) {
+                                int precision, int32_t band_lo, int32_t band_hi, int32_t k_chunk,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!hia::split_prec(precision)) return HIA_ERR_BAD_ARG;
   return similarity_impl(reinterpret_cast<const float*>(workspace), m, k, k, out, ld_out, flavour,
-                         HIA_PREC_3XTF32, band_lo, band_hi, k_chunk, workspace, workspace_bytes, stream, 2);
+                         precision, band_lo, band_hi, k_chunk, workspace, workspace_bytes, stream, 2);
 }
 
 static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, float* out,
@@ -509,10 +595,10 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !out || !workspace || m <= 0 || k <= 0 || ld_x < k || ld_out < m) return HIA_ERR_BAD_ARG;
   if (flavour != HIA_SIM_COSINE_DISTANCE && flavour != HIA_SIM_PEARSON) return HIA_ERR_BAD_ARG;
+  if (precision != HIA_PREC_FP64 && !split_prec(precision)) return HIA_ERR_BAD_ARG;
   if (workspace_bytes < hia_similarity_workspace_bytes(m, k, precision)) return HIA_ERR_WORKSPACE;
   if (precision == HIA_PREC_FP64)
     return similarity_fp64(x, m, k, ld_x, out, ld_out, flavour, workspace, workspace_bytes, stream);
-  if (precision != HIA_PREC_3XTF32) return HIA_ERR_BAD_ARG;
   if (!aligned16(workspace)) return HIA_ERR_ALIGN;
   if (band_hi >= 0 && band_lo > band_hi) return HIA_ERR_BAD_ARG;
   if (band_lo < 0) band_lo = 0;
@@ -522,27 +608,27 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
   HIA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   if (major != 10) return HIA_ERR_ARCH;
 
-  int64_t off_lo, off_run, off_tiles, off_sync;
-  tf32_ws_layout(m, k, &off_lo, &off_run, &off_tiles, &off_sync);
+  int64_t off_lo, off_tiles, off_sync;
+  split_ws_layout(m, k, precision, &off_lo, &off_tiles, &off_sync);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
-  float* hi = reinterpret_cast<float*>(ws);
-  float* lo = reinterpret_cast<float*>(ws + off_lo);
+  void* hi = ws;
+  void* lo = ws + off_lo;
   TileCoord* d_tiles = reinterpret_cast<TileCoord*>(ws + off_tiles);
-  const int kpad = round_up(k, BK);
+  const int kpad = round_up(k, bk_of(precision));
 
   if (phases & 1) {
-    row_prep_kernel<<<m, 256, 0, stream>>>(x, m, k, ld_x, kpad, flavour == HIA_SIM_PEARSON ? 1 : 0, hi, lo);
-    HIA_LAUNCH_CHECK();
+    const int st = launch_prep(x, m, k, ld_x, flavour == HIA_SIM_PEARSON ? 1 : 0, hi, lo, precision, stream);
+    if (st != HIA_OK) return st;
   }
   if (!(phases & 2)) return HIA_OK;
 
-  return launch_gemm(hi, lo, m, m, kpad, 0, m, 1, band_lo, band_hi, out, ld_out, flavour, k_chunk,
+  return launch_gemm(hi, lo, precision, m, m, kpad, 0, m, 1, band_lo, band_hi, out, ld_out, flavour, k_chunk,
                      d_tiles, reinterpret_cast<unsigned int*>(ws + off_sync), sync_counters(m, k), stream);
 }
 
 // Tiles + tensor maps + launch. plane_rows = rows the planes hold (>= n_valid; extra rows must be
 // zero), n_valid = true matrix size, [row0, row0 + rows) = the output rows to compute.
-static int launch_gemm(float* hi, float* lo, int plane_rows, int n_valid, int kpad, int row0, int rows,
+static int launch_gemm(void* hi, void* lo, int prec, int plane_rows, int n_valid, int kpad, int row0, int rows,
                        int symmetric, int band_lo, int band_hi, float* out, int64_t ld_out, int flavour,
                        int k_chunk, hia::TileCoord* d_tiles, unsigned int* sync_ctr, int64_t n_sync,
                        cudaStream_t stream) {
@@ -568,42 +654,51 @@ static int launch_gemm(float* hi, float* lo, int plane_rows, int n_valid, int kp
   HIA_CUDA(ce);
 
   CUtensorMap map_hi, map_lo;
-  int st = make_plane_map(&map_hi, hi, plane_rows, kpad);
+  int st = make_plane_map(&map_hi, hi, plane_rows, kpad, prec);
   if (st != HIA_OK) return st;
-  st = make_plane_map(&map_lo, lo, plane_rows, kpad);
+  st = make_plane_map(&map_lo, lo, plane_rows, kpad, prec);
   if (st != HIA_OK) return st;
 
-  const int num_k_blocks = kpad / BK;
-  if (k_chunk <= 0) k_chunk = 256;   // measured on B200: 1.6e-6 max abs err (1024: 5e-6, unchunked: 1e-4)
-  int kb_per_chunk = max(1, k_chunk / BK);
-  HIA_CUDA(cudaFuncSetAttribute(syrk_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int bk = bk_of(prec);
+  const int num_k_blocks = kpad / bk;
+  // measured on B200 (3xTF32): k_chunk 256 -> 1.6e-6 max abs err (1024: 5e-6, unchunked: 1e-4). The
+  // error grows with the number of MMA steps in one TMEM chain; fp16 steps cover twice the K.
+  if (k_chunk <= 0) k_chunk = (prec == HIA_PREC_3XF16) ? 512 : 256;
+  const int kb_per_chunk = max(1, k_chunk / bk);
   const int grid = min(num_tiles, kNumSMs);
   static const int sync_every = getenv("HIA_SYRK_SYNC") ? atoi(getenv("HIA_SYRK_SYNC")) : kSyncEvery;
+  const int sync_arg = (sync_every >= kSyncEvery) ? sync_every : 0;
   HIA_CUDA(cudaMemsetAsync(sync_ctr, 0, (size_t)n_sync * 4, stream));
-  syrk_tf32x3_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_hi, map_lo, d_tiles, num_tiles, m,
-                                                                num_k_blocks, kb_per_chunk, out, ld_out,
-                                                                flavour, sync_ctr,
-                                                                (sync_every >= kSyncEvery) ? sync_every : 0,
-                                                                row0, min(row0 + rows, m), symmetric);
+  if (prec == HIA_PREC_3XF16) {
+    HIA_CUDA(cudaFuncSetAttribute(syrk_split3_kernel<HIA_PREC_3XF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    syrk_split3_kernel<HIA_PREC_3XF16><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
+        map_hi, map_lo, d_tiles, num_tiles, m, num_k_blocks, kb_per_chunk, out, ld_out, flavour, sync_ctr,
+        sync_arg, row0, min(row0 + rows, m), symmetric);
+  } else {
+    HIA_CUDA(cudaFuncSetAttribute(syrk_split3_kernel<HIA_PREC_3XTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    syrk_split3_kernel<HIA_PREC_3XTF32><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
+        map_hi, map_lo, d_tiles, num_tiles, m, num_k_blocks, kb_per_chunk, out, ld_out, flavour, sync_ctr,
+        sync_arg, row0, min(row0 + rows, m), symmetric);
+  }
   HIA_LAUNCH_CHECK();
   return HIA_OK;
 }
 
 // ------------------------------------------------------------------ row-sharded entry points
 // (the genome-wide high-resolution similarity is the one step with an
-//  exchange: every rank prepares the TF32 planes of ITS rows, the planes are all-gathered by the
+//  exchange: every rank prepares the hi/lo planes of ITS rows, the planes are all-gathered by the
 //  caller (NCCL), then every rank contracts its row block against all rows.)
-HIA_API int32_t hia_sim_kpad(int32_t k) { return hia::round_up(k, hia::BK); }
+HIA_API int32_t hia_sim_kpad(int32_t k, int precision) { return hia::round_up(k, hia::bk_of(precision)); }
+HIA_API int32_t hia_sim_plane_elem_bytes(int precision) { return hia::elem_bytes(precision); }
 
 HIA_API int hia_sim_prep_rows(const float* x_rows, int32_t rows, int32_t k, int64_t ld_x, int flavour,
-                              float* hi_rows, float* lo_rows, void* stream_) {
+                              int precision, void* hi_rows, void* lo_rows, void* stream_) {
   using namespace hia;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!x_rows || !hi_rows || !lo_rows || rows <= 0 || k <= 0 || ld_x < k) return HIA_ERR_BAD_ARG;
-  row_prep_kernel<<<rows, 256, 0, stream>>>(x_rows, rows, k, ld_x, round_up(k, BK),
-                                            flavour == HIA_SIM_PEARSON ? 1 : 0, hi_rows, lo_rows);
-  HIA_LAUNCH_CHECK();
-  return HIA_OK;
+  if (!x_rows || !hi_rows || !lo_rows || rows <= 0 || k <= 0 || ld_x < k || !split_prec(precision))
+    return HIA_ERR_BAD_ARG;
+  if (!aligned16(hi_rows) || !aligned16(lo_rows)) return HIA_ERR_ALIGN;
+  return launch_prep(x_rows, rows, k, ld_x, flavour == HIA_SIM_PEARSON ? 1 : 0, hi_rows, lo_rows, precision, stream);
 }
 
 HIA_API int64_t hia_sim_gemm_rows_workspace_bytes(int32_t n, int32_t k) {
@@ -612,13 +707,13 @@ HIA_API int64_t hia_sim_gemm_rows_workspace_bytes(int32_t n, int32_t k) {
   return (ntiles * (int64_t)sizeof(hia::TileCoord) + 1023) / 1024 * 1024 + sync_counters(n, k) * 4 + 1024;
 }
 
-HIA_API int hia_sim_gemm_rows(float* hi, float* lo, int32_t plane_rows, int32_t n, int32_t k, int32_t row0,
-                              int32_t rows, float* out_rows, int64_t ld_out, int flavour, int32_t k_chunk,
-                              void* workspace, int64_t workspace_bytes, void* stream_) {
+HIA_API int hia_sim_gemm_rows(void* hi, void* lo, int precision, int32_t plane_rows, int32_t n, int32_t k,
+                              int32_t row0, int32_t rows, float* out_rows, int64_t ld_out, int flavour,
+                              int32_t k_chunk, void* workspace, int64_t workspace_bytes, void* stream_) {
   using namespace hia;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!hi || !lo || !out_rows || !workspace || n <= 0 || k <= 0 || plane_rows < n || rows <= 0 ||
-      row0 < 0 || ld_out < n)
+      row0 < 0 || ld_out < n || !split_prec(precision))
     return HIA_ERR_BAD_ARG;
   if (row0 % BM) return HIA_ERR_ALIGN;                    // row blocks start on a 128-row tile boundary
   if (!aligned16(hi) || !aligned16(lo) || !aligned16(workspace)) return HIA_ERR_ALIGN;
@@ -626,7 +721,7 @@ HIA_API int hia_sim_gemm_rows(float* hi, float* lo, int32_t plane_rows, int32_t 
   const int64_t ntiles = (int64_t)((n + BM - 1) / BM) * ((n + BN - 1) / BN);
   const int64_t tiles_al = (ntiles * (int64_t)sizeof(TileCoord) + 1023) / 1024 * 1024;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
-  return launch_gemm(hi, lo, plane_rows, n, round_up(k, BK), row0, rows, 0, 0, -1, out_rows, ld_out, flavour,
-                     k_chunk, reinterpret_cast<TileCoord*>(ws), reinterpret_cast<unsigned int*>(ws + tiles_al),
-                     sync_counters(n, k), stream);
+  return launch_gemm(hi, lo, precision, plane_rows, n, round_up(k, bk_of(precision)), row0, rows, 0, 0, -1,
+                     out_rows, ld_out, flavour, k_chunk, reinterpret_cast<TileCoord*>(ws),
+                     reinterpret_cast<unsigned int*>(ws + tiles_al), sync_counters(n, k), stream);
 }

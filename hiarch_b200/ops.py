@@ -13,7 +13,11 @@ MTX_TRIU, MTX_ALL = 0, 1
 FILL_ZERO, FILL_MIN, FILL_BLOCK_MIN = 0, 1, 2
 OE_LOG, OE_ONLY_INTRA = 1, 2
 SIM_COSINE_DISTANCE, SIM_PEARSON = 0, 1
-PREC_3XTF32, PREC_FP64 = 0, 1
+PREC_3XTF32, PREC_FP64, PREC_3XF16 = 0, 1, 2
+# Default similarity precision: the fp16 hi/lo split (same 22-bit operands as 3xTF32, half the
+# tensor time; header of csrc/hia_syrk.cu). 3XTF32 and FP64 stay selectable per call.
+PREC_DEFAULT = PREC_3XF16
+SPLIT_PRECS = (PREC_3XTF32, PREC_3XF16)
 
 
 def _ptr(t):
@@ -177,13 +181,14 @@ def log_map(x, out=None):
 _ws_cache = {}
 
 
-def similarity(x, flavour=SIM_COSINE_DISTANCE, precision=PREC_3XTF32, band=None, k_chunk=0,
+def similarity(x, flavour=SIM_COSINE_DISTANCE, precision=None, band=None, k_chunk=0,
                out=None, workspace=None):
     """Row x row cosine distance / Pearson of an [m, k] fp32 block -> [m, m] fp32.
     Replaces get_adj_mtx (publish/complex/src/S1_get_adj_mtx.py:8-14)."""
     lib = _lib.load()
     _need_cuda(x)
     assert x.dtype == torch.float32 and x.stride(1) == 1
+    precision = PREC_DEFAULT if precision is None else precision
     m, k = x.shape
     if out is None:
         out = alloc_map(m, x.device)
@@ -343,7 +348,7 @@ def band_entropy(adj, d_lo, d_hi, per=2):
     return out
 
 
-def get_local(block, L=None, short_dis_max_per=.15, precision=PREC_3XTF32):
+def get_local(block, L=None, short_dis_max_per=.15, precision=None):
     """Checkerboard score of one dense block (rows x cols view of a min-filled symmetric map).
     publish/complex/src/main_local.py:19-55. L = mean chromosome length of the block's row
     window (S2_get_entro.py:6-10); defaults to the number of rows. Returns float or None."""
@@ -359,9 +364,10 @@ def get_local(block, L=None, short_dis_max_per=.15, precision=PREC_3XTF32):
         tmp.copy_(block)
         block = tmp
     n = block.shape[0]
+    precision = PREC_DEFAULT if precision is None else precision
     # only the tiles of the distance matrix that touch the band are computed
     adj = similarity(block, flavour=SIM_COSINE_DISTANCE, precision=precision,
-                     band=(smin, min(smax - 1, n - 1)) if precision == PREC_3XTF32 else None,
+                     band=(smin, min(smax - 1, n - 1)) if precision in SPLIT_PRECS else None,
                      out=alloc_map(n, block.device))
     res = band_entropy(adj, smin, smax).cpu().numpy()
     return None if res[1] == 0 else float(res[0])

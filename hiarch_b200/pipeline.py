@@ -13,7 +13,7 @@ from . import _lib, ops
 
 class HotPath:
     def __init__(self, seps, bin_size, k_eig=3, flavour=ops.SIM_PEARSON, device="cuda",
-                 max_nnz=None, eig_block=8, eig_steps=12):
+                 max_nnz=None, eig_block=8, eig_steps=12, precision=None):
         self.lib = _lib.load()
         self.layout = ops.GenomeLayout(seps, device)
         self.n = self.layout.n
@@ -26,7 +26,9 @@ class HotPath:
         self.oe = ops.alloc_map(n, device)           # O/E + log
         self.sim = ops.alloc_map(n, device)          # Pearson / cosine distance
         self.oe_state = ops.OEState(self.layout)
-        self.sim_ws = torch.empty(self.lib.hia_similarity_workspace_bytes(n, n, ops.PREC_3XTF32),
+        self.precision = ops.PREC_DEFAULT if precision is None else precision
+        assert self.precision in ops.SPLIT_PRECS
+        self.sim_ws = torch.empty(self.lib.hia_similarity_workspace_bytes(n, n, self.precision),
                                   dtype=torch.uint8, device=device)
         self.eig_block, self.eig_steps = eig_block, eig_steps
         self.layout.oe_tables(self.bin_size)         # build + upload the SGD pooling tables once
@@ -46,13 +48,13 @@ class HotPath:
 
     def similarity_prep(self):
         st = self.lib.hia_similarity_prep(self.oe.data_ptr(), self.n, self.n, self.oe.stride(0),
-                                          self.flavour, self.sim_ws.data_ptr(), self.sim_ws.numel(),
-                                          ops._stream())
+                                          self.flavour, self.precision, self.sim_ws.data_ptr(),
+                                          self.sim_ws.numel(), ops._stream())
         _lib.check(st, "hia_similarity_prep")
 
     def similarity_gemm(self):
         st = self.lib.hia_similarity_gemm(self.n, self.n, self.sim.data_ptr(), self.sim.stride(0),
-                                          self.flavour, 0, -1, 0, self.sim_ws.data_ptr(),
+                                          self.flavour, self.precision, 0, -1, 0, self.sim_ws.data_ptr(),
                                           self.sim_ws.numel(), ops._stream())
         _lib.check(st, "hia_similarity_gemm")
 

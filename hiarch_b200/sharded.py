@@ -4,7 +4,8 @@ The single exchange step of the hot path (BASELINE.json co
 123 541 bins = 61 GB per fp32 map, too large for one pass on one GPU). Rank r owns the rows
 [r * per, (r + 1) * per) of the normalised map, `per` a multiple of the 128-row MMA tile:
 
-  1. every rank builds the unit-norm TF32 hi/lo planes of ITS rows            (hia_sim_prep_rows)
+  1. every rank builds the unit-norm hi/lo planes of ITS rows (fp16 split by   (hia_sim_prep_rows)
+     default: 2 x 2 B/cell to exchange instead of 2 x 4)
   2. NCCL all-gather of the planes over NVLink (torch.distributed)            -> full planes
   3. every rank contracts its row block against all rows on tcgen05           (hia_sim_gemm_rows)
   4. eigenvectors: block Lanczos where the only pass over the matrix,
@@ -27,7 +28,7 @@ def rows_per_rank(n, world):
 
 
 class ShardedSimilarity:
-    def __init__(self, n, k, flavour=ops.SIM_PEARSON, group=None, device=None):
+    def __init__(self, n, k, flavour=ops.SIM_PEARSON, group=None, device=None, precision=None):
         self.lib = _lib.load()
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -38,12 +39,15 @@ class ShardedSimilarity:
         self.n_pad = self.per * self.world
         self.row0 = self.rank * self.per
         self.rows = max(0, min(n, self.row0 + self.per) - self.row0)
-        self.kpad = self.lib.hia_sim_kpad(k)
+        self.precision = ops.PREC_DEFAULT if precision is None else precision
+        assert self.precision in ops.SPLIT_PRECS
+        self.kpad = self.lib.hia_sim_kpad(k, self.precision)
+        pdt = torch.float16 if self.lib.hia_sim_plane_elem_bytes(self.precision) == 2 else torch.float32
         # full planes (all-gather targets); rows >= n stay zero
-        self.hi = torch.zeros((self.n_pad, self.kpad), dtype=torch.float32, device=self.device)
-        self.lo = torch.zeros((self.n_pad, self.kpad), dtype=torch.float32, device=self.device)
-        self.own_hi = torch.zeros((self.per, self.kpad), dtype=torch.float32, device=self.device)
-        self.own_lo = torch.zeros((self.per, self.kpad), dtype=torch.float32, device=self.device)
+        self.hi = torch.zeros((self.n_pad, self.kpad), dtype=pdt, device=self.device)
+        self.lo = torch.zeros((self.n_pad, self.kpad), dtype=pdt, device=self.device)
+        self.own_hi = torch.zeros((self.per, self.kpad), dtype=pdt, device=self.device)
+        self.own_lo = torch.zeros((self.per, self.kpad), dtype=pdt, device=self.device)
         self.ws = torch.empty(self.lib.hia_sim_gemm_rows_workspace_bytes(n, k), dtype=torch.uint8,
                               device=self.device)
 
@@ -54,7 +58,8 @@ class ShardedSimilarity:
         assert x_rows.shape == (self.rows, self.k) and x_rows.dtype == torch.float32
         if self.rows > 0:
             st = lib.hia_sim_prep_rows(x_rows.data_ptr(), self.rows, self.k, x_rows.stride(0), self.flavour,
-                                       self.own_hi.data_ptr(), self.own_lo.data_ptr(), ops._stream())
+                                       self.precision, self.own_hi.data_ptr(), self.own_lo.data_ptr(),
+                                       ops._stream())
             _lib.check(st, "hia_sim_prep_rows")
         if self.world > 1:
             dist.all_gather_into_tensor(self.hi.view(-1), self.own_hi.view(-1), group=self.group)
@@ -66,7 +71,8 @@ class ShardedSimilarity:
             out_rows = torch.empty((max(self.rows, 1), ops.padded_ld(self.n)), dtype=torch.float32,
                                    device=self.device)[:self.rows, :self.n]
         if self.rows > 0:
-            st = lib.hia_sim_gemm_rows(self.hi.data_ptr(), self.lo.data_ptr(), self.n_pad, self.n, self.k,
+            st = lib.hia_sim_gemm_rows(self.hi.data_ptr(), self.lo.data_ptr(), self.precision, self.n_pad,
+                                       self.n, self.k,
                                        self.row0, self.rows, out_rows.data_ptr(), out_rows.stride(0),
                                        self.flavour, k_chunk, self.ws.data_ptr(), self.ws.numel(),
                                        ops._stream())

@@ -159,6 +159,9 @@ int hia_log_map(const float* x, float* out, int32_t rows, int32_t cols, int64_t 
 #define HIA_SIM_PEARSON 1           /* out = corr,     exact 1 diagonal                    */
 #define HIA_PREC_3XTF32 0           /* tcgen05 kind::tf32, hi/lo split, fp32 accumulate    */
 #define HIA_PREC_FP64 1             /* FP64 DMMA (mma.sync m8n8k4), fp64 accumulate        */
+#define HIA_PREC_3XF16 2            /* tcgen05 kind::f16, hi/lo split of the row scaled by 2^14 (fp16 has
+                                       TF32's 11-bit significand: same 22 bits, K = 16 per MMA instead of
+                                       8 -> half the tensor time and half the plane bytes), fp32 accumulate */
 /* X is m x k (ld_x), out is m x m (ld_out). band_lo/band_hi (in bins, band_hi < 0 = all):
  * only tiles intersecting band_lo <= |i-j| <= band_hi are computed (checkerboard needs
  * 5%..15% of the chromosome length only); other cells of `out` are left untouched.
@@ -169,12 +172,13 @@ int hia_similarity(const float* x, int32_t m, int32_t k, int64_t ld_x, float* ou
                    int flavour, int precision, int32_t band_lo, int32_t band_hi, int32_t k_chunk,
                    void* workspace, int64_t workspace_bytes, void* stream);
 
-/* The two phases of hia_similarity(precision = 3xTF32) as separate calls, so that a caller
- * can time (or overlap) them: prep = fp64 row statistics + TF32 hi/lo planes into the workspace
- * (12 B/cell, HBM-bound); gemm = the tcgen05 contraction + epilogue (tensor-bound). */
-int hia_similarity_prep(const float* x, int32_t m, int32_t k, int64_t ld_x, int flavour,
+/* The two phases of hia_similarity(precision = 3XTF32 | 3XF16) as separate calls, so that a
+ * caller can time (or overlap) them: prep = fp64 row statistics + hi/lo planes into the workspace
+ * (4 B/cell read + 8 (tf32) or 4 (f16) B/cell written, HBM-bound); gemm = the tcgen05 contraction
+ * + epilogue (tensor-bound). The workspace must be sized for the same precision. */
+int hia_similarity_prep(const float* x, int32_t m, int32_t k, int64_t ld_x, int flavour, int precision,
                         void* workspace, int64_t workspace_bytes, void* stream);
-int hia_similarity_gemm(int32_t m, int32_t k, float* out, int64_t ld_out, int flavour,
+int hia_similarity_gemm(int32_t m, int32_t k, float* out, int64_t ld_out, int flavour, int precision,
                         int32_t band_lo, int32_t band_hi, int32_t k_chunk, void* workspace,
                         int64_t workspace_bytes, void* stream);
 
@@ -284,17 +288,19 @@ int hia_gf_pool_scores(const float* x, int64_t ld, const int32_t* pairs8, int32_
                        double* isym, double* xs, double* scores, void* stream);
 
 /* Row-sharded similarity (the one exchange step of the path): every rank
- * prepares the TF32 hi/lo planes of ITS rows (hia_sim_prep_rows; planes are row-major with
- * hia_sim_kpad(k) columns), the caller all-gathers the planes (NCCL), then every rank contracts
+ * prepares the hi/lo planes of ITS rows (hia_sim_prep_rows; planes are row-major with
+ * hia_sim_kpad(k, precision) columns of hia_sim_plane_elem_bytes(precision) bytes: fp32 for
+ * 3XTF32, fp16 for 3XF16), the caller all-gathers the planes (NCCL), then every rank contracts
  * its row block [row0, row0 + rows) against all rows (hia_sim_gemm_rows; row0 % 128 == 0).
  * plane_rows >= n rows are addressable in hi/lo (rows >= n must be zero). out_rows: rows x n. */
-int32_t hia_sim_kpad(int32_t k);
+int32_t hia_sim_kpad(int32_t k, int precision);
+int32_t hia_sim_plane_elem_bytes(int precision);
 int hia_sim_prep_rows(const float* x_rows, int32_t rows, int32_t k, int64_t ld_x, int flavour,
-                      float* hi_rows, float* lo_rows, void* stream);
+                      int precision, void* hi_rows, void* lo_rows, void* stream);
 int64_t hia_sim_gemm_rows_workspace_bytes(int32_t n, int32_t k);
-int hia_sim_gemm_rows(float* hi, float* lo, int32_t plane_rows, int32_t n, int32_t k, int32_t row0,
-                      int32_t rows, float* out_rows, int64_t ld_out, int flavour, int32_t k_chunk,
-                      void* workspace, int64_t workspace_bytes, void* stream);
+int hia_sim_gemm_rows(void* hi, void* lo, int precision, int32_t plane_rows, int32_t n, int32_t k,
+                      int32_t row0, int32_t rows, float* out_rows, int64_t ld_out, int flavour,
+                      int32_t k_chunk, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
 /* a9  top-k eigenvectors of a dense symmetric fp32 matrix (largest algebraic).          */

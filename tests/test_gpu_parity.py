@@ -167,7 +167,7 @@ def _sim_ref(x64, flavour):
 
 @pytest.mark.parametrize("m,k", [(50, 50), (130, 77), (257, 300), (640, 1000), (1000, 33)])
 @pytest.mark.parametrize("flavour", [0, 1])
-@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("precision", [0, 1, 2])        # 3xTF32, FP64 DMMA, 3xF16
 def test_similarity_small(m, k, flavour, precision):
     from hiarch_b200 import ops
     rng = np.random.default_rng(m * 1000 + k)
@@ -178,7 +178,7 @@ def test_similarity_small(m, k, flavour, precision):
     xd.copy_(_dev(x, torch.float32))
     got = ops.similarity(xd, flavour=flavour, precision=precision).cpu().numpy().astype(np.float64)
     ref = _sim_ref(x.astype(np.float64), flavour)
-    assert np.abs(got - ref).max() <= (ATOL if precision == 0 else 5e-7)
+    assert np.abs(got - ref).max() <= (5e-7 if precision == 1 else ATOL)
     assert np.array_equal(got, got.T)
     assert np.all(np.diag(got) == (0.0 if flavour == 0 else 1.0))
 
@@ -194,14 +194,38 @@ def test_similarity_long_k_chunked_accumulation():
     xd.copy_(_dev(x, torch.float32))
     ref = O.pearson(x.astype(np.float64))
     refc = O.cosine_distance(x.astype(np.float64))
-    for k_chunk in (256, 1024, 1 << 20):
-        got = ops.similarity(xd, flavour=1, k_chunk=k_chunk).cpu().numpy().astype(np.float64)
-        err = np.abs(got - ref).max()
-        print(f"pearson k_chunk={k_chunk}: max abs err {err:.3e}")
-        if k_chunk <= 1024:
-            assert err <= ATOL
-    got = ops.similarity(xd, flavour=0).cpu().numpy().astype(np.float64)
-    assert np.abs(got - refc).max() <= ATOL
+    for precision in (ops.PREC_3XTF32, ops.PREC_3XF16):
+        for k_chunk in (0, 256, 1024, 1 << 20):              # 0 = the precision's default
+            got = ops.similarity(xd, flavour=1, k_chunk=k_chunk, precision=precision).cpu().numpy().astype(np.float64)
+            err = np.abs(got - ref).max()
+            print(f"pearson precision={precision} k_chunk={k_chunk}: max abs err {err:.3e}")
+            if k_chunk <= 1024:
+                assert err <= ATOL
+        got = ops.similarity(xd, flavour=0, precision=precision).cpu().numpy().astype(np.float64)
+        assert np.abs(got - refc).max() <= ATOL
+
+
+def test_similarity_f16_split_extreme_rows():
+    """3xF16 planes hold the unit row scaled by 2^14: rows dominated by ONE entry (|xn| -> 1, the
+    fp16 range limit), rows with a huge dynamic range (tiny entries fall into fp16 subnormals) and
+    an all-zero row (NaN like pdist) must behave like the fp64 reference."""
+    from hiarch_b200 import ops
+    rng = np.random.default_rng(9)
+    m, k = 300, 1500
+    x = rng.standard_normal((m, k)).astype(np.float32)
+    x[0, :] = 0.0; x[0, 7] = 5.0                              # a single non-zero entry: xn = 1 exactly
+    x[1, :] *= 1e-4; x[1, 11] = 1e3                           # one dominant + tiny entries
+    x[2, :] = np.exp(rng.uniform(-18, 4, k)).astype(np.float32)     # 9 decades of dynamic range
+    x[3, :] = 0.0                                             # zero row
+    xd = ops.alloc_map(m, cols=k)
+    xd.copy_(_dev(x, torch.float32))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ref = O.cosine_distance(x.astype(np.float64))
+    got = ops.similarity(xd, flavour=0, precision=ops.PREC_3XF16).cpu().numpy().astype(np.float64)
+    ok = np.ones(m, bool); ok[3] = False
+    assert np.abs(got[np.ix_(ok, ok)] - ref[np.ix_(ok, ok)]).max() <= ATOL
+    off = np.arange(m) != 3
+    assert np.all(np.isnan(got[3, off])) and np.all(np.isnan(got[off, 3]))
 
 
 def test_similarity_golden_adj_and_band(golden):

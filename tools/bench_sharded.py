@@ -161,8 +161,9 @@ def main():
     for _ in range(24):
         i = int(rng.integers(0, sh.rows)) if sh.rows else 0
         j = int(rng.integers(0, n))
-        a = (sh.hi[sh.row0 + i].double() + sh.lo[sh.row0 + i].double())
-        b = (sh.hi[j].double() + sh.lo[j].double())
+        unscale = 2.0 ** -14 if sh.hi.dtype == torch.float16 else 1.0     # 3xF16 planes are scaled by 2^14
+        a = (sh.hi[sh.row0 + i].double() + sh.lo[sh.row0 + i].double()) * unscale
+        b = (sh.hi[j].double() + sh.lo[j].double()) * unscale
         ref = float(a @ b)
         ref = 1.0 if (sh.row0 + i) == j else max(-1.0, min(1.0, ref))
         errs.append(abs(float(out[i, j]) - ref))
@@ -176,8 +177,9 @@ def main():
                "oe_log_ms": (oe_ms[-1] if oe_ms else None),
                "similarity_ms": sim, "eig_ms": eig,
                "cells_per_s": cells / ((sim + eig + (oe_ms[-1] if oe_ms else 0.0)) * 1e-3),
-               "executed_tf32_tflops_per_gpu": 3 * 2 * float(sh.per) * n * n / (sim * 1e-3) / 1e12,
-               "allgather_bytes_per_rank": 2 * (world - 1) * sh.per * sh.kpad * 4,
+               "precision": {0: "tf32x3", 2: "f16x3"}[sh.precision],
+               "executed_mma_tflops_per_gpu": 3 * 2 * float(sh.per) * n * n / (sim * 1e-3) / 1e12,
+               "allgather_bytes_per_rank": 2 * (world - 1) * sh.per * sh.kpad * sh.hi.element_size(),
                "max_abs_err_vs_fp64_spotcheck": err}
         if not args.no_eig:
             rec["eigvals"] = [float(t) for t in w.cpu().numpy()]

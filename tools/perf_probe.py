@@ -75,26 +75,27 @@ def main():
         state.min_pos_oe.data_ptr(), 1, st))
     res["oe_apply_log"] = dict(ms=best, gbs=8 * cells / 1e9 / best * 1e3)
     print(json.dumps(res), flush=True)
-    # similarity
+    # similarity: both operand splits
     m = n if args.sim_rows == 0 else min(n, args.sim_rows)
     x = oe[:m]
     simout = ops.alloc_map(m)
-    need = lib.hia_similarity_workspace_bytes(m, n, 0)
-    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
-    best, med = timeit(lambda: ops.similarity(x, flavour=1, out=simout, workspace=ws, k_chunk=args.k_chunk), reps=2)
-    # logical flops of the computed (upper) tiles ~ m*m*k (half of 2*m*m*k)
-    res["similarity_3xtf32"] = dict(ms=best, m=m, k=n, logical_tflops_half=m * m * n / best / 1e9,
-                                    executed_tf32_tflops=3 * m * m * n / best / 1e9)
-    print(json.dumps(res), flush=True)
-    # accuracy spot check vs fp64 on a sub-block
     sub = 256
     xs = x[:sub].double()
     xs = xs - xs.mean(dim=1, keepdim=True)
     xs = xs / xs.norm(dim=1, keepdim=True)
     ref = xs @ xs.T
-    err = (simout[:sub, :sub].double() - ref).abs()
-    err.fill_diagonal_(0)
-    print("similarity max abs err vs fp64 (256x256 corner):", float(err.max()), flush=True)
+    for prec, name in ((ops.PREC_3XTF32, "tf32x3"), (ops.PREC_3XF16, "f16x3")):
+        ws = torch.empty(lib.hia_similarity_workspace_bytes(m, n, prec), dtype=torch.uint8, device="cuda")
+        bp, _ = timeit(lambda: lib.hia_similarity_prep(x.data_ptr(), m, n, x.stride(0), 1, prec, ws.data_ptr(), ws.numel(), st), reps=3)
+        best, med = timeit(lambda: lib.hia_similarity_gemm(m, n, simout.data_ptr(), simout.stride(0), 1, prec, 0, -1,
+                                                           args.k_chunk, ws.data_ptr(), ws.numel(), st), reps=2)
+        err = (simout[:sub, :sub].double() - ref).abs()
+        err.fill_diagonal_(0)
+        # logical flops of the computed (upper) tiles ~ m*m*k (half of 2*m*m*k)
+        res[f"similarity_{name}"] = dict(prep_ms=bp, gemm_ms=best, m=m, k=n, logical_tflops_half=m * m * n / best / 1e9,
+                                         executed_mma_tflops=3 * m * m * n / best / 1e9, max_abs_err_corner=float(err.max()))
+        print(json.dumps(res[f"similarity_{name}"]), flush=True)
+        del ws
     t0 = time.time()
     w, v, info = ops.topk_eig(simout, k=3, return_info=True)
     torch.cuda.synchronize()

@@ -36,27 +36,36 @@
 namespace hia {
 namespace {
 
-constexpr int BM = 128;
-constexpr int BN = 256;
+constexpr int BM = 128;                        // rows of A per CTA
+constexpr int BN = 256;                        // columns of the tile (rows of B)
 constexpr int ROW_BYTES = 128;                 // one SW128 atom of K per row and k-block
 constexpr int UMMA_K_BYTES = 32;               // K extent of one MMA instruction, all kinds
-constexpr int STAGES = 2;
 constexpr int A_BYTES = BM * ROW_BYTES;        // 16 KB
-constexpr int B_BYTES = BN * ROW_BYTES;        // 32 KB
 // elements per k-block: 32 (tf32 planes, fp32 storage) or 64 (fp16 planes)
 __host__ __device__ constexpr int bk_of(int prec) { return prec == HIA_PREC_3XF16 ? 64 : 32; }
 __host__ __device__ constexpr int elem_bytes(int prec) { return prec == HIA_PREC_3XF16 ? 2 : 4; }
 constexpr float kF16Scale = 16384.f;                         // 2^14
 constexpr float kF16Unscale = 1.f / (16384.f * 16384.f);     // 2^-28
-constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // hi + lo planes: 96 KB
 constexpr int EPI_WARPS = 8;                   // 2 per TMEM lane quarter x 128 columns each
 constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr int TRANS_PAD = 33;
-constexpr int SMEM_TILES = STAGES * STAGE_BYTES;                      // 196608
 constexpr int SMEM_TRANS = EPI_WARPS * 32 * TRANS_PAD * 4;            // 16896
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + SMEM_TILES + SMEM_TRANS + 256 /*barriers*/;
 constexpr int TMEM_COLS = 512;
-constexpr unsigned long long kSpinLimit = 1ull << 27;
+
+// CTAS = 1: one CTA per 128 x 256 tile (cta_group::1).
+// CTAS = 2: a CTA pair (cluster of 2 on one TPC, cta_group::2) per 256 x 256 tile: each CTA stages
+//           its 128 rows of A and HALF of B (128 of the 256 B rows); the pair's tensor cores read
+//           both halves. Per CTA and k-block that is 64 KB of TMA writes + 8 KB of operand reads
+//           per MMA instead of 96 KB + 12 KB: the 1-CTA kernel was shared-memory-bandwidth bound
+//           (156 B/clk demanded of 128 B/clk -> 78 % tensor-pipe activity measured).
+template <int CTAS> struct Geo {
+  static constexpr int B_ROWS = BN / CTAS;
+  static constexpr int B_BYTES = B_ROWS * ROW_BYTES;              // 32 KB | 16 KB
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);     // hi + lo planes: 96 KB | 64 KB
+  static constexpr int STAGES = (CTAS == 2) ? 3 : 2;
+  static constexpr int SMEM_TILES = STAGES * STAGE_BYTES;         // 192 KB
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + SMEM_TILES + SMEM_TRANS + 256 /*barriers*/;
+};
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -72,6 +81,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      :: "r"(smem_u32(bar)), "r"(rank) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -81,19 +98,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug traps (kernel error) after ~4 s instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  unsigned long long spins = 0;
+  unsigned int spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) __trap();
+    if ((++spins & 0x3fffu) == 0) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
   }
 }
+template <int CTAS>
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar,
                                             int c_inner, int c_outer) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
+  if constexpr (CTAS == 2) {
+    // executed by both CTAs of the pair; the peer bit of the barrier address is cleared so that
+    // the transaction bytes land on the LEADER's barrier (cute SM100_TMA_2SM_LOAD)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
+  }
 }
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -101,26 +139,33 @@ __device__ __forceinline__ void tcgen05_fence_before() {
 __device__ __forceinline__ void tcgen05_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-template <int PREC>
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int PREC, int CTAS>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                      uint32_t idesc, uint32_t accumulate) {
-  if constexpr (PREC == HIA_PREC_3XF16) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-  }
+#define HIA_UMMA(GROUP, KIND)                                                              \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                           \
+               "tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%0], %1, %2, %3, p;\n\t}" \
+               :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory")
+  if constexpr (PREC == HIA_PREC_3XF16 && CTAS == 2) HIA_UMMA("2", "f16");
+  else if constexpr (PREC == HIA_PREC_3XF16) HIA_UMMA("1", "f16");
+  else if constexpr (CTAS == 2) HIA_UMMA("2", "tf32");
+  else HIA_UMMA("1", "tf32");
+#undef HIA_UMMA
 }
+// MMA completion -> mbarrier (of this CTA, or of both CTAs of the pair at the same offset)
+template <int CTAS>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-               :: "r"(smem_u32(bar)) : "memory");
+  if constexpr (CTAS == 2) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"(smem_u32(bar)) : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -149,61 +194,75 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a/b format [7,10),[10,13)
-// (F16 = 0, TF32 = 2), K-major both, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t idesc_of(int prec) {
+// (F16 = 0, TF32 = 2), K-major both, N>>3 at [17,23), M>>4 at [24,29) (M = 256 for the CTA pair).
+__host__ __device__ constexpr uint32_t idesc_of(int prec, int ctas) {
   const uint32_t fmt = prec == HIA_PREC_3XF16 ? 0u : 2u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)((BM * ctas) >> 4) << 24);
 }
 
-struct TileCoord { int m_blk; int n_blk; };
+struct TileCoord { int m0; int n0; };            // first row / first column of a TILE_M x BN tile
 
 // ------------------------------------------------------------------ the kernel
-template <int PREC>
+template <int PREC, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                    const TileCoord* __restrict__ tiles, int num_tiles, int m, int num_k_blocks,
                    int kb_per_chunk, float* __restrict__ out, long long ld_out, int flavour,
                    unsigned int* __restrict__ sync_ctr, int sync_every, int row0, int row_end,
                    int symmetric) {
+  using G = Geo<CTAS>;
+  constexpr int STAGES = G::STAGES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  float* s_trans = reinterpret_cast<float*>(smem + SMEM_TILES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_TILES + SMEM_TRANS);
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  float* s_trans = reinterpret_cast<float*>(smem + G::SMEM_TILES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::SMEM_TILES + SMEM_TRANS);
+  uint64_t* full_bar = bars;                 // [STAGES]   (pair: the leader's is the one used)
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]   (pair: one per CTA, multicast commit)
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]        (pair: one per CTA, multicast commit)
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]    (pair: the leader's, both CTAs' epilogues arrive)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  uint32_t cta_rank = 0;
+  if constexpr (CTAS == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const int unit = blockIdx.x / CTAS;               // tile-processing unit: a CTA or a CTA pair
+  const int num_units = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_lo) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();   // barriers visible to the peer too
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int chunks_per_tile = (num_k_blocks + kb_per_chunk - 1) / kb_per_chunk;
 
   if (warp == 0) {
-    // ===================================================== TMA producer
+    // ===================================================== TMA producer (one per CTA)
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = tiles[t].m_blk * BM, n0 = tiles[t].n_blk * BN;
+      for (int t = unit; t < num_tiles; t += num_units) {
+        const int m0 = tiles[t].m0 + (int)cta_rank * BM;             // this CTA's rows of A
+        const int nb0 = tiles[t].n0 + (int)cta_rank * G::B_ROWS;     // this CTA's rows of B
         for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           if (sync_every > 0 && (it % sync_every) == 0) {
@@ -212,8 +271,8 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             // apart over a 1.4 ms tile and every operand tile is re-read from HBM).
             // Timing only -- bounded wait, then proceed: cannot deadlock, carries no data.
             const uint32_t step = it / sync_every;
-            const int seq = (t - (int)blockIdx.x) / (int)gridDim.x;
-            const uint32_t expected = (uint32_t)min((int)gridDim.x, num_tiles - seq * (int)gridDim.x);
+            const int seq = (t - unit) / num_units;
+            const uint32_t expected = (uint32_t)(CTAS * min(num_units, num_tiles - seq * num_units));
             atomicAdd(&sync_ctr[step], 1u);
             for (int spin = 0; spin < 256; ++spin) {
               if (*reinterpret_cast<volatile unsigned int*>(&sync_ctr[step]) >= expected) break;
@@ -221,26 +280,30 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             }
           }
           mbar_wait(&empty_bar[s], ph ^ 1);
-          unsigned char* st = smem + s * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          unsigned char* st = smem + s * G::STAGE_BYTES;
+          // the leader's barrier counts the bytes of BOTH CTAs of a pair
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[s], G::STAGE_BYTES * CTAS);
           const int k0 = kb * bk_of(PREC);
-          tma_load_2d(st, &map_hi, &full_bar[s], k0, m0);                               // A hi
-          tma_load_2d(st + A_BYTES, &map_lo, &full_bar[s], k0, m0);                     // A lo
-          tma_load_2d(st + 2 * A_BYTES, &map_hi, &full_bar[s], k0, n0);                 // B hi [0,128)
-          tma_load_2d(st + 2 * A_BYTES + A_BYTES, &map_hi, &full_bar[s], k0, n0 + BM);  // B hi [128,256)
-          tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_lo, &full_bar[s], k0, n0);       // B lo
-          tma_load_2d(st + 2 * A_BYTES + B_BYTES + A_BYTES, &map_lo, &full_bar[s], k0, n0 + BM);
+          tma_load_2d<CTAS>(st, &map_hi, &full_bar[s], k0, m0);                               // A hi
+          tma_load_2d<CTAS>(st + A_BYTES, &map_lo, &full_bar[s], k0, m0);                     // A lo
+          unsigned char* sb = st + 2 * A_BYTES;
+          tma_load_2d<CTAS>(sb, &map_hi, &full_bar[s], k0, nb0);                              // B hi
+          tma_load_2d<CTAS>(sb + G::B_BYTES, &map_lo, &full_bar[s], k0, nb0);                 // B lo
+          if constexpr (CTAS == 1) {                                                         // rows [128,256) of B
+            tma_load_2d<CTAS>(sb + A_BYTES, &map_hi, &full_bar[s], k0, nb0 + BM);
+            tma_load_2d<CTAS>(sb + G::B_BYTES + A_BYTES, &map_lo, &full_bar[s], k0, nb0 + BM);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one thread)
-    if (lane == 0) {
+    // ===================================================== MMA issuer (one thread; pair: the leader's)
+    if (lane == 0 && cta_rank == 0) {
       uint32_t it = 0, chunk_it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = unit; t < num_tiles; t += num_units) {
         for (int ch = 0; ch < chunks_per_tile; ++ch, ++chunk_it) {
           const uint32_t buf = chunk_it & 1, tph = (chunk_it >> 1) & 1;
-          mbar_wait(&tempty_bar[buf], tph ^ 1);           // epilogue drained this accumulator
+          mbar_wait(&tempty_bar[buf], tph ^ 1);           // epilogue(s) drained this accumulator
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
           const int kb_end = min(num_k_blocks, (ch + 1) * kb_per_chunk);
@@ -248,24 +311,24 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(&full_bar[s], ph);
             tcgen05_fence_after();
-            const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+            const uint32_t st = smem_u32(smem + s * G::STAGE_BYTES);
             const uint64_t a_hi = make_kmajor_sw128_desc(st);
             const uint64_t a_lo = make_kmajor_sw128_desc(st + A_BYTES);
             const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * A_BYTES);
-            const uint64_t b_lo = make_kmajor_sw128_desc(st + 2 * A_BYTES + B_BYTES);
-            constexpr uint32_t kIdesc = idesc_of(PREC);
+            const uint64_t b_lo = make_kmajor_sw128_desc(st + 2 * A_BYTES + G::B_BYTES);
+            constexpr uint32_t kIdesc = idesc_of(PREC, CTAS);
 #pragma unroll
             for (int j = 0; j < ROW_BYTES / UMMA_K_BYTES; ++j) {
               const uint64_t adv = (uint64_t)((j * UMMA_K_BYTES) >> 4);   // +32 B per k-step
               const uint32_t first = (kb == ch * kb_per_chunk && j == 0) ? 0u : 1u;
               // small cross terms first, the dominant hi.hi term last
-              umma<PREC>(d_tmem, a_lo + adv, b_hi + adv, kIdesc, first);
-              umma<PREC>(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
-              umma<PREC>(d_tmem, a_hi + adv, b_hi + adv, kIdesc, 1u);
+              umma<PREC, CTAS>(d_tmem, a_lo + adv, b_hi + adv, kIdesc, first);
+              umma<PREC, CTAS>(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+              umma<PREC, CTAS>(d_tmem, a_hi + adv, b_hi + adv, kIdesc, 1u);
             }
-            umma_commit(&empty_bar[s]);                   // frees the smem stage when MMAs retire
+            umma_commit<CTAS>(&empty_bar[s]);             // frees the smem stage (of both CTAs) when MMAs retire
           }
-          umma_commit(&tfull_bar[buf]);                   // accumulator chunk complete
+          umma_commit<CTAS>(&tfull_bar[buf]);             // accumulator chunk complete (in both CTAs)
         }
       }
     }
@@ -274,12 +337,13 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter split the 256
     // accumulator columns. The fp32 running sums of the K chunks live in REGISTERS (128 per
     // thread): a chunk costs 4 x (tcgen05.ld + 32 FADD) per warp, no memory traffic.
+    // (pair: each CTA's TMEM holds ITS 128 rows of the 256 x 256 accumulator.)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     float* trans = s_trans + (warp - 2) * 32 * TRANS_PAD;
     uint32_t chunk_it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = tiles[t].m_blk * BM, n0 = tiles[t].n_blk * BN + half * (BN / 2);
+    for (int t = unit; t < num_tiles; t += num_units) {
+      const int m0 = tiles[t].m0 + (int)cta_rank * BM, n0 = tiles[t].n0 + half * (BN / 2);
       float accr[BN / 2];
 #pragma unroll
       for (int j = 0; j < BN / 2; ++j) accr[j] = 0.f;
@@ -297,7 +361,10 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);       // accumulator buffer is free again
+        if (lane == 0) {                                    // accumulator buffer is free again
+          if constexpr (CTAS == 2) mbar_arrive_cluster(&tempty_bar[buf], 0);
+          else mbar_arrive(&tempty_bar[buf]);
+        }
       }
       // ---- finalize + store (overlaps the next tile's MMAs)
       const int gr_base = m0 + q * 32;                      // first global row of this warp
@@ -342,12 +409,16 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     }
   }
 
+  __syncwarp();
   tcgen05_fence_before();
-  __syncthreads();
+  // pair: neither CTA may exit (or free TMEM) while the other can still touch its barriers / smem
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
-                 :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -486,22 +557,22 @@ int make_plane_map(CUtensorMap* map, void* base, int rows, int kpad, int prec) {
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 inline bool split_prec(int p) { return p == HIA_PREC_3XTF32 || p == HIA_PREC_3XF16; }
 
-// Tiles touching the upper triangle and the band, in super-blocks for L2 reuse.
-int build_tiles(int m, int band_lo, int band_hi, TileCoord* dst) {
-  const int mt = (m + BM - 1) / BM, nt = (m + BN - 1) / BN;
-  const int SBM = 16, SBN = 8;        // super-block = 2048 x 2048 cells
+// Tiles (tile_m x BN) touching the upper triangle and the band, in 2048 x 2048 super-blocks for L2 reuse.
+int build_tiles(int m, int tile_m, int band_lo, int band_hi, TileCoord* dst) {
+  const int mt = (m + tile_m - 1) / tile_m, nt = (m + BN - 1) / BN;
+  const int SBM = 2048 / tile_m, SBN = 2048 / BN;
   int cnt = 0;
   for (int sm = 0; sm < mt; sm += SBM)
     for (int sn = 0; sn < nt; sn += SBN)
       for (int mi = sm; mi < min(sm + SBM, mt); ++mi)
         for (int nj = sn; nj < min(sn + SBN, nt); ++nj) {
-          const long long r0 = (long long)mi * BM, r1 = min((long long)m, r0 + BM) - 1;
+          const long long r0 = (long long)mi * tile_m, r1 = min((long long)m, r0 + tile_m) - 1;
           const long long c0 = (long long)nj * BN, c1 = min((long long)m, c0 + BN) - 1;
           if (c1 < r0) continue;                         // entirely below the diagonal
           // distance range of upper cells in the tile: [max(0, c0 - r1), c1 - r0]
           const long long dmin = max(0ll, c0 - r1), dmax = c1 - r0;
           if (band_hi >= 0 && (dmin > band_hi || dmax < band_lo)) continue;
-          if (dst) { dst[cnt].m_blk = mi; dst[cnt].n_blk = nj; }
+          if (dst) { dst[cnt].m0 = (int)r0; dst[cnt].n0 = (int)c0; }
           ++cnt;
         }
   return cnt;
@@ -626,6 +697,52 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
                      d_tiles, reinterpret_cast<unsigned int*>(ws + off_sync), sync_counters(m, k), stream);
 }
 
+// CTA pairs (cta_group::2) unless HIA_SYRK_CTAS=1 selects the single-CTA kernel.
+static int syrk_ctas() {
+  static const int v = [] {
+    const char* e = getenv("HIA_SYRK_CTAS");
+    return (e && atoi(e) == 1) ? 1 : 2;
+  }();
+  return v;
+}
+
+template <int PREC, int CTAS>
+static int launch_syrk(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const hia::TileCoord* d_tiles,
+                       int num_tiles, int m, int num_k_blocks, int kb_per_chunk, float* out, int64_t ld_out,
+                       int flavour, unsigned int* sync_ctr, int sync_arg, int row0, int row_end,
+                       int symmetric, cudaStream_t stream) {
+  using namespace hia;
+  using G = Geo<CTAS>;
+  auto kern = syrk_split3_kernel<PREC, CTAS>;
+  HIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = G::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int units = kNumSMs / CTAS;
+  if (CTAS == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.gridDim = dim3(kNumSMs, 1, 1);
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess && max_clusters > 0)
+      units = min(units, max_clusters);                   // persistent: never more pairs than can be resident
+    else
+      (void)cudaGetLastError();
+  }
+  units = min(units, num_tiles);
+  cfg.gridDim = dim3(units * CTAS, 1, 1);
+  HIA_CUDA(cudaLaunchKernelEx(&cfg, kern, map_hi, map_lo, d_tiles, num_tiles, m, num_k_blocks, kb_per_chunk, out,
+                              (long long)ld_out, flavour, sync_ctr, sync_arg, row0, row_end, symmetric));
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
 // Tiles + tensor maps + launch. plane_rows = rows the planes hold (>= n_valid; extra rows must be
 // zero), n_valid = true matrix size, [row0, row0 + rows) = the output rows to compute.
 static int launch_gemm(void* hi, void* lo, int prec, int plane_rows, int n_valid, int kpad, int row0, int rows,
@@ -634,17 +751,19 @@ static int launch_gemm(void* hi, void* lo, int prec, int plane_rows, int n_valid
                        cudaStream_t stream) {
   using namespace hia;
   const int m = n_valid;
+  const int ctas = syrk_ctas();
+  const int tile_m = BM * ctas;
   const int max_tiles = ((m + BM - 1) / BM) * ((m + BN - 1) / BN);
   TileCoord* h_tiles = static_cast<TileCoord*>(malloc((size_t)max_tiles * sizeof(TileCoord)));
   if (!h_tiles) return HIA_ERR_BAD_ARG;
   int num_tiles = 0;
   if (symmetric) {
-    num_tiles = build_tiles(m, band_lo, band_hi, h_tiles);
+    num_tiles = build_tiles(m, tile_m, band_lo, band_hi, h_tiles);
   } else {
-    const int mi0 = row0 / BM, mi1 = (min(row0 + rows, m) + BM - 1) / BM, nt = (m + BN - 1) / BN;
+    const int row_end = min(row0 + rows, m), nt = (m + BN - 1) / BN;
     for (int sn = 0; sn < nt; sn += 8)                     // 8-column-tile super blocks for L2 reuse
-      for (int mi = mi0; mi < mi1; ++mi)
-        for (int nj = sn; nj < min(sn + 8, nt); ++nj) { h_tiles[num_tiles].m_blk = mi; h_tiles[num_tiles].n_blk = nj; ++num_tiles; }
+      for (int r = row0; r < row_end; r += tile_m)
+        for (int nj = sn; nj < min(sn + 8, nt); ++nj) { h_tiles[num_tiles].m0 = r; h_tiles[num_tiles].n0 = nj * BN; ++num_tiles; }
   }
   if (num_tiles == 0) { free(h_tiles); return HIA_OK; }
   // pageable H2D: the runtime stages the data before returning, so freeing right after is safe
@@ -665,23 +784,16 @@ static int launch_gemm(void* hi, void* lo, int prec, int plane_rows, int n_valid
   // error grows with the number of MMA steps in one TMEM chain; fp16 steps cover twice the K.
   if (k_chunk <= 0) k_chunk = (prec == HIA_PREC_3XF16) ? 512 : 256;
   const int kb_per_chunk = max(1, k_chunk / bk);
-  const int grid = min(num_tiles, kNumSMs);
   static const int sync_every = getenv("HIA_SYRK_SYNC") ? atoi(getenv("HIA_SYRK_SYNC")) : kSyncEvery;
   const int sync_arg = (sync_every >= kSyncEvery) ? sync_every : 0;
   HIA_CUDA(cudaMemsetAsync(sync_ctr, 0, (size_t)n_sync * 4, stream));
-  if (prec == HIA_PREC_3XF16) {
-    HIA_CUDA(cudaFuncSetAttribute(syrk_split3_kernel<HIA_PREC_3XF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    syrk_split3_kernel<HIA_PREC_3XF16><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
-        map_hi, map_lo, d_tiles, num_tiles, m, num_k_blocks, kb_per_chunk, out, ld_out, flavour, sync_ctr,
-        sync_arg, row0, min(row0 + rows, m), symmetric);
-  } else {
-    HIA_CUDA(cudaFuncSetAttribute(syrk_split3_kernel<HIA_PREC_3XTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    syrk_split3_kernel<HIA_PREC_3XTF32><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
-        map_hi, map_lo, d_tiles, num_tiles, m, num_k_blocks, kb_per_chunk, out, ld_out, flavour, sync_ctr,
-        sync_arg, row0, min(row0 + rows, m), symmetric);
-  }
-  HIA_LAUNCH_CHECK();
-  return HIA_OK;
+  const int row_end = min(row0 + rows, m);
+#define HIA_SYRK_LAUNCH(P, C)                                                                              \
+  launch_syrk<P, C>(map_hi, map_lo, d_tiles, num_tiles, m, num_k_blocks, kb_per_chunk, out, ld_out, flavour, \
+                    sync_ctr, sync_arg, row0, row_end, symmetric, stream)
+  if (prec == HIA_PREC_3XF16) return ctas == 2 ? HIA_SYRK_LAUNCH(HIA_PREC_3XF16, 2) : HIA_SYRK_LAUNCH(HIA_PREC_3XF16, 1);
+  return ctas == 2 ? HIA_SYRK_LAUNCH(HIA_PREC_3XTF32, 2) : HIA_SYRK_LAUNCH(HIA_PREC_3XTF32, 1);
+#undef HIA_SYRK_LAUNCH
 }
 
 // ------------------------------------------------------------------ row-sharded entry points

@@ -223,45 +223,57 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     launches0 = lib.hia_launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-    gemm_ms, prep_ms = [], []
     barrier()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
+    stage_ev = []
     for _ in range(args.steps):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        e[0].record()
         hp.scatter(rows, cols, vals)
+        e[1].record()
         hp.normalise()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record()
+        e[2].record()
         hp.similarity_prep()
-        e1.record()
+        e[3].record()
         hp.similarity_gemm()                       # the dominant kernel, timed on its own stream
-        e2.record()
+        e[4].record()
         w, vecs = hp.eigen()
-        gemm_ms.append((e1, e2))
-        prep_ms.append((e0, e1))
+        e[5].record()
+        stage_ev.append(e)
     t_end.record()
     barrier()
     launches = lib.hia_launch_count() - launches0
     ms_total = max_over_ranks(t_start.elapsed_time(t_end))
     ms_step = ms_total / args.steps
-    gemm = float(np.mean([a.elapsed_time(b) for a, b in gemm_ms]))
-    prep = float(np.mean([a.elapsed_time(b) for a, b in prep_ms]))
+    stage = [float(np.mean([e[i].elapsed_time(e[i + 1]) for e in stage_ev])) for i in range(5)]
+    scat, oe_ms, prep, gemm, eig_ms = stage
     clk = clocks.stop() if rank == 0 else None
 
     # ---- end-to-end arm (pinned host COO -> eigenpairs on host) --------------------------------
-    for _ in range(min(args.warmup, 2)):
-        hp.run_host(rows_h, cols_h, vals_h)
+    # HotPath.run_host_many: the public streaming call; every step copies ITS inputs H2D (2.7 GB from
+    # pinned memory) and reads its eigenpairs back inside the timed region; the copy of step i + 1
+    # runs on a second stream while step i computes (double buffering).
+    for _ in hp.run_host_many([(rows_h, cols_h, vals_h)] * min(args.warmup, 2)):
+        pass
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
-        w_h, v_h = hp.run_host(rows_h, cols_h, vals_h)
+    for w_h, v_h in hp.run_host_many([(rows_h, cols_h, vals_h)] * args.steps):
+        pass
     t1.record()
     barrier()
     e2e_ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+    # the same without overlap (one blocking call per sample), for the record
+    t0s = torch.cuda.Event(enable_timing=True)
+    t1s = torch.cuda.Event(enable_timing=True)
+    t0s.record()
+    hp.run_host(rows_h, cols_h, vals_h)
+    t1s.record()
+    barrier()
+    e2e_serial_ms = max_over_ranks(t0s.elapsed_time(t1s))
 
     if rank != 0:
         if world > 1:
@@ -314,10 +326,20 @@ def run_ours(args):
                    "sharding": "samples by rank, no collective"},
         "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": world * cells / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 12 * nnz, "d2h_bytes_per_step": 3 * 8 + 3 * n * 4},
+                "h2d_bytes_per_step": 12 * nnz, "d2h_bytes_per_step": 3 * 8 + 3 * n * 4,
+                "api": "HotPath.run_host_many (H2D of step i+1 overlaps the compute of step i)",
+                "ms_single_blocking_call": e2e_serial_ms},
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "breakdown_ms": {"similarity_prep": prep, "similarity_gemm": gemm},
+        "breakdown_ms": {"scatter": scat, "oe_log": oe_ms, "similarity_prep": prep, "similarity_gemm": gemm,
+                         "topk_eig": eig_ms},
+        "hbm_kernels": {                     # achieved algorithmic GB/s of the HBM-bound stages (SURVEY 8d bytes)
+            "scatter": {"bytes": 12 * nnz + 4 * cells, "gbs": (12 * nnz + 4 * cells) / scat / 1e6,
+                        "frac": (12 * nnz + 4 * cells) / scat / 1e6 / pk["hbm_gbs"]},
+            "oe_log": {"bytes": 10 * cells, "gbs": 10 * cells / oe_ms / 1e6, "frac": 10 * cells / oe_ms / 1e6 / pk["hbm_gbs"]},
+            "similarity_prep": {"bytes": (4 + 2 * hp.plane_elem_bytes) * cells,
+                                "gbs": (4 + 2 * hp.plane_elem_bytes) * cells / prep / 1e6,
+                                "frac": (4 + 2 * hp.plane_elem_bytes) * cells / prep / 1e6 / pk["hbm_gbs"]}},
         "eigvals": [float(x) for x in w_h],
     }
     print(json.dumps(line), flush=True)

@@ -264,12 +264,18 @@ __global__ void place_block_kernel(const double* __restrict__ src, int rows, int
   *dst = accumulate ? (*dst + src[idx]) : src[idx];
 }
 
-// One-sided (Hestenes) Jacobi on the symmetric D x D matrix built from the lower triangle of H.
-// Single CTA, warp per column pair, round-robin pairing. A and V are col-major in global memory.
+// One-sided (Hestenes) Jacobi on the symmetric dim x dim matrix built from the lower triangle of H.
+// Single CTA, warp per column pair, round-robin pairing. A and V (col-major) live in SHARED memory
+// when 2 dim^2 doubles fit (dim <= 118: every default configuration), else in the global scratch
+// A_g / V_g; V (and lam / order) are written back to global memory at the end. The global-memory
+// version spent 6 ms per solve on L2 round trips between the dependent rotation steps.
 __global__ void __launch_bounds__(1024)
-jacobi_kernel(const double* __restrict__ h, int D, int dim, double* __restrict__ A, double* __restrict__ V,
-              double* __restrict__ lam, int* __restrict__ order, int max_sweeps) {
+jacobi_kernel(const double* __restrict__ h, int D, int dim, double* __restrict__ A_g, double* __restrict__ V_g,
+              double* __restrict__ lam, int* __restrict__ order, int max_sweeps, int use_smem) {
+  extern __shared__ double s_jac[];
   __shared__ int s_rot;
+  double* A = use_smem ? s_jac : A_g;
+  double* V = use_smem ? s_jac + (size_t)dim * dim : V_g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const int m = (dim + 1) & ~1;                      // padded to even (phantom index dim)
   for (int idx = tid; idx < dim * dim; idx += blockDim.x) {
@@ -321,6 +327,8 @@ jacobi_kernel(const double* __restrict__ h, int D, int dim, double* __restrict__
     s = warp_sum(s);
     if (lane == 0) lam[p] = s;
   }
+  if (use_smem)
+    for (int idx = tid; idx < dim * dim; idx += blockDim.x) V_g[idx] = V[idx];
   __syncthreads();
   if (tid == 0) {                                    // descending order (selection sort, dim <= 272)
     for (int i = 0; i < dim; ++i) order[i] = i;
@@ -330,6 +338,55 @@ jacobi_kernel(const double* __restrict__ h, int D, int dim, double* __restrict__
       const int t = order[i]; order[i] = order[best]; order[best] = t;
     }
   }
+}
+
+// After `done` Lanczos steps (dim = done * b Ritz pairs in Z / lam / order): the Lanczos relation
+// C Q = Q T + Q_next B E^T gives the residual of the Ritz pair (theta, z) WITHOUT a pass over C:
+// ||C u - theta u|| = ||B z_last||, B = H[dim : dim + b, dim - b : dim] (the R of the newest block),
+// z_last = the last b entries of z. gap_j = distance of theta_j to the nearest other Ritz value
+// (the sin-theta theorem bounds the eigenvector angle by residual / gap).
+// out[0..k) = estimates, out[k..2k) = gaps, flag = 1 when every pair j < k satisfies
+// est_j <= rel_tol |theta_1|  or  est_j <= angle_tol gap_j.
+__global__ void ritz_check_kernel(const double* __restrict__ h, int D, int dim, int b,
+                                  const double* __restrict__ Z, const double* __restrict__ lam,
+                                  const int* __restrict__ order, int k, double rel_tol, double angle_tol,
+                                  double* __restrict__ out, int* __restrict__ flag) {
+  __shared__ int s_ok[kMaxBlock];
+  const int j = threadIdx.x;
+  if (j < k) {
+    const double* z = Z + (long long)order[j] * dim;
+    double r2 = 0.0;
+    for (int i = 0; i < b; ++i) {
+      double acc = 0.0;
+      for (int c = 0; c < b; ++c) acc += h[(long long)(dim + i) * D + (dim - b + c)] * z[dim - b + c];
+      r2 += acc * acc;
+    }
+    const double est = sqrt(r2), theta = lam[order[j]];
+    double gap = INFINITY;
+    for (int i = 0; i < dim; ++i)
+      if (i != order[j]) gap = fmin(gap, fabs(theta - lam[i]));
+    out[j] = est;
+    out[k + j] = gap;
+    s_ok[j] = (est <= rel_tol * fabs(lam[order[0]])) || (est <= angle_tol * gap);
+  }
+  __syncthreads();
+  if (j == 0) {
+    int ok = 1;
+    for (int i = 0; i < k; ++i) ok &= s_ok[i];
+    *flag = ok;
+  }
+}
+
+// gaps[j] = distance of the j-th largest Ritz value to the nearest other Ritz value
+__global__ void ritz_gap_kernel(const double* __restrict__ lam, const int* __restrict__ order, int dim, int k,
+                                double* __restrict__ gaps) {
+  const int j = threadIdx.x;
+  if (j >= k) return;
+  const double theta = lam[order[j]];
+  double gap = INFINITY;
+  for (int i = 0; i < dim; ++i)
+    if (i != order[j]) gap = fmin(gap, fabs(theta - lam[i]));
+  gaps[j] = gap;
 }
 
 // U[:, j] = Q[:, 0:dim] * Z[:, order[j]], j < k  (thread per row); fp64 + fp32 copies, eigenvalues out
@@ -373,6 +430,8 @@ struct EigWs {
   double *Q, *Y, *U, *H, *G, *G2, *R1, *Rinv, *R2, *Rt, *JA, *JV, *lam, *resid2;
   float *Vf;
   int* order;
+  double* check;      // [2 * kMaxBlock] estimates + gaps of the last convergence check
+  int* flag;
 };
 
 long long carve(unsigned char* base, int n, int b, int steps, EigWs* w) {
@@ -396,6 +455,8 @@ long long carve(unsigned char* base, int n, int b, int steps, EigWs* w) {
   p = take(D * 8); if (w) w->lam = (double*)p;
   p = take(b * 8); if (w) w->resid2 = (double*)p;
   p = take(D * 4); if (w) w->order = (int*)p;
+  p = take(2 * kMaxBlock * 8); if (w) w->check = (double*)p;
+  p = take(256); if (w) w->flag = (int*)p;
   return off + 256;
 }
 
@@ -435,6 +496,15 @@ int cholqr(double* Y, int n, int b, EigWs& w, double* r_out, float* yf, cudaStre
   chol_kernel<<<1, 32, 0, s>>>(w.G2, b, r_out, w.Rinv);
   HIA_LAUNCH_CHECK();
   panel_mul_kernel<<<(n + 255) / 256, 256, 0, s>>>(Y, w.Rinv, b, n, yf);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
+int launch_jacobi(const EigWs& w, int D, int dim, cudaStream_t s) {
+  const size_t need = (size_t)2 * dim * dim * sizeof(double);
+  const int use_smem = need <= 222 * 1024;
+  if (use_smem) HIA_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  jacobi_kernel<<<1, 1024, use_smem ? need : 0, s>>>(w.H, D, dim, w.JA, w.JV, w.lam, w.order, 15, use_smem);
   HIA_LAUNCH_CHECK();
   return HIA_OK;
 }
@@ -533,19 +603,52 @@ HIA_API int hia_eig_absorb(int32_t n, int32_t block, int32_t steps, int32_t j, c
   return HIA_OK;
 }
 
-// ---- Rayleigh-Ritz: eigvals[k], eigvecs[k][n]; the fp32 panel becomes [U, 0] for the residual pass
-HIA_API int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t k, double* eigvals, float* eigvecs,
-                         void* workspace, void* stream_) {
+// ---- convergence check after `steps_done` absorbed steps, without a pass over the matrix: Jacobi on
+// the (steps_done * block)-dimensional projected matrix + the Lanczos residual estimates. Writes
+// *converged_host (synchronises the stream); est_gap_host (optional) receives k estimates + k gaps.
+HIA_API int hia_eig_check(int32_t n, int32_t block, int32_t steps, int32_t steps_done, int32_t k, double rel_tol,
+                          double angle_tol, int32_t* converged_host, double* est_gap_host, void* workspace,
+                          void* stream_) {
   using namespace hia;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   int st = check_shape(n, block, steps);
   if (st != HIA_OK) return st;
-  if (!eigvals || !eigvecs || !workspace || k <= 0 || k > block) return HIA_ERR_BAD_ARG;
-  const int b = block, D = b * (steps + 1), dim = steps * b;
+  if (!converged_host || !workspace || k <= 0 || k > block || steps_done < 1 || steps_done > steps)
+    return HIA_ERR_BAD_ARG;
+  const int b = block, D = b * (steps + 1), dim = steps_done * b;
   EigWs w;
   carve(static_cast<unsigned char*>(workspace), n, b, steps, &w);
-  jacobi_kernel<<<1, 1024, 0, s>>>(w.H, D, dim, w.JA, w.JV, w.lam, w.order, 15);
+  st = launch_jacobi(w, D, dim, s);
+  if (st != HIA_OK) return st;
+  ritz_check_kernel<<<1, 32, 0, s>>>(w.H, D, dim, b, w.JV, w.lam, w.order, k, rel_tol, angle_tol, w.check, w.flag);
   HIA_LAUNCH_CHECK();
+  int flag = 0;
+  HIA_CUDA(cudaMemcpyAsync(&flag, w.flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (est_gap_host) HIA_CUDA(cudaMemcpyAsync(est_gap_host, w.check, (size_t)2 * k * 8, cudaMemcpyDeviceToHost, s));
+  HIA_CUDA(cudaStreamSynchronize(s));
+  *converged_host = flag;
+  return HIA_OK;
+}
+
+// ---- Rayleigh-Ritz on the first `steps_used` blocks: eigvals[k], eigvecs[k][n], gaps[k] (optional:
+// distance to the nearest other Ritz value); the fp32 panel becomes [U, 0] for the residual pass
+HIA_API int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t steps_used, int32_t k,
+                         double* eigvals, float* eigvecs, double* gaps, void* workspace, void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  int st = check_shape(n, block, steps);
+  if (st != HIA_OK) return st;
+  if (!eigvals || !eigvecs || !workspace || k <= 0 || k > block || steps_used < 1 || steps_used > steps)
+    return HIA_ERR_BAD_ARG;
+  const int b = block, D = b * (steps + 1), dim = steps_used * b;
+  EigWs w;
+  carve(static_cast<unsigned char*>(workspace), n, b, steps, &w);
+  st = launch_jacobi(w, D, dim, s);
+  if (st != HIA_OK) return st;
+  if (gaps) {
+    ritz_gap_kernel<<<1, 32, 0, s>>>(w.lam, w.order, dim, k, gaps);
+    HIA_LAUNCH_CHECK();
+  }
   ritz_kernel<<<(n + 255) / 256, 256, 0, s>>>(w.Q, n, dim, w.JV, w.order, w.lam, k, w.U, w.Vf, eigvals);
   HIA_LAUNCH_CHECK();
   HIA_CUDA(cudaMemcpyAsync(eigvecs, w.Vf, (size_t)n * k * 4, cudaMemcpyDeviceToDevice, s));
@@ -574,11 +677,14 @@ HIA_API int hia_eig_resid(int32_t n, int32_t block, int32_t steps, int32_t k, co
   return HIA_OK;
 }
 
-// ---- single-device driver: all phases on one stream, no host round trip
+// ---- single-device driver: all phases on one stream. early_rel_tol / early_angle_tol > 0 enable the
+// pass-free convergence check (hia_eig_check, one tiny D2H flag) after every second step from the
+// fourth on: the cycle stops as soon as the Lanczos residual estimates meet the tolerance instead of
+// always spending `steps` passes over the matrix. *steps_used_host (optional) = steps actually taken.
 HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block, int32_t steps,
-                         uint64_t seed, const float* init_vecs, int32_t n_init, double* eigvals,
-                         float* eigvecs, double* resid, void* workspace, int64_t workspace_bytes,
-                         void* stream) {
+                         uint64_t seed, const float* init_vecs, int32_t n_init, double early_rel_tol,
+                         double early_angle_tol, double* eigvals, float* eigvecs, double* resid, double* gaps,
+                         int32_t* steps_used_host, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace hia;
   if (!c || !eigvals || !eigvecs || !resid || !workspace || ld < n || k <= 0) return HIA_ERR_BAD_ARG;
   if (k > block) return HIA_ERR_BAD_ARG;
@@ -587,16 +693,26 @@ HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32
   EigWs w;
   carve(static_cast<unsigned char*>(workspace), n, block, steps, &w);
   double* ystage = w.Y;                               // n x block staging (row-major)
+  const bool early = early_rel_tol > 0.0 || early_angle_tol > 0.0;
+  int used = steps;
   for (int j = 0; j < steps; ++j) {
     st = hia_eig_symm_rows(c, n, n, ld, block, steps, workspace, ystage, stream);
     if (st != HIA_OK) return st;
     st = hia_eig_absorb(n, block, steps, j, ystage, workspace, stream);
     if (st != HIA_OK) return st;
+    const int done = j + 1;
+    if (early && done >= 4 && (done & 1) == 0 && done < steps) {
+      int conv = 0;
+      st = hia_eig_check(n, block, steps, done, k, early_rel_tol, early_angle_tol, &conv, nullptr, workspace, stream);
+      if (st != HIA_OK) return st;
+      if (conv) { used = done; break; }
+    }
   }
-  st = hia_eig_ritz(n, block, steps, k, eigvals, eigvecs, workspace, stream);
+  if (steps_used_host) *steps_used_host = used;
+  st = hia_eig_ritz(n, block, steps, used, k, eigvals, eigvecs, gaps, workspace, stream);
   if (st != HIA_OK) return st;
   // the residual pass needs a second staging buffer: w.Y is the transposed target of hia_eig_resid
-  double* ystage2 = w.Q + (long long)steps * block * n;   // Q_{steps} is no longer needed
+  double* ystage2 = w.Q + (long long)used * block * n;    // Q_{used} is no longer needed
   st = hia_eig_symm_rows(c, n, n, ld, block, steps, workspace, ystage2, stream);
   if (st != HIA_OK) return st;
   return hia_eig_resid(n, block, steps, k, ystage2, eigvals, resid, workspace, stream);

@@ -157,22 +157,34 @@ inter_block_kernel(const float* __restrict__ map, int n, long long ld,
     __syncthreads();
   };
 
-  for (int r = r0; r < r1; ++r) {
+  auto accumulate = [&](const float4& v, int col_lo) {
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gc = c0 + j;
+      if (gc >= col_lo && gc < n) {
+        sum[j] += vv[j];
+        cnt[j] += (vv[j] != 0.f);
+        if (vv[j] > 0.f) mn[j] = fminf(mn[j], vv[j]);
+      }
+    }
+  };
+  int r = r0;
+  while (r < r1) {
     const int a = bin_chr[r];                              // uniform
     if (a != a_prev) { flush(a_prev); a_prev = a; }
     const int col_lo = chr_start[a + 1];
+    // rows of chromosome a inside this tile: 4 independent 128-bit loads in flight per thread
+    const int r_stop = min(r1, chr_start[a + 1]);
     if (active && c0 + 3 >= col_lo) {
-      const float4 v = ld_stream4(map + (long long)(r - row0) * ld + c0);   // ld % 4 == 0, ld >= n
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gc = c0 + j;
-        if (gc >= col_lo && gc < n) {
-          sum[j] += vv[j];
-          cnt[j] += (vv[j] != 0.f);
-          if (vv[j] > 0.f) mn[j] = fminf(mn[j], vv[j]);
-        }
+      const float* p = map + (long long)(r - row0) * ld + c0;   // ld % 4 == 0, ld >= n
+      for (; r + 4 <= r_stop; r += 4, p += 4 * ld) {
+        const float4 v0 = ld_stream4(p), v1 = ld_stream4(p + ld), v2 = ld_stream4(p + 2 * ld), v3 = ld_stream4(p + 3 * ld);
+        accumulate(v0, col_lo); accumulate(v1, col_lo); accumulate(v2, col_lo); accumulate(v3, col_lo);
       }
+      for (; r < r_stop; ++r, p += ld) accumulate(ld_stream4(p), col_lo);
+    } else {
+      r = r_stop;
     }
   }
   flush(a_prev);
@@ -313,6 +325,11 @@ __global__ void init_min_kernel(float* p) { *p = INFINITY; }
 // ---------------------------------------------------------------------------------------
 // Apply: out = map * inv; optional log. One thread per float4, rows over blockIdx.y.
 // ---------------------------------------------------------------------------------------
+// ln(1 + x) for x > 0 on the SFU: 1 + x is rounded once (<= 6e-8 absolute in the result), lg2.approx
+// has <= 2^-21.4 absolute error near 1 and 2 ulp elsewhere -- three orders below the 1e-5 the
+// path has to hold, and ~20 instructions cheaper than log1pf (the pass was ALU-bound with it).
+__device__ __forceinline__ float fast_log1p_pos(float x) { return __logf(1.f + x); }
+
 __global__ void __launch_bounds__(256)
 oe_apply_kernel(const float* __restrict__ map, float* __restrict__ out, int n, long long ld,
                 const int* __restrict__ chr_start, int n_chr, const short* __restrict__ bin_chr,
@@ -331,35 +348,55 @@ oe_apply_kernel(const float* __restrict__ map, float* __restrict__ out, int n, l
   int cb[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) cb[j] = bin_chr[min(c0 + j, n - 1)];
-  for (int r = row0 + blockIdx.y; r < row_end; r += gridDim.y) {
-    const int a = bin_chr[r];
-    const int s = chr_start[a];
+  const bool full4 = c0 + 3 < n;
+  const bool one_chr = full4 && cb[0] == cb[3];            // the common case: 4 columns, one chromosome
+
+  auto scale = [&](float (&v)[4], int r, int a) {
+    if (one_chr && cb[0] != a) {                           // inter block, one factor for the float4
+      const float f = only_intra ? 0.f : __ldg(&inter_inv[a * n_chr + cb[0]]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= f;
+    } else {
+      const int s = chr_start[a];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (cb[j] == a) v[j] *= __ldg(&inv_expected[s + abs(c0 + j - r)]);
+        else v[j] = only_intra ? 0.f : v[j] * __ldg(&inter_inv[a * n_chr + cb[j]]);
+      }
+    }
+    if (do_log) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (v[j] > 0.f) ? fast_log1p_pos(v[j]) : fill;
+    }
+  };
+
+  int r = row0 + blockIdx.y;
+  if (full4) {
+    // two rows per iteration: two independent 128-bit loads in flight per thread
+    for (; r + (int)gridDim.y < row_end; r += 2 * gridDim.y) {
+      const int r2 = r + gridDim.y;
+      const float4 t0 = ld_stream4(map + (long long)(r - row0) * ld + c0);
+      const float4 t1 = ld_stream4(map + (long long)(r2 - row0) * ld + c0);
+      float v0[4] = {t0.x, t0.y, t0.z, t0.w}, v1[4] = {t1.x, t1.y, t1.z, t1.w};
+      scale(v0, r, bin_chr[r]);
+      scale(v1, r2, bin_chr[r2]);
+      st_stream4(out + (long long)(r - row0) * ld + c0, make_float4(v0[0], v0[1], v0[2], v0[3]));
+      st_stream4(out + (long long)(r2 - row0) * ld + c0, make_float4(v1[0], v1[1], v1[2], v1[3]));
+    }
+  }
+  for (; r < row_end; r += gridDim.y) {
     const float* src = map + (long long)(r - row0) * ld + c0;
     float v[4];
-    if (c0 + 3 < n) {
+    if (full4) {
       const float4 t = ld_stream4(src);
       v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = (c0 + j < n) ? src[j] : 0.f;
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gc = c0 + j;
-      float x;
-      if (cb[j] == a) {
-        const int d = abs(gc - r);
-        x = v[j] * inv_expected[s + d];
-      } else if (only_intra) {
-        x = 0.f;
-      } else {
-        x = v[j] * inter_inv[a * n_chr + cb[j]];
-      }
-      if (do_log) x = (x > 0.f) ? log1pf(x) : fill;
-      v[j] = x;
-    }
+    scale(v, r, bin_chr[r]);
     float* dst = out + (long long)(r - row0) * ld + c0;
-    if (c0 + 3 < n) {
+    if (full4) {
       st_stream4(dst, make_float4(v[0], v[1], v[2], v[3]));
     } else {
       for (int j = 0; j < 4 && c0 + j < n; ++j) dst[j] = v[j];
@@ -394,7 +431,7 @@ log_apply_kernel(const float* __restrict__ x, float* __restrict__ out, int rows,
        i += (long long)gridDim.x * blockDim.x) {
     const long long off = (i / cols) * ld + (i % cols);
     const float v = x[off];
-    out[off] = (v > 0.f) ? log1pf(v) : fill;
+    out[off] = (v > 0.f) ? fast_log1p_pos(v) : fill;
   }
 }
 

@@ -192,8 +192,15 @@ scatter_remap_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
     const int rr = index_map[r], cc = index_map[c];
     if (rr < 0 || cc < 0) continue;
     const float v = vals[e];
-    atomicAdd(out + (long long)rr * ld + cc, v);
-    if (mtx_type == HIA_MTX_TRIU && r != c) atomicAdd(out + (long long)cc * ld + rr, v);
+    if (mtx_type == HIA_MTX_TRIU) {
+      // canonical (upper) coarse cell only; mirror_kernel copies it below the diagonal afterwards,
+      // so the coarse map is symmetric BIT FOR BIT (the O/E passes read the upper triangle only).
+      // An off-diagonal fine entry folded onto the coarse diagonal counts twice (2v is exact).
+      const int lo = min(rr, cc), hi = max(rr, cc);
+      atomicAdd(out + (long long)lo * ld + hi, (lo == hi && r != c) ? 2.f * v : v);
+    } else {
+      atomicAdd(out + (long long)rr * ld + cc, v);
+    }
   }
 }
 
@@ -283,6 +290,11 @@ HIA_API int hia_scatter_coo_remap(const int32_t* rows, const int32_t* cols, cons
     const int grid = (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (nnz + 255) / 256));
     scatter_remap_kernel<<<grid, 256, 0, stream>>>(rows, cols, vals, nnz, n_fine, index_map, mtx_type, out, ld);
     HIA_LAUNCH_CHECK();
+    if (mtx_type == HIA_MTX_TRIU) {
+      dim3 gm((n_out + 31) / 32, (n_out + 31) / 32);
+      mirror_kernel<<<gm, 256, 0, stream>>>(out, n_out, ld);
+      HIA_LAUNCH_CHECK();
+    }
   }
   return HIA_OK;
 }

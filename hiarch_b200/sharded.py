@@ -15,6 +15,8 @@ The single exchange step of the hot path (BASELINE.json co
 Round-1 version: each rank computes its FULL row block (no symmetry saving -> balanced without a
 row permutation); the planes are gathered whole before the contraction (not chunk-pipelined).
 """
+import ctypes
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -80,7 +82,8 @@ class ShardedSimilarity:
         return out_rows
 
 
-def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, max_restarts=8, seed=0, group=None):
+def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, angle_tol=1e-3, max_restarts=8, seed=0,
+                  group=None):
     """Top-k eigenpairs of the symmetric n x n matrix whose rows [row0, row0 + rows) this rank
     holds in `c_rows` (row layout of ShardedSimilarity). Returns (eigvals [k] fp64 device,
     eigvecs [n, k] fp32 device, info) -- identical on every rank."""
@@ -99,6 +102,8 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, max_restarts=8, s
     eigvals = torch.empty(k, dtype=torch.float64, device=dev)
     eigvecs = torch.empty((k, n), dtype=torch.float32, device=dev)
     resid = torch.empty(k, dtype=torch.float64, device=dev)
+    gaps = torch.empty(k, dtype=torch.float64, device=dev)
+    conv = ctypes.c_int32(0)
     s = ops._stream
 
     def matvec():
@@ -114,18 +119,27 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, max_restarts=8, s
     for it in range(max_restarts):
         _lib.check(lib.hia_eig_begin(n, block, steps, seed + it, ops._ptr(init), n_init, ws.data_ptr(),
                                      ws.numel(), s()), "hia_eig_begin")
+        used = steps
         for j in range(steps):
             matvec()
             _lib.check(lib.hia_eig_absorb(n, block, steps, j, y_full.data_ptr(), ws.data_ptr(), s()),
                        "hia_eig_absorb")
-        _lib.check(lib.hia_eig_ritz(n, block, steps, k, eigvals.data_ptr(), eigvecs.data_ptr(),
-                                    ws.data_ptr(), s()), "hia_eig_ritz")
+            done = j + 1
+            if done >= 4 and done % 2 == 0 and done < steps:
+                # replicated and bit-identical on every rank -> every rank takes the same decision
+                _lib.check(lib.hia_eig_check(n, block, steps, done, k, 0.5 * tol, 0.5 * angle_tol,
+                                             ctypes.addressof(conv), None, ws.data_ptr(), s()), "hia_eig_check")
+                if conv.value:
+                    used = done
+                    break
+        _lib.check(lib.hia_eig_ritz(n, block, steps, used, k, eigvals.data_ptr(), eigvecs.data_ptr(),
+                                    gaps.data_ptr(), ws.data_ptr(), s()), "hia_eig_ritz")
         matvec()
         _lib.check(lib.hia_eig_resid(n, block, steps, k, y_full.data_ptr(), eigvals.data_ptr(),
                                      resid.data_ptr(), ws.data_ptr(), s()), "hia_eig_resid")
         r, lam = resid.cpu().numpy(), eigvals.cpu().numpy()
-        info.append((float(r.max()), float(abs(lam[0]))))
-        if np.all(r <= tol * max(abs(lam[0]), 1e-300)):
+        info.append((float(r.max()), float(abs(lam[0])), used))
+        if ops.eig_converged(r, lam, gaps.cpu().numpy(), tol, angle_tol):
             break
         init, n_init = eigvecs.clone(), k
     return eigvals, eigvecs.t(), info

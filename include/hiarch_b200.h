@@ -315,17 +315,27 @@ int hia_sim_gemm_rows(void* hi, void* lo, int precision, int32_t plane_rows, int
 /* +lambda/-lambda of equal magnitude may mix.                                            */
 /* ------------------------------------------------------------------------------------ */
 int64_t hia_topk_eig_workspace_bytes(int32_t n, int32_t block, int32_t steps);
+/* early_rel_tol / early_angle_tol > 0: after every second Lanczos step (from the fourth on) the
+ * Ritz residuals are ESTIMATED from the Lanczos relation (no pass over the matrix; one tiny D2H
+ * flag) and the cycle ends as soon as every wanted pair has est <= early_rel_tol |lambda_1| or
+ * est <= early_angle_tol * gap (gap = distance to the nearest other Ritz value: the sin-theta
+ * bound on the eigenvector angle). resid[k] are always the TRUE residuals ||C u - lambda u|| of
+ * one final pass; gaps[k] (optional, device) the Ritz gaps; *steps_used_host (optional) the steps
+ * taken. */
 int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block, int32_t steps,
-                 uint64_t seed, const float* init_vecs, int32_t n_init, double* eigvals,
-                 float* eigvecs, double* resid, void* workspace, int64_t workspace_bytes,
-                 void* stream);
+                 uint64_t seed, const float* init_vecs, int32_t n_init, double early_rel_tol,
+                 double early_angle_tol, double* eigvals, float* eigvecs, double* resid, double* gaps,
+                 int32_t* steps_used_host, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* The phases of hia_topk_eig as separate calls, so that a row-sharded caller can all-gather the
  * panel between the pass over the matrix and the (replicated, tiny) orthogonalisation:
  *   hia_eig_begin      start block (restart vectors + random), orthonormalised
  *   hia_eig_symm_rows  y_rows[rows x block] (row-major fp64) = C[rows, :] * current fp32 panel
  *   hia_eig_absorb     step j: y_full[n x block] (row-major, all rows) -> H[:, j], Q_{j+1}
- *   hia_eig_ritz       Jacobi on the projected matrix -> eigvals[k], eigvecs[k][n]; panel = [U, 0]
+ *   hia_eig_check      after steps_done steps: Jacobi + Lanczos residual estimates -> *converged_host
+ *                      (synchronises the stream; est_gap_host optional: k estimates + k gaps)
+ *   hia_eig_ritz       Jacobi on the first steps_used blocks -> eigvals[k], eigvecs[k][n], gaps[k]
+ *                      (optional); panel = [U, 0]
  *   hia_eig_resid      y_full = C [U, 0] -> resid[k] = ||C u - lambda u||
  * All take the same (n, block, steps) and the workspace of hia_topk_eig_workspace_bytes. */
 int hia_eig_begin(int32_t n, int32_t block, int32_t steps, uint64_t seed, const float* init_vecs,
@@ -334,8 +344,11 @@ int hia_eig_symm_rows(const float* c_rows, int32_t rows, int32_t n, int64_t ld, 
                       int32_t steps, void* workspace, double* y_rows, void* stream);
 int hia_eig_absorb(int32_t n, int32_t block, int32_t steps, int32_t j, const double* y_full,
                    void* workspace, void* stream);
-int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t k, double* eigvals, float* eigvecs,
-                 void* workspace, void* stream);
+int hia_eig_check(int32_t n, int32_t block, int32_t steps, int32_t steps_done, int32_t k, double rel_tol,
+                  double angle_tol, int32_t* converged_host, double* est_gap_host, void* workspace,
+                  void* stream);
+int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t steps_used, int32_t k,
+                 double* eigvals, float* eigvecs, double* gaps, void* workspace, void* stream);
 int hia_eig_resid(int32_t n, int32_t block, int32_t steps, int32_t k, const double* y_full,
                   const double* eigvals, double* resid, void* workspace, void* stream);
 

@@ -123,3 +123,31 @@ def test_gf_s1_and_gf_s2_steps(golden, case, methods, tmp_path):
         for nm, ty, sc in zip(names_o, g.get(f"gf.{method}.inter_score_type", []), ro):
             got = ours[(nm[1], nm[2], str(ty))]
             assert abs(got - sc) <= 2e-3 * abs(sc) + 2e-5, (nm, ty, got, sc)
+
+
+def test_hot_path_streaming_matches_blocking_calls():
+    """HotPath.run_host_many (double-buffered H2D) returns, sample by sample, what the blocking
+    HotPath.run_host returns, and both match the oracle's eigenpairs."""
+    import torch
+    from hiarch_b200.pipeline import HotPath
+    from oracle import hia_oracle as O
+    lens, bs = [260, 200, 150], 100000
+    samples, refs = [], []
+    hp = None
+    for seed in (1, 2, 3):
+        rows, cols, vals, seps = synth.synth_coo(lens, seed=seed)
+        if hp is None:
+            hp = HotPath(seps, bs, k_eig=3, max_nnz=len(rows) + 4096)
+        pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).pin_memory()
+        samples.append((pin(rows, torch.int32), pin(cols, torch.int32), pin(vals, torch.float32)))
+        dense = O.scatter_coo_sym(rows, cols, vals, sum(lens))
+        refs.append(O.topk_eig(O.pearson(O.oe_map_core(dense, seps, bs)), 3))
+    streamed = list(hp.run_host_many(samples))
+    assert len(streamed) == 3
+    for (w, v), smp, (w_ref, v_ref) in zip(streamed, samples, refs):
+        w2, v2 = hp.run_host(*smp)
+        assert np.allclose(w, w2, rtol=1e-9) and np.allclose(np.abs(v), np.abs(v2), atol=1e-5)
+        assert np.allclose(w, w_ref, rtol=1e-5)
+        for j in range(3):
+            cos = abs(v[:, j].astype(np.float64) @ v_ref[:, j]) / np.linalg.norm(v[:, j])
+            assert cos >= 0.9999, (j, cos)

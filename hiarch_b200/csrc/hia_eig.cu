@@ -45,6 +45,42 @@ __global__ void double_to_float_panel_kernel(const double* __restrict__ src, flo
   if (i < count) dst[i] = (float)src[i];
 }
 
+// packed fp32 FMA (Blackwell FFMA2): two lanes of a 64-bit register pair per instruction
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
+// Sum NACC (32 or 16) per-lane partials across the 32 lanes with a TRANSPOSING butterfly: at every
+// step a lane hands half of its values to its partner and keeps the other half, so the whole
+// reduction costs NACC - 1 shuffles (a butterfly per value costs 5 NACC) and lane l ends up with
+// the complete sum of value (l % NACC).
+template <int NACC>
+__device__ __forceinline__ float lane_transpose_sum(float (&v)[NACC], int lane) {
+  static_assert(NACC == 32 || NACC == 16, "4 rows x block of 8 or 4");
+  if (NACC == 16) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+  }
+#pragma unroll
+  for (int off = NACC / 2; off >= 1; off >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 // Y[n x B] (fp64, col-major, += into a zeroed panel) = C[n x n] (fp32 row-major) * V[n x B] (fp32).
 // CTA = 1024-column chunk x 256 rows: the V chunk (B x 1024 fp32) is staged in shared memory ONCE
 // per CTA and reused by 256 rows; every warp streams its 32 rows in groups of 4 with 128-bit
@@ -69,11 +105,13 @@ symm_panel_kernel(const float* __restrict__ c, int rows, int n, long long ld, co
   for (int g = 0; g < kSymmRowsPerCta / kSymmWarps / kSymmRowsPerWarp; ++g) {
     const int r0 = rbase + g * kSymmRowsPerWarp;
     if (r0 >= rows) break;
-    float acc[kSymmRowsPerWarp][B];
+    // (even-column, odd-column) partial sums: the pairs (a.x, a.y) / (v.x, v.y) are adjacent registers
+    // of the 128-bit loads, so one FFMA2 does two of the four products (the pass was issue-bound)
+    float2 acc[kSymmRowsPerWarp][B];
 #pragma unroll
     for (int r = 0; r < kSymmRowsPerWarp; ++r)
 #pragma unroll
-      for (int j = 0; j < B; ++j) acc[r][j] = 0.f;
+      for (int j = 0; j < B; ++j) acc[r][j] = make_float2(0.f, 0.f);
 #pragma unroll 2
     for (int cc = lane * 4; cc < kSymmCols; cc += 128) {
       const int gc = k0 + cc;
@@ -98,23 +136,24 @@ symm_panel_kernel(const float* __restrict__ c, int rows, int n, long long ld, co
         const float4 vv = *reinterpret_cast<const float4*>(&s_v[j][cc]);
 #pragma unroll
         for (int r = 0; r < kSymmRowsPerWarp; ++r) {
-          acc[r][j] = fmaf(a[r].x, vv.x, acc[r][j]);
-          acc[r][j] = fmaf(a[r].y, vv.y, acc[r][j]);
-          acc[r][j] = fmaf(a[r].z, vv.z, acc[r][j]);
-          acc[r][j] = fmaf(a[r].w, vv.w, acc[r][j]);
+          acc[r][j] = ffma2(make_float2(a[r].x, a[r].y), make_float2(vv.x, vv.y), acc[r][j]);
+          acc[r][j] = ffma2(make_float2(a[r].z, a[r].w), make_float2(vv.z, vv.w), acc[r][j]);
         }
       }
     }
+    float part[kSymmRowsPerWarp * B];
 #pragma unroll
     for (int r = 0; r < kSymmRowsPerWarp; ++r)
 #pragma unroll
-      for (int j = 0; j < B; ++j) {
-        const float s = warp_sum(acc[r][j]);
-        if (lane == ((r * B + j) & 31) && r0 + r < rows) {
-          double* dst = row_major ? &y[(long long)(r0 + r) * B + j] : &y[(long long)j * rows + r0 + r];
-          atomicAdd(dst, (double)s);
-        }
+      for (int j = 0; j < B; ++j) part[r * B + j] = acc[r][j].x + acc[r][j].y;
+    const float total = lane_transpose_sum<kSymmRowsPerWarp * B>(part, lane);
+    {
+      const int idx = lane % (kSymmRowsPerWarp * B), r = idx / B, j = idx % B;
+      if (lane < kSymmRowsPerWarp * B && r0 + r < rows) {
+        double* dst = row_major ? &y[(long long)(r0 + r) * B + j] : &y[(long long)j * rows + r0 + r];
+        atomicAdd(dst, (double)total);
       }
+    }
   }
 }
 
@@ -488,7 +527,7 @@ __global__ void rowmajor_to_colmajor_kernel(const double* __restrict__ src, doub
 
 // Orthonormalise Y (n x b) in place by CholQR; returns R in r_out (b x b), fp32 copy in yf.
 int cholqr(double* Y, int n, int b, EigWs& w, double* r_out, float* yf, cudaStream_t s) {
-  const int rows_per_cta = 8192;
+  const int rows_per_cta = 1024;      // 8192 left <= 32 CTAs for the b x b Gram: 86 us, latency-bound
   HIA_CUDA(cudaMemsetAsync(w.G2, 0, (size_t)b * b * 8, s));
   dim3 grid(b, (n + rows_per_cta - 1) / rows_per_cta);
   gram_kernel<<<grid, 256, 0, s>>>(Y, b, Y, b, n, rows_per_cta, w.G2);
@@ -581,7 +620,7 @@ HIA_API int hia_eig_absorb(int32_t n, int32_t block, int32_t steps, int32_t j, c
   const int p = (j + 1) * b;                         // columns of Q so far
   rowmajor_to_colmajor_kernel<<<(int)(((long long)n * b + 255) / 256), 256, 0, s>>>(y_full, Qn, n, b);
   HIA_LAUNCH_CHECK();
-  const int rows_per_cta = 8192;
+  const int rows_per_cta = 1024;      // 8192 left <= 32 CTAs for the b x b Gram: 86 us, latency-bound
   for (int pass = 0; pass < 2; ++pass) {             // CGS2 against all previous blocks
     HIA_CUDA(cudaMemsetAsync(w.G, 0, (size_t)p * b * 8, s));
     dim3 grid(p, (n + rows_per_cta - 1) / rows_per_cta);
@@ -632,8 +671,9 @@ HIA_API int hia_eig_check(int32_t n, int32_t block, int32_t steps, int32_t steps
 
 // ---- Rayleigh-Ritz on the first `steps_used` blocks: eigvals[k], eigvecs[k][n], gaps[k] (optional:
 // distance to the nearest other Ritz value); the fp32 panel becomes [U, 0] for the residual pass
-HIA_API int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t steps_used, int32_t k,
-                         double* eigvals, float* eigvecs, double* gaps, void* workspace, void* stream_) {
+HIA_API int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t steps_used, int32_t reuse_check,
+                         int32_t k, double* eigvals, float* eigvecs, double* gaps, void* workspace,
+                         void* stream_) {
   using namespace hia;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   int st = check_shape(n, block, steps);
@@ -643,8 +683,10 @@ HIA_API int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t steps_
   const int b = block, D = b * (steps + 1), dim = steps_used * b;
   EigWs w;
   carve(static_cast<unsigned char*>(workspace), n, b, steps, &w);
-  st = launch_jacobi(w, D, dim, s);
-  if (st != HIA_OK) return st;
+  if (!reuse_check) {          // reuse_check: the last hia_eig_check already decomposed exactly this matrix
+    st = launch_jacobi(w, D, dim, s);
+    if (st != HIA_OK) return st;
+  }
   if (gaps) {
     ritz_gap_kernel<<<1, 32, 0, s>>>(w.lam, w.order, dim, k, gaps);
     HIA_LAUNCH_CHECK();
@@ -679,7 +721,7 @@ HIA_API int hia_eig_resid(int32_t n, int32_t block, int32_t steps, int32_t k, co
 
 // ---- single-device driver: all phases on one stream. early_rel_tol / early_angle_tol > 0 enable the
 // pass-free convergence check (hia_eig_check, one tiny D2H flag) after every second step from the
-// fourth on: the cycle stops as soon as the Lanczos residual estimates meet the tolerance instead of
+// sixth on: the cycle stops as soon as the Lanczos residual estimates meet the tolerance instead of
 // always spending `steps` passes over the matrix. *steps_used_host (optional) = steps actually taken.
 HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block, int32_t steps,
                          uint64_t seed, const float* init_vecs, int32_t n_init, double early_rel_tol,
@@ -694,22 +736,22 @@ HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32
   carve(static_cast<unsigned char*>(workspace), n, block, steps, &w);
   double* ystage = w.Y;                               // n x block staging (row-major)
   const bool early = early_rel_tol > 0.0 || early_angle_tol > 0.0;
-  int used = steps;
+  int used = steps, reuse = 0;
   for (int j = 0; j < steps; ++j) {
     st = hia_eig_symm_rows(c, n, n, ld, block, steps, workspace, ystage, stream);
     if (st != HIA_OK) return st;
     st = hia_eig_absorb(n, block, steps, j, ystage, workspace, stream);
     if (st != HIA_OK) return st;
     const int done = j + 1;
-    if (early && done >= 4 && (done & 1) == 0 && done < steps) {
+    if (early && done >= 6 && (done & 1) == 0 && done < steps) {
       int conv = 0;
       st = hia_eig_check(n, block, steps, done, k, early_rel_tol, early_angle_tol, &conv, nullptr, workspace, stream);
       if (st != HIA_OK) return st;
-      if (conv) { used = done; break; }
+      if (conv) { used = done; reuse = 1; break; }
     }
   }
   if (steps_used_host) *steps_used_host = used;
-  st = hia_eig_ritz(n, block, steps, used, k, eigvals, eigvecs, gaps, workspace, stream);
+  st = hia_eig_ritz(n, block, steps, used, reuse, k, eigvals, eigvecs, gaps, workspace, stream);
   if (st != HIA_OK) return st;
   // the residual pass needs a second staging buffer: w.Y is the transposed target of hia_eig_resid
   double* ystage2 = w.Q + (long long)used * block * n;    // Q_{used} is no longer needed

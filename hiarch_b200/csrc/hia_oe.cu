@@ -328,6 +328,9 @@ __global__ void init_min_kernel(float* p) { *p = INFINITY; }
 // ln(1 + x) for x > 0 on the SFU: 1 + x is rounded once (<= 6e-8 absolute in the result), lg2.approx
 // has <= 2^-21.4 absolute error near 1 and 2 ulp elsewhere -- three orders below the 1e-5 the
 // path has to hold, and ~20 instructions cheaper than log1pf (the pass was ALU-bound with it).
+// The fill value of the non-positive cells MUST come from the same function: in the reference it is
+// bit-identical to the value of the (many) cells that attain the minimum, and the percentile
+// stages downstream (strict inequalities on a large tie group) depend on that tie.
 __device__ __forceinline__ float fast_log1p_pos(float x) { return __logf(1.f + x); }
 
 __global__ void __launch_bounds__(256)
@@ -343,7 +346,7 @@ oe_apply_kernel(const float* __restrict__ map, float* __restrict__ out, int n, l
   float fill = 0.f;
   if (do_log) {
     const float m = *min_pos_oe;
-    fill = (m == INFINITY) ? 0.f : log1pf(m);
+    fill = (m == INFINITY) ? 0.f : fast_log1p_pos(m);
   }
   int cb[4];
 #pragma unroll
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(256)
 log_apply_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int cols, long long ld,
                  const float* __restrict__ min_pos) {
   const float m = *min_pos;
-  const float fill = (m == INFINITY) ? 0.f : log1pf(m);
+  const float fill = (m == INFINITY) ? 0.f : fast_log1p_pos(m);
   const long long total = (long long)rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {

@@ -315,7 +315,7 @@ int hia_sim_gemm_rows(void* hi, void* lo, int precision, int32_t plane_rows, int
 /* +lambda/-lambda of equal magnitude may mix.                                            */
 /* ------------------------------------------------------------------------------------ */
 int64_t hia_topk_eig_workspace_bytes(int32_t n, int32_t block, int32_t steps);
-/* early_rel_tol / early_angle_tol > 0: after every second Lanczos step (from the fourth on) the
+/* early_rel_tol / early_angle_tol > 0: after every second Lanczos step (from the sixth on) the
  * Ritz residuals are ESTIMATED from the Lanczos relation (no pass over the matrix; one tiny D2H
  * flag) and the cycle ends as soon as every wanted pair has est <= early_rel_tol |lambda_1| or
  * est <= early_angle_tol * gap (gap = distance to the nearest other Ritz value: the sin-theta
@@ -334,8 +334,9 @@ int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block
  *   hia_eig_absorb     step j: y_full[n x block] (row-major, all rows) -> H[:, j], Q_{j+1}
  *   hia_eig_check      after steps_done steps: Jacobi + Lanczos residual estimates -> *converged_host
  *                      (synchronises the stream; est_gap_host optional: k estimates + k gaps)
- *   hia_eig_ritz       Jacobi on the first steps_used blocks -> eigvals[k], eigvecs[k][n], gaps[k]
- *                      (optional); panel = [U, 0]
+ *   hia_eig_ritz       Jacobi on the first steps_used blocks (skipped when reuse_check != 0: the last
+ *                      hia_eig_check ran with steps_done == steps_used) -> eigvals[k], eigvecs[k][n],
+ *                      gaps[k] (optional); panel = [U, 0]
  *   hia_eig_resid      y_full = C [U, 0] -> resid[k] = ||C u - lambda u||
  * All take the same (n, block, steps) and the workspace of hia_topk_eig_workspace_bytes. */
 int hia_eig_begin(int32_t n, int32_t block, int32_t steps, uint64_t seed, const float* init_vecs,
@@ -347,8 +348,8 @@ int hia_eig_absorb(int32_t n, int32_t block, int32_t steps, int32_t j, const dou
 int hia_eig_check(int32_t n, int32_t block, int32_t steps, int32_t steps_done, int32_t k, double rel_tol,
                   double angle_tol, int32_t* converged_host, double* est_gap_host, void* workspace,
                   void* stream);
-int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t steps_used, int32_t k,
-                 double* eigvals, float* eigvecs, double* gaps, void* workspace, void* stream);
+int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t steps_used, int32_t reuse_check,
+                 int32_t k, double* eigvals, float* eigvecs, double* gaps, void* workspace, void* stream);
 int hia_eig_resid(int32_t n, int32_t block, int32_t steps, int32_t k, const double* y_full,
                   const double* eigvals, double* resid, void* workspace, void* stream);
 

@@ -19,7 +19,7 @@ PROTOTYPES = {
     "hia_status_string": (ctypes.c_char_p, [c_int]),
     "hia_last_cuda_error": (ctypes.c_char_p, []),
     "hia_launch_count": (ctypes.c_uint64, []),
-    "hia_scatter_workspace_bytes": (c_i64, [c_i32]),
+    "hia_scatter_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "hia_scatter_coo_sym": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_int, c_int,
                                     c_vp, c_i32, c_vp, c_vp]),
     "hia_scatter_coo_remap": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_i64, c_int, c_vp]),
@@ -74,6 +74,7 @@ PROTOTYPES = {
     "hia_eig_begin": (c_int, [c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_i32, c_vp, c_i64, c_vp]),
     "hia_eig_symm_rows": (c_int, [c_vp, c_i32, c_i32, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "hia_eig_absorb": (c_int, [c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "hia_eig_first_check": (c_i32, [c_i32]),
     "hia_eig_check": (c_int, [c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_double, ctypes.c_double, c_vp, c_vp,
                               c_vp, c_vp]),
     "hia_eig_ritz": (c_int, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),

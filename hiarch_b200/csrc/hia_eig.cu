@@ -340,11 +340,12 @@ jacobi_kernel(const double* __restrict__ h, int D, int dim, double* __restrict__
           alpha += x * x; beta += y * y; gamma += x * y;
         }
         alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
-        if (fabs(gamma) <= 1e-13 * sqrt(alpha * beta) || gamma == 0.0) continue;
+        // |gamma| <= 1e-12 sqrt(alpha beta), compared squared: no sqrt on the dependent chain
+        if (gamma * gamma <= 1e-24 * alpha * beta || gamma == 0.0) continue;
         if (lane == 0) s_rot = 1;
         const double zeta = (beta - alpha) / (2.0 * gamma);
         const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+        const double cs = rsqrt(1.0 + t * t), sn = cs * t;
         double* vp = V + (long long)p * dim; double* vq = V + (long long)q * dim;
         for (int r = lane; r < dim; r += 32) {
           const double x = ap[r], y = aq[r];
@@ -719,9 +720,13 @@ HIA_API int hia_eig_resid(int32_t n, int32_t block, int32_t steps, int32_t k, co
   return HIA_OK;
 }
 
+// First convergence check after 2/3 of the steps (each check costs a Jacobi solve of the projected
+// matrix, ~1 ms in one CTA: about one pass over a 30 k map), then after every second step.
+HIA_API int32_t hia_eig_first_check(int32_t steps) { return steps * 2 / 3 > 4 ? steps * 2 / 3 : 4; }
+
 // ---- single-device driver: all phases on one stream. early_rel_tol / early_angle_tol > 0 enable the
-// pass-free convergence check (hia_eig_check, one tiny D2H flag) after every second step from the
-// sixth on: the cycle stops as soon as the Lanczos residual estimates meet the tolerance instead of
+// pass-free convergence check (hia_eig_check, one tiny D2H flag) after every second step from
+// hia_eig_first_check(steps) on: the cycle stops as soon as the Lanczos residual estimates meet the tolerance instead of
 // always spending `steps` passes over the matrix. *steps_used_host (optional) = steps actually taken.
 HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block, int32_t steps,
                          uint64_t seed, const float* init_vecs, int32_t n_init, double early_rel_tol,
@@ -743,7 +748,7 @@ HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32
     st = hia_eig_absorb(n, block, steps, j, ystage, workspace, stream);
     if (st != HIA_OK) return st;
     const int done = j + 1;
-    if (early && done >= 6 && (done & 1) == 0 && done < steps) {
+    if (early && done >= hia_eig_first_check(steps) && ((done - hia_eig_first_check(steps)) & 1) == 0 && done < steps) {
       int conv = 0;
       st = hia_eig_check(n, block, steps, done, k, early_rel_tol, early_angle_tol, &conv, nullptr, workspace, stream);
       if (st != HIA_OK) return st;

@@ -7,7 +7,14 @@
 // complex/src/main_local.py:112-115.
 //
 // HBM-bound: 12 B/nnz read + 4 B/cell written (fill) + 4..8 B/nnz scattered.
-// Zero fill:  memset -> RED.ADD scatter of the direct entries -> tiled mirror (triu input).
+// Zero fill, entries sorted by row (every COO that comes out of a CSR matrix or a .mtx file the
+//             pipeline writes; detected on the device, no host round trip):
+//             row_ptr_kernel (reads the row indices once: 4 B/nnz) -> fill_rows_sorted_kernel: one
+//             CTA per (row, 16 K-column segment) zeroes a shared-memory row buffer, adds the row's
+//             entries into it (shared-memory atomics: duplicates are summed) and writes the segment
+//             with coalesced stores (8 B/nnz read + 4 B per upper cell written; no memset, no
+//             read-modify-write of DRAM sectors) -> tiled mirror (triu input).
+// Zero fill, any order:  zero fill -> RED.ADD scatter of the direct entries -> tiled mirror.
 // Min fill:   NaN sentinel fill -> store 0 at present cells -> RED.ADD scatter -> min over the
 //             *scattered* cells (so duplicates are summed before the min, like coo->csr then
 //             np.min(data)) -> replace the remaining sentinels by the (per-block) min -> mirror.
@@ -144,7 +151,8 @@ template <bool kAdd>
 __global__ void __launch_bounds__(256)
 scatter_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
                const float* __restrict__ vals, long long nnz, int n, int mtx_type,
-               float* __restrict__ out, long long ld) {
+               float* __restrict__ out, long long ld, const int* __restrict__ only_if_flag) {
+  if (only_if_flag && !*only_if_flag) return;              // the sorted-row path did the work
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
     int r = rows[e], c = cols[e];
@@ -152,6 +160,65 @@ scatter_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
     if (mtx_type == HIA_MTX_TRIU && c < r) continue;
     if (kAdd) atomicAdd(out + (long long)r * ld + c, vals[e]);
     else out[(long long)r * ld + c] = 0.f;
+  }
+}
+
+// ---- sorted-row fast path ------------------------------------------------------------------
+// row_ptr[q] = first entry of row q (q in [0, n]); *flag |= 1 when the row indices are not
+// non-decreasing or out of range (the caller-independent fallback kernels then do the work).
+__global__ void __launch_bounds__(256)
+row_ptr_kernel(const int* __restrict__ rows, long long nnz, int n, long long* __restrict__ row_ptr,
+               int* __restrict__ flag) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+    const int r = rows[e];
+    const int prev = (e > 0) ? rows[e - 1] : -1;
+    if (r < 0 || r >= n || r < prev) { bad = true; continue; }
+    if (r != prev)
+      for (int q = max(prev, -1) + 1; q <= r; ++q) row_ptr[q] = e;
+    if (e == nnz - 1)
+      for (int q = r + 1; q <= n; ++q) row_ptr[q] = nnz;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+constexpr int kSegCols = 16384;              // 64 KB of shared memory per CTA, 3 CTAs per SM
+constexpr int kSegThreads = 512;
+
+__global__ void __launch_bounds__(kSegThreads)
+fill_rows_sorted_kernel(const int* __restrict__ cols, const float* __restrict__ vals,
+                        const long long* __restrict__ row_ptr, const int* __restrict__ flag, int n,
+                        long long ld, int mtx_type, float* __restrict__ out) {
+  extern __shared__ float s_row[];
+  if (*flag) return;
+  const int r = blockIdx.y;
+  const int c_lo = (mtx_type == HIA_MTX_TRIU) ? r : 0;     // a 'triu' row starts on the diagonal
+  const int seg_lo = c_lo + blockIdx.x * kSegCols;
+  if (seg_lo >= n) return;
+  const int seg_n = min(kSegCols, n - seg_lo);
+  for (int i = threadIdx.x; i < seg_n; i += blockDim.x) s_row[i] = 0.f;
+  __syncthreads();
+  const long long e0 = row_ptr[r], e1 = row_ptr[r + 1];
+  for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const int c = cols[e] - seg_lo;
+    if (c >= 0 && c < seg_n) atomicAdd(&s_row[c], vals[e]);
+  }
+  __syncthreads();
+  float* dst = out + (long long)r * ld + seg_lo;
+  for (int i = threadIdx.x; i < seg_n; i += blockDim.x) dst[i] = s_row[i];
+}
+
+// fallback zero fill (any entry order): does nothing when the sorted-row path ran
+__global__ void __launch_bounds__(256)
+zero_fill_if_kernel(float* __restrict__ out, int n, long long ld, const int* __restrict__ only_if_flag) {
+  if (!*only_if_flag) return;
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c0 >= n) return;
+  for (int r = blockIdx.y; r < n; r += gridDim.y) {
+    float* p = out + (long long)r * ld + c0;
+    if (c0 + 3 < n) *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
+    else for (int j = 0; j < 4 && c0 + j < n; ++j) p[j] = 0.f;
   }
 }
 
@@ -342,9 +409,14 @@ HIA_API int hia_bin_stats(const float* x, int32_t n, int64_t ld, double* row_sum
   return HIA_OK;
 }
 
-HIA_API int64_t hia_scatter_workspace_bytes(int32_t n_chr) {
+// workspace: [keys: n_chr^2 + 1 u32 (min fill)] [flag: 1 int, 256-byte slot] [row_ptr: n + 1 i64]
+static int64_t scatter_keys_bytes(int32_t n_chr) {
   if (n_chr < 1) n_chr = 1;
-  return (int64_t)((int64_t)n_chr * n_chr + 1) * 4;
+  return ((int64_t)((int64_t)n_chr * n_chr + 1) * 4 + 255) / 256 * 256;
+}
+HIA_API int64_t hia_scatter_workspace_bytes(int32_t n, int32_t n_chr) {
+  if (n < 0) n = 0;
+  return scatter_keys_bytes(n_chr) + 256 + ((int64_t)n + 1) * 8;
 }
 
 HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const float* vals,
@@ -363,14 +435,33 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
 
   const int threads = 256;
   const int grid_e = (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (nnz + threads - 1) / threads));
-  if (fill_mode == HIA_FILL_ZERO) {
+  if (fill_mode == HIA_FILL_ZERO && workspace && nnz > 0 && aligned16(workspace)) {
+    // sorted-row path, with the any-order kernels as a device-side fallback (flag)
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    int* flag = reinterpret_cast<int*>(ws + scatter_keys_bytes(n_chr));
+    long long* row_ptr = reinterpret_cast<long long*>(ws + scatter_keys_bytes(n_chr) + 256);
+    HIA_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
+    row_ptr_kernel<<<grid_e, threads, 0, stream>>>(rows, nnz, n, row_ptr, flag);
+    HIA_LAUNCH_CHECK();
+    HIA_CUDA(cudaFuncSetAttribute(fill_rows_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSegCols * (int)sizeof(float)));
+    dim3 grid_f((n + kSegCols - 1) / kSegCols, n);
+    fill_rows_sorted_kernel<<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(cols, vals, row_ptr, flag, n,
+                                                                                        ld, mtx_type, out);
+    HIA_LAUNCH_CHECK();
+    dim3 grid_z((n + threads * 4 - 1) / (threads * 4), min(n, 4096));
+    zero_fill_if_kernel<<<grid_z, threads, 0, stream>>>(out, n, ld, flag);
+    HIA_LAUNCH_CHECK();
+    scatter_kernel<true><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld, flag);
+    HIA_LAUNCH_CHECK();
+  } else if (fill_mode == HIA_FILL_ZERO) {
     if (ld == n) {
       HIA_CUDA(cudaMemsetAsync(out, 0, (size_t)n * n * sizeof(float), stream));
     } else {
       HIA_CUDA(cudaMemset2DAsync(out, (size_t)ld * 4, 0, (size_t)n * 4, n, stream));
     }
     if (nnz > 0) {
-      scatter_kernel<true><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld);
+      scatter_kernel<true><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld, nullptr);
       HIA_LAUNCH_CHECK();
     }
   } else {
@@ -383,9 +474,9 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
     fill_const_kernel<<<grid, threads, 0, stream>>>(out, n, ld, nanf(""));
     HIA_LAUNCH_CHECK();
     if (nnz > 0) {
-      scatter_kernel<false><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld);
+      scatter_kernel<false><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld, nullptr);
       HIA_LAUNCH_CHECK();
-      scatter_kernel<true><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld);
+      scatter_kernel<true><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld, nullptr);
       HIA_LAUNCH_CHECK();
       block_min_kernel<<<grid_e, threads, sh, stream>>>(rows, cols, out, ld, nnz, n, mtx_type, chr_start,
                                                           n_chr, fill_mode == HIA_FILL_BLOCK_MIN, keys);

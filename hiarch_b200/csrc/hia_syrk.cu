@@ -445,12 +445,18 @@ __device__ __forceinline__ void split_hi_lo(float xn, typename PlaneT<PREC>::typ
   }
 }
 
+// ncu (N = 30 894): the first version read the map TWICE from DRAM (7.4 GB): 148 x 8 CTAs x 123 KB rows
+// in flight = 146 MB > the 126 MB L2, so the second pass missed. Now 512-thread CTAs (<= 4 per SM:
+// 73 MB of rows in flight) and the second pass walks the row BACKWARDS, i.e. most-recently-read
+// first, which is what an LRU-like L2 still holds.
+constexpr int kPrepThreads = 512;
+
 template <int PREC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kPrepThreads, 4)
 row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int kpad, int center,
                 typename PlaneT<PREC>::type* __restrict__ hi, typename PlaneT<PREC>::type* __restrict__ lo) {
   typedef typename PlaneT<PREC>::type P;
-  __shared__ double s_red[8][2];
+  __shared__ double s_red[kPrepThreads / 32][2];
   __shared__ double s_val[2];
   const int r = blockIdx.x;
   if (r >= m) return;
@@ -478,7 +484,7 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
   __syncthreads();
   if (tid == 0) {
     double t1 = 0, t2 = 0;
-    for (int i = 0; i < 8; ++i) { t1 += s_red[i][0]; t2 += s_red[i][1]; }
+    for (int i = 0; i < kPrepThreads / 32; ++i) { t1 += s_red[i][0]; t2 += s_red[i][1]; }
     // Pearson: centre on the mean; cosine: centre on 0 (= shift back)
     const double mean_s = center ? t1 / (double)k : -shift;      // mean of (x - shift)
     const double ss = t2 - 2.0 * mean_s * t1 + (double)k * mean_s * mean_s;   // sum (x - shift - mean_s)^2
@@ -489,10 +495,11 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
   const double mean = s_val[0], inv = s_val[1];
   P* ph = hi + (long long)r * kpad;
   P* pl = lo + (long long)r * kpad;
-  // second pass: 4 cells per thread (128-bit loads; 128-/64-bit plane stores; kpad % 4 == 0 and the
-  // plane rows are 16-byte aligned by construction)
+  // second pass, back to front: 4 cells per thread (128-bit loads; 128-/64-bit plane stores; kpad % 4
+  // == 0 and the plane rows are 16-byte aligned by construction)
   if (vec_ok) {
-    for (int j4 = tid; j4 < (kpad >> 2); j4 += blockDim.x) {
+    const int n4 = kpad >> 2;
+    for (int j4 = n4 - 1 - tid; j4 >= 0; j4 -= blockDim.x) {
       const int j = j4 << 2;
       float xv[4] = {0.f, 0.f, 0.f, 0.f};
       if (j + 3 < k) {
@@ -519,7 +526,7 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
       }
     }
   } else {
-    for (int j = tid; j < kpad; j += blockDim.x) {
+    for (int j = kpad - 1 - tid; j >= 0; j -= blockDim.x) {
       P h = P(0.f), l = P(0.f);
       if (j < k) split_hi_lo<PREC>((float)(((double)row[j] - mean) * inv), h, l);
       ph[j] = h;
@@ -582,10 +589,10 @@ int launch_prep(const float* x, int rows, int k, long long ld_x, int center, voi
                 cudaStream_t stream) {
   const int kpad = round_up(k, bk_of(prec));
   if (prec == HIA_PREC_3XF16)
-    row_prep_kernel<HIA_PREC_3XF16><<<rows, 256, 0, stream>>>(x, rows, k, ld_x, kpad, center,
+    row_prep_kernel<HIA_PREC_3XF16><<<rows, kPrepThreads, 0, stream>>>(x, rows, k, ld_x, kpad, center,
                                                              static_cast<__half*>(hi), static_cast<__half*>(lo));
   else
-    row_prep_kernel<HIA_PREC_3XTF32><<<rows, 256, 0, stream>>>(x, rows, k, ld_x, kpad, center,
+    row_prep_kernel<HIA_PREC_3XTF32><<<rows, kPrepThreads, 0, stream>>>(x, rows, k, ld_x, kpad, center,
                                                               static_cast<float*>(hi), static_cast<float*>(lo));
   HIA_LAUNCH_CHECK();
   return HIA_OK;

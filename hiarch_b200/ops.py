@@ -86,6 +86,9 @@ class GenomeLayout:
 
 
 # ------------------------------------------------------------------------------- a1/a2 scatter
+_scatter_ws = {}
+
+
 def scatter_coo_sym(rows, cols, vals, n, mtx_type=MTX_TRIU, fill_mode=FILL_ZERO, layout=None,
                     out=None):
     """COO (int32 rows, int32 cols, fp32 vals; CUDA) -> dense symmetric fp32 [n, n] view.
@@ -97,15 +100,19 @@ def scatter_coo_sym(rows, cols, vals, n, mtx_type=MTX_TRIU, fill_mode=FILL_ZERO,
     rows, cols, vals = rows.contiguous(), cols.contiguous(), vals.contiguous()
     if out is None:
         out = alloc_map(n, rows.device)
-    ws = None
     n_chr = 0
     chr_start = None
     if fill_mode != FILL_ZERO:
         if layout is None:
             layout = GenomeLayout([(0, n - 1)], rows.device)
         n_chr, chr_start = layout.n_chr, layout.chr_start
-        ws = torch.empty(lib.hia_scatter_workspace_bytes(n_chr) // 4, dtype=torch.float32,
-                         device=rows.device)
+    key = (str(rows.device), n, n_chr, _stream())               # one scratch per stream: calls may overlap
+    ws = _scatter_ws.get(key)
+    if ws is None:
+        ws = torch.empty(lib.hia_scatter_workspace_bytes(n, n_chr), dtype=torch.uint8, device=rows.device)
+        if len(_scatter_ws) > 8:
+            _scatter_ws.clear()
+        _scatter_ws[key] = ws
     st = lib.hia_scatter_coo_sym(_ptr(rows), _ptr(cols), _ptr(vals), rows.numel(), n, _ptr(out),
                                  out.stride(0), mtx_type, fill_mode, _ptr(chr_start), n_chr,
                                  _ptr(ws), _stream())

@@ -56,9 +56,14 @@ uint64_t hia_launch_count(void);
 #define HIA_FILL_MIN       1  /* absent cells = min(all entries) (has_neg, whole matrix)     */
 #define HIA_FILL_BLOCK_MIN 2  /* absent cells = min(entries of that chromosome-pair block)   */
                               /* (yield_by_chro(triu=True) + to_dense, main_local.py:112-115) */
-/* workspace: (C*C + 1) floats. Duplicate (i,j) are summed (coo->csr). Explicit zero
- * entries are stored as 0 (they are not "absent"). out is n x n, ld >= n. */
-int64_t hia_scatter_workspace_bytes(int32_t n_chr);
+/* workspace: hia_scatter_workspace_bytes(n, n_chr) bytes, 16-byte aligned (min-fill keys + the row
+ * pointers of the sorted-row path). Optional for HIA_FILL_ZERO: with a workspace, entries that are
+ * sorted by row (any COO taken from a CSR matrix / a .mtx file of the pipeline; checked on the
+ * device) are written row by row through shared memory -- no memset, no read-modify-write --
+ * and any other order falls back, on the device, to zero fill + atomic adds; without a workspace
+ * only the latter runs. Duplicate (i,j) are summed (coo->csr). Explicit zero entries are stored
+ * as 0 (they are not "absent"). out is n x n, ld >= n. */
+int64_t hia_scatter_workspace_bytes(int32_t n, int32_t n_chr);
 int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz,
                         int32_t n, float* out, int64_t ld, int mtx_type, int fill_mode,
                         const int32_t* chr_start, int32_t n_chr, void* workspace, void* stream);
@@ -315,7 +320,8 @@ int hia_sim_gemm_rows(void* hi, void* lo, int precision, int32_t plane_rows, int
 /* +lambda/-lambda of equal magnitude may mix.                                            */
 /* ------------------------------------------------------------------------------------ */
 int64_t hia_topk_eig_workspace_bytes(int32_t n, int32_t block, int32_t steps);
-/* early_rel_tol / early_angle_tol > 0: after every second Lanczos step (from the sixth on) the
+/* early_rel_tol / early_angle_tol > 0: after every second Lanczos step (from step
+ * hia_eig_first_check(steps) = max(4, 2 steps / 3) on) the
  * Ritz residuals are ESTIMATED from the Lanczos relation (no pass over the matrix; one tiny D2H
  * flag) and the cycle ends as soon as every wanted pair has est <= early_rel_tol |lambda_1| or
  * est <= early_angle_tol * gap (gap = distance to the nearest other Ritz value: the sin-theta
@@ -345,6 +351,7 @@ int hia_eig_symm_rows(const float* c_rows, int32_t rows, int32_t n, int64_t ld, 
                       int32_t steps, void* workspace, double* y_rows, void* stream);
 int hia_eig_absorb(int32_t n, int32_t block, int32_t steps, int32_t j, const double* y_full,
                    void* workspace, void* stream);
+int32_t hia_eig_first_check(int32_t steps);
 int hia_eig_check(int32_t n, int32_t block, int32_t steps, int32_t steps_done, int32_t k, double rel_tol,
                   double angle_tol, int32_t* converged_host, double* est_gap_host, void* workspace,
                   void* stream);

@@ -83,6 +83,35 @@ def test_scatter_duplicates_lower_entries_and_empty():
     assert float(empty.abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("n", [257, 17000])
+def test_scatter_sorted_row_path_and_fallback(n):
+    """Row-sorted entries take the shared-memory row path (duplicates, lower-triangle entries of a
+    'triu' input, empty rows, rows longer than one 16 K-column segment); the same entries shuffled
+    take the atomic fallback; both must equal the oracle bit for bit (small-integer values: any
+    summation order is exact)."""
+    from hiarch_b200 import ops
+    rng = np.random.default_rng(n)
+    nnz = 40 * n
+    rows = rng.integers(0, n, nnz).astype(np.int32)
+    rows[rows % 7 == 3] = 5                                    # empty rows + one very long row
+    cols = rng.integers(0, n, nnz).astype(np.int32)
+    vals = rng.integers(-8, 9, nnz).astype(np.float32)
+    order = np.argsort(rows, kind="stable")                    # row-sorted, columns in random order
+    for mtx_type, name in ((ops.MTX_TRIU, "triu"), (ops.MTX_ALL, "all")):
+        ref = O.scatter_coo_sym(rows, cols, vals, n, mtx_type=name).astype(np.float32)
+        for idx in (order, rng.permutation(nnz)):
+            got = ops.scatter_coo_sym(_dev(rows[idx], torch.int32), _dev(cols[idx], torch.int32),
+                                      _dev(vals[idx], torch.float32), n, mtx_type=mtx_type)
+            assert np.array_equal(got.cpu().numpy(), ref)
+    # out-of-range entries are ignored on both paths (like the any-order kernel always did)
+    bad_r = np.concatenate([rows[order], [n - 1]]).astype(np.int32)
+    bad_c = np.concatenate([cols[order], [n + 3]]).astype(np.int32)
+    bad_v = np.concatenate([vals[order], [5.0]]).astype(np.float32)
+    got = ops.scatter_coo_sym(_dev(bad_r, torch.int32), _dev(bad_c, torch.int32), _dev(bad_v, torch.float32), n,
+                              mtx_type=ops.MTX_ALL)
+    assert np.array_equal(got.cpu().numpy(), O.scatter_coo_sym(rows, cols, vals, n, mtx_type="all").astype(np.float32))
+
+
 # --------------------------------------------------------------------------------- O/E + log
 def _check_oe(dense64, seps, bs):
     from hiarch_b200 import ops

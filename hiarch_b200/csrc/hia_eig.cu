@@ -18,7 +18,7 @@ namespace hia {
 namespace {
 
 constexpr int kMaxBlock = 16;
-constexpr int kSymmCols = 1024;       // columns of C per shared-memory V chunk
+constexpr int kSymmCols = 2048;       // columns of C per shared-memory V chunk (64 KB at block 8: dynamic)
 constexpr int kSymmRowsPerWarp = 4;
 constexpr int kSymmWarps = 8;
 constexpr int kSymmRows = kSymmRowsPerWarp * kSymmWarps;   // 32 rows per CTA
@@ -82,7 +82,7 @@ __device__ __forceinline__ float lane_transpose_sum(float (&v)[NACC], int lane) 
 }
 
 // Y[n x B] (fp64, col-major, += into a zeroed panel) = C[n x n] (fp32 row-major) * V[n x B] (fp32).
-// CTA = 1024-column chunk x 256 rows: the V chunk (B x 1024 fp32) is staged in shared memory ONCE
+// CTA = 2048-column chunk x 256 rows: the V chunk (B x 2048 fp32) is staged in shared memory ONCE
 // per CTA and reused by 256 rows; every warp streams its 32 rows in groups of 4 with 128-bit
 // loads, fp32 partials over the chunk, butterfly reduce, one fp64 atomicAdd per (row, vector).
 constexpr int kSymmRowsPerCta = 256;
@@ -92,7 +92,8 @@ symm_panel_kernel(const float* __restrict__ c, int rows, int n, long long ld, co
                   double* __restrict__ y, int row_major) {
   // c: rows x n block of the matrix (rows <= n); v: n x B panel (col-major, ld n);
   // y: rows x B, row-major (row_major != 0) or col-major with ld = rows
-  __shared__ __align__(16) float s_v[B][kSymmCols];
+  extern __shared__ __align__(16) unsigned char s_symm_raw[];
+  float (*s_v)[kSymmCols] = reinterpret_cast<float (*)[kSymmCols]>(s_symm_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * kSymmCols;
   for (int idx = threadIdx.x; idx < B * kSymmCols; idx += blockDim.x) {
@@ -505,7 +506,9 @@ int launch_symm(const float* c, int rows, int n, long long ld, const float* v, d
                 cudaStream_t s) {
   HIA_CUDA(cudaMemsetAsync(y, 0, (size_t)rows * B * sizeof(double), s));
   dim3 grid((n + kSymmCols - 1) / kSymmCols, (rows + kSymmRowsPerCta - 1) / kSymmRowsPerCta);
-  symm_panel_kernel<B><<<grid, kSymmWarps * 32, 0, s>>>(c, rows, n, ld, v, y, row_major);
+  const int smem = B * kSymmCols * (int)sizeof(float);
+  HIA_CUDA(cudaFuncSetAttribute(symm_panel_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  symm_panel_kernel<B><<<grid, kSymmWarps * 32, smem, s>>>(c, rows, n, ld, v, y, row_major);
   count_launch();
   return cuda_ok(cudaGetLastError());
 }

@@ -169,16 +169,32 @@ scatter_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
 __global__ void __launch_bounds__(256)
 row_ptr_kernel(const int* __restrict__ rows, long long nnz, int n, long long* __restrict__ row_ptr,
                int* __restrict__ flag) {
-  long long stride = (long long)gridDim.x * blockDim.x;
+  // 4 consecutive entries per thread (one 128-bit load + the entry before them)
+  const long long groups = (nnz + 3) >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
   bool bad = false;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
-    const int r = rows[e];
-    const int prev = (e > 0) ? rows[e - 1] : -1;
-    if (r < 0 || r >= n || r < prev) { bad = true; continue; }
-    if (r != prev)
-      for (int q = max(prev, -1) + 1; q <= r; ++q) row_ptr[q] = e;
-    if (e == nnz - 1)
-      for (int q = r + 1; q <= n; ++q) row_ptr[q] = nnz;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    const long long e0 = g << 2;
+    int rv[4];
+    if (e0 + 3 < nnz) {
+      const int4 t = *reinterpret_cast<const int4*>(rows + e0);     // cudaMalloc'd arrays: 16-byte aligned
+      rv[0] = t.x; rv[1] = t.y; rv[2] = t.z; rv[3] = t.w;
+    } else {
+      for (int i = 0; i < 4; ++i) rv[i] = (e0 + i < nnz) ? rows[e0 + i] : 0;
+    }
+    int prev = (e0 > 0) ? rows[e0 - 1] : -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long e = e0 + i;
+      if (e >= nnz) break;
+      const int r = rv[i];
+      if (r < 0 || r >= n || r < prev) { bad = true; prev = r; continue; }
+      if (r != prev)
+        for (int q = max(prev, -1) + 1; q <= r; ++q) row_ptr[q] = e;
+      if (e == nnz - 1)
+        for (int q = r + 1; q <= n; ++q) row_ptr[q] = nnz;
+      prev = r;
+    }
   }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
@@ -197,16 +213,43 @@ fill_rows_sorted_kernel(const int* __restrict__ cols, const float* __restrict__ 
   const int seg_lo = c_lo + blockIdx.x * kSegCols;
   if (seg_lo >= n) return;
   const int seg_n = min(kSegCols, n - seg_lo);
+  const long long e0 = row_ptr[r], e1 = row_ptr[r + 1];    // in flight while the buffer is zeroed
   for (int i = threadIdx.x; i < seg_n; i += blockDim.x) s_row[i] = 0.f;
   __syncthreads();
-  const long long e0 = row_ptr[r], e1 = row_ptr[r + 1];
-  for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-    const int c = cols[e] - seg_lo;
-    if (c >= 0 && c < seg_n) atomicAdd(&s_row[c], vals[e]);
+  // the row's entries: scalar head up to a 16-byte boundary, 128-bit body (two groups in flight), scalar tail
+  const long long a0 = min(e1, (e0 + 3) & ~3ll), a1 = max(a0, e1 & ~3ll);
+  auto add = [&](int c, float v) {
+    c -= seg_lo;
+    if (c >= 0 && c < seg_n) atomicAdd(&s_row[c], v);
+  };
+  for (long long e = e0 + threadIdx.x; e < a0; e += blockDim.x) add(cols[e], vals[e]);
+  const long long ng = (a1 - a0) >> 2;
+  long long g = threadIdx.x;
+  for (; g + blockDim.x < ng; g += 2 * blockDim.x) {
+    const int4 c0 = *reinterpret_cast<const int4*>(cols + a0 + 4 * g);
+    const float4 v0 = *reinterpret_cast<const float4*>(vals + a0 + 4 * g);
+    const int4 c1 = *reinterpret_cast<const int4*>(cols + a0 + 4 * (g + blockDim.x));
+    const float4 v1 = *reinterpret_cast<const float4*>(vals + a0 + 4 * (g + blockDim.x));
+    add(c0.x, v0.x); add(c0.y, v0.y); add(c0.z, v0.z); add(c0.w, v0.w);
+    add(c1.x, v1.x); add(c1.y, v1.y); add(c1.z, v1.z); add(c1.w, v1.w);
   }
+  for (; g < ng; g += blockDim.x) {
+    const int4 c0 = *reinterpret_cast<const int4*>(cols + a0 + 4 * g);
+    const float4 v0 = *reinterpret_cast<const float4*>(vals + a0 + 4 * g);
+    add(c0.x, v0.x); add(c0.y, v0.y); add(c0.z, v0.z); add(c0.w, v0.w);
+  }
+  for (long long e = a1 + threadIdx.x; e < e1; e += blockDim.x) add(cols[e], vals[e]);
   __syncthreads();
   float* dst = out + (long long)r * ld + seg_lo;
-  for (int i = threadIdx.x; i < seg_n; i += blockDim.x) dst[i] = s_row[i];
+  // 128-bit stores from the first 16-byte aligned cell of the segment on
+  const int head = min(seg_n, (int)((4 - ((((long long)r * ld + seg_lo)) & 3)) & 3));
+  for (int i = threadIdx.x; i < head; i += blockDim.x) dst[i] = s_row[i];
+  const int nv = (seg_n - head) >> 2;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const int o = head + 4 * i;
+    *reinterpret_cast<float4*>(dst + o) = make_float4(s_row[o], s_row[o + 1], s_row[o + 2], s_row[o + 3]);
+  }
+  for (int i = head + 4 * nv + threadIdx.x; i < seg_n; i += blockDim.x) dst[i] = s_row[i];
 }
 
 // fallback zero fill (any entry order): does nothing when the sorted-row path ran
@@ -435,7 +478,8 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
 
   const int threads = 256;
   const int grid_e = (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (nnz + threads - 1) / threads));
-  if (fill_mode == HIA_FILL_ZERO && workspace && nnz > 0 && aligned16(workspace)) {
+  if (fill_mode == HIA_FILL_ZERO && workspace && nnz > 0 && aligned16(workspace) && aligned16(rows) &&
+      aligned16(cols) && aligned16(vals)) {
     // sorted-row path, with the any-order kernels as a device-side fallback (flag)
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     int* flag = reinterpret_cast<int*>(ws + scatter_keys_bytes(n_chr));

@@ -18,7 +18,7 @@ namespace hia {
 namespace {
 
 constexpr int kMaxBlock = 16;
-constexpr int kSymmCols = 2048;       // columns of C per shared-memory V chunk (64 KB at block 8: dynamic)
+constexpr int kSymmCols = 1024;       // columns of C per shared-memory V chunk (2048 measured slower: 844 vs 815 us)
 constexpr int kSymmRowsPerWarp = 4;
 constexpr int kSymmWarps = 8;
 constexpr int kSymmRows = kSymmRowsPerWarp * kSymmWarps;   // 32 rows per CTA
@@ -82,7 +82,7 @@ __device__ __forceinline__ float lane_transpose_sum(float (&v)[NACC], int lane) 
 }
 
 // Y[n x B] (fp64, col-major, += into a zeroed panel) = C[n x n] (fp32 row-major) * V[n x B] (fp32).
-// CTA = 2048-column chunk x 256 rows: the V chunk (B x 2048 fp32) is staged in shared memory ONCE
+// CTA = 1024-column chunk x 256 rows: the V chunk (B x 1024 fp32) is staged in shared memory ONCE
 // per CTA and reused by 256 rows; every warp streams its 32 rows in groups of 4 with 128-bit
 // loads, fp32 partials over the chunk, butterfly reduce, one fp64 atomicAdd per (row, vector).
 constexpr int kSymmRowsPerCta = 256;

@@ -115,6 +115,18 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, angle_tol=1e-3, m
         else:
             y_full.copy_(y_rows)
 
+    vote = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def agree(flag):
+        """Every rank must take the SAME branch (the collectives of the next step have to pair up).
+        The replicated Lanczos state is equal only up to the rounding of the fp64 atomics in the Gram
+        kernels, so a borderline estimate could flip on one rank: decide by a MIN all-reduce."""
+        if world == 1:
+            return bool(flag)
+        vote.fill_(1 if flag else 0)
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN, group=group)
+        return bool(vote.item())
+
     init, n_init, info = None, 0, []
     for it in range(max_restarts):
         _lib.check(lib.hia_eig_begin(n, block, steps, seed + it, ops._ptr(init), n_init, ws.data_ptr(),
@@ -127,10 +139,10 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, angle_tol=1e-3, m
                        "hia_eig_absorb")
             done = j + 1
             if done >= first_check and (done - first_check) % 2 == 0 and done < steps:
-                # replicated and bit-identical on every rank -> every rank takes the same decision
+                # replicated on every rank; the branch is taken by agreement (see agree())
                 _lib.check(lib.hia_eig_check(n, block, steps, done, k, 0.5 * tol, 0.5 * angle_tol,
                                              ctypes.addressof(conv), None, ws.data_ptr(), s()), "hia_eig_check")
-                if conv.value:
+                if agree(conv.value):
                     used, reuse = done, 1
                     break
         _lib.check(lib.hia_eig_ritz(n, block, steps, used, reuse, k, eigvals.data_ptr(), eigvecs.data_ptr(),
@@ -140,7 +152,7 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, angle_tol=1e-3, m
                                      resid.data_ptr(), ws.data_ptr(), s()), "hia_eig_resid")
         r, lam = resid.cpu().numpy(), eigvals.cpu().numpy()
         info.append((float(r.max()), float(abs(lam[0])), used))
-        if ops.eig_converged(r, lam, gaps.cpu().numpy(), tol, angle_tol):
+        if agree(ops.eig_converged(r, lam, gaps.cpu().numpy(), tol, angle_tol)):
             break
         init, n_init = eigvecs.clone(), k
     return eigvals, eigvecs.t(), info

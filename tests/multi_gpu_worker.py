@@ -34,6 +34,12 @@ def main():
     w2, v2, info = topk_eig_rows(mine, n, k=3)
     cos = [float(abs((v1[:, j].double() @ v2[:, j].double())) / (v1[:, j].double().norm() * v2[:, j].double().norm()))
            for j in range(3)]
+    # forced restarts + in-cycle convergence checks (short cycles, unreachable tolerance): the ranks
+    # must keep taking the same branches, and the result must still match the single-GPU solver
+    w3, v3, info3 = ops.topk_eig(full, k=3, steps=6, tol=1e-14, angle_tol=0.0, max_restarts=3, return_info=True)
+    w4, v4, info4 = topk_eig_rows(mine, n, k=3, steps=6, tol=1e-14, angle_tol=0.0, max_restarts=3)
+    restart_rel = float(((w3 - w4).abs() / w3.abs()).max())
+    restart_cycles = [len(info3), len(info4)]
     # row-sharded O/E + log against the single-GPU passes, on a multi-chromosome count map
     lens = [n // 2, n // 3, n - n // 2 - n // 3]
     lam, seps = synth.rate_matrix(lens, seed=3)
@@ -48,7 +54,8 @@ def main():
     got_oe, _ = obs_d_exp_rows(counts[r0:r0 + nr], layout, 100000, r0)
     oe_err = float((got_oe - ref_oe[r0:r0 + nr]).abs().max()) if nr else 0.0
     rec = {"rank": rank, "world": world, "rows": [sh.row0, sh.rows], "sim_err": sim_err, "oe_err": oe_err,
-           "eig_rel": float(((w1 - w2).abs() / w1.abs()).max()), "cos": cos, "info": info}
+           "eig_rel": float(((w1 - w2).abs() / w1.abs()).max()), "cos": cos, "info": info,
+           "restart_rel": restart_rel, "restart_cycles": restart_cycles}
     D.barrier()
     sys.stdout.write("REC " + json.dumps(rec) + "\n")
     sys.stdout.flush()

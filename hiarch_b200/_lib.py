@@ -78,6 +78,7 @@ PROTOTYPES = {
     "hia_eig_check": (c_int, [c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_double, ctypes.c_double, c_vp, c_vp,
                               c_vp, c_vp]),
     "hia_eig_ritz": (c_int, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hia_eig_set_ritz": (c_int, [c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "hia_eig_resid": (c_int, [c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 

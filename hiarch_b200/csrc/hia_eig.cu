@@ -158,7 +158,7 @@ symm_panel_kernel(const float* __restrict__ c, int rows, int n, long long ld, co
   }
 }
 
-// G[p x b] (row-major, += ) = A[:, 0:p]^T B[:, 0:b]; A, B col-major fp64 with ld = n.
+// Gpart[chunk][p x b] (row-major) = A[chunk rows, 0:p]^T B[chunk rows, 0:b]; A, B col-major fp64, ld = n.
 __global__ void __launch_bounds__(256)
 gram_kernel(const double* __restrict__ a, int p, const double* __restrict__ bm, int b, int n,
             int rows_per_cta, double* __restrict__ g) {
@@ -188,8 +188,19 @@ gram_kernel(const double* __restrict__ a, int p, const double* __restrict__ bm, 
   if (threadIdx.x < b) {
     double s = 0.0;
     for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
-    atomicAdd(&g[i * b + threadIdx.x], s);
+    // per-row-chunk partial, summed in a FIXED order by gram_reduce_kernel: the replicated solvers of
+    // a row-sharded run must stay bit-identical (atomics would make the rounding order-dependent)
+    g[((long long)blockIdx.y * p + i) * b + threadIdx.x] = s;
   }
+}
+
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const double* __restrict__ gpart, int chunks, int count, double* __restrict__ g) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  double s = 0.0;
+  for (int c = 0; c < chunks; ++c) s += gpart[(long long)c * count + idx];
+  g[idx] = s;
 }
 
 // Y[:, j] -= sum_i A[:, i] G[i][j]   (thread per row)
@@ -468,12 +479,27 @@ resid_kernel(const double* __restrict__ w, const double* __restrict__ u, const d
 __global__ void sqrt_kernel(double* x, int k) { if (threadIdx.x < k) x[threadIdx.x] = sqrt(x[threadIdx.x]); }
 
 struct EigWs {
-  double *Q, *Y, *U, *H, *G, *G2, *R1, *Rinv, *R2, *Rt, *JA, *JV, *lam, *resid2;
+  double *Q, *Y, *U, *H, *G, *G2, *R1, *Rinv, *R2, *Rt, *JA, *JV, *lam, *resid2, *Gpart;
   float *Vf;
   int* order;
   double* check;      // [2 * kMaxBlock] estimates + gaps of the last convergence check
   int* flag;
 };
+
+constexpr int kGramRowsPerCta = 1024;   // 8192 left <= 32 CTAs for the b x b Gram: 86 us, latency-bound
+inline int gram_chunks(int n) { return (n + kGramRowsPerCta - 1) / kGramRowsPerCta; }
+
+// G (p x b) = A[:, 0:p]^T B, deterministic: partials per row chunk + ordered reduction
+int gram(const double* a, int p, const double* bm, int b, int n, double* gpart, double* g, cudaStream_t s) {
+  dim3 grid(p, gram_chunks(n));
+  gram_kernel<<<grid, 256, 0, s>>>(a, p, bm, b, n, kGramRowsPerCta, gpart);
+  HIA_LAUNCH_CHECK();
+  gram_reduce_kernel<<<(p * b + 255) / 256, 256, 0, s>>>(gpart, gram_chunks(n), p * b, g);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
+long long carve(unsigned char* base, int n, int b, int steps, EigWs* w);
 
 long long carve(unsigned char* base, int n, int b, int steps, EigWs* w) {
   const long long D = (long long)b * (steps + 1);
@@ -497,6 +523,7 @@ long long carve(unsigned char* base, int n, int b, int steps, EigWs* w) {
   p = take(b * 8); if (w) w->resid2 = (double*)p;
   p = take(D * 4); if (w) w->order = (int*)p;
   p = take(2 * kMaxBlock * 8); if (w) w->check = (double*)p;
+  p = take((long long)gram_chunks(n) * D * b * 8); if (w) w->Gpart = (double*)p;
   p = take(256); if (w) w->flag = (int*)p;
   return off + 256;
 }
@@ -531,11 +558,8 @@ __global__ void rowmajor_to_colmajor_kernel(const double* __restrict__ src, doub
 
 // Orthonormalise Y (n x b) in place by CholQR; returns R in r_out (b x b), fp32 copy in yf.
 int cholqr(double* Y, int n, int b, EigWs& w, double* r_out, float* yf, cudaStream_t s) {
-  const int rows_per_cta = 1024;      // 8192 left <= 32 CTAs for the b x b Gram: 86 us, latency-bound
-  HIA_CUDA(cudaMemsetAsync(w.G2, 0, (size_t)b * b * 8, s));
-  dim3 grid(b, (n + rows_per_cta - 1) / rows_per_cta);
-  gram_kernel<<<grid, 256, 0, s>>>(Y, b, Y, b, n, rows_per_cta, w.G2);
-  HIA_LAUNCH_CHECK();
+  int gst = gram(Y, b, Y, b, n, w.Gpart, w.G2, s);
+  if (gst != HIA_OK) return gst;
   chol_kernel<<<1, 32, 0, s>>>(w.G2, b, r_out, w.Rinv);
   HIA_LAUNCH_CHECK();
   panel_mul_kernel<<<(n + 255) / 256, 256, 0, s>>>(Y, w.Rinv, b, n, yf);
@@ -624,12 +648,9 @@ HIA_API int hia_eig_absorb(int32_t n, int32_t block, int32_t steps, int32_t j, c
   const int p = (j + 1) * b;                         // columns of Q so far
   rowmajor_to_colmajor_kernel<<<(int)(((long long)n * b + 255) / 256), 256, 0, s>>>(y_full, Qn, n, b);
   HIA_LAUNCH_CHECK();
-  const int rows_per_cta = 1024;      // 8192 left <= 32 CTAs for the b x b Gram: 86 us, latency-bound
   for (int pass = 0; pass < 2; ++pass) {             // CGS2 against all previous blocks
-    HIA_CUDA(cudaMemsetAsync(w.G, 0, (size_t)p * b * 8, s));
-    dim3 grid(p, (n + rows_per_cta - 1) / rows_per_cta);
-    gram_kernel<<<grid, 256, 0, s>>>(w.Q, p, Qn, b, n, rows_per_cta, w.G);
-    HIA_LAUNCH_CHECK();
+    st = gram(w.Q, p, Qn, b, n, w.Gpart, w.G, s);
+    if (st != HIA_OK) return st;
     panel_sub_kernel<<<(n + 255) / 256, 256, (size_t)p * b * 8, s>>>(w.Q, p, w.G, b, n, Qn);
     HIA_LAUNCH_CHECK();
     place_block_kernel<<<(p * b + 255) / 256, 256, 0, s>>>(w.G, p, b, w.H, D, 0, j * b, pass);
@@ -699,6 +720,32 @@ HIA_API int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t steps_
   HIA_LAUNCH_CHECK();
   HIA_CUDA(cudaMemcpyAsync(eigvecs, w.Vf, (size_t)n * k * 4, cudaMemcpyDeviceToDevice, s));
   if (k < b) HIA_CUDA(cudaMemsetAsync(w.Vf + (long long)k * n, 0, (size_t)(b - k) * n * 4, s));
+  return HIA_OK;
+}
+
+// ---- row-sharded callers: install the Ritz vectors chosen by ONE rank (broadcast by the caller) as
+// the current panel [U, 0] and as U for the residual. Every rank decomposes its own replicated copy
+// of the projected matrix; with clustered Ritz values the order (or the rotation inside a cluster)
+// can differ between ranks by rounding alone, and panels that differ across ranks turn the
+// all-gathered product into garbage.
+__global__ void set_ritz_kernel(const float* __restrict__ src, long long count, double* __restrict__ u,
+                                float* __restrict__ vf) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) { const float v = src[i]; u[i] = (double)v; vf[i] = v; }
+}
+HIA_API int hia_eig_set_ritz(int32_t n, int32_t block, int32_t steps, int32_t k, const float* eigvecs,
+                             void* workspace, void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  int st = check_shape(n, block, steps);
+  if (st != HIA_OK) return st;
+  if (!eigvecs || !workspace || k <= 0 || k > block) return HIA_ERR_BAD_ARG;
+  EigWs w;
+  carve(static_cast<unsigned char*>(workspace), n, block, steps, &w);
+  const long long count = (long long)n * k;
+  set_ritz_kernel<<<(int)((count + 255) / 256), 256, 0, s>>>(eigvecs, count, w.U, w.Vf);
+  HIA_LAUNCH_CHECK();
+  if (k < block) HIA_CUDA(cudaMemsetAsync(w.Vf + (long long)k * n, 0, (size_t)(block - k) * n * 4, s));
   return HIA_OK;
 }
 

@@ -147,6 +147,15 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, angle_tol=1e-3, m
                     break
         _lib.check(lib.hia_eig_ritz(n, block, steps, used, reuse, k, eigvals.data_ptr(), eigvecs.data_ptr(),
                                     gaps.data_ptr(), ws.data_ptr(), s()), "hia_eig_ritz")
+        if world > 1:
+            # one rank's Ritz pairs for everybody: with clustered Ritz values the replicated Jacobi
+            # solves can order (or rotate) them differently by rounding alone, and a panel that
+            # differs across ranks turns the all-gathered product C [U, 0] into garbage
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            for t in (eigvals, eigvecs, gaps):
+                dist.broadcast(t, src=src, group=group)
+            _lib.check(lib.hia_eig_set_ritz(n, block, steps, k, eigvecs.data_ptr(), ws.data_ptr(), s()),
+                       "hia_eig_set_ritz")
         matvec()
         _lib.check(lib.hia_eig_resid(n, block, steps, k, y_full.data_ptr(), eigvals.data_ptr(),
                                      resid.data_ptr(), ws.data_ptr(), s()), "hia_eig_resid")

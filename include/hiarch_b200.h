@@ -357,6 +357,11 @@ int hia_eig_check(int32_t n, int32_t block, int32_t steps, int32_t steps_done, i
                   void* stream);
 int hia_eig_ritz(int32_t n, int32_t block, int32_t steps, int32_t steps_used, int32_t reuse_check,
                  int32_t k, double* eigvals, float* eigvecs, double* gaps, void* workspace, void* stream);
+/* row-sharded callers: after hia_eig_ritz, broadcast eigvals / eigvecs / gaps from one rank and
+ * install them with hia_eig_set_ritz, so that the panel of the residual pass (and the restart
+ * vectors) are identical on every rank even when clustered Ritz values order differently. */
+int hia_eig_set_ritz(int32_t n, int32_t block, int32_t steps, int32_t k, const float* eigvecs,
+                     void* workspace, void* stream);
 int hia_eig_resid(int32_t n, int32_t block, int32_t steps, int32_t k, const double* y_full,
                   const double* eigvals, double* resid, void* workspace, void* stream);
 

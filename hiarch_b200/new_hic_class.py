@@ -478,11 +478,11 @@ class SpsHiCMtx(HiCMtx):
         if out_triu:
             self.to_triu(inplace=True)
         m = self.matrix.tocoo()
-        arr = np.vstack([m.row, m.col, m.data]).T
-        if out_int:
-            np.savetxt(out_file, arr, fmt="%d\t%d\t%d")
+        if out_int or fmt is None:
+            from .mtx_io import write_mtx
+            write_mtx(out_file, m.row, m.col, m.data, out_int=out_int)      # native writer, byte-identical
         else:
-            np.savetxt(out_file, arr, fmt="%d\t%d\t%.2f" if fmt is None else fmt)
+            np.savetxt(out_file, np.vstack([m.row, m.col, m.data]).T, fmt=fmt)
         if out_window:
             self.row_window.to_output(change_suffix(out_file, '.window.bed'))
         print("Window file and sparse matrix file have been outputted.")
@@ -501,8 +501,9 @@ def concat_mtxes(mtxes, row_window=None, col_window=None, **other_mtx_kwargs):
 def read_sps_file(sps_file, row_window_file=None, col_window_file=None,
                   mtx_type=None, intra=None, has_neg=None):
     """:2576-2602: tab separated (row, col, value) -> SpsHiCMtx."""
-    df = pd.read_table(sps_file, names=['row', 'col', 'value'])
-    df.dropna(inplace=True)
+    from .mtx_io import read_mtx
+    r_, c_, v_ = read_mtx(sps_file)               # native parser: pd.read_table(...) + dropna
+    df = {'row': r_, 'col': c_, 'value': v_}
     if row_window_file is None and col_window_file is None:
         row_window, col_window = None, None
         shape = (int(np.max(df['row'])) + 1, int(np.max(df['col'])) + 1)
@@ -515,8 +516,7 @@ def read_sps_file(sps_file, row_window_file=None, col_window_file=None,
     else:
         row_window, col_window = GenomeIndex(row_window_file), GenomeIndex(col_window_file)
         shape = (row_window.max_idx + 1, col_window.max_idx + 1)
-    m = sps.coo_matrix((df['value'].values, (df['row'].values.astype(np.int64),
-                                             df['col'].values.astype(np.int64))), shape=shape)
+    m = sps.coo_matrix((df['value'], (df['row'], df['col'])), shape=shape)
     out = SpsHiCMtx(m, mtx_file=sps_file, row_window=row_window, col_window=col_window,
                     mtx_type=mtx_type, intra=intra, has_neg=has_neg)
     out.mtx_name = sps_file.split('/')[-1].split('.sps.mtx')[0]

@@ -230,7 +230,8 @@ def correct_map(sps_file, index_file, output, ab_chrs=None, fig_output=None, do_
     lo, hi = np.minimum(r, c), np.maximum(r, c)                   # to_all -> permute -> to_triu
     order = np.lexsort((hi, lo))
     arr = np.vstack([lo[order], hi[order], v[order]]).T
-    np.savetxt(f'{output}.clean_de_ode.mtx', arr, fmt="%d\t%d\t%.2f")
+    from .mtx_io import write_mtx
+    write_mtx(f'{output}.clean_de_ode.mtx', arr[:, 0], arr[:, 1], arr[:, 2])
     new_index.to_output(f'{output}.clean_window.bed')
     import scipy.sparse as sps
     n = len(old_index)

@@ -365,6 +365,29 @@ int hia_eig_set_ritz(int32_t n, int32_t block, int32_t steps, int32_t k, const f
 int hia_eig_resid(int32_t n, int32_t block, int32_t steps, int32_t k, const double* y_full,
                   const double* eigvals, double* resid, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------ */
+/* f2  the text wire format between the pipeline's processes (HOST functions, HOST memory) */
+/* replaces pd.read_table(sps_file, names=['row','col','value']) + dropna (read_sps_file,  */
+/*          new_hic_class.py:2580-2581) and np.savetxt(fmt="%d\t%d\t%.2f")                  */
+/*          (SpsHiCMtx.to_output, new_hic_class.py:2290-2297)                              */
+/* ------------------------------------------------------------------------------------ */
+/* Exact statistics: entries the file holds after blank-line skipping and dropna (>= 0), or a negative
+ * hia_status (cannot open, or a field that is neither a number nor a missing-value marker).
+ * max_row / max_col / has_neg are optional outputs. threads <= 0: all hardware threads. */
+int64_t hia_mtx_scan(const char* path, int32_t threads, int64_t* max_row, int64_t* max_col,
+                     int32_t* has_neg);
+/* Upper bound on the entries: the number of lines (no parsing). */
+int64_t hia_mtx_count_lines(const char* path, int32_t threads);
+/* Parse (one pass) into caller-owned host arrays of `capacity` entries (>= the entries of the file:
+ * hia_mtx_count_lines or hia_mtx_scan), file order kept; *n_out = entries written. Any output
+ * pointer may be NULL; rows32 / cols32 / vals32 are the int32 / fp32 forms the device kernels take
+ * (point them at pinned memory to upload without another pass). */
+int hia_mtx_parse(const char* path, int32_t threads, int64_t capacity, int64_t* rows, int64_t* cols,
+                  double* vals, int32_t* rows32, int32_t* cols32, float* vals32, int64_t* n_out);
+/* value_format 0: "%d\t%d\t%.2f" (correctly rounded like CPython / glibc); 1: "%d\t%d\t%d". */
+int hia_mtx_write(const char* path, int64_t n, const int64_t* rows, const int64_t* cols, const double* vals,
+                  int value_format, int32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,129 @@
+"""CPU: f2 -- the native .mtx reader / writer against pandas.read_table(+dropna) and numpy.savetxt,
+i.e. against exactly what the reference calls (publish/new_hic_class.py:2580-2581, :2290-2297)."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from hiarch_b200 import mtx_io
+
+
+def _pandas_read(path):
+    df = pd.read_table(path, names=['row', 'col', 'value'])
+    df.dropna(inplace=True)
+    return df['row'].values.astype(np.int64), df['col'].values.astype(np.int64), df['value'].values.astype(np.float64)
+
+
+def _same_as_pandas(path):
+    r, c, v = mtx_io.read_mtx(path)
+    pr, pc, pv = _pandas_read(path)
+    assert np.array_equal(r, pr) and np.array_equal(c, pc)
+    assert np.array_equal(v, pv)                      # bit for bit, not allclose
+    return r, c, v
+
+
+def test_reader_matches_pandas_on_pipeline_files(tmp_path):
+    rng = np.random.default_rng(0)
+    n = 300_000                                        # several thread slices
+    rows = rng.integers(0, 30000, n)
+    cols = rng.integers(0, 30000, n)
+    vals = np.concatenate([rng.gamma(2.0, 30.0, n // 2), rng.normal(0, 3, n - n // 2)])
+    path = str(tmp_path / "a.mtx")
+    np.savetxt(path, np.vstack([rows, cols, vals]).T, fmt="%d\t%d\t%.2f")
+    r, c, v = _same_as_pandas(path)
+    assert len(r) == n
+    # integer-valued third column (out_int files), and a file without a trailing newline
+    path2 = str(tmp_path / "b.mtx")
+    np.savetxt(path2, np.vstack([rows[:1000], cols[:1000], np.floor(vals[:1000])]).T, fmt="%d\t%d\t%d")
+    with open(path2, "rb+") as fh:
+        fh.seek(-1, os.SEEK_END)
+        fh.truncate()
+    _same_as_pandas(path2)
+
+
+def test_reader_edge_cases_like_pandas(tmp_path):
+    path = str(tmp_path / "edge.mtx")
+    with open(path, "w", newline="") as fh:
+        fh.write("0\t1\t2.50\n"
+                 "\n"                                   # blank line: skipped
+                 "3\t4\t\n"                             # missing value -> NaN -> dropna
+                 "5\t6\n"                               # two fields -> NaN -> dropna
+                 "7\t8\tnan\n"                          # explicit NaN -> dropna
+                 "9\t10\t-0.00\n"
+                 "11\t12\t1e-05\n"                      # exponent
+                 "13\t14\t123456789.125\r\n"            # CRLF
+                 "15\t16\t0.1\n"
+                 "17\t18\t179769313486231570000000000000000000000.0\n"
+                 "19\t20\t-1234567.89\n"
+                 "21\t22\t.5\n"
+                 "23\t24\t5.\n"
+                 "25\t26\t+3.25\n"
+                 "27\t28\t0.300000000000004\n"           # 15 significant digits: still exact in both
+                 "29\t30\t1.7976931348623157e308\n"
+                 "31\t32\t4.9e-324")                    # no trailing newline
+    r, c, v = _same_as_pandas(path)
+    assert list(r) == [0, 9, 11, 13, 15, 17, 19, 21, 23, 25, 27, 29, 31]
+    assert np.signbit(v[1]) and v[1] == 0.0
+    # a field that is not a number is an error, not a silent NaN
+    bad = str(tmp_path / "bad.mtx")
+    open(bad, "w").write("0\t1\t2.5\n0\tx\t1.0\n")
+    with pytest.raises(Exception):
+        mtx_io.read_mtx(bad)
+    with pytest.raises(Exception):
+        mtx_io.read_mtx(str(tmp_path / "missing.mtx"))
+    # literals with more than 15 significant digits: pandas' default parser (xstrtod) is NOT correctly
+    # rounded there (0.30000000000000004 -> 0.3); ours is (== Python float()); never more than 1 ulp apart.
+    # The pipeline's own files are "%.2f": far inside the range where both are exact.
+    lits = ["0.30000000000000004", "123456789.123456789", "3.141592653589793238", "2.2250738585072014e-308"]
+    longp = str(tmp_path / "long.mtx")
+    open(longp, "w").write("".join(f"{i}\t{i}\t{l}\n" for i, l in enumerate(lits)))
+    _, _, v = mtx_io.read_mtx(longp)
+    pv = _pandas_read(longp)[2]
+    assert [float(x) for x in v] == [float(l) for l in lits]
+    assert np.all(np.abs(v - pv) <= np.spacing(np.abs(v)))
+    empty = str(tmp_path / "empty.mtx")
+    open(empty, "w").close()
+    r, c, v = mtx_io.read_mtx(empty)
+    assert len(r) == 0
+
+
+def test_writer_is_byte_identical_to_savetxt(tmp_path):
+    rng = np.random.default_rng(1)
+    n = 400_000
+    rows = rng.integers(0, 123541, n)
+    cols = rng.integers(0, 123541, n)
+    vals = np.concatenate([
+        rng.gamma(2.0, 30.0, n // 4), rng.normal(0, 3, n // 4),
+        rng.integers(-100000, 100000, n // 4) / 8.0,            # exact binary ties at the 3rd decimal: x.xx5
+        rng.integers(-10**7, 10**7, n - 3 * (n // 4)) / 1000.0])  # decimal .xx5 inputs (not ties in binary)
+    special = np.array([0.0, -0.0, -0.001, 0.005, 0.015, 0.025, 0.125, 0.375, 2.675, 1e15, -1e15, 1e22,
+                        123456789012.345, 0.994999999999, 0.995, 0.9950000000000001, 5e-324, 99999999999.995,
+                        1e11, 1e11 - 0.005, np.inf, -np.inf, np.nan])
+    vals = np.concatenate([vals, special])
+    rows = np.concatenate([rows, np.arange(len(special))])
+    cols = np.concatenate([cols, np.arange(len(special))])
+    ours, ref = str(tmp_path / "ours.mtx"), str(tmp_path / "ref.mtx")
+    mtx_io.write_mtx(ours, rows, cols, vals)
+    np.savetxt(ref, np.vstack([rows, cols, vals]).T, fmt="%d\t%d\t%.2f")
+    assert open(ours, "rb").read() == open(ref, "rb").read()
+    # out_int: '%d' % float truncates toward zero
+    fin = np.isfinite(vals)
+    mtx_io.write_mtx(ours, rows[fin], cols[fin], vals[fin], out_int=True)
+    np.savetxt(ref, np.vstack([rows[fin], cols[fin], vals[fin]]).T, fmt="%d\t%d\t%d")
+    assert open(ours, "rb").read() == open(ref, "rb").read()
+
+
+def test_write_then_read_round_trip_and_pinned32(tmp_path):
+    rng = np.random.default_rng(2)
+    n = 100_000
+    rows, cols = rng.integers(0, 5000, n), rng.integers(0, 5000, n)
+    vals = np.round(rng.gamma(2.0, 30.0, n), 2)
+    path = str(tmp_path / "rt.mtx")
+    mtx_io.write_mtx(path, rows, cols, vals)
+    r, c, v, (r32, c32, v32) = mtx_io.read_mtx(path, pinned32=True)
+    assert np.array_equal(r, rows) and np.array_equal(c, cols) and np.array_equal(v, vals)
+    import torch
+    assert r32.is_pinned() == torch.cuda.is_available()
+    assert np.array_equal(r32.numpy(), rows.astype(np.int32)) and np.array_equal(c32.numpy(), cols.astype(np.int32))
+    assert np.array_equal(v32.numpy(), vals.astype(np.float32))

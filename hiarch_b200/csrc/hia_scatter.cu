@@ -208,9 +208,9 @@ fill_rows_sorted_kernel(const int* __restrict__ cols, const float* __restrict__ 
                         long long ld, int mtx_type, float* __restrict__ out) {
   extern __shared__ float s_row[];
   if (*flag) return;
-  const int r = blockIdx.y;
+  const int r = blockIdx.x;                                // rows on x: gridDim.y stops at 65 535
   const int c_lo = (mtx_type == HIA_MTX_TRIU) ? r : 0;     // a 'triu' row starts on the diagonal
-  const int seg_lo = c_lo + blockIdx.x * kSegCols;
+  const int seg_lo = c_lo + blockIdx.y * kSegCols;
   if (seg_lo >= n) return;
   const int seg_n = min(kSegCols, n - seg_lo);
   const long long e0 = row_ptr[r], e1 = row_ptr[r + 1];    // in flight while the buffer is zeroed
@@ -489,7 +489,7 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
     HIA_LAUNCH_CHECK();
     HIA_CUDA(cudaFuncSetAttribute(fill_rows_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kSegCols * (int)sizeof(float)));
-    dim3 grid_f((n + kSegCols - 1) / kSegCols, n);
+    dim3 grid_f(n, (n + kSegCols - 1) / kSegCols);
     fill_rows_sorted_kernel<<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(cols, vals, row_ptr, flag, n,
                                                                                         ld, mtx_type, out);
     HIA_LAUNCH_CHECK();

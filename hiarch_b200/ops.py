@@ -4,7 +4,6 @@ Every function here launches hand-written sm_100a kernels through libhiarch_b200
 current torch stream; torch only owns the memory. No op has a CPU or torch fallback.
 """
 import ctypes
-import os
 
 import numpy as np
 import torch
@@ -188,8 +187,6 @@ def log_map(x, out=None):
 
 
 # ------------------------------------------------------------------------------- a8 similarity
-_ws_cache = {}
-
 
 def similarity(x, flavour=SIM_COSINE_DISTANCE, precision=None, band=None, k_chunk=0,
                out=None, workspace=None):
@@ -253,9 +250,8 @@ def topk_eig(c, k=3, block=8, steps=None, tol=1e-6, angle_tol=1e-3, max_restarts
     init, n_init, info = None, 0, []
     for it in range(max_restarts):
         # the in-cycle estimates use half the tolerances: the final, true residual must pass too
-        early = 1.0 if (it == 0 or os.environ.get("HIA_EIG_EARLY_RESTARTS", "1") != "0") else 0.0
         st = lib.hia_topk_eig(_ptr(c), n, c.stride(0), k, block, steps, seed + it, _ptr(init), n_init,
-                              early * 0.5 * tol, early * 0.5 * angle_tol, _ptr(eigvals), _ptr(eigvecs), stats.data_ptr(),
+                              0.5 * tol, 0.5 * angle_tol, _ptr(eigvals), _ptr(eigvecs), stats.data_ptr(),
                               stats.data_ptr() + 8 * k, ctypes.addressof(used), _ptr(ws), ws.numel(), _stream())
         _lib.check(st, "hia_topk_eig")
         sg = stats.cpu().numpy()

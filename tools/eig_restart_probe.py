@@ -36,13 +36,7 @@ def main():
     res = {}
     for name, kw in (("default", {}),
                      ("no_early", dict(angle_tol=0.0, tol=1e-6)),
-                     ("early_first_cycle_only", dict(_first_only=True)),
                      ("steps16", dict(steps=16))):
-        first_only = kw.pop("_first_only", False)
-        if first_only:
-            os.environ["HIA_EIG_EARLY_RESTARTS"] = "0"
-        else:
-            os.environ.pop("HIA_EIG_EARLY_RESTARTS", None)
         t1 = time.time()
         w, v, info = ops.topk_eig(sim, k=3, return_info=True, **kw)
         torch.cuda.synchronize()

@@ -80,6 +80,11 @@ def cpu_step(dense, seps, res):
     return O.topk_eig(c, 3)
 
 
+def workload_name(args, n):
+    return (f"genome-wide human {args.res // 1000} kb ({n} bins, {float(n) * n:.3g} cells) "
+            "scatter -> O/E+log -> Pearson -> top-3 eigvec, one sample per GPU")
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -95,6 +100,8 @@ def run_reference(args):
         return
     dense, seps, chroms = cpu_sample(args)
     n = dense.shape[0]
+    from hiarch_b200 import synth
+    n_full = sum(nb for _, nb in synth.hg38_bins(args.res)[: args.chroms])
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_step(dense, seps, args.res)
     t0 = time.perf_counter()
@@ -110,8 +117,9 @@ def run_reference(args):
         "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "impl": "reference",
-        "config": {"workload": "genome-wide human 100 kb O/E+log -> Pearson -> top-3 eigvec "
-                               "(bounded CPU sample of the same workload)", "bins": n, "res": args.res},
+        "config": {"workload": workload_name(args, n_full),
+                   "bins": n_full, "chromosomes": args.chroms,
+                   "sample": f"each step = a bounded sample of that workload: {n} bins ({'+'.join(chroms)})"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": blas_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -319,8 +327,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": f"{args.precision} (fp32 storage, fp64 reductions)",
         "data": "synthetic",
-        "config": {"workload": f"genome-wide human {args.res // 1000} kb ({n} bins, {cells:.3g} cells) "
-                               "scatter -> O/E+log -> Pearson -> top-3 eigvec, one sample per GPU",
+        "config": {"workload": workload_name(args, n),
                    "bins": n, "nnz_upper": nnz, "chromosomes": len(lens),
                    "l2": "inputs (>=0.9 GB) exceed the 126 MB L2; no explicit flush",
                    "sharding": "samples by rank, no collective"},

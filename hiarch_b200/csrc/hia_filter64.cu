@@ -17,17 +17,10 @@
 // re-quantised as nearbyint(x * 10^decimals) / 10^decimals in fp64, i.e. the double a "%.2f"
 // text field parses to (the pipeline hands maps over as %.2f text, new_hic_class.py:2298).
 #include "hia_common.cuh"
+#include "hia_box64_core.cuh"
 
 namespace hia {
 namespace {
-
-__device__ __forceinline__ int reflect_idx64(int i, int n) {
-  if (n == 1) return 0;
-  const int p = 2 * n;
-  i %= p;
-  if (i < 0) i += p;
-  return i < n ? i : p - 1 - i;
-}
 
 __device__ __forceinline__ unsigned long long double_to_ordered(double d) {
   const unsigned long long b = (unsigned long long)__double_as_longlong(d);
@@ -48,41 +41,35 @@ __global__ void load_f64_kernel(const float* __restrict__ x, long long ld, int r
   a[i] = v;
 }
 
-// uniform_filter1d along axis 0: thread per column, the whole column sequentially (scipy order)
-__global__ void box64_axis0_kernel(const double* __restrict__ in, double* __restrict__ out, int rows,
-                                   int cols, int size) {
+// uniform_filter1d along the SLOW axis of a [len][lines] array (element (l, c) at in[l * lines + c]):
+// thread per line c, the whole line sequentially in scipy's order (tmp = sum of the first window in
+// order; tmp += new - old; out = tmp / size), coalesced across the threads of a warp. The
+// arithmetic chain is sequential by construction (every partial sum is rounded), so the only
+// parallelism is across lines; memory-level parallelism comes from the interior loop, where no
+// index reflects and 8 steps of loads (independent of the chain) are issued before they are consumed.
+__global__ void __launch_bounds__(64)
+box64_lines_kernel(const double* __restrict__ in, double* __restrict__ out, int len, int lines, int size) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  const int s1 = size / 2;
-  double tmp = 0.0;
-  for (int ll = 0; ll < size; ++ll) tmp += in[(long long)reflect_idx64(ll - s1, rows) * cols + c];
-  const double fs = (double)size;
-  out[c] = tmp / fs;
-  for (int ll = 1; ll < rows; ++ll) {
-    const double nw = in[(long long)reflect_idx64(ll + size - 1 - s1, rows) * cols + c];
-    const double od = in[(long long)reflect_idx64(ll - 1 - s1, rows) * cols + c];
-    tmp += nw - od;
-    out[(long long)ll * cols + c] = tmp / fs;
-  }
+  if (c < lines) box64_line(in, out, len, lines, c, size);
 }
 
-// uniform_filter1d along axis 1: thread per row, the whole row sequentially
-__global__ void box64_axis1_kernel(const double* __restrict__ in, double* __restrict__ out, int rows,
-                                   int cols, int size) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  const double* line = in + (long long)r * cols;
-  double* oline = out + (long long)r * cols;
-  const int s1 = size / 2;
-  double tmp = 0.0;
-  for (int ll = 0; ll < size; ++ll) tmp += line[reflect_idx64(ll - s1, cols)];
-  const double fs = (double)size;
-  oline[0] = tmp / fs;
-  for (int ll = 1; ll < cols; ++ll) {
-    const double nw = line[reflect_idx64(ll + size - 1 - s1, cols)];
-    const double od = line[reflect_idx64(ll - 1 - s1, cols)];
-    tmp += nw - od;
-    oline[ll] = tmp / fs;
+// out[c][r] = in[r][c] (32 x 32 tiles through shared memory, both sides coalesced): the fast-axis
+// pass of the box filter runs as a slow-axis pass on the transposed array.
+__global__ void __launch_bounds__(256)
+transpose64_kernel(const double* __restrict__ in, double* __restrict__ out, int rows, int cols) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    if (r < rows && c < cols) tile[i][tx] = in[(long long)r * cols + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) out[(long long)c * rows + r] = tile[tx][i];
   }
 }
 
@@ -214,6 +201,31 @@ __global__ void zscore64_kernel(const double* __restrict__ a, int rows, int cols
   out[(long long)r * ld_out + c] = (float)v;
 }
 
+// the same from the TRANSPOSED fp64 array at[c][r] (what the transposed fast-axis pass leaves)
+__global__ void __launch_bounds__(256)
+zscore64_t_kernel(const double* __restrict__ at, int rows, int cols, const Sel64* st,
+                  float* __restrict__ out, long long ld_out, int normalise) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) tile[i][tx] = at[(long long)c * rows + r];
+  }
+  __syncthreads();
+  const double mean = normalise ? st->mean_std[0] : 0.0, sd = normalise ? st->mean_std[1] : 1.0;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    if (r < rows && c < cols) {
+      double v = tile[tx][i];
+      if (normalise) v = (v - mean) / sd;
+      out[(long long)r * ld_out + c] = (float)v;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace hia
 
@@ -240,31 +252,40 @@ HIA_API int hia_used_filter_f64(const float* x, int32_t rows, int32_t cols, int6
   if (decimals >= 0) { scale = 1.0; for (int i = 0; i < decimals; ++i) scale *= 10.0; }
   load_f64_kernel<<<blocks, 256, 0, s>>>(x, ld_in, rows, cols, scale, A);
   HIA_LAUNCH_CHECK();
-  if (size > 1) {                                        // scipy: size 1 (and 0) leave the block as is
-    box64_axis0_kernel<<<(cols + 127) / 128, 128, 0, s>>>(A, B, rows, cols, size);
+  const bool filtered = size > 1;                        // scipy: size 1 (and 0) leave the block as is
+  if (filtered) {
+    // axis 0 on A -> B; axis 1 = the same slow-axis pass on B^T: B -> A (transpose) -> B. The
+    // filtered block ends up TRANSPOSED in B; the order statistics / moments below do not care.
+    box64_lines_kernel<<<(cols + 63) / 64, 64, 0, s>>>(A, B, rows, cols, size);
     HIA_LAUNCH_CHECK();
-    box64_axis1_kernel<<<(rows + 127) / 128, 128, 0, s>>>(B, A, rows, cols, size);
+    transpose64_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, s>>>(B, A, rows, cols);
+    HIA_LAUNCH_CHECK();
+    box64_lines_kernel<<<(rows + 63) / 64, 64, 0, s>>>(A, B, cols, rows, size);
     HIA_LAUNCH_CHECK();
   }
+  const double* F = filtered ? B : A;
   if (normalise) {
     const double q_hi = mid_vmax_per / 100.0, q_lo = (100.0 - mid_vmax_per) / 100.0;
     sel64_init_kernel<<<1, 256, 0, s>>>(st, n, q_hi, q_lo);
     HIA_LAUNCH_CHECK();
     const int grid = (int)std::min<long long>(blocks, (long long)kNumSMs * 8);
     for (int pass = 0; pass < 8; ++pass) {
-      sel64_pass_kernel<<<grid, 256, 0, s>>>(A, n, pass, st);
+      sel64_pass_kernel<<<grid, 256, 0, s>>>(F, n, pass, st);
       HIA_LAUNCH_CHECK();
       sel64_scan_kernel<<<1, 256, 0, s>>>(st);
       HIA_LAUNCH_CHECK();
     }
     sel64_finish_kernel<<<1, 32, 0, s>>>(st);
     HIA_LAUNCH_CHECK();
-    moments64_kernel<<<grid, 256, 0, s>>>(A, n, st);
+    moments64_kernel<<<grid, 256, 0, s>>>(F, n, st);
     HIA_LAUNCH_CHECK();
     moments64_finish_kernel<<<1, 32, 0, s>>>(st);
     HIA_LAUNCH_CHECK();
   }
-  zscore64_kernel<<<blocks, 256, 0, s>>>(A, rows, cols, st, out, ld_out, normalise);
+  if (filtered)
+    zscore64_t_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, s>>>(F, rows, cols, st, out, ld_out, normalise);
+  else
+    zscore64_kernel<<<blocks, 256, 0, s>>>(F, rows, cols, st, out, ld_out, normalise);
   HIA_LAUNCH_CHECK();
   return HIA_OK;
 }

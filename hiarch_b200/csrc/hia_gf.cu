@@ -11,6 +11,7 @@
 //      preprocess.py:8-48) and the template scores of to_confor
 //      (publish/confor/src/S5_sim_to_pat/to_confor.py:35-47).
 #include "hia_common.cuh"
+#include "hia_intra_x_core.cuh"
 
 namespace hia {
 namespace {
@@ -263,6 +264,105 @@ intra_x_kernel(const float* __restrict__ m, int n, long long ld, int k_len, doub
   }
 }
 
+
+// ------------------------------------------------------------------ a13 intra-x, prefix-sum path
+// The same response in O(n^2): along a row of M the kernel of every centre is a tent (two linear
+// pieces) in the column index, both for the lower cells (q <= r) and for the mirrored upper cells
+// (q > r) -- hia_intra_x_core.cuh. Rows are processed in panels of R rows:
+//   ix_prefix_kernel : one CTA per row, block scan of (v, q v) in fp64 -> P[row][0..n] (16 B / cell)
+//   ix_eval_kernel   : thread per centre x sub-chunk of 32 rows, <= 8 prefix look-ups per (row, centre),
+//                      register accumulators -> partial[sub][c]
+//   ix_accum_kernel  : fixed-order sum of the partials into acc[c]; the last panel divides.
+// Deterministic (no atomics). The panel of prefix sums (<= 96 MB) stays L2-resident between the
+// scan and the look-ups.
+__global__ void __launch_bounds__(256)
+ix_prefix_kernel(const float* __restrict__ m, int n, long long ld, int r0, IxPrefix* __restrict__ P) {
+  __shared__ float s_in[2][1024];
+  __shared__ double s_w[2][8][2];
+  const float* row = m + (long long)(r0 + blockIdx.x) * ld;
+  IxPrefix* out = P + (size_t)blockIdx.x * (size_t)(n + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { IxPrefix z; z.s0 = 0.0; z.s1 = 0.0; out[0] = z; }
+  double c0 = 0.0, c1 = 0.0;                             // carry of the previous tiles (same in every thread)
+  int buf = 0;
+  for (int tile = 0; tile < n; tile += 1024, buf ^= 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = tile + j * 256 + tid;                // coalesced scalar loads: block views need no alignment
+      s_in[buf][j * 256 + tid] = q < n ? row[q] : 0.f;
+    }
+    __syncthreads();
+    const int q0 = tile + 4 * tid;
+    double a0[4], a1[4], t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double v = (double)s_in[buf][4 * tid + j];
+      t0 += v; t1 += (double)(q0 + j) * v;
+      a0[j] = t0; a1[j] = t1;
+    }
+    double w0 = t0, w1 = t1;                             // warp inclusive scan of the thread totals
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double y0 = __shfl_up_sync(0xffffffffu, w0, o), y1 = __shfl_up_sync(0xffffffffu, w1, o);
+      if (lane >= o) { w0 += y0; w1 += y1; }
+    }
+    if (lane == 31) { s_w[buf][warp][0] = w0; s_w[buf][warp][1] = w1; }
+    double e0 = __shfl_up_sync(0xffffffffu, w0, 1), e1 = __shfl_up_sync(0xffffffffu, w1, 1);
+    if (lane == 0) { e0 = 0.0; e1 = 0.0; }               // exclusive within the warp
+    __syncthreads();
+    double b0 = c0, b1 = c1, tot0 = 0.0, tot1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double x0 = s_w[buf][k][0], x1 = s_w[buf][k][1];
+      if (k < warp) { b0 += x0; b1 += x1; }
+      tot0 += x0; tot1 += x1;
+    }
+    b0 += e0; b1 += e1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q0 + j < n) { IxPrefix p; p.s0 = b0 + a0[j]; p.s1 = b1 + a1[j]; out[q0 + j + 1] = p; }
+    c0 += tot0; c1 += tot1;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+ix_eval_kernel(const IxPrefix* __restrict__ P, int n, int k_len, int r0, int rows, int rows_per_sub,
+               IxPrefix* __restrict__ partial) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= n) return;
+  const IxCentre cc = ix_centre(c, n, k_len);
+  const int lo = blockIdx.y * rows_per_sub;
+  const int hi = min(rows, lo + rows_per_sub);
+  double num = 0.0, den = 0.0;
+  for (int i = lo; i < hi; ++i)
+    ix_row_contrib(cc, n, k_len, r0 + i, P + (size_t)i * (size_t)(n + 1), num, den);
+  IxPrefix p; p.s0 = num; p.s1 = den;
+  partial[(size_t)blockIdx.y * n + c] = p;
+}
+
+__global__ void ix_accum_kernel(const IxPrefix* __restrict__ partial, int n, int subs, IxPrefix* __restrict__ acc,
+                                int first, int last, double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double num = 0.0, den = 0.0;
+  if (!first) { const IxPrefix a = acc[c]; num = a.s0; den = a.s1; }
+  for (int k = 0; k < subs; ++k) { const IxPrefix p = partial[(size_t)k * n + c]; num += p.s0; den += p.s1; }
+  IxPrefix a; a.s0 = num; a.s1 = den;
+  acc[c] = a;
+  if (last) out[c] = num / den;
+}
+
+constexpr int kIxRowsPerSub = 32;
+// rows per panel: the prefix panel is kept <= 96 MB (L2-resident on B200), 32 <= R <= 1024, multiple of 32
+inline int ix_panel_rows(int n) {
+  long long r = (96ll << 20) / (16ll * ((long long)n + 1));
+  r = (r / 32) * 32;
+  if (r < 32) r = 32;
+  if (r > 1024) r = 1024;
+  const long long n32 = (((long long)n + 31) / 32) * 32;
+  return (int)(r < n32 ? r : n32);
+}
+
 }  // namespace
 }  // namespace hia
 
@@ -273,6 +373,38 @@ HIA_API int hia_intra_x_response(const float* block, int32_t n, int64_t ld, int3
   if (!block || !out || n <= 0 || ld < n || k_len <= 0) return HIA_ERR_BAD_ARG;
   intra_x_kernel<<<n, 256, 0, s>>>(block, n, ld, k_len, out);
   HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
+HIA_API int64_t hia_intra_x_workspace_bytes(int32_t n) {
+  using namespace hia;
+  if (n <= 0) return 0;
+  const int64_t R = ix_panel_rows(n), subs = (R + kIxRowsPerSub - 1) / kIxRowsPerSub;
+  return 16 * (R * ((int64_t)n + 1) + subs * (int64_t)n + (int64_t)n) + 256;
+}
+
+HIA_API int hia_intra_x_response_prefix(const float* block, int32_t n, int64_t ld, int32_t k_len, double* out,
+                                        void* workspace, int64_t workspace_bytes, void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (!block || !out || !workspace || n <= 0 || ld < n || k_len <= 0) return HIA_ERR_BAD_ARG;
+  if (workspace_bytes < hia_intra_x_workspace_bytes(n)) return HIA_ERR_WORKSPACE;
+  if (!aligned16(workspace)) return HIA_ERR_ALIGN;
+  const int R = ix_panel_rows(n);
+  const int max_subs = (R + kIxRowsPerSub - 1) / kIxRowsPerSub;
+  IxPrefix* P = static_cast<IxPrefix*>(workspace);
+  IxPrefix* partial = P + (size_t)R * (size_t)(n + 1);
+  IxPrefix* acc = partial + (size_t)max_subs * (size_t)n;
+  for (int r0 = 0; r0 < n; r0 += R) {
+    const int rows = n - r0 < R ? n - r0 : R;
+    const int subs = (rows + kIxRowsPerSub - 1) / kIxRowsPerSub;
+    ix_prefix_kernel<<<rows, 256, 0, s>>>(block, n, ld, r0, P);
+    HIA_LAUNCH_CHECK();
+    ix_eval_kernel<<<dim3((n + 127) / 128, subs), 128, 0, s>>>(P, n, k_len, r0, rows, kIxRowsPerSub, partial);
+    HIA_LAUNCH_CHECK();
+    ix_accum_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, n, subs, acc, r0 == 0, r0 + R >= n, out);
+    HIA_LAUNCH_CHECK();
+  }
   return HIA_OK;
 }
 

@@ -4,6 +4,7 @@ Every function here launches hand-written sm_100a kernels through libhiarch_b200
 current torch stream; torch only owns the memory. No op has a CPU or torch fallback.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -600,14 +601,29 @@ def norm_to_zero_mean_block(block, mid_vmax_per=66):
 
 
 # ------------------------------------------------------------------------------- a13 intra-x
-def intra_x_response(block):
-    """get_intra_x (S2_2_find_by_intra_x.py:116-126) of one intra block -> fp64 device [n]."""
+def intra_x_response(block, method=None, workspace=None):
+    """get_intra_x (S2_2_find_by_intra_x.py:116-126) of one intra block -> fp64 device [n].
+
+    method 'prefix' (default; env HIA_INTRA_X overrides): row prefix sums, O(n^2)
+    (`hia_intra_x_response_prefix`); 'direct': every band cell of every centre, O(n^2 k_len)
+    (`hia_intra_x_response`, the on-device cross-check)."""
     lib = _lib.load()
     _need_cuda(block)
     n = block.shape[0]
     assert block.shape == (n, n) and block.dtype == torch.float32 and block.stride(1) == 1
     k_len = max(3, int(n * .05))
     out = torch.empty(n, dtype=torch.float64, device=block.device)
+    method = method or os.environ.get("HIA_INTRA_X", "prefix")
+    if method not in ("prefix", "direct"):
+        raise ValueError(f"intra_x_response: unknown method {method!r}")
+    if method == "prefix":
+        need = lib.hia_intra_x_workspace_bytes(n)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=block.device)
+        st = lib.hia_intra_x_response_prefix(_ptr(block), n, block.stride(0), k_len, _ptr(out),
+                                             _ptr(workspace), workspace.numel(), _stream())
+        _lib.check(st, "hia_intra_x_response_prefix")
+        return out
     st = lib.hia_intra_x_response(_ptr(block), n, block.stride(0), k_len, _ptr(out), _stream())
     _lib.check(st, "hia_intra_x_response")
     return out

@@ -254,6 +254,13 @@ int hia_smooth1d_reflect(const double* in, double* out, int32_t n, const int32_t
 /* line-distance kernel of half-width k_len = max(3, int(.05 n)). out[n] fp64 (device).       */
 int hia_intra_x_response(const float* block, int32_t n, int64_t ld, int32_t k_len, double* out,
                          void* stream);
+/* The same response in O(n^2) instead of O(n^2 k_len): along a row of M every centre's kernel  */
+/* is a tent in the column index, so row prefix sums of (v, column * v) give each (row, centre)  */
+/* term from <= 8 look-ups. Deterministic; fp64 throughout; `block` needs no alignment. The      */
+/* direct kernel above stays as the on-device cross-check.                                       */
+int64_t hia_intra_x_workspace_bytes(int32_t n);
+int hia_intra_x_response_prefix(const float* block, int32_t n, int64_t ld, int32_t k_len, double* out,
+                                void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
 /* a7  box (uniform) and median filters, scipy.ndimage 'reflect' boundary                 */

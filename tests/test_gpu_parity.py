@@ -513,19 +513,39 @@ def test_used_filter_box_only_is_bit_exact_vs_scipy():
 
 
 # --------------------------------------------------------------------------------- a13 intra-x
-def test_intra_x_response(golden):
+@pytest.mark.parametrize("method", ["prefix", "direct"])
+def test_intra_x_response(golden, method):
     from hiarch_b200 import ops
     g = golden("g1chr")
-    got = ops.intra_x_response(_mapdev(g["filt"])).cpu().numpy()
+    got = ops.intra_x_response(_mapdev(g["filt"]), method=method).cpu().numpy()
     ref = g["intra_x"]
     assert np.all(np.abs(got - ref) <= 1e-4 * np.abs(ref) + 1e-7)
     rng = np.random.default_rng(2)
-    for n in (61, 150):
+    for n in (1, 2, 61, 150):
         a = rng.standard_normal((n, n))
-        a = (a + a.T) / 2
-        got = ops.intra_x_response(_mapdev(a)).cpu().numpy()
+        if n != 150:
+            a = (a + a.T) / 2                                    # n = 150: unsymmetric block
+        got = ops.intra_x_response(_mapdev(a), method=method).cpu().numpy()
         ref = O.intra_x(a.astype(np.float32).astype(np.float64))
         assert np.all(np.abs(got - ref) <= 1e-9 + 1e-9 * np.abs(ref))
+
+
+def test_intra_x_prefix_equals_direct_on_a_multi_panel_block_view():
+    """O(n^2) prefix-sum path vs the direct band evaluation: several row panels (n > 1024), a
+    ragged last tile, and an unaligned view into a larger map (odd offset, ld of the parent)."""
+    from hiarch_b200 import ops
+    rng = np.random.default_rng(11)
+    n_par, off, n = 2400, 131, 2113
+    d = np.abs(np.arange(n_par)[:, None] - np.arange(n_par)[None, :])
+    parent = (rng.poisson(50.0 * (d + 1.0) ** -1.0 + 1.0) + rng.random((n_par, n_par))).astype(np.float32)
+    dev = _mapdev(parent)
+    view = dev[off:off + n, off:off + n]
+    a = ops.intra_x_response(view, method="prefix").cpu().numpy()
+    b = ops.intra_x_response(view, method="direct").cpu().numpy()
+    assert np.all(np.isfinite(a))
+    assert np.all(np.abs(a - b) <= 1e-10 * np.abs(b)), (np.abs(a - b) / np.abs(b)).max()
+    a2 = ops.intra_x_response(view, method="prefix").cpu().numpy()
+    assert np.array_equal(a, a2)                                 # deterministic (no atomics)
 
 
 # --------------------------------------------------------------------------------- f1 preprocess

@@ -12,6 +12,7 @@ namespace hia {
 
 void set_last_cuda_error(cudaError_t e);
 void count_launch();          // per-process counter of kernels launched by this library
+int sel_aggregate();          // 1 (default): warp-aggregated histogram adds (match.any); HIA_SEL_AGG=0 -> plain atomics
 
 inline int cuda_ok(cudaError_t e) {
   if (e == cudaSuccess) return HIA_OK;

@@ -1,5 +1,6 @@
 // Library-level entry points: version, status strings, last CUDA error.
 #include "hia_common.cuh"
+#include <stdlib.h>
 
 namespace hia {
 static thread_local char g_last_err[256] = "";
@@ -11,6 +12,11 @@ void set_last_cuda_error(cudaError_t e) {
 }
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+// read on every call (a getenv, next to kernel launches): tools time both settings in one process
+int sel_aggregate() {
+  const char* e = getenv("HIA_SEL_AGG");
+  return !(e && e[0] == '0');
+}
 }  // namespace hia
 
 HIA_API uint64_t hia_launch_count(void) { return __atomic_load_n(&hia::g_launches, __ATOMIC_RELAXED); }

@@ -73,11 +73,19 @@ transpose64_kernel(const double* __restrict__ in, double* __restrict__ out, int 
   }
 }
 
-// ---- exact order statistics on 64-bit keys: 8 passes of 8 bits, up to 4 ranks
+// ---- exact order statistics on 64-bit keys: 8 passes of 8 bits, up to 4 ranks. Ranks whose key
+// prefixes coincide share one histogram ("slot": the two ranks of a percentile nearly always do,
+// and in pass 0 all four), and the shared-memory adds are aggregated per warp by (slot, digit)
+// with match.any: box-filtered maps put almost every key into a handful of leading digits, and
+// un-aggregated same-address atomics serialise.
 struct Sel64 {
-  unsigned long long hist[4][256];
-  unsigned long long prefix[4];
-  unsigned long long rank[4];
+  unsigned long long hist[4][256];     // per slot
+  unsigned long long prefix[4];        // per rank: key bits decided so far (right aligned)
+  unsigned long long rank[4];          // per rank: residual rank inside its prefix
+  unsigned long long slot_prefix[4];
+  int slot_of_rank[4];
+  int n_slots;
+  int pad;
   double gamma[2];
   double pct[2];       // p_hi (66), p_lo (34)
   double sums[6];
@@ -101,46 +109,84 @@ __global__ void sel64_init_kernel(Sel64* st, long long n, double q_hi, double q_
       st->rank[2 * q] = (unsigned long long)lo_i;
       st->rank[2 * q + 1] = (unsigned long long)hi_i;
     }
-    for (int r = 0; r < 4; ++r) st->prefix[r] = 0ull;
+    for (int r = 0; r < 4; ++r) { st->prefix[r] = 0ull; st->slot_of_rank[r] = 0; st->slot_prefix[r] = 0ull; }
+    st->n_slots = 1;
   }
 }
 
 __global__ void __launch_bounds__(256)
-sel64_pass_kernel(const double* __restrict__ a, long long n, int pass, Sel64* st) {
-  __shared__ unsigned int s_hist[4][256];
+sel64_pass_kernel(const double* __restrict__ a, long long n, int pass, Sel64* st, int aggregate) {
+  __shared__ unsigned int s_hist[4 * 256];
   __shared__ unsigned long long s_prefix[4];
-  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0u;
-  if (threadIdx.x < 4) s_prefix[threadIdx.x] = st->prefix[threadIdx.x];
+  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) s_hist[i] = 0u;
+  if (threadIdx.x < 4) s_prefix[threadIdx.x] = st->slot_prefix[threadIdx.x];
+  const int n_slots = st->n_slots;
   __syncthreads();
   const int shift = 56 - 8 * pass;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const unsigned long long key = double_to_ordered(a[i]);
-    const unsigned long long hi = (pass == 0) ? 0ull : (key >> (shift + 8));
-    const unsigned int dig = (unsigned int)((key >> shift) & 0xffull);
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // warp-uniform trip count: every lane reaches the match / vote instructions
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += 4 * stride) {
+    double v[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-      if (hi == s_prefix[r]) atomicAdd(&s_hist[r][dig], 1u);
+    for (int k = 0; k < 4; ++k) {
+      const long long i = base + k * stride + lane;
+      v[k] = i < n ? a[i] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = base + k * stride + lane;
+      unsigned int agg = 0xffffffffu;
+      if (i < n) {
+        const unsigned long long key = double_to_ordered(v[k]);
+        const unsigned long long hi = (pass == 0) ? 0ull : (key >> (shift + 8));
+        const unsigned int dig = (unsigned int)((key >> shift) & 0xffull);
+        for (int sl = 0; sl < n_slots; ++sl)
+          if (hi == s_prefix[sl]) agg = (unsigned int)sl * 256u + dig;    // slot prefixes are distinct
+      }
+      if (!aggregate) {
+        if (agg != 0xffffffffu) atomicAdd(&s_hist[agg], 1u);
+      } else if (__any_sync(0xffffffffu, agg != 0xffffffffu)) {
+        const unsigned int peers = __match_any_sync(0xffffffffu, agg);
+        if (agg != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&s_hist[agg], (unsigned int)__popc(peers));
+      }
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
-    const unsigned int v = (&s_hist[0][0])[i];
-    if (v) atomicAdd(&(&st->hist[0][0])[i], (unsigned long long)v);
+  for (int i = threadIdx.x; i < n_slots * 256; i += blockDim.x) {
+    const unsigned int c = s_hist[i];
+    if (c) atomicAdd(&(&st->hist[0][0])[i], (unsigned long long)c);
   }
 }
 
+// after each pass: every rank finds its digit in its slot's histogram, the prefixes grow by 8 bits,
+// the slot list (distinct prefixes) is rebuilt, the histograms are cleared
 __global__ void sel64_scan_kernel(Sel64* st) {
+  __shared__ unsigned long long s_newprefix[4];
   const int r = threadIdx.x;
   if (r < 4) {
+    const unsigned long long* h = st->hist[st->slot_of_rank[r]];
     unsigned long long cum = 0, target = st->rank[r];
     int bin = 255;
     for (int i = 0; i < 256; ++i) {
-      const unsigned long long c = st->hist[r][i];
+      const unsigned long long c = h[i];
       if (target < cum + c) { bin = i; break; }
       cum += c;
     }
     st->rank[r] = target - cum;
-    st->prefix[r] = (st->prefix[r] << 8) | (unsigned long long)bin;
+    s_newprefix[r] = (st->prefix[r] << 8) | (unsigned long long)bin;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ns = 0;
+    for (int q = 0; q < 4; ++q) {
+      st->prefix[q] = s_newprefix[q];
+      int found = -1;
+      for (int sl = 0; sl < ns; ++sl) if (st->slot_prefix[sl] == s_newprefix[q]) { found = sl; break; }
+      if (found < 0) { st->slot_prefix[ns] = s_newprefix[q]; found = ns++; }
+      st->slot_of_rank[q] = found;
+    }
+    st->n_slots = ns;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
@@ -269,8 +315,9 @@ HIA_API int hia_used_filter_f64(const float* x, int32_t rows, int32_t cols, int6
     sel64_init_kernel<<<1, 256, 0, s>>>(st, n, q_hi, q_lo);
     HIA_LAUNCH_CHECK();
     const int grid = (int)std::min<long long>(blocks, (long long)kNumSMs * 8);
+    const int aggregate = sel_aggregate();
     for (int pass = 0; pass < 8; ++pass) {
-      sel64_pass_kernel<<<grid, 256, 0, s>>>(F, n, pass, st);
+      sel64_pass_kernel<<<grid, 256, 0, s>>>(F, n, pass, st, aggregate);
       HIA_LAUNCH_CHECK();
       sel64_scan_kernel<<<1, 256, 0, s>>>(st);
       HIA_LAUNCH_CHECK();

@@ -49,7 +49,7 @@ __global__ void sel_init_kernel(SelState* st, unsigned long long n) {
 // equal the slot's prefix. Pass 0 has a single slot (empty prefix) and also counts x>0 / x<0.
 template <int PASS>
 __global__ void __launch_bounds__(kSelThreads)
-sel_pass_kernel(const float* __restrict__ x, int rows, int cols, long long ld, SelState* st) {
+sel_pass_kernel(const float* __restrict__ x, int rows, int cols, long long ld, SelState* st, int aggregate) {
   extern __shared__ unsigned int s_hist[];             // [n_slots][kBins]
   __shared__ unsigned int s_prefix[kMaxRanks];
   __shared__ unsigned long long s_pos, s_neg;
@@ -64,23 +64,39 @@ sel_pass_kernel(const float* __restrict__ x, int rows, int cols, long long ld, S
   unsigned int pos = 0, neg = 0;
   const int c4 = (cols + 3) / 4;
   const long long total = (long long)rows * c4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / c4), c0 = (int)(i % c4) * 4;
-    const float* p = x + (long long)r * ld + c0;
-    float v[4];
-    int nv = min(4, cols - c0);
-    if (nv == 4) { const float4 t = ld_stream4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-    else { for (int j = 0; j < 4; ++j) v[j] = (j < nv) ? p[j] : 0.f; }
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count (pass 0 aggregates its adds per warp with match.any: the leading 11
+  // bits of nearly all keys of a map fall into a handful of bins, and same-address shared-memory
+  // atomics serialise)
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < total;
+       base += (long long)gridDim.x * blockDim.x) {
+    const long long i = base + lane;
+    const bool live = i < total;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    int nv = 0;
+    if (live) {
+      const int r = (int)(i / c4), c0 = (int)(i % c4) * 4;
+      const float* p = x + (long long)r * ld + c0;
+      nv = min(4, cols - c0);
+      if (nv == 4) { const float4 t = ld_stream4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+      else { for (int j = 0; j < 4; ++j) v[j] = (j < nv) ? p[j] : 0.f; }
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (j >= nv) break;
       const unsigned int key = float_to_ordered(v[j]);
       if (PASS == 0) {
-        pos += (v[j] > 0.f);
-        neg += (v[j] < 0.f);
-        atomicAdd(&s_hist[key >> shift], 1u);
+        const bool on = j < nv;
+        pos += (on && v[j] > 0.f);
+        neg += (on && v[j] < 0.f);
+        const unsigned int agg = on ? (key >> shift) : 0xffffffffu;
+        if (aggregate) {
+          const unsigned int peers = __match_any_sync(0xffffffffu, agg);
+          if (on && lane == __ffs(peers) - 1) atomicAdd(&s_hist[agg], (unsigned int)__popc(peers));
+        } else if (on) {
+          atomicAdd(&s_hist[agg], 1u);
+        }
       } else {
+        if (j >= nv) continue;
         const unsigned int hi = (hshift >= 32) ? 0u : (key >> hshift);
         const unsigned int dig = (key >> shift) & mask;
         for (int s = 0; s < n_slots; ++s)
@@ -333,17 +349,17 @@ HIA_API int hia_percentiles(const float* x, int32_t rows, int32_t cols, int64_t 
     HIA_CUDA(cudaFuncSetAttribute(sel_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_full));
     attr_done = true;
   }
-  sel_pass_kernel<0><<<grid, kSelThreads, kBins * 4, s>>>(x, rows, cols, ld, st);
+  sel_pass_kernel<0><<<grid, kSelThreads, kBins * 4, s>>>(x, rows, cols, ld, st, sel_aggregate());
   HIA_LAUNCH_CHECK();
   sel_ranks_kernel<<<1, 32, 0, s>>>(st, modes, quantiles, nq);
   HIA_LAUNCH_CHECK();
   sel_scan_kernel<<<1, kMaxRanks * 32, 0, s>>>(st, 0);
   HIA_LAUNCH_CHECK();
-  sel_pass_kernel<1><<<grid, kSelThreads, sh_full, s>>>(x, rows, cols, ld, st);
+  sel_pass_kernel<1><<<grid, kSelThreads, sh_full, s>>>(x, rows, cols, ld, st, 0);
   HIA_LAUNCH_CHECK();
   sel_scan_kernel<<<1, kMaxRanks * 32, 0, s>>>(st, 1);
   HIA_LAUNCH_CHECK();
-  sel_pass_kernel<2><<<grid, kSelThreads, sh_full, s>>>(x, rows, cols, ld, st);
+  sel_pass_kernel<2><<<grid, kSelThreads, sh_full, s>>>(x, rows, cols, ld, st, 0);
   HIA_LAUNCH_CHECK();
   sel_scan_kernel<<<1, kMaxRanks * 32, 0, s>>>(st, 2);
   HIA_LAUNCH_CHECK();

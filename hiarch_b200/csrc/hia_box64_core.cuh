@@ -20,11 +20,15 @@ HIA_BOX_HD int reflect_idx64(int i, int n) {
   return i < n ? i : p - 1 - i;
 }
 
+// steps of loads in flight per thread in the interior (one thread per line: a 25 k-bin block runs
+// only ~170 threads per SM, so the bytes in flight have to come from each thread)
+constexpr int kBoxUnroll = 16;
+
 // Line c of a [len][lines] array (element (l, c) at in[l * lines + c]), sequentially:
 //   tmp = sum of the first window in order; out[0] = tmp / size;
 //   tmp += new - old; out[l] = tmp / size.
 // Every partial sum is rounded, so the chain is sequential by construction; the interior steps
-// (no index reflects) issue 8 steps of loads -- independent of the chain -- before consuming them.
+// (no index reflects) issue kBoxUnroll steps of loads -- independent of the chain -- before consuming them.
 HIA_BOX_HD void box64_line(const double* __restrict__ in, double* __restrict__ out, int len, int lines,
                            int c, int size) {
   const int s1 = size / 2;
@@ -42,15 +46,15 @@ HIA_BOX_HD void box64_line(const double* __restrict__ in, double* __restrict__ o
     tmp += nw - od;
     out[(long long)ll * ls + c] = tmp / fs;
   }
-  for (; ll + 7 <= int_hi; ll += 8) {
+  for (; ll + (kBoxUnroll - 1) <= int_hi; ll += kBoxUnroll) {
     const double* pn = in + (long long)(ll + size - 1 - s1) * ls + c;
     const double* po = in + (long long)(ll - 1 - s1) * ls + c;
     double* pw = out + (long long)ll * ls + c;
-    double nw[8], od[8];
+    double nw[kBoxUnroll], od[kBoxUnroll];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { nw[k] = pn[(long long)k * ls]; od[k] = po[(long long)k * ls]; }
+    for (int k = 0; k < kBoxUnroll; ++k) { nw[k] = pn[(long long)k * ls]; od[k] = po[(long long)k * ls]; }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { tmp += nw[k] - od[k]; pw[(long long)k * ls] = tmp / fs; }
+    for (int k = 0; k < kBoxUnroll; ++k) { tmp += nw[k] - od[k]; pw[(long long)k * ls] = tmp / fs; }
   }
   for (; ll < len; ++ll) {
     const double nw = in[(long long)reflect_idx64(ll + size - 1 - s1, len) * ls + c];

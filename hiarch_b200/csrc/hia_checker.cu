@@ -12,7 +12,7 @@
 // percentiles need 4 exact order statistics of the *duplicated* list (each value appears twice:
 // lower then upper diagonal), found by a block-wide radix select on order-preserving keys;
 // then one pass counts the kept values and bins them. band_reduce_kernel replays the
-// sequential "more than 200 pending" chunking over the per-diagonal counts (tiny).
+// sequential "more than 200 pending" chunking over the per-diagonal counts.
 #include "hia_common.cuh"
 
 namespace hia {
@@ -126,9 +126,10 @@ band_stats_kernel(const float* __restrict__ adj, int n, long long ld, int d_lo,
   if (threadIdx.x < kHistBins) my_hist[threadIdx.x] = (long long)s_bins[threadIdx.x] * dup;
 }
 
-// Sequential chunking over the diagonals (main_local.py:41-55). One warp.
-__global__ void band_reduce_kernel(const long long* __restrict__ kept, const long long* __restrict__ hist,
-                                   int nd, int min_count, double* __restrict__ out) {
+// Sequential chunking over the diagonals (main_local.py:41-55). One warp; the fallback for very
+// wide ranges (chunk table beyond 48 KB of shared memory).
+__global__ void band_reduce_seq_kernel(const long long* __restrict__ kept, const long long* __restrict__ hist,
+                                       int nd, int min_count, double* __restrict__ out) {
   const int lane = threadIdx.x;
   long long pending = 0;
   double bins = 0.0;                                    // lane b holds bin b of the pending histogram
@@ -151,6 +152,54 @@ __global__ void band_reduce_kernel(const long long* __restrict__ kept, const lon
   if (lane == 0) { out[0] = n_ent ? ent_sum / n_ent : nan(""); out[1] = (double)n_ent; }
 }
 
+// The same in two phases (one CTA): only the chunk BOUNDARIES are sequential ("more than
+// min_count pending -> emit, reset": an integer walk over the per-diagonal counts staged in shared
+// memory); the entropy of each chunk -- at chromosome scale every diagonal is a chunk of its own --
+// is a warp's work, 32 chunks at a time. The entropies are summed in a fixed order.
+__global__ void __launch_bounds__(1024)
+band_reduce_kernel(const long long* __restrict__ kept, const long long* __restrict__ hist,
+                   int nd, int min_count, double* __restrict__ out) {
+  extern __shared__ int s_tab[];                        // [nd] counts, then [nd] last diagonal of chunk c
+  __shared__ int s_nchunks;
+  __shared__ double s_part[32];
+  int* s_kept = s_tab;
+  int* s_end = s_tab + nd;
+  for (int i = threadIdx.x; i < nd; i += blockDim.x) s_kept[i] = (int)kept[i];    // <= 2 n
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long pending = 0;
+    int nc = 0;
+    for (int i = 0; i < nd; ++i) {
+      pending += s_kept[i];
+      if (pending > min_count) { s_end[nc++] = i; pending = 0; }
+    }
+    s_nchunks = nc;
+  }
+  __syncthreads();
+  const int nc = s_nchunks;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double part = 0.0;
+  for (int c = warp; c < nc; c += 32) {
+    const int i0 = c ? s_end[c - 1] + 1 : 0, i1 = s_end[c];
+    double bins = 0.0;
+    if (lane < kHistBins)
+      for (int i = i0; i <= i1; ++i) bins += (double)hist[(long long)i * kHistBins + lane];
+    const double tot = warp_sum(lane < kHistBins ? bins : 0.0);
+    const double p = bins / tot;                        // tot == 0 -> NaN like the reference
+    double term = (lane < kHistBins && bins > 0.0) ? -p * log(p) : 0.0;
+    if (tot == 0.0 && lane == 0) term = nan("");
+    part += warp_sum(term);
+  }
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double e = 0.0;
+    for (int w = 0; w < 32; ++w) e += s_part[w];
+    out[0] = nc ? e / nc : nan("");
+    out[1] = (double)nc;
+  }
+}
+
 }  // namespace
 }  // namespace hia
 
@@ -167,7 +216,7 @@ HIA_API int hia_band_entropy(const float* adj, int32_t n, int64_t ld, int32_t d_
   if (!adj || !edges30 || !out2 || !workspace || n <= 0 || ld < n || d_lo < 0) return HIA_ERR_BAD_ARG;
   const int nd = d_hi - d_lo;
   if (nd <= 0) {                                         // empty range: no entropy chunk -> None
-    band_reduce_kernel<<<1, 32, 0, s>>>(nullptr, nullptr, 0, min_count, out2);
+    band_reduce_seq_kernel<<<1, 32, 0, s>>>(nullptr, nullptr, 0, min_count, out2);
     HIA_LAUNCH_CHECK();
     return HIA_OK;
   }
@@ -181,7 +230,11 @@ HIA_API int hia_band_entropy(const float* adj, int32_t n, int64_t ld, int32_t d_
   band_stats_kernel<<<nd, kBandThreads, sh, s>>>(adj, n, ld, d_lo, edges30, per / 100.0,
                                                  (100.0 - per) / 100.0, kept, hist);
   HIA_LAUNCH_CHECK();
-  band_reduce_kernel<<<1, 32, 0, s>>>(kept, hist, nd, min_count, out2);
+  const size_t sh_tab = (size_t)2 * nd * sizeof(int);
+  if (sh_tab <= 40 * 1024)
+    band_reduce_kernel<<<1, 1024, sh_tab, s>>>(kept, hist, nd, min_count, out2);
+  else
+    band_reduce_seq_kernel<<<1, 32, 0, s>>>(kept, hist, nd, min_count, out2);
   HIA_LAUNCH_CHECK();
   return HIA_OK;
 }

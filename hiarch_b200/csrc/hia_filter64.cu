@@ -31,14 +31,17 @@ __device__ __forceinline__ double ordered_to_double(unsigned long long k) {
   return __longlong_as_double((long long)b);
 }
 
-__global__ void load_f64_kernel(const float* __restrict__ x, long long ld, int rows, int cols,
-                                double scale, double* __restrict__ a) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)rows * cols) return;
-  const int r = (int)(i / cols), c = (int)(i % cols);
-  double v = (double)x[(long long)r * ld + c];
-  if (scale > 0.0) v = nearbyint(v * scale) / scale;     // the double the decimal text parses to
-  a[i] = v;
+// grid (column groups of 256, row stripes): no integer division per element
+__global__ void __launch_bounds__(256)
+load_f64_kernel(const float* __restrict__ x, long long ld, int rows, int cols, double scale,
+                double* __restrict__ a) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    double v = (double)x[(long long)r * ld + c];
+    if (scale > 0.0) v = nearbyint(v * scale) / scale;   // the double the decimal text parses to
+    a[(long long)r * cols + c] = v;
+  }
 }
 
 // uniform_filter1d along the SLOW axis of a [len][lines] array (element (l, c) at in[l * lines + c]):
@@ -73,7 +76,8 @@ transpose64_kernel(const double* __restrict__ in, double* __restrict__ out, int 
   }
 }
 
-// ---- exact order statistics on 64-bit keys: 8 passes of 8 bits, up to 4 ranks. Ranks whose key
+// ---- exact order statistics on 64-bit keys: 8 passes of 8 bits (3 over the map, 5 over the
+// candidates the third one keeps), up to 4 ranks. Ranks whose key
 // prefixes coincide share one histogram ("slot": the two ranks of a percentile nearly always do,
 // and in pass 0 all four), and the shared-memory adds are aggregated per warp by (slot, digit)
 // with match.any: box-filtered maps put almost every key into a handful of leading digits, and
@@ -86,6 +90,7 @@ struct Sel64 {
   int slot_of_rank[4];
   int n_slots;
   int pad;
+  unsigned long long cand_n;           // candidates kept by the compacting pass
   double gamma[2];
   double pct[2];       // p_hi (66), p_lo (34)
   double sums[6];
@@ -111,44 +116,81 @@ __global__ void sel64_init_kernel(Sel64* st, long long n, double q_hi, double q_
     }
     for (int r = 0; r < 4; ++r) { st->prefix[r] = 0ull; st->slot_of_rank[r] = 0; st->slot_prefix[r] = 0ull; }
     st->n_slots = 1;
+    st->cand_n = 0ull;
   }
 }
 
+// One pass: per-slot histogram of digit `pass` over the keys whose higher bits equal a slot prefix.
+// The source is the whole array (n_host elements) or, when n_dev is given, the candidate list a
+// COMPACT pass left behind. COMPACT (the pass with 16 decided bits): every element that matches a
+// slot prefix is also appended to `cand` -- a few per cent of a map unless it is massively tied --
+// so that the remaining five passes stream the candidates instead of the map. The append is
+// aggregated per CTA iteration (1024 elements): warp ballots -> shared counter -> ONE global add.
+template <bool COMPACT>
 __global__ void __launch_bounds__(256)
-sel64_pass_kernel(const double* __restrict__ a, long long n, int pass, Sel64* st, int aggregate) {
+sel64_pass_kernel(const double* __restrict__ a, long long n_host, const unsigned long long* __restrict__ n_dev,
+                  int pass, Sel64* st, int aggregate, double* __restrict__ cand, unsigned long long* cand_count) {
   __shared__ unsigned int s_hist[4 * 256];
-  __shared__ unsigned long long s_prefix[4];
+  __shared__ unsigned int s_cnt;
+  __shared__ unsigned long long s_base;
   for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) s_hist[i] = 0u;
-  if (threadIdx.x < 4) s_prefix[threadIdx.x] = st->slot_prefix[threadIdx.x];
   const int n_slots = st->n_slots;
+  unsigned long long pf[4];                              // ~0 never equals a (<= 56-bit) prefix
+#pragma unroll
+  for (int sl = 0; sl < 4; ++sl) pf[sl] = sl < n_slots ? st->slot_prefix[sl] : ~0ull;
+  const long long n = n_dev ? (long long)*n_dev : n_host;
   __syncthreads();
   const int shift = 56 - 8 * pass;
-  const int lane = threadIdx.x & 31;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  // warp-uniform trip count: every lane reaches the match / vote instructions
-  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += 4 * stride) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  constexpr long long kChunk = 4 * 256;
+  // block-uniform trip count: every thread reaches the votes and the barriers
+  for (long long base = (long long)blockIdx.x * kChunk; base < n; base += (long long)gridDim.x * kChunk) {
     double v[4];
+    unsigned int agg[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const long long i = base + k * stride + lane;
+      const long long i = base + k * 256 + tid;
       v[k] = i < n ? a[i] : 0.0;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const long long i = base + k * stride + lane;
-      unsigned int agg = 0xffffffffu;
+      const long long i = base + k * 256 + tid;
+      agg[k] = 0xffffffffu;
       if (i < n) {
         const unsigned long long key = double_to_ordered(v[k]);
         const unsigned long long hi = (pass == 0) ? 0ull : (key >> (shift + 8));
         const unsigned int dig = (unsigned int)((key >> shift) & 0xffull);
-        for (int sl = 0; sl < n_slots; ++sl)
-          if (hi == s_prefix[sl]) agg = (unsigned int)sl * 256u + dig;    // slot prefixes are distinct
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl)
+          if (hi == pf[sl]) agg[k] = (unsigned int)sl * 256u + dig;       // slot prefixes are distinct
       }
       if (!aggregate) {
-        if (agg != 0xffffffffu) atomicAdd(&s_hist[agg], 1u);
-      } else if (__any_sync(0xffffffffu, agg != 0xffffffffu)) {
-        const unsigned int peers = __match_any_sync(0xffffffffu, agg);
-        if (agg != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&s_hist[agg], (unsigned int)__popc(peers));
+        if (agg[k] != 0xffffffffu) atomicAdd(&s_hist[agg[k]], 1u);
+      } else if (__any_sync(0xffffffffu, agg[k] != 0xffffffffu)) {
+        const unsigned int peers = __match_any_sync(0xffffffffu, agg[k]);
+        if (agg[k] != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&s_hist[agg[k]], (unsigned int)__popc(peers));
+      }
+    }
+    if (COMPACT) {
+      if (tid == 0) s_cnt = 0u;
+      __syncthreads();
+      unsigned int bal[4], tot = 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { bal[k] = __ballot_sync(0xffffffffu, agg[k] != 0xffffffffu); tot += __popc(bal[k]); }
+      unsigned int woff = 0u;
+      if (lane == 0 && tot) woff = atomicAdd(&s_cnt, tot);
+      woff = __shfl_sync(0xffffffffu, woff, 0);
+      __syncthreads();
+      if (tid == 0 && s_cnt) s_base = atomicAdd(cand_count, (unsigned long long)s_cnt);
+      __syncthreads();
+      if (tot) {
+        unsigned long long dst = s_base + woff;
+        const unsigned int below = (1u << lane) - 1u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (agg[k] != 0xffffffffu) cand[dst + __popc(bal[k] & below)] = v[k];
+          dst += __popc(bal[k]);
+        }
       }
     }
   }
@@ -296,7 +338,7 @@ HIA_API int hia_used_filter_f64(const float* x, int32_t rows, int32_t cols, int6
   const int blocks = (int)((n + 255) / 256);
   double scale = 0.0;
   if (decimals >= 0) { scale = 1.0; for (int i = 0; i < decimals; ++i) scale *= 10.0; }
-  load_f64_kernel<<<blocks, 256, 0, s>>>(x, ld_in, rows, cols, scale, A);
+  load_f64_kernel<<<dim3((cols + 255) / 256, std::min(rows, 16384)), 256, 0, s>>>(x, ld_in, rows, cols, scale, A);
   HIA_LAUNCH_CHECK();
   const bool filtered = size > 1;                        // scipy: size 1 (and 0) leave the block as is
   if (filtered) {
@@ -315,9 +357,17 @@ HIA_API int hia_used_filter_f64(const float* x, int32_t rows, int32_t cols, int6
     sel64_init_kernel<<<1, 256, 0, s>>>(st, n, q_hi, q_lo);
     HIA_LAUNCH_CHECK();
     const int grid = (int)std::min<long long>(blocks, (long long)kNumSMs * 8);
+    const int pgrid = (int)std::min<long long>((n + 1023) / 1024, (long long)kNumSMs * 8);
     const int aggregate = sel_aggregate();
+    double* cand = filtered ? A : B;                     // the fp64 array that is free at this point
+    constexpr int kCompactPass = 2;                      // 16 bits decided: sign, exponent, 4 mantissa bits
     for (int pass = 0; pass < 8; ++pass) {
-      sel64_pass_kernel<<<grid, 256, 0, s>>>(F, n, pass, st, aggregate);
+      if (pass < kCompactPass)
+        sel64_pass_kernel<false><<<pgrid, 256, 0, s>>>(F, n, nullptr, pass, st, aggregate, nullptr, nullptr);
+      else if (pass == kCompactPass)
+        sel64_pass_kernel<true><<<pgrid, 256, 0, s>>>(F, n, nullptr, pass, st, aggregate, cand, &st->cand_n);
+      else
+        sel64_pass_kernel<false><<<pgrid, 256, 0, s>>>(cand, 0, &st->cand_n, pass, st, aggregate, nullptr, nullptr);
       HIA_LAUNCH_CHECK();
       sel64_scan_kernel<<<1, 256, 0, s>>>(st);
       HIA_LAUNCH_CHECK();

@@ -62,16 +62,19 @@ HIA_HD int ix_clamp_int(double v, int lo, int hi) {
   return (int)v;
 }
 
-// sum_{q = lo}^{hi} (alpha + beta q) m[q] from the prefix sums (empty when lo > hi)
+// sum_{q = lo}^{hi} (alpha + beta q) m[q] from the prefix sums. Branch-free: an empty piece
+// (lo > hi) reads P[hi + 1] twice and contributes exactly 0, so the look-ups of all pieces of a
+// (row, centre) pair are independent loads the hardware can overlap. Requires 0 <= hi + 1 <= n and,
+// for a non-empty piece, 0 <= lo.
 HIA_HD double ix_piece(const IxPrefix* P, int lo, int hi, double alpha, double beta) {
-  if (lo > hi) return 0.0;
+  lo = lo > hi ? hi + 1 : lo;
   const IxPrefix p1 = P[hi + 1], p0 = P[lo];
   return alpha * (p1.s0 - p0.s0) + beta * (p1.s1 - p0.s1);
 }
 // sum_{q = lo}^{hi} (alpha + beta q)
 HIA_HD double ix_linsum(int lo, int hi, double alpha, double beta) {
-  if (lo > hi) return 0.0;
-  const double cnt = (double)(hi - lo + 1);
+  const int c = hi - lo + 1;
+  const double cnt = c > 0 ? (double)c : 0.0;
   return alpha * cnt + beta * 0.5 * ((double)lo + (double)hi) * cnt;
 }
 

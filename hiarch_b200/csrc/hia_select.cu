@@ -47,60 +47,73 @@ __global__ void sel_init_kernel(SelState* st, unsigned long long n) {
 
 // One streaming pass: per-slot histogram of the current digit of all keys whose higher bits
 // equal the slot's prefix. Pass 0 has a single slot (empty prefix) and also counts x>0 / x<0.
+// Grid (column groups of 1024, row stripes): a thread owns one float4 column group and walks
+// down its stripe of rows -- no integer division in the loop, slot prefixes in registers.
 template <int PASS>
 __global__ void __launch_bounds__(kSelThreads)
 sel_pass_kernel(const float* __restrict__ x, int rows, int cols, long long ld, SelState* st, int aggregate) {
   extern __shared__ unsigned int s_hist[];             // [n_slots][kBins]
-  __shared__ unsigned int s_prefix[kMaxRanks];
   __shared__ unsigned long long s_pos, s_neg;
   const int n_slots = (PASS == 0) ? 1 : st->n_slots;
   for (int i = threadIdx.x; i < n_slots * kBins; i += blockDim.x) s_hist[i] = 0u;
-  if (threadIdx.x < kMaxRanks) s_prefix[threadIdx.x] = st->slot_prefix[threadIdx.x];
   if (threadIdx.x == 0) { s_pos = 0ull; s_neg = 0ull; }
+  unsigned int pf[kMaxRanks];                          // 0xffffffff never equals a (<= 22-bit) prefix
+#pragma unroll
+  for (int s = 0; s < kMaxRanks; ++s) pf[s] = (PASS != 0 && s < n_slots) ? st->slot_prefix[s] : 0xffffffffu;
   __syncthreads();
   constexpr int shift = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
   constexpr unsigned int mask = (PASS == 2) ? 0x3ffu : 0x7ffu;
   constexpr int hshift = (PASS == 0) ? 32 : (PASS == 1 ? 21 : 10);   // bits above the digit
   unsigned int pos = 0, neg = 0;
-  const int c4 = (cols + 3) / 4;
-  const long long total = (long long)rows * c4;
   const int lane = threadIdx.x & 31;
-  // warp-uniform trip count (pass 0 aggregates its adds per warp with match.any: the leading 11
-  // bits of nearly all keys of a map fall into a handful of bins, and same-address shared-memory
-  // atomics serialise)
-  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < total;
-       base += (long long)gridDim.x * blockDim.x) {
-    const long long i = base + lane;
-    const bool live = i < total;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    int nv = 0;
-    if (live) {
-      const int r = (int)(i / c4), c0 = (int)(i % c4) * 4;
-      const float* p = x + (long long)r * ld + c0;
-      nv = min(4, cols - c0);
-      if (nv == 4) { const float4 t = ld_stream4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-      else { for (int j = 0; j < 4; ++j) v[j] = (j < nv) ? p[j] : 0.f; }
+  const int c0 = (blockIdx.x * kSelThreads + threadIdx.x) * 4;
+  const int nv = min(4, cols - c0);                    // <= 0: this thread owns no column (it still votes)
+  const float* col = x + c0;
+  // the trip count depends on blockIdx.y only: every lane of a warp reaches the match instruction.
+  // kRowsInFlight rows are loaded before any is consumed (the 64 KB of histograms of passes 1 / 2
+  // leave 3 CTAs per SM: the loads in flight per thread make up for the occupancy).
+  constexpr int kRowsInFlight = 4;
+  for (int r0 = blockIdx.y; r0 < rows; r0 += kRowsInFlight * gridDim.y) {
+    float v[kRowsInFlight][4];
+    int nvr[kRowsInFlight];
+#pragma unroll
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const int r = r0 + u * gridDim.y;
+      nvr[u] = r < rows ? nv : 0;
+      v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+      if (nvr[u] == 4) {
+        const float4 t = ld_stream4(col + (long long)r * ld);
+        v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w;
+      } else if (nvr[u] > 0) {
+        const float* p = col + (long long)r * ld;
+        for (int j = 0; j < nvr[u]; ++j) v[u][j] = p[j];
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const unsigned int key = float_to_ordered(v[j]);
-      if (PASS == 0) {
-        const bool on = j < nv;
-        pos += (on && v[j] > 0.f);
-        neg += (on && v[j] < 0.f);
-        const unsigned int agg = on ? (key >> shift) : 0xffffffffu;
-        if (aggregate) {
-          const unsigned int peers = __match_any_sync(0xffffffffu, agg);
-          if (on && lane == __ffs(peers) - 1) atomicAdd(&s_hist[agg], (unsigned int)__popc(peers));
-        } else if (on) {
-          atomicAdd(&s_hist[agg], 1u);
+    for (int u = 0; u < kRowsInFlight; ++u) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned int key = float_to_ordered(v[u][j]);
+        const bool on = j < nvr[u];
+        if (PASS == 0) {
+          pos += (on && v[u][j] > 0.f);
+          neg += (on && v[u][j] < 0.f);
+          const unsigned int agg = on ? (key >> shift) : 0xffffffffu;
+          if (aggregate) {
+            // the leading 11 bits of nearly all keys of a map fall into a handful of bins
+            const unsigned int peers = __match_any_sync(0xffffffffu, agg);
+            if (on && lane == __ffs(peers) - 1) atomicAdd(&s_hist[agg], (unsigned int)__popc(peers));
+          } else if (on) {
+            atomicAdd(&s_hist[agg], 1u);
+          }
+        } else {
+          const unsigned int hi = (hshift >= 32) ? 0u : (key >> hshift);
+          const unsigned int dig = (key >> shift) & mask;
+          int slot = -1;                               // slot prefixes are distinct: at most one matches
+#pragma unroll
+          for (int s = 0; s < kMaxRanks; ++s) slot = (hi == pf[s]) ? s : slot;
+          if (on && slot >= 0) atomicAdd(&s_hist[slot * kBins + dig], 1u);
         }
-      } else {
-        if (j >= nv) continue;
-        const unsigned int hi = (hshift >= 32) ? 0u : (key >> hshift);
-        const unsigned int dig = (key >> shift) & mask;
-        for (int s = 0; s < n_slots; ++s)
-          if (hi == s_prefix[s]) atomicAdd(&s_hist[s * kBins + dig], 1u);
       }
     }
   }
@@ -340,8 +353,9 @@ HIA_API int hia_percentiles(const float* x, int32_t rows, int32_t cols, int64_t 
   const unsigned long long n = (unsigned long long)rows * (unsigned long long)cols;
   sel_init_kernel<<<(kMaxRanks * kBins + 255) / 256, 256, 0, s>>>(st, n);
   HIA_LAUNCH_CHECK();
-  const long long vec = (long long)rows * ((cols + 3) / 4);
-  const int grid = (int)std::min<long long>((vec + kSelThreads - 1) / kSelThreads, (long long)kNumSMs * 8);
+  const int gx = (cols + 4 * kSelThreads - 1) / (4 * kSelThreads);
+  const int gy = std::max(1, std::min(rows, (kNumSMs * 8 + gx - 1) / gx));
+  const dim3 grid(gx, gy);
   const size_t sh_full = (size_t)kMaxRanks * kBins * 4;        // 64 KB
   static bool attr_done = false;
   if (!attr_done) {

@@ -512,6 +512,26 @@ def test_used_filter_box_only_is_bit_exact_vs_scipy():
         assert np.array_equal(out.cpu().numpy(), ref.astype(np.float32))
 
 
+def test_used_filter_normalised_on_massively_tied_blocks():
+    """used_filter = box filter + norm_to_zero_mean on count-like blocks: a few distinct levels
+    (nearly every cell is a candidate of the exact 64-bit select: the compacting pass keeps almost the
+    whole block), size 1 (no filter: the candidate list lives in the other fp64 buffer), a constant
+    block interior, rectangular shapes."""
+    from hiarch_b200 import ops
+    rng = np.random.default_rng(21)
+    for shape, size, levels in (((90, 70), 1, 3), ((90, 70), 4, 6), ((257, 129), 7, 2), ((64, 200), 5, 40),
+                                ((300, 300), 30, 4)):
+        a = rng.integers(0, levels, shape).astype(np.float64)
+        a[: shape[0] // 3, : shape[1] // 3] = 1.0                      # a constant patch: exact ties after the filter
+        d = _mapdev(a)
+        out = _mapdev(np.zeros(shape))
+        ops.used_filter(d, size, out, decimals=2, normalise=True)
+        ref = O.norm_to_zero_mean(O.box_filter_reflect(a, size) if size > 1 else a)
+        got = out.cpu().numpy().astype(np.float64)
+        assert np.all(np.isfinite(got))
+        assert np.all(np.abs(got - ref) <= 2e-6 + 2e-7 * np.abs(ref)), (shape, size, np.abs(got - ref).max())
+
+
 # --------------------------------------------------------------------------------- a13 intra-x
 @pytest.mark.parametrize("method", ["prefix", "direct"])
 def test_intra_x_response(golden, method):

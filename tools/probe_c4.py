@@ -19,7 +19,12 @@ import torch
 from hiarch_b200 import ops, synth
 
 
+ONCE = False          # --once: every stage exactly once (the ncu launch-list pass)
+
+
 def timed(fn, reps=2, warm=1):
+    if ONCE:
+        reps, warm = 1, 0
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -39,7 +44,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--res", type=int, default=10000)
     ap.add_argument("--direct-full", action="store_true", help="also time the direct intra-x kernel at full size (~4 s per call)")
+    ap.add_argument("--once", action="store_true", help="run every stage once, default settings only (for ncu)")
     args = ap.parse_args()
+    global ONCE
+    ONCE = args.once
     t_start = time.time()
     out = {}
 
@@ -65,7 +73,7 @@ def main():
     filt = ops.alloc_map(n)
 
     # ---- exact percentile selects: aggregated vs plain shared-memory atomics
-    for agg in ("1", "0"):
+    for agg in (("1",) if ONCE else ("1", "0")):
         os.environ["HIA_SEL_AGG"] = agg
         ms = timed(lambda: ops.main_filter(de, layout, out=filt, decimals=-1))
         note(f"main_filter_agg{agg}", {"ms": ms, "gbs_8B_per_cell": 8 * cells / ms / 1e6})
@@ -77,13 +85,14 @@ def main():
             note("main_filter_agg_settings_identical", bool(torch.equal(ref_filt, filt)))
             del ref_filt
     os.environ["HIA_SEL_AGG"] = "1"
-    ops.main_filter(de, layout, out=filt, decimals=-1)
+    if not ONCE:
+        ops.main_filter(de, layout, out=filt, decimals=-1)
 
     # ---- intra-x
     ms = timed(lambda: ops.intra_x_response(filt, method="prefix"))
     note("intra_x_prefix", {"ms": ms, "workspace_mb": ops._lib.load().hia_intra_x_workspace_bytes(n) / 2**20,
                             "cells_per_s": cells / ms * 1e3})
-    m = 5000
+    m = 1000 if ONCE else 5000
     sub = filt[:m, :m]
     a = ops.intra_x_response(sub, method="prefix")
     b = ops.intra_x_response(sub, method="direct")

@@ -1,6 +1,6 @@
 """Mirror of publish/confor (global-folding score) on the CUDA ops.
 
-filter_io / main_filter        publish/confor/src/S1_preprocess/S1_1_filtering.py:21-52
+used_filter / main_filter / filter_io   publish/confor/src/S1_preprocess/S1_1_filtering.py:13-52
 main_find_anchor               publish/confor/src/S1_preprocess/S1_2_find_anchor_main.py:8-45
 to_train_mtx                   publish/confor/src/S2_to_train_mtx/to_train_mtx.py:75-129
 to_confor / main_to_confor     publish/confor/src/S5_sim_to_pat/to_confor.py:35-93
@@ -21,6 +21,18 @@ confor_suffix = '.confor.txt'
 intra_ave_names = ops.INTRA_AVE_NAMES
 inter_ave_names = ops.INTER_AVE_NAMES
 X_SIZE = 16
+
+
+def used_filter(sps_mtx, decimals=2):
+    """S1_1_filtering.py:13-16 on one chromosome(-pair) block: box filter of size
+    int(mean(chr_lens) * .1) ('reflect') + norm_to_zero_mean, through the fused fp64 scipy-order
+    replica (`hia_used_filter_f64`). `decimals`: decimal quantisation of the block's values (2 for a
+    map read from a %.2f .mtx; -1 = not quantised)."""
+    d = sps_mtx.to_dense() if isinstance(sps_mtx, SpsHiCMtx) else sps_mtx
+    size = int(np.mean(np.array(list(sps_mtx.row_window.chr_lens.values())) * .1))
+    out = ops.alloc_map(d.shape[0], d.dmatrix.device, cols=d.shape[1])
+    ops.used_filter(d.dmatrix, size, out, decimals=decimals, normalise=True)
+    return ArrayHiCMtx(out, copy_mtx_paras=d, has_neg=True)
 
 
 def main_filter(sps_map, decimals=2):
@@ -140,13 +152,51 @@ def to_train_mtx(sps_file, window_file, center_file, spe_name, do_plot=False, fi
     return intra, inter
 
 
-def to_confor(xs, ave_names, do_trans=False):
-    """to_confor.py:35-64: long-format table (name, species, chr1, chr2, type, score). The
-    template products were already taken on the GPU (`xs.scores`, inter = max with transposed)."""
+def get_n_norm_ave_maps(ave_maps):
+    """to_confor.py:12-25: every template / sum(|template|), flattened (keys starting with '_' are
+    loadmat's metadata)."""
+    return {k: (np.asarray(v, dtype=np.float64) / np.sum(np.abs(v))).reshape((-1,))
+            for k, v in ave_maps.items() if not k.startswith('_')}
+
+
+def change_map_name(ave_maps, ave_names):
+    """to_confor.py:28-32."""
+    u_names = sorted(int(float(i)) for i in ave_maps if not i.startswith('_'))
+    return {ave_names[i]: ave_maps[str(u_names[i])] for i in range(len(u_names))}
+
+
+def _template_scores_device(xs_arr, ave_maps, do_trans):
+    """scores = X (P x 256) . T^T (256 x k) for caller-supplied templates, max with the transposed
+    images for inter pairs (to_confor.py:39-46): a P x 256 x 5 product, taken on the GPU (torch /
+    cuBLAS: plumbing-sized; the built-in templates never come here, their scores are produced by
+    `hia_gf_pool_scores` together with the images)."""
+    import torch
+    dev = "cuda"
+    x = torch.as_tensor(np.asarray(xs_arr, dtype=np.float64), device=dev)
+    t = torch.as_tensor(np.vstack([np.asarray(v, dtype=np.float64).reshape(-1) for v in ave_maps.values()]),
+                        device=dev)
+    scores = x @ t.T
+    if do_trans:
+        idx = torch.arange(X_SIZE * X_SIZE, device=dev).reshape(X_SIZE, X_SIZE).T.reshape(-1)
+        scores = torch.maximum(scores, x[:, idx] @ t.T)
+    return scores.cpu().numpy()
+
+
+def to_confor(xs, ave_maps, do_trans=False):
+    """to_confor.py:35-64: long-format table (name, species, chr1, chr2, type, score).
+    `ave_maps`: the reference's dict name -> normalised 256-vector (scores are then taken against
+    THESE templates), or just the template names in order -- then the products the GPU already
+    took against the shipped templates (`xs.scores`, inter = max with transposed) are used."""
     if xs.xs is None or len(xs.names) == 0:
         return pd.DataFrame([])
-    scores = pd.DataFrame(xs.scores, xs.out_names(), columns=list(ave_names))
+    if isinstance(ave_maps, dict):
+        values = _template_scores_device(xs.xs, ave_maps, do_trans)
+        columns = list(ave_maps.keys())
+    else:
+        values, columns = xs.scores, list(ave_maps)
+    scores = pd.DataFrame(values, xs.out_names(), columns=columns)
     scores.reset_index(inplace=True, names=['name'])
+    scores['name'] = scores['name'].str.rstrip()
     parts = scores['name'].str.split(':', expand=True)
     scores['species'] = parts.iloc[:, 0]
     scores['chr1'] = parts.iloc[:, 1]
@@ -154,9 +204,23 @@ def to_confor(xs, ave_names, do_trans=False):
     return pd.melt(scores, id_vars=['name', 'species', 'chr1', 'chr2'], var_name='type', value_name='score')
 
 
-def main_to_confor(intra_xs, inter_xs, out_dir):
-    """to_confor.py:77-93 + out_confor (:67-74)."""
-    allc = pd.concat([to_confor(intra_xs, intra_ave_names), to_confor(inter_xs, inter_ave_names, True)], axis=0)
+# the shipped templates (publish/confor/{intra,inter}_ave_maps.mat, carried as data/ave_maps.npz)
+intra_ave_map_file = None
+inter_ave_map_file = None
+
+
+def main_to_confor(intra_xs, inter_xs, out_dir, intra_ave_file=intra_ave_map_file,
+                   inter_ave_file=inter_ave_map_file):
+    """to_confor.py:77-93 + out_confor (:67-74). `*_ave_file`: a .mat of templates (keys '0'..'4')
+    to score against instead of the shipped ones (None)."""
+    def maps(path, names):
+        if path is None:
+            return names
+        from scipy.io import loadmat
+        return change_map_name(get_n_norm_ave_maps(loadmat(path)), names)
+
+    allc = pd.concat([to_confor(intra_xs, maps(intra_ave_file, intra_ave_names)),
+                      to_confor(inter_xs, maps(inter_ave_file, inter_ave_names), do_trans=True)], axis=0)
     allc = allc.sort_values(['species', 'chr1', 'chr2'])
     for species in allc['species'].unique():
         if os.path.exists(f'{out_dir}/{species}'):

@@ -2,8 +2,9 @@
 
 The hot path shards with NO data-path collective: samples, and inside a
 sample chromosome blocks, are independent. The only collectives are the timing ones of
-bench.py (barrier, max over ranks). The row-sharded genome-wide similarity (config C5) is the
-single place that needs an exchange (an all-gather of the TF32 planes) -- not built in round 1.
+bench.py (barrier, max over ranks). The row-sharded genome-wide chain (config C5) is the single
+place that needs an exchange (all-gather of the operand planes / Lanczos panels, small
+all-reduces): hiarch_b200/sharded.py.
 """
 import os
 

@@ -101,7 +101,9 @@ class ParallelFunc:
     def shards(self, thread):
         return [[self.file_names[i] for i in idx] for idx in yield_mp_idxes(len(self.file_names), thread)]
 
-    def vali_parallel(self, out_file=None, thread=None, capture_paras=True):
+    def vali_parallel(self, out_file=None, thread=2, capture_paras=True):
+        """:573-603. `thread` = worker processes (reference default 2); None or 0 = one per visible GPU.
+        Worker i runs on GPU i mod n_gpus."""
         import torch
         import torch.multiprocessing as mp
         n_gpus = torch.cuda.device_count() if torch.cuda.is_available() else 0

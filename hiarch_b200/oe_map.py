@@ -3,6 +3,7 @@
 oe_map_core    publish/oe_map/S2_oe.py:10-15            obs_d_exp(sgd_mean, k=.2) -> log, fused
 tid_off_outliers / main_denoise   publish/oe_map/S3_denoise.py:85-107
 norm_to_zero_mean / remove_outliers / norm_de_mtx       publish/oe_map/S4_norm_value.py:10-46
+oe_map_main / oe_map_io / norm_dis                      publish/oe_map/main_get_oe.py:10-76, publish/HiArch/NormDis.py:10-17
 """
 import numpy as np
 
@@ -91,3 +92,43 @@ def main_denoise(sps_map, wavelet=None):
         s2, e2 = d.col_window.chr_seps[c2]
         out[s1:e1 + 1, s2:e2 + 1].copy_(den.dmatrix)
     return res
+
+
+def oe_map_main(sps_mtx, output=None, fig_output=None, centr_loc=None,
+                do_filt_chr_by_name=False, counts_must_decrese=True):
+    """main_get_oe.py:10-59, the NormDis step on an already parsed map: preprocess_mtx ->
+    oe_map_core -> `<output>.ode.mtx` (+ `.window.bed`) -> main_denoise -> norm_de_mtx ->
+    `<output>.de_ode.mtx`. The plots (`fig_output`, `centr_loc`) are out of scope and ignored; the
+    wavelet inside main_denoise is the identity (see denoise_one_method)."""
+    from .preprocess import preprocess_mtx
+    pro_mtx = preprocess_mtx(sps_mtx, do_filt_chr_by_name)
+    if pro_mtx is None:
+        print(f'Warning: Not found proper matrix for {sps_mtx.mtx_file}')
+        return None
+    print(f'Processed matrix size is {tuple(pro_mtx.shape)}')
+    chr_lens_list = list(pro_mtx.row_window.chr_lens.values())
+    print(f'Chr num is {len(chr_lens_list)}. Max chr size is {np.max(chr_lens_list)}, min is {np.min(chr_lens_list)}.')
+    ode_mtx = oe_map_core(pro_mtx, counts_must_decrese=counts_must_decrese)
+    print('Matrix normalization DONE.')
+    if output is not None:
+        ode_mtx.to_sps().to_output(f'{output}.ode.mtx')
+    de_ode_mtx = norm_de_mtx(main_denoise(ode_mtx))
+    print('Denoise normalized matrix DONE.')
+    if output is not None:
+        de_ode_mtx.to_sps().to_output(f'{output}.de_ode.mtx', out_window=False)
+    return de_ode_mtx
+
+
+def oe_map_io(mtx_file, output, fig_output=None, do_filt_chr_by_name=False, counts_must_decrese=True,
+              index_file=None, input_centr_loc=None, thread=1):
+    """main_get_oe.py:64-76."""
+    from .new_hic_class import read_matrix
+    sps_mtx = read_matrix(mtx_file, index_file, thread=thread)
+    return oe_map_main(sps_mtx, output, fig_output, None, do_filt_chr_by_name, counts_must_decrese)
+
+
+def norm_dis(sps_file, index_file, output, fig_output=None, do_filt_chr_by_name=True,
+             counts_must_decrese=True):
+    """publish/HiArch/NormDis.py:10-17 (step 1 of one_click_pipeline.sh)."""
+    return oe_map_io(sps_file, output, fig_output, index_file=index_file,
+                     do_filt_chr_by_name=do_filt_chr_by_name, counts_must_decrese=counts_must_decrese)

@@ -351,6 +351,24 @@ def median_filter_reflect(M, size):
     return median_filter(np.asarray(M, dtype=np.float64), size=size, mode="reflect")
 
 
+def main_denoise(M, seps, wavelet=None):
+    """main_denoise, oe_map/S3_denoise.py:95-107 = tid_off_outliers, then per chromosome(-pair)
+    block used_denoise (:76-79): [wavelet ->] median filter of size max(2, int(len(row chromosome)
+    * .01)) ('reflect'). The wavelet (skimage db3 / VisuShrink, :45-47) is third-party, absent and
+    unpinned: `wavelet` is a callable applied per block, None = identity ("wavelet=identity")."""
+    M = tid_off_outliers(M)
+    out = np.empty_like(M)
+    for (s1, e1) in seps:
+        size = int(np.mean(np.array([e1 - s1 + 1]) * .01))
+        size = 2 if size < 2 else size
+        for (s2, e2) in seps:
+            blk = M[s1:e1 + 1, s2:e2 + 1]
+            if wavelet is not None:
+                blk = wavelet(blk)
+            out[s1:e1 + 1, s2:e2 + 1] = median_filter_reflect(blk, size)
+    return out
+
+
 def filter_sizes(mean_chr_len):
     """(median size, box size): S3_denoise.py:50-51 with ratio .01 (:76-79); :55 with ratio .1."""
     med = int(np.mean(np.array([mean_chr_len]) * .01))

@@ -25,6 +25,11 @@ BOUNDARY = {
     "iutils.read_matrix": ["read_matrix"],
     "oe_map.S1_preprocess": ["preprocess_mtx"],
     "oe_map.S2_oe": ["oe_map_core"],
+    "oe_map.main_get_oe": ["oe_map_main", "oe_map_io"],
+    "NormDis": ["norm_dis"],
+    "GF_S1_get_center": ["anchors_io"],
+    "GF_S2_get_score": ["get_confor"],
+    "oe_map.S3_denoise": ["denoise_one_method", "tid_off_outliers", "main_denoise"],
     "oe_map.S4_norm_value": ["norm_to_zero_mean", "remove_outliers", "norm_de_mtx"],
     "complex.src.S1_get_adj_mtx": ["get_adj_mtx"],
     "complex.src.main_local": ["get_local", "main_local", "local_io"],

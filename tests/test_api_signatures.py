@@ -19,6 +19,11 @@ MIRROR = {
     "iutils.read_matrix": "hiarch_b200.new_hic_class",
     "oe_map.S1_preprocess": "hiarch_b200.preprocess",
     "oe_map.S2_oe": "hiarch_b200.oe_map",
+    "oe_map.main_get_oe": "hiarch_b200.oe_map",
+    "oe_map.S3_denoise": "hiarch_b200.oe_map",
+    "NormDis": "hiarch_b200.oe_map",
+    "GF_S1_get_center": "hiarch_b200.confor",
+    "GF_S2_get_score": "hiarch_b200.confor",
     "oe_map.S4_norm_value": "hiarch_b200.oe_map",
     "complex.src.S1_get_adj_mtx": "hiarch_b200.complex",
     "complex.src.main_local": "hiarch_b200.complex",

@@ -151,3 +151,28 @@ def test_hot_path_streaming_matches_blocking_calls():
         for j in range(3):
             cos = abs(v[:, j].astype(np.float64) @ v_ref[:, j]) / np.linalg.norm(v[:, j])
             assert cos >= 0.9999, (j, cos)
+
+
+@pytest.mark.xfail(strict=False, reason="added at the end of round 1 with no GPU minutes left: first run pending")
+def test_norm_dis_step_against_reference_files(golden, tmp_path):
+    """Step 1 of one_click_pipeline.sh (publish/HiArch/NormDis.py): `.mtx` + `.window.bed` in,
+    `.ode.mtx` / `.window.bed` / `.de_ode.mtx` out, against the files the real reference wrote for
+    the same input (wavelet = identity on both sides, tests/golden/gen_golden_normdis.py)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from gen_golden_normdis import CASE
+    from hiarch_b200 import oe_map
+    g = golden("gnormdis")
+    mtx, bed = synth.write_sample(f"{tmp_path}/s", **CASE)
+    out = f"{tmp_path}/res"
+    de = oe_map.norm_dis(mtx, bed, out)
+    assert de is not None and tuple(de.shape) == g["de_ode.dense"].shape
+    assert open(f"{out}.window.bed").read() == str(g["window_bed"])          # bins kept by preprocess_mtx
+    assert not os.path.exists(f"{out}.de_window.bed")
+    for tag in ("ode", "de_ode"):
+        mine = np.loadtxt(f"{out}.{tag}.mtx")
+        assert mine.shape[0] == len(g[f"{tag}.vals"]), tag
+        assert np.array_equal(mine[:, 0], g[f"{tag}.rows"]) and np.array_equal(mine[:, 1], g[f"{tag}.cols"]), tag
+        assert np.abs(mine[:, 2] - g[f"{tag}.vals"]).max() <= 0.0100001, tag     # one %.2f unit (fp32 storage)
+        assert np.mean(mine[:, 2] != g[f"{tag}.vals"]) < 2e-3, tag
+    assert np.abs(de.matrix - g["de_ode.dense"]).max() <= 2e-5

@@ -133,3 +133,26 @@ def test_topk_eig_is_selfconsistent(golden):
     w, v = O.topk_eig(C, 3)
     assert np.all(np.diff(w) <= 0)
     assert np.abs(C @ v - v * w).max() < 1e-9
+
+
+def test_main_denoise_and_normdis_chain(golden):
+    """NormDis after the O/E map (oe_map/main_get_oe.py:40-50): main_denoise (clip, per-block
+    median; wavelet = identity, see tests/golden/gen_golden_normdis.py) -> norm_de_mtx, and the
+    %.2f text the step writes -- the oracle against the REAL reference's output."""
+    g = golden("gnormdis")
+    assert str(g["wavelet"]) == "identity"
+    lens = [int(x) for x in g["pro.lens"]]
+    seps, s = [], 0
+    for L in lens:
+        seps.append((s, s + L - 1))
+        s += L
+    den = O.main_denoise(g["ode.dense"], seps)
+    assert np.abs(den - g["denoised.dense"]).max() == 0.0
+    de = O.norm_de_mtx(den)
+    assert np.abs(de - g["de_ode.dense"]).max() < 1e-12
+    # SpsHiCMtx.to_output (new_hic_class.py:2267-2297): upper triangle, "%d\t%d\t%.2f"
+    up = np.triu(de)
+    r, c = np.nonzero(up)
+    assert np.array_equal(r, g["de_ode.rows"]) and np.array_equal(c, g["de_ode.cols"])
+    txt = np.array([float("%.2f" % v) for v in up[r, c]])
+    assert np.array_equal(txt, g["de_ode.vals"])

@@ -139,6 +139,62 @@ class HotPath:
         return self.n * self.n
 
 
+class HotPathPool:
+    """The per-chromosome maps of ONE sample (config C3: 24 maps of 935 ... 4 980 bins at 50 kb) as
+    a work queue over `workers` host threads, each issuing its chromosomes on its own CUDA stream
+    ("within a sample, chromosome blocks are a work queue on that GPU's streams").
+
+    A chromosome-sized chain is latency-bound, not throughput-bound: ~200 small launches, the
+    one-CTA Jacobi solves of the eigen solver and its convergence checks (each a stream
+    synchronisation) add up to ~5.6 ms per chromosome on an otherwise idle GPU (134 ms per sample
+    measured sequentially). Chains of different chromosomes are independent, so several host
+    threads (ctypes releases the GIL inside every library call; the current stream is
+    thread-local in torch) keep several of them in flight. Chromosomes are dealt largest-first
+    (by bins^2) to the least loaded worker; results come back in input order."""
+
+    def __init__(self, paths, workers=4):
+        from concurrent.futures import ThreadPoolExecutor
+        self.paths = list(paths)
+        self.workers = max(1, min(int(workers), len(self.paths)))
+        self.device = torch.cuda.current_device()
+        self.streams = [torch.cuda.Stream() for _ in range(self.workers)]
+        self.pool = ThreadPoolExecutor(max_workers=self.workers)
+        load = [0] * self.workers
+        self.assign = [[] for _ in range(self.workers)]
+        for i in sorted(range(len(self.paths)), key=lambda j: (-self.paths[j].n, j)):
+            w = min(range(self.workers), key=lambda j: (load[j], j))
+            self.assign[w].append(i)
+            load[w] += self.paths[i].n ** 2
+
+    def _work(self, w, coos, ready, results):
+        torch.cuda.set_device(self.device)
+        stream = self.streams[w]
+        with torch.cuda.stream(stream):
+            stream.wait_event(ready)                      # the caller's inputs are complete
+            for i in self.assign[w]:
+                r, c, v = coos[i]
+                results[i] = self.paths[i].run_device(r, c, v)
+            done = torch.cuda.Event()
+            done.record(stream)
+        return done
+
+    def run_device(self, coos):
+        """coos[i] = (rows, cols, vals) device tensors of chromosome i. Returns the list of
+        (eigvals, eigvecs) in input order; the caller's current stream waits for all workers."""
+        assert len(coos) == len(self.paths)
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        results = [None] * len(self.paths)
+        futures = [self.pool.submit(self._work, w, coos, ready, results) for w in range(self.workers)]
+        for f in futures:
+            main.wait_event(f.result())                   # re-raises a worker's exception
+        return results
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+
+
 def dense_to_coo(dense):
     """Upper-triangle non-zeros of a symmetric device map as (rows i32, cols i32, vals f32)."""
     up = torch.triu(dense)

@@ -176,3 +176,32 @@ def test_norm_dis_step_against_reference_files(golden, tmp_path):
         assert np.abs(mine[:, 2] - g[f"{tag}.vals"]).max() <= 0.0100001, tag     # one %.2f unit (fp32 storage)
         assert np.mean(mine[:, 2] != g[f"{tag}.vals"]) < 2e-3, tag
     assert np.abs(de.matrix - g["de_ode.dense"]).max() <= 2e-5
+
+
+@pytest.mark.xfail(strict=False, reason="added at the end of round 1 with no GPU minutes left: first run pending")
+def test_hot_path_pool_matches_sequential_chains():
+    """HotPathPool (chromosomes of one sample on several host threads / streams) returns what the
+    sequential loop returns: same eigenvalues, eigenvectors up to sign."""
+    import torch
+    from hiarch_b200.pipeline import HotPath, HotPathPool, dense_to_coo
+    lens = [300, 180, 420, 260, 150]
+    paths, coos = [], []
+    for i, n in enumerate(lens):
+        dense, seps = synth.device_dense_map([n], seed=40 + i)
+        coos.append(dense_to_coo(dense))
+        paths.append(HotPath(seps, 100000, k_eig=3))
+    seq = []
+    for hp, (r, c, v) in zip(paths, coos):
+        w, vecs = hp.run_device(r, c, v)
+        seq.append((w.cpu().numpy(), vecs.cpu().numpy()))
+    pool = HotPathPool(paths, workers=3)
+    assert sorted(i for a in pool.assign for i in a) == list(range(len(lens)))
+    for _ in range(2):                                            # buffers are reused across calls
+        res = pool.run_device(coos)
+        torch.cuda.synchronize()
+        for (w0, v0), (w1, v1) in zip(seq, res):
+            w1, v1 = w1.cpu().numpy(), v1.cpu().numpy()
+            assert np.allclose(w0, w1, rtol=1e-6)
+            cos = np.abs(np.sum(v0 * v1, axis=0)) / (np.linalg.norm(v0, axis=0) * np.linalg.norm(v1, axis=0))
+            assert np.all(cos >= 0.9999), cos
+    pool.close()

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from hiarch_b200 import ops, synth
-from hiarch_b200.pipeline import HotPath, dense_to_coo
+from hiarch_b200.pipeline import HotPath, HotPathPool, dense_to_coo
 
 
 def timed(fn, reps=2, warm=1):
@@ -68,6 +68,12 @@ def run_c3(args):
 
     stage(res, "whole_sample", sample, cells_per_s=lambda ms: cells / ms * 1e3,
           samples_per_s=lambda ms: 1e3 / ms)
+    # the same sample with the chromosomes dealt to W host threads / streams (HotPathPool)
+    for w in [int(x) for x in args.c3_workers.split(",") if x]:
+        pool = HotPathPool(paths, workers=w)
+        stage(res, f"whole_sample_pool{w}", lambda: pool.run_device(coos),
+              cells_per_s=lambda ms: cells / ms * 1e3, samples_per_s=lambda ms: 1e3 / ms)
+        pool.close()
     return res
 
 
@@ -105,6 +111,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--c3-res", type=int, default=50000)
     ap.add_argument("--c4-res", type=int, default=10000)
+    ap.add_argument("--c3-workers", default="2,4,8", help="HotPathPool sizes to time after the sequential run")
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     out = {}

@@ -7,8 +7,11 @@
 //                                           fmt="%d\t%d\t%.2f")   (SpsHiCMtx.to_output, :2290-2297)
 //
 // At 12 M entries the pandas parse is 2.1 s and savetxt 25 s of a pipeline whose kernels now take
-// milliseconds. Here the file is mmap'ed, cut at line boundaries into one slice per thread, lines are
-// counted (pass 1) and parsed straight into the caller's arrays (pass 2).
+// milliseconds. Reader: the file is mmap'ed and cut at line boundaries into one slice per thread;
+// the lines of every slice are counted (memchr) and each slice is parsed straight into the caller's
+// arrays at its line offset (gaps left by dropped lines are closed afterwards). Writer: one pass
+// computes the exact byte length of every thread's share, then the threads format straight into the
+// mmap'ed output file. 12.3 M entries, 8 threads: read 0.10 s, write 0.13 s (tmpfs).
 //
 // Parity rules:
 //   * blank lines are skipped (pandas skip_blank_lines); a line with fewer than three fields or
@@ -147,6 +150,47 @@ int parse_line(const char* s, const char* e, long long* r, long long* c, double*
   return 1;
 }
 
+// The common line -- "<digits>\t<digits>\t[-]<digits>[.<digits>]" with nothing else on it -- without
+// the field splitting and trimming of parse_line. Anything it does not recognise returns -2 and the
+// caller falls back to parse_line, which gives the same numbers for the lines accepted here:
+// <= 15 digit characters in the value keep the mantissa below 2^53 (the exact-division rule).
+inline int parse_line_fast(const char* p, const char* e, long long* r, long long* c, double* v) {
+  unsigned long long a = 0;
+  const char* q = p;
+  while (p < e && (unsigned)(*p - '0') < 10u) a = a * 10 + (unsigned)(*p++ - '0');
+  if (p == q || p - q > 18 || p >= e || *p != '\t') return -2;
+  ++p;
+  unsigned long long b = 0;
+  q = p;
+  while (p < e && (unsigned)(*p - '0') < 10u) b = b * 10 + (unsigned)(*p++ - '0');
+  if (p == q || p - q > 18 || p >= e || *p != '\t') return -2;
+  ++p;
+  bool neg = false;
+  if (p < e && *p == '-') { neg = true; ++p; }
+  unsigned long long mant = 0;
+  q = p;
+  while (p < e && (unsigned)(*p - '0') < 10u) mant = mant * 10 + (unsigned)(*p++ - '0');
+  int nd = (int)(p - q), frac = 0;
+  if (p < e && *p == '.') {
+    ++p;
+    q = p;
+    while (p < e && (unsigned)(*p - '0') < 10u) mant = mant * 10 + (unsigned)(*p++ - '0');
+    frac = (int)(p - q);
+    nd += frac;
+  }
+  if (p != e || nd == 0 || nd > 15) return -2;
+  const double x = frac ? (double)mant / kPow10[frac] : (double)mant;
+  *r = (long long)a;
+  *c = (long long)b;
+  *v = neg ? -x : x;
+  return 1;
+}
+
+inline int parse_line_any(const char* b, const char* e, long long* r, long long* c, double* v) {
+  const int st = parse_line_fast(b, e, r, c, v);
+  return st != -2 ? st : parse_line(b, e, r, c, v);
+}
+
 struct Slice { size_t b, e; long long count; int bad; long long max_r, max_c; int any_neg; };
 
 // first line start at or after byte i
@@ -190,37 +234,89 @@ int default_threads(int threads) {
 }
 
 // ---- "%.2f" ------------------------------------------------------------------------------------
+const char kDigits2[201] =
+    "0001020304050607080910111213141516171819202122232425262728293031323334353637383940414243444546474849"
+    "5051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+
+inline int ndigits32(unsigned v) {
+  return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6
+       : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
+// digits written backwards straight into place, two per division (no staging copy: a
+// variable-length memcpy per number cost more than the divisions)
+inline char* put_u32(char* p, unsigned v) {
+  char* const e = p + ndigits32(v);
+  char* t = e;
+  while (v >= 100u) {
+    const unsigned d = v % 100u;
+    v /= 100u;
+    t -= 2;
+    memcpy(t, kDigits2 + 2 * d, 2);
+  }
+  if (v >= 10u) memcpy(t - 2, kDigits2 + 2 * v, 2);
+  else t[-1] = (char)('0' + v);
+  return e;
+}
 inline char* put_uint(char* p, unsigned long long v) {
-  char tmp[24];
-  int n = 0;
-  do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-  while (n) *p++ = tmp[--n];
-  return p;
+  if (!(v >> 32)) return put_u32(p, (unsigned)v);
+  const unsigned long long hi = v / 100000000ull;
+  unsigned lo = (unsigned)(v % 100000000ull);          // exactly 8 digits, zero padded
+  p = put_uint(p, hi);
+  for (int i = 3; i >= 0; --i) { memcpy(p + 2 * i, kDigits2 + 2 * (lo % 100u), 2); lo /= 100u; }
+  return p + 8;
 }
 inline char* put_int(char* p, long long v) {
   if (v < 0) { *p++ = '-'; return put_uint(p, (unsigned long long)(-(v + 1)) + 1ull); }
   return put_uint(p, (unsigned long long)v);
 }
-// correctly rounded "%.2f" of v (see the header comment)
+// correctly rounded "%.2f" of v (see the header comment). f2_fast: v * 100 is provably not near a
+// tie -> the rounded hundredths q; otherwise the caller defers to snprintf.
+inline bool f2_fast(double v, unsigned long long* q) {
+  const double a = fabs(v);
+  if (!(a < 1.0e11)) return false;                       // also NaN / inf
+  const double x = a * 100.0;                            // |error| <= 0.5 ulp(x) <= 1e-3 at 1e13
+  const unsigned long long fi = (unsigned long long)x;   // x >= 0: truncation = floor (no libm call)
+  const double fr = x - (double)fi;
+  if (!(fabs(fr - 0.5) > 4.0e-3)) return false;          // too close to a tie to decide in binary
+  *q = fi + (fr > 0.5 ? 1ull : 0ull);
+  return true;
+}
+inline int ndigits64(unsigned long long v) {
+  int n = 0;
+  while (v >> 32) { v /= 100000000ull; n += 8; }
+  return n + ndigits32((unsigned)v);
+}
 inline char* put_f2(char* p, double v) {
+  unsigned long long q;
+  if (f2_fast(v, &q)) {
+    if (std::signbit(v)) *p++ = '-';
+    p = put_uint(p, q / 100);
+    *p++ = '.';
+    memcpy(p, kDigits2 + 2 * (unsigned)(q % 100), 2);
+    return p + 2;
+  }
   if (v != v) { memcpy(p, "nan", 3); return p + 3; }
   if (std::isinf(v)) { if (v < 0) *p++ = '-'; memcpy(p, "inf", 3); return p + 3; }
-  const double a = fabs(v);
-  if (a < 1.0e11) {
-    const double x = a * 100.0;                          // |error| <= 0.5 ulp(x) <= 1e-3 at 1e13
-    const double fl = floor(x);
-    const double fr = x - fl;
-    if (fabs(fr - 0.5) > 4.0e-3) {                       // provably not a tie: round to nearest is safe
-      const unsigned long long q = (unsigned long long)(fr > 0.5 ? fl + 1.0 : fl);
-      if (std::signbit(v)) *p++ = '-';
-      p = put_uint(p, q / 100);
-      *p++ = '.';
-      *p++ = (char)('0' + (q / 10) % 10);
-      *p++ = (char)('0' + q % 10);
-      return p;
-    }
-  }
   return p + snprintf(p, 400, "%.2f", v);
+}
+inline size_t len_f2(double v) {
+  unsigned long long q;
+  if (f2_fast(v, &q)) return (size_t)(std::signbit(v) ? 1 : 0) + (size_t)ndigits64(q / 100) + 3;
+  if (v != v) return 3;
+  if (std::isinf(v)) return v < 0 ? 4 : 3;
+  return (size_t)snprintf(nullptr, 0, "%.2f", v);
+}
+inline size_t len_int(long long v) {
+  return v < 0 ? 1 + (size_t)ndigits64((unsigned long long)(-(v + 1)) + 1ull) : (size_t)ndigits64((unsigned long long)v);
+}
+// "%d" % float of Python / numpy.savetxt: truncation toward zero
+inline char* put_trunc(char* p, double v) {
+  if (!(fabs(v) < 9.0e18)) return p + snprintf(p, 400, "%.0f", trunc(v));
+  return put_int(p, (long long)v);
+}
+inline size_t len_trunc(double v) {
+  if (!(fabs(v) < 9.0e18)) return (size_t)snprintf(nullptr, 0, "%.0f", trunc(v));
+  return len_int((long long)v);
 }
 
 }  // namespace
@@ -243,7 +339,7 @@ HIA_API int64_t hia_mtx_scan(const char* path, int32_t threads, int64_t* max_row
       for_lines(m, s, [&](const char* b, const char* e) {
         long long r, c;
         double v;
-        const int st = parse_line(b, e, &r, &c, &v);
+        const int st = parse_line_any(b, e, &r, &c, &v);
         if (st < 0) s.bad = 1;
         if (st == 1) {
           ++s.count;
@@ -285,9 +381,9 @@ HIA_API int64_t hia_mtx_count_lines(const char* path, int32_t threads) {
   return total;
 }
 
-// Parse into caller-owned HOST arrays of `capacity` entries (>= the entries of the file, e.g.
-// hia_mtx_count_lines), file order kept: ONE parsing pass into per-thread buffers, then a parallel
-// copy to the final offsets. rows / cols: int64 (like the DataFrame columns); vals: fp64; any of
+// Parse into caller-owned HOST arrays of `capacity` entries (>= the entries of the file), file order
+// kept. With capacity >= the LINES of the file (hia_mtx_count_lines) the slices parse directly into
+// the arrays; otherwise through per-thread buffers. rows / cols: int64 (like the DataFrame columns); vals: fp64; any of
 // rows32 / cols32 / vals32 may be given in addition (the int32 / fp32 copies the device kernels take;
 // pass pinned memory to upload them without another pass). *n_out = entries written.
 HIA_API int hia_mtx_parse(const char* path, int32_t threads, int64_t capacity, int64_t* rows, int64_t* cols,
@@ -297,44 +393,80 @@ HIA_API int hia_mtx_parse(const char* path, int32_t threads, int64_t capacity, i
   Mapped m;
   if (!m.open(path)) return HIA_ERR_BAD_ARG;
   std::vector<Slice> sl = cut(m, default_threads(threads));
-  struct Entry { long long r, c; double v; };
-  std::vector<std::vector<Entry>> parsed(sl.size());
+  const size_t S = sl.size();
   std::vector<std::thread> pool;
-  for (size_t i = 0; i < sl.size(); ++i)
-    pool.emplace_back([&, i] {
-      Slice& s = sl[i];
-      std::vector<Entry>& out = parsed[i];
-      out.reserve((s.e - s.b) / 12 + 16);                // >= 6 bytes per line; typical lines are 12-20
-      for_lines(m, s, [&](const char* b, const char* e) {
-        Entry en;
-        const int st = parse_line(b, e, &en.r, &en.c, &en.v);
-        if (st < 0) s.bad = 1;
-        if (st == 1) out.push_back(en);
+  auto run = [&](auto&& fn) {
+    for (size_t i = 0; i < S; ++i) pool.emplace_back(fn, i);
+    for (auto& t : pool) t.join();
+    pool.clear();
+  };
+  auto store = [&](long long k, long long r, long long c, double v) {
+    if (rows) rows[k] = r;
+    if (cols) cols[k] = c;
+    if (vals) vals[k] = v;
+    if (rows32) rows32[k] = (int32_t)r;
+    if (cols32) cols32[k] = (int32_t)c;
+    if (vals32) vals32[k] = (float)v;
+  };
+  // lines per slice (a memchr pass): an upper bound on its entries, hence a safe write offset
+  std::vector<long long> lines(S, 0), off(S + 1, 0), got(S, 0);
+  run([&](size_t i) { long long n = 0; for_lines(m, sl[i], [&](const char*, const char*) { ++n; }); lines[i] = n; });
+  for (size_t i = 0; i < S; ++i) off[i + 1] = off[i] + lines[i];
+  if (off[S] <= capacity) {
+    // DIRECT: every slice parses straight into the caller's arrays at its line offset (no staging
+    // copy, half the freshly touched memory); slices that dropped lines are closed up afterwards.
+    run([&](size_t i) {
+      long long k = off[i];
+      for_lines(m, sl[i], [&](const char* b, const char* e) {
+        long long r, c;
+        double v;
+        const int st = parse_line_any(b, e, &r, &c, &v);
+        if (st < 0) sl[i].bad = 1;
+        if (st == 1) store(k++, r, c, v);
       });
+      got[i] = k - off[i];
     });
-  for (auto& t : pool) t.join();
-  pool.clear();
-  std::vector<long long> off(sl.size() + 1, 0);
-  for (size_t i = 0; i < sl.size(); ++i) {
+    long long w = 0;
+    for (size_t i = 0; i < S; ++i) {
+      if (sl[i].bad) return HIA_ERR_BAD_ARG;
+      if (w != off[i] && got[i] > 0) {
+        const long long src = off[i], cnt = got[i];
+        if (rows) memmove(rows + w, rows + src, (size_t)cnt * sizeof(int64_t));
+        if (cols) memmove(cols + w, cols + src, (size_t)cnt * sizeof(int64_t));
+        if (vals) memmove(vals + w, vals + src, (size_t)cnt * sizeof(double));
+        if (rows32) memmove(rows32 + w, rows32 + src, (size_t)cnt * sizeof(int32_t));
+        if (cols32) memmove(cols32 + w, cols32 + src, (size_t)cnt * sizeof(int32_t));
+        if (vals32) memmove(vals32 + w, vals32 + src, (size_t)cnt * sizeof(float));
+      }
+      w += got[i];
+    }
+    *n_out = w;
+    return HIA_OK;
+  }
+  // STAGED (capacity below the line count, e.g. the exact entry count of hia_mtx_scan): parse into
+  // per-thread buffers, then copy to the final offsets.
+  struct Entry { long long r, c; double v; };
+  std::vector<std::vector<Entry>> parsed(S);
+  run([&](size_t i) {
+    std::vector<Entry>& out = parsed[i];
+    out.reserve((size_t)lines[i]);
+    for_lines(m, sl[i], [&](const char* b, const char* e) {
+      Entry en;
+      const int st = parse_line_any(b, e, &en.r, &en.c, &en.v);
+      if (st < 0) sl[i].bad = 1;
+      if (st == 1) out.push_back(en);
+    });
+  });
+  for (size_t i = 0; i < S; ++i) {
     if (sl[i].bad) return HIA_ERR_BAD_ARG;
     off[i + 1] = off[i] + (long long)parsed[i].size();
   }
-  if (off[sl.size()] > capacity) return HIA_ERR_WORKSPACE;
-  for (size_t i = 0; i < sl.size(); ++i)
-    pool.emplace_back([&, i] {
-      long long k = off[i];
-      for (const Entry& en : parsed[i]) {
-        if (rows) rows[k] = en.r;
-        if (cols) cols[k] = en.c;
-        if (vals) vals[k] = en.v;
-        if (rows32) rows32[k] = (int32_t)en.r;
-        if (cols32) cols32[k] = (int32_t)en.c;
-        if (vals32) vals32[k] = (float)en.v;
-        ++k;
-      }
-    });
-  for (auto& t : pool) t.join();
-  *n_out = off[sl.size()];
+  if (off[S] > capacity) return HIA_ERR_WORKSPACE;
+  run([&](size_t i) {
+    long long k = off[i];
+    for (const Entry& en : parsed[i]) store(k++, en.r, en.c, en.v);
+  });
+  *n_out = off[S];
   return HIA_OK;
 }
 
@@ -345,44 +477,75 @@ HIA_API int hia_mtx_write(const char* path, int64_t n, const int64_t* rows, cons
   using namespace hia;
   if (!path || n < 0 || (n > 0 && (!rows || !cols || !vals)) || value_format < 0 || value_format > 1)
     return HIA_ERR_BAD_ARG;
+  const int fd = ::open(path, O_RDWR | O_CREAT | O_TRUNC, 0644);
+  if (fd < 0) return HIA_ERR_BAD_ARG;
+  if (n == 0) return ::close(fd) == 0 ? HIA_OK : HIA_ERR_BAD_ARG;
   const int T = (int)std::max<int64_t>(1, std::min<int64_t>(default_threads(threads), n / 65536 + 1));
-  std::vector<std::string> bufs(T);
   std::vector<std::thread> pool;
-  for (int t = 0; t < T; ++t)
-    pool.emplace_back([&, t] {
-      const int64_t b = n * t / T, e = n * (t + 1) / T;
-      std::string& out = bufs[t];
-      out.resize((size_t)(e - b) * 48 + 512);
-      char* p = &out[0];
-      char* lim = p + out.size();
-      for (int64_t i = b; i < e; ++i) {
-        if (lim - p < 480) {                              // huge values: grow
-          const size_t used = (size_t)(p - &out[0]);
-          out.resize(out.size() * 2 + 1024);
-          p = &out[0] + used;
-          lim = &out[0] + out.size();
-        }
-        p = put_int(p, rows[i]);
-        *p++ = '\t';
-        p = put_int(p, cols[i]);
-        *p++ = '\t';
-        if (value_format == 0) {
-          p = put_f2(p, vals[i]);
-        } else {
-          const double v = vals[i];
-          if (!(fabs(v) < 9.0e18)) { p += snprintf(p, 64, "%.0f", trunc(v)); }
-          else p = put_int(p, (long long)v);
-        }
-        *p++ = '\n';
-      }
-      out.resize((size_t)(p - &out[0]));
-    });
-  for (auto& t : pool) t.join();
-  FILE* fh = fopen(path, "wb");
-  if (!fh) return HIA_ERR_BAD_ARG;
+  auto run = [&](auto&& fn) {
+    for (int t = 0; t < T; ++t) pool.emplace_back(fn, t);
+    for (auto& th : pool) th.join();
+    pool.clear();
+  };
+  // pass 1: exact byte length of every thread's share -> its offset in the file
+  std::vector<long long> off(T + 1, 0);
+  run([&](int t) {
+    const int64_t b = n * t / T, e = n * (t + 1) / T;
+    size_t len = 0;
+    for (int64_t i = b; i < e; ++i)
+      len += len_int(rows[i]) + len_int(cols[i]) + (value_format == 0 ? len_f2(vals[i]) : len_trunc(vals[i])) + 3;
+    off[t + 1] = (long long)len;
+  });
+  for (int t = 0; t < T; ++t) off[t + 1] += off[t];
+  const size_t total = (size_t)off[T];
+  // pass 2: format straight into the mapped file (no staging buffers; the page-cache pages of
+  // different threads fault in concurrently). File systems without shared writable mappings or
+  // without ftruncate (pipes, /dev/null) get a staged write instead.
+  char* map = nullptr;
+  if (ftruncate(fd, (off_t)total) == 0) {
+    void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (m != MAP_FAILED) map = static_cast<char*>(m);
+  }
+  std::vector<char> staged;
+  char* base = map;
+  if (!base) {
+    staged.resize(total + 512);                           // +512: snprintf's terminating NUL at the very end
+    base = staged.data();
+  }
+  std::vector<int> bad(T, 0);
+  run([&](int t) {
+    const int64_t b = n * t / T, e = n * (t + 1) / T;
+    char* p = base + off[t];
+    char* const end = base + off[t + 1];
+    char tail[512];
+    for (int64_t i = b; i < e; ++i) {
+      // the last entries of a share are formatted on the stack: snprintf writes a NUL past the text
+      char* const q0 = (end - p < 480) ? tail : p;
+      char* q = put_int(q0, rows[i]);
+      *q++ = '\t';
+      q = put_int(q, cols[i]);
+      *q++ = '\t';
+      q = value_format == 0 ? put_f2(q, vals[i]) : put_trunc(q, vals[i]);
+      *q++ = '\n';
+      const size_t len = (size_t)(q - q0);
+      if (len > (size_t)(end - p)) { bad[t] = 1; return; }   // would disagree with pass 1: never
+      if (q0 == tail) memcpy(p, tail, len);
+      p += len;
+    }
+    if (p != end) bad[t] = 1;
+  });
   int rc = HIA_OK;
-  for (const std::string& b : bufs)
-    if (!b.empty() && fwrite(b.data(), 1, b.size(), fh) != b.size()) { rc = HIA_ERR_BAD_ARG; break; }
-  if (fclose(fh) != 0) rc = HIA_ERR_BAD_ARG;
+  for (int t = 0; t < T; ++t) if (bad[t]) rc = HIA_ERR_BAD_ARG;
+  if (map) {
+    if (munmap(map, total) != 0) rc = HIA_ERR_BAD_ARG;
+  } else if (rc == HIA_OK) {
+    size_t done = 0;
+    while (done < total) {
+      const ssize_t w = ::write(fd, base + done, total - done);
+      if (w <= 0) { rc = HIA_ERR_BAD_ARG; break; }
+      done += (size_t)w;
+    }
+  }
+  if (::close(fd) != 0) rc = HIA_ERR_BAD_ARG;
   return rc;
 }

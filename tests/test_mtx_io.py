@@ -127,3 +127,49 @@ def test_write_then_read_round_trip_and_pinned32(tmp_path):
     assert r32.is_pinned() == torch.cuda.is_available()
     assert np.array_equal(r32.numpy(), rows.astype(np.int32)) and np.array_equal(c32.numpy(), cols.astype(np.int32))
     assert np.array_equal(v32.numpy(), vals.astype(np.float32))
+
+
+def test_dropped_lines_across_slices_direct_and_staged_paths(tmp_path):
+    """Blank / incomplete / NaN lines sprinkled over a file of several thread slices: the direct
+    parse (capacity = lines of the file) closes the gaps the dropped lines leave in every slice; a
+    capacity of exactly the entry count (hia_mtx_scan) takes the staged path. Both equal pandas."""
+    import ctypes
+    from hiarch_b200 import _lib
+    rng = np.random.default_rng(3)
+    n = 200_000
+    rows, cols = rng.integers(0, 5000, n), rng.integers(0, 5000, n)
+    vals = np.round(rng.normal(0, 50, n), 2)
+    kind = rng.choice(5, n, p=[.9, .03, .03, .02, .02])
+    path = str(tmp_path / "gaps.mtx")
+    with open(path, "w") as fh:
+        for r, c, v, k in zip(rows, cols, vals, kind):
+            if k == 0:
+                fh.write("%d\t%d\t%.2f\n" % (r, c, v))
+            elif k == 1:
+                fh.write("\n")
+            elif k == 2:
+                fh.write("%d\t%d\n" % (r, c))
+            elif k == 3:
+                fh.write("%d\t%d\tnan\n" % (r, c))
+            else:
+                fh.write("%d\t%d\t%.3e\r\n" % (r, c, v))              # slow path: exponent + CRLF
+    pr, pc, pv = _pandas_read(path)
+    for threads in (1, 3, 8):
+        r, c, v = mtx_io.read_mtx(path, threads=threads)                  # direct path
+        assert np.array_equal(r, pr) and np.array_equal(c, pc) and np.array_equal(v, pv)
+    lib = _lib.load()
+    mr, mc, neg = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
+    cnt = lib.hia_mtx_scan(path.encode(), 4, ctypes.addressof(mr), ctypes.addressof(mc), ctypes.addressof(neg))
+    assert cnt == len(pr) and mr.value == pr.max() and mc.value == pc.max() and neg.value == 1
+    assert cnt < lib.hia_mtx_count_lines(path.encode(), 4)
+    r = np.empty(cnt, np.int64); c = np.empty(cnt, np.int64); v = np.empty(cnt, np.float64)
+    r32 = np.empty(cnt, np.int32); v32 = np.empty(cnt, np.float32)
+    got = ctypes.c_int64(0)
+    st = lib.hia_mtx_parse(path.encode(), 4, cnt, r.ctypes.data, c.ctypes.data, v.ctypes.data,
+                           r32.ctypes.data, None, v32.ctypes.data, ctypes.addressof(got))     # staged path
+    assert st == 0 and got.value == cnt
+    assert np.array_equal(r, pr) and np.array_equal(c, pc) and np.array_equal(v, pv)
+    assert np.array_equal(r32, pr.astype(np.int32)) and np.array_equal(v32, pv.astype(np.float32))
+    st = lib.hia_mtx_parse(path.encode(), 4, cnt - 1, r.ctypes.data, c.ctypes.data, v.ctypes.data,
+                           None, None, None, ctypes.addressof(got))
+    assert st == -5                                                        # HIA_ERR_WORKSPACE

@@ -532,6 +532,29 @@ def test_used_filter_normalised_on_massively_tied_blocks():
         assert np.all(np.abs(got - ref) <= 2e-6 + 2e-7 * np.abs(ref)), (shape, size, np.abs(got - ref).max())
 
 
+@pytest.mark.xfail(strict=False, reason="added at the end of round 1 with no GPU minutes left: first run pending")
+def test_oe_and_min_fill_on_the_option_fixtures(golden):
+    """goptions.npz (real reference, tests/golden/gen_golden_options.py): ragged chromosomes
+    (70 / 12 / 31 / 6 bins, all-zero diagonals, an all-zero inter block), only_intra, and the global
+    minimum fill of a has_neg file with explicit 0.00 entries."""
+    from hiarch_b200 import ops
+    g = golden("goptions")
+
+    def seps_of(lens):
+        out, s = [], 0
+        for L in lens:
+            out.append((s, s + int(L) - 1))
+            s += int(L)
+        return out
+
+    _check_oe(g["r.dense"], seps_of(g["r.lens"]), 1000000)
+    _check_oe(g["a.dense"], seps_of(g["a.lens"]), 400000)
+    n = int(g["a.lens"].sum())
+    got = ops.scatter_coo_sym(_dev(g["de.rows"], torch.int32), _dev(g["de.cols"], torch.int32),
+                              _dev(g["de.vals"], torch.float32), n, fill_mode=ops.FILL_MIN)
+    assert np.array_equal(got.cpu().numpy(), g["dense.global_min"].astype(np.float32))
+
+
 # --------------------------------------------------------------------------------- a13 intra-x
 @pytest.mark.parametrize("method", ["prefix", "direct"])
 def test_intra_x_response(golden, method):

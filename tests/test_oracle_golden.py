@@ -156,3 +156,38 @@ def test_main_denoise_and_normdis_chain(golden):
     assert np.array_equal(r, g["de_ode.rows"]) and np.array_equal(c, g["de_ode.cols"])
     txt = np.array([float("%.2f" % v) for v in up[r, c]])
     assert np.array_equal(txt, g["de_ode.vals"])
+
+
+def _seps_of(lens):
+    out, s = [], 0
+    for L in lens:
+        out.append((s, s + int(L) - 1))
+        s += int(L)
+    return out
+
+
+def test_option_and_edge_variants(golden):
+    """Oracle vs the REAL reference on the variants the main fixtures do not reach
+    (tests/golden/gen_golden_options.py): only_intra (with and without the clamp), log of a map with
+    zero blocks, ragged chromosomes (70 / 12 / 31 / 6 bins) at low depth, the global minimum fill of
+    a has_neg file in the pipeline's order (explicit 0.00 entries stay 0), main_local with
+    short_dis_max_per=.3."""
+    g = golden("goptions")
+    sa, sr = _seps_of(g["a.lens"]), _seps_of(g["r.lens"])
+    oi = O.obs_d_exp(g["a.dense"], sa, 400000, only_intra=True)
+    assert np.array_equal(oi, g["oe.only_intra"])
+    assert np.array_equal(O.obs_d_exp(g["a.dense"], sa, 400000, counts_must_decrese=False, only_intra=True),
+                          g["oe.noclamp_only_intra"])
+    assert np.array_equal(O.log_map(oi), g["log.only_intra"])
+    oer = O.obs_d_exp(g["r.dense"], sr, 1000000)
+    assert np.array_equal(oer, g["oe.ragged"])
+    assert np.array_equal(O.log_map(oer), g["log.ragged"])
+    assert int(g["dense.n_explicit_zero"]) > 0
+    n = int(g["a.lens"].sum())
+    dense = O.scatter_coo_sym(g["de.rows"], g["de.cols"], g["de.vals"], n, has_neg=True)
+    assert np.array_equal(dense, g["dense.global_min"])
+    blockwise = O.scatter_coo_sym(g["de.rows"], g["de.cols"], g["de.vals"], n, has_neg=True, seps=sa)
+    table = O.main_local(blockwise, sa, ["chr1", "chr2", "chr3"], short_dis_max_per=.3)
+    assert [t[0] for t in table] == list(g["checker.sd30.accord_chro"])
+    assert [t[1] for t in table] == list(g["checker.sd30.other_chro"])
+    assert np.abs(np.array([t[2] for t in table]) - g["checker.sd30.accord"]).max() < 1e-12

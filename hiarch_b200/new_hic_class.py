@@ -498,6 +498,28 @@ def concat_mtxes(mtxes, row_window=None, col_window=None, **other_mtx_kwargs):
     return parent
 
 
+def _csr_from_sorted_coo(rows, cols, vals, shape):
+    """CSR straight from entries that are already in canonical order (row-major, columns strictly
+    increasing inside a row, no duplicates) -- every file the pipeline writes (`to_output` walks a
+    CSR matrix). The same arrays scipy's coo -> csr produces (:2596-2600), without its sort
+    (0.7 s per 12 M entries). Returns None when the order is anything else."""
+    n = len(rows)
+    if n == 0 or shape[0] <= 0 or shape[1] <= 0:
+        return None
+    if rows.min() < 0 or cols.min() < 0 or rows.max() >= shape[0] or cols.max() >= shape[1]:
+        return None                                 # let scipy raise its own error
+    key = rows.astype(np.int64) * np.int64(shape[1]) + cols
+    if n > 1 and not np.all(key[1:] > key[:-1]):
+        return None
+    idx_dtype = np.int32 if max(shape[0], shape[1], n) < 2 ** 31 - 1 else np.int64
+    indptr = np.zeros(shape[0] + 1, dtype=idx_dtype)
+    np.cumsum(np.bincount(rows, minlength=shape[0]), out=indptr[1:])
+    m = sps.csr_matrix((np.asarray(vals, dtype=np.float64), cols.astype(idx_dtype), indptr), shape=shape)
+    m.has_sorted_indices = True
+    m.has_canonical_format = True
+    return m
+
+
 def read_sps_file(sps_file, row_window_file=None, col_window_file=None,
                   mtx_type=None, intra=None, has_neg=None):
     """:2576-2602: tab separated (row, col, value) -> SpsHiCMtx."""
@@ -516,7 +538,9 @@ def read_sps_file(sps_file, row_window_file=None, col_window_file=None,
     else:
         row_window, col_window = GenomeIndex(row_window_file), GenomeIndex(col_window_file)
         shape = (row_window.max_idx + 1, col_window.max_idx + 1)
-    m = sps.coo_matrix((df['value'], (df['row'], df['col'])), shape=shape)
+    m = _csr_from_sorted_coo(df['row'], df['col'], df['value'], shape)
+    if m is None:                                   # any other order / duplicates: scipy's coo -> csr
+        m = sps.coo_matrix((df['value'], (df['row'], df['col'])), shape=shape)
     out = SpsHiCMtx(m, mtx_file=sps_file, row_window=row_window, col_window=col_window,
                     mtx_type=mtx_type, intra=intra, has_neg=has_neg)
     out.mtx_name = sps_file.split('/')[-1].split('.sps.mtx')[0]

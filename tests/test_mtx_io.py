@@ -173,3 +173,43 @@ def test_dropped_lines_across_slices_direct_and_staged_paths(tmp_path):
     st = lib.hia_mtx_parse(path.encode(), 4, cnt - 1, r.ctypes.data, c.ctypes.data, v.ctypes.data,
                            None, None, None, ctypes.addressof(got))
     assert st == -5                                                        # HIA_ERR_WORKSPACE
+
+
+def test_read_sps_file_csr_fast_path_equals_scipy(tmp_path):
+    """read_sps_file builds the CSR directly when the file is in canonical order (what to_output
+    writes) and falls back to scipy's coo -> csr otherwise: identical arrays either way."""
+    import scipy.sparse as sps
+    from hiarch_b200.new_hic_class import read_sps_file, _csr_from_sorted_coo
+    rng = np.random.default_rng(9)
+    n = 400
+    dense = np.triu(np.round(rng.gamma(1.0, 2.0, (n, n)) * (rng.random((n, n)) < .3), 2))
+    dense[5, :] = 0                                               # an empty row
+    dense[7, 9] = 0
+    r, c = np.nonzero(dense)
+    v = dense[r, c]
+    v[3] = 0.0                                                    # an explicit zero is a stored entry
+    sorted_path, shuffled_path, dup_path = (str(tmp_path / f"{k}.mtx") for k in ("s", "u", "d"))
+    np.savetxt(sorted_path, np.vstack([r, c, v]).T, fmt="%d\t%d\t%.2f")
+    perm = rng.permutation(len(r))
+    np.savetxt(shuffled_path, np.vstack([r[perm], c[perm], v[perm]]).T, fmt="%d\t%d\t%.2f")
+    np.savetxt(dup_path, np.vstack([np.r_[r, r[:10]], np.r_[c, c[:10]], np.r_[v, v[:10]]]).T, fmt="%d\t%d\t%.2f")
+    vv = np.array([float("%.2f" % x) for x in v])
+    ref = sps.coo_matrix((vv, (r, c)), shape=(n, n)).tocsr()
+    assert _csr_from_sorted_coo(r[perm], c[perm], vv[perm], (n, n)) is None
+    assert _csr_from_sorted_coo(np.r_[r, r[-1:]], np.r_[c, c[-1:]], np.r_[vv, vv[-1:]], (n, n)) is None
+    for path in (sorted_path, shuffled_path):
+        m = read_sps_file(path).matrix                           # shape from the largest indices
+        assert m.shape == (r.max() + 1, c.max() + 1)
+    bed = str(tmp_path / "w.bed")
+    with open(bed, "w") as fh:
+        for i in range(n):
+            fh.write(f"chr1\t{i * 1000}\t{(i + 1) * 1000}\t{i}\n")
+    for path in (sorted_path, shuffled_path):
+        m = read_sps_file(path, bed).matrix
+        assert m.shape == ref.shape and m.dtype == ref.dtype
+        assert np.array_equal(m.indptr, ref.indptr) and np.array_equal(m.indices, ref.indices)
+        assert np.array_equal(m.data, ref.data) and m.indices.dtype == ref.indices.dtype
+        assert m.nnz == len(r)                                    # the explicit zero is kept
+    d = read_sps_file(dup_path, bed).matrix                       # duplicates are summed by scipy
+    ref_d = sps.coo_matrix((np.r_[vv, vv[:10]], (np.r_[r, r[:10]], np.r_[c, c[:10]])), shape=(n, n)).tocsr()
+    assert (d != ref_d).nnz == 0 and d.nnz == ref_d.nnz

@@ -385,8 +385,12 @@ class SpsHiCMtx(HiCMtx):
     def __init__(self, sps_mtx, mtx_file=None, row_window=None, col_window=None,
                  mtx_type=None, intra=None, has_neg=None, copy_mtx_paras=None, shape=None):
         super().__init__()
-        if isinstance(sps_mtx, tuple):
-            sps_mtx = sps.coo_matrix(sps_mtx, shape=shape)
+        if isinstance(sps_mtx, tuple):                  # (vals, (rows, cols)) like scipy's coo_matrix
+            vals, (rows, cols) = sps_mtx
+            fast = None
+            if shape is not None:                       # row-major entries (torch.nonzero order): no sort
+                fast = _csr_from_sorted_coo(np.asarray(rows), np.asarray(cols), np.asarray(vals), tuple(shape))
+            sps_mtx = fast if fast is not None else sps.coo_matrix(sps_mtx, shape=shape)
         self.matrix = sps_mtx if isinstance(sps_mtx, sps.csr_matrix) else sps_mtx.tocsr()
         self.shape = self.matrix.shape
         self._init_meta(mtx_file, row_window, col_window, mtx_type, intra, has_neg, copy_mtx_paras)

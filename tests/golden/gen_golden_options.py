@@ -29,7 +29,7 @@ from hiarch_b200 import synth  # noqa: E402
 warnings.filterwarnings("ignore")
 
 A = dict(names=["chr1", "chr2", "chr3"], lens=[90, 70, 60], bin_size=400000, seed=51)
-R = dict(names=["c1", "c2", "c3", "c4"], lens=[70, 12, 31, 6], bin_size=1000000, seed=52, depth=0.02, lam_inter=0.05)
+R = dict(names=["c1", "c2", "c3", "c4"], lens=[70, 12, 31, 6], bin_size=1000000, seed=52, depth=0.002, lam_inter=0.02)
 
 
 def quiet(fn, *a, **k):

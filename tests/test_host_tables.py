@@ -68,6 +68,31 @@ def test_tables_reproduce_expected(golden, case):
     assert np.allclose(mine, g["expected_last_block"], rtol=1e-12, atol=0)
 
 
+def test_tables_on_ragged_low_depth_chromosomes(golden):
+    """The numpy model of the finalize kernel on the ragged fixture (70 / 12 / 31 / 6 bins, all-zero
+    diagonals): expected vectors equal the oracle's (pinned to the real reference by
+    test_oracle_golden.py::test_option_and_edge_variants), and dividing by them reproduces the
+    reference's O/E block."""
+    g = golden("goptions")
+    dense, bs = g["r.dense"], 1000000
+    s = 0
+    for L in [int(x) for x in g["r.lens"]]:
+        blk = dense[s:s + L, s:s + L]
+        for clamp in (True, False):
+            ref = np.array(O.sgd_mean_expected(blk, bs), dtype=np.float64)
+            if clamp:
+                ref = np.array(O.monotone_clamp(ref))
+            assert np.allclose(expected_from_tables(blk, bs, clamp), ref, rtol=1e-12, atol=0), (L, clamp)
+        exp = expected_from_tables(blk, bs, True)
+        d = np.abs(np.subtract.outer(np.arange(L), np.arange(L)))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            oe = blk / exp[d]
+        ref_oe = g["oe.ragged"][s:s + L, s:s + L]
+        ok = np.isfinite(oe)
+        assert np.allclose(oe[ok], ref_oe[ok], rtol=1e-12, atol=0)
+        s += L
+
+
 def test_clamp_formula_on_adversarial_vectors():
     rng = np.random.default_rng(0)
     for _ in range(200):

@@ -178,6 +178,7 @@ def test_norm_dis_step_against_reference_files(golden, tmp_path):
     assert np.abs(de.matrix - g["de_ode.dense"]).max() <= 2e-5
 
 
+@pytest.mark.timeout(180)
 @pytest.mark.xfail(strict=False, reason="added at the end of round 1 with no GPU minutes left: first run pending")
 def test_hot_path_pool_matches_sequential_chains():
     """HotPathPool (chromosomes of one sample on several host threads / streams) returns what the

@@ -357,12 +357,10 @@ HIA_API int hia_percentiles(const float* x, int32_t rows, int32_t cols, int64_t 
   const int gy = std::max(1, std::min(rows, (kNumSMs * 8 + gx - 1) / gx));
   const dim3 grid(gx, gy);
   const size_t sh_full = (size_t)kMaxRanks * kBins * 4;        // 64 KB
-  static bool attr_done = false;
-  if (!attr_done) {
-    HIA_CUDA(cudaFuncSetAttribute(sel_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_full));
-    HIA_CUDA(cudaFuncSetAttribute(sel_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_full));
-    attr_done = true;
-  }
+  // per call: the attribute belongs to the CURRENT device's copy of the function (a process may
+  // drive several devices), and setting it is a few hundred nanoseconds
+  HIA_CUDA(cudaFuncSetAttribute(sel_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_full));
+  HIA_CUDA(cudaFuncSetAttribute(sel_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_full));
   sel_pass_kernel<0><<<grid, kSelThreads, kBins * 4, s>>>(x, rows, cols, ld, st, sel_aggregate());
   HIA_LAUNCH_CHECK();
   sel_ranks_kernel<<<1, 32, 0, s>>>(st, modes, quantiles, nq);

@@ -3,8 +3,10 @@
 Every function here launches hand-written sm_100a kernels through libhiarch_b200.so on the
 current torch stream; torch only owns the memory. No op has a CPU or torch fallback.
 """
+import collections
 import ctypes
 import os
+import threading
 
 import numpy as np
 import torch
@@ -87,7 +89,9 @@ class GenomeLayout:
 
 
 # ------------------------------------------------------------------------------- a1/a2 scatter
-_scatter_ws = {}
+_scatter_ws = collections.OrderedDict()     # (device, n, n_chr, stream) -> workspace, bounded LRU
+_scatter_ws_lock = threading.Lock()
+_SCATTER_WS_MAX = 64
 
 
 def scatter_coo_sym(rows, cols, vals, n, mtx_type=MTX_TRIU, fill_mode=FILL_ZERO, layout=None,
@@ -108,12 +112,15 @@ def scatter_coo_sym(rows, cols, vals, n, mtx_type=MTX_TRIU, fill_mode=FILL_ZERO,
             layout = GenomeLayout([(0, n - 1)], rows.device)
         n_chr, chr_start = layout.n_chr, layout.chr_start
     key = (str(rows.device), n, n_chr, _stream())               # one scratch per stream: calls may overlap
-    ws = _scatter_ws.get(key)
-    if ws is None:
-        ws = torch.empty(lib.hia_scatter_workspace_bytes(n, n_chr), dtype=torch.uint8, device=rows.device)
-        if len(_scatter_ws) > 8:
-            _scatter_ws.clear()
-        _scatter_ws[key] = ws
+    with _scatter_ws_lock:                      # HotPathPool calls this from several host threads
+        ws = _scatter_ws.get(key)
+        if ws is None:
+            ws = torch.empty(lib.hia_scatter_workspace_bytes(n, n_chr), dtype=torch.uint8, device=rows.device)
+            _scatter_ws[key] = ws
+            while len(_scatter_ws) > _SCATTER_WS_MAX:
+                _scatter_ws.popitem(last=False)
+        else:
+            _scatter_ws.move_to_end(key)
     st = lib.hia_scatter_coo_sym(_ptr(rows), _ptr(cols), _ptr(vals), rows.numel(), n, _ptr(out),
                                  out.stride(0), mtx_type, fill_mode, _ptr(chr_start), n_chr,
                                  _ptr(ws), _stream())

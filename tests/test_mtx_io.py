@@ -213,3 +213,32 @@ def test_read_sps_file_csr_fast_path_equals_scipy(tmp_path):
     d = read_sps_file(dup_path, bed).matrix                       # duplicates are summed by scipy
     ref_d = sps.coo_matrix((np.r_[vv, vv[:10]], (np.r_[r, r[:10]], np.r_[c, c[:10]])), shape=(n, n)).tocsr()
     assert (d != ref_d).nnz == 0 and d.nnz == ref_d.nnz
+
+
+def test_reader_vs_pandas_by_literal_form(tmp_path):
+    """Differential check over many literal forms: plain decimals of <= 15 digits (every file the
+    pipeline writes) are bit-identical to pandas; longer literals and exponent forms are parsed
+    correctly rounded (strtod) where pandas' fast xstrtod is a few ulp off -- so they may differ from
+    pandas, but never from Python's float()."""
+    import re
+    rng = np.random.default_rng(7)
+    forms = ["%.2f", "%.10f", "%.17g", "%d", "+%.3f", "%.3e", "00%.1f", "%.15f"]
+    n = 40000
+    path = str(tmp_path / "forms.mtx")
+    texts = []
+    with open(path, "w") as fh:
+        for _ in range(n):
+            x = rng.normal(0, 100) * 10.0 ** int(rng.integers(-6, 6))
+            f = forms[int(rng.integers(0, len(forms)))]
+            t = f % (int(x) if f == "%d" else (abs(x) if f[0] in "+0" else x))
+            texts.append(t)
+            fh.write("%d\t%d\t%s\n" % (rng.integers(0, 10 ** 6), rng.integers(0, 10 ** 6), t))
+    r, c, v = mtx_io.read_mtx(path, threads=3)
+    pr, pc, pv = _pandas_read(path)
+    assert np.array_equal(r, pr) and np.array_equal(c, pc)
+    exact = np.array([float(t) for t in texts])
+    assert np.array_equal(v, exact)                               # correctly rounded, every form
+    short = np.array([("e" not in t) and len(re.sub(r"[^0-9]", "", t)) <= 15 for t in texts])
+    assert short.sum() > n // 3
+    assert np.array_equal(v[short], pv[short])                    # == pandas wherever pandas is exact
+    assert np.all(np.abs(v - pv) <= 1e-11 * np.abs(v))

@@ -407,6 +407,52 @@ oe_apply_kernel(const float* __restrict__ map, float* __restrict__ out, int n, l
   }
 }
 
+// The same from the UPPER triangle only (HIA_OE_FROM_UPPER): O/E and log are symmetric functions of
+// a symmetric map (the expected vector depends on |c - r|, inter_inv[a][b] == inter_inv[b][a]), so
+// a 32 x 32 tile (bi <= bj) of the upper triangle is read once, its result written to out[r][c] and,
+// transposed through shared memory, to out[c][r]: 2 + 4 instead of 4 + 4 bytes per cell, and the
+// lower triangle of `map` is never read -- the scatter can skip its mirror pass
+// (HIA_MTX_TRIU_UPPER). Bit-identical to oe_apply_kernel on a mirrored map.
+__global__ void __launch_bounds__(256)
+oe_apply_upper_kernel(const float* __restrict__ map, float* __restrict__ out, int n, long long ld,
+                      const int* __restrict__ chr_start, int n_chr, const short* __restrict__ bin_chr,
+                      const float* __restrict__ inv_expected, const float* __restrict__ inter_inv,
+                      const float* __restrict__ min_pos_oe, int flags) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;            // tile (bi, bj) of the upper triangle
+  if (bj < bi) return;
+  const bool do_log = flags & HIA_OE_LOG;
+  const bool only_intra = flags & HIA_OE_ONLY_INTRA;
+  float fill = 0.f;
+  if (do_log) {
+    const float m = *min_pos_oe;
+    fill = (m == INFINITY) ? 0.f : fast_log1p_pos(m);
+  }
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int c = bj * 32 + tx;
+  const int cb = bin_chr[min(c, n - 1)];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = bi * 32 + ty + 8 * k;
+    float v = 0.f;
+    if (r < n && c < n && c >= r) {
+      v = map[(long long)r * ld + c];
+      const int a = bin_chr[r];
+      if (a == cb) v *= __ldg(&inv_expected[chr_start[a] + (c - r)]);
+      else v = only_intra ? 0.f : v * __ldg(&inter_inv[a * n_chr + cb]);
+      if (do_log) v = (v > 0.f) ? fast_log1p_pos(v) : fill;
+      out[(long long)r * ld + c] = v;
+    }
+    tile[ty + 8 * k][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = bj * 32 + ty + 8 * k, cc = bi * 32 + tx;  // transposed position
+    if (r < n && cc < n && r > cc) out[(long long)r * ld + cc] = tile[tx][ty + 8 * k];
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Stand-alone ArrayHiCMtx.log (new_hic_class.py:2076-2094) for maps that did not come out of
 // hia_oe_apply: pass 1 = min positive value, pass 2 = x>0 ? ln(x+1) : ln(min_pos + 1).
@@ -556,6 +602,14 @@ static int apply_impl(const float* map, float* out, int32_t n, int64_t ld, const
     return HIA_ERR_BAD_ARG;
   if (!aligned16(map) || !aligned16(out) || (ld & 3)) return HIA_ERR_ALIGN;
   if (rows == 0) return HIA_OK;
+  if (flags & HIA_OE_FROM_UPPER) {                       // whole maps only; in place is fine (cell by cell)
+    if (row0 != 0 || rows != n) return HIA_ERR_BAD_ARG;
+    dim3 gu((n + 31) / 32, (n + 31) / 32);
+    oe_apply_upper_kernel<<<gu, 256, 0, stream>>>(map, out, n, ld, chr_start, n_chr, bin_chr, inv_expected,
+                                                  inter_inv, min_pos_oe, flags);
+    HIA_LAUNCH_CHECK();
+    return HIA_OK;
+  }
   const int threads = 256;
   dim3 grid((n + threads * 4 - 1) / (threads * 4), min(rows, 2048));
   oe_apply_kernel<<<grid, threads, 0, stream>>>(map, out, n, ld, chr_start, n_chr, bin_chr,

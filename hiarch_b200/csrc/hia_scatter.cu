@@ -470,8 +470,13 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!out || n <= 0 || ld < n || nnz < 0) return HIA_ERR_BAD_ARG;
   if (nnz > 0 && (!rows || !cols || !vals)) return HIA_ERR_BAD_ARG;
-  if (mtx_type != HIA_MTX_TRIU && mtx_type != HIA_MTX_ALL) return HIA_ERR_BAD_ARG;
+  if (mtx_type != HIA_MTX_TRIU && mtx_type != HIA_MTX_ALL && mtx_type != HIA_MTX_TRIU_UPPER) return HIA_ERR_BAD_ARG;
   if (fill_mode < HIA_FILL_ZERO || fill_mode > HIA_FILL_BLOCK_MIN) return HIA_ERR_BAD_ARG;
+  const bool mirror = (mtx_type == HIA_MTX_TRIU);
+  if (mtx_type == HIA_MTX_TRIU_UPPER) {                  // upper triangle only: no mirror pass
+    if (fill_mode != HIA_FILL_ZERO) return HIA_ERR_BAD_ARG;
+    mtx_type = HIA_MTX_TRIU;
+  }
   if (!aligned16(out) || (ld & 3)) return HIA_ERR_ALIGN;
   if (fill_mode != HIA_FILL_ZERO && (!workspace || !chr_start || n_chr < 1)) return HIA_ERR_BAD_ARG;
   if (n_chr > kMaxChr) return HIA_ERR_UNSUPPORTED;
@@ -529,7 +534,7 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
     fixup_kernel<<<grid, threads, sh, stream>>>(out, n, ld, fill_mode, mtx_type, chr_start, n_chr, keys);
     HIA_LAUNCH_CHECK();
   }
-  if (mtx_type == HIA_MTX_TRIU) {                          // to_all: triu(M,0).T + triu(M,1)
+  if (mirror) {                                            // to_all: triu(M,0).T + triu(M,1)
     dim3 gm((n + 31) / 32, (n + 31) / 32);
     mirror_kernel<<<gm, 256, 0, stream>>>(out, n, ld);
     HIA_LAUNCH_CHECK();

@@ -14,9 +14,9 @@ import torch
 from . import _lib
 from .sgd import oe_tables
 
-MTX_TRIU, MTX_ALL = 0, 1
+MTX_TRIU, MTX_ALL, MTX_TRIU_UPPER = 0, 1, 2      # TRIU_UPPER: no mirror pass, lower triangle unwritten
 FILL_ZERO, FILL_MIN, FILL_BLOCK_MIN = 0, 1, 2
-OE_LOG, OE_ONLY_INTRA = 1, 2
+OE_LOG, OE_ONLY_INTRA, OE_FROM_UPPER = 1, 2, 4
 SIM_COSINE_DISTANCE, SIM_PEARSON = 0, 1
 PREC_3XTF32, PREC_FP64, PREC_3XF16 = 0, 1, 2
 # Default similarity precision: the fp16 hi/lo split (same 22-bit operands as 3xTF32, half the
@@ -146,10 +146,12 @@ class OEState:
 
 
 def obs_d_exp(dense, layout, bin_size, k=.2, counts_must_decrese=True, only_intra=False,
-              log=False, out=None, state=None):
+              log=False, out=None, state=None, from_upper=False):
     """O/E (mode='sgd_mean') of a symmetric dense map, optionally fused with ArrayHiCMtx.log.
     Replaces HiCMtx.obs_d_exp (publish/new_hic_class.py:1121-1290) + log (:2076-2094).
-    `out` may alias `dense` (in place). Returns (out, OEState)."""
+    `out` may alias `dense` (in place). Returns (out, OEState). from_upper=True: only the upper
+    triangle of `dense` is read (it may come from scatter_coo_sym(mtx_type=MTX_TRIU_UPPER)); the
+    result is the same full symmetric map."""
     lib = _lib.load()
     _need_cuda(dense)
     n = layout.n
@@ -173,7 +175,7 @@ def obs_d_exp(dense, layout, bin_size, k=.2, counts_must_decrese=True, only_intr
                              _ptr(state.expected), _ptr(state.inv_expected),
                              _ptr(state.inter_inv), _ptr(state.min_pos_oe), stream)
     _lib.check(st, "hia_oe_finalize")
-    flags = (OE_LOG if log else 0) | (OE_ONLY_INTRA if only_intra else 0)
+    flags = (OE_LOG if log else 0) | (OE_ONLY_INTRA if only_intra else 0) | (OE_FROM_UPPER if from_upper else 0)
     st = lib.hia_oe_apply(_ptr(dense), _ptr(out), n, dense.stride(0), _ptr(layout.chr_start),
                           layout.n_chr, _ptr(layout.bin_chr), _ptr(state.inv_expected),
                           _ptr(state.inter_inv), _ptr(state.min_pos_oe), flags, stream)

@@ -52,6 +52,9 @@ uint64_t hia_launch_count(void);
 /* ------------------------------------------------------------------------------------ */
 #define HIA_MTX_TRIU 0   /* entries with col < row are ignored; result mirrored */
 #define HIA_MTX_ALL  1   /* entries stored as given                             */
+#define HIA_MTX_TRIU_UPPER 2 /* like TRIU, HIA_FILL_ZERO only: the upper triangle is scattered, the lower
+                              * triangle of `out` is left UNWRITTEN (for consumers that read the upper
+                              * triangle only: hia_oe_expected_pass, hia_oe_apply(HIA_OE_FROM_UPPER)) */
 #define HIA_FILL_ZERO      0  /* absent cells = 0                (has_neg == False)          */
 #define HIA_FILL_MIN       1  /* absent cells = min(all entries) (has_neg, whole matrix)     */
 #define HIA_FILL_BLOCK_MIN 2  /* absent cells = min(entries of that chromosome-pair block)   */
@@ -132,6 +135,10 @@ int hia_oe_finalize(const double* diag_sum, const float* diag_minpos, const doub
  *        HIA_OE_ONLY_INTRA -> inter blocks are written as 0            (only_intra=True) */
 #define HIA_OE_LOG 1
 #define HIA_OE_ONLY_INTRA 2
+/* hia_oe_apply only (whole maps): read the upper triangle of `map` only and write both halves of
+ * `out` (the transposed half through shared memory). Same result bit for bit on a symmetric map;
+ * pairs with HIA_MTX_TRIU_UPPER of the scatter (no mirror pass). Opt-in, see DESIGN.md 6. */
+#define HIA_OE_FROM_UPPER 4
 int hia_oe_apply(const float* map, float* out, int32_t n, int64_t ld, const int32_t* chr_start,
                  int32_t n_chr, const int16_t* bin_chr, const float* inv_expected,
                  const float* inter_inv, const float* min_pos_oe, int flags, void* stream);

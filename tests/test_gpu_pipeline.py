@@ -206,3 +206,35 @@ def test_hot_path_pool_matches_sequential_chains():
             cos = np.abs(np.sum(v0 * v1, axis=0)) / (np.linalg.norm(v0, axis=0) * np.linalg.norm(v1, axis=0))
             assert np.all(cos >= 0.9999), cos
     pool.close()
+
+
+@pytest.mark.xfail(strict=False, reason="added at the end of round 1 with no GPU minutes left: first run pending")
+def test_upper_only_mode_is_bit_identical(monkeypatch):
+    """HIA_UPPER_ONLY=1 (scatter without the mirror pass + O/E apply from the upper triangle, both
+    halves written through a shared-memory transpose) gives the same O/E map bit for bit."""
+    import torch
+    from hiarch_b200 import ops
+    from hiarch_b200.pipeline import HotPath
+    lens, bs = [333, 150, 97], 100000                              # ragged 32 x 32 edge tiles
+    rows, cols, vals, seps = synth.synth_coo(lens, seed=9)
+    dev = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt)
+    coo = (dev(rows, torch.int32), dev(cols, torch.int32), dev(vals, torch.float32))
+    ref = HotPath(seps, bs, k_eig=3)
+    assert not ref.upper_only
+    w0, v0 = ref.run_device(*coo)
+    monkeypatch.setenv("HIA_UPPER_ONLY", "1")
+    hp = HotPath(seps, bs, k_eig=3)
+    assert hp.upper_only
+    hp.raw.fill_(float("nan"))                                     # the lower triangle must never be read
+    w1, v1 = hp.run_device(*coo)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.triu(hp.raw), torch.triu(ref.raw))
+    assert torch.equal(hp.oe, ref.oe)
+    assert torch.equal(hp.sim, ref.sim)
+    assert np.allclose(w0.cpu().numpy(), w1.cpu().numpy(), rtol=1e-12)
+    # only_intra and no-log variants of the apply pass
+    layout = ops.GenomeLayout(seps)
+    for kw in (dict(log=False), dict(log=True, only_intra=True)):
+        a, _ = ops.obs_d_exp(ref.raw, layout, bs, **kw)
+        b, _ = ops.obs_d_exp(hp.raw, layout, bs, from_upper=True, **kw)
+        assert torch.equal(a, b), kw

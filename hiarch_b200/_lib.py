@@ -73,6 +73,8 @@ PROTOTYPES = {
     "hia_sim_gemm_rows_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "hia_sim_gemm_rows": (c_int, [c_vp, c_vp, c_int, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_int,
                                   c_i32, c_vp, c_i64, c_vp]),
+    "hia_sim_gemm_rows_cols": (c_int, [c_vp, c_vp, c_int, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64,
+                                       c_int, c_i32, c_vp, c_i64, c_vp]),
     "hia_mtx_scan": (c_i64, [ctypes.c_char_p, c_i32, c_vp, c_vp, c_vp]),
     "hia_mtx_count_lines": (c_i64, [ctypes.c_char_p, c_i32]),
     "hia_mtx_parse": (c_int, [ctypes.c_char_p, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -642,7 +642,7 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
 static int launch_gemm(void* hi, void* lo, int prec, int plane_rows, int n_valid, int kpad, int row0, int rows,
                        int symmetric, int band_lo, int band_hi, float* out, int64_t ld_out, int flavour,
                        int k_chunk, hia::TileCoord* d_tiles, unsigned int* sync_ctr, int64_t n_sync,
-                       cudaStream_t stream);
+                       cudaStream_t stream, int col0 = 0, int cols = -1);
 
 HIA_API int hia_similarity(const float* x, int32_t m, int32_t k, int64_t ld_x, float* out,
                            int64_t ld_out, int flavour, int precision, int32_t band_lo,
@@ -755,7 +755,7 @@ static int launch_syrk(const CUtensorMap& map_hi, const CUtensorMap& map_lo, con
 static int launch_gemm(void* hi, void* lo, int prec, int plane_rows, int n_valid, int kpad, int row0, int rows,
                        int symmetric, int band_lo, int band_hi, float* out, int64_t ld_out, int flavour,
                        int k_chunk, hia::TileCoord* d_tiles, unsigned int* sync_ctr, int64_t n_sync,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int col0, int cols) {
   using namespace hia;
   const int m = n_valid;
   const int ctas = syrk_ctas();
@@ -767,8 +767,11 @@ static int launch_gemm(void* hi, void* lo, int prec, int plane_rows, int n_valid
   if (symmetric) {
     num_tiles = build_tiles(m, tile_m, band_lo, band_hi, h_tiles);
   } else {
-    const int row_end = min(row0 + rows, m), nt = (m + BN - 1) / BN;
-    for (int sn = 0; sn < nt; sn += 8)                     // 8-column-tile super blocks for L2 reuse
+    // row block x column range [col0, col0 + cols) (cols < 0: every column); col0 % BN == 0
+    const int row_end = min(row0 + rows, m);
+    const int col_end = cols < 0 ? m : min(col0 + cols, m);
+    const int nt0 = col0 / BN, nt = (col_end + BN - 1) / BN;
+    for (int sn = nt0; sn < nt; sn += 8)                   // 8-column-tile super blocks for L2 reuse
       for (int r = row0; r < row_end; r += tile_m)
         for (int nj = sn; nj < min(sn + 8, nt); ++nj) { h_tiles[num_tiles].m0 = r; h_tiles[num_tiles].n0 = nj * BN; ++num_tiles; }
   }
@@ -843,4 +846,29 @@ HIA_API int hia_sim_gemm_rows(void* hi, void* lo, int precision, int32_t plane_r
   return launch_gemm(hi, lo, precision, plane_rows, n, round_up(k, bk_of(precision)), row0, rows, 0, 0, -1,
                      out_rows, ld_out, flavour, k_chunk, reinterpret_cast<TileCoord*>(ws),
                      reinterpret_cast<unsigned int*>(ws + tiles_al), sync_counters(n, k), stream);
+}
+
+// The same for a COLUMN RANGE of the row block: out_rows[r - row0][c] for r in [row0, row0 + rows),
+// c in [col0, col0 + cols), col0 a multiple of 256. n = number of valid plane rows / columns
+// (>= col0 + cols; columns >= n are masked). The ring schedule of hiarch_b200/sharded.py calls it
+// with the planes of the own rows and of ONE peer block stacked in one buffer ([own | peer]) and a
+// column-shifted `out_rows` pointer, while the next peer's planes arrive over NVLink.
+HIA_API int hia_sim_gemm_rows_cols(void* hi, void* lo, int precision, int32_t plane_rows, int32_t n, int32_t k,
+                                   int32_t row0, int32_t rows, int32_t col0, int32_t cols, float* out_rows,
+                                   int64_t ld_out, int flavour, int32_t k_chunk, void* workspace,
+                                   int64_t workspace_bytes, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!hi || !lo || !out_rows || !workspace || n <= 0 || k <= 0 || plane_rows < n || rows <= 0 ||
+      row0 < 0 || col0 < 0 || cols <= 0 || col0 + cols > n || !split_prec(precision))
+    return HIA_ERR_BAD_ARG;
+  if ((row0 % BM) || (col0 % BN)) return HIA_ERR_ALIGN;
+  if (!aligned16(hi) || !aligned16(lo) || !aligned16(workspace)) return HIA_ERR_ALIGN;
+  if (workspace_bytes < hia_sim_gemm_rows_workspace_bytes(n, k)) return HIA_ERR_WORKSPACE;
+  const int64_t ntiles = (int64_t)((n + BM - 1) / BM) * ((n + BN - 1) / BN);
+  const int64_t tiles_al = (ntiles * (int64_t)sizeof(TileCoord) + 1023) / 1024 * 1024;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  return launch_gemm(hi, lo, precision, plane_rows, n, round_up(k, bk_of(precision)), row0, rows, 0, 0, -1,
+                     out_rows, ld_out, flavour, k_chunk, reinterpret_cast<TileCoord*>(ws),
+                     reinterpret_cast<unsigned int*>(ws + tiles_al), sync_counters(n, k), stream, col0, cols);
 }

@@ -320,6 +320,15 @@ int64_t hia_sim_gemm_rows_workspace_bytes(int32_t n, int32_t k);
 int hia_sim_gemm_rows(void* hi, void* lo, int precision, int32_t plane_rows, int32_t n, int32_t k,
                       int32_t row0, int32_t rows, float* out_rows, int64_t ld_out, int flavour,
                       int32_t k_chunk, void* workspace, int64_t workspace_bytes, void* stream);
+/* The same for the column range [col0, col0 + cols) of the row block only (col0 % 256 == 0,
+ * col0 + cols <= n). For the ring schedule of the row-sharded contraction (sharded.py): the planes
+ * of the own rows and of one peer block are stacked in one buffer and `out_rows` is passed
+ * column-shifted, so each unordered pair of row blocks is contracted once while the next peer's
+ * planes are in flight. */
+int hia_sim_gemm_rows_cols(void* hi, void* lo, int precision, int32_t plane_rows, int32_t n, int32_t k,
+                           int32_t row0, int32_t rows, int32_t col0, int32_t cols, float* out_rows,
+                           int64_t ld_out, int flavour, int32_t k_chunk, void* workspace,
+                           int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
 /* a9  top-k eigenvectors of a dense symmetric fp32 matrix (largest algebraic).          */

@@ -11,7 +11,7 @@ import torch.distributed as dist
 
 from hiarch_b200 import dist as D
 from hiarch_b200 import ops
-from hiarch_b200.sharded import ShardedSimilarity, topk_eig_rows, obs_d_exp_rows, rows_per_rank
+from hiarch_b200.sharded import RingSimilarity, ShardedSimilarity, topk_eig_rows, obs_d_exp_rows, rows_per_rank
 from hiarch_b200 import synth
 
 
@@ -30,6 +30,12 @@ def main():
     mine = sh.run(x[sh.row0:sh.row0 + sh.rows])
     ref_rows = full[sh.row0:sh.row0 + sh.rows]
     sim_err = float((mine - ref_rows).abs().max()) if sh.rows else 0.0
+    ring_err = None
+    if os.environ.get("HIA_TEST_RING") == "1":          # opt-in until the ring path has run once on GPUs
+        ring = RingSimilarity(n, n, flavour=ops.SIM_PEARSON)
+        ring_rows = ring.run(x[ring.row0:ring.row0 + ring.rows])
+        torch.cuda.synchronize()
+        ring_err = float((ring_rows - ref_rows).abs().max()) if ring.rows else 0.0
     w1, v1, _ = ops.topk_eig(full, k=3, return_info=True)
     w2, v2, info = topk_eig_rows(mine, n, k=3)
     cos = [float(abs((v1[:, j].double() @ v2[:, j].double())) / (v1[:, j].double().norm() * v2[:, j].double().norm()))
@@ -55,7 +61,7 @@ def main():
     oe_err = float((got_oe - ref_oe[r0:r0 + nr]).abs().max()) if nr else 0.0
     rec = {"rank": rank, "world": world, "rows": [sh.row0, sh.rows], "sim_err": sim_err, "oe_err": oe_err,
            "eig_rel": float(((w1 - w2).abs() / w1.abs()).max()), "cos": cos, "info": info,
-           "restart_rel": restart_rel, "restart_cycles": restart_cycles}
+           "restart_rel": restart_rel, "restart_cycles": restart_cycles, "ring_err": ring_err}
     D.barrier()
     sys.stdout.write("REC " + json.dumps(rec) + "\n")
     sys.stdout.flush()

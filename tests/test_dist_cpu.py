@@ -63,3 +63,41 @@ def test_parallel_func_sharding_without_gpu(tmp_path):
     cap = CaptureParas()
     cap.write("#para-near_num: 12\nnoise\n")
     assert cap.paras == {"near_num": "12"}
+
+
+def test_ring_schedule_covers_every_block_pair_once():
+    from hiarch_b200.sharded import ring_schedule
+    for world in range(1, 10):
+        steps = ring_schedule(world)
+        assert len(steps) == world // 2 + 1
+        pairs = [tuple(sorted(p)) for st in steps for p in st]
+        assert sorted(pairs) == sorted((a, b) for a in range(world) for b in range(a, world))   # once each
+        per_rank = [sum(1 for st in steps for (r, _) in st if r == k) for k in range(world)]
+        assert max(per_rank) - min(per_rank) <= 1                                             # balanced
+        assert max(per_rank) == world // 2 + 1
+
+
+def _run_ring(world, n, k, port):
+    import json
+    import re
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "ring_cpu_worker.py"), str(n), str(k)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    recs = [json.loads(m) for m in re.findall(r"REC (\{.*?\})(?=\s|REC|$)", out.stdout)]
+    assert len(recs) == world
+    return sorted(recs, key=lambda r: r["rank"])
+
+
+def test_ring_similarity_exchange_logic_on_gloo():
+    """RingSimilarity's schedule / plane exchange / mirrored-block return with a torch stand-in for
+    the kernels: every rank ends up with exactly its rows of the full Pearson matrix (ragged and
+    empty last blocks included), having contracted only world/2 + 1 blocks."""
+    for world, n, port in ((2, 200, 29621), (3, 300, 29622), (4, 400, 29623), (4, 300, 29624)):
+        recs = _run_ring(world, n, 24, port)
+        assert sum(r["rows"] for r in recs) == n
+        for r in recs:
+            assert r["nan"] == 0, r                              # every column block was filled
+            assert r["err"] < 1e-12, r
+            assert r["blocks"] == r["expected_blocks"] and len(r["blocks"]) <= world // 2 + 1

@@ -21,7 +21,7 @@ import torch.distributed as dist
 
 from hiarch_b200 import dist as D
 from hiarch_b200 import ops, synth
-from hiarch_b200.sharded import ShardedSimilarity, topk_eig_rows
+from hiarch_b200.sharded import RingSimilarity, ShardedSimilarity, topk_eig_rows
 
 
 def make_rows(n, row0, rows, seed, device, chunk=2048):
@@ -99,6 +99,9 @@ def main():
     ap.add_argument("--bins", type=int, default=0, help="override the bin count")
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--no-eig", action="store_true")
+    ap.add_argument("--ring", action="store_true",
+                    help="also time RingSimilarity (symmetric ring schedule, plane exchange hidden behind the "
+                         "contraction) and compare its rows with the all-gather path")
     args = ap.parse_args()
     # a rank that dies must not leave the others in a 10-minute NCCL watchdog wait
     os.environ.setdefault("TORCH_NCCL_HEARTBEAT_TIMEOUT_SEC", "120")
@@ -168,19 +171,39 @@ def main():
         ref = 1.0 if (sh.row0 + i) == j else max(-1.0, min(1.0, ref))
         errs.append(abs(float(out[i, j]) - ref))
     err = D.max_over_ranks(max(errs) if errs else 0.0)
+    meta = {"per": sh.per, "kpad": sh.kpad, "elem": sh.hi.element_size(), "prec": sh.precision}
+    ring_ms, ring_diff = None, None
+    if args.ring:
+        del sh.hi, sh.lo, sh.own_hi, sh.own_lo              # make room: the ring keeps its own (smaller) buffers
+        torch.cuda.empty_cache()
+        ring = RingSimilarity(n, n, flavour=ops.SIM_PEARSON)
+        out2 = torch.empty((max(ring.rows, 1), ops.padded_ld(n)), dtype=torch.float32, device=dev)[:ring.rows, :n]
+        rt = []
+        for it in range(args.steps + 1):
+            D.barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            ring.run(x, out_rows=out2)
+            r1.record()
+            D.barrier()
+            if it > 0:
+                rt.append(D.max_over_ranks(r0.elapsed_time(r1)))
+        ring_ms = float(np.mean(rt))
+        ring_diff = D.max_over_ranks(float((out2 - out).abs().max()) if ring.rows else 0.0)
     if rank == 0:
         sim = float(np.mean(times["similarity"]))
         eig = float(np.mean(times["eig"]))
         cells = float(n) * n
         rec = {"workload": f"row-sharded Pearson + top-3 eigvec, {n} bins ({cells:.3g} cells), {world} GPUs",
-               "n_gpus": world, "bins": n, "rows_per_rank": sh.per,
+               "n_gpus": world, "bins": n, "rows_per_rank": meta["per"],
                "oe_log_ms": (oe_ms[-1] if oe_ms else None),
                "similarity_ms": sim, "eig_ms": eig,
                "cells_per_s": cells / ((sim + eig + (oe_ms[-1] if oe_ms else 0.0)) * 1e-3),
-               "precision": {0: "tf32x3", 2: "f16x3"}[sh.precision],
-               "executed_mma_tflops_per_gpu": 3 * 2 * float(sh.per) * n * n / (sim * 1e-3) / 1e12,
-               "allgather_bytes_per_rank": 2 * (world - 1) * sh.per * sh.kpad * sh.hi.element_size(),
-               "max_abs_err_vs_fp64_spotcheck": err}
+               "precision": {0: "tf32x3", 2: "f16x3"}[meta["prec"]],
+               "executed_mma_tflops_per_gpu": 3 * 2 * float(meta["per"]) * n * n / (sim * 1e-3) / 1e12,
+               "allgather_bytes_per_rank": 2 * (world - 1) * meta["per"] * meta["kpad"] * meta["elem"],
+               "max_abs_err_vs_fp64_spotcheck": err,
+               "ring_similarity_ms": ring_ms, "ring_vs_allgather_max_abs_diff": ring_diff}
         if not args.no_eig:
             rec["eigvals"] = [float(t) for t in w.cpu().numpy()]
             rec["eig_info"] = info

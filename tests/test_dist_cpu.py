@@ -109,3 +109,17 @@ def test_ring_similarity_exchange_logic_on_gloo():
             assert r["nan"] == 0, r                              # every column block was filled
             assert r["err"] < 1e-12, r
             assert r["blocks"] == r["expected_blocks"] and len(r["blocks"]) <= world // 2 + 1
+
+
+def test_ring_similarity_single_process():
+    """world = 1 (no process group): the schedule degenerates to the diagonal block."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from ring_cpu_worker import CpuRing
+    rng = np.random.default_rng(1)
+    x = torch.from_numpy(rng.standard_normal((150, 40)))
+    ring = CpuRing(150, 40)
+    out = ring.run(x)
+    xc = x - x.mean(dim=1, keepdim=True)
+    xc = xc / xc.norm(dim=1, keepdim=True)
+    assert ring.blocks_done == [0] and float((out - xc @ xc.t()).abs().max()) < 1e-12

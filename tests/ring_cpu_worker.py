@@ -46,7 +46,14 @@ class CpuRing(sharded.RingSimilarity):
         col0 = 0 if diagonal else self.per_pad
         a = self.hi[b][:self.rows]
         bb = self.hi[b][col0:col0 + cols]
-        out_rows[:, peer * self.per:peer * self.per + cols] = a @ bb.t()
+        # store exactly like the kernel behind RingSimilarity._block: element (r, gc) of the stacked
+        # problem, gc in [col0, col0 + cols), goes to base[(r - row0) * ld + gc] where `base` is the
+        # output pointer shifted by (peer * per - col0) columns
+        flat, ld = out_rows.view(-1), out_rows.stride(0)
+        shift = peer * self.per - col0
+        idx = shift + torch.arange(self.rows)[:, None] * ld + torch.arange(col0, col0 + cols)[None, :]
+        assert int(idx.min()) >= 0 and int(idx.max()) < flat.numel()
+        flat[idx.reshape(-1)] = (a @ bb.t()).reshape(-1)
 
     def _new_out(self):
         return torch.full((self.rows, self.n), float("nan"), dtype=torch.float64)

@@ -183,8 +183,8 @@ class RingSimilarity:
                            device=self.device)[:self.rows, :self.n]
 
     def _side(self):
-        """Context + handle of the stream the exchanges are issued on."""
-        return torch.cuda.stream(self.comm_stream), self.comm_stream
+        """(factory of a fresh context, handle) of the stream the plane exchanges are issued on."""
+        return (lambda: torch.cuda.stream(self.comm_stream)), self.comm_stream
 
     def _fence(self, stream):
         """`stream` waits for everything issued so far on the current stream (and vice versa with
@@ -222,7 +222,7 @@ class RingSimilarity:
             if self._computes(t, r):
                 recvs += [(p[:self.per], src) for p in self._peer_slots(b)]
             self._fence(side)                             # the slot's previous user (step t - 2) is done
-            with side_ctx:
+            with side_ctx():
                 return self._exchange(sends, recvs)
 
         if len(self.steps) > 1:

@@ -59,7 +59,7 @@ class CpuRing(sharded.RingSimilarity):
         return torch.full((self.rows, self.n), float("nan"), dtype=torch.float64)
 
     def _side(self):
-        return contextlib.nullcontext(), None
+        return contextlib.nullcontext, None
 
     def _fence(self, stream):
         pass

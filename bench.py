@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--precision", default="f16x3", choices=["f16x3", "tf32x3"],
                     help="operand split of the Pearson contraction (both carry 22 significant bits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-checks", action="store_true", help="skip the in-run fp64 parity checks")
+    ap.add_argument("--no-row-sharded", action="store_true", help="N > 1: skip the row-sharded genome-wide chain")
+    ap.add_argument("--row-sharded-res", type=int, default=0,
+                    help="bin size of the row-sharded chain (default: 50 kb at 2 GPUs, 25 kb at 4 / 8)")
     ap.add_argument("--cpu-sample-chroms", default="chr16,chr17,chr18,chr19,chr20,chr21,chr22")
     return ap.parse_args()
 
@@ -100,6 +104,13 @@ def blas_threads():
         return os.cpu_count()
 
 
+def all_host_cores():
+    """Context manager: BLAS on every host core, whatever the launcher exported (torchrun sets
+    OMP_NUM_THREADS=1 for N > 1, which round 1's reference arm silently inherited)."""
+    from threadpoolctl import threadpool_limits
+    return threadpool_limits(limits=os.cpu_count(), user_api="blas")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -108,25 +119,27 @@ def run_reference(args):
     n = dense.shape[0]
     from hiarch_b200 import synth
     n_full = sum(nb for _, nb in synth.hg38_bins(args.res)[: args.chroms])
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_step(dense, seps, args.res)
-    t0 = time.perf_counter()
     steps = max(1, args.steps)
-    for _ in range(steps):
-        cpu_step(dense, seps, args.res)
-    dt = (time.perf_counter() - t0) / steps
+    with all_host_cores():
+        cores = blas_threads()
+        for _ in range(max(0, args.warmup)):
+            cpu_step(dense, seps, args.res)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_step(dense, seps, args.res)
+        dt = (time.perf_counter() - t0) / steps
     value = n * n / dt
     sample = (f"{'+'.join(chroms)} at {args.res // 1000} kb = {n} bins ({n * n:.3g} cells) per step; "
               "O/E+log numpy per-diagonal loops 1 thread, Pearson GEMM (BLAS, all threads) + ARPACK eigsh(k=3)")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "impl": "reference",
         "config": {"workload": workload_name(args, n_full),
                    "bins": n_full, "chromosomes": args.chroms,
                    "sample": f"each step = a bounded sample of that workload: {n} bins ({'+'.join(chroms)})"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -183,6 +196,198 @@ class Clocks:
                 "sm_max_mhz": float(max(smax)) if smax else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
+
+
+# --------------------------------------------------------------------------------------------
+# in-run checks, the like-for-like sample, the row-sharded chain
+# --------------------------------------------------------------------------------------------
+def parity_checks(hp, rows, cols, vals, w_h, v_h, stripe=384):
+    """Asserted on every rank after the timed steps (state of the last step):
+      scatter  bit-exact against a torch index_put of the same COO (sampled rows);
+      O/E+log  one inter-chromosome block against  ln(1 + v / mean(non-zero))  in fp64 (<= 1e-5);
+      Pearson  a `stripe`-row stripe against fp64 centred / normalised dot products (<= 1e-5);
+      eigen    ||C u - lambda u|| / lambda_1 and orthonormality of the returned vectors in fp64.
+    The oracle comparisons proper (incl. the intra-chromosome SGD pooling) are tests/."""
+    import torch
+    n = hp.n
+    dev = hp.raw.device
+    out = {}
+    g = torch.Generator(device="cpu")
+    g.manual_seed(11)
+    # scatter: rows r0..r0+255 of the dense map rebuilt from the COO
+    r0 = int(torch.randint(0, max(1, n - 256), (1,), generator=g))
+    sel = (rows >= r0) & (rows < r0 + 256)
+    ref = torch.zeros((256, n), dtype=torch.float32, device=dev)
+    ref.index_put_(((rows[sel] - r0).long(), cols[sel].long()), vals[sel], accumulate=True)
+    got = hp.raw[r0:r0 + 256]
+    cmask = torch.arange(n, device=dev)[None, :] >= (torch.arange(256, device=dev) + r0)[:, None]
+    out["scatter_upper_mismatches"] = int(((got != ref) & cmask).sum())
+    out["scatter_symmetry_mismatches"] = int((hp.raw[r0:r0 + 256, r0:r0 + 256] != hp.raw[r0:r0 + 256, r0:r0 + 256].t()).sum())
+    assert out["scatter_upper_mismatches"] == 0 and out["scatter_symmetry_mismatches"] == 0, out
+    # O/E + log on the inter block (chr 1 rows, last chromosome's columns)
+    (s1, e1), (s2, e2) = hp.layout.seps[0], hp.layout.seps[-1]
+    if len(hp.layout.seps) > 1:
+        blk = hp.raw[s1:e1 + 1, s2:e2 + 1].double()
+        nz = blk != 0
+        ref_oe = torch.log1p(blk / (blk.sum() / nz.sum()))
+        got_oe = hp.oe[s1:e1 + 1, s2:e2 + 1].double()
+        out["oe_inter_block_max_abs_err"] = float((got_oe - ref_oe)[blk > 0].abs().max())
+        assert out["oe_inter_block_max_abs_err"] <= 1e-5, out
+    # Pearson stripe in fp64
+    q0 = int(torch.randint(0, max(1, n - stripe), (1,), generator=g))
+    def unit(a):
+        a = a - a.mean(dim=1, keepdim=True)
+        return a / a.norm(dim=1, keepdim=True)
+    a = unit(hp.oe[q0:q0 + stripe].double())
+    err = 0.0
+    for c0 in range(0, n, 4096):
+        b = unit(hp.oe[c0:c0 + 4096].double())
+        ref_c = (a @ b.t()).clamp(-1.0, 1.0)
+        got_c = hp.sim[q0:q0 + stripe, c0:c0 + 4096].double()
+        ii = torch.arange(q0, q0 + a.shape[0], device=dev)[:, None]
+        jj = torch.arange(c0, c0 + b.shape[0], device=dev)[None, :]
+        ref_c = torch.where(ii == jj, torch.ones_like(ref_c), ref_c)
+        err = max(err, float((got_c - ref_c).abs().max()))
+    out["pearson_stripe_rows"] = int(a.shape[0])
+    out["pearson_stripe_max_abs_err"] = err
+    assert err <= 1e-5, out
+    # eigenpairs: residual against the GPU's own C in fp64, row block by row block
+    v = torch.from_numpy(np.ascontiguousarray(v_h)).to(dev).double()
+    lam = torch.from_numpy(np.ascontiguousarray(w_h)).to(dev).double()
+    cu = torch.empty_like(v)
+    for c0 in range(0, n, 4096):
+        cu[c0:c0 + 4096] = hp.sim[c0:c0 + 4096].double() @ v
+    res = (cu - v * lam[None, :]).norm(dim=0) / lam[0].abs()
+    gram = v.t() @ v
+    out["eig_rel_residual_max"] = float(res.max())
+    out["eig_orthonormality_err"] = float((gram - torch.eye(v.shape[1], device=dev, dtype=torch.float64)).abs().max())
+    gaps = (lam[:-1] - lam[1:]).abs().min() if lam.numel() > 1 else lam[0].abs()
+    # sin(angle to the true eigenvector) <= residual / gap; |cos| >= 0.9999 <=> sin <= 1.4e-2
+    out["eig_angle_bound"] = float((res * lam[0].abs()).max() / gaps)
+    assert out["eig_angle_bound"] <= 1.4e-2 and out["eig_orthonormality_err"] <= 1e-5, out
+    return out
+
+
+def gpu_on_sample(args, dense_host, seps, prec, steps=5, warmup=3):
+    """The GPU arm on the CPU baseline's own bounded sample (same map, same chain)."""
+    import torch
+    from hiarch_b200.pipeline import HotPath
+    up = np.triu(dense_host)
+    r, c = np.nonzero(up)
+    rows = torch.from_numpy(r.astype(np.int32)).cuda()
+    cols = torch.from_numpy(c.astype(np.int32)).cuda()
+    vals = torch.from_numpy(up[r, c].astype(np.float32)).cuda()
+    nnz, n = rows.numel(), dense_host.shape[0]
+    hp = HotPath(seps, args.res, k_eig=3, max_nnz=nnz, precision=prec)
+    rows_h, cols_h, vals_h = (t.cpu().pin_memory() for t in (rows, cols, vals))
+    for _ in range(warmup):
+        hp.run_device(rows, cols, vals)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        hp.run_device(rows, cols, vals)
+    b.record()
+    torch.cuda.synchronize()
+    dev_ms = a.elapsed_time(b) / steps
+    for _ in hp.run_host_many([(rows_h, cols_h, vals_h)] * 2):
+        pass
+    torch.cuda.synchronize()
+    a.record()
+    for _ in hp.run_host_many([(rows_h, cols_h, vals_h)] * steps):
+        pass
+    b.record()
+    torch.cuda.synchronize()
+    e2e_ms = a.elapsed_time(b) / steps
+    return {"gpu_ms_per_step": dev_ms, "gpu_cells_per_s": n * n / (dev_ms * 1e-3),
+            "gpu_e2e_ms_per_step": e2e_ms, "gpu_e2e_cells_per_s": n * n / (e2e_ms * 1e-3)}
+
+
+def run_row_sharded(args, world, rank, local, pk, steps=2):
+    """N > 1: ONE fixed genome-wide map row-sharded over the N ranks (BASELINE.json config C5 at 4 / 8
+    GPUs: 25 kb, 123 541 bins; 50 kb, 61 775 bins at 2 GPUs): synthetic count rows -> row-sharded
+    O/E + log (all-reduce of the diagonal statistics) -> Pearson by the symmetric ring over peer
+    memory (copy-engine plane pulls + P2P stores of the mirrored blocks) -> top-3 eigenvectors
+    (all-gather of the n x 8 panel per Lanczos step). Strong scaling: total work is fixed."""
+    import torch
+    import torch.distributed as dist
+    from hiarch_b200 import synth
+    from hiarch_b200.sharded import RowShardedPath
+
+    res = args.row_sharded_res or (50000 if world == 2 else 25000)
+    lens = [nb for _, nb in synth.hg38_bins(res)]
+    n = sum(lens)
+    dev = torch.device("cuda", local)
+
+    def mx(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    path_kind, ipc_error = "ring over peer memory (CUDA IPC + copy-engine pulls + P2P mirrored stores)", None
+    try:
+        path = RowShardedPath(synth.chr_seps_from_lens(lens), res, k_eig=3, ring=True)
+        ok = 1
+    except Exception as e:                                   # peer mapping unavailable on this box
+        ipc_error, ok = repr(e)[:300], 0
+    t = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if int(t.item()) == 0:
+        path_kind = "NCCL all-gather of the planes (peer mapping unavailable)"
+        path = RowShardedPath(synth.chr_seps_from_lens(lens), res, k_eig=3, ring=False)
+    counts, _ = synth.device_count_rows(lens, path.row0, path.rows, 5, dev)
+    oe_rows = torch.empty((max(path.rows, 1), counts.stride(0)), dtype=torch.float32, device=dev)[:path.rows, :n]
+    ms = {"oe_log": [], "similarity": [], "eig": [], "total": []}
+    info = None
+    for it in range(steps + 1):                              # first iteration = warm-up
+        barrier()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record()
+        path.normalise(counts, out_rows=oe_rows)
+        e[1].record()
+        path.similarity(timing=path.ring)
+        e[2].record()
+        w, v, info = path.eigen()
+        e[3].record()
+        barrier()
+        if it > 0:
+            for key, (i, j) in (("oe_log", (0, 1)), ("similarity", (1, 2)), ("eig", (2, 3)), ("total", (0, 3))):
+                ms[key].append(mx(e[i].elapsed_time(e[j])))
+    ring_stats = path.sim.collect_stats() if path.ring else {}
+    err, cnt = path.spot_check_fp64(n_own=16, n_other=64)
+    # eigen residual of the sharded result: || C[rows, :] u - lambda u[rows] ||, all-reduced
+    vv = v.double()
+    lam = w.double()
+    cu = path.sim_rows.double() @ vv if path.rows * n <= 2 ** 31 else torch.cat(
+        [path.sim_rows[i:i + 2048].double() @ vv for i in range(0, path.rows, 2048)])
+    r2 = ((cu - vv[path.row0:path.row0 + path.rows] * lam[None, :]) ** 2).sum(dim=0)
+    dist.all_reduce(r2)
+    eig_res = float((r2.sqrt() / lam[0].abs()).max())
+    exposed = mx(ring_stats.get("exposed_wait_ms", 0.0))
+    sim_ms = float(np.mean(ms["similarity"]))
+    total_ms = float(np.mean(ms["total"]))
+    blocks = ring_stats.get("block_products", float(world))
+    flop_exec = 3 * 2.0 * blocks * path.per * path.per * n          # executed MMA flops of this rank
+    rec = {"workload": f"genome-wide human {res // 1000} kb ({n} bins, {float(n) * n:.3g} cells) row-sharded over "
+                       f"{world} GPUs: count rows -> O/E+log -> Pearson -> top-3 eigvec",
+           "scaling": "strong", "bins": n, "rows_per_rank": path.per, "path": path_kind, "peer_mapping_error": ipc_error,
+           "ms": {k: float(np.mean(v_)) for k, v_ in ms.items()},
+           "cells_per_s": float(n) * n / (total_ms * 1e-3),
+           "similarity": {"block_products_per_rank": blocks, "block_ms": ring_stats.get("block_ms"),
+                          "executed_mma_tflops_per_gpu": flop_exec / (sim_ms * 1e-3) / 1e12,
+                          "plane_bytes_pulled_per_rank": ring_stats.get("pulled_bytes"),
+                          "p2p_store_bytes_per_rank": ring_stats.get("p2p_store_bytes"),
+                          "exposed_comm_ms": exposed,
+                          "note": "exposed_comm_ms = time the compute stream waited for a plane pull (max over "
+                                  "ranks, last timed step); the pulls run on copy engines behind the previous block"},
+           "fp64_spot_check": {"entries": cnt, "max_abs_err": err},
+           "eig": {"eigvals": [float(x) for x in w.cpu().numpy()], "cycles": info, "rel_residual_max": eig_res}}
+    assert err <= 1e-5, rec
+    return rec
 
 # --------------------------------------------------------------------------------------------
 # our arm
@@ -289,10 +494,22 @@ def run_ours(args):
     barrier()
     e2e_serial_ms = max_over_ranks(t0s.elapsed_time(t1s))
 
+    # ---- in-run parity checks on the state of the last step (torch fp64 on the device; the oracle
+    # comparisons proper live in tests/): a bench line of a wrong result is worthless
+    checks = parity_checks(hp, rows, cols, vals, w_h, v_h) if not args.no_checks else None
+
+    # ---- the row-sharded genome-wide chain (the one path with an exchange step), all ranks ------
+    row_sharded = None
+    if world > 1 and not args.no_row_sharded:
+        del hp, rows, cols, vals, rows_h, cols_h, vals_h
+        torch.cuda.empty_cache()
+        row_sharded = run_row_sharded(args, world, rank, local, pk)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    plane_elem_bytes = 2 if args.precision == "f16x3" else 4
 
     # ---- roofline of the dominant kernel (syrk_split3_kernel) ----------------------------------
     # algorithmic flops per launch: N^2 * K multiply-adds counted as the symmetric half,
@@ -310,20 +527,29 @@ def run_ours(args):
     kind = "fp16" if args.precision == "f16x3" else "TF32"
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_logical, "unit": "TFLOP/s",
                 "frac": achieved / peak_logical, "traffic": traffic,
+                "traffic_source": (f"profiles/{os.path.basename(tpath)}: dram__bytes_read.sum + dram__bytes_write.sum of "
+                                   "one ncu --set full capture of this kernel on this workload (not an in-run counter)")
+                if traffic is not None else None,
                 "frac_of_burst_peak": achieved / (pk["bf16_tflops"] / rate_div / 3.0),
                 "kernel": f"syrk_split3_kernel<{args.precision}>", "ms_per_launch": gemm,
                 "note": ("achieved = N^3 logical flops (upper-triangle SYRK) / CUDA-event time of the "
                          f"kernel; peak = bf16_tflops_sustained{'' if rate_div == 1 else '/2'} ({kind} dense) "
                          f"/3 (3-term split), {pk_src}; executed {kind} rate = {3 * achieved:.1f} TFLOP/s")}
 
-    cpu_baseline = None
+    cpu_baseline, same_sample = None, None
     if not args.no_cpu_baseline:
         d_cpu, seps_cpu, chroms_cpu = cpu_sample(args)
-        t0c = time.perf_counter()
-        cpu_step(d_cpu, seps_cpu, args.res)
-        dtc = time.perf_counter() - t0c
+        with all_host_cores():
+            cores = blas_threads()
+            t0c = time.perf_counter()
+            cpu_step(d_cpu, seps_cpu, args.res)
+            dtc = time.perf_counter() - t0c
         nc = d_cpu.shape[0]
-        cpu_baseline = {"value": nc * nc / dtc, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+        # the GPU arm on the SAME bounded sample (device-resident and end to end): one like-for-like pair
+        same_sample = gpu_on_sample(args, d_cpu, seps_cpu, prec)
+        same_sample.update({"bins": nc, "chroms": "+".join(chroms_cpu), "cpu_cells_per_s": nc * nc / dtc,
+                            "cpu_cores": cores})
+        cpu_baseline = {"value": nc * nc / dtc, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": (f"{'+'.join(chroms_cpu)} at {args.res // 1000} kb = {nc} bins, "
                                    f"{dtc:.1f} s: oracle port (numpy restatement of the reference; "
                                    "O/E numpy per-diagonal loops 1 thread, Pearson GEMM on all BLAS threads, ARPACK eigsh(k=3))")}
@@ -336,7 +562,7 @@ def run_ours(args):
         "config": {"workload": workload_name(args, n),
                    "bins": n, "nnz_upper": nnz, "chromosomes": len(lens),
                    "l2": "inputs (>=0.9 GB) exceed the 126 MB L2; no explicit flush",
-                   "sharding": "samples by rank, no collective"},
+                   "sharding": "samples by rank, no collective (the row_sharded sub-record is the path with an exchange)"},
         "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": world * cells / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 12 * nnz, "d2h_bytes_per_step": 3 * 8 + 3 * n * 4,
@@ -350,11 +576,19 @@ def run_ours(args):
             "scatter": {"bytes": 12 * nnz + 4 * cells, "gbs": (12 * nnz + 4 * cells) / scat / 1e6,
                         "frac": (12 * nnz + 4 * cells) / scat / 1e6 / pk["hbm_gbs"]},
             "oe_log": {"bytes": 10 * cells, "gbs": 10 * cells / oe_ms / 1e6, "frac": 10 * cells / oe_ms / 1e6 / pk["hbm_gbs"]},
-            "similarity_prep": {"bytes": (4 + 2 * hp.plane_elem_bytes) * cells,
-                                "gbs": (4 + 2 * hp.plane_elem_bytes) * cells / prep / 1e6,
-                                "frac": (4 + 2 * hp.plane_elem_bytes) * cells / prep / 1e6 / pk["hbm_gbs"]}},
+            "similarity_prep": {"bytes": (4 + 2 * plane_elem_bytes) * cells,
+                                "gbs": (4 + 2 * plane_elem_bytes) * cells / prep / 1e6,
+                                "frac": (4 + 2 * plane_elem_bytes) * cells / prep / 1e6 / pk["hbm_gbs"]},
+            "all_three": {"bytes": 12 * nnz + (4 + 10 + 4 + 2 * plane_elem_bytes) * cells,
+                          "gbs": (12 * nnz + (18 + 2 * plane_elem_bytes) * cells) / (scat + oe_ms + prep) / 1e6,
+                          "frac": (12 * nnz + (18 + 2 * plane_elem_bytes) * cells) / (scat + oe_ms + prep) / 1e6
+                          / pk["hbm_gbs"]}},
         "eigvals": [float(x) for x in w_h],
+        "checks": checks,
+        "same_sample": same_sample,
     }
+    if row_sharded is not None:
+        line["row_sharded"] = row_sharded
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -36,6 +36,7 @@ PROTOTYPES = {
                                           c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hia_oe_apply_rows": (c_int, [c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp,
                                   c_vp, c_int, c_vp]),
+    "hia_oe_apply_f64": (c_int, [c_vp, c_i32, c_i64, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "hia_log_map": (c_int, [c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp]),
     "hia_similarity_workspace_bytes": (c_i64, [c_i32, c_i32, c_int]),
     "hia_similarity": (c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_int, c_int, c_i32, c_i32,
@@ -73,8 +74,12 @@ PROTOTYPES = {
     "hia_sim_gemm_rows_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "hia_sim_gemm_rows": (c_int, [c_vp, c_vp, c_int, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_int,
                                   c_i32, c_vp, c_i64, c_vp]),
-    "hia_sim_gemm_rows_cols": (c_int, [c_vp, c_vp, c_int, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64,
-                                       c_int, c_i32, c_vp, c_i64, c_vp]),
+    "hia_sim_gemm_block": (c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_int, c_i32, c_i32, c_i32, c_i32, c_i32,
+                                   c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_i32, c_vp, c_i64, c_vp]),
+    "hia_ipc_export": (c_int, [c_vp, c_vp, c_vp]),
+    "hia_ipc_open": (c_int, [c_vp, c_vp]),
+    "hia_ipc_close": (c_int, [c_vp]),
+    "hia_peer_copy": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "hia_mtx_scan": (c_i64, [ctypes.c_char_p, c_i32, c_vp, c_vp, c_vp]),
     "hia_mtx_count_lines": (c_i64, [ctypes.c_char_p, c_i32]),
     "hia_mtx_parse": (c_int, [ctypes.c_char_p, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -34,7 +34,8 @@ inline int cuda_ok(cudaError_t e) {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-constexpr int kNumSMs = 148;   // B200
+// Streaming multiprocessors of the current device (148 on B200), queried once per process.
+int num_sms();
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

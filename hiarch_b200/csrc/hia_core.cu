@@ -17,6 +17,20 @@ int sel_aggregate() {
   const char* e = getenv("HIA_SEL_AGG");
   return !(e && e[0] == '0');
 }
+int num_sms() {
+  static int cached = 0;
+  int v = __atomic_load_n(&cached, __ATOMIC_RELAXED);
+  if (v == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+      (void)cudaGetLastError();
+      return 148;                       // B200; not cached, so a later call can still query
+    }
+    __atomic_store_n(&cached, v, __ATOMIC_RELAXED);
+  }
+  return v;
+}
 }  // namespace hia
 
 HIA_API uint64_t hia_launch_count(void) { return __atomic_load_n(&hia::g_launches, __ATOMIC_RELAXED); }

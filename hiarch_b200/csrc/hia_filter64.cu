@@ -356,8 +356,8 @@ HIA_API int hia_used_filter_f64(const float* x, int32_t rows, int32_t cols, int6
     const double q_hi = mid_vmax_per / 100.0, q_lo = (100.0 - mid_vmax_per) / 100.0;
     sel64_init_kernel<<<1, 256, 0, s>>>(st, n, q_hi, q_lo);
     HIA_LAUNCH_CHECK();
-    const int grid = (int)std::min<long long>(blocks, (long long)kNumSMs * 8);
-    const int pgrid = (int)std::min<long long>((n + 1023) / 1024, (long long)kNumSMs * 8);
+    const int grid = (int)std::min<long long>(blocks, (long long)num_sms() * 8);
+    const int pgrid = (int)std::min<long long>((n + 1023) / 1024, (long long)num_sms() * 8);
     const int aggregate = sel_aggregate();
     double* cand = filtered ? A : B;                     // the fp64 array that is free at this point
     constexpr int kCompactPass = 2;                      // 16 bits decided: sign, exponent, 4 mantissa bits

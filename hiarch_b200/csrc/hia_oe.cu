@@ -453,6 +453,34 @@ oe_apply_upper_kernel(const float* __restrict__ map, float* __restrict__ out, in
   }
 }
 
+// Raw O/E in fp64 (obs_d_exp without log at class level, new_hic_class.py:1263-1282): the fp32 map
+// holds 1e-5 absolute only up to ~50; this variant divides the (exact) fp32 counts by the fp64
+// expected vector / the fp64 mean of the non-zero cells like the reference and stores doubles.
+__global__ void __launch_bounds__(256)
+oe_apply_f64_kernel(const float* __restrict__ map, long long ld, double* __restrict__ out, long long ld_out, int n,
+                    const int* __restrict__ chr_start, int n_chr, const short* __restrict__ bin_chr,
+                    const double* __restrict__ expected, const double* __restrict__ inter_sum,
+                    const unsigned long long* __restrict__ inter_nnz, int only_intra) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int b = bin_chr[c];
+  for (int r = blockIdx.y; r < n; r += gridDim.y) {
+    const int a = bin_chr[r];
+    double v = (double)map[(long long)r * ld + c];
+    if (a == b) {
+      const double ex = expected[chr_start[a] + abs(c - r)];
+      if (ex > 0.0) v = v / ex;                                          // exp <= 0: skipped (:1264)
+    } else if (only_intra) {
+      v = 0.0;
+    } else {
+      const int u = (a < b) ? a * n_chr + b : b * n_chr + a;            // statistics live in the upper block
+      const unsigned long long cnt = inter_nnz[u];
+      if (cnt > 0) v = v / (inter_sum[u] / (double)cnt);                // / mean(non-zero) (:1278-1280)
+    }
+    out[(long long)r * ld_out + c] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Stand-alone ArrayHiCMtx.log (new_hic_class.py:2076-2094) for maps that did not come out of
 // hia_oe_apply: pass 1 = min positive value, pass 2 = x>0 ? ln(x+1) : ln(min_pos + 1).
@@ -495,7 +523,7 @@ HIA_API int hia_log_map(const float* x, float* out, int32_t rows, int32_t cols, 
   init_min_kernel<<<1, 1, 0, stream>>>(min_pos_ws);
   HIA_LAUNCH_CHECK();
   const long long total = (long long)rows * cols;
-  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
   min_pos_kernel<<<grid, 256, 0, stream>>>(x, rows, cols, ld, min_pos_ws);
   HIA_LAUNCH_CHECK();
   log_apply_kernel<<<grid, 256, 0, stream>>>(x, out, rows, cols, ld, min_pos_ws);
@@ -632,4 +660,21 @@ HIA_API int hia_oe_apply_rows(const float* map_rows, float* out_rows, int32_t n,
                               const float* min_pos_oe, int flags, void* stream) {
   return apply_impl(map_rows, out_rows, n, ld, chr_start, n_chr, bin_chr, inv_expected, inter_inv,
                     min_pos_oe, flags, row0, rows, stream);
+}
+
+HIA_API int hia_oe_apply_f64(const float* map, int32_t n, int64_t ld, double* out, int64_t ld_out,
+                             const int32_t* chr_start, int32_t n_chr, const int16_t* bin_chr,
+                             const double* expected, const double* inter_sum, const int64_t* inter_nnz,
+                             int flags, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!map || !out || !chr_start || !bin_chr || !expected || !inter_sum || !inter_nnz || n <= 0 || n_chr <= 0 ||
+      ld < n || ld_out < n || (flags & (HIA_OE_LOG | HIA_OE_FROM_UPPER)))
+    return HIA_ERR_BAD_ARG;
+  dim3 grid((n + 255) / 256, min(n, 1024));
+  oe_apply_f64_kernel<<<grid, 256, 0, stream>>>(map, ld, out, ld_out, n, chr_start, n_chr, bin_chr, expected,
+                                                inter_sum, reinterpret_cast<const unsigned long long*>(inter_nnz),
+                                                (flags & HIA_OE_ONLY_INTRA) ? 1 : 0);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
 }

@@ -397,7 +397,7 @@ HIA_API int hia_scatter_coo_remap(const int32_t* rows, const int32_t* cols, cons
   if (mtx_type != HIA_MTX_TRIU && mtx_type != HIA_MTX_ALL) return HIA_ERR_BAD_ARG;
   HIA_CUDA(cudaMemset2DAsync(out, (size_t)ld * 4, 0, (size_t)n_out * 4, n_out, stream));
   if (nnz > 0) {
-    const int grid = (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (nnz + 255) / 256));
+    const int grid = (int)max((int64_t)1, min((int64_t)num_sms() * 16, (nnz + 255) / 256));
     scatter_remap_kernel<<<grid, 256, 0, stream>>>(rows, cols, vals, nnz, n_fine, index_map, mtx_type, out, ld);
     HIA_LAUNCH_CHECK();
     if (mtx_type == HIA_MTX_TRIU) {
@@ -418,7 +418,7 @@ HIA_API int hia_coo_block_nnz(const int32_t* rows, const int32_t* cols, const fl
   if (nnz > 0 && (!rows || !cols || !vals)) return HIA_ERR_BAD_ARG;
   HIA_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_chr * n_chr * 8, stream));
   if (nnz > 0) {
-    const int grid = (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (nnz + 255) / 256));
+    const int grid = (int)max((int64_t)1, min((int64_t)num_sms() * 16, (nnz + 255) / 256));
     coo_block_nnz_kernel<<<grid, 256, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, bin_chr, n_chr, counts);
     HIA_LAUNCH_CHECK();
   }
@@ -435,7 +435,7 @@ HIA_API int hia_coo_bin_sums(const int32_t* rows, const int32_t* cols, const flo
   if (mtx_type != HIA_MTX_TRIU && mtx_type != HIA_MTX_ALL) return HIA_ERR_BAD_ARG;
   HIA_CUDA(cudaMemsetAsync(bin_sum, 0, (size_t)n_out * 8, stream));
   if (nnz > 0) {
-    const int grid = (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (nnz + 255) / 256));
+    const int grid = (int)max((int64_t)1, min((int64_t)num_sms() * 16, (nnz + 255) / 256));
     coo_bin_sums_kernel<<<grid, 256, 0, stream>>>(rows, cols, vals, nnz, n_fine, index_map, mtx_type, bin_sum);
     HIA_LAUNCH_CHECK();
   }
@@ -482,7 +482,7 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
   if (n_chr > kMaxChr) return HIA_ERR_UNSUPPORTED;
 
   const int threads = 256;
-  const int grid_e = (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (nnz + threads - 1) / threads));
+  const int grid_e = (int)max((int64_t)1, min((int64_t)num_sms() * 16, (nnz + threads - 1) / threads));
   if (fill_mode == HIA_FILL_ZERO && workspace && nnz > 0 && aligned16(workspace) && aligned16(rows) &&
       aligned16(cols) && aligned16(vals)) {
     // sorted-row path, with the any-order kernels as a device-side fallback (flag)

@@ -354,7 +354,7 @@ HIA_API int hia_percentiles(const float* x, int32_t rows, int32_t cols, int64_t 
   sel_init_kernel<<<(kMaxRanks * kBins + 255) / 256, 256, 0, s>>>(st, n);
   HIA_LAUNCH_CHECK();
   const int gx = (cols + 4 * kSelThreads - 1) / (4 * kSelThreads);
-  const int gy = std::max(1, std::min(rows, (kNumSMs * 8 + gx - 1) / gx));
+  const int gy = std::max(1, std::min(rows, (num_sms() * 8 + gx - 1) / gx));
   const dim3 grid(gx, gy);
   const size_t sh_full = (size_t)kMaxRanks * kBins * 4;        // 64 KB
   // per call: the attribute belongs to the CURRENT device's copy of the function (a process may
@@ -401,7 +401,7 @@ HIA_API int hia_core_moments(const float* x, int32_t rows, int32_t cols, int64_t
   if (!aligned16(x) || (ld & 3)) return HIA_ERR_ALIGN;
   HIA_CUDA(cudaMemsetAsync(workspace6, 0, 6 * sizeof(double), s));
   const long long vec = (long long)rows * ((cols + 3) / 4);
-  const int grid = (int)std::min<long long>((vec + 255) / 256, (long long)kNumSMs * 8);
+  const int grid = (int)std::min<long long>((vec + 255) / 256, (long long)num_sms() * 8);
   moments_kernel<<<grid, 256, 0, s>>>(x, rows, cols, ld, vmin, vmax, workspace6);
   HIA_LAUNCH_CHECK();
   moments_finish_kernel<<<1, 32, 0, s>>>(workspace6, vmin, vmax, mean_std);

@@ -201,16 +201,39 @@ __host__ __device__ constexpr uint32_t idesc_of(int prec, int ctas) {
          ((uint32_t)((BM * ctas) >> 4) << 24);
 }
 
-struct TileCoord { int m0; int n0; };            // first row / first column of a TILE_M x BN tile
+struct TileCoord { int m0; int n0; };            // first A row / first B row of a TILE_M x BN tile
+
+// Everything the kernel needs besides the four tensor maps. A (rows of the output) and B (columns
+// of the output) may be DIFFERENT plane sets (row-sharded ring: A = own rows, B = a peer block
+// staged in local HBM); the tile coordinates are plane-row indices of A and of B.
+//   out  [(r - row0) * ld_out + (c - col0)]   direct store, r in [row0, row_end), c in [col0, col_end)
+//   out_t[(c - col0) * ld_t   + (r - row0)]   transposed store of the same cell (optional). In the
+//         symmetric single-map case out_t == out; in the ring it is the PEER GPU's row block
+//         (a P2P pointer: the mirrored half of the symmetric result travels over NVLink straight
+//         out of the epilogue, there is no separate exchange step).
+//   symmetric: A == B, only cells c >= r are produced directly and c > r transposed.
+//   has_diag : A and B index the same rows, cells with c == r get the exact constant.
+struct SyrkArgs {
+  const TileCoord* tiles;
+  int num_tiles, num_k_blocks, kb_per_chunk, flavour;
+  float* out;
+  long long ld_out;
+  float* out_t;
+  long long ld_t;
+  unsigned int* sync_ctr;
+  int sync_every, row0, row_end, col0, col_end, symmetric, has_diag;
+};
 
 // ------------------------------------------------------------------ the kernel
 template <int PREC, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                   const TileCoord* __restrict__ tiles, int num_tiles, int m, int num_k_blocks,
-                   int kb_per_chunk, float* __restrict__ out, long long ld_out, int flavour,
-                   unsigned int* __restrict__ sync_ctr, int sync_every, int row0, int row_end,
-                   int symmetric) {
+                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                   const SyrkArgs a) {
+  const TileCoord* __restrict__ tiles = a.tiles;
+  const int num_tiles = a.num_tiles, num_k_blocks = a.num_k_blocks, kb_per_chunk = a.kb_per_chunk;
+  const int flavour = a.flavour, sync_every = a.sync_every, symmetric = a.symmetric;
+  unsigned int* __restrict__ sync_ctr = a.sync_ctr;
   using G = Geo<CTAS>;
   constexpr int STAGES = G::STAGES;
   extern __shared__ unsigned char smem_raw[];
@@ -234,6 +257,8 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_b_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_b_lo) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -287,11 +312,11 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
           tma_load_2d<CTAS>(st, &map_hi, &full_bar[s], k0, m0);                               // A hi
           tma_load_2d<CTAS>(st + A_BYTES, &map_lo, &full_bar[s], k0, m0);                     // A lo
           unsigned char* sb = st + 2 * A_BYTES;
-          tma_load_2d<CTAS>(sb, &map_hi, &full_bar[s], k0, nb0);                              // B hi
-          tma_load_2d<CTAS>(sb + G::B_BYTES, &map_lo, &full_bar[s], k0, nb0);                 // B lo
+          tma_load_2d<CTAS>(sb, &map_b_hi, &full_bar[s], k0, nb0);                            // B hi
+          tma_load_2d<CTAS>(sb + G::B_BYTES, &map_b_lo, &full_bar[s], k0, nb0);               // B lo
           if constexpr (CTAS == 1) {                                                         // rows [128,256) of B
-            tma_load_2d<CTAS>(sb + A_BYTES, &map_hi, &full_bar[s], k0, nb0 + BM);
-            tma_load_2d<CTAS>(sb + G::B_BYTES + A_BYTES, &map_lo, &full_bar[s], k0, nb0 + BM);
+            tma_load_2d<CTAS>(sb + A_BYTES, &map_b_hi, &full_bar[s], k0, nb0 + BM);
+            tma_load_2d<CTAS>(sb + G::B_BYTES + A_BYTES, &map_b_lo, &full_bar[s], k0, nb0 + BM);
           }
         }
       }
@@ -367,14 +392,19 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         }
       }
       // ---- finalize + store (overlaps the next tile's MMAs)
-      const int gr_base = m0 + q * 32;                      // first global row of this warp
+      const int gr_base = m0 + q * 32;                      // first A row of this warp
       const float diag_val = (flavour == HIA_SIM_COSINE_DISTANCE) ? 0.f : 1.f;
+      float* __restrict__ out = a.out;
+      float* __restrict__ out_t = a.out_t;
+      const long long ld_out = a.ld_out, ld_t = a.ld_t;
+      const int row0 = a.row0, row_end = a.row_end, col0 = a.col0, col_end = a.col_end;
+      const int has_diag = a.has_diag;
 #pragma unroll
       for (int cg = 0; cg < BN / 64; ++cg) {
         const int gc_base = n0 + cg * 32;
         // symmetric: skip column groups entirely below the diagonal for this warp's rows
         const bool needed = symmetric ? (gc_base + 31 >= gr_base) : true;
-        if (needed && gr_base < m && gc_base < m) {
+        if (needed && gr_base < row_end && gc_base < col_end) {
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -384,24 +414,28 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             f[j] = (flavour == HIA_SIM_COSINE_DISTANCE) ? (1.f - c) : c;
           }
           const int gr = gr_base + lane;
-          if (symmetric) {
-            // mirrored store out[gc][gr] (lanes = consecutive gr -> coalesced)
+          if (out_t != nullptr && gr < row_end) {
+            // transposed store out_t[c][r] (lanes = consecutive r -> one 128-byte line per column)
+            float* tp = out_t + (long long)(gc_base - col0) * ld_t + (gr - row0);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int gc = gc_base + j;
-              if (gr < m && gc < m && gc > gr) out[(long long)gc * ld_out + gr] = f[j];
+              if (gc < col_end && (!symmetric || gc > gr)) tp[(long long)j * ld_t] = f[j];
             }
           }
-          // direct store out[gr][gc] through a 32x32 shared transpose (coalesced rows);
-          // row-block mode: every column, rows relative to the block's first row
+          // direct store out[r][c] through a 32x32 shared transpose (coalesced rows)
 #pragma unroll
           for (int j = 0; j < 32; ++j) trans[lane * TRANS_PAD + j] = f[j];
           __syncwarp();
+          const int gc = gc_base + lane;
+          if (gc < col_end) {
 #pragma unroll 4
-          for (int i = 0; i < 32; ++i) {
-            const int r = gr_base + i, gc = gc_base + lane;
-            if (r < row_end && gc < m && (gc >= r || !symmetric))
-              out[(long long)(r - row0) * ld_out + gc] = (gc == r) ? diag_val : trans[i * TRANS_PAD + lane];
+            for (int i = 0; i < 32; ++i) {
+              const int r = gr_base + i;
+              if (r < row_end && (gc >= r || !symmetric))
+                out[(long long)(r - row0) * ld_out + (gc - col0)] =
+                    (has_diag && gc == r) ? diag_val : trans[i * TRANS_PAD + lane];
+            }
           }
           __syncwarp();
         }
@@ -564,25 +598,68 @@ int make_plane_map(CUtensorMap* map, void* base, int rows, int kpad, int prec) {
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 inline bool split_prec(int p) { return p == HIA_PREC_3XTF32 || p == HIA_PREC_3XF16; }
 
-// Tiles (tile_m x BN) touching the upper triangle and the band, in 2048 x 2048 super-blocks for L2 reuse.
-int build_tiles(int m, int tile_m, int band_lo, int band_hi, TileCoord* dst) {
-  const int mt = (m + tile_m - 1) / tile_m, nt = (m + BN - 1) / BN;
-  const int SBM = 2048 / tile_m, SBN = 2048 / BN;
-  int cnt = 0;
-  for (int sm = 0; sm < mt; sm += SBM)
-    for (int sn = 0; sn < nt; sn += SBN)
-      for (int mi = sm; mi < min(sm + SBM, mt); ++mi)
-        for (int nj = sn; nj < min(sn + SBN, nt); ++nj) {
-          const long long r0 = (long long)mi * tile_m, r1 = min((long long)m, r0 + tile_m) - 1;
-          const long long c0 = (long long)nj * BN, c1 = min((long long)m, c0 + BN) - 1;
-          if (c1 < r0) continue;                         // entirely below the diagonal
-          // distance range of upper cells in the tile: [max(0, c0 - r1), c1 - r0]
-          const long long dmin = max(0ll, c0 - r1), dmax = c1 - r0;
-          if (band_hi >= 0 && (dmin > band_hi || dmax < band_lo)) continue;
-          if (dst) { dst[cnt].m0 = (int)r0; dst[cnt].n0 = (int)c0; }
-          ++cnt;
-        }
-  return cnt;
+// The tile list: tile_m x BN tiles of A rows [row0, row_end) x B rows [col0, col_end) in 2048 x 2048
+// super-blocks (concurrently running CTAs then share operand row blocks through L2). symmetric: only
+// tiles that touch the upper triangle and the requested |i - j| band are kept. The list is built ON
+// THE DEVICE (one CTA, ordered compaction): no pageable host -> device copy that would synchronise the
+// host with the stream on every call (and would make the call impossible to capture in a CUDA graph);
+// the host only COUNTS the tiles (same predicate) to size the grid.
+struct TileSpace {
+  int row0, row_end, col0, col_end, tile_m, symmetric, band_lo, band_hi;
+  __host__ __device__ int mt() const { return (row_end - row0 + tile_m - 1) / tile_m; }
+  __host__ __device__ int nt() const { return (col_end - col0 + BN - 1) / BN; }
+  __host__ __device__ int sbm() const { return 2048 / tile_m; }
+  __host__ __device__ int nsbn() const { return (nt() + 2048 / BN - 1) / (2048 / BN); }
+  __host__ __device__ int nsbm() const { return (mt() + sbm() - 1) / sbm(); }
+  __host__ __device__ long long candidates() const { return (long long)nsbm() * nsbn() * sbm() * (2048 / BN); }
+  // candidate c (super-block major, then row tile, then column tile) -> kept?, coordinates
+  __host__ __device__ bool tile(long long c, TileCoord* t) const {
+    const int SBN = 2048 / BN, per_sb = sbm() * SBN;
+    const int sb = (int)(c / per_sb), w = (int)(c % per_sb);
+    const int mi = (sb / nsbn()) * sbm() + w / SBN, nj = (sb % nsbn()) * SBN + w % SBN;
+    if (mi >= mt() || nj >= nt()) return false;
+    const int r0 = row0 + mi * tile_m, c0 = col0 + nj * BN;
+    if (symmetric) {
+      const int r1 = (r0 + tile_m < row_end ? r0 + tile_m : row_end) - 1;
+      const int c1 = (c0 + BN < col_end ? c0 + BN : col_end) - 1;
+      if (c1 < r0) return false;                         // entirely below the diagonal
+      // distance range of the upper cells of the tile: [max(0, c0 - r1), c1 - r0]
+      const int dmin = c0 - r1 > 0 ? c0 - r1 : 0, dmax = c1 - r0;
+      if (band_hi >= 0 && (dmin > band_hi || dmax < band_lo)) return false;
+    }
+    t->m0 = r0;
+    t->n0 = c0;
+    return true;
+  }
+  int count() const {
+    if (!symmetric) return mt() * nt();
+    int cnt = 0;
+    TileCoord t;
+    for (long long c = 0, e = candidates(); c < e; ++c) cnt += tile(c, &t) ? 1 : 0;
+    return cnt;
+  }
+};
+
+__global__ void __launch_bounds__(1024) tile_list_kernel(const TileSpace ts, TileCoord* __restrict__ dst) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  const long long total = ts.candidates();
+  for (long long c0 = 0; c0 < total; c0 += 1024) {
+    TileCoord t;
+    const bool keep = (c0 + tid < total) && ts.tile(c0 + tid, &t);
+    const unsigned int bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[w] = __popc(bal);
+    __syncthreads();
+    int before = 0, all = 0;
+    for (int i = 0; i < 32; ++i) { const int v = s_warp[i]; before += (i < w) ? v : 0; all += v; }
+    if (keep) dst[s_base + before + __popc(bal & ((1u << lane) - 1u))] = t;
+    __syncthreads();
+    if (tid == 0) s_base += all;
+    __syncthreads();
+  }
 }
 
 int launch_prep(const float* x, int rows, int k, long long ld_x, int center, void* hi, void* lo, int prec,
@@ -611,7 +688,7 @@ constexpr int kSyncEvery = 32;          // k-blocks between producer rendezvous
 static int64_t sync_counters(int m, int k) {
   using namespace hia;
   const int64_t ntiles = (int64_t)((m + BM - 1) / BM) * ((m + BN - 1) / BN);
-  const int64_t per_cta = ntiles / kNumSMs + 2;
+  const int64_t per_cta = ntiles / num_sms() + 2;
   return per_cta * (round_up(k, 32) / 32) / kSyncEvery + 64;      // sized for the smaller k-block
 }
 static int64_t split_ws_layout(int m, int k, int prec, int64_t* off_lo, int64_t* off_tiles,
@@ -639,10 +716,21 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
                            int64_t ld_out, int flavour, int precision, int32_t band_lo,
                            int32_t band_hi, int32_t k_chunk, void* workspace,
                            int64_t workspace_bytes, void* stream_, int phases);
-static int launch_gemm(void* hi, void* lo, int prec, int plane_rows, int n_valid, int kpad, int row0, int rows,
-                       int symmetric, int band_lo, int band_hi, float* out, int64_t ld_out, int flavour,
-                       int k_chunk, hia::TileCoord* d_tiles, unsigned int* sync_ctr, int64_t n_sync,
-                       cudaStream_t stream, int col0 = 0, int cols = -1);
+// One contraction job: out = f(A planes . B planes^T) on a range of A rows x B rows (see SyrkArgs).
+struct GemmJob {
+  void *a_hi, *a_lo;  int a_plane_rows;       // planes of the output's rows
+  void *b_hi, *b_lo;  int b_plane_rows;       // planes of the output's columns (may be the same buffers)
+  int prec, kpad;
+  int row0, row_end, col0, col_end;           // plane-row ranges (row0 % tile_m == 0, col0 % 256 == 0)
+  int symmetric, has_diag, band_lo, band_hi;
+  float* out;  int64_t ld_out;                // out[(r - row0)][(c - col0)]
+  float* out_t;  int64_t ld_t;                // optional transposed copy out_t[(c - col0)][(r - row0)]
+  int flavour, k_chunk;
+  hia::TileCoord* d_tiles;  unsigned int* sync_ctr;  int64_t n_sync;
+};
+
+static int launch_gemm(const GemmJob& j, cudaStream_t stream);
+static int check_sm100();
 
 HIA_API int hia_similarity(const float* x, int32_t m, int32_t k, int64_t ld_x, float* out,
                            int64_t ld_out, int flavour, int precision, int32_t band_lo,
@@ -681,10 +769,7 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
   if (band_hi >= 0 && band_lo > band_hi) return HIA_ERR_BAD_ARG;
   if (band_lo < 0) band_lo = 0;
 
-  int dev = 0, major = 0;
-  HIA_CUDA(cudaGetDevice(&dev));
-  HIA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
-  if (major != 10) return HIA_ERR_ARCH;
+  { const int st = check_sm100(); if (st != HIA_OK) return st; }
 
   int64_t off_lo, off_tiles, off_sync;
   split_ws_layout(m, k, precision, &off_lo, &off_tiles, &off_sync);
@@ -700,8 +785,25 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
   }
   if (!(phases & 2)) return HIA_OK;
 
-  return launch_gemm(hi, lo, precision, m, m, kpad, 0, m, 1, band_lo, band_hi, out, ld_out, flavour, k_chunk,
-                     d_tiles, reinterpret_cast<unsigned int*>(ws + off_sync), sync_counters(m, k), stream);
+  GemmJob j = {};
+  j.a_hi = j.b_hi = hi;
+  j.a_lo = j.b_lo = lo;
+  j.a_plane_rows = j.b_plane_rows = m;
+  j.prec = precision;
+  j.kpad = kpad;
+  j.row0 = j.col0 = 0;
+  j.row_end = j.col_end = m;
+  j.symmetric = j.has_diag = 1;
+  j.band_lo = band_lo;
+  j.band_hi = band_hi;
+  j.out = j.out_t = out;                       // the lower triangle is the exact mirror
+  j.ld_out = j.ld_t = ld_out;
+  j.flavour = flavour;
+  j.k_chunk = k_chunk;
+  j.d_tiles = d_tiles;
+  j.sync_ctr = reinterpret_cast<unsigned int*>(ws + off_sync);
+  j.n_sync = sync_counters(m, k);
+  return launch_gemm(j, stream);
 }
 
 // CTA pairs (cta_group::2) unless HIA_SYRK_CTAS=1 selects the single-CTA kernel.
@@ -713,21 +815,58 @@ static int syrk_ctas() {
   return v;
 }
 
+// Per (kernel instantiation, device): opt-in shared memory once, resident cluster count once.
 template <int PREC, int CTAS>
-static int launch_syrk(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const hia::TileCoord* d_tiles,
-                       int num_tiles, int m, int num_k_blocks, int kb_per_chunk, float* out, int64_t ld_out,
-                       int flavour, unsigned int* sync_ctr, int sync_arg, int row0, int row_end,
-                       int symmetric, cudaStream_t stream) {
+static int syrk_units(int* units_out) {
+  using namespace hia;
+  using G = Geo<CTAS>;
+  static int cached_units[16] = {0};
+  int dev = 0;
+  HIA_CUDA(cudaGetDevice(&dev));
+  const int slot = dev & 15;
+  int units = __atomic_load_n(&cached_units[slot], __ATOMIC_ACQUIRE);
+  if (units == 0) {
+    auto kern = syrk_split3_kernel<PREC, CTAS>;
+    HIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+    const int sms = num_sms();
+    units = sms / CTAS;
+    if (CTAS == 2) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = G::SMEM_BYTES;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cfg.gridDim = dim3(sms / 2 * 2, 1, 1);
+      int max_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess && max_clusters > 0)
+        units = min(units, max_clusters);                 // persistent: never more pairs than can be resident
+      else
+        (void)cudaGetLastError();
+    }
+    __atomic_store_n(&cached_units[slot], units, __ATOMIC_RELEASE);
+  }
+  *units_out = units;
+  return HIA_OK;
+}
+
+template <int PREC, int CTAS>
+static int launch_syrk(const CUtensorMap* maps, const hia::SyrkArgs& args, cudaStream_t stream) {
   using namespace hia;
   using G = Geo<CTAS>;
   auto kern = syrk_split3_kernel<PREC, CTAS>;
-  HIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+  int units = 0;
+  const int st = syrk_units<PREC, CTAS>(&units);
+  if (st != HIA_OK) return st;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = G::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  int units = kNumSMs / CTAS;
   if (CTAS == 2) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
@@ -735,75 +874,70 @@ static int launch_syrk(const CUtensorMap& map_hi, const CUtensorMap& map_lo, con
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cfg.gridDim = dim3(kNumSMs, 1, 1);
-    int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess && max_clusters > 0)
-      units = min(units, max_clusters);                   // persistent: never more pairs than can be resident
-    else
-      (void)cudaGetLastError();
   }
-  units = min(units, num_tiles);
+  units = min(units, args.num_tiles);
   cfg.gridDim = dim3(units * CTAS, 1, 1);
-  HIA_CUDA(cudaLaunchKernelEx(&cfg, kern, map_hi, map_lo, d_tiles, num_tiles, m, num_k_blocks, kb_per_chunk, out,
-                              (long long)ld_out, flavour, sync_ctr, sync_arg, row0, row_end, symmetric));
+  HIA_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], args));
   HIA_LAUNCH_CHECK();
   return HIA_OK;
 }
 
-// Tiles + tensor maps + launch. plane_rows = rows the planes hold (>= n_valid; extra rows must be
-// zero), n_valid = true matrix size, [row0, row0 + rows) = the output rows to compute.
-static int launch_gemm(void* hi, void* lo, int prec, int plane_rows, int n_valid, int kpad, int row0, int rows,
-                       int symmetric, int band_lo, int band_hi, float* out, int64_t ld_out, int flavour,
-                       int k_chunk, hia::TileCoord* d_tiles, unsigned int* sync_ctr, int64_t n_sync,
-                       cudaStream_t stream, int col0, int cols) {
+// Tile list (device) + tensor maps + launch. Everything is stream-ordered and capturable: no host
+// allocation, no pageable copy, no per-call attribute / occupancy query.
+static int launch_gemm(const GemmJob& j, cudaStream_t stream) {
   using namespace hia;
-  const int m = n_valid;
   const int ctas = syrk_ctas();
-  const int tile_m = BM * ctas;
-  const int max_tiles = ((m + BM - 1) / BM) * ((m + BN - 1) / BN);
-  TileCoord* h_tiles = static_cast<TileCoord*>(malloc((size_t)max_tiles * sizeof(TileCoord)));
-  if (!h_tiles) return HIA_ERR_BAD_ARG;
-  int num_tiles = 0;
-  if (symmetric) {
-    num_tiles = build_tiles(m, tile_m, band_lo, band_hi, h_tiles);
-  } else {
-    // row block x column range [col0, col0 + cols) (cols < 0: every column); col0 % BN == 0
-    const int row_end = min(row0 + rows, m);
-    const int col_end = cols < 0 ? m : min(col0 + cols, m);
-    const int nt0 = col0 / BN, nt = (col_end + BN - 1) / BN;
-    for (int sn = nt0; sn < nt; sn += 8)                   // 8-column-tile super blocks for L2 reuse
-      for (int r = row0; r < row_end; r += tile_m)
-        for (int nj = sn; nj < min(sn + 8, nt); ++nj) { h_tiles[num_tiles].m0 = r; h_tiles[num_tiles].n0 = nj * BN; ++num_tiles; }
-  }
-  if (num_tiles == 0) { free(h_tiles); return HIA_OK; }
-  // pageable H2D: the runtime stages the data before returning, so freeing right after is safe
-  cudaError_t ce = cudaMemcpyAsync(d_tiles, h_tiles, (size_t)num_tiles * sizeof(TileCoord),
-                                   cudaMemcpyHostToDevice, stream);
-  free(h_tiles);
-  HIA_CUDA(ce);
+  TileSpace ts = {j.row0, j.row_end, j.col0, j.col_end, BM * ctas, j.symmetric, j.band_lo, j.band_hi};
+  const int num_tiles = ts.count();
+  if (num_tiles == 0) return HIA_OK;
+  tile_list_kernel<<<1, 1024, 0, stream>>>(ts, j.d_tiles);
+  HIA_LAUNCH_CHECK();
 
-  CUtensorMap map_hi, map_lo;
-  int st = make_plane_map(&map_hi, hi, plane_rows, kpad, prec);
-  if (st != HIA_OK) return st;
-  st = make_plane_map(&map_lo, lo, plane_rows, kpad, prec);
+  CUtensorMap maps[4];
+  int st = make_plane_map(&maps[0], j.a_hi, j.a_plane_rows, j.kpad, j.prec);
+  if (st == HIA_OK) st = make_plane_map(&maps[1], j.a_lo, j.a_plane_rows, j.kpad, j.prec);
+  if (st == HIA_OK) st = make_plane_map(&maps[2], j.b_hi, j.b_plane_rows, j.kpad, j.prec);
+  if (st == HIA_OK) st = make_plane_map(&maps[3], j.b_lo, j.b_plane_rows, j.kpad, j.prec);
   if (st != HIA_OK) return st;
 
-  const int bk = bk_of(prec);
-  const int num_k_blocks = kpad / bk;
+  const int bk = bk_of(j.prec);
   // measured on B200 (3xTF32): k_chunk 256 -> 1.6e-6 max abs err (1024: 5e-6, unchunked: 1e-4). The
   // error grows with the number of MMA steps in one TMEM chain; fp16 steps cover twice the K.
-  if (k_chunk <= 0) k_chunk = (prec == HIA_PREC_3XF16) ? 512 : 256;
-  const int kb_per_chunk = max(1, k_chunk / bk);
+  const int k_chunk = j.k_chunk > 0 ? j.k_chunk : (j.prec == HIA_PREC_3XF16 ? 512 : 256);
   static const int sync_every = getenv("HIA_SYRK_SYNC") ? atoi(getenv("HIA_SYRK_SYNC")) : kSyncEvery;
-  const int sync_arg = (sync_every >= kSyncEvery) ? sync_every : 0;
-  HIA_CUDA(cudaMemsetAsync(sync_ctr, 0, (size_t)n_sync * 4, stream));
-  const int row_end = min(row0 + rows, m);
-#define HIA_SYRK_LAUNCH(P, C)                                                                              \
-  launch_syrk<P, C>(map_hi, map_lo, d_tiles, num_tiles, m, num_k_blocks, kb_per_chunk, out, ld_out, flavour, \
-                    sync_ctr, sync_arg, row0, row_end, symmetric, stream)
-  if (prec == HIA_PREC_3XF16) return ctas == 2 ? HIA_SYRK_LAUNCH(HIA_PREC_3XF16, 2) : HIA_SYRK_LAUNCH(HIA_PREC_3XF16, 1);
-  return ctas == 2 ? HIA_SYRK_LAUNCH(HIA_PREC_3XTF32, 2) : HIA_SYRK_LAUNCH(HIA_PREC_3XTF32, 1);
-#undef HIA_SYRK_LAUNCH
+  HIA_CUDA(cudaMemsetAsync(j.sync_ctr, 0, (size_t)j.n_sync * 4, stream));
+  SyrkArgs a;
+  a.tiles = j.d_tiles;
+  a.num_tiles = num_tiles;
+  a.num_k_blocks = j.kpad / bk;
+  a.kb_per_chunk = max(1, k_chunk / bk);
+  a.flavour = j.flavour;
+  a.out = j.out;
+  a.ld_out = j.ld_out;
+  a.out_t = j.out_t;
+  a.ld_t = j.ld_t;
+  a.sync_ctr = j.sync_ctr;
+  a.sync_every = (sync_every >= kSyncEvery) ? sync_every : 0;
+  a.row0 = j.row0;
+  a.row_end = j.row_end;
+  a.col0 = j.col0;
+  a.col_end = j.col_end;
+  a.symmetric = j.symmetric;
+  a.has_diag = j.has_diag;
+  if (j.prec == HIA_PREC_3XF16)
+    return ctas == 2 ? launch_syrk<HIA_PREC_3XF16, 2>(maps, a, stream) : launch_syrk<HIA_PREC_3XF16, 1>(maps, a, stream);
+  return ctas == 2 ? launch_syrk<HIA_PREC_3XTF32, 2>(maps, a, stream) : launch_syrk<HIA_PREC_3XTF32, 1>(maps, a, stream);
+}
+
+static int check_sm100() {
+  static int major = 0;
+  if (major == 0) {
+    int dev = 0, mj = 0;
+    HIA_CUDA(cudaGetDevice(&dev));
+    HIA_CUDA(cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, dev));
+    major = mj;
+  }
+  return major == 10 ? HIA_OK : HIA_ERR_ARCH;
 }
 
 // ------------------------------------------------------------------ row-sharded entry points
@@ -829,6 +963,19 @@ HIA_API int64_t hia_sim_gemm_rows_workspace_bytes(int32_t n, int32_t k) {
   return (ntiles * (int64_t)sizeof(hia::TileCoord) + 1023) / 1024 * 1024 + sync_counters(n, k) * 4 + 1024;
 }
 
+static int rows_ws(void* workspace, int64_t workspace_bytes, int32_t n, int32_t k, GemmJob* j) {
+  using namespace hia;
+  if (!aligned16(workspace)) return HIA_ERR_ALIGN;
+  if (workspace_bytes < hia_sim_gemm_rows_workspace_bytes(n, k)) return HIA_ERR_WORKSPACE;
+  const int64_t ntiles = (int64_t)((n + BM - 1) / BM) * ((n + BN - 1) / BN);
+  const int64_t tiles_al = (ntiles * (int64_t)sizeof(TileCoord) + 1023) / 1024 * 1024;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  j->d_tiles = reinterpret_cast<TileCoord*>(ws);
+  j->sync_ctr = reinterpret_cast<unsigned int*>(ws + tiles_al);
+  j->n_sync = sync_counters(n, k);
+  return HIA_OK;
+}
+
 HIA_API int hia_sim_gemm_rows(void* hi, void* lo, int precision, int32_t plane_rows, int32_t n, int32_t k,
                               int32_t row0, int32_t rows, float* out_rows, int64_t ld_out, int flavour,
                               int32_t k_chunk, void* workspace, int64_t workspace_bytes, void* stream_) {
@@ -837,38 +984,82 @@ HIA_API int hia_sim_gemm_rows(void* hi, void* lo, int precision, int32_t plane_r
   if (!hi || !lo || !out_rows || !workspace || n <= 0 || k <= 0 || plane_rows < n || rows <= 0 ||
       row0 < 0 || ld_out < n || !split_prec(precision))
     return HIA_ERR_BAD_ARG;
-  if (row0 % BM) return HIA_ERR_ALIGN;                    // row blocks start on a 128-row tile boundary
-  if (!aligned16(hi) || !aligned16(lo) || !aligned16(workspace)) return HIA_ERR_ALIGN;
-  if (workspace_bytes < hia_sim_gemm_rows_workspace_bytes(n, k)) return HIA_ERR_WORKSPACE;
-  const int64_t ntiles = (int64_t)((n + BM - 1) / BM) * ((n + BN - 1) / BN);
-  const int64_t tiles_al = (ntiles * (int64_t)sizeof(TileCoord) + 1023) / 1024 * 1024;
-  unsigned char* ws = static_cast<unsigned char*>(workspace);
-  return launch_gemm(hi, lo, precision, plane_rows, n, round_up(k, bk_of(precision)), row0, rows, 0, 0, -1,
-                     out_rows, ld_out, flavour, k_chunk, reinterpret_cast<TileCoord*>(ws),
-                     reinterpret_cast<unsigned int*>(ws + tiles_al), sync_counters(n, k), stream);
+  if (row0 % BM) return HIA_ERR_ALIGN;                    // row blocks start on a 128-row boundary
+  if (!aligned16(hi) || !aligned16(lo)) return HIA_ERR_ALIGN;
+  int st = check_sm100();
+  if (st != HIA_OK) return st;
+  GemmJob j = {};
+  st = rows_ws(workspace, workspace_bytes, n, k, &j);
+  if (st != HIA_OK) return st;
+  j.a_hi = j.b_hi = hi;
+  j.a_lo = j.b_lo = lo;
+  j.a_plane_rows = j.b_plane_rows = plane_rows;
+  j.prec = precision;
+  j.kpad = round_up(k, bk_of(precision));
+  j.row0 = row0;
+  j.row_end = min(row0 + rows, n);
+  j.col0 = 0;
+  j.col_end = n;
+  j.symmetric = 0;
+  j.has_diag = 1;
+  j.band_lo = 0;
+  j.band_hi = -1;
+  j.out = out_rows;
+  j.ld_out = ld_out;
+  j.out_t = nullptr;
+  j.ld_t = 0;
+  j.flavour = flavour;
+  j.k_chunk = k_chunk;
+  return launch_gemm(j, stream);
 }
 
-// The same for a COLUMN RANGE of the row block: out_rows[r - row0][c] for r in [row0, row0 + rows),
-// c in [col0, col0 + cols), col0 a multiple of 256. n = number of valid plane rows / columns
-// (>= col0 + cols; columns >= n are masked). The ring schedule of hiarch_b200/sharded.py calls it
-// with the planes of the own rows and of ONE peer block stacked in one buffer ([own | peer]) and a
-// column-shifted `out_rows` pointer, while the next peer's planes arrive over NVLink.
-HIA_API int hia_sim_gemm_rows_cols(void* hi, void* lo, int precision, int32_t plane_rows, int32_t n, int32_t k,
-                                   int32_t row0, int32_t rows, int32_t col0, int32_t cols, float* out_rows,
-                                   int64_t ld_out, int flavour, int32_t k_chunk, void* workspace,
-                                   int64_t workspace_bytes, void* stream_) {
+// One block of the row-sharded contraction (the ring schedule of hiarch_b200/sharded.py):
+//   out  [i - a_row0][j - b_row0] = f(A[i] . B[j])   i in [a_row0, a_row0 + a_rows), j in [b_row0, b_row0 + b_rows)
+//   out_t[j - b_row0][i - a_row0] = the same value   (optional; may be a peer GPU's memory)
+// A and B are separate plane sets (row indices are plane rows). symmetric != 0: B must be A and the
+// ranges equal: only the upper triangle is contracted, out_t receives the strict upper cells
+// transposed (pass out_t = out, ld_t = ld_out for a full symmetric block) and the diagonal is the
+// exact constant.
+HIA_API int hia_sim_gemm_block(void* a_hi, void* a_lo, int32_t a_plane_rows, void* b_hi, void* b_lo,
+                               int32_t b_plane_rows, int precision, int32_t k, int32_t a_row0, int32_t a_rows,
+                               int32_t b_row0, int32_t b_rows, int symmetric, float* out, int64_t ld_out,
+                               float* out_t, int64_t ld_t, int flavour, int32_t k_chunk, void* workspace,
+                               int64_t workspace_bytes, void* stream_) {
   using namespace hia;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!hi || !lo || !out_rows || !workspace || n <= 0 || k <= 0 || plane_rows < n || rows <= 0 ||
-      row0 < 0 || col0 < 0 || cols <= 0 || col0 + cols > n || !split_prec(precision))
+  if (!a_hi || !a_lo || !b_hi || !b_lo || !out || !workspace || k <= 0 || a_rows <= 0 || b_rows <= 0 ||
+      a_row0 < 0 || b_row0 < 0 || a_row0 + a_rows > a_plane_rows || b_row0 + b_rows > b_plane_rows ||
+      ld_out < b_rows || (out_t && ld_t < a_rows) || !split_prec(precision))
     return HIA_ERR_BAD_ARG;
-  if ((row0 % BM) || (col0 % BN)) return HIA_ERR_ALIGN;
-  if (!aligned16(hi) || !aligned16(lo) || !aligned16(workspace)) return HIA_ERR_ALIGN;
-  if (workspace_bytes < hia_sim_gemm_rows_workspace_bytes(n, k)) return HIA_ERR_WORKSPACE;
-  const int64_t ntiles = (int64_t)((n + BM - 1) / BM) * ((n + BN - 1) / BN);
-  const int64_t tiles_al = (ntiles * (int64_t)sizeof(TileCoord) + 1023) / 1024 * 1024;
-  unsigned char* ws = static_cast<unsigned char*>(workspace);
-  return launch_gemm(hi, lo, precision, plane_rows, n, round_up(k, bk_of(precision)), row0, rows, 0, 0, -1,
-                     out_rows, ld_out, flavour, k_chunk, reinterpret_cast<TileCoord*>(ws),
-                     reinterpret_cast<unsigned int*>(ws + tiles_al), sync_counters(n, k), stream, col0, cols);
+  if (symmetric && (a_hi != b_hi || a_lo != b_lo || a_row0 != b_row0 || a_rows != b_rows)) return HIA_ERR_BAD_ARG;
+  if ((a_row0 % BM) || (b_row0 % BM)) return HIA_ERR_ALIGN;
+  if (!aligned16(a_hi) || !aligned16(a_lo) || !aligned16(b_hi) || !aligned16(b_lo)) return HIA_ERR_ALIGN;
+  int st = check_sm100();
+  if (st != HIA_OK) return st;
+  GemmJob j = {};
+  st = rows_ws(workspace, workspace_bytes, max(a_rows, b_rows), k, &j);
+  if (st != HIA_OK) return st;
+  j.a_hi = a_hi;
+  j.a_lo = a_lo;
+  j.a_plane_rows = a_plane_rows;
+  j.b_hi = b_hi;
+  j.b_lo = b_lo;
+  j.b_plane_rows = b_plane_rows;
+  j.prec = precision;
+  j.kpad = round_up(k, bk_of(precision));
+  j.row0 = a_row0;
+  j.row_end = a_row0 + a_rows;
+  j.col0 = b_row0;
+  j.col_end = b_row0 + b_rows;
+  j.symmetric = symmetric ? 1 : 0;
+  j.has_diag = symmetric ? 1 : 0;
+  j.band_lo = 0;
+  j.band_hi = -1;
+  j.out = out;
+  j.ld_out = ld_out;
+  j.out_t = out_t;
+  j.ld_t = ld_t;
+  j.flavour = flavour;
+  j.k_chunk = k_chunk;
+  return launch_gemm(j, stream);
 }

@@ -219,10 +219,23 @@ class HiCMtx:
                                    counts_must_decrese=counts_must_decrese, only_intra=only_intra)
         new_mtx = ArrayHiCMtx(out, copy_mtx_paras=dense, mtx_type='all', has_neg=False)
         new_mtx._oe_state = state
+        new_mtx._oe_src = (dense.dmatrix, layout, k, counts_must_decrese, only_intra)
         if return_exp_counts:
             s, e = layout.seps[-1]                        # the reference returns the last block's vector
             return new_mtx, state.expected[s:e + 1].cpu().numpy()
         return new_mtx
+
+    def oe_float64(self):
+        """Not in the reference: the raw O/E map of the `obs_d_exp` call that produced this object
+        as a float64 CUDA tensor, divided in double like the reference (1e-5 absolute for entries
+        of any size; the fp32 `dmatrix` carries 6e-8 relative, i.e. 1e-5 only up to values of ~50)."""
+        src = getattr(self, "_oe_src", None)
+        if src is None:
+            raise ValueError("oe_float64() is available on the result of obs_d_exp() only")
+        dmatrix, layout, k, clamp, only_intra = src
+        out, _ = ops.obs_d_exp(dmatrix, layout, self.row_window.bin_size, k=k, counts_must_decrese=clamp,
+                               only_intra=only_intra, fp64_out=True)
+        return out
 
     # ---- block iteration (:1372-1396) -------------------------------------------------------
     def yield_by_chro(self, only_intra=False, triu=False):

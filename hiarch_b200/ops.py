@@ -146,21 +146,23 @@ class OEState:
 
 
 def obs_d_exp(dense, layout, bin_size, k=.2, counts_must_decrese=True, only_intra=False,
-              log=False, out=None, state=None, from_upper=False):
+              log=False, out=None, state=None, from_upper=False, fp64_out=False):
     """O/E (mode='sgd_mean') of a symmetric dense map, optionally fused with ArrayHiCMtx.log.
     Replaces HiCMtx.obs_d_exp (publish/new_hic_class.py:1121-1290) + log (:2076-2094).
     `out` may alias `dense` (in place). Returns (out, OEState). from_upper=True: only the upper
     triangle of `dense` is read (it may come from scatter_coo_sym(mtx_type=MTX_TRIU_UPPER)); the
-    result is the same full symmetric map."""
+    result is the same full symmetric map. fp64_out=True (raw O/E only, log=False): the result is
+    a float64 [n, n] tensor divided in double like the reference -- 1e-5 absolute for entries of any
+    size (the fp32 map carries its 6e-8 relative rounding, i.e. 1e-5 only up to values of ~50)."""
     lib = _lib.load()
     _need_cuda(dense)
     n = layout.n
     assert dense.shape == (n, n) and dense.dtype == torch.float32 and dense.stride(1) == 1
     pool_gid, use_code = layout.oe_tables(bin_size, k)
     state = OEState(layout) if state is None else state
-    if out is None:
+    if out is None and not fp64_out:
         out = alloc_map(n, dense.device)
-    assert out.stride(0) == dense.stride(0), "in/out maps must share the leading dimension"
+    assert fp64_out or out.stride(0) == dense.stride(0), "in/out maps must share the leading dimension"
     stream = _stream()
     st = lib.hia_oe_expected_pass(_ptr(dense), n, dense.stride(0), _ptr(layout.chr_start),
                                   layout.chr_start_host.ctypes.data, layout.n_chr,
@@ -175,6 +177,15 @@ def obs_d_exp(dense, layout, bin_size, k=.2, counts_must_decrese=True, only_intr
                              _ptr(state.expected), _ptr(state.inv_expected),
                              _ptr(state.inter_inv), _ptr(state.min_pos_oe), stream)
     _lib.check(st, "hia_oe_finalize")
+    if fp64_out:
+        if log or from_upper:
+            raise _lib.HiaError("fp64_out is the raw O/E of a full symmetric map (log=False, from_upper=False)")
+        out64 = torch.empty((n, n), dtype=torch.float64, device=dense.device)
+        st = lib.hia_oe_apply_f64(_ptr(dense), n, dense.stride(0), _ptr(out64), n, _ptr(layout.chr_start),
+                                  layout.n_chr, _ptr(layout.bin_chr), _ptr(state.expected), _ptr(state.inter_sum),
+                                  _ptr(state.inter_nnz), OE_ONLY_INTRA if only_intra else 0, stream)
+        _lib.check(st, "hia_oe_apply_f64")
+        return out64, state
     flags = (OE_LOG if log else 0) | (OE_ONLY_INTRA if only_intra else 0) | (OE_FROM_UPPER if from_upper else 0)
     st = lib.hia_oe_apply(_ptr(dense), _ptr(out), n, dense.stride(0), _ptr(layout.chr_start),
                           layout.n_chr, _ptr(layout.bin_chr), _ptr(state.inv_expected),

@@ -12,8 +12,9 @@ The single exchange step of the hot path (BASELINE.json co
      Y[rows] = C[rows, :] V, is local and the n x 8 fp64 panel is all-gathered per step;
      the tiny orthogonalisation / Rayleigh-Ritz is replicated (bit-identical on all ranks).
 
-Round-1 version: each rank computes its FULL row block (no symmetry saving -> balanced without a
-row permutation); the planes are gathered whole before the contraction (not chunk-pipelined).
+`ShardedSimilarity` is the plain version (NCCL all-gather of the planes, every rank contracts its
+full row block); `RingSimilarity` is the fast one: peer memory instead of collectives, each
+unordered pair of row blocks contracted once, plane transfers on the copy engines behind the MMAs.
 """
 import ctypes
 
@@ -82,37 +83,57 @@ class ShardedSimilarity:
         return out_rows
 
 
-def ring_schedule(world):
-    """steps[t] = [(rank, peer), ...]: at step t `rank` contracts its row block against `peer`'s.
-    Every unordered pair of row blocks appears exactly once (the similarity matrix is symmetric: the
-    other half is the transposed block, sent back over NVLink): step 0 = the diagonal blocks, step t
-    pairs r with r + t (mod world); for an even world the antipodal step is taken by the lower
-    rank of each pair only. world / 2 + 1 steps instead of world block products per rank."""
-    steps = []
-    for t in range(world // 2 + 1):
-        pairs = []
-        for r in range(world):
-            s = (r + t) % world
-            if t == 0 or 2 * t < world or (2 * t == world and r < s):
-                pairs.append((r, s))
-        steps.append(pairs)
-    return steps
+def ring_plan(world, rank, per, n):
+    """The block products of `rank` in the symmetric ring schedule ("by symmetry only
+    s >= r tiles are needed"). Every unordered pair of row blocks is contracted exactly once; the
+    mirrored half C[R_s, R_r] = C[R_r, R_s]^T is written by the same kernel into the peer's rows.
+
+      step 0          the diagonal block (upper triangle only: half a block product)
+      step t          rank r against block s = r + t (mod world), 0 < 2 t < world: a full block
+      step world / 2  (even world) the antipodal pair splits ITS block in two: the lower rank
+                      contracts its first h rows against all of the peer's, the higher rank all
+                      of its rows against the peer's rows [h, ...): half a block each, so every
+                      rank does world / 2 block products in total (8 GPUs: 4 instead of 8).
+
+    Returns a list of jobs (dict): t, peer, symmetric, a0, a_rows (own rows, block-local),
+    b0, b_rows (the peer's rows, block-local). Jobs with no rows are omitted."""
+    def valid(r):
+        return max(0, min(n, (r + 1) * per) - r * per)
+
+    jobs = []
+    mine = valid(rank)
+    if mine > 0:
+        jobs.append(dict(t=0, peer=rank, symmetric=True, a0=0, a_rows=mine, b0=0, b_rows=mine))
+    for t in range(1, world // 2 + 1):
+        s = (rank + t) % world
+        if 2 * t < world:
+            a0, a_rows, b0, b_rows = 0, mine, 0, valid(s)
+        elif 2 * t == world:
+            h = (per // 2) // 128 * 128
+            if rank < s:
+                a0, a_rows, b0, b_rows = 0, min(h, mine), 0, valid(s)
+            else:
+                a0, a_rows, b0, b_rows = 0, mine, min(h, valid(s)), valid(s) - min(h, valid(s))
+        else:
+            continue
+        if a_rows > 0 and b_rows > 0:
+            jobs.append(dict(t=t, peer=s, symmetric=False, a0=a0, a_rows=a_rows, b0=b0, b_rows=b_rows))
+    return jobs
 
 
 class RingSimilarity:
-    """Row-sharded similarity with the symmetry used and the plane exchange hidden behind the
-    contraction (opt-in alternative to ShardedSimilarity; written after the round-1 GPU budget was
-    spent: its exchange logic is covered by world-size-2/3/4 gloo tests with a torch stand-in for the
-    kernel, the kernel path itself has NOT run yet).
+    """Row-sharded similarity over peer memory: the symmetry is used (world / 2 block products per
+    rank instead of world) and nothing but the tensor-core kernel runs on the SMs.
 
-    Per step t of `ring_schedule`: rank r holds the planes of block s = r + t in the peer slot of a
-    stacked buffer [own rows | peer rows] (one tensor map serves both operands of the tcgen05
-    kernel), contracts C[R_r, R_s] straight into its output rows (hia_sim_gemm_rows_cols with a
-    column-shifted output pointer), sends the finished block to s -- which stores its transpose as
-    C[R_s, R_r], bit-identical by construction -- while the planes of block r + t + 1 arrive in the
-    other buffer (P2P send / recv on a side stream). 7.6 GB of planes per step at 25 kb against a
-    ~120 ms block product: the transfer is off the critical path, and each rank does world/2 + 1
-    block products instead of world (8 GPUs: 4.5 instead of 8)."""
+    Every rank exports the hi/lo planes of ITS rows and its output rows (CUDA IPC, peer.py). Per job of
+    `ring_plan`: the peer block's planes are PULLED into one of two local staging slots by a copy
+    engine on a side stream (7.7 GB per block at 25 kb over NVLink against a ~120 ms block product:
+    off the critical path, and -- unlike an NCCL send/recv -- it takes no SM from the persistent
+    148-CTA kernel, so the overlap is real); `hia_sim_gemm_block` contracts own rows x staged rows,
+    stores C[R_r, R_s] into the own output rows and its transpose straight into the PEER's output
+    rows over NVLink from the epilogue (bit-identical mirror by construction). Two tiny all-reduces
+    (entry: every rank's planes exist and its previous result is no longer read; exit: every
+    mirrored store has landed) are the only collectives."""
 
     def __init__(self, n, k, flavour=ops.SIM_PEARSON, group=None, device=None, precision=None):
         self.group = group
@@ -120,144 +141,154 @@ class RingSimilarity:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n, self.k, self.flavour = n, k, flavour
         self.per = rows_per_rank(n, self.world)
-        self.per_pad = (self.per + 255) // 256 * 256          # the peer slot starts on a column-tile boundary
         self.row0 = self.rank * self.per
         self.rows = self.valid(self.rank)
-        self.steps = ring_schedule(self.world)
+        self.jobs = ring_plan(self.world, self.rank, self.per, n)
         self.precision = ops.PREC_DEFAULT if precision is None else precision
         self.device = device
+        self.stats = {}
         self._alloc()
 
     def valid(self, r):
         """Rows of block r that exist (the last block may be ragged or empty)."""
         return max(0, min(self.n, (r + 1) * self.per) - r * self.per)
 
-    def global_rank(self, r):
-        return dist.get_global_rank(self.group, r) if self.group is not None else r
-
-    # ---- backend: CUDA library (overridden by the CPU stand-in of the tests) --------------------
+    # ---- backend: CUDA library + peer memory (overridden by the CPU stand-in of the tests) ----------
     def _alloc(self):
+        from .peer import PeerBuffer
         self.lib = _lib.load()
         assert self.precision in ops.SPLIT_PRECS
         self.device = self.device or torch.device("cuda", torch.cuda.current_device())
         self.kpad = self.lib.hia_sim_kpad(self.k, self.precision)
-        pdt = torch.float16 if self.lib.hia_sim_plane_elem_bytes(self.precision) == 2 else torch.float32
-        comb = self.per_pad + self.per
-        # two stacked buffers (double buffering of the peer slot); rows that are never written stay zero
-        self.hi = [torch.zeros((comb, self.kpad), dtype=pdt, device=self.device) for _ in range(2)]
-        self.lo = [torch.zeros((comb, self.kpad), dtype=pdt, device=self.device) for _ in range(2)]
-        self.ws = torch.empty(self.lib.hia_sim_gemm_rows_workspace_bytes(comb, self.k), dtype=torch.uint8,
+        self.elem = self.lib.hia_sim_plane_elem_bytes(self.precision)
+        pdt = torch.float16 if self.elem == 2 else torch.float32
+        # own planes [2 (hi, lo), per, kpad] (exported; rows >= self.rows stay zero) and two staging slots
+        self.own = torch.zeros((2, self.per, self.kpad), dtype=pdt, device=self.device)
+        self.slots = [torch.zeros((2, self.per, self.kpad), dtype=pdt, device=self.device) for _ in range(2)] \
+            if self.world > 1 else []
+        self.ld = ops.padded_ld(self.n)
+        self.out_buf = torch.empty((self.per, self.ld), dtype=torch.float32, device=self.device)   # exported
+        self.ws = torch.empty(self.lib.hia_sim_gemm_rows_workspace_bytes(self.per, self.k), dtype=torch.uint8,
                               device=self.device)
-        self.comm_stream = torch.cuda.Stream(device=self.device)
+        self.peer_planes = PeerBuffer(self.own, self.group)
+        self.peer_out = PeerBuffer(self.out_buf, self.group)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     def _prep(self, x_rows):
         if self.rows > 0:
             st = self.lib.hia_sim_prep_rows(x_rows.data_ptr(), self.rows, self.k, x_rows.stride(0), self.flavour,
-                                            self.precision, self.hi[0].data_ptr(), self.lo[0].data_ptr(),
+                                            self.precision, self.own[0].data_ptr(), self.own[1].data_ptr(),
                                             ops._stream())
             _lib.check(st, "hia_sim_prep_rows")
-        self.hi[1][:self.per].copy_(self.hi[0][:self.per])
-        self.lo[1][:self.per].copy_(self.lo[0][:self.per])
 
-    def _own_planes(self):
-        return [self.hi[0][:self.per], self.lo[0][:self.per]]
+    def _rendezvous(self):
+        """Stream-ordered barrier: when it completes on this rank's stream, every rank has finished
+        everything it enqueued before its own call."""
+        if self.world > 1:
+            dist.all_reduce(self._flag, group=self.group)
 
-    def _peer_slots(self, b):
-        return [self.hi[b][self.per_pad:], self.lo[b][self.per_pad:]]
+    def _pull(self, slot, job):
+        """Planes rows [b0, b0 + b_rows) of the peer -> the same rows of staging slot `slot`, on the
+        copy stream (the caller orders it after the slot's previous reader)."""
+        row_bytes = self.kpad * self.elem
+        for plane in range(2):
+            off = (plane * self.per + job["b0"]) * row_bytes
+            dst = self.slots[slot][plane, job["b0"]:job["b0"] + job["b_rows"]]
+            self.peer_planes.pull(dst, job["peer"], off, job["b_rows"] * row_bytes, self.copy_stream.cuda_stream)
 
-    def _block(self, b, peer, out_rows, diagonal):
-        """out_rows[:, peer block columns] = own rows x (own | peer-slot) rows of buffer b."""
-        cols = self.valid(peer)
-        if self.rows == 0 or cols == 0:
-            return
-        col0 = 0 if diagonal else self.per_pad
-        shifted = out_rows.data_ptr() + 4 * (peer * self.per - col0)      # column c of the buffer -> global column
-        st = self.lib.hia_sim_gemm_rows_cols(self.hi[b].data_ptr(), self.lo[b].data_ptr(), self.precision,
-                                             self.per_pad + self.per, col0 + cols, self.k, 0, self.rows, col0, cols,
-                                             shifted, out_rows.stride(0), self.flavour, 0, self.ws.data_ptr(),
-                                             self.ws.numel(), ops._stream())
-        _lib.check(st, "hia_sim_gemm_rows_cols")
+    def block_offsets(self, job):
+        """Element offsets (backend independent) of a job's two stores: cell (i, j) of the block
+        (i = own row a0 + i', j = peer row b0 + j') goes to
+            own  output buffer[out_off + i' * ld + j']        (columns of block `peer`)
+            peer output buffer[t_off   + j' * ld + i']        (columns of block `rank`, transposed)."""
+        r, s, per, ld = self.rank, job["peer"], self.per, self.ld
+        return job["a0"] * ld + s * per + job["b0"], job["b0"] * ld + r * per + job["a0"]
 
-    def _new_out(self):
-        return torch.empty((max(self.rows, 1), ops.padded_ld(self.n)), dtype=torch.float32,
-                           device=self.device)[:self.rows, :self.n]
+    def _block(self, slot, job):
+        per, ld = self.per, self.ld
+        out_off, t_off = self.block_offsets(job)
+        out = self.out_buf.data_ptr() + 4 * out_off
+        if job["symmetric"]:
+            b_planes, out_t = self.own, out
+        else:
+            b_planes, out_t = self.slots[slot], self.peer_out.ptr(job["peer"]) + 4 * t_off
+        st = self.lib.hia_sim_gemm_block(self.own[0].data_ptr(), self.own[1].data_ptr(), per,
+                                         b_planes[0].data_ptr(), b_planes[1].data_ptr(), per,
+                                         self.precision, self.k, job["a0"], job["a_rows"], job["b0"], job["b_rows"],
+                                         1 if job["symmetric"] else 0, out, ld, out_t, ld, self.flavour, 0,
+                                         self.ws.data_ptr(), self.ws.numel(), ops._stream())
+        _lib.check(st, "hia_sim_gemm_block")
 
-    def _side(self):
-        """(factory of a fresh context, handle) of the stream the plane exchanges are issued on."""
-        return (lambda: torch.cuda.stream(self.comm_stream)), self.comm_stream
+    def _streams(self):
+        return torch.cuda.current_stream(), self.copy_stream
 
-    def _fence(self, stream):
-        """`stream` waits for everything issued so far on the current stream (and vice versa with
-        the returned event)."""
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        stream.wait_event(ev)
+    def _event(self, timing=False):
+        return torch.cuda.Event(enable_timing=timing)
 
     # ---- schedule (backend independent) ---------------------------------------------------------
-    def _exchange(self, sends, recvs):
-        """sends / recvs: [(tensor, group rank)]. Posted together (deadlock-free), returns the works."""
-        p2p = [dist.P2POp(dist.isend, t, self.global_rank(r), group=self.group) for t, r in sends] + \
-              [dist.P2POp(dist.irecv, t, self.global_rank(r), group=self.group) for t, r in recvs]
-        return dist.batch_isend_irecv(p2p) if p2p else []
-
-    def _computes(self, t, r):
-        return (r, (r + t) % self.world) in self.steps[t]
-
-    def run(self, x_rows, out_rows=None):
-        """x_rows: this rank's rows of the map [rows, k]. Returns out_rows [rows, n]."""
-        W, r = self.world, self.rank
+    def run(self, x_rows, timing=False):
+        """x_rows: this rank's rows of the map [rows, k]. Returns out_rows [rows, n] (a view of the
+        exported output buffer: valid until the next run). timing=True records per-job CUDA events;
+        `self.stats` then holds kernel / exposed-wait milliseconds after `collect_stats()`."""
         assert x_rows.shape == (self.rows, self.k)
+        main, side = self._streams()
         self._prep(x_rows)
-        out_rows = self._new_out() if out_rows is None else out_rows
-        side_ctx, side = self._side()
-        pending_planes = None
+        self._rendezvous()                      # all planes exist; nobody still reads the previous result
+        ready = self._event()
+        ready.record(main)
+        remote = [j for j in self.jobs if not j["symmetric"]]
+        pulled, freed, marks = {}, {}, []
 
-        def post_planes(t, b):
-            """Planes for step t: own planes go to the rank that will contract against them, the
-            peer's arrive in the peer slot of buffer b."""
-            sends, recvs = [], []
-            dst, src = (r - t) % W, (r + t) % W
-            if self._computes(t, dst):
-                sends += [(p, dst) for p in self._own_planes()]
-            if self._computes(t, r):
-                recvs += [(p[:self.per], src) for p in self._peer_slots(b)]
-            self._fence(side)                             # the slot's previous user (step t - 2) is done
-            with side_ctx():
-                return self._exchange(sends, recvs)
+        def post_pull(i):
+            slot = i & 1
+            side.wait_event(freed.get(slot, ready))       # the slot's previous reader is done
+            self._pull(slot, remote[i])
+            ev = self._event()
+            ev.record(side)
+            pulled[i] = ev
 
-        if len(self.steps) > 1:
-            pending_planes = post_planes(1, 1)
-        block_works, keep = [], []
-        for t in range(len(self.steps)):
-            b = t & 1
-            if t >= 1:
-                for w in pending_planes:
-                    w.wait()                              # the current stream waits for the planes of step t
-                pending_planes = post_planes(t + 1, (t + 1) & 1) if t + 1 < len(self.steps) else None
-            s = (r + t) % W
-            if self._computes(t, r):
-                self._block(b, s, out_rows, diagonal=(t == 0))
-            if t == 0:
-                continue
-            # the finished block goes to its mirror owner; the block computed FOR this rank comes back
-            q = (r - t) % W
-            sends, recvs = [], []
-            if self._computes(t, r) and self.rows > 0 and self.valid(s) > 0:
-                blk = out_rows[:, s * self.per:s * self.per + self.valid(s)].contiguous()
-                sends.append((blk, s))
-                keep.append(blk)
-            mirror = None
-            if self._computes(t, q) and self.rows > 0 and self.valid(q) > 0:
-                mirror = torch.empty((self.valid(q), self.rows), dtype=out_rows.dtype, device=out_rows.device)
-                recvs.append((mirror, q))
-            works = self._exchange(sends, recvs)
-            block_works.append((works, mirror, q))
-        for works, mirror, q in block_works:
-            for w in works:
-                w.wait()
-            if mirror is not None:
-                out_rows[:, q * self.per:q * self.per + self.valid(q)].copy_(mirror.t())
-        return out_rows
+        if remote:
+            post_pull(0)
+        ri = 0
+        for job in self.jobs:
+            slot = 0
+            if not job["symmetric"]:
+                slot = ri & 1
+                if timing:
+                    w0 = self._event(True)
+                    w0.record(main)
+                main.wait_event(pulled[ri])
+                if ri + 1 < len(remote):
+                    post_pull(ri + 1)                     # overlaps this job's contraction
+            if timing:
+                k0 = self._event(True)
+                k0.record(main)
+            self._block(slot, job)
+            done = self._event(timing)
+            done.record(main)
+            if not job["symmetric"]:
+                freed[slot] = done
+                ri += 1
+            if timing:
+                marks.append((job, w0 if not job["symmetric"] else None, k0, done))
+        self._rendezvous()                      # every rank's mirrored stores have landed
+        self._marks = marks
+        return self.out_buf[:self.rows, :self.n]
+
+    def collect_stats(self):
+        """After a synchronised run(timing=True): per-job kernel ms and the ms the main stream waited
+        for planes (the exposed, non-overlapped part of the exchange)."""
+        kern = [k0.elapsed_time(done) for _, _, k0, done in self._marks]
+        wait = [w0.elapsed_time(k0) for _, w0, k0, _ in self._marks if w0 is not None]
+        row_bytes = self.kpad * self.elem
+        self.stats = {"block_ms": kern, "exposed_wait_ms": float(sum(wait)),
+                      "pulled_bytes": int(sum(2 * j["b_rows"] * row_bytes for j in self.jobs if not j["symmetric"])),
+                      "p2p_store_bytes": int(sum(4 * j["a_rows"] * j["b_rows"] for j in self.jobs
+                                                 if not j["symmetric"])),
+                      "block_products": float(sum((0.5 if j["symmetric"] else 1.0) * j["a_rows"] * j["b_rows"]
+                                                  for j in self.jobs) / max(1, self.per) ** 2)}
+        return self.stats
 
 
 def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, angle_tol=1e-3, max_restarts=8, seed=0,
@@ -384,3 +415,90 @@ def obs_d_exp_rows(map_rows, layout, bin_size, row0, k=.2, counts_must_decrese=T
                                      st_.inv_expected.data_ptr(), st_.inter_inv.data_ptr(),
                                      st_.min_pos_oe.data_ptr(), flags, s), "hia_oe_apply_rows")
     return out_rows, st_
+
+
+class RowShardedPath:
+    """The genome-wide high-resolution chain on the GPUs of one box (BASELINE.json config C5):
+    count rows -> row-sharded O/E + log -> RingSimilarity (Pearson) -> top-k eigenvectors.
+    Every rank holds the rows [rank * per, (rank + 1) * per) of every map. `ring=False` keeps the
+    plain all-gather version (ShardedSimilarity), e.g. where peer mapping is not available."""
+
+    def __init__(self, seps, bin_size, k_eig=3, group=None, device=None, ring=True, precision=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.layout = ops.GenomeLayout(seps, self.device)
+        self.n = self.layout.n
+        self.bin_size = int(bin_size)
+        self.k_eig = k_eig
+        self.layout.oe_tables(self.bin_size)
+        self.per = rows_per_rank(self.n, self.world)
+        self.row0 = self.rank * self.per
+        self.rows = max(0, min(self.n, self.row0 + self.per) - self.row0)
+        self.ring = ring
+        if ring:
+            self.sim = RingSimilarity(self.n, self.n, flavour=ops.SIM_PEARSON, group=group, device=self.device,
+                                      precision=precision)
+        else:
+            self.sim = ShardedSimilarity(self.n, self.n, flavour=ops.SIM_PEARSON, group=group, device=self.device,
+                                         precision=precision)
+            self._out = torch.empty((max(self.rows, 1), ops.padded_ld(self.n)), dtype=torch.float32,
+                                    device=self.device)[:self.rows, :self.n]
+        self.oe_rows = None
+
+    def normalise(self, count_rows, out_rows=None):
+        self.oe_rows, self.oe_state = obs_d_exp_rows(count_rows, self.layout, self.bin_size, self.row0, log=True,
+                                                     out_rows=out_rows, group=self.group)
+        return self.oe_rows
+
+    def similarity(self, timing=False):
+        if self.ring:
+            self.sim_rows = self.sim.run(self.oe_rows, timing=timing)
+        else:
+            self.sim_rows = self.sim.run(self.oe_rows, out_rows=self._out)
+        return self.sim_rows
+
+    def eigen(self, tol=1e-6):
+        return topk_eig_rows(self.sim_rows, self.n, k=self.k_eig, tol=tol, group=self.group)
+
+    def run(self, count_rows):
+        self.normalise(count_rows)
+        self.similarity()
+        return self.eigen()
+
+    def spot_check_fp64(self, n_own=16, n_other=64, seed=0):
+        """Max |sim_rows[i, j] - Pearson_fp64(oe[i], oe[j])| over n_own own rows x n_other rows drawn
+        from the whole genome (the same on every rank; their O/E rows are summed in from their
+        owners with one all-reduce), in torch fp64 -- independent of the tcgen05 path. Returns
+        (max abs error over all ranks, entries checked over all ranks)."""
+        g = np.random.default_rng(seed)
+        cols = np.sort(g.choice(self.n, size=min(n_other, self.n), replace=False))
+        buf = torch.zeros((len(cols), self.n), dtype=torch.float32, device=self.device)
+        for q, j in enumerate(cols):
+            if self.row0 <= j < self.row0 + self.rows:
+                buf[q] = self.oe_rows[j - self.row0]
+        if self.world > 1:
+            dist.all_reduce(buf, group=self.group)
+        err, cnt = 0.0, 0
+        if self.rows > 0:
+            gi = np.random.default_rng(seed + 1 + self.rank)
+            own = np.sort(gi.choice(self.rows, size=min(n_own, self.rows), replace=False))
+            a = self.oe_rows[torch.as_tensor(own, device=self.device)].double()
+            b = buf.double()
+            a = a - a.mean(dim=1, keepdim=True)
+            b = b - b.mean(dim=1, keepdim=True)
+            ref = (a / a.norm(dim=1, keepdim=True)) @ (b / b.norm(dim=1, keepdim=True)).t()
+            ref = ref.clamp(-1.0, 1.0)
+            got = self.sim_rows[torch.as_tensor(own, device=self.device)][:, torch.as_tensor(cols, device=self.device)]
+            same = torch.as_tensor(own + self.row0, device=self.device)[:, None] == \
+                torch.as_tensor(cols, device=self.device)[None, :]
+            ref = torch.where(same, torch.ones_like(ref), ref)
+            err = float((got.double() - ref).abs().max())
+            cnt = ref.numel()
+        if self.world > 1:
+            t = torch.tensor([err, float(cnt)], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t[0:1], op=dist.ReduceOp.MAX, group=self.group)
+            dist.all_reduce(t[1:2], op=dist.ReduceOp.SUM, group=self.group)
+            err, cnt = float(t[0]), int(t[1])
+        return err, cnt

@@ -157,6 +157,16 @@ int hia_oe_apply_rows(const float* map_rows, float* out_rows, int32_t n, int64_t
                       int32_t rows, const int32_t* chr_start, int32_t n_chr, const int16_t* bin_chr,
                       const float* inv_expected, const float* inter_inv, const float* min_pos_oe,
                       int flags, void* stream);
+/* Raw O/E in fp64 (class-level obs_d_exp without log): out[r][c] = map[r][c] / expected[|c - r|]
+ * inside a chromosome, / mean of the non-zero cells of the block between chromosomes, in double like
+ * the reference (new_hic_class.py:1263-1282). `expected`, `inter_sum`, `inter_nnz` are the outputs of
+ * hia_oe_expected_pass + hia_oe_finalize. flags: HIA_OE_ONLY_INTRA only. The fp32 map of
+ * hia_oe_apply holds 1e-5 absolute up to values of ~50; this one everywhere. */
+int hia_oe_apply_f64(const float* map, int32_t n, int64_t ld, double* out, int64_t ld_out,
+                     const int32_t* chr_start, int32_t n_chr, const int16_t* bin_chr,
+                     const double* expected, const double* inter_sum, const int64_t* inter_nnz,
+                     int flags, void* stream);
+
 
 /* Stand-alone ArrayHiCMtx.log (new_hic_class.py:2076-2094) for a map that did not come out of
  * hia_oe_apply: x>0 -> ln(x+1); x<=0 -> min over positives of ln(x+1). min_pos_ws: 1 float. */
@@ -320,15 +330,32 @@ int64_t hia_sim_gemm_rows_workspace_bytes(int32_t n, int32_t k);
 int hia_sim_gemm_rows(void* hi, void* lo, int precision, int32_t plane_rows, int32_t n, int32_t k,
                       int32_t row0, int32_t rows, float* out_rows, int64_t ld_out, int flavour,
                       int32_t k_chunk, void* workspace, int64_t workspace_bytes, void* stream);
-/* The same for the column range [col0, col0 + cols) of the row block only (col0 % 256 == 0,
- * col0 + cols <= n). For the ring schedule of the row-sharded contraction (sharded.py): the planes
- * of the own rows and of one peer block are stacked in one buffer and `out_rows` is passed
- * column-shifted, so each unordered pair of row blocks is contracted once while the next peer's
- * planes are in flight. */
-int hia_sim_gemm_rows_cols(void* hi, void* lo, int precision, int32_t plane_rows, int32_t n, int32_t k,
-                           int32_t row0, int32_t rows, int32_t col0, int32_t cols, float* out_rows,
-                           int64_t ld_out, int flavour, int32_t k_chunk, void* workspace,
-                           int64_t workspace_bytes, void* stream);
+/* One block of the row-sharded contraction (ring schedule of hiarch_b200/sharded.py; SURVEY.md
+ * section 8e "by symmetry only s >= r tiles are needed"):
+ *   out  [i - a_row0][j - b_row0] = f(A[i] . B[j])   i in [a_row0, a_row0 + a_rows), j in [b_row0, b_row0 + b_rows)
+ *   out_t[j - b_row0][i - a_row0] = the same value   (optional, NULL = no transposed copy)
+ * A (a_hi/a_lo, a_plane_rows addressable rows) and B are separate plane sets; a_row0 % 128 == 0,
+ * b_row0 % 128 == 0. out_t may point into a PEER GPU's memory (hia_ipc_open): the mirrored half of the
+ * symmetric result then leaves the epilogue over NVLink, there is no separate exchange step.
+ * symmetric != 0 (B must be A, equal ranges): only the upper triangle is contracted, the diagonal
+ * is the exact constant and out_t receives the strict upper cells transposed (out_t = out,
+ * ld_t = ld_out gives the full symmetric block). Workspace: hia_sim_gemm_rows_workspace_bytes(
+ * max(a_rows, b_rows), k). */
+int hia_sim_gemm_block(void* a_hi, void* a_lo, int32_t a_plane_rows, void* b_hi, void* b_lo,
+                       int32_t b_plane_rows, int precision, int32_t k, int32_t a_row0, int32_t a_rows,
+                       int32_t b_row0, int32_t b_rows, int symmetric, float* out, int64_t ld_out,
+                       float* out_t, int64_t ld_t, int flavour, int32_t k_chunk, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
+/* Peer memory of the row-sharded path (one process per GPU on one NVSwitch box): a rank exports a
+ * device buffer (hia_ipc_export: 64-byte CUDA IPC handle of the allocation + the pointer's offset
+ * in it), the other ranks map it (hia_ipc_open -> base pointer valid in the calling process until
+ * hia_ipc_close). hia_peer_copy is a stream-ordered copy between any two such pointers; it runs on
+ * a copy engine over NVLink, so it overlaps the tensor-core kernel without taking SMs from it. */
+int hia_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset);
+int hia_ipc_open(const void* handle64, void** base_out);
+int hia_ipc_close(void* base);
+int hia_peer_copy(void* dst, const void* src, int64_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
 /* a9  top-k eigenvectors of a dense symmetric fp32 matrix (largest algebraic).          */

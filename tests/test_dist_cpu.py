@@ -65,16 +65,32 @@ def test_parallel_func_sharding_without_gpu(tmp_path):
     assert cap.paras == {"near_num": "12"}
 
 
-def test_ring_schedule_covers_every_block_pair_once():
-    from hiarch_b200.sharded import ring_schedule
-    for world in range(1, 10):
-        steps = ring_schedule(world)
-        assert len(steps) == world // 2 + 1
-        pairs = [tuple(sorted(p)) for st in steps for p in st]
-        assert sorted(pairs) == sorted((a, b) for a in range(world) for b in range(a, world))   # once each
-        per_rank = [sum(1 for st in steps for (r, _) in st if r == k) for k in range(world)]
-        assert max(per_rank) - min(per_rank) <= 1                                             # balanced
-        assert max(per_rank) == world // 2 + 1
+def test_ring_plan_covers_every_cell_once_and_is_balanced():
+    """Pure schedule: over all ranks the direct + mirrored stores of `ring_plan` write every cell of
+    the n x n matrix exactly once, and every rank contracts ~world / 2 block products."""
+    from hiarch_b200.sharded import ring_plan, rows_per_rank
+    for world, n in [(1, 300), (2, 1000), (3, 1000), (4, 1100), (5, 900), (8, 4000), (8, 3000), (4, 300), (6, 2000),
+                     (8, 4096), (2, 1024), (4, 2048), (7, 7 * 256)]:
+        per = rows_per_rank(n, world)
+        cover = np.zeros((n, n), dtype=np.int32)
+        work = []
+        for r in range(world):
+            w = 0.0
+            for j in ring_plan(world, r, per, n):
+                i0, j0 = r * per + j["a0"], j["peer"] * per + j["b0"]
+                assert j["a0"] % 128 == 0 and j["b0"] % 128 == 0
+                if j["symmetric"]:
+                    cover[i0:i0 + j["a_rows"], j0:j0 + j["b_rows"]] += 1
+                    w += 0.5 * j["a_rows"] * j["b_rows"]
+                else:
+                    cover[i0:i0 + j["a_rows"], j0:j0 + j["b_rows"]] += 1
+                    cover[j0:j0 + j["b_rows"], i0:i0 + j["a_rows"]] += 1
+                    w += j["a_rows"] * j["b_rows"]
+            work.append(w / per ** 2)
+        assert cover.min() == 1 and cover.max() == 1, (world, n)
+        assert max(work) <= world / 2 + 1e-9, (world, n, work)          # never more than world / 2 blocks
+        if n == world * per and per % 256 == 0:                         # full blocks: perfectly balanced
+            assert max(work) - min(work) <= 1e-9 and abs(work[0] - world / 2) <= 1e-9, (world, n, work)
 
 
 def _free_port():
@@ -99,16 +115,18 @@ def _run_ring(world, n, k, port=None):
 
 
 def test_ring_similarity_exchange_logic_on_gloo():
-    """RingSimilarity's schedule / plane exchange / mirrored-block return with a torch stand-in for
-    the kernels: every rank ends up with exactly its rows of the full Pearson matrix (ragged and
-    empty last blocks included), having contracted only world/2 + 1 blocks."""
-    for world, n in ((2, 200), (3, 300), (4, 400), (4, 300)):
+    """RingSimilarity's schedule on shared-memory "peer" buffers with a torch stand-in for the
+    kernels: every rank ends up with exactly its rows of the full Pearson matrix (ragged and empty
+    last blocks included), every remote block was pulled before it was contracted, and no rank
+    contracted more than world / 2 block products."""
+    for world, n in ((2, 600), (3, 700), (4, 1100), (4, 300)):
         recs = _run_ring(world, n, 24)
         assert sum(r["rows"] for r in recs) == n
         for r in recs:
             assert r["nan"] == 0, r                              # every column block was filled
             assert r["err"] < 1e-12, r
-            assert r["blocks"] == r["expected_blocks"] and len(r["blocks"]) <= world // 2 + 1
+            assert r["pulls"] == [b for b in r["blocks"] if b != r["rank"]], r
+            assert r["work"] <= world / 2 * r["per"] ** 2 + 1e-9, r
 
 
 def test_ring_similarity_single_process():
@@ -119,7 +137,10 @@ def test_ring_similarity_single_process():
     rng = np.random.default_rng(1)
     x = torch.from_numpy(rng.standard_normal((150, 40)))
     ring = CpuRing(150, 40)
-    out = ring.run(x)
-    xc = x - x.mean(dim=1, keepdim=True)
-    xc = xc / xc.norm(dim=1, keepdim=True)
-    assert ring.blocks_done == [0] and float((out - xc @ xc.t()).abs().max()) < 1e-12
+    try:
+        out = ring.run(x)
+        xc = x - x.mean(dim=1, keepdim=True)
+        xc = xc / xc.norm(dim=1, keepdim=True)
+        assert [e[2] for e in ring.log] == [0] and float((out - xc @ xc.t()).abs().max()) < 1e-12
+    finally:
+        ring.cleanup()

@@ -12,6 +12,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 @pytest.mark.parametrize("n", [1500, 3333])
 def test_row_sharded_similarity_and_eigen_match_single_gpu(n):
     import torch
@@ -20,7 +27,7 @@ def test_row_sharded_similarity_and_eigen_match_single_gpu(n):
         pytest.skip("needs 2 GPUs")
     world = 2 if ngpu < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29631",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(n)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-3000:]
@@ -32,7 +39,10 @@ def test_row_sharded_similarity_and_eigen_match_single_gpu(n):
         assert r["restart_rel"] <= 1e-6 and r["restart_cycles"] == [3, 3], r
         assert r["oe_err"] <= 2e-6, r                   # fp64 partial sums add in a different order
         assert min(r["cos"]) >= 0.9999, r
-        if r.get("ring_err") is not None:               # HIA_TEST_RING=1: the symmetric ring schedule
-            assert r["ring_err"] <= 2e-6, r
+        assert r["ring_err"] <= 2e-6, r                 # symmetric ring over peer memory == single GPU
+        assert r["ring_sym"] == 0.0, r                  # the diagonal block is symmetric bit for bit
+        assert r["ring_blocks"] <= world / 2 + 1e-9, r  # world / 2 block products per rank, not world
+        assert r["chain_err"] <= 1e-5 and r["chain_cnt"] >= 256, r      # in-run fp64 spot check of the chain
+        assert r["chain_eig_rel"] <= 1e-6 and min(r["chain_cos"]) >= 0.9999, r
     covered = sorted((r["rows"][0], r["rows"][1]) for r in recs)
     assert sum(c[1] for c in covered) == n

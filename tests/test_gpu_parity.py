@@ -129,6 +129,11 @@ def _check_oe(dense64, seps, bs):
             assert np.allclose(exp[s:e + 1], rexp, rtol=1e-6, atol=0)
     go = got_oe.cpu().numpy().astype(np.float64)
     assert np.all(np.abs(go - ref_oe) <= ATOL + 2e-7 * np.abs(ref_oe))
+    # the fp64 output holds the north star's 1e-5 ABSOLUTE with no relative term, whatever the value
+    got64, _ = ops.obs_d_exp(dmap, layout, bs, fp64_out=True)
+    assert got64.dtype == torch.float64 and np.abs(got64.cpu().numpy() - ref_oe).max() <= ATOL
+    got64_oi, _ = ops.obs_d_exp(dmap, layout, bs, only_intra=True, fp64_out=True)
+    assert np.abs(got64_oi.cpu().numpy() - O.obs_d_exp(dense64, seps, bs, only_intra=True)).max() <= ATOL
     assert np.abs(got_log.cpu().numpy().astype(np.float64) - ref_log).max() <= ATOL
     # no clamp, only_intra
     got_nc, _ = ops.obs_d_exp(dmap, layout, bs, counts_must_decrese=False, log=True)
@@ -159,6 +164,8 @@ def test_oe_against_reference_golden(golden, case):
     got_log, _ = ops.obs_d_exp(dense, layout, bs, log=True)
     ref = g["oe"]
     assert np.all(np.abs(got.cpu().numpy() - ref) <= ATOL + 2e-7 * np.abs(ref))
+    got64, _ = ops.obs_d_exp(dense, layout, bs, fp64_out=True)          # raw O/E: 1e-5 absolute, no relative term
+    assert np.abs(got64.cpu().numpy() - ref).max() <= ATOL
     assert np.abs(got_log.cpu().numpy() - g["oe_log"]).max() <= ATOL
     s, e = seps[-1]
     assert np.allclose(state.expected.cpu().numpy()[s:e + 1], g["expected_last_block"], rtol=1e-6)

@@ -41,54 +41,7 @@ def make_rows(n, row0, rows, seed, device, chunk=2048):
     return x
 
 
-def _hash_uniform(key, salt):
-    """Counter-based uniform in (0, 1) from an int64 key (splitmix-like; wraps mod 2^64)."""
-    z = key + salt
-    z = (z ^ (z >> 30)) * -4658895280553007687          # 0xBF58476D1CE4E5B9 as int64
-    z = (z ^ (z >> 27)) * -7723592293110705685          # 0x94D049BB133111EB
-    z = z ^ (z >> 31)
-    return ((z >> 11) & ((1 << 53) - 1)).double() * (1.0 / (1 << 53)) * (1 - 2e-16) + 1e-16
-
-
-def make_count_rows(lens, row0, rows, seed, device, lam_inter=0.6, chunk=1024):
-    """rows x n block of a SYMMETRIC synthetic count map (SURVEY 8d generator): the sample of cell
-    (i, j) is a deterministic function of (min(i,j), max(i,j), seed), so every rank generates a
-    consistent slice without any rank holding the whole map. Poisson by inverse CDF (lambda <= 12)
-    or the rounded normal approximation (lambda > 12)."""
-    n = int(sum(lens))
-    seps = synth.chr_seps_from_lens(lens)
-    rng = np.random.default_rng(seed)
-    comps = np.stack([np.sqrt(b) * np.concatenate([synth.compartment_track(L, rng, max(3, L // (40 * (m + 1))))
-                                                   for L in lens]) for m, b in enumerate(synth.COMPONENT_BETAS)], axis=1)
-    comp = torch.from_numpy(comps).to(device=device, dtype=torch.float32)
-    bin_chr = torch.from_numpy(np.concatenate([np.full(L, c, dtype=np.int64) for c, L in enumerate(lens)])).to(device)
-    x = torch.empty((rows, ops.padded_ld(n)), dtype=torch.float32, device=device)[:, :n]
-    jj = torch.arange(n, device=device, dtype=torch.int64)
-    for r in range(0, rows, chunk):
-        r1 = min(rows, r + chunk)
-        ii = torch.arange(row0 + r, row0 + r1, device=device, dtype=torch.int64)
-        lo_ = torch.minimum(ii[:, None], jj[None, :])
-        hi_ = torch.maximum(ii[:, None], jj[None, :])
-        key = lo_ * n + hi_
-        cc = 1.0 + comp[row0 + r:row0 + r1] @ comp.T
-        same = bin_chr[row0 + r:row0 + r1, None] == bin_chr[None, :]
-        d = (hi_ - lo_).float()
-        lam = torch.where(same, synth.A_INTRA * (d + 1.0) ** (-synth.ALPHA) * cc, lam_inter * cc).double()
-        u = _hash_uniform(key, seed * 7919 + 1)
-        # small lambda: inverse CDF
-        k = torch.zeros_like(lam)
-        p = torch.exp(-lam)
-        cdf = p.clone()
-        for t in range(1, 40):
-            k += (u > cdf).double()
-            p = p * lam / t
-            cdf += p
-        # large lambda: normal approximation with a second hashed uniform (Box-Muller)
-        u2 = _hash_uniform(key, seed * 7919 + 2)
-        z = torch.sqrt(-2.0 * torch.log(u)) * torch.cos(2 * np.pi * u2)
-        big = torch.clamp(torch.round(lam + torch.sqrt(lam) * z), min=0.0)
-        x[r:r1] = torch.where(lam > 12.0, big, k).float()
-    return x, seps
+make_count_rows = synth.device_count_rows
 
 
 def main():

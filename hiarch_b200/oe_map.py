@@ -76,10 +76,36 @@ def denoise_one_method(sps_mtx, mode='wavelet', sigma=None, spatial_sigma_ratio=
     return ArrayHiCMtx(out, copy_mtx_paras=d)
 
 
+class WaveletSkippedWarning(UserWarning):
+    """The wavelet step of the reference's denoise was not applied (see main_denoise)."""
+
+
+def _resolve_wavelet(wavelet):
+    """None -> warn loudly (the output then differs from the reference pipeline's), 'identity' ->
+    the caller opted out explicitly, callable -> applied per block."""
+    if wavelet is None:
+        import warnings
+        msg = ("wavelet denoise (skimage denoise_wavelet db3/VisuShrink, publish/oe_map/S3_denoise.py:43-47) "
+               "is NOT applied: scikit-image/PyWavelets arithmetic is third-party and unpinned. The "
+               "`.de_ode.mtx` written under the reference's name is clip -> median only. Pass "
+               "wavelet=<callable on a block> to apply one, or wavelet='identity' to silence this.")
+        warnings.warn(msg, WaveletSkippedWarning, stacklevel=3)
+        print(f'Warning: {msg}')
+        return None
+    if isinstance(wavelet, str):
+        if wavelet != 'identity':
+            raise ValueError(f"wavelet={wavelet!r}: pass a callable or 'identity'")
+        return None
+    return wavelet
+
+
 def main_denoise(sps_map, wavelet=None):
-    """S3_denoise.py:95-107: clip to [p2, p98], then per block wavelet -> median. The wavelet is
-    NOT available (see denoise_one_method); `wavelet` may be a callable applied per block to
-    keep both sides of a comparison identical; default = skip it (identity)."""
+    """S3_denoise.py:95-107: clip to [p2, p98], then per block wavelet -> median. The reference's
+    wavelet is NOT available (see denoise_one_method): `wavelet` = a callable applied per block
+    (e.g. the same substitute on both sides of a comparison), 'identity' = skip it knowingly,
+    None (default) = skip it with a WaveletSkippedWarning + a 'Warning:' line on stdout. The result
+    carries `.wavelet_applied`."""
+    wavelet = _resolve_wavelet(wavelet)
     d = _dense_all(sps_map)
     clipped = tid_off_outliers(d)
     out = ops.alloc_map(d.shape[0], d.dmatrix.device)
@@ -91,15 +117,16 @@ def main_denoise(sps_map, wavelet=None):
         s1, e1 = d.row_window.chr_seps[c1]
         s2, e2 = d.col_window.chr_seps[c2]
         out[s1:e1 + 1, s2:e2 + 1].copy_(den.dmatrix)
+    res.wavelet_applied = wavelet is not None
     return res
 
 
 def oe_map_main(sps_mtx, output=None, fig_output=None, centr_loc=None,
-                do_filt_chr_by_name=False, counts_must_decrese=True):
+                do_filt_chr_by_name=False, counts_must_decrese=True, wavelet=None):
     """main_get_oe.py:10-59, the NormDis step on an already parsed map: preprocess_mtx ->
     oe_map_core -> `<output>.ode.mtx` (+ `.window.bed`) -> main_denoise -> norm_de_mtx ->
-    `<output>.de_ode.mtx`. The plots (`fig_output`, `centr_loc`) are out of scope and ignored; the
-    wavelet inside main_denoise is the identity (see denoise_one_method)."""
+    `<output>.de_ode.mtx`. The plots (`fig_output`, `centr_loc`) are out of scope and ignored;
+    `wavelet` goes to main_denoise (None = skipped WITH a warning, see there)."""
     from .preprocess import preprocess_mtx
     pro_mtx = preprocess_mtx(sps_mtx, do_filt_chr_by_name)
     if pro_mtx is None:
@@ -112,7 +139,7 @@ def oe_map_main(sps_mtx, output=None, fig_output=None, centr_loc=None,
     print('Matrix normalization DONE.')
     if output is not None:
         ode_mtx.to_sps().to_output(f'{output}.ode.mtx')
-    de_ode_mtx = norm_de_mtx(main_denoise(ode_mtx))
+    de_ode_mtx = norm_de_mtx(main_denoise(ode_mtx, wavelet=wavelet))
     print('Denoise normalized matrix DONE.')
     if output is not None:
         de_ode_mtx.to_sps().to_output(f'{output}.de_ode.mtx', out_window=False)
@@ -120,15 +147,16 @@ def oe_map_main(sps_mtx, output=None, fig_output=None, centr_loc=None,
 
 
 def oe_map_io(mtx_file, output, fig_output=None, do_filt_chr_by_name=False, counts_must_decrese=True,
-              index_file=None, input_centr_loc=None, thread=1):
+              index_file=None, input_centr_loc=None, thread=1, wavelet=None):
     """main_get_oe.py:64-76."""
     from .new_hic_class import read_matrix
     sps_mtx = read_matrix(mtx_file, index_file, thread=thread)
-    return oe_map_main(sps_mtx, output, fig_output, None, do_filt_chr_by_name, counts_must_decrese)
+    return oe_map_main(sps_mtx, output, fig_output, None, do_filt_chr_by_name, counts_must_decrese, wavelet=wavelet)
 
 
 def norm_dis(sps_file, index_file, output, fig_output=None, do_filt_chr_by_name=True,
-             counts_must_decrese=True):
+             counts_must_decrese=True, wavelet=None):
     """publish/HiArch/NormDis.py:10-17 (step 1 of one_click_pipeline.sh)."""
     return oe_map_io(sps_file, output, fig_output, index_file=index_file,
-                     do_filt_chr_by_name=do_filt_chr_by_name, counts_must_decrese=counts_must_decrese)
+                     do_filt_chr_by_name=do_filt_chr_by_name, counts_must_decrese=counts_must_decrese,
+                     wavelet=wavelet)

@@ -41,6 +41,20 @@ class CaptureParas(io.StringIO):
         return len(s)
 
 
+class PerCell:
+    """Picklable per-file keyword value: `template.format(cell=name)` (what update_para_output
+    stores; a lambda would not survive the pickling of the spawned workers' arguments)."""
+
+    def __init__(self, template):
+        self.template = template
+
+    def __call__(self, cell):
+        return self.template.format(cell=cell)
+
+    def __repr__(self):
+        return f"PerCell({self.template!r})"
+
+
 def _worker(shard_id, file_names, mtx_files, func, func_kwargs, n_gpus, capture_paras, sink):
     import torch
     if n_gpus > 0:
@@ -96,7 +110,7 @@ class ParallelFunc:
         self.func_kwargs.update(new_dict)
 
     def update_para_output(self, output, output_para='output'):
-        self.func_kwargs[output_para] = lambda cell: f'{output}/{cell}'
+        self.func_kwargs[output_para] = PerCell(str(output).replace('{', '{{').replace('}', '}}') + '/{cell}')
 
     def shards(self, thread):
         return [[self.file_names[i] for i in idx] for idx in yield_mp_idxes(len(self.file_names), thread)]
@@ -115,6 +129,13 @@ class ParallelFunc:
                 _worker(i, names, self.mtx_files, self.func, self.func_kwargs, n_gpus, capture_paras, sink)
             results = sink
         else:
+            import pickle
+            for name, v in self.func_kwargs.items():      # fail early and clearly, not inside a worker
+                try:
+                    pickle.dumps(v)
+                except Exception as e:
+                    raise TypeError(f"func_kwargs[{name!r}] cannot be sent to the worker processes ({e}); use a "
+                                    "module-level function or run_hic_dataset.PerCell('...{cell}...')") from e
             ctx = mp.get_context("spawn")
             with ctx.Manager() as manager:
                 sink = manager.list()

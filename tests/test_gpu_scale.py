@@ -66,7 +66,7 @@ def test_c2_oe_blocks_against_the_oracle(c2):
             ref = O.oe_inter_block(blk)
         got = hp.oe[sa:ea + 1, sb:eb + 1].cpu().numpy().astype(np.float64)
         pos = ref > 0
-        assert pos.sum() > 0.5 * pos.size
+        assert pos.sum() > 0.2 * pos.size
         assert np.abs(got[pos] - np.log(ref[pos] + 1)).max() <= ATOL
         if (~pos).any():
             f = np.unique(got[~pos])

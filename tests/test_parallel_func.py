@@ -82,3 +82,19 @@ def test_worker_failure_is_reported(samples):
     pf = ParallelFunc("synth", "ds", failing, mtx_files=samples)
     with pytest.raises(RuntimeError):
         pf.vali_parallel(thread=2)
+
+
+def out_path_result(mtx, output=None):
+    return {"output": output}
+
+
+def test_update_para_output_survives_spawned_workers(samples, tmp_path):
+    """update_para_output stored a lambda, which cannot be pickled for the spawned workers."""
+    pf = ParallelFunc("synth", "ds", out_path_result, mtx_files=samples)
+    pf.update_para_output(str(tmp_path / "res{1}"))
+    t = pf.vali_parallel(thread=2, capture_paras=False)
+    assert list(t["output"]) == [f"{tmp_path}/res{{1}}/{c}" for c in sorted(samples)]
+    pf.update_func_kwargs({"output": lambda cell: cell})          # a lambda: refused up front, clearly
+    with pytest.raises(TypeError, match="cannot be sent to the worker processes"):
+        pf.vali_parallel(thread=2)
+    assert list(pf.vali_parallel(thread=1, capture_paras=False)["output"]) == sorted(samples)   # in-process is fine

@@ -222,8 +222,16 @@ def parity_checks(hp, rows, cols, vals, w_h, v_h, stripe=384):
     got = hp.raw[r0:r0 + 256]
     cmask = torch.arange(n, device=dev)[None, :] >= (torch.arange(256, device=dev) + r0)[:, None]
     out["scatter_upper_mismatches"] = int(((got != ref) & cmask).sum())
-    out["scatter_symmetry_mismatches"] = int((hp.raw[r0:r0 + 256, r0:r0 + 256] != hp.raw[r0:r0 + 256, r0:r0 + 256].t()).sum())
-    assert out["scatter_upper_mismatches"] == 0 and out["scatter_symmetry_mismatches"] == 0, out
+    out["raw_map"] = "upper triangle only (no mirror pass)" if hp.upper_only else "symmetric"
+    if not hp.upper_only:
+        d = hp.raw[r0:r0 + 256, r0:r0 + 256]
+        out["scatter_symmetry_mismatches"] = int((d != d.t()).sum())
+        assert out["scatter_symmetry_mismatches"] == 0, out
+    assert out["scatter_upper_mismatches"] == 0, out
+    blk_oe = hp.oe[r0:r0 + 256, r0 + 300:r0 + 556] if r0 + 556 <= n else None
+    if blk_oe is not None:                                   # the O/E map itself is symmetric bit for bit
+        out["oe_symmetry_mismatches"] = int((blk_oe != hp.oe[r0 + 300:r0 + 556, r0:r0 + 256].t()).sum())
+        assert out["oe_symmetry_mismatches"] == 0, out
     # O/E + log on the inter block (chr 1 rows, last chromosome's columns)
     (s1, e1), (s2, e2) = hp.layout.seps[0], hp.layout.seps[-1]
     if len(hp.layout.seps) > 1:
@@ -347,7 +355,8 @@ def run_row_sharded(args, world, rank, local, pk, steps=2):
         barrier()
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record()
-        path.normalise(counts, out_rows=oe_rows)
+        oe_marks = []
+        path.normalise(counts, out_rows=oe_rows, marks=oe_marks)
         e[1].record()
         path.similarity(timing=path.ring)
         e[2].record()
@@ -358,6 +367,7 @@ def run_row_sharded(args, world, rank, local, pk, steps=2):
             for key, (i, j) in (("oe_log", (0, 1)), ("similarity", (1, 2)), ("eig", (2, 3)), ("total", (0, 3))):
                 ms[key].append(mx(e[i].elapsed_time(e[j])))
     ring_stats = path.sim.collect_stats() if path.ring else {}
+    oe_phases = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(oe_marks[:-1], oe_marks[1:])}
     err, cnt = path.spot_check_fp64(n_own=16, n_other=64)
     # eigen residual of the sharded result: || C[rows, :] u - lambda u[rows] ||, all-reduced
     vv = v.double()
@@ -376,6 +386,7 @@ def run_row_sharded(args, world, rank, local, pk, steps=2):
                        f"{world} GPUs: count rows -> O/E+log -> Pearson -> top-3 eigvec",
            "scaling": "strong", "bins": n, "rows_per_rank": path.per, "path": path_kind, "peer_mapping_error": ipc_error,
            "ms": {k: float(np.mean(v_)) for k, v_ in ms.items()},
+           "oe_log_phases_ms_rank0": oe_phases,
            "cells_per_s": float(n) * n / (total_ms * 1e-3),
            "similarity": {"block_products_per_rank": blocks, "block_ms": ring_stats.get("block_ms"),
                           "executed_mma_tflops_per_gpu": flop_exec / (sim_ms * 1e-3) / 1e12,

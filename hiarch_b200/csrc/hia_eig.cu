@@ -534,7 +534,11 @@ int launch_symm(const float* c, int rows, int n, long long ld, const float* v, d
   HIA_CUDA(cudaMemsetAsync(y, 0, (size_t)rows * B * sizeof(double), s));
   dim3 grid((n + kSymmCols - 1) / kSymmCols, (rows + kSymmRowsPerCta - 1) / kSymmRowsPerCta);
   const int smem = B * kSymmCols * (int)sizeof(float);
-  HIA_CUDA(cudaFuncSetAttribute(symm_panel_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static bool attr_set = false;                            // once per process and instantiation
+  if (!attr_set) {
+    HIA_CUDA(cudaFuncSetAttribute(symm_panel_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
   symm_panel_kernel<B><<<grid, kSymmWarps * 32, smem, s>>>(c, rows, n, ld, v, y, row_major);
   count_launch();
   return cuda_ok(cudaGetLastError());

@@ -492,13 +492,18 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
     HIA_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
     row_ptr_kernel<<<grid_e, threads, 0, stream>>>(rows, nnz, n, row_ptr, flag);
     HIA_LAUNCH_CHECK();
-    HIA_CUDA(cudaFuncSetAttribute(fill_rows_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSegCols * (int)sizeof(float)));
+    static bool attr_set = false;                          // once per process (idempotent)
+    if (!attr_set) {
+      HIA_CUDA(cudaFuncSetAttribute(fill_rows_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSegCols * (int)sizeof(float)));
+      attr_set = true;
+    }
     dim3 grid_f(n, (n + kSegCols - 1) / kSegCols);
     fill_rows_sorted_kernel<<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(cols, vals, row_ptr, flag, n,
                                                                                         ld, mtx_type, out);
     HIA_LAUNCH_CHECK();
-    dim3 grid_z((n + threads * 4 - 1) / (threads * 4), min(n, 4096));
+    // (a 4096-row grid of CTAs that only read the flag and exit cost 69 us per call: launch list r1)
+    dim3 grid_z((n + threads * 4 - 1) / (threads * 4), min(n, 64));
     zero_fill_if_kernel<<<grid_z, threads, 0, stream>>>(out, n, ld, flag);
     HIA_LAUNCH_CHECK();
     scatter_kernel<true><<<grid_e, threads, 0, stream>>>(rows, cols, vals, nnz, n, mtx_type, out, ld, flag);

@@ -221,7 +221,7 @@ struct SyrkArgs {
   float* out_t;
   long long ld_t;
   unsigned int* sync_ctr;
-  int sync_every, row0, row_end, col0, col_end, symmetric, has_diag;
+  int sync_every, row0, row_end, col0, col_end, symmetric, has_diag, same_planes;
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -284,6 +284,9 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
   if (warp == 0) {
     // ===================================================== TMA producer (one per CTA)
     if (lane == 0) {
+      // one plane set (A == B): both operands go through the SAME two descriptors
+      const CUtensorMap* mb_hi = a.same_planes ? &map_hi : &map_b_hi;
+      const CUtensorMap* mb_lo = a.same_planes ? &map_lo : &map_b_lo;
       uint32_t it = 0;
       for (int t = unit; t < num_tiles; t += num_units) {
         const int m0 = tiles[t].m0 + (int)cta_rank * BM;             // this CTA's rows of A
@@ -312,11 +315,11 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
           tma_load_2d<CTAS>(st, &map_hi, &full_bar[s], k0, m0);                               // A hi
           tma_load_2d<CTAS>(st + A_BYTES, &map_lo, &full_bar[s], k0, m0);                     // A lo
           unsigned char* sb = st + 2 * A_BYTES;
-          tma_load_2d<CTAS>(sb, &map_b_hi, &full_bar[s], k0, nb0);                            // B hi
-          tma_load_2d<CTAS>(sb + G::B_BYTES, &map_b_lo, &full_bar[s], k0, nb0);               // B lo
+          tma_load_2d<CTAS>(sb, mb_hi, &full_bar[s], k0, nb0);                                // B hi
+          tma_load_2d<CTAS>(sb + G::B_BYTES, mb_lo, &full_bar[s], k0, nb0);                   // B lo
           if constexpr (CTAS == 1) {                                                         // rows [128,256) of B
-            tma_load_2d<CTAS>(sb + A_BYTES, &map_b_hi, &full_bar[s], k0, nb0 + BM);
-            tma_load_2d<CTAS>(sb + G::B_BYTES + A_BYTES, &map_b_lo, &full_bar[s], k0, nb0 + BM);
+            tma_load_2d<CTAS>(sb + A_BYTES, mb_hi, &full_bar[s], k0, nb0 + BM);
+            tma_load_2d<CTAS>(sb + G::B_BYTES + A_BYTES, mb_lo, &full_bar[s], k0, nb0 + BM);
           }
         }
       }
@@ -569,6 +572,105 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
   }
 }
 
+// Register-staged variant (the default whenever the rows are 16-byte aligned and <= 131 072 long):
+// the row is read from DRAM exactly ONCE. A cluster of CS = 1 / 2 / 4 CTAs of 1024 threads owns a row;
+// every thread loads 8 float4 (all 128-bit loads issued before the first use: 128 KB in flight per
+// SM), accumulates the fp64 sum / sum of squares of its 32 cells, the cluster combines the CTA
+// partials through distributed shared memory (every CTA stores its pair into every CTA of the
+// cluster, one cluster barrier, fixed summation order), and the hi/lo planes are produced straight
+// from the registers. 4 + 4 (f16) or 4 + 8 (tf32) bytes per cell, nothing re-read.
+constexpr int kRegThreads = 1024;
+constexpr int kRegVec = 8;                                   // float4 per thread
+constexpr int kRegCellsPerCta = kRegThreads * kRegVec * 4;   // 32 768
+
+template <int PREC>
+__global__ void __launch_bounds__(kRegThreads, 1)
+row_prep_reg_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int kpad, int center,
+                    typename PlaneT<PREC>::type* __restrict__ hi, typename PlaneT<PREC>::type* __restrict__ lo) {
+  typedef typename PlaneT<PREC>::type P;
+  __shared__ double s_red[kRegThreads / 32][2];
+  __shared__ double s_part[4][2];                            // partials of the (<= 4) CTAs of the cluster
+  uint32_t cs, cr;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(cs));
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cr));
+  const int r = blockIdx.x / (int)cs;                        // grid = m * cs: never beyond the last row
+  const float* row = x + (long long)r * ld_x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n4 = kpad >> 2;                                  // float4 groups of the plane row
+  const int g0 = (int)cr * kRegThreads * kRegVec;            // first group of this CTA
+  const float shift_f = __ldg(row);
+  const double shift = (double)shift_f;
+  float4 v[kRegVec];
+  // cells beyond the row take the value of the shift: they add exactly 0 to both sums (no masks below)
+#pragma unroll
+  for (int i = 0; i < kRegVec; ++i) {
+    const int j = (g0 + tid + i * kRegThreads) << 2;
+    if (j + 3 < k) v[i] = ld_stream4(row + j);
+    else {
+      v[i].x = (j < k) ? row[j] : shift_f;
+      v[i].y = (j + 1 < k) ? row[j + 1] : shift_f;
+      v[i].z = (j + 2 < k) ? row[j + 2] : shift_f;
+      v[i].w = shift_f;
+    }
+  }
+  double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < kRegVec; ++i) {
+    const double a = (double)v[i].x - shift, b = (double)v[i].y - shift, c = (double)v[i].z - shift,
+                 d = (double)v[i].w - shift;
+    s1 += (a + b) + (c + d);
+    s2 += (a * a + b * b) + (c * c + d * d);
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) { s_red[w][0] = s1; s_red[w][1] = s2; }
+  __syncthreads();
+  if (tid == 0) {
+    double t1 = 0, t2 = 0;
+    for (int i = 0; i < kRegThreads / 32; ++i) { t1 += s_red[i][0]; t2 += s_red[i][1]; }
+    if (cs == 1) { s_part[0][0] = t1; s_part[0][1] = t2; }
+    else {
+      const uint32_t local = smem_u32(&s_part[cr][0]);
+      for (uint32_t dst = 0; dst < cs; ++dst) {              // my pair into slot `cr` of every CTA
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(dst));
+        asm volatile("st.shared::cluster.f64 [%0], %1;" :: "r"(remote), "d"(t1) : "memory");
+        asm volatile("st.shared::cluster.f64 [%0], %1;" :: "r"(remote + 8), "d"(t2) : "memory");
+      }
+    }
+  }
+  if (cs == 1) __syncthreads(); else cluster_sync_all();
+  double t1 = 0.0, t2 = 0.0;
+  for (uint32_t i = 0; i < cs; ++i) { t1 += s_part[i][0]; t2 += s_part[i][1]; }
+  // Pearson: centre on the mean; cosine: centre on 0 (= shift back)
+  const double mean_s = center ? t1 / (double)k : -shift;
+  const double ss = t2 - 2.0 * mean_s * t1 + (double)k * mean_s * mean_s;
+  const double mean = mean_s + shift;
+  const double inv = 1.0 / sqrt(ss > 0.0 ? ss : 0.0);        // inf for an all-zero row -> NaN, like pdist
+  P* ph = hi + (long long)r * kpad;
+  P* pl = lo + (long long)r * kpad;
+#pragma unroll
+  for (int i = 0; i < kRegVec; ++i) {
+    const int g = g0 + tid + i * kRegThreads;
+    if (g >= n4) continue;
+    const int j = g << 2;
+    const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    P h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (j + q < k) split_hi_lo<PREC>((float)(((double)e[q] - mean) * inv), h[q], l[q]);
+      else { h[q] = P(0.f); l[q] = P(0.f); }
+    }
+    if constexpr (PREC == HIA_PREC_3XF16) {
+      *reinterpret_cast<uint2*>(ph + j) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(pl + j) = *reinterpret_cast<const uint2*>(l);
+    } else {
+      *reinterpret_cast<float4*>(ph + j) = *reinterpret_cast<const float4*>(h);
+      *reinterpret_cast<float4*>(pl + j) = *reinterpret_cast<const float4*>(l);
+    }
+  }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -662,9 +764,37 @@ __global__ void __launch_bounds__(1024) tile_list_kernel(const TileSpace ts, Til
   }
 }
 
+template <int PREC>
+int launch_prep_reg(const float* x, int rows, int k, long long ld_x, int kpad, int center, void* hi, void* lo,
+                    int cs, cudaStream_t stream) {
+  typedef typename PlaneT<PREC>::type P;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)rows * cs, 1, 1);
+  cfg.blockDim = dim3(kRegThreads, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HIA_CUDA(cudaLaunchKernelEx(&cfg, row_prep_reg_kernel<PREC>, x, rows, k, ld_x, kpad, center,
+                              static_cast<P*>(hi), static_cast<P*>(lo)));
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
 int launch_prep(const float* x, int rows, int k, long long ld_x, int center, void* hi, void* lo, int prec,
                 cudaStream_t stream) {
   const int kpad = round_up(k, bk_of(prec));
+  // one DRAM read per cell: rows staged in the registers of a 1 / 2 / 4-CTA cluster (HIA_PREP_REG=0: two-pass kernel)
+  static const bool use_reg = !(getenv("HIA_PREP_REG") && atoi(getenv("HIA_PREP_REG")) == 0);
+  const int cs = kpad <= kRegCellsPerCta ? 1 : (kpad <= 2 * kRegCellsPerCta ? 2 : 4);
+  if (use_reg && kpad <= 4 * kRegCellsPerCta && aligned16(x) && (ld_x & 3) == 0) {
+    if (prec == HIA_PREC_3XF16) return launch_prep_reg<HIA_PREC_3XF16>(x, rows, k, ld_x, kpad, center, hi, lo, cs, stream);
+    return launch_prep_reg<HIA_PREC_3XTF32>(x, rows, k, ld_x, kpad, center, hi, lo, cs, stream);
+  }
   if (prec == HIA_PREC_3XF16)
     row_prep_kernel<HIA_PREC_3XF16><<<rows, kPrepThreads, 0, stream>>>(x, rows, k, ld_x, kpad, center,
                                                              static_cast<__half*>(hi), static_cast<__half*>(lo));
@@ -924,6 +1054,7 @@ static int launch_gemm(const GemmJob& j, cudaStream_t stream) {
   a.col_end = j.col_end;
   a.symmetric = j.symmetric;
   a.has_diag = j.has_diag;
+  a.same_planes = (j.a_hi == j.b_hi && j.a_lo == j.b_lo && j.a_plane_rows == j.b_plane_rows) ? 1 : 0;
   if (j.prec == HIA_PREC_3XF16)
     return ctas == 2 ? launch_syrk<HIA_PREC_3XF16, 2>(maps, a, stream) : launch_syrk<HIA_PREC_3XF16, 1>(maps, a, stream);
   return ctas == 2 ? launch_syrk<HIA_PREC_3XTF32, 2>(maps, a, stream) : launch_syrk<HIA_PREC_3XTF32, 1>(maps, a, stream);

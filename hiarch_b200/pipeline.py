@@ -15,7 +15,7 @@ from . import _lib, ops
 
 class HotPath:
     def __init__(self, seps, bin_size, k_eig=3, flavour=ops.SIM_PEARSON, device="cuda",
-                 max_nnz=None, eig_block=8, eig_steps=12, precision=None):
+                 max_nnz=None, eig_block=8, eig_steps=12, precision=None, upper_only=None):
         self.lib = _lib.load()
         self.layout = ops.GenomeLayout(seps, device)
         self.n = self.layout.n
@@ -35,7 +35,10 @@ class HotPath:
                                   dtype=torch.uint8, device=device)
         self.eig_block, self.eig_steps = eig_block, eig_steps
         self.layout.oe_tables(self.bin_size)         # build + upload the SGD pooling tables once
-        self.upper_only = os.environ.get("HIA_UPPER_ONLY", "0") == "1"
+        # upper_only (default; HIA_UPPER_ONLY=0 or upper_only=False for the mirrored map): the expected pass
+        # and the apply pass read the upper triangle of `raw` only, so the scatter skips its mirror pass and
+        # `raw` keeps an UNWRITTEN lower triangle (`raw_symmetric()` completes it on demand)
+        self.upper_only = (os.environ.get("HIA_UPPER_ONLY", "1") == "1") if upper_only is None else bool(upper_only)
         self.max_nnz = max_nnz
         if max_nnz:
             self.d_rows = torch.empty(max_nnz, dtype=torch.int32, device=device)
@@ -43,10 +46,14 @@ class HotPath:
             self.d_vals = torch.empty(max_nnz, dtype=torch.float32, device=device)
 
     # ---- stages -------------------------------------------------------------------------
+    def raw_symmetric(self):
+        """The dense symmetric count map (a copy when `raw` holds the upper triangle only)."""
+        if not self.upper_only:
+            return self.raw
+        up = torch.triu(self.raw)
+        return up + torch.triu(up, 1).t()
+
     def scatter(self, rows, cols, vals):
-        # upper_only (opt-in, HIA_UPPER_ONLY=1): the expected pass and the apply pass read the upper
-        # triangle only, so the scatter's mirror pass (0.9 of 2.2 ms at 30 894 bins) is skipped and
-        # `raw` keeps an unwritten lower triangle
         mt = ops.MTX_TRIU_UPPER if self.upper_only else ops.MTX_TRIU
         return ops.scatter_coo_sym(rows, cols, vals, self.n, mtx_type=mt, out=self.raw)
 

@@ -377,7 +377,7 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, angle_tol=1e-3, m
 
 
 def obs_d_exp_rows(map_rows, layout, bin_size, row0, k=.2, counts_must_decrese=True, only_intra=False,
-                   log=True, out_rows=None, group=None):
+                   log=True, out_rows=None, group=None, marks=None):
     """Row-sharded O/E (+log): `map_rows` = global rows [row0, row0 + rows) of the symmetric map.
     Partial diagonal / inter-block statistics are all-reduced (N + 3 C^2 numbers), the SGD pooling
     + clamp is replicated, the apply pass touches the own rows only. Returns (out_rows, state)."""
@@ -388,23 +388,34 @@ def obs_d_exp_rows(map_rows, layout, bin_size, row0, k=.2, counts_must_decrese=T
     pool_gid, use_code = layout.oe_tables(bin_size, k)
     st_ = ops.OEState(layout)
     s = ops._stream()
+
+    def mark(name):                      # optional per-phase CUDA events (bench.py)
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
     _lib.check(lib.hia_oe_expected_pass_rows(map_rows.data_ptr(), n, map_rows.stride(0), row0, rows,
                                              layout.chr_start.data_ptr(), layout.chr_start_host.ctypes.data,
                                              layout.n_chr, st_.diag_sum.data_ptr(), st_.diag_minpos.data_ptr(),
                                              st_.inter_sum.data_ptr(), st_.inter_nnz.data_ptr(),
                                              st_.inter_minpos.data_ptr(), layout.bin_chr.data_ptr(), s),
                "hia_oe_expected_pass_rows")
+    mark("expected_pass")
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         for t in (st_.diag_sum, st_.inter_sum, st_.inter_nnz):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         for t in (st_.diag_minpos, st_.inter_minpos):
             dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    mark("all_reduce")
     _lib.check(lib.hia_oe_finalize(st_.diag_sum.data_ptr(), st_.diag_minpos.data_ptr(), st_.inter_sum.data_ptr(),
                                    st_.inter_nnz.data_ptr(), st_.inter_minpos.data_ptr(),
                                    layout.chr_start.data_ptr(), layout.n_chr, n, pool_gid.data_ptr(),
                                    use_code.data_ptr(), 1 if counts_must_decrese else 0,
                                    st_.expected.data_ptr(), st_.inv_expected.data_ptr(),
                                    st_.inter_inv.data_ptr(), st_.min_pos_oe.data_ptr(), s), "hia_oe_finalize")
+    mark("finalize")
     if out_rows is None:
         out_rows = torch.empty((max(rows, 1), map_rows.stride(0)), dtype=torch.float32,
                                device=map_rows.device)[:rows, :n]
@@ -414,6 +425,7 @@ def obs_d_exp_rows(map_rows, layout, bin_size, row0, k=.2, counts_must_decrese=T
                                      layout.chr_start.data_ptr(), layout.n_chr, layout.bin_chr.data_ptr(),
                                      st_.inv_expected.data_ptr(), st_.inter_inv.data_ptr(),
                                      st_.min_pos_oe.data_ptr(), flags, s), "hia_oe_apply_rows")
+    mark("apply")
     return out_rows, st_
 
 
@@ -447,9 +459,9 @@ class RowShardedPath:
                                     device=self.device)[:self.rows, :self.n]
         self.oe_rows = None
 
-    def normalise(self, count_rows, out_rows=None):
+    def normalise(self, count_rows, out_rows=None, marks=None):
         self.oe_rows, self.oe_state = obs_d_exp_rows(count_rows, self.layout, self.bin_size, self.row0, log=True,
-                                                     out_rows=out_rows, group=self.group)
+                                                     out_rows=out_rows, group=self.group, marks=marks)
         return self.oe_rows
 
     def similarity(self, timing=False):

@@ -539,7 +539,6 @@ def test_used_filter_normalised_on_massively_tied_blocks():
         assert np.all(np.abs(got - ref) <= 2e-6 + 2e-7 * np.abs(ref)), (shape, size, np.abs(got - ref).max())
 
 
-@pytest.mark.xfail(strict=False, reason="added at the end of round 1 with no GPU minutes left: first run pending")
 def test_oe_and_min_fill_on_the_option_fixtures(golden):
     """goptions.npz (real reference, tests/golden/gen_golden_options.py): ragged chromosomes
     (70 / 12 / 31 / 6 bins, all-zero diagonals, an all-zero inter block), only_intra, and the global

@@ -46,14 +46,15 @@ def test_c2_scatter_is_bit_exact(c2):
     ref = torch.zeros((n, n), dtype=torch.float32, device="cuda")
     ref.index_put_((rows.long(), cols.long()), vals, accumulate=True)
     ref = torch.triu(ref) + torch.triu(ref, 1).t()
-    assert torch.equal(hp.raw, ref)
+    assert hp.upper_only and torch.equal(torch.triu(hp.raw), torch.triu(ref))     # raw = upper triangle only
+    assert torch.equal(hp.raw_symmetric(), ref)
 
 
 def test_c2_oe_blocks_against_the_oracle(c2):
     hp, seps, names = c2["hp"], c2["seps"], c2["names"]
     a, b = names.index("chr21"), names.index("chr22")
     (s1, e1), (s2, e2) = seps[a], seps[b]
-    raw = hp.raw
+    raw = hp.raw_symmetric()                                    # hp.raw itself holds the upper triangle only
     # the fill of non-positive cells is ln(1 + min positive O/E) over the WHOLE map: take the logged
     # value of the smallest positive cell from the oracle blocks as an upper bound and require that the
     # GPU uses ONE value everywhere that is <= every positive logged cell
@@ -75,7 +76,7 @@ def test_c2_oe_blocks_against_the_oracle(c2):
             assert f[0] <= np.log(ref[pos] + 1).min() + ATOL
     assert len(set(fills)) <= 1
     if fills:
-        pos_all = hp.raw > 0
+        pos_all = hp.raw_symmetric() > 0
         assert abs(float(hp.oe[pos_all].min()) - fills[0]) <= 1e-7          # == the global minimum of the logged map
 
 

@@ -1,38 +1,58 @@
-"""CPU: numpy emulation of the loop structure of `oe_apply_upper_kernel` (csrc/hia_oe.cu: 32 x 32
-tiles of the upper triangle, 256 threads as (tx, ty), 4 rows per thread, shared tile, transposed
-write) against a direct evaluation of the full symmetric map. Written from the kernel source: it
-guards the index logic (diagonal tiles, ragged edge tiles, the lower triangle of the input is
-NaN-poisoned and must never be read) of a kernel that had not run on a GPU when it was written."""
+"""CPU: numpy emulation of the loop structure of `oe_apply_upper_kernel` (csrc/hia_oe.cu: 64 x 64
+tiles of the upper triangle, 256 threads as (tx = float4 column group, ty), 4 rows per thread, all
+four 128-bit loads before any store, shared tile, transposed 128-bit write) against a direct
+evaluation of the full symmetric map. Written from the kernel source: it guards the index logic
+(diagonal tiles, ragged edge tiles and float4 groups that straddle the diagonal or the edge; the
+lower triangle of the input is NaN-poisoned and must never reach the output)."""
 import numpy as np
+T = 64
 def emulate(map_, n, ld, chr_start, bin_chr, inv_expected, inter_inv, n_chr, only_intra, do_log, fill):
     out=np.full((n,ld),np.nan,dtype=np.float32)
-    nt=(n+31)//32
+    nt=(n+T-1)//T
     for bi in range(nt):
         for bj in range(nt):
             if bj<bi: continue
-            tile=np.zeros((32,33),dtype=np.float32)
+            tile=np.zeros((T,T+1),dtype=np.float32)
+            diag_tile = bi==bj
             # phase 1
             for tid in range(256):
-                tx,ty=tid&31,tid>>5
-                c=bj*32+tx
-                cb=bin_chr[min(c,n-1)]
+                tx,ty=tid&15,tid>>4
+                c0=bj*T+4*tx
+                cb=[bin_chr[min(c0+j,n-1)] for j in range(4)]
                 for k in range(4):
-                    r=bi*32+ty+8*k
-                    v=np.float32(0)
-                    if r<n and c<n and c>=r:
-                        v=np.float32(map_[r,c])
-                        a=bin_chr[r]
-                        if a==cb: v=np.float32(v*inv_expected[chr_start[a]+(c-r)])
-                        else: v=np.float32(0) if only_intra else np.float32(v*inter_inv[a*n_chr+cb])
-                        if do_log: v=np.float32(np.log(np.float32(1)+v)) if v>0 else fill
-                        out[r,c]=v
-                    tile[ty+8*k,tx]=v
+                    r=bi*T+ty+16*k
+                    v=[np.float32(0)]*4
+                    if r<n and c0<n:
+                        a=bin_chr[r]; s=chr_start[a]
+                        assert c0+3<ld                      # the 128-bit load stays inside the padded row
+                        raw=[np.float32(map_[r,c0+j]) for j in range(4)]
+                        for j in range(4):
+                            c=c0+j
+                            if c<n and c>=r:
+                                x=raw[j]
+                                if cb[j]==a: x=np.float32(x*inv_expected[s+(c-r)])
+                                else: x=np.float32(0) if only_intra else np.float32(x*inter_inv[a*n_chr+cb[j]])
+                                if do_log: x=np.float32(np.log(np.float32(1)+x)) if x>0 else fill
+                                v[j]=x
+                        if c0>=r and c0+3<n:
+                            for j in range(4): out[r,c0+j]=v[j]       # one float4 store
+                        else:
+                            for j in range(4):
+                                if c0+j<n and c0+j>=r: out[r,c0+j]=v[j]
+                    for j in range(4): tile[ty+16*k,4*tx+j]=v[j]
             # phase 2
             for tid in range(256):
-                tx,ty=tid&31,tid>>5
+                tx,ty=tid&15,tid>>4
                 for k in range(4):
-                    r=bj*32+ty+8*k; cc=bi*32+tx
-                    if r<n and cc<n and r>cc: out[r,cc]=tile[tx,ty+8*k]
+                    R=bj*T+ty+16*k; C0=bi*T+4*tx
+                    if R>=n or C0>=n: continue
+                    v=[tile[4*tx+j,ty+16*k] for j in range(4)]
+                    if not diag_tile:
+                        assert C0+3<n and C0+3<R
+                        for j in range(4): out[R,C0+j]=v[j]
+                    else:
+                        for j in range(4):
+                            if C0+j<R: out[R,C0+j]=v[j]
     return out
 def direct(full, n, chr_start, bin_chr, inv_expected, inter_inv, n_chr, only_intra, do_log, fill):
     out=np.zeros((n,n),dtype=np.float32)
@@ -46,7 +66,7 @@ def direct(full, n, chr_start, bin_chr, inv_expected, inter_inv, n_chr, only_int
     return out
 def test_upper_apply_kernel_index_logic():
     rng = np.random.default_rng(0)
-    for lens in ([70,45,20],[33],[31,1,64]):
+    for lens in ([70,45,20],[33],[31,1,64],[64,64],[130,2,61]):
         n=sum(lens); ld=(n+3)//4*4
         chr_start=np.concatenate([[0],np.cumsum(lens)]).astype(int)
         bin_chr=np.repeat(np.arange(len(lens)),lens)

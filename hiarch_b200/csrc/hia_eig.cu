@@ -13,9 +13,12 @@
 //   T = sym(H) -> Jacobi -> Ritz vectors U = Q Z[:, top k]; residuals ||C u - lambda u||
 // Panels are stored column-major (each vector contiguous, ld = n).
 #include "hia_common.cuh"
+#include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace hia {
 namespace {
+namespace cg = cooperative_groups;
 
 constexpr int kMaxBlock = 16;
 constexpr int kSymmCols = 1024;       // columns of C per shared-memory V chunk (2048 measured slower: 844 vs 815 us)
@@ -156,6 +159,178 @@ symm_panel_kernel(const float* __restrict__ c, int rows, int n, long long ld, co
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Y = C V from the UPPER TRIANGLE of a symmetric C only: half the DRAM bytes of symm_panel_kernel
+// (the pass is HBM-bound). A CTA owns a block of 128 columns J and a segment of 1024 rows that lies
+// on or above it; lane l of every warp owns the 4 columns c0 + 4 l .. + 3 for the whole CTA, warps take
+// groups of 4 rows. Every loaded cell C[r][c] (c >= r) feeds BOTH products
+//     row part     y[r] += C[r][c] v[c]            (v of the lane's 4 columns lives in registers)
+//     column part  y[c] += C[r][c] v[r]  (c > r)   (accumulators of the lane's 4 columns in registers)
+// Row parts are reduced over the 32 lanes (transposing butterfly) and written -- not added -- to a
+// partial buffer P[J][r][B]; column parts are reduced over the 8 warps through shared memory and
+// written to Pc[segment][c][B]. symm_upper_reduce_kernel then sums the partials of a row in a fixed
+// order in fp64 (deterministic; the extra traffic is 2 x 128 B per 2 KB of C, ~12 %).
+// ---------------------------------------------------------------------------------------------
+constexpr int kUpCols = 128;               // columns per CTA
+constexpr int kUpSeg = 1024;               // rows per CTA
+constexpr int kUpWarps = 8;
+
+template <int B>
+__global__ void __launch_bounds__(kUpWarps * 32)
+symm_upper_kernel(const float* __restrict__ c, int n, long long ld, const float* __restrict__ v_cm,
+                  float* __restrict__ prow, float* __restrict__ pcol) {
+  // v_cm: n x B panel, column-major (ld n). prow: [nJ][n][B], pcol: [nSeg][n][B] (fp32)
+  extern __shared__ __align__(16) unsigned char s_up_raw[];
+  float (*s_vr)[B] = reinterpret_cast<float (*)[B]>(s_up_raw);                 // v of the segment's rows [kUpSeg][B]
+  float (*s_col)[kUpCols * B] = reinterpret_cast<float (*)[kUpCols * B]>(s_up_raw);   // aliased after the loop
+  const int J = blockIdx.x, seg = blockIdx.y;
+  const int c0 = J * kUpCols, r_seg = seg * kUpSeg;
+  if (r_seg > c0 + kUpCols - 1) return;                     // segment entirely below the block
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r_end = min(min(n, r_seg + kUpSeg), c0 + kUpCols);   // rows beyond the block's last column: nothing above the diagonal
+  for (int idx = threadIdx.x; idx < kUpSeg * B; idx += blockDim.x) {
+    const int r = r_seg + idx / B, j = idx % B;
+    s_vr[idx / B][j] = (r < n) ? v_cm[(long long)j * n + r] : 0.f;
+  }
+  const int gc = c0 + 4 * lane;                             // first of the lane's 4 columns
+  float vc[4][B];                                           // v at the lane's columns
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < B; ++j) vc[q][j] = (gc + q < n) ? v_cm[(long long)j * n + gc + q] : 0.f;
+  float2 cacc[4][B / 2];                                    // column parts: [column][vector pair]
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < B / 2; ++j) cacc[q][j] = make_float2(0.f, 0.f);
+  __syncthreads();
+
+  float* prow_j = prow + (long long)J * n * B;
+  // 8 rows per warp and iteration: all eight 128-bit loads are issued before the first use
+  for (int r0 = r_seg + warp * 8; r0 < r_end; r0 += kUpWarps * 8) {
+    float4 a[8];
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int r = r0 + rr;
+      if (r < r_end && gc < n && gc + 3 >= r) {
+        if (gc + 3 < n) a[rr] = ld_stream4(c + (long long)r * ld + gc);
+        else {
+          const float* p = c + (long long)r * ld + gc;
+          a[rr].x = p[0];
+          a[rr].y = (gc + 1 < n) ? p[1] : 0.f;
+          a[rr].z = (gc + 2 < n) ? p[2] : 0.f;
+          a[rr].w = 0.f;
+        }
+      } else a[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float2 racc[4][B / 2];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int r = r0 + 4 * h + rr;
+        float e[4] = {a[4 * h + rr].x, a[4 * h + rr].y, a[4 * h + rr].z, a[4 * h + rr].w};
+        if (gc < r) {                                       // the float4 straddles the diagonal: mask c < r
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (gc + q < r) e[q] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < B / 2; ++j) racc[rr][j] = make_float2(0.f, 0.f);
+        // row part: sum_q e[q] * v[c_q]
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 ee = make_float2(e[q], e[q]);
+#pragma unroll
+          for (int j = 0; j < B / 2; ++j) racc[rr][j] = ffma2(ee, make_float2(vc[q][2 * j], vc[q][2 * j + 1]), racc[rr][j]);
+        }
+        // column part: e[q] * v[r] for c_q > r (the diagonal cell belongs to the row part only)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (gc + q == r) e[q] = 0.f;
+        const float4* vr4 = reinterpret_cast<const float4*>(&s_vr[min(r, r_seg + kUpSeg - 1) - r_seg][0]);
+        float vr[B];
+#pragma unroll
+        for (int j4 = 0; j4 < B / 4; ++j4) {
+          const float4 t = vr4[j4];
+          vr[4 * j4] = t.x; vr[4 * j4 + 1] = t.y; vr[4 * j4 + 2] = t.z; vr[4 * j4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 ee = make_float2(e[q], e[q]);
+#pragma unroll
+          for (int j = 0; j < B / 2; ++j) cacc[q][j] = ffma2(ee, make_float2(vr[2 * j], vr[2 * j + 1]), cacc[q][j]);
+        }
+      }
+      float part[4 * B];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int j = 0; j < B / 2; ++j) { part[rr * B + 2 * j] = racc[rr][j].x; part[rr * B + 2 * j + 1] = racc[rr][j].y; }
+      const float total = lane_transpose_sum<4 * B>(part, lane);
+      const int idx = lane % (4 * B), rr = idx / B, j = idx % B;
+      if (lane < 4 * B && r0 + 4 * h + rr < r_end) prow_j[(long long)(r0 + 4 * h + rr) * B + j] = total;
+    }
+  }
+  // column parts: reduce over the warps (fixed order) and write Pc[seg][c][B]
+  __syncthreads();                                          // s_vr is dead: alias it
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < B / 2; ++j) {
+      s_col[warp][(4 * lane + q) * B + 2 * j] = cacc[q][j].x;
+      s_col[warp][(4 * lane + q) * B + 2 * j + 1] = cacc[q][j].y;
+    }
+  __syncthreads();
+  float* pcol_s = pcol + ((long long)seg * n + c0) * B;
+  for (int idx = threadIdx.x; idx < kUpCols * B; idx += blockDim.x) {
+    if (c0 + idx / B >= n) break;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kUpWarps; ++w) t += s_col[w][idx];
+    pcol_s[idx] = t;
+  }
+}
+
+// y[r][j] (fp64, row-major) = sum over the column blocks J >= block(r) of P[J][r][j]
+//                           + sum over the row segments seg <= segment(r) of Pc[seg][r][j]
+template <int B>
+__global__ void __launch_bounds__(256)
+symm_upper_reduce_kernel(const float* __restrict__ prow, const float* __restrict__ pcol, int n,
+                         double* __restrict__ y) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * B) return;
+  const int r = (int)(idx / B);
+  const int nJ = (n + kUpCols - 1) / kUpCols;
+  double s = 0.0;
+  for (int J = r / kUpCols; J < nJ; ++J) s += (double)prow[(long long)J * n * B + idx];
+  // column parts of cell (r', r), r' < r, were produced by the segments that hold rows r' < r of block(r)
+  for (int seg = 0; seg <= min(r, (r / kUpCols) * kUpCols + kUpCols - 1) / kUpSeg; ++seg)
+    s += (double)pcol[(long long)seg * n * B + idx];
+  y[idx] = s;
+}
+
+long long symm_upper_ws_bytes(int n, int b) {
+  const long long nJ = (n + kUpCols - 1) / kUpCols, nSeg = (n + kUpSeg - 1) / kUpSeg;
+  return (nJ + nSeg) * (long long)n * b * 4 + 256;
+}
+
+template <int B>
+int launch_symm_upper(const float* c, int n, long long ld, const float* v, double* y, void* ws, cudaStream_t s) {
+  const int nJ = (n + kUpCols - 1) / kUpCols, nSeg = (n + kUpSeg - 1) / kUpSeg;
+  float* prow = static_cast<float*>(ws);
+  float* pcol = prow + (long long)nJ * n * B;
+  const int smem = max(kUpSeg * B, kUpWarps * kUpCols * B) * (int)sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    HIA_CUDA(cudaFuncSetAttribute(symm_upper_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  symm_upper_kernel<B><<<dim3(nJ, nSeg), kUpWarps * 32, smem, s>>>(c, n, ld, v, prow, pcol);
+  HIA_LAUNCH_CHECK();
+  symm_upper_reduce_kernel<B><<<(int)(((long long)n * B + 255) / 256), 256, 0, s>>>(prow, pcol, n, y);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
 }
 
 // Gpart[chunk][p x b] (row-major) = A[chunk rows, 0:p]^T B[chunk rows, 0:b]; A, B col-major fp64, ld = n.
@@ -478,6 +653,215 @@ resid_kernel(const double* __restrict__ w, const double* __restrict__ u, const d
 }
 __global__ void sqrt_kernel(double* x, int k) { if (threadIdx.x < k) x[threadIdx.x] = sqrt(x[threadIdx.x]); }
 
+// ---------------------------------------------------------------------------------------------
+// One Lanczos step after the pass over the matrix, as ONE cooperative kernel (grid-wide barriers
+// between the phases instead of ~20 dependent launches: gram + reduce + subtract + place, twice;
+// gram + reduce + Cholesky + multiply, twice; R2 R1; place -- the launch list of round 1 showed
+// ~2.2 ms of such kernels plus ~3 ms of launch gaps per 8-step cycle at 30 894 bins):
+//   Qn = Y (row-major staging -> column-major block j + 1 of Q)
+//   twice:  G = Q[:, 0:p]^T Qn;  Qn -= Q G;  H[0:p, j-block] (+)= G                       (CGS2)
+//   twice:  S = Qn^T Qn = R^T R;  Qn = Qn R^-1                                            (CholQR2)
+//   H[(j+1)-block, j-block] = R2 R1;  fp32 copy of Qn = the next panel
+// CTA c owns the rows [c * rows_per_cta, ...). Every Gram matrix is reduced in a FIXED order (per-CTA
+// partials, then entry e summed over the CTAs by CTA e mod G): bit-identical on every rank of a
+// row-sharded run, like the kernels it replaces. The b x b Cholesky is computed redundantly by every
+// CTA (same inputs, same code: same bits) -- cheaper than another grid-wide barrier.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStepThreads = 256;
+constexpr int kMaxStepGrid = 256;          // upper bound of the grid (workspace sizing)
+
+struct StepArgs {
+  const double* y_full;                    // n x b row-major (all rows)
+  double* Q;                               // n x D column-major
+  double* H;                               // D x D row-major
+  double* Gpart;                           // [grid][p * b]
+  double* G;                               // [p * b] reduced (also b * b for the Cholesky steps)
+  double* R1;                              // b x b
+  double* R2;                              // b x b
+  float* Vf;                               // n x b column-major fp32 (next panel)
+  int n, b, D, j, rows_per_cta;
+};
+
+// Cholesky of the symmetric b x b matrix g (row-major, shared) -> R (upper), Rinv (upper), by one warp's
+// lane 0 ... small and on the critical path of every CTA, so plain registers / shared arrays only.
+__device__ void chol_small(const double* g, int b, double* R, double* Ri) {
+  double dmax = 0.0;
+  for (int i = 0; i < b; ++i) dmax = fmax(dmax, g[i * b + i]);
+  bool dead[kMaxBlock];
+  for (int i = 0; i < b * b; ++i) { R[i] = 0.0; Ri[i] = 0.0; }
+  for (int j = 0; j < b; ++j) {
+    double d = g[j * b + j];
+    for (int t = 0; t < j; ++t) d -= R[t * b + j] * R[t * b + j];
+    dead[j] = !(d > 1e-24 * dmax) || !(dmax > 0.0);
+    if (dead[j]) { R[j * b + j] = 0.0; continue; }
+    const double rjj = sqrt(d);
+    R[j * b + j] = rjj;
+    const double inv = 1.0 / rjj;
+    for (int c = j + 1; c < b; ++c) {
+      double s = 0.5 * (g[j * b + c] + g[c * b + j]);
+      for (int t = 0; t < j; ++t) s -= R[t * b + j] * R[t * b + c];
+      R[j * b + c] = s * inv;
+    }
+  }
+  for (int j = 0; j < b; ++j) {
+    if (dead[j]) continue;
+    Ri[j * b + j] = 1.0 / R[j * b + j];
+    for (int i = j - 1; i >= 0; --i) {
+      if (dead[i]) continue;
+      double s = 0.0;
+      for (int t = i + 1; t <= j; ++t) s += R[i * b + t] * Ri[t * b + j];
+      Ri[i * b + j] = -s / R[i * b + i];
+    }
+  }
+}
+
+template <int B>
+__global__ void __launch_bounds__(kStepThreads)
+lanczos_step_kernel(const StepArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double s_g[272 * B];                         // reduced Gram matrix (p <= 272 rows)
+  __shared__ double s_r[B * B], s_ri[B * B], s_r1[B * B];
+  const int n = a.n, D = a.D, j = a.j;
+  const int p = (j + 1) * B;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int r_lo = min(n, cta * a.rows_per_cta), r_hi = min(n, r_lo + a.rows_per_cta);
+  double* Qn = a.Q + (long long)p * n;                    // block j + 1
+
+  // ---- Qn <- Y (own rows)
+  for (int r = r_lo + tid; r < r_hi; r += kStepThreads) {
+#pragma unroll
+    for (int c = 0; c < B; ++c) Qn[(long long)c * n + r] = a.y_full[(long long)r * B + c];
+  }
+  __syncthreads();
+
+  // Gram partial of this CTA: out[i][c] = sum_{r in slice} A[r][i] Qn[r][c], i < pa; A column-major (ld n).
+  // Warp w owns the columns i = w, w + 8, ...; four of them per sweep over the slice (the B values of
+  // a Qn row are loaded once per sweep and row), lanes stride over the rows, butterfly at the end.
+  auto gram_partial = [&](const double* A, int pa) {
+    double* out = a.Gpart + (long long)cta * pa * B;
+    const int per_warp = (pa + 7) / 8;
+    for (int ii0 = 0; ii0 < per_warp; ii0 += 4) {
+      double acc[4][B];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int c = 0; c < B; ++c) acc[u][c] = 0.0;
+      for (int r = r_lo + lane; r < r_hi; r += 32) {
+        double q[B];
+#pragma unroll
+        for (int c = 0; c < B; ++c) q[c] = Qn[(long long)c * n + r];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = warp + 8 * (ii0 + u);
+          if (i < pa) {
+            const double x = A[(long long)i * n + r];
+#pragma unroll
+            for (int c = 0; c < B; ++c) acc[u][c] += x * q[c];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = warp + 8 * (ii0 + u);
+#pragma unroll
+        for (int c = 0; c < B; ++c) acc[u][c] = warp_sum(acc[u][c]);
+        if (i < pa && lane == 0) {
+#pragma unroll
+          for (int c = 0; c < B; ++c) out[i * B + c] = acc[u][c];
+        }
+      }
+    }
+  };
+  // fixed-order reduction of the per-CTA partials into a.G, then into shared memory of every CTA
+  auto gram_reduce = [&](int pa) {
+    grid.sync();
+    const int cnt = pa * B;
+    for (int e = cta * kStepThreads + tid; e < cnt; e += G * kStepThreads) {
+      double s = 0.0;
+      for (int c = 0; c < G; ++c) s += a.Gpart[(long long)c * cnt + e];
+      a.G[e] = s;
+    }
+    grid.sync();
+    for (int e = tid; e < cnt; e += kStepThreads) s_g[e] = a.G[e];
+    __syncthreads();
+  };
+
+  // ---- CGS2 against all previous blocks
+  for (int pass = 0; pass < 2; ++pass) {
+    gram_partial(a.Q, p);
+    gram_reduce(p);
+    for (int r = r_lo + tid; r < r_hi; r += kStepThreads) {
+      double acc[B];
+#pragma unroll
+      for (int c = 0; c < B; ++c) acc[c] = 0.0;
+      for (int i = 0; i < p; ++i) {
+        const double x = a.Q[(long long)i * n + r];
+#pragma unroll
+        for (int c = 0; c < B; ++c) acc[c] += x * s_g[i * B + c];
+      }
+#pragma unroll
+      for (int c = 0; c < B; ++c) Qn[(long long)c * n + r] -= acc[c];
+    }
+    if (cta == 0) {
+      for (int e = tid; e < p * B; e += kStepThreads) {
+        double* dst = &a.H[(long long)(e / B) * D + j * B + (e % B)];
+        *dst = pass ? (*dst + s_g[e]) : s_g[e];
+      }
+    }
+    __syncthreads();                                        // s_g is rewritten by the next reduction
+  }
+  // ---- CholQR2: Qn = Q_{j+1} (R2 R1)
+  for (int pass = 0; pass < 2; ++pass) {
+    gram_partial(Qn, B);
+    gram_reduce(B);
+    if (tid == 0) chol_small(s_g, B, s_r, s_ri);
+    __syncthreads();
+    if (pass == 0 && tid < B * B) s_r1[tid] = s_r[tid];
+    const bool last = pass == 1;
+    for (int r = r_lo + tid; r < r_hi; r += kStepThreads) {
+      double in[B], out[B];
+#pragma unroll
+      for (int c = 0; c < B; ++c) in[c] = Qn[(long long)c * n + r];
+#pragma unroll
+      for (int c = 0; c < B; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int t = 0; t < B; ++t) s += in[t] * s_ri[t * B + c];
+        out[c] = s;
+      }
+#pragma unroll
+      for (int c = 0; c < B; ++c) {
+        Qn[(long long)c * n + r] = out[c];
+        if (last) a.Vf[(long long)c * n + r] = (float)out[c];
+      }
+    }
+    __syncthreads();
+  }
+  if (cta == 0 && tid < B * B) {                            // H[(j+1)-block, j-block] = R2 R1
+    const int i = tid / B, c = tid % B;
+    double s = 0.0;
+    for (int t = 0; t < B; ++t) s += s_r[i * B + t] * s_r1[t * B + c];
+    a.H[(long long)(p + i) * D + j * B + c] = s;
+    a.R1[tid] = s_r1[tid];
+    a.R2[tid] = s_r[tid];
+  }
+}
+
+// grid of the cooperative step kernel: one CTA per SM at most (always co-resident), fewer for small n
+int step_grid(int n) { return max(1, min(min(num_sms(), kMaxStepGrid), (n + 127) / 128)); }
+
+template <int B>
+int launch_step(const StepArgs& a, cudaStream_t s) {
+  StepArgs args = a;
+  const int G = step_grid(a.n);
+  args.rows_per_cta = (a.n + G - 1) / G;
+  void* params[] = {&args};
+  HIA_CUDA(cudaLaunchCooperativeKernel((const void*)lanczos_step_kernel<B>, dim3(G), dim3(kStepThreads), params, 0, s));
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+
 struct EigWs {
   double *Q, *Y, *U, *H, *G, *G2, *R1, *Rinv, *R2, *Rt, *JA, *JV, *lam, *resid2, *Gpart;
   float *Vf;
@@ -523,7 +907,7 @@ long long carve(unsigned char* base, int n, int b, int steps, EigWs* w) {
   p = take(b * 8); if (w) w->resid2 = (double*)p;
   p = take(D * 4); if (w) w->order = (int*)p;
   p = take(2 * kMaxBlock * 8); if (w) w->check = (double*)p;
-  p = take((long long)gram_chunks(n) * D * b * 8); if (w) w->Gpart = (double*)p;
+  p = take((long long)max(gram_chunks(n), kMaxStepGrid) * D * b * 8); if (w) w->Gpart = (double*)p;
   p = take(256); if (w) w->flag = (int*)p;
   return off + 256;
 }
@@ -648,6 +1032,13 @@ HIA_API int hia_eig_absorb(int32_t n, int32_t block, int32_t steps, int32_t j, c
   const int b = block, D = b * (steps + 1);
   EigWs w;
   carve(static_cast<unsigned char*>(workspace), n, b, steps, &w);
+  static const bool coop = !(getenv("HIA_EIG_COOP") && atoi(getenv("HIA_EIG_COOP")) == 0);
+  if (coop) {                                           // one cooperative kernel for the whole step
+    StepArgs a;
+    a.y_full = y_full; a.Q = w.Q; a.H = w.H; a.Gpart = w.Gpart; a.G = w.G; a.R1 = w.R1; a.R2 = w.R2; a.Vf = w.Vf;
+    a.n = n; a.b = b; a.D = D; a.j = j; a.rows_per_cta = 0;
+    return b == 8 ? launch_step<8>(a, s) : launch_step<4>(a, s);
+  }
   double* Qn = w.Q + (long long)(j + 1) * b * n;
   const int p = (j + 1) * b;                         // columns of Q so far
   rowmajor_to_colmajor_kernel<<<(int)(((long long)n * b + 255) / 256), 256, 0, s>>>(y_full, Qn, n, b);
@@ -782,22 +1173,39 @@ HIA_API int32_t hia_eig_first_check(int32_t steps) { return steps * 2 / 3 > 4 ? 
 // pass-free convergence check (hia_eig_check, one tiny D2H flag) after every second step from
 // hia_eig_first_check(steps) on: the cycle stops as soon as the Lanczos residual estimates meet the tolerance instead of
 // always spending `steps` passes over the matrix. *steps_used_host (optional) = steps actually taken.
+HIA_API int64_t hia_eig_symm_upper_workspace_bytes(int32_t n, int32_t block) {
+  if (n <= 0 || (block != 4 && block != 8)) return 0;
+  return hia::symm_upper_ws_bytes(n, block);
+}
+
+// upper_ws (optional, hia_eig_symm_upper_workspace_bytes): the matrix is SYMMETRIC and only its upper
+// triangle is read by the passes (half the DRAM bytes; the lower triangle is never touched).
 HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block, int32_t steps,
                          uint64_t seed, const float* init_vecs, int32_t n_init, double early_rel_tol,
                          double early_angle_tol, double* eigvals, float* eigvecs, double* resid, double* gaps,
-                         int32_t* steps_used_host, void* workspace, int64_t workspace_bytes, void* stream) {
+                         int32_t* steps_used_host, void* workspace, int64_t workspace_bytes, void* upper_ws,
+                         int64_t upper_ws_bytes, void* stream) {
   using namespace hia;
   if (!c || !eigvals || !eigvecs || !resid || !workspace || ld < n || k <= 0) return HIA_ERR_BAD_ARG;
   if (k > block) return HIA_ERR_BAD_ARG;
+  if (upper_ws && upper_ws_bytes < hia_eig_symm_upper_workspace_bytes(n, block)) return HIA_ERR_WORKSPACE;
+  if (upper_ws && (!aligned16(upper_ws) || !aligned16(c) || (ld & 3))) return HIA_ERR_ALIGN;
   int st = hia_eig_begin(n, block, steps, seed, init_vecs, n_init, workspace, workspace_bytes, stream);
   if (st != HIA_OK) return st;
   EigWs w;
   carve(static_cast<unsigned char*>(workspace), n, block, steps, &w);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto pass = [&](double* y) -> int {                 // y (n x block, row-major fp64) = C * current fp32 panel
+    if (upper_ws)
+      return block == 8 ? launch_symm_upper<8>(c, n, ld, w.Vf, y, upper_ws, s)
+                        : launch_symm_upper<4>(c, n, ld, w.Vf, y, upper_ws, s);
+    return hia_eig_symm_rows(c, n, n, ld, block, steps, workspace, y, stream);
+  };
   double* ystage = w.Y;                               // n x block staging (row-major)
   const bool early = early_rel_tol > 0.0 || early_angle_tol > 0.0;
   int used = steps, reuse = 0;
   for (int j = 0; j < steps; ++j) {
-    st = hia_eig_symm_rows(c, n, n, ld, block, steps, workspace, ystage, stream);
+    st = pass(ystage);
     if (st != HIA_OK) return st;
     st = hia_eig_absorb(n, block, steps, j, ystage, workspace, stream);
     if (st != HIA_OK) return st;
@@ -814,7 +1222,7 @@ HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32
   if (st != HIA_OK) return st;
   // the residual pass needs a second staging buffer: w.Y is the transposed target of hia_eig_resid
   double* ystage2 = w.Q + (long long)used * block * n;    // Q_{used} is no longer needed
-  st = hia_eig_symm_rows(c, n, n, ld, block, steps, workspace, ystage2, stream);
+  st = pass(ystage2);
   if (st != HIA_OK) return st;
   return hia_eig_resid(n, block, steps, k, ystage2, eigvals, resid, workspace, stream);
 }

@@ -573,23 +573,23 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
 }
 
 // Register-staged variant (the default whenever the rows are 16-byte aligned and <= 131 072 long):
-// the row is read from DRAM exactly ONCE. A cluster of CS = 1 / 2 / 4 CTAs of 1024 threads owns a row;
-// every thread loads 8 float4 (all 128-bit loads issued before the first use: 128 KB in flight per
-// SM), accumulates the fp64 sum / sum of squares of its 32 cells, the cluster combines the CTA
+// the row is read from DRAM exactly ONCE. A cluster of <= 8 CTAs of T = 256 / 512 / 1024 threads owns a
+// row (T = the smallest that covers the row with 8 CTAs: small CTAs, several per SM, so that the
+// load / reduce / store phases of different rows overlap on one SM -- one 1024-thread CTA per SM was
+// 2.35 ms at 30 894 bins against 2.0 ms of the two-pass kernel); every thread loads 8 float4 (all
+// 128-bit loads issued before the first use), accumulates the fp64 sum / sum of squares of its 32 cells, the cluster combines the CTA
 // partials through distributed shared memory (every CTA stores its pair into every CTA of the
 // cluster, one cluster barrier, fixed summation order), and the hi/lo planes are produced straight
 // from the registers. 4 + 4 (f16) or 4 + 8 (tf32) bytes per cell, nothing re-read.
-constexpr int kRegThreads = 1024;
 constexpr int kRegVec = 8;                                   // float4 per thread
-constexpr int kRegCellsPerCta = kRegThreads * kRegVec * 4;   // 32 768
 
-template <int PREC>
-__global__ void __launch_bounds__(kRegThreads, 1)
+template <int PREC, int kRegThreads>
+__global__ void __launch_bounds__(kRegThreads, 1024 / kRegThreads)
 row_prep_reg_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int kpad, int center,
                     typename PlaneT<PREC>::type* __restrict__ hi, typename PlaneT<PREC>::type* __restrict__ lo) {
   typedef typename PlaneT<PREC>::type P;
   __shared__ double s_red[kRegThreads / 32][2];
-  __shared__ double s_part[4][2];                            // partials of the (<= 4) CTAs of the cluster
+  __shared__ double s_part[8][2];                            // partials of the (<= 8) CTAs of the cluster
   uint32_t cs, cr;
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(cs));
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cr));
@@ -764,13 +764,13 @@ __global__ void __launch_bounds__(1024) tile_list_kernel(const TileSpace ts, Til
   }
 }
 
-template <int PREC>
+template <int PREC, int T>
 int launch_prep_reg(const float* x, int rows, int k, long long ld_x, int kpad, int center, void* hi, void* lo,
                     int cs, cudaStream_t stream) {
   typedef typename PlaneT<PREC>::type P;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)rows * cs, 1, 1);
-  cfg.blockDim = dim3(kRegThreads, 1, 1);
+  cfg.blockDim = dim3(T, 1, 1);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -779,21 +779,29 @@ int launch_prep_reg(const float* x, int rows, int k, long long ld_x, int kpad, i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  HIA_CUDA(cudaLaunchKernelEx(&cfg, row_prep_reg_kernel<PREC>, x, rows, k, ld_x, kpad, center,
+  HIA_CUDA(cudaLaunchKernelEx(&cfg, row_prep_reg_kernel<PREC, T>, x, rows, k, ld_x, kpad, center,
                               static_cast<P*>(hi), static_cast<P*>(lo)));
   HIA_LAUNCH_CHECK();
   return HIA_OK;
+}
+template <int PREC>
+int launch_prep_reg_t(const float* x, int rows, int k, long long ld_x, int kpad, int center, void* hi, void* lo,
+                      cudaStream_t stream) {
+  const int cells256 = 256 * kRegVec * 4;                  // 8 192 cells per 256-thread CTA
+  auto cs_of = [&](int t) { return (kpad + t * kRegVec * 4 - 1) / (t * kRegVec * 4); };
+  if (kpad <= 8 * cells256) return launch_prep_reg<PREC, 256>(x, rows, k, ld_x, kpad, center, hi, lo, cs_of(256), stream);
+  if (kpad <= 16 * cells256) return launch_prep_reg<PREC, 512>(x, rows, k, ld_x, kpad, center, hi, lo, cs_of(512), stream);
+  return launch_prep_reg<PREC, 1024>(x, rows, k, ld_x, kpad, center, hi, lo, cs_of(1024), stream);
 }
 
 int launch_prep(const float* x, int rows, int k, long long ld_x, int center, void* hi, void* lo, int prec,
                 cudaStream_t stream) {
   const int kpad = round_up(k, bk_of(prec));
-  // one DRAM read per cell: rows staged in the registers of a 1 / 2 / 4-CTA cluster (HIA_PREP_REG=0: two-pass kernel)
+  // one DRAM read per cell: rows staged in the registers of a CTA cluster (HIA_PREP_REG=0: two-pass kernel)
   static const bool use_reg = !(getenv("HIA_PREP_REG") && atoi(getenv("HIA_PREP_REG")) == 0);
-  const int cs = kpad <= kRegCellsPerCta ? 1 : (kpad <= 2 * kRegCellsPerCta ? 2 : 4);
-  if (use_reg && kpad <= 4 * kRegCellsPerCta && aligned16(x) && (ld_x & 3) == 0) {
-    if (prec == HIA_PREC_3XF16) return launch_prep_reg<HIA_PREC_3XF16>(x, rows, k, ld_x, kpad, center, hi, lo, cs, stream);
-    return launch_prep_reg<HIA_PREC_3XTF32>(x, rows, k, ld_x, kpad, center, hi, lo, cs, stream);
+  if (use_reg && kpad <= 8 * 1024 * kRegVec * 4 && aligned16(x) && (ld_x & 3) == 0) {
+    if (prec == HIA_PREC_3XF16) return launch_prep_reg_t<HIA_PREC_3XF16>(x, rows, k, ld_x, kpad, center, hi, lo, stream);
+    return launch_prep_reg_t<HIA_PREC_3XTF32>(x, rows, k, ld_x, kpad, center, hi, lo, stream);
   }
   if (prec == HIA_PREC_3XF16)
     row_prep_kernel<HIA_PREC_3XF16><<<rows, kPrepThreads, 0, stream>>>(x, rows, k, ld_x, kpad, center,

@@ -242,7 +242,7 @@ def eig_converged(resid, lam, gaps, tol, angle_tol):
 
 
 def topk_eig(c, k=3, block=8, steps=None, tol=1e-6, angle_tol=1e-3, max_restarts=8, seed=0,
-             return_info=False):
+             return_info=False, symmetric=True, workspace=None):
     """Largest-algebraic k eigenpairs of a dense symmetric fp32 matrix (e.g. the Pearson map).
     No reference implementation exists (oracle: numpy.linalg.eigh) -- north-star item.
     Block Lanczos on the device. A cycle of at most `steps` passes over the matrix ends as soon as
@@ -250,7 +250,10 @@ def topk_eig(c, k=3, block=8, steps=None, tol=1e-6, angle_tol=1e-3, max_restarts
     true residuals ||C u - lambda u|| of one final pass decide convergence: each <= tol |lambda_1|,
     or each <= angle_tol * (distance to the nearest other Ritz value), i.e. an eigenvector angle of
     at most angle_tol (|cos| >= 1 - angle_tol^2 / 2; the north star asks for 0.9999). Otherwise the
-    cycle restarts from the Ritz vectors. Returns (eigvals[k] fp64, eigvecs[n, k] fp32)."""
+    cycle restarts from the Ritz vectors. Returns (eigvals[k] fp64, eigvecs[n, k] fp32).
+    symmetric=True (default; HIA_EIG_UPPER=0 switches it off): the passes read the upper triangle of `c`
+    only (half the DRAM bytes); pass symmetric=False for a matrix whose two triangles differ.
+    workspace: optional dict reused across calls (buffers keyed by shape)."""
     lib = _lib.load()
     _need_cuda(c)
     n = c.shape[0]
@@ -263,7 +266,17 @@ def topk_eig(c, k=3, block=8, steps=None, tol=1e-6, angle_tol=1e-3, max_restarts
     if block * (steps + 1) > n or k > block:
         raise _lib.HiaError(f"matrix of {n} bins is too small for k={k}")
     dev = c.device
-    ws = torch.empty(lib.hia_topk_eig_workspace_bytes(n, block, steps), dtype=torch.uint8, device=dev)
+    cache = workspace if workspace is not None else {}
+    key = ("eig", n, block, steps, str(dev))
+    if key not in cache:
+        cache[key] = torch.empty(lib.hia_topk_eig_workspace_bytes(n, block, steps), dtype=torch.uint8, device=dev)
+    ws = cache[key]
+    upper = None
+    if symmetric and os.environ.get("HIA_EIG_UPPER", "1") != "0" and c.data_ptr() % 16 == 0 and c.stride(0) % 4 == 0:
+        ukey = ("eig_upper", n, block, str(dev))
+        if ukey not in cache:
+            cache[ukey] = torch.empty(lib.hia_eig_symm_upper_workspace_bytes(n, block), dtype=torch.uint8, device=dev)
+        upper = cache[ukey]
     eigvals = torch.empty(k, dtype=torch.float64, device=dev)
     eigvecs = torch.empty((k, n), dtype=torch.float32, device=dev)
     stats = torch.empty(2 * k, dtype=torch.float64, device=dev)       # residuals | gaps: one D2H read
@@ -273,7 +286,8 @@ def topk_eig(c, k=3, block=8, steps=None, tol=1e-6, angle_tol=1e-3, max_restarts
         # the in-cycle estimates use half the tolerances: the final, true residual must pass too
         st = lib.hia_topk_eig(_ptr(c), n, c.stride(0), k, block, steps, seed + it, _ptr(init), n_init,
                               0.5 * tol, 0.5 * angle_tol, _ptr(eigvals), _ptr(eigvecs), stats.data_ptr(),
-                              stats.data_ptr() + 8 * k, ctypes.addressof(used), _ptr(ws), ws.numel(), _stream())
+                              stats.data_ptr() + 8 * k, ctypes.addressof(used), _ptr(ws), ws.numel(), _ptr(upper),
+                              0 if upper is None else upper.numel(), _stream())
         _lib.check(st, "hia_topk_eig")
         sg = stats.cpu().numpy()
         lam = eigvals.cpu().numpy()

@@ -39,6 +39,7 @@ class HotPath:
         # and the apply pass read the upper triangle of `raw` only, so the scatter skips its mirror pass and
         # `raw` keeps an UNWRITTEN lower triangle (`raw_symmetric()` completes it on demand)
         self.upper_only = (os.environ.get("HIA_UPPER_ONLY", "1") == "1") if upper_only is None else bool(upper_only)
+        self._eig_ws = {}                            # eigen-solver workspaces, allocated on first use
         self.max_nnz = max_nnz
         if max_nnz:
             self.d_rows = torch.empty(max_nnz, dtype=torch.int32, device=device)
@@ -80,7 +81,8 @@ class HotPath:
         return self.sim
 
     def eigen(self, tol=1e-6):
-        return ops.topk_eig(self.sim, k=self.k_eig, block=self.eig_block, steps=self.eig_steps, tol=tol)
+        return ops.topk_eig(self.sim, k=self.k_eig, block=self.eig_block, steps=self.eig_steps, tol=tol,
+                            workspace=self._eig_ws)
 
     # ---- whole path ---------------------------------------------------------------------
     def run_device(self, rows, cols, vals):

@@ -377,11 +377,16 @@ int64_t hia_topk_eig_workspace_bytes(int32_t n, int32_t block, int32_t steps);
  * est <= early_angle_tol * gap (gap = distance to the nearest other Ritz value: the sin-theta
  * bound on the eigenvector angle). resid[k] are always the TRUE residuals ||C u - lambda u|| of
  * one final pass; gaps[k] (optional, device) the Ritz gaps; *steps_used_host (optional) the steps
- * taken. */
+ * taken. upper_ws (optional; hia_eig_symm_upper_workspace_bytes(n, block) bytes, 16-byte aligned):
+ * every pass reads the UPPER TRIANGLE of the (symmetric) matrix only -- each loaded cell feeds
+ * both y[r] += c v[col] and y[col] += c v[r] -- i.e. half the DRAM bytes of the HBM-bound pass;
+ * the lower triangle is never touched. NULL = the full-matrix pass. */
+int64_t hia_eig_symm_upper_workspace_bytes(int32_t n, int32_t block);
 int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block, int32_t steps,
                  uint64_t seed, const float* init_vecs, int32_t n_init, double early_rel_tol,
                  double early_angle_tol, double* eigvals, float* eigvecs, double* resid, double* gaps,
-                 int32_t* steps_used_host, void* workspace, int64_t workspace_bytes, void* stream);
+                 int32_t* steps_used_host, void* workspace, int64_t workspace_bytes, void* upper_ws,
+                 int64_t upper_ws_bytes, void* stream);
 
 /* The phases of hia_topk_eig as separate calls, so that a row-sharded caller can all-gather the
  * panel between the pass over the matrix and the (replicated, tiny) orthogonalisation:

@@ -83,3 +83,74 @@ def test_upper_apply_kernel_index_logic():
                 ref=direct(full,n,chr_start,bin_chr,inv_expected,inter_inv,C,only_intra,do_log,fill)
                 assert not np.isnan(got).any(), (lens,only_intra,do_log)
                 assert np.array_equal(got,ref), (lens,only_intra,do_log,np.abs(got-ref).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# symm_upper_kernel + symm_upper_reduce_kernel (csrc/hia_eig.cu): y = C v from the upper triangle
+# only. The emulation follows the kernel's work decomposition -- (column block J, row segment) items,
+# the early exit, r_end, the float4 groups of a lane with their three masks (below the diagonal,
+# diagonal cell for the column part, beyond the edge), the partial buffers P[J][r] / Pc[seg][c] and
+# the index ranges of the reduce kernel -- with NaN-poisoned partial buffers and a NaN-poisoned lower
+# triangle: any cell read that the kernel must not read, or any partial read that was never
+# written, shows up as NaN.
+# ---------------------------------------------------------------------------------------------
+UP_COLS, UP_SEG, UP_WARPS = 128, 1024, 8
+
+
+def emulate_symm_upper(c, v):
+    n, b = v.shape
+    nJ, nSeg = -(-n // UP_COLS), -(-n // UP_SEG)
+    prow = np.full((nJ, n, b), np.nan)
+    pcol = np.full((nSeg, n, b), np.nan)
+    for J in range(nJ):
+        for seg in range(nSeg):
+            c0, r_seg = J * UP_COLS, seg * UP_SEG
+            if r_seg > c0 + UP_COLS - 1:
+                continue
+            r_end = min(n, r_seg + UP_SEG, c0 + UP_COLS)
+            cacc = np.zeros((UP_COLS, b))
+            for r0 in range(r_seg, r_end, 8):                       # a warp's group of 8 rows
+                for r in range(r0, r0 + 8):
+                    racc = np.zeros(b)
+                    for lane in range(32):
+                        gc = c0 + 4 * lane
+                        if not (r < r_end and gc < n and gc + 3 >= r):
+                            continue                                 # no load at all
+                        e = np.array([c[r, gc + q] if gc + q < n else 0.0 for q in range(4)])
+                        for q in range(4):
+                            if gc + q < r:
+                                e[q] = 0.0                           # below the diagonal (NaN-poisoned in the input)
+                        for q in range(4):
+                            if gc + q < n:
+                                racc += e[q] * v[gc + q]
+                        for q in range(4):
+                            if gc + q == r:
+                                e[q] = 0.0                           # the diagonal cell: row part only
+                        for q in range(4):
+                            cacc[4 * lane + q] += e[q] * v[r]
+                    if r < r_end:
+                        prow[J, r] = racc
+            for cl in range(UP_COLS):
+                if c0 + cl < n:
+                    pcol[seg, c0 + cl] = cacc[cl]
+    y = np.zeros((n, b))
+    for r in range(n):
+        for J in range(r // UP_COLS, nJ):
+            y[r] += prow[J, r]
+        for seg in range(0, min(r, (r // UP_COLS) * UP_COLS + UP_COLS - 1) // UP_SEG + 1):
+            y[r] += pcol[seg, r]
+    return y
+
+
+def test_symm_upper_pass_index_logic():
+    rng = np.random.default_rng(3)
+    for n in (5, 127, 128, 129, 300, 1024 + 130, 2 * 1024 + 7):
+        b = 4
+        up = np.triu(rng.standard_normal((n, n)))
+        full = up + np.triu(up, 1).T
+        poisoned = np.where(np.arange(n)[:, None] > np.arange(n)[None, :], np.nan, full)
+        v = rng.standard_normal((n, b))
+        with np.errstate(invalid="ignore"):
+            y = emulate_symm_upper(poisoned, v)
+        assert not np.isnan(y).any(), n
+        assert np.abs(y - full @ v).max() < 1e-9, n

@@ -958,7 +958,11 @@ int cholqr(double* Y, int n, int b, EigWs& w, double* r_out, float* yf, cudaStre
 int launch_jacobi(const EigWs& w, int D, int dim, cudaStream_t s) {
   const size_t need = (size_t)2 * dim * dim * sizeof(double);
   const int use_smem = need <= 222 * 1024;
-  if (use_smem) HIA_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  static bool attr_set = false;                            // once: the largest size that is ever requested
+  if (use_smem && !attr_set) {
+    HIA_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+    attr_set = true;
+  }
   jacobi_kernel<<<1, 1024, use_smem ? need : 0, s>>>(w.H, D, dim, w.JA, w.JV, w.lam, w.order, 15, use_smem);
   HIA_LAUNCH_CHECK();
   return HIA_OK;
@@ -1032,7 +1036,8 @@ HIA_API int hia_eig_absorb(int32_t n, int32_t block, int32_t steps, int32_t j, c
   const int b = block, D = b * (steps + 1);
   EigWs w;
   carve(static_cast<unsigned char*>(workspace), n, b, steps, &w);
-  static const bool coop = !(getenv("HIA_EIG_COOP") && atoi(getenv("HIA_EIG_COOP")) == 0);
+  const char* env_coop = getenv("HIA_EIG_COOP");         // read per call: tools time both in one process
+  const bool coop = !(env_coop && atoi(env_coop) == 0);
   if (coop) {                                           // one cooperative kernel for the whole step
     StepArgs a;
     a.y_full = y_full; a.Q = w.Q; a.H = w.H; a.Gpart = w.Gpart; a.G = w.G; a.R1 = w.R1; a.R2 = w.R2; a.Vf = w.Vf;

@@ -241,6 +241,51 @@ def eig_converged(resid, lam, gaps, tol, angle_tol):
     return bool(angle_tol > 0 and np.all(resid <= angle_tol * gaps))
 
 
+def _eig_shape(n, k, block, steps):
+    if n < 2 * block:
+        block = 4
+    if steps is None:
+        steps = 12
+    steps = max(1, min(steps, n // block - 1, 272 // block - 1))
+    if block * (steps + 1) > n or k > block:
+        raise _lib.HiaError(f"matrix of {n} bins is too small for k={k}")
+    return block, steps
+
+
+class EigBuffers:
+    """Workspaces + outputs of one eigen solve of an n x n matrix, allocated once (HotPath keeps one;
+    a CUDA-graph capture needs every buffer to exist before the capture starts)."""
+
+    def __init__(self, n, k, block, steps, device, symmetric=True):
+        lib = _lib.load()
+        self.n, self.k, self.block, self.steps = n, k, block, steps
+        self.ws = torch.empty(lib.hia_topk_eig_workspace_bytes(n, block, steps), dtype=torch.uint8, device=device)
+        self.upper = None
+        # measured at 30 894 bins: the upper-triangle pass halves the DRAM bytes but not the FMAs or the
+        # reductions, and the pass is issue-bound: 1.14 ms against 0.82 ms of the full pass -> opt-in
+        if symmetric and os.environ.get("HIA_EIG_UPPER", "0") == "1":
+            self.upper = torch.empty(lib.hia_eig_symm_upper_workspace_bytes(n, block), dtype=torch.uint8, device=device)
+        self.eigvals = torch.empty(k, dtype=torch.float64, device=device)
+        self.eigvecs = torch.empty((k, n), dtype=torch.float32, device=device)
+        self.stats = torch.empty(2 * k, dtype=torch.float64, device=device)       # residuals | gaps: one D2H read
+        self.used = ctypes.c_int32(0)
+
+
+def topk_eig_cycle(c, buf, seed=0, init=None, n_init=0, early_tol=0.0, early_angle_tol=0.0):
+    """ONE Lanczos cycle enqueued on the current stream; results stay on the device in `buf`
+    (eigvals, eigvecs, stats = true residuals | Ritz gaps). With early_tol = early_angle_tol = 0 the
+    cycle runs all `buf.steps` steps and contains no host synchronisation at all (capturable in a
+    CUDA graph); otherwise the in-cycle convergence checks read one flag each."""
+    lib = _lib.load()
+    n, k = buf.n, buf.k
+    upper = buf.upper if (buf.upper is not None and c.data_ptr() % 16 == 0 and c.stride(0) % 4 == 0) else None
+    st = lib.hia_topk_eig(_ptr(c), n, c.stride(0), k, buf.block, buf.steps, seed, _ptr(init), n_init,
+                          early_tol, early_angle_tol, _ptr(buf.eigvals), _ptr(buf.eigvecs), buf.stats.data_ptr(),
+                          buf.stats.data_ptr() + 8 * k, ctypes.addressof(buf.used), _ptr(buf.ws), buf.ws.numel(),
+                          _ptr(upper), 0 if upper is None else upper.numel(), _stream())
+    _lib.check(st, "hia_topk_eig")
+
+
 def topk_eig(c, k=3, block=8, steps=None, tol=1e-6, angle_tol=1e-3, max_restarts=8, seed=0,
              return_info=False, symmetric=True, workspace=None):
     """Largest-algebraic k eigenpairs of a dense symmetric fp32 matrix (e.g. the Pearson map).
@@ -251,52 +296,31 @@ def topk_eig(c, k=3, block=8, steps=None, tol=1e-6, angle_tol=1e-3, max_restarts
     or each <= angle_tol * (distance to the nearest other Ritz value), i.e. an eigenvector angle of
     at most angle_tol (|cos| >= 1 - angle_tol^2 / 2; the north star asks for 0.9999). Otherwise the
     cycle restarts from the Ritz vectors. Returns (eigvals[k] fp64, eigvecs[n, k] fp32).
-    symmetric=True (default; HIA_EIG_UPPER=0 switches it off): the passes read the upper triangle of `c`
-    only (half the DRAM bytes); pass symmetric=False for a matrix whose two triangles differ.
+    symmetric=True with HIA_EIG_UPPER=1: the passes read the upper triangle of `c` only (half the DRAM
+    bytes, but measured slower than the full pass, which is issue-bound: opt-in).
     workspace: optional dict reused across calls (buffers keyed by shape)."""
-    lib = _lib.load()
     _need_cuda(c)
     n = c.shape[0]
     assert c.shape == (n, n) and c.dtype == torch.float32 and c.stride(1) == 1
-    if n < 2 * block:
-        block = 4
-    if steps is None:
-        steps = 12
-    steps = max(1, min(steps, n // block - 1, 272 // block - 1))
-    if block * (steps + 1) > n or k > block:
-        raise _lib.HiaError(f"matrix of {n} bins is too small for k={k}")
-    dev = c.device
+    block, steps = _eig_shape(n, k, block, steps)
     cache = workspace if workspace is not None else {}
-    key = ("eig", n, block, steps, str(dev))
+    key = ("eig", n, k, block, steps, str(c.device), bool(symmetric))
     if key not in cache:
-        cache[key] = torch.empty(lib.hia_topk_eig_workspace_bytes(n, block, steps), dtype=torch.uint8, device=dev)
-    ws = cache[key]
-    upper = None
-    if symmetric and os.environ.get("HIA_EIG_UPPER", "1") != "0" and c.data_ptr() % 16 == 0 and c.stride(0) % 4 == 0:
-        ukey = ("eig_upper", n, block, str(dev))
-        if ukey not in cache:
-            cache[ukey] = torch.empty(lib.hia_eig_symm_upper_workspace_bytes(n, block), dtype=torch.uint8, device=dev)
-        upper = cache[ukey]
-    eigvals = torch.empty(k, dtype=torch.float64, device=dev)
-    eigvecs = torch.empty((k, n), dtype=torch.float32, device=dev)
-    stats = torch.empty(2 * k, dtype=torch.float64, device=dev)       # residuals | gaps: one D2H read
-    used = ctypes.c_int32(0)
+        cache[key] = EigBuffers(n, k, block, steps, c.device, symmetric)
+    buf = cache[key]
     init, n_init, info = None, 0, []
     for it in range(max_restarts):
         # the in-cycle estimates use half the tolerances: the final, true residual must pass too
-        st = lib.hia_topk_eig(_ptr(c), n, c.stride(0), k, block, steps, seed + it, _ptr(init), n_init,
-                              0.5 * tol, 0.5 * angle_tol, _ptr(eigvals), _ptr(eigvecs), stats.data_ptr(),
-                              stats.data_ptr() + 8 * k, ctypes.addressof(used), _ptr(ws), ws.numel(), _ptr(upper),
-                              0 if upper is None else upper.numel(), _stream())
-        _lib.check(st, "hia_topk_eig")
-        sg = stats.cpu().numpy()
-        lam = eigvals.cpu().numpy()
+        topk_eig_cycle(c, buf, seed + it, init, n_init, 0.5 * tol, 0.5 * angle_tol)
+        sg = buf.stats.cpu().numpy()
+        lam = buf.eigvals.cpu().numpy()
         r, gaps = sg[:k], sg[k:]
-        info.append((float(r.max()), float(abs(lam[0])), int(used.value)))
+        info.append((float(r.max()), float(abs(lam[0])), int(buf.used.value)))
         if eig_converged(r, lam, gaps, tol, angle_tol):
             break
-        init, n_init = eigvecs.clone(), k
-    out = (eigvals, eigvecs.t())
+        init, n_init = buf.eigvecs.clone(), k
+    # fresh tensors: the buffers are reused by the next call
+    out = (buf.eigvals.clone(), buf.eigvecs.t().clone() if workspace is not None else buf.eigvecs.t())
     return out + (info,) if return_info else out
 
 

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from hiarch_b200 import ops, synth
-from hiarch_b200.pipeline import HotPath, HotPathPool, dense_to_coo
+from hiarch_b200.pipeline import HotPath, HotPathPool, SampleGraph, dense_to_coo
 
 
 def timed(fn, reps=2, warm=1):
@@ -74,6 +74,20 @@ def run_c3(args):
         stage(res, f"whole_sample_pool{w}", lambda: pool.run_device(coos),
               cells_per_s=lambda ms: cells / ms * 1e3, samples_per_s=lambda ms: 1e3 / ms)
         pool.close()
+    # the whole sample as ONE CUDA graph with forked branches (device time incl. the result read-back)
+    for br in [int(x) for x in args.c3_branches.split(",") if x]:
+        try:
+            sg = SampleGraph(paths, [r.numel() for r, _, _ in coos], branches=br)
+            sg.load(coos)
+            sg.capture()
+            stage(res, f"whole_sample_graph{br}", lambda: sg.run(coos), cells_per_s=lambda ms: cells / ms * 1e3,
+                  samples_per_s=lambda ms: 1e3 / ms)
+            res[f"whole_sample_graph{br}"]["eig_fallbacks"] = sg.fallbacks
+            stage(res, f"whole_sample_graph{br}_replay_only", lambda: sg.graph.replay())
+            del sg
+        except Exception as exc:
+            res[f"whole_sample_graph{br}"] = dict(error=f"{type(exc).__name__}: {exc}")
+            traceback.print_exc()
     return res
 
 
@@ -112,6 +126,7 @@ def main():
     ap.add_argument("--c3-res", type=int, default=50000)
     ap.add_argument("--c4-res", type=int, default=10000)
     ap.add_argument("--c3-workers", default="2,4,8", help="HotPathPool sizes to time after the sequential run")
+    ap.add_argument("--c3-branches", default="4,8,12", help="SampleGraph branch counts to time")
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     out = {}

@@ -481,17 +481,23 @@ def run_ours(args):
     scat, oe_ms, prep, gemm, eig_ms = stage
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- end-to-end arm (pinned host COO -> eigenpairs on host) --------------------------------
-    # HotPath.run_host_many: the public streaming call; every step copies ITS inputs H2D (2.7 GB from
-    # pinned memory) and reads its eigenpairs back inside the timed region; the copy of step i + 1
-    # runs on a second stream while step i computes (double buffering).
-    for _ in hp.run_host_many([(rows_h, cols_h, vals_h)] * min(args.warmup, 2)):
+    # ---- end-to-end arm (pinned host CSR -> eigenpairs on host) --------------------------------
+    # HotPath.run_host_many: the public streaming call; every step copies ITS inputs H2D from pinned
+    # memory and reads its eigenpairs back inside the timed region; the copy of step i + 1 runs on a
+    # second stream while step i computes (double buffering). The sample travels as CSR -- what the
+    # reference's SpsHiCMtx holds (scipy CSR) -- with 16-bit column indices when n <= 65 536: 6 bytes per
+    # entry instead of the 12 of the COO triple (round 1: 2.69 GB per step; all ranks of a box pull from
+    # the same host memory, which is what bent the 1 -> 8 GPU e2e curve).
+    from hiarch_b200.pipeline import CsrSample
+    csr_h = CsrSample(*ops.coo_to_csr_host(rows_h.numpy(), cols_h.numpy(), vals_h.numpy(), n))
+    h2d_bytes = hp.sample_bytes(csr_h)
+    for _ in hp.run_host_many([csr_h] * min(args.warmup, 2)):
         pass
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for w_h, v_h in hp.run_host_many([(rows_h, cols_h, vals_h)] * args.steps):
+    for w_h, v_h in hp.run_host_many([csr_h] * args.steps):
         pass
     t1.record()
     barrier()
@@ -500,10 +506,31 @@ def run_ours(args):
     t0s = torch.cuda.Event(enable_timing=True)
     t1s = torch.cuda.Event(enable_timing=True)
     t0s.record()
-    hp.run_host(rows_h, cols_h, vals_h)
+    hp.run_host(csr_h)
     t1s.record()
     barrier()
     e2e_serial_ms = max_over_ranks(t0s.elapsed_time(t1s))
+    # H2D alone, all ranks at once (they share the host memory system): the slowest rank's GB/s
+    t0c = torch.cuda.Event(enable_timing=True)
+    t1c = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0c.record()
+    hp._upload(csr_h, (hp.d_rows, hp.d_cols, hp.d_vals, hp.d_rowptr))
+    t1c.record()
+    barrier()
+    h2d_alone_ms = max_over_ranks(t0c.elapsed_time(t1c))
+    # ... and the COO triple through the same call (round 1's wire format), for comparison
+    t0o = torch.cuda.Event(enable_timing=True)
+    t1o = torch.cuda.Event(enable_timing=True)
+    for _ in hp.run_host_many([(rows_h, cols_h, vals_h)] * 2):
+        pass
+    barrier()
+    t0o.record()
+    for _ in hp.run_host_many([(rows_h, cols_h, vals_h)] * args.steps):
+        pass
+    t1o.record()
+    barrier()
+    e2e_coo_ms = max_over_ranks(t0o.elapsed_time(t1o)) / args.steps
 
     # ---- in-run parity checks on the state of the last step (torch fp64 on the device; the oracle
     # comparisons proper live in tests/): a bench line of a wrong result is worthless
@@ -512,7 +539,7 @@ def run_ours(args):
     # ---- the row-sharded genome-wide chain (the one path with an exchange step), all ranks ------
     row_sharded = None
     if world > 1 and not args.no_row_sharded:
-        del hp, rows, cols, vals, rows_h, cols_h, vals_h
+        del hp, rows, cols, vals, rows_h, cols_h, vals_h, csr_h
         torch.cuda.empty_cache()
         row_sharded = run_row_sharded(args, world, rank, local, pk)
 
@@ -576,9 +603,15 @@ def run_ours(args):
                    "sharding": "samples by rank, no collective (the row_sharded sub-record is the path with an exchange)"},
         "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": world * cells / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 12 * nnz, "d2h_bytes_per_step": 3 * 8 + 3 * n * 4,
-                "api": "HotPath.run_host_many (H2D of step i+1 overlaps the compute of step i)",
-                "ms_single_blocking_call": e2e_serial_ms},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 3 * 8 + 3 * n * 4,
+                "api": "HotPath.run_host_many on CsrSample (H2D of step i+1 overlaps the compute of step i)",
+                "wire_format": f"CSR: int64 row_ptr + {'uint16' if n <= 65536 else 'int32'} cols + fp32 vals "
+                               f"({h2d_bytes / nnz:.2f} B/entry)",
+                "ms_single_blocking_call": e2e_serial_ms,
+                "h2d_alone_ms_slowest_rank": h2d_alone_ms,
+                "h2d_gbs_per_rank_all_ranks_copying": h2d_bytes / h2d_alone_ms / 1e6,
+                "coo_triple": {"ms_per_step": e2e_coo_ms, "h2d_bytes_per_step": 12 * nnz,
+                               "value": world * cells / (e2e_coo_ms * 1e-3)}},
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "breakdown_ms": {"scatter": scat, "oe_log": oe_ms, "similarity_prep": prep, "similarity_gemm": gemm,

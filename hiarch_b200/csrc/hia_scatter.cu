@@ -202,12 +202,22 @@ row_ptr_kernel(const int* __restrict__ rows, long long nnz, int n, long long* __
 constexpr int kSegCols = 16384;              // 64 KB of shared memory per CTA, 3 CTAs per SM
 constexpr int kSegThreads = 512;
 
+// 4 consecutive column indices (entry index % 4 == 0): one 128-bit (int32) or 64-bit (uint16) load
+__device__ __forceinline__ int4 load_cols4(const int* p) { return *reinterpret_cast<const int4*>(p); }
+__device__ __forceinline__ int4 load_cols4(const unsigned short* p) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  return make_int4((int)(t.x & 0xffffu), (int)(t.x >> 16), (int)(t.y & 0xffffu), (int)(t.y >> 16));
+}
+
+// CT = int (COO / CSR with 32-bit columns) or unsigned short (CSR with 16-bit columns, n <= 65 536:
+// 6 instead of 8 bytes per entry over PCIe and out of HBM)
+template <typename CT>
 __global__ void __launch_bounds__(kSegThreads)
-fill_rows_sorted_kernel(const int* __restrict__ cols, const float* __restrict__ vals,
+fill_rows_sorted_kernel(const CT* __restrict__ cols, const float* __restrict__ vals,
                         const long long* __restrict__ row_ptr, const int* __restrict__ flag, int n,
                         long long ld, int mtx_type, float* __restrict__ out) {
   extern __shared__ float s_row[];
-  if (*flag) return;
+  if (flag && *flag) return;
   const int r = blockIdx.x;                                // rows on x: gridDim.y stops at 65 535
   const int c_lo = (mtx_type == HIA_MTX_TRIU) ? r : 0;     // a 'triu' row starts on the diagonal
   const int seg_lo = c_lo + blockIdx.y * kSegCols;
@@ -222,23 +232,23 @@ fill_rows_sorted_kernel(const int* __restrict__ cols, const float* __restrict__ 
     c -= seg_lo;
     if (c >= 0 && c < seg_n) atomicAdd(&s_row[c], v);
   };
-  for (long long e = e0 + threadIdx.x; e < a0; e += blockDim.x) add(cols[e], vals[e]);
+  for (long long e = e0 + threadIdx.x; e < a0; e += blockDim.x) add((int)cols[e], vals[e]);
   const long long ng = (a1 - a0) >> 2;
   long long g = threadIdx.x;
   for (; g + blockDim.x < ng; g += 2 * blockDim.x) {
-    const int4 c0 = *reinterpret_cast<const int4*>(cols + a0 + 4 * g);
+    const int4 c0 = load_cols4(cols + a0 + 4 * g);
     const float4 v0 = *reinterpret_cast<const float4*>(vals + a0 + 4 * g);
-    const int4 c1 = *reinterpret_cast<const int4*>(cols + a0 + 4 * (g + blockDim.x));
+    const int4 c1 = load_cols4(cols + a0 + 4 * (g + blockDim.x));
     const float4 v1 = *reinterpret_cast<const float4*>(vals + a0 + 4 * (g + blockDim.x));
     add(c0.x, v0.x); add(c0.y, v0.y); add(c0.z, v0.z); add(c0.w, v0.w);
     add(c1.x, v1.x); add(c1.y, v1.y); add(c1.z, v1.z); add(c1.w, v1.w);
   }
   for (; g < ng; g += blockDim.x) {
-    const int4 c0 = *reinterpret_cast<const int4*>(cols + a0 + 4 * g);
+    const int4 c0 = load_cols4(cols + a0 + 4 * g);
     const float4 v0 = *reinterpret_cast<const float4*>(vals + a0 + 4 * g);
     add(c0.x, v0.x); add(c0.y, v0.y); add(c0.z, v0.z); add(c0.w, v0.w);
   }
-  for (long long e = a1 + threadIdx.x; e < e1; e += blockDim.x) add(cols[e], vals[e]);
+  for (long long e = a1 + threadIdx.x; e < e1; e += blockDim.x) add((int)cols[e], vals[e]);
   __syncthreads();
   float* dst = out + (long long)r * ld + seg_lo;
   // 128-bit stores from the first 16-byte aligned cell of the segment on
@@ -494,13 +504,13 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
     HIA_LAUNCH_CHECK();
     static bool attr_set = false;                          // once per process (idempotent)
     if (!attr_set) {
-      HIA_CUDA(cudaFuncSetAttribute(fill_rows_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      HIA_CUDA(cudaFuncSetAttribute(fill_rows_sorted_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSegCols * (int)sizeof(float)));
       attr_set = true;
     }
     dim3 grid_f(n, (n + kSegCols - 1) / kSegCols);
-    fill_rows_sorted_kernel<<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(cols, vals, row_ptr, flag, n,
-                                                                                        ld, mtx_type, out);
+    fill_rows_sorted_kernel<int><<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(cols, vals, row_ptr, flag, n,
+                                                                                             ld, mtx_type, out);
     HIA_LAUNCH_CHECK();
     // (a 4096-row grid of CTAs that only read the flag and exit cost 69 us per call: launch list r1)
     dim3 grid_z((n + threads * 4 - 1) / (threads * 4), min(n, 64));
@@ -540,6 +550,48 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
     HIA_LAUNCH_CHECK();
   }
   if (mirror) {                                            // to_all: triu(M,0).T + triu(M,1)
+    dim3 gm((n + 31) / 32, (n + 31) / 32);
+    mirror_kernel<<<gm, 256, 0, stream>>>(out, n, ld);
+    HIA_LAUNCH_CHECK();
+  }
+  return HIA_OK;
+}
+
+// CSR input (what SpsHiCMtx.matrix is: scipy CSR, publish/new_hic_class.py:2158-2161): row_ptr[n + 1]
+// (int64, device), column indices as int32 (col_bytes = 4) or uint16 (col_bytes = 2, n <= 65 536), values
+// fp32. Zero fill only. Rows are sorted by construction, so there is no row-pointer pass and no
+// fallback: 8 (or 6) bytes per entry instead of the 12 of the COO triple -- the bytes that cross PCIe
+// in the end-to-end path. Entries with a column outside [0, n) (or below the diagonal for the
+// 'triu' types) are ignored; duplicates are summed.
+HIA_API int hia_scatter_csr_sym(const int64_t* row_ptr, const void* cols, int col_bytes, const float* vals,
+                                int32_t n, float* out, int64_t ld, int mtx_type, void* stream_) {
+  using namespace hia;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!row_ptr || !cols || !vals || !out || n <= 0 || ld < n) return HIA_ERR_BAD_ARG;
+  if (col_bytes != 4 && col_bytes != 2) return HIA_ERR_BAD_ARG;
+  if (col_bytes == 2 && n > 65536) return HIA_ERR_UNSUPPORTED;
+  if (mtx_type != HIA_MTX_TRIU && mtx_type != HIA_MTX_ALL && mtx_type != HIA_MTX_TRIU_UPPER) return HIA_ERR_BAD_ARG;
+  if (!aligned16(out) || (ld & 3) || !aligned16(cols) || !aligned16(vals)) return HIA_ERR_ALIGN;
+  const bool mirror = (mtx_type == HIA_MTX_TRIU);
+  const int mt = (mtx_type == HIA_MTX_ALL) ? HIA_MTX_ALL : HIA_MTX_TRIU;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HIA_CUDA(cudaFuncSetAttribute(fill_rows_sorted_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSegCols * (int)sizeof(float)));
+    HIA_CUDA(cudaFuncSetAttribute(fill_rows_sorted_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSegCols * (int)sizeof(float)));
+    attr_set = true;
+  }
+  dim3 grid_f(n, (n + kSegCols - 1) / kSegCols);
+  const long long* rp = reinterpret_cast<const long long*>(row_ptr);
+  if (col_bytes == 4)
+    fill_rows_sorted_kernel<int><<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(
+        static_cast<const int*>(cols), vals, rp, nullptr, n, ld, mt, out);
+  else
+    fill_rows_sorted_kernel<unsigned short><<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(
+        static_cast<const unsigned short*>(cols), vals, rp, nullptr, n, ld, mt, out);
+  HIA_LAUNCH_CHECK();
+  if (mirror) {
     dim3 gm((n + 31) / 32, (n + 31) / 32);
     mirror_kernel<<<gm, 256, 0, stream>>>(out, n, ld);
     HIA_LAUNCH_CHECK();

@@ -128,6 +128,42 @@ def scatter_coo_sym(rows, cols, vals, n, mtx_type=MTX_TRIU, fill_mode=FILL_ZERO,
     return out
 
 
+def scatter_csr_sym(row_ptr, cols, vals, n, mtx_type=MTX_TRIU, out=None):
+    """CSR (int64 row_ptr [n + 1], int32 or uint16 cols, fp32 vals; CUDA) -> dense fp32 [n, n] view, zero
+    fill: the scatter for matrices that arrive as CSR (scipy's layout of SpsHiCMtx.matrix), 8 or 6
+    bytes per entry instead of the 12 of a COO triple."""
+    lib = _lib.load()
+    _need_cuda(row_ptr, cols, vals)
+    assert row_ptr.dtype == torch.int64 and row_ptr.numel() == n + 1 and vals.dtype == torch.float32
+    assert cols.dtype in (torch.int32, torch.uint16, torch.int16)
+    if out is None:
+        out = alloc_map(n, vals.device)
+    st = lib.hia_scatter_csr_sym(_ptr(row_ptr), _ptr(cols), cols.element_size(), _ptr(vals), n, _ptr(out),
+                                 out.stride(0), mtx_type, _stream())
+    _lib.check(st, "hia_scatter_csr_sym")
+    return out
+
+
+def coo_to_csr_host(rows, cols, vals, n, cols16=None):
+    """Row-sorted host COO (numpy / CPU tensors) -> (row_ptr int64 [n + 1], cols int32 | uint16, vals fp32)
+    pinned CPU tensors. cols16 (default: n <= 65 536): 16-bit column indices."""
+    rows = np.asarray(rows)
+    cols = np.asarray(cols)
+    vals = np.asarray(vals, dtype=np.float32)
+    if rows.size and np.any(rows[1:] < rows[:-1]):
+        order = np.argsort(rows, kind="stable")
+        rows, cols, vals = rows[order], cols[order], vals[order]
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=n), out=row_ptr[1:])
+    cols16 = (n <= 65536) if cols16 is None else cols16
+    ct = np.uint16 if cols16 else np.int32
+    out = []
+    for a in (row_ptr, cols.astype(ct), vals):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        out.append(t.pin_memory() if torch.cuda.is_available() else t)
+    return tuple(out)
+
+
 # ------------------------------------------------------------------------------- a4/a5 O/E
 class OEState:
     """Device-side by-products of the O/E passes (kept for inspection / return_exp_counts)."""

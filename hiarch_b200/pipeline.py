@@ -5,12 +5,18 @@
 this is the object `bench.py` times and the call a user of the class-level API makes for the
 BASELINE.json configs that the shipped CLI pipeline never reaches.
 """
+import collections
 import os
 
 import numpy as np
 import torch
 
 from . import _lib, ops
+
+# A sample in CSR form (host or device tensors): row_ptr int64 [n + 1], cols int32 | uint16 [nnz],
+# vals fp32 [nnz] -- 8 or 6 bytes per entry over PCIe instead of the 12 of a COO triple
+# (ops.coo_to_csr_host builds one from row-sorted COO arrays).
+CsrSample = collections.namedtuple("CsrSample", "row_ptr cols vals")
 
 
 class HotPath:
@@ -45,6 +51,7 @@ class HotPath:
             self.d_rows = torch.empty(max_nnz, dtype=torch.int32, device=device)
             self.d_cols = torch.empty(max_nnz, dtype=torch.int32, device=device)
             self.d_vals = torch.empty(max_nnz, dtype=torch.float32, device=device)
+            self.d_rowptr = torch.empty(n + 1, dtype=torch.int64, device=device)
 
     # ---- stages -------------------------------------------------------------------------
     def raw_symmetric(self):
@@ -53,6 +60,10 @@ class HotPath:
             return self.raw
         up = torch.triu(self.raw)
         return up + torch.triu(up, 1).t()
+
+    def scatter_csr(self, row_ptr, cols, vals):
+        mt = ops.MTX_TRIU_UPPER if self.upper_only else ops.MTX_TRIU
+        return ops.scatter_csr_sym(row_ptr, cols, vals, self.n, mtx_type=mt, out=self.raw)
 
     def scatter(self, rows, cols, vals):
         mt = ops.MTX_TRIU_UPPER if self.upper_only else ops.MTX_TRIU
@@ -85,36 +96,64 @@ class HotPath:
                             workspace=self._eig_ws)
 
     # ---- whole path ---------------------------------------------------------------------
-    def run_device(self, rows, cols, vals):
-        """Inputs already in HBM. Returns (eigvals [k] fp64, eigvecs [n, k] fp32) on the device."""
-        self.scatter(rows, cols, vals)
+    def run_device(self, rows, cols=None, vals=None):
+        """Inputs already in HBM: COO (rows, cols, vals) or one CsrSample. Returns (eigvals [k] fp64,
+        eigvecs [n, k] fp32) on the device."""
+        if isinstance(rows, CsrSample):
+            self.scatter_csr(*rows)
+        else:
+            self.scatter(rows, cols, vals)
         self.normalise()
         self.similarity()
         return self.eigen()
 
-    def run_host(self, rows_h, cols_h, vals_h):
-        """End to end from pinned HOST buffers: H2D of the COO, the whole path, D2H of the
-        eigenpairs. Returns (eigvals ndarray [k], eigvecs ndarray [n, k])."""
+    def _upload(self, smp, bufs):
+        """H2D of one sample (COO triple or CsrSample of pinned host tensors) into the device buffers
+        `bufs` = (rows, cols, vals, row_ptr) on the current stream. Returns what run_device takes."""
+        d_rows, d_cols, d_vals, d_rowptr = bufs
+        if isinstance(smp, CsrSample):
+            nnz = smp.vals.numel()
+            assert nnz <= self.max_nnz and smp.row_ptr.numel() == self.n + 1
+            c = d_cols.view(smp.cols.dtype)[:nnz] if smp.cols.dtype != torch.int32 else d_cols[:nnz]
+            d_rowptr.copy_(smp.row_ptr, non_blocking=True)
+            c.copy_(smp.cols, non_blocking=True)
+            d_vals[:nnz].copy_(smp.vals, non_blocking=True)
+            return (CsrSample(d_rowptr, c, d_vals[:nnz]),)
+        rows_h, cols_h, vals_h = smp
         nnz = rows_h.numel()
-        assert self.max_nnz and nnz <= self.max_nnz
-        r, c, v = self.d_rows[:nnz], self.d_cols[:nnz], self.d_vals[:nnz]
+        assert nnz <= self.max_nnz
+        r, c, v = d_rows[:nnz], d_cols[:nnz], d_vals[:nnz]
         r.copy_(rows_h, non_blocking=True)
         c.copy_(cols_h, non_blocking=True)
         v.copy_(vals_h, non_blocking=True)
-        w, vecs = self.run_device(r, c, v)
+        return r, c, v
+
+    @staticmethod
+    def sample_bytes(smp):
+        """Bytes that cross PCIe for one sample."""
+        return int(sum(t.numel() * t.element_size() for t in smp))
+
+    def run_host(self, rows_h, cols_h=None, vals_h=None):
+        """End to end from pinned HOST buffers: H2D of the COO (or of one CsrSample), the whole path,
+        D2H of the eigenpairs. Returns (eigvals ndarray [k], eigvecs ndarray [n, k])."""
+        assert self.max_nnz
+        smp = rows_h if isinstance(rows_h, CsrSample) else (rows_h, cols_h, vals_h)
+        args = self._upload(smp, (self.d_rows, self.d_cols, self.d_vals, self.d_rowptr))
+        w, vecs = self.run_device(*args)
         return w.cpu().numpy(), vecs.cpu().numpy()
 
     def run_host_many(self, samples):
         """A stream of samples (the reference's ParallelFunc loop over a dataset, one GPU): the COO of
         sample i + 1 is copied H2D on a second stream into the other device buffer while sample i
         is computed, so the PCIe time (2.7 GB at 100 kb genome-wide) hides behind the compute.
-        samples: iterable of (rows_h, cols_h, vals_h) pinned host tensors. Yields (eigvals, eigvecs)
-        as numpy arrays, in order."""
+        samples: iterable of (rows_h, cols_h, vals_h) pinned host tensors or CsrSample (8 / 6 instead of
+        12 bytes per entry over PCIe). Yields (eigvals, eigvecs) as numpy arrays, in order."""
         assert self.max_nnz
         if not hasattr(self, "_bufs2"):
             dev = self.device
-            self._bufs2 = [(self.d_rows, self.d_cols, self.d_vals),
-                           (torch.empty_like(self.d_rows), torch.empty_like(self.d_cols), torch.empty_like(self.d_vals))]
+            self._bufs2 = [(self.d_rows, self.d_cols, self.d_vals, self.d_rowptr),
+                           (torch.empty_like(self.d_rows), torch.empty_like(self.d_cols), torch.empty_like(self.d_vals),
+                            torch.empty_like(self.d_rowptr))]
             self._copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream()
         copied = [torch.cuda.Event(), torch.cuda.Event()]
@@ -123,34 +162,27 @@ class HotPath:
         freed[1].record(main)
 
         def issue_copy(slot, smp):
-            rows_h, cols_h, vals_h = smp
-            nnz = rows_h.numel()
-            assert nnz <= self.max_nnz
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(freed[slot])            # the compute that read this buffer is done
-                r, c, v = (b[:nnz] for b in self._bufs2[slot])
-                r.copy_(rows_h, non_blocking=True)
-                c.copy_(cols_h, non_blocking=True)
-                v.copy_(vals_h, non_blocking=True)
+                args = self._upload(smp, self._bufs2[slot])
                 copied[slot].record(self._copy_stream)
-            return nnz
+            return args
 
         it = iter(samples)
         cur = next(it, None)
         if cur is None:
             return
-        nnz_cur = issue_copy(0, cur)
+        args_cur = issue_copy(0, cur)
         i = 0
         while cur is not None:
             slot = i & 1
             nxt = next(it, None)
-            nnz_nxt = issue_copy(slot ^ 1, nxt) if nxt is not None else 0
+            args_nxt = issue_copy(slot ^ 1, nxt) if nxt is not None else None
             main.wait_event(copied[slot])
-            r, c, v = (b[:nnz_cur] for b in self._bufs2[slot])
-            w, vecs = self.run_device(r, c, v)
+            w, vecs = self.run_device(*args_cur)
             freed[slot].record(main)
             yield w.cpu().numpy(), vecs.cpu().numpy()
-            cur, nnz_cur, i = nxt, nnz_nxt, i + 1
+            cur, args_cur, i = nxt, args_nxt, i + 1
 
     def cells(self):
         return self.n * self.n
@@ -227,12 +259,15 @@ class SampleGraph:
     the tail is padded with explicit zeros at (n - 1, n - 1), which keeps the entries row-sorted and
     adds 0.0 to one cell."""
 
-    def __init__(self, paths, nnz_caps, branches=8, eig_steps=8):
+    def __init__(self, paths, nnz_caps, branches=8, eig_steps=12):
         self.paths = list(paths)
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.branches = max(1, min(int(branches), len(self.paths)))
         self.nnz_caps = [int(c) for c in nnz_caps]
         self.bufs, self.eig = [], []
+        kmax = max(hp.k_eig for hp in self.paths)
+        # residuals | gaps | eigenvalues of every chromosome in ONE tensor: one D2H read per sample
+        self.summary = torch.zeros((len(self.paths), 3 * kmax), dtype=torch.float64, device=self.device)
         for hp, cap in zip(self.paths, self.nnz_caps):
             self.bufs.append((torch.full((cap,), hp.n - 1, dtype=torch.int32, device=self.device),
                               torch.full((cap,), hp.n - 1, dtype=torch.int32, device=self.device),
@@ -254,7 +289,10 @@ class SampleGraph:
         hp.scatter(r, c, v)
         hp.normalise()
         hp.similarity()
-        ops.topk_eig_cycle(hp.sim, self.eig[i])            # all steps, no early check: no host read
+        e = self.eig[i]
+        ops.topk_eig_cycle(hp.sim, e)                       # all steps, no early check: no host read
+        self.summary[i, :2 * e.k].copy_(e.stats, non_blocking=True)
+        self.summary[i, 2 * e.k:3 * e.k].copy_(e.eigvals, non_blocking=True)
 
     def load(self, coos):
         """Copy the sample's COO arrays (device or pinned host tensors) into the fixed buffers."""
@@ -302,12 +340,13 @@ class SampleGraph:
             self.load(coos)
         self.graph.replay()
         out = []
-        stats = [(e.stats.cpu().numpy(), e.eigvals.cpu().numpy()) for e in self.eig]     # first .cpu() synchronises
+        summary = self.summary.cpu().numpy()                          # the one synchronising read
         self.fallbacks = 0
-        for i, (sg, lam) in enumerate(stats):
+        for i in range(len(self.paths)):
             k = self.eig[i].k
+            sg, lam = summary[i, :2 * k], summary[i, 2 * k:3 * k]
             if ops.eig_converged(sg[:k], lam, sg[k:], tol, angle_tol):
-                out.append((lam, self.eig[i].eigvecs.t().cpu().numpy()))
+                out.append((lam.copy(), self.eig[i].eigvecs.t().cpu().numpy()))
             else:                                                     # finish with the restarting solver
                 self.fallbacks += 1
                 w, vecs = ops.topk_eig(self.paths[i].sim, k=k, block=self.paths[i].eig_block, tol=tol,

@@ -70,6 +70,14 @@ int64_t hia_scatter_workspace_bytes(int32_t n, int32_t n_chr);
 int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz,
                         int32_t n, float* out, int64_t ld, int mtx_type, int fill_mode,
                         const int32_t* chr_start, int32_t n_chr, void* workspace, void* stream);
+/* The same from CSR (SpsHiCMtx.matrix is a scipy CSR matrix, publish/new_hic_class.py:2158-2161):
+ * row_ptr[n + 1] int64, column indices int32 (col_bytes = 4) or uint16 (col_bytes = 2, n <= 65 536),
+ * values fp32; zero fill. 8 (6) bytes per entry instead of 12: the bytes that cross PCIe in the
+ * end-to-end path. No row-pointer pass, no fallback (CSR rows are sorted by construction).
+ * Row r of an 'ALL' map starts at column 0; a 'triu' row at the diagonal (earlier columns ignored). */
+int hia_scatter_csr_sym(const int64_t* row_ptr, const void* cols, int col_bytes, const float* vals,
+                        int32_t n, float* out, int64_t ld, int mtx_type, void* stream);
+
 
 /* ------------------------------------------------------------------------------------ */
 /* f1  coarse-graining / trimming as an index remap fused into the scatter                 */

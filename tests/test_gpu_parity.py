@@ -41,6 +41,48 @@ def test_scatter_zero_fill_bit_exact(golden, case):
     assert np.array_equal(dense.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("case", ["g3chr", "g1chr", "gquirk"])
+@pytest.mark.parametrize("cols16", [False, True])
+def test_scatter_from_csr_bit_exact(golden, case, cols16):
+    """CSR input (int32 and uint16 column indices) gives the oracle's dense map bit for bit, for the
+    mirrored, the upper-only and the 'all' matrix types; unsorted columns, duplicates, an empty row
+    and out-of-range columns included."""
+    from hiarch_b200 import ops
+    g = golden(case)
+    n = int(g["in.lens"].sum())
+    rows, cols, vals = g["in.rows"].copy(), g["in.cols"].copy(), g["in.vals"].copy()
+    rng = np.random.default_rng(1)
+    # shuffle the entries inside every row (CSR does not promise sorted columns) and add duplicates
+    dup = rng.choice(rows.size, size=50, replace=False)
+    drows, dcols = rows[dup], cols[dup]
+    rows, cols, vals = np.r_[rows, drows], np.r_[cols, dcols], np.r_[vals, vals[dup] * 0.5]
+    order = np.lexsort((rng.random(rows.size), rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    ref = O.scatter_coo_sym(rows, cols, vals, n).astype(np.float32)
+    rp, cc, vv = ops.coo_to_csr_host(rows, cols, vals, n, cols16=cols16)
+    assert cc.dtype == (torch.uint16 if cols16 else torch.int32) and rp.dtype == torch.int64
+    rp, cc, vv = rp.cuda(), cc.cuda(), vv.cuda()
+    full = ops.scatter_csr_sym(rp, cc, vv, n, mtx_type=ops.MTX_TRIU)
+    got = full.cpu().numpy()
+    # duplicates are summed in fp32 in an order of their own: last bit there, exact everywhere else
+    dmask = np.zeros((n, n), dtype=bool)
+    dmask[drows, dcols] = True
+    dmask |= dmask.T
+    assert np.array_equal(got[~dmask], ref[~dmask])
+    assert np.allclose(got[dmask], ref[dmask], rtol=3e-7, atol=0)
+    up = ops.alloc_map(n)
+    up.fill_(float("nan"))
+    ops.scatter_csr_sym(rp, cc, vv, n, mtx_type=ops.MTX_TRIU_UPPER, out=up)
+    iu = np.triu_indices(n)
+    assert np.array_equal(up.cpu().numpy()[iu], got[iu])             # upper triangle written, lower untouched
+    assert torch.isnan(torch.tril(up, -1)[np.tril_indices(n, -1)]).all()
+    # 'all' type: the symmetric matrix as CSR of every cell
+    fr, fc = np.nonzero(ref)
+    rp2, cc2, vv2 = ops.coo_to_csr_host(fr, fc, ref[fr, fc], n, cols16=cols16)
+    allm = ops.scatter_csr_sym(rp2.cuda(), cc2.cuda(), vv2.cuda(), n, mtx_type=ops.MTX_ALL)
+    assert np.array_equal(allm.cpu().numpy(), ref)
+
+
 @pytest.mark.parametrize("case", ["g3chr", "g1chr"])
 def test_scatter_min_fill_bit_exact(golden, case):
     from hiarch_b200 import ops

@@ -142,8 +142,17 @@ def test_hot_path_streaming_matches_blocking_calls():
         samples.append((pin(rows, torch.int32), pin(cols, torch.int32), pin(vals, torch.float32)))
         dense = O.scatter_coo_sym(rows, cols, vals, sum(lens))
         refs.append(O.topk_eig(O.pearson(O.oe_map_core(dense, seps, bs)), 3))
+    from hiarch_b200 import ops
+    from hiarch_b200.pipeline import CsrSample
     streamed = list(hp.run_host_many(samples))
     assert len(streamed) == 3
+    # the same samples as CSR (16-bit columns: 6 bytes per entry over PCIe) through the same call
+    csr = [CsrSample(*ops.coo_to_csr_host(r.numpy(), c.numpy(), v.numpy(), sum(lens))) for r, c, v in samples]
+    assert all(s_.cols.dtype == torch.uint16 for s_ in csr)
+    streamed_csr = list(hp.run_host_many(csr))
+    for (w, v), (wc, vc) in zip(streamed, streamed_csr):
+        assert np.allclose(w, wc, rtol=1e-9) and np.allclose(np.abs(v), np.abs(vc), atol=1e-5)   # same dense map
+    assert hp.sample_bytes(csr[0]) < 0.55 * hp.sample_bytes(samples[0])
     for (w, v), smp, (w_ref, v_ref) in zip(streamed, samples, refs):
         w2, v2 = hp.run_host(*smp)
         assert np.allclose(w, w2, rtol=1e-9) and np.allclose(np.abs(v), np.abs(v2), atol=1e-5)

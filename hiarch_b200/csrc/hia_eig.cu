@@ -511,6 +511,22 @@ jacobi_kernel(const double* __restrict__ h, int D, int dim, double* __restrict__
     V[(long long)col * dim + row] = (row == col) ? 1.0 : 0.0;
   }
   __syncthreads();
+  // Noise floor of the column inner products. Every rotation perturbs the columns by ~eps ||T||, so
+  // gamma = a_p . a_q cannot be driven below ~eps ||T|| max(||a_p||, ||a_q||): pairs of columns that
+  // belong to SMALL Ritz values never met the purely relative test (|gamma| <= 1e-12 ||a_p|| ||a_q||)
+  // and every solve ran all `max_sweeps` sweeps (1.59 ms at dim 64, launch list of round 1 / 2) for
+  // rotations that change nothing. amax = max_p ||a_p||^2 ~ ||T||^2.
+  __shared__ double s_amax;
+  if (tid == 0) s_amax = 0.0;
+  __syncthreads();
+  for (int p = warp; p < dim; p += nwarps) {
+    double a2 = 0.0;
+    for (int r = lane; r < dim; r += 32) { const double x = A[(long long)p * dim + r]; a2 += x * x; }
+    a2 = warp_sum(a2);
+    if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(&s_amax), (unsigned long long)__double_as_longlong(a2));
+  }
+  __syncthreads();
+  const double floor2 = 1.2e-28 * s_amax;                // (50 eps)^2 ||T||^2
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     if (tid == 0) s_rot = 0;
     __syncthreads();
@@ -527,11 +543,16 @@ jacobi_kernel(const double* __restrict__ h, int D, int dim, double* __restrict__
           alpha += x * x; beta += y * y; gamma += x * y;
         }
         alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
-        // |gamma| <= 1e-12 sqrt(alpha beta), compared squared: no sqrt on the dependent chain
-        if (gamma * gamma <= 1e-24 * alpha * beta || gamma == 0.0) continue;
+        // |gamma| <= 1e-12 sqrt(alpha beta), compared squared (no sqrt on the dependent chain), or
+        // below the noise floor
+        const double g2 = gamma * gamma;
+        if (g2 <= 1e-24 * alpha * beta || g2 <= floor2 * fmax(alpha, beta) || gamma == 0.0) continue;
         if (lane == 0) s_rot = 1;
-        const double zeta = (beta - alpha) / (2.0 * gamma);
-        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (beta - alpha) / (2 gamma), written with
+        // ONE division and one square root:  t = sign(d g) |2 gamma| / (|d| + sqrt(d^2 + 4 gamma^2))
+        const double d = beta - alpha, tg = 2.0 * gamma;
+        const double den = fabs(d) + sqrt(d * d + tg * tg);
+        const double t = copysign(fabs(tg) / den, d * tg >= 0.0 ? 1.0 : -1.0);
         const double cs = rsqrt(1.0 + t * t), sn = cs * t;
         double* vp = V + (long long)p * dim; double* vq = V + (long long)q * dim;
         for (int r = lane; r < dim; r += 32) {
@@ -1172,7 +1193,15 @@ HIA_API int hia_eig_resid(int32_t n, int32_t block, int32_t steps, int32_t k, co
 
 // First convergence check after 2/3 of the steps (each check costs a Jacobi solve of the projected
 // matrix, ~1 ms in one CTA: about one pass over a 30 k map), then after every second step.
-HIA_API int32_t hia_eig_first_check(int32_t steps) { return steps * 2 / 3 > 4 ? steps * 2 / 3 : 4; }
+HIA_API int32_t hia_eig_first_check(int32_t steps) {
+  const char* e = getenv("HIA_EIG_FIRST_CHECK");        // tuning knob (tools)
+  if (e && atoi(e) > 0) return atoi(e);
+  return steps * 2 / 3 > 4 ? steps * 2 / 3 : 4;
+}
+static int eig_check_every() {
+  const char* e = getenv("HIA_EIG_CHECK_EVERY");
+  return (e && atoi(e) > 0) ? atoi(e) : 2;
+}
 
 // ---- single-device driver: all phases on one stream. early_rel_tol / early_angle_tol > 0 enable the
 // pass-free convergence check (hia_eig_check, one tiny D2H flag) after every second step from
@@ -1215,7 +1244,8 @@ HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32
     st = hia_eig_absorb(n, block, steps, j, ystage, workspace, stream);
     if (st != HIA_OK) return st;
     const int done = j + 1;
-    if (early && done >= hia_eig_first_check(steps) && ((done - hia_eig_first_check(steps)) & 1) == 0 && done < steps) {
+    if (early && done >= hia_eig_first_check(steps) && ((done - hia_eig_first_check(steps)) % eig_check_every()) == 0 &&
+        done < steps) {
       int conv = 0;
       st = hia_eig_check(n, block, steps, done, k, early_rel_tol, early_angle_tol, &conv, nullptr, workspace, stream);
       if (st != HIA_OK) return st;

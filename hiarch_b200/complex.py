@@ -13,15 +13,18 @@ min_n_short_sims = ops.MIN_N_SHORT_SIMS
 
 
 def get_adj_mtx(input_mtx, metric='cosine'):
-    """squareform(pdist(M, 'cosine')) on tcgen05 (3xTF32)."""
-    if metric != 'cosine':
-        raise NotImplementedError("only metric='cosine' (the pipeline's metric)")
+    """squareform(pdist(M, metric)) on tcgen05. metric: 'cosine' (the pipeline's, S1_get_adj_mtx.py:8) or
+    'correlation' (1 - Pearson, the same contraction on row-centred rows). scipy's other pdist
+    metrics are not inner-product shaped and are not on the hot path: NotImplementedError."""
+    flavours = {'cosine': ops.SIM_COSINE_DISTANCE, 'correlation': ops.SIM_CORRELATION_DISTANCE}
+    if metric not in flavours:
+        raise NotImplementedError(f"metric={metric!r}: only 'cosine' and 'correlation' run on the tensor cores")
     blk = input_mtx.dmatrix
     if blk.data_ptr() % 16 or blk.stride(0) % 4 or blk.stride(1) != 1:
         tmp = ops.alloc_map(blk.shape[0], blk.device, cols=blk.shape[1])
         tmp.copy_(blk)
         blk = tmp
-    adj = ops.similarity(blk, flavour=ops.SIM_COSINE_DISTANCE)
+    adj = ops.similarity(blk, flavour=flavours[metric])
     return ArrayHiCMtx(adj, copy_mtx_paras=input_mtx, has_neg=False, col_window=input_mtx.row_window,
                        mtx_type='all')
 

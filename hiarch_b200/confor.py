@@ -167,18 +167,20 @@ def change_map_name(ave_maps, ave_names):
 
 def _template_scores_device(xs_arr, ave_maps, do_trans):
     """scores = X (P x 256) . T^T (256 x k) for caller-supplied templates, max with the transposed
-    images for inter pairs (to_confor.py:39-46): a P x 256 x 5 product, taken on the GPU (torch /
-    cuBLAS: plumbing-sized; the built-in templates never come here, their scores are produced by
-    `hia_gf_pool_scores` together with the images)."""
+    images for inter pairs (to_confor.py:39-46): `hia_template_scores`, fp64 like the reference (the
+    built-in templates never come here, their scores are produced by `hia_gf_pool_scores` together
+    with the images)."""
     import torch
-    dev = "cuda"
-    x = torch.as_tensor(np.asarray(xs_arr, dtype=np.float64), device=dev)
-    t = torch.as_tensor(np.vstack([np.asarray(v, dtype=np.float64).reshape(-1) for v in ave_maps.values()]),
-                        device=dev)
-    scores = x @ t.T
-    if do_trans:
-        idx = torch.arange(X_SIZE * X_SIZE, device=dev).reshape(X_SIZE, X_SIZE).T.reshape(-1)
-        scores = torch.maximum(scores, x[:, idx] @ t.T)
+    from . import _lib
+    lib = _lib.load()
+    x = torch.as_tensor(np.ascontiguousarray(np.asarray(xs_arr, dtype=np.float64)), device="cuda")
+    t = torch.as_tensor(np.ascontiguousarray(np.vstack([np.asarray(v, dtype=np.float64).reshape(-1)
+                                                        for v in ave_maps.values()])), device="cuda")
+    assert x.shape[1] == X_SIZE * X_SIZE == t.shape[1] == 256
+    scores = torch.empty((x.shape[0], t.shape[0]), dtype=torch.float64, device="cuda")
+    st = lib.hia_template_scores(x.data_ptr(), x.shape[0], t.data_ptr(), t.shape[0], 1 if do_trans else 0,
+                                 scores.data_ptr(), ops._stream())
+    _lib.check(st, "hia_template_scores")
     return scores.cpu().numpy()
 
 

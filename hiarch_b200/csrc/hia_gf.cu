@@ -473,3 +473,41 @@ HIA_API int hia_gf_pool_scores(const float* x, int64_t ld, const int32_t* pairs8
   HIA_LAUNCH_CHECK();
   return HIA_OK;
 }
+
+// Scores of P pooled images against CALLER-SUPPLIED templates (to_confor with a user's .mat,
+// publish/confor/src/S5_sim_to_pat/to_confor.py:35-47): scores[p][t] = xs[p] . tmpl[t]; do_trans:
+// max with the score of the transposed 16 x 16 image (inter-chromosome pairs, :42-46). One warp per
+// (image, template); fp64 like the reference. (Round 1 took this branch through torch / cuBLAS.)
+namespace hia {
+namespace {
+__global__ void __launch_bounds__(256)
+template_scores_kernel(const double* __restrict__ xs, const double* __restrict__ tmpl, int n_img, int n_tmpl,
+                       int do_trans, double* __restrict__ scores) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_img * n_tmpl) return;
+  const int p = w / n_tmpl, t = w % n_tmpl;
+  const double* x = xs + (long long)p * 256;
+  const double* tm = tmpl + (long long)t * 256;
+  double a = 0.0, b = 0.0;
+  for (int i = lane; i < 256; i += 32) {
+    const double tv = tm[i];
+    a += x[i] * tv;
+    b += x[(i & 15) * 16 + (i >> 4)] * tv;                 // element i of the transposed image
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) scores[(long long)p * n_tmpl + t] = do_trans ? fmax(a, b) : a;
+}
+}  // namespace
+}  // namespace hia
+
+HIA_API int hia_template_scores(const double* xs, int32_t n_img, const double* tmpl, int32_t n_tmpl, int do_trans,
+                                double* scores, void* stream_) {
+  using namespace hia;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (!xs || !tmpl || !scores || n_img <= 0 || n_tmpl <= 0) return HIA_ERR_BAD_ARG;
+  const long long warps = (long long)n_img * n_tmpl;
+  template_scores_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, s>>>(xs, tmpl, n_img, n_tmpl, do_trans ? 1 : 0, scores);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}

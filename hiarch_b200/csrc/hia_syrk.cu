@@ -396,7 +396,7 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       }
       // ---- finalize + store (overlaps the next tile's MMAs)
       const int gr_base = m0 + q * 32;                      // first A row of this warp
-      const float diag_val = (flavour == HIA_SIM_COSINE_DISTANCE) ? 0.f : 1.f;
+      const float diag_val = (flavour == HIA_SIM_PEARSON) ? 1.f : 0.f;       // distances: exact 0 diagonal
       float* __restrict__ out = a.out;
       float* __restrict__ out_t = a.out_t;
       const long long ld_out = a.ld_out, ld_t = a.ld_t;
@@ -414,7 +414,7 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             const float raw = (PREC == HIA_PREC_3XF16) ? accr[cg * 32 + j] * kF16Unscale : accr[cg * 32 + j];
             float c = fminf(1.f, fmaxf(-1.f, raw));         // |cos| clipped to 1 like scipy
             if (raw != raw) c = raw;                        // NaN stays NaN
-            f[j] = (flavour == HIA_SIM_COSINE_DISTANCE) ? (1.f - c) : c;
+            f[j] = (flavour == HIA_SIM_PEARSON) ? c : (1.f - c);
           }
           const int gr = gr_base + lane;
           if (out_t != nullptr && gr < row_end) {
@@ -901,7 +901,8 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
   using namespace hia;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !out || !workspace || m <= 0 || k <= 0 || ld_x < k || ld_out < m) return HIA_ERR_BAD_ARG;
-  if (flavour != HIA_SIM_COSINE_DISTANCE && flavour != HIA_SIM_PEARSON) return HIA_ERR_BAD_ARG;
+  if (flavour != HIA_SIM_COSINE_DISTANCE && flavour != HIA_SIM_PEARSON && flavour != HIA_SIM_CORRELATION_DISTANCE)
+    return HIA_ERR_BAD_ARG;
   if (precision != HIA_PREC_FP64 && !split_prec(precision)) return HIA_ERR_BAD_ARG;
   if (workspace_bytes < hia_similarity_workspace_bytes(m, k, precision)) return HIA_ERR_WORKSPACE;
   if (precision == HIA_PREC_FP64)
@@ -921,7 +922,7 @@ static int similarity_impl(const float* x, int32_t m, int32_t k, int64_t ld_x, f
   const int kpad = round_up(k, bk_of(precision));
 
   if (phases & 1) {
-    const int st = launch_prep(x, m, k, ld_x, flavour == HIA_SIM_PEARSON ? 1 : 0, hi, lo, precision, stream);
+    const int st = launch_prep(x, m, k, ld_x, flavour != HIA_SIM_COSINE_DISTANCE ? 1 : 0, hi, lo, precision, stream);
     if (st != HIA_OK) return st;
   }
   if (!(phases & 2)) return HIA_OK;
@@ -1096,7 +1097,7 @@ HIA_API int hia_sim_prep_rows(const float* x_rows, int32_t rows, int32_t k, int6
   if (!x_rows || !hi_rows || !lo_rows || rows <= 0 || k <= 0 || ld_x < k || !split_prec(precision))
     return HIA_ERR_BAD_ARG;
   if (!aligned16(hi_rows) || !aligned16(lo_rows)) return HIA_ERR_ALIGN;
-  return launch_prep(x_rows, rows, k, ld_x, flavour == HIA_SIM_PEARSON ? 1 : 0, hi_rows, lo_rows, precision, stream);
+  return launch_prep(x_rows, rows, k, ld_x, flavour != HIA_SIM_COSINE_DISTANCE ? 1 : 0, hi_rows, lo_rows, precision, stream);
 }
 
 HIA_API int64_t hia_sim_gemm_rows_workspace_bytes(int32_t n, int32_t k) {

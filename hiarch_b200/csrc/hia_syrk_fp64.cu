@@ -115,7 +115,7 @@ syrk_fp64_kernel(const float* __restrict__ x, int m, int k, long long ld_x,
         double v = acc[i][j][e];
         if (fabs(v) > 1.0) v = copysign(1.0, v);          // scipy pdist clips |cos| to 1
         float o;
-        if (flavour == HIA_SIM_COSINE_DISTANCE) o = (c == r) ? 0.f : (float)(1.0 - v);
+        if (flavour != HIA_SIM_PEARSON) o = (c == r) ? 0.f : (float)(1.0 - v);
         else o = (c == r) ? 1.f : (float)v;
         out[(long long)r * ld_out + c] = o;
         if (c != r) out[(long long)c * ld_out + r] = o;
@@ -131,7 +131,7 @@ int similarity_fp64(const float* x, int m, int k, long long ld_x, float* out, lo
   if (workspace_bytes < similarity_fp64_workspace(m, k)) return HIA_ERR_WORKSPACE;
   double* mean = static_cast<double*>(workspace);
   double* inv = mean + m;
-  row_stats_kernel<<<m, 256, 0, stream>>>(x, m, k, ld_x, flavour == HIA_SIM_PEARSON ? 1 : 0, mean, inv);
+  row_stats_kernel<<<m, 256, 0, stream>>>(x, m, k, ld_x, flavour != HIA_SIM_COSINE_DISTANCE ? 1 : 0, mean, inv);
   HIA_LAUNCH_CHECK();
   dim3 grid((m + TN - 1) / TN, (m + TM - 1) / TM);
   syrk_fp64_kernel<<<grid, 256, 0, stream>>>(x, m, k, ld_x, mean, inv, out, ld_out, flavour);

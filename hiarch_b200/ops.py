@@ -17,7 +17,7 @@ from .sgd import oe_tables
 MTX_TRIU, MTX_ALL, MTX_TRIU_UPPER = 0, 1, 2      # TRIU_UPPER: no mirror pass, lower triangle unwritten
 FILL_ZERO, FILL_MIN, FILL_BLOCK_MIN = 0, 1, 2
 OE_LOG, OE_ONLY_INTRA, OE_FROM_UPPER = 1, 2, 4
-SIM_COSINE_DISTANCE, SIM_PEARSON = 0, 1
+SIM_COSINE_DISTANCE, SIM_PEARSON, SIM_CORRELATION_DISTANCE = 0, 1, 2
 PREC_3XTF32, PREC_FP64, PREC_3XF16 = 0, 1, 2
 # Default similarity precision: the fp16 hi/lo split (same 22-bit operands as 3xTF32, half the
 # tensor time; header of csrc/hia_syrk.cu). 3XTF32 and FP64 stay selectable per call.

@@ -187,6 +187,7 @@ int hia_log_map(const float* x, float* out, int32_t rows, int32_t cols, int64_t 
 /* ------------------------------------------------------------------------------------ */
 #define HIA_SIM_COSINE_DISTANCE 0   /* out = 1 - cos, exact 0 diagonal (pdist/squareform) */
 #define HIA_SIM_PEARSON 1           /* out = corr,     exact 1 diagonal                    */
+#define HIA_SIM_CORRELATION_DISTANCE 2   /* out = 1 - corr, exact 0 diagonal (pdist 'correlation') */
 #define HIA_PREC_3XTF32 0           /* tcgen05 kind::tf32, hi/lo split, fp32 accumulate    */
 #define HIA_PREC_FP64 1             /* FP64 DMMA (mma.sync m8n8k4), fp64 accumulate        */
 #define HIA_PREC_3XF16 2            /* tcgen05 kind::f16, hi/lo split of the row scaled by 2^14 (fp16 has
@@ -323,6 +324,13 @@ int hia_used_filter_f64(const float* x, int32_t rows, int32_t cols, int64_t ld_i
 int hia_gf_pool_scores(const float* x, int64_t ld, const int32_t* pairs8, int32_t n_pairs,
                        const double* tmpl_intra, const double* tmpl_inter, double* pooled,
                        double* isym, double* xs, double* scores, void* stream);
+/* Scores of n_img pooled 16 x 16 images (xs [n_img][256] fp64, device) against CALLER-SUPPLIED,
+ * already normalised templates (tmpl [n_tmpl][256] fp64): scores[p][t] = xs[p] . tmpl[t]; do_trans:
+ * max with the transposed image's score (inter pairs). to_confor with a user's template file,
+ * confor/src/S5_sim_to_pat/to_confor.py:35-47. */
+int hia_template_scores(const double* xs, int32_t n_img, const double* tmpl, int32_t n_tmpl, int do_trans,
+                        double* scores, void* stream);
+
 
 /* Row-sharded similarity (the one exchange step of the path): every rank
  * prepares the hi/lo planes of ITS rows (hia_sim_prep_rows; planes are row-major with

@@ -697,3 +697,37 @@ def test_remap_scatter_and_coo_statistics_vs_numpy():
     np.add.at(ref_cnt, (chr_of[r[nz]], chr_of[c[nz]]), 1)
     np.add.at(ref_cnt, (chr_of[c[nz & off]], chr_of[r[nz & off]]), 1)
     assert np.array_equal(cnt.cpu().numpy().reshape(3, 3), ref_cnt)
+
+
+def test_get_adj_mtx_metrics_against_scipy_pdist():
+    """get_adj_mtx(metric=...) (S1_get_adj_mtx.py:8-14 forwards any metric to pdist): 'cosine' and
+    'correlation' run on the tensor cores and match scipy to 1e-5; anything else refuses loudly."""
+    from scipy.spatial.distance import pdist, squareform
+    from hiarch_b200 import complex as cx
+    from hiarch_b200.new_hic_class import ArrayHiCMtx
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((300, 417)) + 0.7 * rng.standard_normal((300, 1)) + 0.4
+    m = ArrayHiCMtx(x.astype(np.float32), mtx_type='all', has_neg=True)
+    x32 = x.astype(np.float32).astype(np.float64)
+    for metric in ("cosine", "correlation"):
+        got = cx.get_adj_mtx(m, metric=metric).matrix
+        ref = squareform(pdist(x32, metric))
+        assert np.abs(got - ref).max() <= ATOL, metric
+        assert np.all(np.diag(got) == 0.0)
+    with pytest.raises(NotImplementedError):
+        cx.get_adj_mtx(m, metric="euclidean")
+
+
+def test_template_scores_for_caller_supplied_templates():
+    """to_confor with a caller's template dict (to_confor.py:35-47) on the native kernel: plain and
+    transposed-max scores against numpy fp64."""
+    from hiarch_b200 import confor
+    rng = np.random.default_rng(4)
+    xs = rng.standard_normal((37, 256))
+    tm = {f"t{i}": rng.standard_normal(256) for i in range(5)}
+    t = np.vstack(list(tm.values()))
+    plain = confor._template_scores_device(xs, tm, False)
+    assert np.abs(plain - xs @ t.T).max() <= 1e-12
+    xt = xs.reshape(-1, 16, 16).transpose(0, 2, 1).reshape(-1, 256)
+    both = confor._template_scores_device(xs, tm, True)
+    assert np.abs(both - np.maximum(xs @ t.T, xt @ t.T)).max() <= 1e-12

@@ -372,8 +372,7 @@ def run_row_sharded(args, world, rank, local, pk, steps=2):
     # eigen residual of the sharded result: || C[rows, :] u - lambda u[rows] ||, all-reduced
     vv = v.double()
     lam = w.double()
-    cu = path.sim_rows.double() @ vv if path.rows * n <= 2 ** 31 else torch.cat(
-        [path.sim_rows[i:i + 2048].double() @ vv for i in range(0, path.rows, 2048)])
+    cu = torch.cat([path.sim_rows[i:i + 2048].double() @ vv for i in range(0, max(path.rows, 1), 2048)])
     r2 = ((cu - vv[path.row0:path.row0 + path.rows] * lam[None, :]) ** 2).sum(dim=0)
     dist.all_reduce(r2)
     eig_res = float((r2.sqrt() / lam[0].abs()).max())

@@ -19,13 +19,12 @@ def _free_port():
         return sk.getsockname()[1]
 
 
-@pytest.mark.parametrize("n", [1500, 3333])
-def test_row_sharded_similarity_and_eigen_match_single_gpu(n):
+@pytest.mark.parametrize("n,world", [(1500, 2), (3333, 2), (3333, 4), (2900, 3), (4000, 8)])
+def test_row_sharded_similarity_and_eigen_match_single_gpu(n, world):
     import torch
     ngpu = torch.cuda.device_count()
-    if ngpu < 2:
-        pytest.skip("needs 2 GPUs")
-    world = 2 if ngpu < 4 else 4
+    if ngpu < world:
+        pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(n)]

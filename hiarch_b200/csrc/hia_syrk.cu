@@ -503,10 +503,11 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
   // shift by the first element: keeps sum((x - s)^2) - n (mean - s)^2 well conditioned
   const double shift = (double)row[0];
   double s1 = 0.0, s2 = 0.0;
+  const unsigned long long keep = l2_policy_evict_last();
   if (vec_ok) {
     const int k4 = k >> 2;
     for (int j = tid; j < k4; j += blockDim.x) {
-      const float4 v = *reinterpret_cast<const float4*>(row + 4 * j);
+      const float4 v = ld_keep4(row + 4 * j, keep);        // stays in L2 for the second pass
       const double a = (double)v.x - shift, b = (double)v.y - shift, c = (double)v.z - shift, d = (double)v.w - shift;
       s1 += (a + b) + (c + d);
       s2 += (a * a + b * b) + (c * c + d * d);
@@ -540,7 +541,7 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
       const int j = j4 << 2;
       float xv[4] = {0.f, 0.f, 0.f, 0.f};
       if (j + 3 < k) {
-        const float4 v = *reinterpret_cast<const float4*>(row + j);
+        const float4 v = ld_last4(row + j);                  // last use: evict first
         xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
       } else {
         for (int e = 0; e < 4; ++e) if (j + e < k) xv[e] = row[j + e];
@@ -554,12 +555,13 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
           h[e] = P(0.f); l[e] = P(0.f);
         }
       }
+      // streaming stores: the planes must not evict the rows that still wait for their second pass
       if constexpr (PREC == HIA_PREC_3XF16) {
-        *reinterpret_cast<uint2*>(ph + j) = *reinterpret_cast<const uint2*>(h);
-        *reinterpret_cast<uint2*>(pl + j) = *reinterpret_cast<const uint2*>(l);
+        st_cs_u2(ph + j, *reinterpret_cast<const uint2*>(h));
+        st_cs_u2(pl + j, *reinterpret_cast<const uint2*>(l));
       } else {
-        *reinterpret_cast<float4*>(ph + j) = *reinterpret_cast<const float4*>(h);
-        *reinterpret_cast<float4*>(pl + j) = *reinterpret_cast<const float4*>(l);
+        st_cs_f4(ph + j, *reinterpret_cast<const float4*>(h));
+        st_cs_f4(pl + j, *reinterpret_cast<const float4*>(l));
       }
     }
   } else {

@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-checks", action="store_true", help="skip the in-run fp64 parity checks")
     ap.add_argument("--no-row-sharded", action="store_true", help="N > 1: skip the row-sharded genome-wide chain")
+    ap.add_argument("--no-c3", action="store_true", help="skip the per-chromosome batch (config C3)")
+    ap.add_argument("--c3-samples", type=int, default=64)
     ap.add_argument("--row-sharded-res", type=int, default=0,
                     help="bin size of the row-sharded chain (default: 50 kb at 2 GPUs, 25 kb at 4 / 8)")
     ap.add_argument("--cpu-sample-chroms", default="chr16,chr17,chr18,chr19,chr20,chr21,chr22")
@@ -317,6 +319,47 @@ def gpu_on_sample(args, dense_host, seps, prec, steps=5, warmup=3):
             "gpu_e2e_ms_per_step": e2e_ms, "gpu_e2e_cells_per_s": n * n / (e2e_ms * 1e-3)}
 
 
+def run_c3(args, world, rank, max_over_ranks, barrier, res=50000, workers=8):
+    """BASELINE.json config C3: `--c3-samples` (64) samples x 24 per-chromosome maps at 50 kb (935 ... 4 980
+    bins, 1.9e8 cells per sample), sharded by sample over the ranks like the reference's ParallelFunc
+    (publish/run_hic_dataset.py:259-269, :573-603), no communication. Each chromosome goes through
+    scatter -> O/E + log -> Pearson -> top-3 eigenvectors; the 24 chains of a sample run on 8 host
+    threads / streams (pipeline.HotPathPool: chromosome-sized chains are latency-bound). Every rank
+    re-runs ITS synthetic sample (device-resident COO) samples / world times."""
+    import torch
+    from hiarch_b200 import synth
+    from hiarch_b200.pipeline import HotPath, HotPathPool, dense_to_coo
+    bins = synth.hg38_bins(res)
+    paths, coos, cells = [], [], 0
+    for i, (_, n) in enumerate(bins):
+        dense, seps = synth.device_dense_map([n], seed=1000 * rank + 100 + i)
+        coos.append(dense_to_coo(dense))
+        paths.append(HotPath(seps, res, k_eig=3))
+        cells += n * n
+        del dense
+    pool = HotPathPool(paths, workers=workers)
+    n_local = [args.c3_samples // world + (1 if r < args.c3_samples % world else 0) for r in range(world)][rank]
+    for _ in range(2):
+        pool.run_device(coos)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n_local):
+        out = pool.run_device(coos)
+        w_last = out[0][0].cpu()                                  # the sample's results are read back
+    b.record()
+    barrier()
+    ms = max_over_ranks(a.elapsed_time(b))
+    pool.close()
+    del pool, paths, coos
+    torch.cuda.empty_cache()
+    return {"workload": f"{args.c3_samples} samples x {len(bins)} per-chromosome maps at {res // 1000} kb "
+                        f"({cells:.3g} cells per sample), sharded by sample over {world} GPU(s)",
+            "samples": args.c3_samples, "ms_total": ms, "samples_per_s": args.c3_samples / (ms * 1e-3),
+            "ms_per_sample_per_gpu": ms / max(1, -(-args.c3_samples // world)),
+            "cells_per_s": args.c3_samples * cells / (ms * 1e-3), "host_threads_per_gpu": workers}
+
+
 def run_row_sharded(args, world, rank, local, pk, steps=2):
     """N > 1: ONE fixed genome-wide map row-sharded over the N ranks (BASELINE.json config C5 at 4 / 8
     GPUs: 25 kb, 123 541 bins; 50 kb, 61 775 bins at 2 GPUs): synthetic count rows -> row-sharded
@@ -547,6 +590,9 @@ def run_ours(args):
     # comparisons proper live in tests/): a bench line of a wrong result is worthless
     checks = parity_checks(hp, rows, cols, vals, w_h, v_h) if not args.no_checks else None
 
+    # ---- config C3: 64 samples x 24 per-chromosome maps at 50 kb, sharded by sample over the ranks -----
+    c3 = run_c3(args, world, rank, max_over_ranks, barrier) if not args.no_c3 else None
+
     # ---- the row-sharded genome-wide chain (the one path with an exchange step), all ranks ------
     row_sharded = None
     if world > 1 and not args.no_row_sharded:
@@ -638,6 +684,7 @@ def run_ours(args):
         "eigvals": [float(x) for x in w_h],
         "checks": checks,
         "same_sample": same_sample,
+        "c3": c3,
     }
     if row_sharded is not None:
         line["row_sharded"] = row_sharded

@@ -161,6 +161,105 @@ symm_panel_kernel(const float* __restrict__ c, int rows, int n, long long ld, co
   }
 }
 
+// The same pass with the matrix stream decoupled from the registers: every lane copies ITS float4 of
+// each of the 4 rows of an iteration straight into a per-warp shared-memory ring (cp.async, 16 bytes,
+// zero fill beyond the edge) `kAsyncStages` iterations ahead, and reads back exactly what it copied
+// -- no cross-lane hand-off, so cp.async.wait_group is the only synchronisation. The register-staged
+// kernel above keeps 8 float4 per lane in flight and is limited to 2 CTAs per SM by its 124
+// registers: ncu (30 894 bins) showed 57 % of DRAM peak at 24 % warp occupancy and 33 % issue
+// utilisation -- latency-bound, not issue-bound. Here 2 CTAs x 8 warps x 4 stages x 2 KB = 128 KB of
+// loads are in flight per SM.
+constexpr int kAsyncStages = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int B>
+__global__ void __launch_bounds__(kSymmWarps * 32, 2)
+symm_panel_async_kernel(const float* __restrict__ c, int rows, int n, long long ld, const float* __restrict__ v,
+                        double* __restrict__ y, int row_major) {
+  extern __shared__ __align__(16) unsigned char s_symm_raw[];
+  float (*s_v)[kSymmCols] = reinterpret_cast<float (*)[kSymmCols]>(s_symm_raw);
+  // ring[warp][stage][row 0..3][lane] float4
+  float4* s_ring = reinterpret_cast<float4*>(s_symm_raw + (size_t)B * kSymmCols * sizeof(float));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * kSymmCols;
+  for (int idx = threadIdx.x; idx < B * kSymmCols; idx += blockDim.x) {
+    const int j = idx / kSymmCols, col = idx % kSymmCols;
+    s_v[j][col] = (k0 + col < n) ? v[(long long)j * n + k0 + col] : 0.f;
+  }
+  __syncthreads();
+  float4* ring = s_ring + (size_t)warp * kAsyncStages * kSymmRowsPerWarp * 32;
+  const int rbase = blockIdx.y * kSymmRowsPerCta + warp * (kSymmRowsPerCta / kSymmWarps);
+  constexpr int kGroups = kSymmRowsPerCta / kSymmWarps / kSymmRowsPerWarp;      // 8 row groups per warp
+  constexpr int kSteps = kSymmCols / 128;                                      // 8 column steps per group
+  constexpr int kIters = kGroups * kSteps;
+  // iteration it -> (row group, column step); copies 4 rows x 16 bytes per lane
+  auto issue = [&](int it) {
+    if (it < kIters) {
+      const int g = it / kSteps, cc = (it % kSteps) * 128 + lane * 4;
+      const int gc = k0 + cc;
+      float4* dst = ring + (size_t)(it % kAsyncStages) * kSymmRowsPerWarp * 32 + lane;
+#pragma unroll
+      for (int r = 0; r < kSymmRowsPerWarp; ++r) {
+        const int gr = rbase + g * kSymmRowsPerWarp + r;
+        const bool ok = gr < rows && gc < n;
+        const int bytes = ok ? min(16, (n - gc) * 4) : 0;        // zero fill beyond the matrix
+        cp_async16(dst + r * 32, ok ? (const void*)(c + (long long)gr * ld + gc) : (const void*)c, bytes);
+      }
+    }
+    cp_async_commit();                                           // (empty groups keep the count uniform)
+  };
+#pragma unroll
+  for (int it = 0; it < kAsyncStages - 1; ++it) issue(it);
+  float2 acc[kSymmRowsPerWarp][B];
+  for (int it = 0; it < kIters; ++it) {
+    const int g = it / kSteps, st = it % kSteps;
+    if (st == 0) {
+#pragma unroll
+      for (int r = 0; r < kSymmRowsPerWarp; ++r)
+#pragma unroll
+        for (int j = 0; j < B; ++j) acc[r][j] = make_float2(0.f, 0.f);
+    }
+    issue(it + kAsyncStages - 1);
+    cp_async_wait<kAsyncStages - 1>();                           // iteration `it` has landed
+    const float4* src = ring + (size_t)(it % kAsyncStages) * kSymmRowsPerWarp * 32 + lane;
+    float4 a[kSymmRowsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kSymmRowsPerWarp; ++r) a[r] = src[r * 32];
+    const int cc = st * 128 + lane * 4;
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const float4 vv = *reinterpret_cast<const float4*>(&s_v[j][cc]);
+#pragma unroll
+      for (int r = 0; r < kSymmRowsPerWarp; ++r) {
+        acc[r][j] = ffma2(make_float2(a[r].x, a[r].y), make_float2(vv.x, vv.y), acc[r][j]);
+        acc[r][j] = ffma2(make_float2(a[r].z, a[r].w), make_float2(vv.z, vv.w), acc[r][j]);
+      }
+    }
+    if (st == kSteps - 1) {
+      const int r0 = rbase + g * kSymmRowsPerWarp;
+      float part[kSymmRowsPerWarp * B];
+#pragma unroll
+      for (int r = 0; r < kSymmRowsPerWarp; ++r)
+#pragma unroll
+        for (int j = 0; j < B; ++j) part[r * B + j] = acc[r][j].x + acc[r][j].y;
+      const float total = lane_transpose_sum<kSymmRowsPerWarp * B>(part, lane);
+      const int idx = lane % (kSymmRowsPerWarp * B), r = idx / B, j = idx % B;
+      if (lane < kSymmRowsPerWarp * B && r0 + r < rows) {
+        double* dstp = row_major ? &y[(long long)(r0 + r) * B + j] : &y[(long long)j * rows + r0 + r];
+        atomicAdd(dstp, (double)total);
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // ---------------------------------------------------------------------------------------------
 // Y = C V from the UPPER TRIANGLE of a symmetric C only: half the DRAM bytes of symm_panel_kernel
 // (the pass is HBM-bound). A CTA owns a block of 128 columns J and a segment of 1024 rows that lies
@@ -959,12 +1058,19 @@ int launch_symm(const float* c, int rows, int n, long long ld, const float* v, d
   HIA_CUDA(cudaMemsetAsync(y, 0, (size_t)rows * B * sizeof(double), s));
   dim3 grid((n + kSymmCols - 1) / kSymmCols, (rows + kSymmRowsPerCta - 1) / kSymmRowsPerCta);
   const int smem = B * kSymmCols * (int)sizeof(float);
+  const int smem_async = smem + kSymmWarps * kAsyncStages * kSymmRowsPerWarp * 32 * (int)sizeof(float4);
   static bool attr_set = false;                            // once per process and instantiation
   if (!attr_set) {
     HIA_CUDA(cudaFuncSetAttribute(symm_panel_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HIA_CUDA(cudaFuncSetAttribute(symm_panel_async_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_async));
     attr_set = true;
   }
-  symm_panel_kernel<B><<<grid, kSymmWarps * 32, smem, s>>>(c, rows, n, ld, v, y, row_major);
+  const char* e = getenv("HIA_EIG_ASYNC");                 // read per call: tools time both in one process
+  const bool use_async = !(e && atoi(e) == 0) && ((reinterpret_cast<uintptr_t>(c) & 15u) == 0) && (ld & 3) == 0;
+  if (use_async)
+    symm_panel_async_kernel<B><<<grid, kSymmWarps * 32, smem_async, s>>>(c, rows, n, ld, v, y, row_major);
+  else
+    symm_panel_kernel<B><<<grid, kSymmWarps * 32, smem, s>>>(c, rows, n, ld, v, y, row_major);
   count_launch();
   return cuda_ok(cudaGetLastError());
 }

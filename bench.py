@@ -551,11 +551,13 @@ def run_ours(args):
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for w_h, v_h in hp.run_host_many([csr_h] * args.steps):
+    e2e_stats = {}
+    for w_h, v_h in hp.run_host_many([csr_h] * args.steps, stats=e2e_stats):
         pass
     t1.record()
     barrier()
     e2e_ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+    e2e_parts = {k: max_over_ranks(float(np.mean(v[1:] if len(v) > 1 else v))) for k, v in e2e_stats.items()}
     # the same without overlap (one blocking call per sample), for the record
     t0s = torch.cuda.Event(enable_timing=True)
     t1s = torch.cuda.Event(enable_timing=True)
@@ -662,6 +664,7 @@ def run_ours(args):
                 "wire_format": f"CSR: int64 row_ptr + {'uint16' if n <= 65536 else 'int32'} cols + fp32 vals "
                                f"({h2d_bytes / nnz:.2f} B/entry)",
                 "ms_single_blocking_call": e2e_serial_ms,
+                "in_loop_ms_slowest_rank": e2e_parts,       # H2D of the next sample / wait for it / compute, per step
                 "h2d_alone_ms_slowest_rank": h2d_alone_ms,
                 "h2d_gbs_per_rank_all_ranks_copying": h2d_bytes / h2d_alone_ms / 1e6,
                 "coo_triple": {"ms_per_step": e2e_coo_ms, "h2d_bytes_per_step": 12 * nnz,

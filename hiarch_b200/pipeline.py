@@ -142,7 +142,7 @@ class HotPath:
         w, vecs = self.run_device(*args)
         return w.cpu().numpy(), vecs.cpu().numpy()
 
-    def run_host_many(self, samples):
+    def run_host_many(self, samples, stats=None):
         """A stream of samples (the reference's ParallelFunc loop over a dataset, one GPU): the COO of
         sample i + 1 is copied H2D on a second stream into the other device buffer while sample i
         is computed, so the PCIe time (2.7 GB at 100 kb genome-wide) hides behind the compute.
@@ -156,14 +156,22 @@ class HotPath:
                             torch.empty_like(self.d_rowptr))]
             self._copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream()
-        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        timing = stats is not None                                    # per-step H2D / compute device times
+        copied = [torch.cuda.Event(enable_timing=timing), torch.cuda.Event(enable_timing=timing)]
+        started = [torch.cuda.Event(enable_timing=timing), torch.cuda.Event(enable_timing=timing)]
         freed = [torch.cuda.Event(), torch.cuda.Event()]
         freed[0].record(main)
         freed[1].record(main)
+        if timing:
+            stats.setdefault("h2d_ms", [])
+            stats.setdefault("compute_ms", [])
+            stats.setdefault("wait_for_copy_ms", [])
 
         def issue_copy(slot, smp):
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(freed[slot])            # the compute that read this buffer is done
+                if timing:
+                    started[slot].record(self._copy_stream)
                 args = self._upload(smp, self._bufs2[slot])
                 copied[slot].record(self._copy_stream)
             return args
@@ -178,10 +186,24 @@ class HotPath:
             slot = i & 1
             nxt = next(it, None)
             args_nxt = issue_copy(slot ^ 1, nxt) if nxt is not None else None
+            if timing:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record(main)
             main.wait_event(copied[slot])
+            if timing:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record(main)
             w, vecs = self.run_device(*args_cur)
             freed[slot].record(main)
-            yield w.cpu().numpy(), vecs.cpu().numpy()
+            if timing:
+                e2 = torch.cuda.Event(enable_timing=True)
+                e2.record(main)
+            res = (w.cpu().numpy(), vecs.cpu().numpy())               # synchronises the step
+            if timing:
+                stats["h2d_ms"].append(started[slot].elapsed_time(copied[slot]))
+                stats["wait_for_copy_ms"].append(e0.elapsed_time(e1))
+                stats["compute_ms"].append(e1.elapsed_time(e2))
+            yield res
             cur, args_cur, i = nxt, args_nxt, i + 1
 
     def cells(self):

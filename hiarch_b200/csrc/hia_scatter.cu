@@ -218,9 +218,13 @@ fill_rows_sorted_kernel(const CT* __restrict__ cols, const float* __restrict__ v
                         long long ld, int mtx_type, float* __restrict__ out) {
   extern __shared__ float s_row[];
   if (flag && *flag) return;
-  const int r = blockIdx.x;                                // rows on x: gridDim.y stops at 65 535
+  // 1-D grid, the segments of a row in ADJACENT CTAs: every segment's CTA walks all entries of the row,
+  // and the first layout (segments on blockIdx.y, i.e. ~n CTAs apart) re-read them from DRAM (ncu:
+  // 3.07 GB read for 1.8 GB of entries, L2 hit rate 7 %); neighbours find them in L2.
+  const int segs = (n + kSegCols - 1) / kSegCols;
+  const int r = blockIdx.x / segs;
   const int c_lo = (mtx_type == HIA_MTX_TRIU) ? r : 0;     // a 'triu' row starts on the diagonal
-  const int seg_lo = c_lo + blockIdx.y * kSegCols;
+  const int seg_lo = c_lo + (blockIdx.x % segs) * kSegCols;
   if (seg_lo >= n) return;
   const int seg_n = min(kSegCols, n - seg_lo);
   const long long e0 = row_ptr[r], e1 = row_ptr[r + 1];    // in flight while the buffer is zeroed
@@ -508,7 +512,7 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
                                     kSegCols * (int)sizeof(float)));
       attr_set = true;
     }
-    dim3 grid_f(n, (n + kSegCols - 1) / kSegCols);
+    dim3 grid_f((unsigned)n * ((n + kSegCols - 1) / kSegCols), 1);
     fill_rows_sorted_kernel<int><<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(cols, vals, row_ptr, flag, n,
                                                                                              ld, mtx_type, out);
     HIA_LAUNCH_CHECK();
@@ -582,7 +586,7 @@ HIA_API int hia_scatter_csr_sym(const int64_t* row_ptr, const void* cols, int co
                                   kSegCols * (int)sizeof(float)));
     attr_set = true;
   }
-  dim3 grid_f(n, (n + kSegCols - 1) / kSegCols);
+  dim3 grid_f((unsigned)n * ((n + kSegCols - 1) / kSegCols), 1);
   const long long* rp = reinterpret_cast<const long long*>(row_ptr);
   if (col_bytes == 4)
     fill_rows_sorted_kernel<int><<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(

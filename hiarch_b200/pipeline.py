@@ -157,8 +157,7 @@ class HotPath:
             self._copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream()
         timing = stats is not None                                    # per-step H2D / compute device times
-        copied = [torch.cuda.Event(enable_timing=timing), torch.cuda.Event(enable_timing=timing)]
-        started = [torch.cuda.Event(enable_timing=timing), torch.cuda.Event(enable_timing=timing)]
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
         freed = [torch.cuda.Event(), torch.cuda.Event()]
         freed[0].record(main)
         freed[1].record(main)
@@ -168,24 +167,48 @@ class HotPath:
             stats.setdefault("wait_for_copy_ms", [])
 
         def issue_copy(slot, smp):
+            tm = None
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(freed[slot])            # the compute that read this buffer is done
-                if timing:
-                    started[slot].record(self._copy_stream)
+                if timing:                                            # fresh events per sample (read one step late)
+                    tm = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    tm[0].record(self._copy_stream)
                 args = self._upload(smp, self._bufs2[slot])
                 copied[slot].record(self._copy_stream)
-            return args
+                if timing:
+                    tm[1].record(self._copy_stream)
+            return args, tm
+
+        # results leave through pinned host buffers, one step late: sample i is handed to the caller after
+        # the work of sample i + 1 has been enqueued, so the host-side read-back / bookkeeping of a
+        # sample never sits between two samples on the GPU timeline
+        if not hasattr(self, "_res_pin"):
+            self._res_pin = [(torch.empty(self.k_eig, dtype=torch.float64).pin_memory(),
+                              torch.empty((self.n, self.k_eig), dtype=torch.float32).pin_memory()) for _ in range(2)]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        pending = None
+
+        def collect(slot, marks):
+            done[slot].synchronize()
+            w_pin, v_pin = self._res_pin[slot]
+            if marks is not None:
+                e0, e1, e2, tm = marks
+                stats["h2d_ms"].append(tm[0].elapsed_time(tm[1]))
+                stats["wait_for_copy_ms"].append(e0.elapsed_time(e1))
+                stats["compute_ms"].append(e1.elapsed_time(e2))
+            return w_pin.numpy().copy(), v_pin.numpy().copy()
 
         it = iter(samples)
         cur = next(it, None)
         if cur is None:
             return
-        args_cur = issue_copy(0, cur)
+        args_cur, tm_cur = issue_copy(0, cur)
         i = 0
         while cur is not None:
             slot = i & 1
             nxt = next(it, None)
-            args_nxt = issue_copy(slot ^ 1, nxt) if nxt is not None else None
+            args_nxt, tm_nxt = issue_copy(slot ^ 1, nxt) if nxt is not None else (None, None)
+            marks = None
             if timing:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record(main)
@@ -198,13 +221,17 @@ class HotPath:
             if timing:
                 e2 = torch.cuda.Event(enable_timing=True)
                 e2.record(main)
-            res = (w.cpu().numpy(), vecs.cpu().numpy())               # synchronises the step
-            if timing:
-                stats["h2d_ms"].append(started[slot].elapsed_time(copied[slot]))
-                stats["wait_for_copy_ms"].append(e0.elapsed_time(e1))
-                stats["compute_ms"].append(e1.elapsed_time(e2))
-            yield res
-            cur, args_cur, i = nxt, args_nxt, i + 1
+                marks = (e0, e1, e2, tm_cur)
+            w_pin, v_pin = self._res_pin[slot]
+            w_pin.copy_(w, non_blocking=True)
+            v_pin.copy_(vecs, non_blocking=True)
+            done[slot].record(main)
+            if pending is not None:
+                yield collect(*pending)                                # sample i - 1, while sample i runs
+            pending = (slot, marks)
+            cur, args_cur, tm_cur, i = nxt, args_nxt, tm_nxt, i + 1
+        if pending is not None:
+            yield collect(*pending)
 
     def cells(self):
         return self.n * self.n

@@ -69,7 +69,7 @@ PROTOTYPES = {
                                     c_i64, c_vp, c_i64, c_vp]),
     "hia_topk_eig_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),
     "hia_eig_symm_upper_workspace_bytes": (c_i64, [c_i32, c_i32]),
-    "hia_topk_eig": (c_int, [c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_i32,
+    "hia_topk_eig": (c_int, [c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_i32,
                              ctypes.c_double, ctypes.c_double, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,
                              c_i64, c_vp]),
     "hia_sim_kpad": (c_i32, [c_i32, c_int]),

@@ -295,15 +295,16 @@ class EigBuffers:
     def __init__(self, n, k, block, steps, device, symmetric=True):
         lib = _lib.load()
         self.n, self.k, self.block, self.steps = n, k, block, steps
+        self.kk = block                                  # Ritz pairs kept: the whole block (restart quality)
         self.ws = torch.empty(lib.hia_topk_eig_workspace_bytes(n, block, steps), dtype=torch.uint8, device=device)
         self.upper = None
         # measured at 30 894 bins: the upper-triangle pass halves the DRAM bytes but not the FMAs or the
         # reductions, and the pass is issue-bound: 1.14 ms against 0.82 ms of the full pass -> opt-in
         if symmetric and os.environ.get("HIA_EIG_UPPER", "0") == "1":
             self.upper = torch.empty(lib.hia_eig_symm_upper_workspace_bytes(n, block), dtype=torch.uint8, device=device)
-        self.eigvals = torch.empty(k, dtype=torch.float64, device=device)
-        self.eigvecs = torch.empty((k, n), dtype=torch.float32, device=device)
-        self.stats = torch.empty(2 * k, dtype=torch.float64, device=device)       # residuals | gaps: one D2H read
+        self.eigvals = torch.empty(self.kk, dtype=torch.float64, device=device)
+        self.eigvecs = torch.empty((self.kk, n), dtype=torch.float32, device=device)
+        self.stats = torch.empty(2 * self.kk, dtype=torch.float64, device=device)  # residuals | gaps: one D2H read
         self.used = ctypes.c_int32(0)
 
 
@@ -313,11 +314,11 @@ def topk_eig_cycle(c, buf, seed=0, init=None, n_init=0, early_tol=0.0, early_ang
     cycle runs all `buf.steps` steps and contains no host synchronisation at all (capturable in a
     CUDA graph); otherwise the in-cycle convergence checks read one flag each."""
     lib = _lib.load()
-    n, k = buf.n, buf.k
+    n, k, kk = buf.n, buf.k, buf.kk
     upper = buf.upper if (buf.upper is not None and c.data_ptr() % 16 == 0 and c.stride(0) % 4 == 0) else None
-    st = lib.hia_topk_eig(_ptr(c), n, c.stride(0), k, buf.block, buf.steps, seed, _ptr(init), n_init,
+    st = lib.hia_topk_eig(_ptr(c), n, c.stride(0), k, kk, buf.block, buf.steps, seed, _ptr(init), n_init,
                           early_tol, early_angle_tol, _ptr(buf.eigvals), _ptr(buf.eigvecs), buf.stats.data_ptr(),
-                          buf.stats.data_ptr() + 8 * k, ctypes.addressof(buf.used), _ptr(buf.ws), buf.ws.numel(),
+                          buf.stats.data_ptr() + 8 * kk, ctypes.addressof(buf.used), _ptr(buf.ws), buf.ws.numel(),
                           _ptr(upper), 0 if upper is None else upper.numel(), _stream())
     _lib.check(st, "hia_topk_eig")
 
@@ -349,14 +350,14 @@ def topk_eig(c, k=3, block=8, steps=None, tol=1e-6, angle_tol=1e-3, max_restarts
         # the in-cycle estimates use half the tolerances: the final, true residual must pass too
         topk_eig_cycle(c, buf, seed + it, init, n_init, 0.5 * tol, 0.5 * angle_tol)
         sg = buf.stats.cpu().numpy()
-        lam = buf.eigvals.cpu().numpy()
-        r, gaps = sg[:k], sg[k:]
+        lam = buf.eigvals.cpu().numpy()[:k]
+        r, gaps = sg[:k], sg[buf.kk:buf.kk + k]
         info.append((float(r.max()), float(abs(lam[0])), int(buf.used.value)))
         if eig_converged(r, lam, gaps, tol, angle_tol):
             break
-        init, n_init = buf.eigvecs.clone(), k
+        init, n_init = buf.eigvecs.clone(), buf.kk          # restart from the whole block of Ritz vectors
     # fresh tensors: the buffers are reused by the next call
-    out = (buf.eigvals.clone(), buf.eigvecs.t().clone() if workspace is not None else buf.eigvecs.t())
+    out = (buf.eigvals[:k].clone(), buf.eigvecs[:k].t().clone() if workspace is not None else buf.eigvecs[:k].t())
     return out + (info,) if return_info else out
 
 

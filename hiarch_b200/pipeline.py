@@ -340,8 +340,10 @@ class SampleGraph:
         hp.similarity()
         e = self.eig[i]
         ops.topk_eig_cycle(hp.sim, e)                       # all steps, no early check: no host read
-        self.summary[i, :2 * e.k].copy_(e.stats, non_blocking=True)
-        self.summary[i, 2 * e.k:3 * e.k].copy_(e.eigvals, non_blocking=True)
+        k = e.k                                              # residuals | gaps | eigenvalues of the k wanted pairs
+        self.summary[i, :k].copy_(e.stats[:k], non_blocking=True)
+        self.summary[i, k:2 * k].copy_(e.stats[e.kk:e.kk + k], non_blocking=True)
+        self.summary[i, 2 * k:3 * k].copy_(e.eigvals[:k], non_blocking=True)
 
     def load(self, coos):
         """Copy the sample's COO arrays (device or pinned host tensors) into the fixed buffers."""
@@ -395,7 +397,7 @@ class SampleGraph:
             k = self.eig[i].k
             sg, lam = summary[i, :2 * k], summary[i, 2 * k:3 * k]
             if ops.eig_converged(sg[:k], lam, sg[k:], tol, angle_tol):
-                out.append((lam.copy(), self.eig[i].eigvecs.t().cpu().numpy()))
+                out.append((lam.copy(), self.eig[i].eigvecs[:k].t().cpu().numpy()))
             else:                                                     # finish with the restarting solver
                 self.fallbacks += 1
                 w, vecs = ops.topk_eig(self.paths[i].sim, k=k, block=self.paths[i].eig_block, tol=tol,

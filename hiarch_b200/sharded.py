@@ -308,10 +308,11 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, angle_tol=1e-3, m
     ws = torch.empty(lib.hia_topk_eig_workspace_bytes(n, block, steps), dtype=torch.uint8, device=dev)
     y_rows = torch.zeros((per, block), dtype=torch.float64, device=dev)
     y_full = torch.zeros((per * world, block), dtype=torch.float64, device=dev)
-    eigvals = torch.empty(k, dtype=torch.float64, device=dev)
-    eigvecs = torch.empty((k, n), dtype=torch.float32, device=dev)
-    resid = torch.empty(k, dtype=torch.float64, device=dev)
-    gaps = torch.empty(k, dtype=torch.float64, device=dev)
+    kk = block                   # Ritz pairs kept: the whole block (restart quality on clustered spectra)
+    eigvals = torch.empty(kk, dtype=torch.float64, device=dev)
+    eigvecs = torch.empty((kk, n), dtype=torch.float32, device=dev)
+    resid = torch.empty(kk, dtype=torch.float64, device=dev)
+    gaps = torch.empty(kk, dtype=torch.float64, device=dev)
     conv = ctypes.c_int32(0)
     s = ops._stream
 
@@ -354,7 +355,7 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, angle_tol=1e-3, m
                 if agree(conv.value):
                     used, reuse = done, 1
                     break
-        _lib.check(lib.hia_eig_ritz(n, block, steps, used, reuse, k, eigvals.data_ptr(), eigvecs.data_ptr(),
+        _lib.check(lib.hia_eig_ritz(n, block, steps, used, reuse, kk, eigvals.data_ptr(), eigvecs.data_ptr(),
                                     gaps.data_ptr(), ws.data_ptr(), s()), "hia_eig_ritz")
         if world > 1:
             # one rank's Ritz pairs for everybody: with clustered Ritz values the replicated Jacobi
@@ -363,17 +364,17 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, angle_tol=1e-3, m
             src = dist.get_global_rank(group, 0) if group is not None else 0
             for t in (eigvals, eigvecs, gaps):
                 dist.broadcast(t, src=src, group=group)
-            _lib.check(lib.hia_eig_set_ritz(n, block, steps, k, eigvecs.data_ptr(), ws.data_ptr(), s()),
+            _lib.check(lib.hia_eig_set_ritz(n, block, steps, kk, eigvecs.data_ptr(), ws.data_ptr(), s()),
                        "hia_eig_set_ritz")
         matvec()
-        _lib.check(lib.hia_eig_resid(n, block, steps, k, y_full.data_ptr(), eigvals.data_ptr(),
+        _lib.check(lib.hia_eig_resid(n, block, steps, kk, y_full.data_ptr(), eigvals.data_ptr(),
                                      resid.data_ptr(), ws.data_ptr(), s()), "hia_eig_resid")
-        r, lam = resid.cpu().numpy(), eigvals.cpu().numpy()
+        r, lam = resid.cpu().numpy()[:k], eigvals.cpu().numpy()[:k]
         info.append((float(r.max()), float(abs(lam[0])), used))
-        if agree(ops.eig_converged(r, lam, gaps.cpu().numpy(), tol, angle_tol)):
+        if agree(ops.eig_converged(r, lam, gaps.cpu().numpy()[:k], tol, angle_tol)):
             break
-        init, n_init = eigvecs.clone(), k
-    return eigvals, eigvecs.t(), info
+        init, n_init = eigvecs.clone(), kk                  # restart from the whole block of Ritz vectors
+    return eigvals[:k], eigvecs[:k].t(), info
 
 
 def obs_d_exp_rows(map_rows, layout, bin_size, row0, k=.2, counts_must_decrese=True, only_intra=False,

@@ -398,7 +398,9 @@ int64_t hia_topk_eig_workspace_bytes(int32_t n, int32_t block, int32_t steps);
  * both y[r] += c v[col] and y[col] += c v[r] -- i.e. half the DRAM bytes of the HBM-bound pass;
  * the lower triangle is never touched. NULL = the full-matrix pass. */
 int64_t hia_eig_symm_upper_workspace_bytes(int32_t n, int32_t block);
-int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t block, int32_t steps,
+/* k_keep (k <= k_keep <= block, 0 = k): Ritz pairs returned (eigvals / eigvecs / resid / gaps hold k_keep
+ * entries); convergence is judged on the first k, the rest make better restart blocks. */
+int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32_t k_keep, int32_t block, int32_t steps,
                  uint64_t seed, const float* init_vecs, int32_t n_init, double early_rel_tol,
                  double early_angle_tol, double* eigvals, float* eigvecs, double* resid, double* gaps,
                  int32_t* steps_used_host, void* workspace, int64_t workspace_bytes, void* upper_ws,

@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-checks", action="store_true", help="skip the in-run fp64 parity checks")
     ap.add_argument("--no-row-sharded", action="store_true", help="N > 1: skip the row-sharded genome-wide chain")
     ap.add_argument("--no-c3", action="store_true", help="skip the per-chromosome batch (config C3)")
+    ap.add_argument("--only-row-sharded", action="store_true",
+                    help="N > 1: run only the row-sharded chain and print its record (development sweeps)")
     ap.add_argument("--c3-samples", type=int, default=64)
     ap.add_argument("--row-sharded-res", type=int, default=0,
                     help="bin size of the row-sharded chain (default: 50 kb at 2 GPUs, 25 kb at 4 / 8)")
@@ -465,6 +467,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     pk, pk_src = peaks()
+    if args.only_row_sharded and world > 1:
+        rec = run_row_sharded(args, world, rank, local, pk)
+        if rank == 0:
+            print(json.dumps({"row_sharded": rec}), flush=True)
+        dist.destroy_process_group()
+        return
 
     bins = synth.hg38_bins(args.res)[: args.chroms]
     lens = [n for _, n in bins]

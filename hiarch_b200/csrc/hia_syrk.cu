@@ -1047,12 +1047,13 @@ static int launch_gemm(const GemmJob& j, cudaStream_t stream) {
   const int bk = bk_of(j.prec);
   // measured on B200 (3xTF32): k_chunk 256 -> 1.6e-6 max abs err (1024: 5e-6, unchunked: 1e-4). The
   // error grows with the number of MMA steps in one TMEM chain; fp16 steps cover twice the K.
-  // (The TMEM accumulate truncates: the error of a chunk grows with its number of MMA steps and is
-  //  systematic, so it adds up over the chunks. fp16 default 512: 3e-7 measured on the 100 kb count map,
-  //  K = 30 894. On the sparser 50 / 25 kb count maps 512 gave 3.8e-6 / 8.0e-6 on sampled entries
-  //  (bench.py row_sharded.fp64_spot_check) -- too close to the 1e-5 budget -- so long rows take 256.)
+  // (Default 512 for fp16: 3e-7 measured on the 100 kb count map at K = 30 894, 3.8e-6 / 8.0e-6 on sampled
+  //  entries of the 50 / 25 kb count maps (bench.py row_sharded.fp64_spot_check). 256 was NOT better on
+  //  those maps -- 5.5e-6 at 50 kb -- so the error there is not the in-chunk truncation alone.
+  //  HIA_K_CHUNK overrides the default for sweeps.)
+  static const int env_chunk = getenv("HIA_K_CHUNK") ? atoi(getenv("HIA_K_CHUNK")) : 0;
   const int k_chunk = j.k_chunk > 0 ? j.k_chunk
-                                    : (j.prec == HIA_PREC_3XF16 ? (j.kpad > 40000 ? 256 : 512) : 256);
+                                    : (env_chunk > 0 ? env_chunk : (j.prec == HIA_PREC_3XF16 ? 512 : 256));
   static const int sync_every = getenv("HIA_SYRK_SYNC") ? atoi(getenv("HIA_SYRK_SYNC")) : kSyncEvery;
   HIA_CUDA(cudaMemsetAsync(j.sync_ctr, 0, (size_t)j.n_sync * 4, stream));
   SyrkArgs a;

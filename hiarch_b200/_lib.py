@@ -68,6 +68,7 @@ PROTOTYPES = {
     "hia_used_filter_f64": (c_int, [c_vp, c_i32, c_i32, c_i64, c_i32, c_i32, c_int, ctypes.c_double, c_vp,
                                     c_i64, c_vp, c_i64, c_vp]),
     "hia_topk_eig_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),
+    "hia_projected_eig": (c_int, [c_vp, c_i32, c_i32, c_i32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hia_eig_symm_upper_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "hia_topk_eig": (c_int, [c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_i32,
                              ctypes.c_double, ctypes.c_double, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,

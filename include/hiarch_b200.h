@@ -397,6 +397,14 @@ int64_t hia_topk_eig_workspace_bytes(int32_t n, int32_t block, int32_t steps);
  * every pass reads the UPPER TRIANGLE of the (symmetric) matrix only -- each loaded cell feeds
  * both y[r] += c v[col] and y[col] += c v[r] -- i.e. half the DRAM bytes of the HBM-bound pass;
  * the lower triangle is never touched. NULL = the full-matrix pass. */
+/* The projected (Rayleigh-Ritz) eigenproblem of the Lanczos solver on its own (tests / tools): h is D x D
+ * row-major, the lower triangle of its leading dim x dim block is the symmetric matrix (dim <= 272).
+ * z: dim x dim doubles column-major, lam[dim], order[dim] (device): pair j (j-th largest, j < kk <= 16) is
+ * lam[order[j]] with eigenvector column order[j]. solver 0: Householder tridiagonalisation + Sturm
+ * multisection + inverse iteration for the kk largest pairs only (dim <= 160; lam[order[kk]] is the next
+ * eigenvalue, the rest -1e300); solver 1: one-sided Jacobi (all pairs). scratch: dim x dim doubles. */
+int hia_projected_eig(const double* h, int32_t D, int32_t dim, int32_t kk, int solver, double* z, double* lam,
+                      int32_t* order, double* scratch, void* stream);
 int64_t hia_eig_symm_upper_workspace_bytes(int32_t n, int32_t block);
 /* k_keep (k <= k_keep <= block, 0 = k): Ritz pairs returned (eigvals / eigvecs / resid / gaps hold k_keep
  * entries); convergence is judged on the first k, the rest make better restart blocks. */

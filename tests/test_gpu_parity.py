@@ -731,3 +731,61 @@ def test_template_scores_for_caller_supplied_templates():
     xt = xs.reshape(-1, 16, 16).transpose(0, 2, 1).reshape(-1, 256)
     both = confor._template_scores_device(xs, tm, True)
     assert np.abs(both - np.maximum(xs @ t.T, xt @ t.T)).max() <= 1e-12
+
+
+def _projected_cases():
+    rng = np.random.default_rng(21)
+    cases = []
+    for n in (1, 2, 3, 8, 24, 64, 96, 104, 160):
+        a = rng.standard_normal((n, n))
+        cases.append((f"wishart{n}", a @ a.T / max(n, 1)))
+    q, _ = np.linalg.qr(rng.standard_normal((72, 72)))
+    cases.append(("clustered", (q * np.r_[1410.5, 1404.5, 1392.2, 900, 800, np.linspace(500, 0.01, 67)]) @ q.T))
+    q, _ = np.linalg.qr(rng.standard_normal((104, 104)))
+    cases.append(("near_degenerate_indefinite", (q * np.r_[100.0, 100.0 + 1e-9, 99.0, np.linspace(50, -3, 101)]) @ q.T))
+    t = np.zeros((64, 64))
+    for i in range(64):
+        for j in range(max(0, i - 8), min(64, i + 9)):
+            t[i, j] = rng.standard_normal() / (1 + abs(i - j))
+    cases.append(("banded_graded", (t + t.T) / 2 + np.diag(np.r_[202.0, 113.0, 62.0, 41.0, np.geomspace(3.5, 0.02, 60)])))
+    cases.append(("diagonal", np.diag(np.linspace(5, 1, 16))))
+    return cases
+
+
+@pytest.mark.parametrize("solver", [0, 1])
+def test_projected_eigensolvers_against_eigh(solver):
+    """The Rayleigh-Ritz step of the Lanczos solver on its own: the partial solver (Householder +
+    Sturm multisection + inverse iteration, top kk pairs) and the one-sided Jacobi against
+    numpy.linalg.eigh -- Wishart, clustered (the 25 kb spectrum), near-degenerate + indefinite, banded
+    and graded like a Krylov matrix, diagonal, and the 1 x 1 ... 3 x 3 corner cases."""
+    from hiarch_b200 import _lib, ops
+    lib = _lib.load()
+    for name, t in _projected_cases():
+        t = (t + t.T) / 2
+        n = t.shape[0]
+        kk = min(8, n)
+        D = n + 8
+        h = np.zeros((D, D))
+        h[:n, :n] = np.tril(t)
+        dh = torch.from_numpy(h).cuda()
+        z = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+        lam = torch.zeros(n, dtype=torch.float64, device="cuda")
+        order = torch.zeros(n, dtype=torch.int32, device="cuda")
+        scratch = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+        _lib.check(lib.hia_projected_eig(dh.data_ptr(), D, n, kk, solver, z.data_ptr(), lam.data_ptr(),
+                                         order.data_ptr(), scratch.data_ptr(), ops._stream()), "hia_projected_eig")
+        torch.cuda.synchronize()
+        w, u = np.linalg.eigh(t)
+        w, u = w[::-1], u[:, ::-1]
+        o = order.cpu().numpy()
+        lam_h = lam.cpu().numpy()[o]
+        zc = z.cpu().numpy()                                   # [column][row] because column-major
+        scale = max(abs(w[0]), abs(w[-1]), 1e-300)
+        got = lam_h[:kk]
+        assert np.abs(got - w[:kk]).max() <= 1e-12 * scale, (name, solver)
+        if solver == 0 and n > kk:
+            assert abs(lam_h[kk] - w[kk]) <= 1e-12 * scale, (name, "next eigenvalue")
+        vecs = np.stack([zc[o[j]] for j in range(kk)], axis=1)       # n x kk
+        res = np.linalg.norm(t @ vecs - vecs * got[None, :], axis=0)
+        assert res.max() <= 1e-10 * scale, (name, solver, res.max())
+        assert np.abs(vecs.T @ vecs - np.eye(kk)).max() <= 1e-9, (name, solver)

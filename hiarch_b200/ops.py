@@ -281,8 +281,8 @@ def _eig_shape(n, k, block, steps):
     if n < 2 * block:
         block = 4
     if steps is None:
-        steps = 12
-    steps = max(1, min(steps, n // block - 1, 272 // block - 1))
+        steps = 19              # Krylov dimension <= 160 (the partial projected eigensolver's limit); cycles
+    steps = max(1, min(steps, n // block - 1, 272 // block - 1))     # end early at the first passed check
     if block * (steps + 1) > n or k > block:
         raise _lib.HiaError(f"matrix of {n} bins is too small for k={k}")
     return block, steps

@@ -21,7 +21,7 @@ CsrSample = collections.namedtuple("CsrSample", "row_ptr cols vals")
 
 class HotPath:
     def __init__(self, seps, bin_size, k_eig=3, flavour=ops.SIM_PEARSON, device="cuda",
-                 max_nnz=None, eig_block=8, eig_steps=12, precision=None, upper_only=None):
+                 max_nnz=None, eig_block=8, eig_steps=19, precision=None, upper_only=None):
         self.lib = _lib.load()
         self.layout = ops.GenomeLayout(seps, device)
         self.n = self.layout.n

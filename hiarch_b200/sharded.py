@@ -291,7 +291,7 @@ class RingSimilarity:
         return self.stats
 
 
-def topk_eig_rows(c_rows, n, k=3, block=8, steps=12, tol=1e-6, angle_tol=1e-3, max_restarts=8, seed=0,
+def topk_eig_rows(c_rows, n, k=3, block=8, steps=19, tol=1e-6, angle_tol=1e-3, max_restarts=8, seed=0,
                   group=None):
     """Top-k eigenpairs of the symmetric n x n matrix whose rows [row0, row0 + rows) this rank
     holds in `c_rows` (row layout of ShardedSimilarity). Returns (eigvals [k] fp64 device,

@@ -342,13 +342,13 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=19, tol=1e-6, angle_tol=1e-3, m
         _lib.check(lib.hia_eig_begin(n, block, steps, seed + it, ops._ptr(init), n_init, ws.data_ptr(),
                                      ws.numel(), s()), "hia_eig_begin")
         used, reuse = steps, 0
-        first_check = lib.hia_eig_first_check(steps)
+        first_check, every = lib.hia_eig_first_check(steps), lib.hia_eig_check_every()
         for j in range(steps):
             matvec()
             _lib.check(lib.hia_eig_absorb(n, block, steps, j, y_full.data_ptr(), ws.data_ptr(), s()),
                        "hia_eig_absorb")
             done = j + 1
-            if done >= first_check and (done - first_check) % 2 == 0 and done < steps:
+            if done >= first_check and (done - first_check) % every == 0 and done < steps:
                 # replicated on every rank; the branch is taken by agreement (see agree())
                 _lib.check(lib.hia_eig_check(n, block, steps, done, k, 0.5 * tol, 0.5 * angle_tol,
                                              ctypes.addressof(conv), None, ws.data_ptr(), s()), "hia_eig_check")

@@ -92,8 +92,8 @@ PROTOTYPES = {
     "hia_eig_begin": (c_int, [c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_i32, c_vp, c_i64, c_vp]),
     "hia_eig_symm_rows": (c_int, [c_vp, c_i32, c_i32, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "hia_eig_absorb": (c_int, [c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
-    "hia_eig_first_check": (c_i32, [c_i32]),
-    "hia_eig_check_every": (c_i32, []),
+    "hia_eig_first_check": (c_i32, [c_i32, c_i32]),
+    "hia_eig_check_every": (c_i32, [c_i32]),
     "hia_eig_check": (c_int, [c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_double, ctypes.c_double, c_vp, c_vp,
                               c_vp, c_vp]),
     "hia_eig_ritz": (c_int, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -1602,22 +1602,24 @@ HIA_API int hia_eig_resid(int32_t n, int32_t block, int32_t steps, int32_t k, co
   return HIA_OK;
 }
 
-// First convergence check after min(7, 2/3 of the steps) steps (a check solves the projected
-// eigenproblem: ~0.4 ms with the partial solver incl. the flag read-back, 1.4+ ms with the Jacobi fallback).
-HIA_API int32_t hia_eig_first_check(int32_t steps) {
+// Cadence of the pass-free convergence checks. A check solves the projected eigenproblem and reads one
+// flag back (~0.4 ms with the partial solver); a Lanczos step costs a pass over the matrix (0.7 ms at
+// 30 894 bins, ~20 us at 2 000). Large matrices: first check after min(7, 2/3 of the steps) steps, then
+// after EVERY step (measured at 30 894 bins: first check at 5 / 6 / 7 -> 9.5 / 9.1 / 8.5 ms per solve, against
+// 10.0 ms with "step 8, then every second step"). Small matrices (chromosome-sized chains, where the
+// checks are the cost): step min(8, 2/3 of the steps), then every second step.
+HIA_API int32_t hia_eig_first_check(int32_t n, int32_t steps) {
   const char* e = getenv("HIA_EIG_FIRST_CHECK");        // tuning knob (tools)
   if (e && atoi(e) > 0) return atoi(e);
-  const int f = steps * 2 / 3 < 7 ? steps * 2 / 3 : 7;    // step 7 at the latest (long cycles check early too)
+  const int cap = n >= 16384 ? 7 : 8;
+  const int f = steps * 2 / 3 < cap ? steps * 2 / 3 : cap;
   return f > 4 ? f : 4;
 }
-// Checks after EVERY step from the first one on: a check costs ~0.4 ms with the partial projected
-// solver (measured at 30 894 bins: first check 5 / 6 / 7 -> 9.5 / 9.1 / 8.5 ms per solve, against 10.0 ms
-// with "step 8, then every second step"), a saved Lanczos step 0.7 ms.
-HIA_API int32_t hia_eig_check_every(void) {
+HIA_API int32_t hia_eig_check_every(int32_t n) {
   const char* e = getenv("HIA_EIG_CHECK_EVERY");
-  return (e && atoi(e) > 0) ? atoi(e) : 1;
+  if (e && atoi(e) > 0) return atoi(e);
+  return n >= 16384 ? 1 : 2;
 }
-static int eig_check_every() { return hia_eig_check_every(); }
 
 // ---- single-device driver: all phases on one stream. early_rel_tol / early_angle_tol > 0 enable the
 // pass-free convergence check (hia_eig_check, one tiny D2H flag) after every second step from
@@ -1693,8 +1695,8 @@ HIA_API int hia_topk_eig(const float* c, int32_t n, int64_t ld, int32_t k, int32
     st = hia_eig_absorb(n, block, steps, j, ystage, workspace, stream);
     if (st != HIA_OK) return st;
     const int done = j + 1;
-    if (early && done >= hia_eig_first_check(steps) && ((done - hia_eig_first_check(steps)) % eig_check_every()) == 0 &&
-        done < steps) {
+    if (early && done >= hia_eig_first_check(n, steps) &&
+        ((done - hia_eig_first_check(n, steps)) % hia_eig_check_every(n)) == 0 && done < steps) {
       int conv = 0;
       st = hia_eig_check(n, block, steps, done, k, early_rel_tol, early_angle_tol, &conv, nullptr, workspace, stream);
       if (st != HIA_OK) return st;

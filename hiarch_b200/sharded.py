@@ -342,7 +342,7 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=19, tol=1e-6, angle_tol=1e-3, m
         _lib.check(lib.hia_eig_begin(n, block, steps, seed + it, ops._ptr(init), n_init, ws.data_ptr(),
                                      ws.numel(), s()), "hia_eig_begin")
         used, reuse = steps, 0
-        first_check, every = lib.hia_eig_first_check(steps), lib.hia_eig_check_every()
+        first_check, every = lib.hia_eig_first_check(n, steps), lib.hia_eig_check_every(n)
         for j in range(steps):
             matvec()
             _lib.check(lib.hia_eig_absorb(n, block, steps, j, y_full.data_ptr(), ws.data_ptr(), s()),

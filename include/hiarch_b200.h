@@ -386,8 +386,8 @@ int hia_peer_copy(void* dst, const void* src, int64_t bytes, void* stream);
 /* +lambda/-lambda of equal magnitude may mix.                                            */
 /* ------------------------------------------------------------------------------------ */
 int64_t hia_topk_eig_workspace_bytes(int32_t n, int32_t block, int32_t steps);
-/* early_rel_tol / early_angle_tol > 0: after every hia_eig_check_every()-th Lanczos step (from step
- * hia_eig_first_check(steps) = max(4, min(7, 2 steps / 3)) on) the
+/* early_rel_tol / early_angle_tol > 0: after every hia_eig_check_every(n)-th Lanczos step (from step
+ * hia_eig_first_check(n, steps) on; n >= 16 384: step 7, then every step; smaller: step 8, every second) the
  * Ritz residuals are ESTIMATED from the Lanczos relation (no pass over the matrix; one tiny D2H
  * flag) and the cycle ends as soon as every wanted pair has est <= early_rel_tol |lambda_1| or
  * est <= early_angle_tol * gap (gap = distance to the nearest other Ritz value: the sin-theta
@@ -432,8 +432,8 @@ int hia_eig_symm_rows(const float* c_rows, int32_t rows, int32_t n, int64_t ld, 
                       int32_t steps, void* workspace, double* y_rows, void* stream);
 int hia_eig_absorb(int32_t n, int32_t block, int32_t steps, int32_t j, const double* y_full,
                    void* workspace, void* stream);
-int32_t hia_eig_first_check(int32_t steps);
-int32_t hia_eig_check_every(void);   /* steps between two checks after the first one (1) */
+int32_t hia_eig_first_check(int32_t n, int32_t steps);   /* first pass-free convergence check after this many steps */
+int32_t hia_eig_check_every(int32_t n);                  /* steps between two checks after the first one */
 int hia_eig_check(int32_t n, int32_t block, int32_t steps, int32_t steps_done, int32_t k, double rel_tol,
                   double angle_tol, int32_t* converged_host, double* est_gap_host, void* workspace,
                   void* stream);

@@ -23,12 +23,18 @@ PROTOTYPES = {
     "hia_scatter_coo_sym": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_int, c_int,
                                     c_vp, c_i32, c_vp, c_vp]),
     "hia_scatter_csr_sym": (c_int, [c_vp, c_vp, c_int, c_vp, c_i32, c_vp, c_i64, c_int, c_vp]),
+    "hia_scatter_coo_sym_stats": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_int, c_vp, c_i32, c_vp, c_vp,
+                                          c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hia_scatter_csr_sym_stats": (c_int, [c_vp, c_vp, c_int, c_vp, c_i32, c_vp, c_i64, c_int, c_vp, c_i32, c_vp, c_vp,
+                                          c_vp, c_vp, c_vp, c_vp]),
     "hia_scatter_coo_remap": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_i64, c_int, c_vp]),
     "hia_coo_block_nnz": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_int, c_vp, c_i32, c_vp, c_vp]),
     "hia_coo_bin_sums": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_int, c_vp, c_vp]),
     "hia_bin_stats": (c_int, [c_vp, c_i32, c_i64, c_vp, c_vp, c_vp]),
     "hia_oe_expected_pass": (c_int, [c_vp, c_i32, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp,
                                      c_vp, c_vp, c_vp]),
+    "hia_oe_expected_pass_ex": (c_int, [c_vp, c_i32, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp,
+                                        c_vp, c_vp, c_vp, c_vp]),
     "hia_oe_finalize": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_int,
                                 c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hia_oe_apply": (c_int, [c_vp, c_vp, c_i32, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_int,

@@ -102,8 +102,9 @@ inter_block_kernel(const float* __restrict__ map, int n, long long ld,
                    const int* __restrict__ chr_start, int n_chr,
                    const short* __restrict__ bin_chr, double* __restrict__ inter_sum,
                    unsigned long long* __restrict__ inter_nnz, float* __restrict__ inter_minpos,
-                   int row0, int row_end) {
+                   int row0, int row_end, const int* __restrict__ skip_if) {
   extern __shared__ unsigned char smem_raw[];
+  if (skip_if && *skip_if) return;                        // the scatter produced these statistics already
   double* s_sum = reinterpret_cast<double*>(smem_raw);
   unsigned long long* s_nnz = reinterpret_cast<unsigned long long*>(s_sum + n_chr);
   float* s_min = reinterpret_cast<float*>(s_nnz + n_chr);
@@ -191,10 +192,12 @@ inter_block_kernel(const float* __restrict__ map, int n, long long ld,
 }
 
 __global__ void init_expected_kernel(double* diag_sum, float* diag_minpos, int n, double* inter_sum,
-                                     unsigned long long* inter_nnz, float* inter_minpos, int cc) {
+                                     unsigned long long* inter_nnz, float* inter_minpos, int cc,
+                                     const int* __restrict__ inter_valid) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { diag_sum[i] = 0.0; diag_minpos[i] = INFINITY; }
-  if (i < cc) { inter_sum[i] = 0.0; inter_nnz[i] = 0ull; inter_minpos[i] = INFINITY; }
+  // inter_valid (optional): the scatter already produced the inter-chromosome statistics
+  if (i < cc && !(inter_valid && *inter_valid)) { inter_sum[i] = 0.0; inter_nnz[i] = 0ull; inter_minpos[i] = INFINITY; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -576,7 +579,7 @@ HIA_API int hia_log_map(const float* x, float* out, int32_t rows, int32_t cols, 
   return HIA_OK;
 }
 
-static int expected_pass_impl(const float* map, int32_t n, int64_t ld, const int32_t* chr_start,
+static int expected_pass_impl(const int32_t* inter_valid, const float* map, int32_t n, int64_t ld, const int32_t* chr_start,
                               const int32_t* chr_start_host, int32_t n_chr, double* diag_sum,
                               float* diag_minpos, double* inter_sum, unsigned long long* inter_nnz,
                               float* inter_minpos, const int16_t* bin_chr, int row0, int rows,
@@ -592,7 +595,7 @@ static int expected_pass_impl(const float* map, int32_t n, int64_t ld, const int
   const int cc = n_chr * n_chr;
   const int cnt = max(n, cc);
   init_expected_kernel<<<(cnt + 255) / 256, 256, 0, stream>>>(diag_sum, diag_minpos, n, inter_sum,
-                                                             inter_nnz, inter_minpos, cc);
+                                                             inter_nnz, inter_minpos, cc, inter_valid);
   HIA_LAUNCH_CHECK();
   if (rows == 0) return HIA_OK;
   int max_len = 0;
@@ -610,7 +613,7 @@ static int expected_pass_impl(const float* map, int32_t n, int64_t ld, const int
     const size_t sh = (size_t)n_chr * (8 + 8 + 4);
     inter_block_kernel<<<grid_i, kInterThreads, sh, stream>>>(map, n, ld, chr_start, n_chr, bin_chr,
                                                               inter_sum, inter_nnz, inter_minpos,
-                                                              row0, row0 + rows);
+                                                              row0, row0 + rows, inter_valid);
     HIA_LAUNCH_CHECK();
   }
   return HIA_OK;
@@ -621,7 +624,19 @@ HIA_API int hia_oe_expected_pass(const float* map, int32_t n, int64_t ld, const 
                                  float* diag_minpos, double* inter_sum,
                                  unsigned long long* inter_nnz, float* inter_minpos,
                                  const int16_t* bin_chr, void* stream) {
-  return expected_pass_impl(map, n, ld, chr_start, chr_start_host, n_chr, diag_sum, diag_minpos,
+  return expected_pass_impl(nullptr, map, n, ld, chr_start, chr_start_host, n_chr, diag_sum, diag_minpos,
+                            inter_sum, inter_nnz, inter_minpos, bin_chr, 0, n, stream);
+}
+
+// The same when the scatter may already have produced the inter-chromosome statistics
+// (hia_scatter_*_sym_stats): *inter_valid (device int) != 0 -> they are kept and the pass over the
+// inter-chromosome part of the map is skipped (the diagonal statistics are always computed).
+HIA_API int hia_oe_expected_pass_ex(const float* map, int32_t n, int64_t ld, const int32_t* chr_start,
+                                    const int32_t* chr_start_host, int32_t n_chr, double* diag_sum,
+                                    float* diag_minpos, double* inter_sum, unsigned long long* inter_nnz,
+                                    float* inter_minpos, const int16_t* bin_chr, const int32_t* inter_valid,
+                                    void* stream) {
+  return expected_pass_impl(inter_valid, map, n, ld, chr_start, chr_start_host, n_chr, diag_sum, diag_minpos,
                             inter_sum, inter_nnz, inter_minpos, bin_chr, 0, n, stream);
 }
 
@@ -635,7 +650,7 @@ HIA_API int hia_oe_expected_pass_rows(const float* map_rows, int32_t n, int64_t 
                                       float* diag_minpos, double* inter_sum,
                                       unsigned long long* inter_nnz, float* inter_minpos,
                                       const int16_t* bin_chr, void* stream) {
-  return expected_pass_impl(map_rows, n, ld, chr_start, chr_start_host, n_chr, diag_sum, diag_minpos,
+  return expected_pass_impl(nullptr, map_rows, n, ld, chr_start, chr_start_host, n_chr, diag_sum, diag_minpos,
                             inter_sum, inter_nnz, inter_minpos, bin_chr, row0, rows, stream);
 }
 

@@ -211,13 +211,37 @@ __device__ __forceinline__ int4 load_cols4(const unsigned short* p) {
 
 // CT = int (COO / CSR with 32-bit columns) or unsigned short (CSR with 16-bit columns, n <= 65 536:
 // 6 instead of 8 bytes per entry over PCIe and out of HBM)
-template <typename CT>
+// Optional by-product of the fill (STATS): the inter-chromosome statistics of the O/E expected pass
+// (sum, non-zero count and smallest positive value of every upper block a < b; what
+// inter_block_kernel of hia_oe.cu computes from the dense map) taken from the finished row segment
+// while it is still in shared memory -- saves the 1.8 GB re-read of the upper triangle (0.5 ms at
+// 30 894 bins). Every thread keeps (chromosome, sum, count, min) for the run of columns it walks and
+// flushes into per-CTA tables when the chromosome changes; one global atomic per (row, chromosome).
+constexpr int kStatsMaxChr = 64;
+struct InterStats {
+  const int* chr_start;
+  const short* bin_chr;
+  int n_chr;
+  double* sum;
+  unsigned long long* nnz;
+  float* minpos;
+  int* valid;               // set to 1 by the kernel (the sorted-row path ran: the statistics are complete)
+};
+
+template <typename CT, bool STATS>
 __global__ void __launch_bounds__(kSegThreads)
 fill_rows_sorted_kernel(const CT* __restrict__ cols, const float* __restrict__ vals,
                         const long long* __restrict__ row_ptr, const int* __restrict__ flag, int n,
-                        long long ld, int mtx_type, float* __restrict__ out) {
+                        long long ld, int mtx_type, float* __restrict__ out, const InterStats st) {
   extern __shared__ float s_row[];
+  __shared__ double s_sum[STATS ? kStatsMaxChr : 1];
+  __shared__ unsigned long long s_nnz[STATS ? kStatsMaxChr : 1];
+  __shared__ float s_min[STATS ? kStatsMaxChr : 1];
   if (flag && *flag) return;
+  if (STATS) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *st.valid = 1;
+    for (int i = threadIdx.x; i < st.n_chr; i += blockDim.x) { s_sum[i] = 0.0; s_nnz[i] = 0ull; s_min[i] = INFINITY; }
+  }
   // 1-D grid, the segments of a row in ADJACENT CTAs: every segment's CTA walks all entries of the row,
   // and the first layout (segments on blockIdx.y, i.e. ~n CTAs apart) re-read them from DRAM (ncu:
   // 3.07 GB read for 1.8 GB of entries, L2 hit rate 7 %); neighbours find them in L2.
@@ -255,15 +279,57 @@ fill_rows_sorted_kernel(const CT* __restrict__ cols, const float* __restrict__ v
   for (long long e = a1 + threadIdx.x; e < e1; e += blockDim.x) add((int)cols[e], vals[e]);
   __syncthreads();
   float* dst = out + (long long)r * ld + seg_lo;
+  // per-thread running statistics of the inter-chromosome cells it writes (STATS)
+  int cur_b = -1, col_lo = 0x7fffffff, a_chr = 0;
+  float fsum = 0.f, fmin = INFINITY;
+  unsigned int fcnt = 0;
+  if (STATS) { a_chr = st.bin_chr[r]; col_lo = st.chr_start[a_chr + 1]; }
+  auto flush = [&]() {
+    if (cur_b >= 0 && (fcnt | (fsum != 0.f))) {
+      atomicAdd(&s_sum[cur_b], (double)fsum);
+      atomicAdd(&s_nnz[cur_b], (unsigned long long)fcnt);
+      if (fmin != INFINITY) atomic_min_pos_float(&s_min[cur_b], fmin);
+    }
+    fsum = 0.f; fcnt = 0; fmin = INFINITY;
+  };
+  auto stat = [&](int c, float v) {                       // c: global column of a written cell
+    if (c < col_lo) return;
+    const int b = st.bin_chr[c];
+    if (b != cur_b) { flush(); cur_b = b; }
+    fsum += v;
+    fcnt += (v != 0.f);
+    if (v > 0.f) fmin = fminf(fmin, v);
+  };
   // 128-bit stores from the first 16-byte aligned cell of the segment on
   const int head = min(seg_n, (int)((4 - ((((long long)r * ld + seg_lo)) & 3)) & 3));
-  for (int i = threadIdx.x; i < head; i += blockDim.x) dst[i] = s_row[i];
+  for (int i = threadIdx.x; i < head; i += blockDim.x) {
+    dst[i] = s_row[i];
+    if (STATS) stat(seg_lo + i, s_row[i]);
+  }
   const int nv = (seg_n - head) >> 2;
   for (int i = threadIdx.x; i < nv; i += blockDim.x) {
     const int o = head + 4 * i;
-    *reinterpret_cast<float4*>(dst + o) = make_float4(s_row[o], s_row[o + 1], s_row[o + 2], s_row[o + 3]);
+    const float4 q = make_float4(s_row[o], s_row[o + 1], s_row[o + 2], s_row[o + 3]);
+    *reinterpret_cast<float4*>(dst + o) = q;
+    if (STATS && seg_lo + o + 3 >= col_lo) {
+      stat(seg_lo + o, q.x); stat(seg_lo + o + 1, q.y); stat(seg_lo + o + 2, q.z); stat(seg_lo + o + 3, q.w);
+    }
   }
-  for (int i = head + 4 * nv + threadIdx.x; i < seg_n; i += blockDim.x) dst[i] = s_row[i];
+  for (int i = head + 4 * nv + threadIdx.x; i < seg_n; i += blockDim.x) {
+    dst[i] = s_row[i];
+    if (STATS) stat(seg_lo + i, s_row[i]);
+  }
+  if (STATS) {
+    flush();
+    __syncthreads();
+    for (int i = threadIdx.x; i < st.n_chr; i += blockDim.x) {
+      if (s_nnz[i] | (s_sum[i] != 0.0)) {
+        atomicAdd(&st.sum[a_chr * st.n_chr + i], s_sum[i]);
+        atomicAdd(&st.nnz[a_chr * st.n_chr + i], s_nnz[i]);
+      }
+      if (s_min[i] != INFINITY) atomic_min_pos_float(&st.minpos[a_chr * st.n_chr + i], s_min[i]);
+    }
+  }
 }
 
 // fallback zero fill (any entry order): does nothing when the sorted-row path ran
@@ -476,12 +542,32 @@ HIA_API int64_t hia_scatter_workspace_bytes(int32_t n, int32_t n_chr) {
   return scatter_keys_bytes(n_chr) + 256 + ((int64_t)n + 1) * 8;
 }
 
-HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const float* vals,
-                                int64_t nnz, int32_t n, float* out, int64_t ld, int mtx_type,
-                                int fill_mode, const int32_t* chr_start, int32_t n_chr,
-                                void* workspace, void* stream_) {
+namespace hia {
+namespace {
+__global__ void init_inter_stats_kernel(double* sum, unsigned long long* nnz, float* minpos, int cc, int* valid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cc) { sum[i] = 0.0; nnz[i] = 0ull; minpos[i] = INFINITY; }
+  if (i == 0) *valid = 0;
+}
+int init_inter_stats(const InterStats& st, cudaStream_t stream) {
+  const int cc = st.n_chr * st.n_chr;
+  init_inter_stats_kernel<<<(cc + 255) / 256, 256, 0, stream>>>(st.sum, st.nnz, st.minpos, cc, st.valid);
+  HIA_LAUNCH_CHECK();
+  return HIA_OK;
+}
+}  // namespace
+}  // namespace hia
+
+static int scatter_coo_impl(const int32_t* rows, const int32_t* cols, const float* vals,
+                            int64_t nnz, int32_t n, float* out, int64_t ld, int mtx_type,
+                            int fill_mode, const int32_t* chr_start, int32_t n_chr,
+                            void* workspace, void* stream_, const hia::InterStats* stats) {
   using namespace hia;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (stats) {
+    const int st = init_inter_stats(*stats, stream);
+    if (st != HIA_OK) return st;
+  }
   if (!out || n <= 0 || ld < n || nnz < 0) return HIA_ERR_BAD_ARG;
   if (nnz > 0 && (!rows || !cols || !vals)) return HIA_ERR_BAD_ARG;
   if (mtx_type != HIA_MTX_TRIU && mtx_type != HIA_MTX_ALL && mtx_type != HIA_MTX_TRIU_UPPER) return HIA_ERR_BAD_ARG;
@@ -508,13 +594,19 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
     HIA_LAUNCH_CHECK();
     static bool attr_set = false;                          // once per process (idempotent)
     if (!attr_set) {
-      HIA_CUDA(cudaFuncSetAttribute(fill_rows_sorted_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kSegCols * (int)sizeof(float)));
+      HIA_CUDA((cudaFuncSetAttribute(fill_rows_sorted_kernel<int, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kSegCols * (int)sizeof(float))));
+      HIA_CUDA((cudaFuncSetAttribute(fill_rows_sorted_kernel<int, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kSegCols * (int)sizeof(float))));
       attr_set = true;
     }
     dim3 grid_f((unsigned)n * ((n + kSegCols - 1) / kSegCols), 1);
-    fill_rows_sorted_kernel<int><<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(cols, vals, row_ptr, flag, n,
-                                                                                             ld, mtx_type, out);
+    if (stats)
+      fill_rows_sorted_kernel<int, true><<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(
+          cols, vals, row_ptr, flag, n, ld, mtx_type, out, *stats);
+    else
+      fill_rows_sorted_kernel<int, false><<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(
+          cols, vals, row_ptr, flag, n, ld, mtx_type, out, InterStats{});
     HIA_LAUNCH_CHECK();
     // (a 4096-row grid of CTAs that only read the flag and exit cost 69 us per call: launch list r1)
     dim3 grid_z((n + threads * 4 - 1) / (threads * 4), min(n, 64));
@@ -561,16 +653,46 @@ HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const 
   return HIA_OK;
 }
 
+HIA_API int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const float* vals,
+                                int64_t nnz, int32_t n, float* out, int64_t ld, int mtx_type,
+                                int fill_mode, const int32_t* chr_start, int32_t n_chr,
+                                void* workspace, void* stream) {
+  return scatter_coo_impl(rows, cols, vals, nnz, n, out, ld, mtx_type, fill_mode, chr_start, n_chr, workspace,
+                          stream, nullptr);
+}
+
+// The same (zero fill) with the inter-chromosome statistics of the O/E expected pass as a by-product
+// of the row-sorted fill: inter_sum / inter_nnz / inter_minpos [n_chr^2] as hia_oe_expected_pass
+// defines them, *stats_valid (device int) = 1 when they are complete (row-sorted input; the any-order
+// fallback leaves 0 and hia_oe_expected_pass_ex then computes them from the dense map). n_chr <= 64.
+HIA_API int hia_scatter_coo_sym_stats(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz,
+                                      int32_t n, float* out, int64_t ld, int mtx_type, const int32_t* chr_start,
+                                      int32_t n_chr, const int16_t* bin_chr, double* inter_sum,
+                                      unsigned long long* inter_nnz, float* inter_minpos, int32_t* stats_valid,
+                                      void* workspace, void* stream) {
+  using namespace hia;
+  if (!chr_start || !bin_chr || !inter_sum || !inter_nnz || !inter_minpos || !stats_valid || n_chr < 1 ||
+      n_chr > kStatsMaxChr || !workspace)
+    return HIA_ERR_BAD_ARG;
+  InterStats st = {chr_start, bin_chr, n_chr, inter_sum, inter_nnz, inter_minpos, stats_valid};
+  return scatter_coo_impl(rows, cols, vals, nnz, n, out, ld, mtx_type, HIA_FILL_ZERO, nullptr, 0, workspace, stream, &st);
+}
+
 // CSR input (what SpsHiCMtx.matrix is: scipy CSR, publish/new_hic_class.py:2158-2161): row_ptr[n + 1]
 // (int64, device), column indices as int32 (col_bytes = 4) or uint16 (col_bytes = 2, n <= 65 536), values
 // fp32. Zero fill only. Rows are sorted by construction, so there is no row-pointer pass and no
 // fallback: 8 (or 6) bytes per entry instead of the 12 of the COO triple -- the bytes that cross PCIe
 // in the end-to-end path. Entries with a column outside [0, n) (or below the diagonal for the
 // 'triu' types) are ignored; duplicates are summed.
-HIA_API int hia_scatter_csr_sym(const int64_t* row_ptr, const void* cols, int col_bytes, const float* vals,
-                                int32_t n, float* out, int64_t ld, int mtx_type, void* stream_) {
+static int scatter_csr_impl(const int64_t* row_ptr, const void* cols, int col_bytes, const float* vals,
+                            int32_t n, float* out, int64_t ld, int mtx_type, void* stream_,
+                            const hia::InterStats* stats) {
   using namespace hia;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (stats) {
+    const int st = init_inter_stats(*stats, stream);
+    if (st != HIA_OK) return st;
+  }
   if (!row_ptr || !cols || !vals || !out || n <= 0 || ld < n) return HIA_ERR_BAD_ARG;
   if (col_bytes != 4 && col_bytes != 2) return HIA_ERR_BAD_ARG;
   if (col_bytes == 2 && n > 65536) return HIA_ERR_UNSUPPORTED;
@@ -580,20 +702,31 @@ HIA_API int hia_scatter_csr_sym(const int64_t* row_ptr, const void* cols, int co
   const int mt = (mtx_type == HIA_MTX_ALL) ? HIA_MTX_ALL : HIA_MTX_TRIU;
   static bool attr_set = false;
   if (!attr_set) {
-    HIA_CUDA(cudaFuncSetAttribute(fill_rows_sorted_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSegCols * (int)sizeof(float)));
-    HIA_CUDA(cudaFuncSetAttribute(fill_rows_sorted_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSegCols * (int)sizeof(float)));
+    const int bytes = kSegCols * (int)sizeof(float);
+    HIA_CUDA((cudaFuncSetAttribute(fill_rows_sorted_kernel<int, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
+    HIA_CUDA((cudaFuncSetAttribute(fill_rows_sorted_kernel<int, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
+    HIA_CUDA((cudaFuncSetAttribute(fill_rows_sorted_kernel<unsigned short, false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
+    HIA_CUDA((cudaFuncSetAttribute(fill_rows_sorted_kernel<unsigned short, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
     attr_set = true;
   }
   dim3 grid_f((unsigned)n * ((n + kSegCols - 1) / kSegCols), 1);
   const long long* rp = reinterpret_cast<const long long*>(row_ptr);
-  if (col_bytes == 4)
-    fill_rows_sorted_kernel<int><<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(
-        static_cast<const int*>(cols), vals, rp, nullptr, n, ld, mt, out);
+  const size_t sh = kSegCols * sizeof(float);
+  const InterStats none = {};
+  if (col_bytes == 4 && stats)
+    fill_rows_sorted_kernel<int, true><<<grid_f, kSegThreads, sh, stream>>>(static_cast<const int*>(cols), vals, rp,
+                                                                            nullptr, n, ld, mt, out, *stats);
+  else if (col_bytes == 4)
+    fill_rows_sorted_kernel<int, false><<<grid_f, kSegThreads, sh, stream>>>(static_cast<const int*>(cols), vals, rp,
+                                                                             nullptr, n, ld, mt, out, none);
+  else if (stats)
+    fill_rows_sorted_kernel<unsigned short, true><<<grid_f, kSegThreads, sh, stream>>>(
+        static_cast<const unsigned short*>(cols), vals, rp, nullptr, n, ld, mt, out, *stats);
   else
-    fill_rows_sorted_kernel<unsigned short><<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(
-        static_cast<const unsigned short*>(cols), vals, rp, nullptr, n, ld, mt, out);
+    fill_rows_sorted_kernel<unsigned short, false><<<grid_f, kSegThreads, sh, stream>>>(
+        static_cast<const unsigned short*>(cols), vals, rp, nullptr, n, ld, mt, out, none);
   HIA_LAUNCH_CHECK();
   if (mirror) {
     dim3 gm((n + 31) / 32, (n + 31) / 32);
@@ -601,4 +734,24 @@ HIA_API int hia_scatter_csr_sym(const int64_t* row_ptr, const void* cols, int co
     HIA_LAUNCH_CHECK();
   }
   return HIA_OK;
+}
+
+HIA_API int hia_scatter_csr_sym(const int64_t* row_ptr, const void* cols, int col_bytes, const float* vals,
+                                int32_t n, float* out, int64_t ld, int mtx_type, void* stream) {
+  return scatter_csr_impl(row_ptr, cols, col_bytes, vals, n, out, ld, mtx_type, stream, nullptr);
+}
+
+// CSR input + the inter-chromosome statistics of the O/E expected pass (see hia_scatter_coo_sym_stats);
+// CSR rows are sorted by construction, so *stats_valid is always 1 afterwards.
+HIA_API int hia_scatter_csr_sym_stats(const int64_t* row_ptr, const void* cols, int col_bytes, const float* vals,
+                                      int32_t n, float* out, int64_t ld, int mtx_type, const int32_t* chr_start,
+                                      int32_t n_chr, const int16_t* bin_chr, double* inter_sum,
+                                      unsigned long long* inter_nnz, float* inter_minpos, int32_t* stats_valid,
+                                      void* stream) {
+  using namespace hia;
+  if (!chr_start || !bin_chr || !inter_sum || !inter_nnz || !inter_minpos || !stats_valid || n_chr < 1 ||
+      n_chr > kStatsMaxChr)
+    return HIA_ERR_BAD_ARG;
+  InterStats st = {chr_start, bin_chr, n_chr, inter_sum, inter_nnz, inter_minpos, stats_valid};
+  return scatter_csr_impl(row_ptr, cols, col_bytes, vals, n, out, ld, mtx_type, stream, &st);
 }

@@ -95,10 +95,12 @@ _SCATTER_WS_MAX = 64
 
 
 def scatter_coo_sym(rows, cols, vals, n, mtx_type=MTX_TRIU, fill_mode=FILL_ZERO, layout=None,
-                    out=None):
+                    out=None, oe_state=None):
     """COO (int32 rows, int32 cols, fp32 vals; CUDA) -> dense symmetric fp32 [n, n] view.
     Replaces read_sps_file/to_all/to_dense (publish/new_hic_class.py:2576-2602, :2229-2246,
-    :2209-2224)."""
+    :2209-2224). oe_state (an OEState of `layout`, zero fill only): the inter-chromosome statistics
+    of the O/E expected pass are taken from the row segments while they are in shared memory
+    (`oe_state.inter_valid` then tells obs_d_exp to skip its pass over the inter part of the map)."""
     lib = _lib.load()
     _need_cuda(rows, cols, vals)
     assert rows.dtype == torch.int32 and cols.dtype == torch.int32 and vals.dtype == torch.float32
@@ -121,6 +123,13 @@ def scatter_coo_sym(rows, cols, vals, n, mtx_type=MTX_TRIU, fill_mode=FILL_ZERO,
                 _scatter_ws.popitem(last=False)
         else:
             _scatter_ws.move_to_end(key)
+    if oe_state is not None and fill_mode == FILL_ZERO and layout is not None and layout.n_chr <= 64:
+        st = lib.hia_scatter_coo_sym_stats(_ptr(rows), _ptr(cols), _ptr(vals), rows.numel(), n, _ptr(out),
+                                           out.stride(0), mtx_type, _ptr(layout.chr_start), layout.n_chr,
+                                           _ptr(layout.bin_chr), _ptr(oe_state.inter_sum), _ptr(oe_state.inter_nnz),
+                                           _ptr(oe_state.inter_minpos), _ptr(oe_state.inter_valid), _ptr(ws), _stream())
+        _lib.check(st, "hia_scatter_coo_sym_stats")
+        return out
     st = lib.hia_scatter_coo_sym(_ptr(rows), _ptr(cols), _ptr(vals), rows.numel(), n, _ptr(out),
                                  out.stride(0), mtx_type, fill_mode, _ptr(chr_start), n_chr,
                                  _ptr(ws), _stream())
@@ -128,7 +137,7 @@ def scatter_coo_sym(rows, cols, vals, n, mtx_type=MTX_TRIU, fill_mode=FILL_ZERO,
     return out
 
 
-def scatter_csr_sym(row_ptr, cols, vals, n, mtx_type=MTX_TRIU, out=None):
+def scatter_csr_sym(row_ptr, cols, vals, n, mtx_type=MTX_TRIU, out=None, layout=None, oe_state=None):
     """CSR (int64 row_ptr [n + 1], int32 or uint16 cols, fp32 vals; CUDA) -> dense fp32 [n, n] view, zero
     fill: the scatter for matrices that arrive as CSR (scipy's layout of SpsHiCMtx.matrix), 8 or 6
     bytes per entry instead of the 12 of a COO triple."""
@@ -138,6 +147,13 @@ def scatter_csr_sym(row_ptr, cols, vals, n, mtx_type=MTX_TRIU, out=None):
     assert cols.dtype in (torch.int32, torch.uint16, torch.int16)
     if out is None:
         out = alloc_map(n, vals.device)
+    if oe_state is not None and layout is not None and layout.n_chr <= 64:      # + the inter statistics of the O/E pass
+        st = lib.hia_scatter_csr_sym_stats(_ptr(row_ptr), _ptr(cols), cols.element_size(), _ptr(vals), n, _ptr(out),
+                                           out.stride(0), mtx_type, _ptr(layout.chr_start), layout.n_chr,
+                                           _ptr(layout.bin_chr), _ptr(oe_state.inter_sum), _ptr(oe_state.inter_nnz),
+                                           _ptr(oe_state.inter_minpos), _ptr(oe_state.inter_valid), _stream())
+        _lib.check(st, "hia_scatter_csr_sym_stats")
+        return out
     st = lib.hia_scatter_csr_sym(_ptr(row_ptr), _ptr(cols), cols.element_size(), _ptr(vals), n, _ptr(out),
                                  out.stride(0), mtx_type, _stream())
     _lib.check(st, "hia_scatter_csr_sym")
@@ -179,17 +195,21 @@ class OEState:
         self.inv_expected = torch.empty(n, dtype=torch.float32, device=dev)
         self.inter_inv = torch.empty(cc, dtype=torch.float32, device=dev)
         self.min_pos_oe = torch.empty(1, dtype=torch.float32, device=dev)
+        self.inter_valid = torch.zeros(1, dtype=torch.int32, device=dev)   # set by scatter_*_sym(oe_state=...)
 
 
 def obs_d_exp(dense, layout, bin_size, k=.2, counts_must_decrese=True, only_intra=False,
-              log=False, out=None, state=None, from_upper=False, fp64_out=False):
+              log=False, out=None, state=None, from_upper=False, fp64_out=False, inter_from_scatter=False):
     """O/E (mode='sgd_mean') of a symmetric dense map, optionally fused with ArrayHiCMtx.log.
     Replaces HiCMtx.obs_d_exp (publish/new_hic_class.py:1121-1290) + log (:2076-2094).
     `out` may alias `dense` (in place). Returns (out, OEState). from_upper=True: only the upper
     triangle of `dense` is read (it may come from scatter_coo_sym(mtx_type=MTX_TRIU_UPPER)); the
     result is the same full symmetric map. fp64_out=True (raw O/E only, log=False): the result is
     a float64 [n, n] tensor divided in double like the reference -- 1e-5 absolute for entries of any
-    size (the fp32 map carries its 6e-8 relative rounding, i.e. 1e-5 only up to values of ~50)."""
+    size (the fp32 map carries its 6e-8 relative rounding, i.e. 1e-5 only up to values of ~50).
+    inter_from_scatter=True: `state` was handed to the scatter that produced `dense`
+    (scatter_*_sym(oe_state=state)); where that scatter already took the inter-chromosome statistics
+    (`state.inter_valid` on the device) the pass over the inter part of the map is skipped."""
     lib = _lib.load()
     _need_cuda(dense)
     n = layout.n
@@ -200,12 +220,13 @@ def obs_d_exp(dense, layout, bin_size, k=.2, counts_must_decrese=True, only_intr
         out = alloc_map(n, dense.device)
     assert fp64_out or out.stride(0) == dense.stride(0), "in/out maps must share the leading dimension"
     stream = _stream()
-    st = lib.hia_oe_expected_pass(_ptr(dense), n, dense.stride(0), _ptr(layout.chr_start),
-                                  layout.chr_start_host.ctypes.data, layout.n_chr,
-                                  _ptr(state.diag_sum), _ptr(state.diag_minpos),
-                                  _ptr(state.inter_sum), _ptr(state.inter_nnz),
-                                  _ptr(state.inter_minpos), _ptr(layout.bin_chr), stream)
-    _lib.check(st, "hia_oe_expected_pass")
+    st = lib.hia_oe_expected_pass_ex(_ptr(dense), n, dense.stride(0), _ptr(layout.chr_start),
+                                     layout.chr_start_host.ctypes.data, layout.n_chr,
+                                     _ptr(state.diag_sum), _ptr(state.diag_minpos),
+                                     _ptr(state.inter_sum), _ptr(state.inter_nnz),
+                                     _ptr(state.inter_minpos), _ptr(layout.bin_chr),
+                                     _ptr(state.inter_valid) if inter_from_scatter else 0, stream)
+    _lib.check(st, "hia_oe_expected_pass_ex")
     st = lib.hia_oe_finalize(_ptr(state.diag_sum), _ptr(state.diag_minpos), _ptr(state.inter_sum),
                              _ptr(state.inter_nnz), _ptr(state.inter_minpos),
                              _ptr(layout.chr_start), layout.n_chr, n, _ptr(pool_gid),

@@ -46,6 +46,8 @@ class HotPath:
         # `raw` keeps an UNWRITTEN lower triangle (`raw_symmetric()` completes it on demand)
         self.upper_only = (os.environ.get("HIA_UPPER_ONLY", "1") == "1") if upper_only is None else bool(upper_only)
         self._eig_ws = {}                            # eigen-solver workspaces, allocated on first use
+        # the scatter takes the inter-chromosome statistics of the O/E pass from its row segments (HIA_FUSE_STATS=0: off)
+        self.fuse_inter_stats = os.environ.get("HIA_FUSE_STATS", "1") == "1" and 1 < self.layout.n_chr <= 64
         self.max_nnz = max_nnz
         if max_nnz:
             self.d_rows = torch.empty(max_nnz, dtype=torch.int32, device=device)
@@ -63,15 +65,17 @@ class HotPath:
 
     def scatter_csr(self, row_ptr, cols, vals):
         mt = ops.MTX_TRIU_UPPER if self.upper_only else ops.MTX_TRIU
-        return ops.scatter_csr_sym(row_ptr, cols, vals, self.n, mtx_type=mt, out=self.raw)
+        return ops.scatter_csr_sym(row_ptr, cols, vals, self.n, mtx_type=mt, out=self.raw, layout=self.layout,
+                                   oe_state=self.oe_state if self.fuse_inter_stats else None)
 
     def scatter(self, rows, cols, vals):
         mt = ops.MTX_TRIU_UPPER if self.upper_only else ops.MTX_TRIU
-        return ops.scatter_coo_sym(rows, cols, vals, self.n, mtx_type=mt, out=self.raw)
+        return ops.scatter_coo_sym(rows, cols, vals, self.n, mtx_type=mt, out=self.raw, layout=self.layout,
+                                   oe_state=self.oe_state if self.fuse_inter_stats else None)
 
     def normalise(self):
         ops.obs_d_exp(self.raw, self.layout, self.bin_size, log=True, out=self.oe, state=self.oe_state,
-                      from_upper=self.upper_only)
+                      from_upper=self.upper_only, inter_from_scatter=self.fuse_inter_stats)
         return self.oe
 
     def similarity_prep(self):

@@ -77,6 +77,20 @@ int hia_scatter_coo_sym(const int32_t* rows, const int32_t* cols, const float* v
  * Row r of an 'ALL' map starts at column 0; a 'triu' row at the diagonal (earlier columns ignored). */
 int hia_scatter_csr_sym(const int64_t* row_ptr, const void* cols, int col_bytes, const float* vals,
                         int32_t n, float* out, int64_t ld, int mtx_type, void* stream);
+/* Zero-fill scatter + the inter-chromosome statistics of the O/E expected pass as a by-product of the
+ * row-sorted fill (taken from the finished row segment while it is in shared memory: saves the re-read
+ * of the upper triangle by hia_oe_expected_pass). inter_sum / inter_nnz / inter_minpos [n_chr^2] as the
+ * expected pass defines them; *stats_valid (device int) = 1 when complete (row-sorted COO, any CSR),
+ * 0 after the any-order fallback -- hand it to hia_oe_expected_pass_ex. n_chr <= 64. */
+int hia_scatter_coo_sym_stats(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz, int32_t n,
+                              float* out, int64_t ld, int mtx_type, const int32_t* chr_start, int32_t n_chr,
+                              const int16_t* bin_chr, double* inter_sum, unsigned long long* inter_nnz,
+                              float* inter_minpos, int32_t* stats_valid, void* workspace, void* stream);
+int hia_scatter_csr_sym_stats(const int64_t* row_ptr, const void* cols, int col_bytes, const float* vals, int32_t n,
+                              float* out, int64_t ld, int mtx_type, const int32_t* chr_start, int32_t n_chr,
+                              const int16_t* bin_chr, double* inter_sum, unsigned long long* inter_nnz,
+                              float* inter_minpos, int32_t* stats_valid, void* stream);
+
 
 
 /* ------------------------------------------------------------------------------------ */
@@ -156,6 +170,12 @@ int hia_oe_apply(const float* map, float* out, int32_t n, int64_t ld, const int3
  * diag_minpos / inter_minpos over the ranks -- two small all-reduces), runs hia_oe_finalize on the
  * reduced arrays (replicated) and applies to its own rows. The upper-triangle rule (column >=
  * row) makes the partial sums disjoint. */
+/* hia_oe_expected_pass when the scatter may already hold the inter-chromosome statistics
+ * (hia_scatter_*_sym_stats): *inter_valid (device int) != 0 -> kept, the inter part of the map is not read. */
+int hia_oe_expected_pass_ex(const float* map, int32_t n, int64_t ld, const int32_t* chr_start,
+                            const int32_t* chr_start_host, int32_t n_chr, double* diag_sum, float* diag_minpos,
+                            double* inter_sum, unsigned long long* inter_nnz, float* inter_minpos,
+                            const int16_t* bin_chr, const int32_t* inter_valid, void* stream);
 int hia_oe_expected_pass_rows(const float* map_rows, int32_t n, int64_t ld, int32_t row0, int32_t rows,
                               const int32_t* chr_start, const int32_t* chr_start_host, int32_t n_chr,
                               double* diag_sum, float* diag_minpos, double* inter_sum,

@@ -789,3 +789,49 @@ def test_projected_eigensolvers_against_eigh(solver):
         res = np.linalg.norm(t @ vecs - vecs * got[None, :], axis=0)
         assert res.max() <= 1e-10 * scale, (name, solver, res.max())
         assert np.abs(vecs.T @ vecs - np.eye(kk)).max() <= 1e-9, (name, solver)
+
+
+@pytest.mark.parametrize("mode", ["coo_sorted", "coo_shuffled", "csr32", "csr16"])
+def test_scatter_takes_the_inter_statistics_of_the_oe_pass(mode):
+    """hia_scatter_*_sym_stats: the inter-chromosome statistics the fill kernel takes from its row
+    segments equal those of the expected pass over the dense map (counts and minima exactly, sums to
+    fp64 rounding), for row-sorted COO and CSR; an unsorted COO falls back (valid = 0) and the expected
+    pass computes them. The O/E map that follows is the same to 1e-6."""
+    from hiarch_b200 import ops
+    lens, bs = [260, 33, 140, 75], 100000
+    rows, cols, vals, seps = synth.synth_coo(lens, seed=17, lam_inter=1.5)
+    n = sum(lens)
+    # duplicates (summed before the statistics are taken) and an explicit zero entry
+    rows = np.r_[rows, rows[:40], rows[100]]
+    cols = np.r_[cols, cols[:40], cols[100]]
+    vals = np.r_[vals, 0.5 * vals[:40], -vals[100]]
+    order = np.lexsort((cols, rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    layout = ops.GenomeLayout(seps)
+    ref_state = ops.OEState(layout)
+    dense = ops.scatter_coo_sym(_dev(rows, torch.int32), _dev(cols, torch.int32), _dev(vals, torch.float32), n,
+                                mtx_type=ops.MTX_TRIU_UPPER)
+    ref_oe, _ = ops.obs_d_exp(dense, layout, bs, log=True, state=ref_state, from_upper=True)
+    st = ops.OEState(layout)
+    out = ops.alloc_map(n)
+    if mode.startswith("coo"):
+        r, c, v = rows, cols, vals
+        if mode == "coo_shuffled":
+            p = np.random.default_rng(0).permutation(rows.size)
+            r, c, v = rows[p], cols[p], vals[p]
+        ops.scatter_coo_sym(_dev(r, torch.int32), _dev(c, torch.int32), _dev(v, torch.float32), n,
+                            mtx_type=ops.MTX_TRIU_UPPER, layout=layout, out=out, oe_state=st)
+    else:
+        rp, cc, vv = ops.coo_to_csr_host(rows, cols, vals, n, cols16=(mode == "csr16"))
+        ops.scatter_csr_sym(rp.cuda(), cc.cuda(), vv.cuda(), n, mtx_type=ops.MTX_TRIU_UPPER, out=out, layout=layout,
+                            oe_state=st)
+    torch.cuda.synchronize()
+    assert int(st.inter_valid.item()) == (0 if mode == "coo_shuffled" else 1)
+    iu = np.triu_indices(n)
+    assert np.array_equal(out.cpu().numpy()[iu], dense.cpu().numpy()[iu]) or mode == "coo_shuffled"
+    if mode != "coo_shuffled":
+        assert torch.equal(st.inter_nnz, ref_state.inter_nnz)
+        assert torch.equal(st.inter_minpos, ref_state.inter_minpos)
+        assert np.allclose(st.inter_sum.cpu().numpy(), ref_state.inter_sum.cpu().numpy(), rtol=1e-6, atol=0)
+    got_oe, _ = ops.obs_d_exp(out, layout, bs, log=True, state=st, from_upper=True, inter_from_scatter=True)
+    assert float((got_oe - ref_oe).abs().max()) <= 1e-6

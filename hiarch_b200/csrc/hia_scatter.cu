@@ -217,6 +217,10 @@ __device__ __forceinline__ int4 load_cols4(const unsigned short* p) {
 // while it is still in shared memory -- saves the 1.8 GB re-read of the upper triangle (0.5 ms at
 // 30 894 bins). Every thread keeps (chromosome, sum, count, min) for the run of columns it walks and
 // flushes into per-CTA tables when the chromosome changes; one global atomic per (row, chromosome).
+// MEASURED AND REJECTED as a default: correct (tests), but a thread's columns are 2 048 apart, so it
+// flushes on almost every iteration, and 512 threads hammering a few fp64 shared-memory words (CAS
+// loops) turned the 1.0 ms fill into 12 ms. Kept behind the *_stats entry points / HIA_FUSE_STATS=1;
+// a per-chromosome block reduction over the finished segment would be the way to make it pay.
 constexpr int kStatsMaxChr = 64;
 struct InterStats {
   const int* chr_start;

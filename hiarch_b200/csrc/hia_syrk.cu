@@ -808,12 +808,22 @@ int launch_prep(const float* x, int rows, int k, long long ld_x, int center, voi
     if (prec == HIA_PREC_3XF16) return launch_prep_reg_t<HIA_PREC_3XF16>(x, rows, k, ld_x, kpad, center, hi, lo, stream);
     return launch_prep_reg_t<HIA_PREC_3XTF32>(x, rows, k, ld_x, kpad, center, hi, lo, stream);
   }
+  // Rows in flight = CTAs per SM x SMs x row bytes must stay inside L2 for the second pass to hit it.
+  // HIA_PREP_CTAS (1 .. 4, default 4 = the register limit) caps the CTAs per SM by padding the launch with
+  // unused dynamic shared memory (tuning knob; measured in profiles/).
+  const char* e_ctas = getenv("HIA_PREP_CTAS");
+  const int ctas = e_ctas ? max(1, min(4, atoi(e_ctas))) : 4;
+  const size_t pad = ctas >= 4 ? 0 : (size_t)(200 * 1024 / ctas);
+  if (pad) {
+    HIA_CUDA(cudaFuncSetAttribute(row_prep_kernel<HIA_PREC_3XF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    HIA_CUDA(cudaFuncSetAttribute(row_prep_kernel<HIA_PREC_3XTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
   if (prec == HIA_PREC_3XF16)
-    row_prep_kernel<HIA_PREC_3XF16><<<rows, kPrepThreads, 0, stream>>>(x, rows, k, ld_x, kpad, center,
-                                                             static_cast<__half*>(hi), static_cast<__half*>(lo));
+    row_prep_kernel<HIA_PREC_3XF16><<<rows, kPrepThreads, pad, stream>>>(x, rows, k, ld_x, kpad, center,
+                                                               static_cast<__half*>(hi), static_cast<__half*>(lo));
   else
-    row_prep_kernel<HIA_PREC_3XTF32><<<rows, kPrepThreads, 0, stream>>>(x, rows, k, ld_x, kpad, center,
-                                                              static_cast<float*>(hi), static_cast<float*>(lo));
+    row_prep_kernel<HIA_PREC_3XTF32><<<rows, kPrepThreads, pad, stream>>>(x, rows, k, ld_x, kpad, center,
+                                                                static_cast<float*>(hi), static_cast<float*>(lo));
   HIA_LAUNCH_CHECK();
   return HIA_OK;
 }

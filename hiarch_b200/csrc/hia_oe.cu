@@ -179,11 +179,29 @@ inter_block_kernel(const float* __restrict__ map, int n, long long ld,
     const int r_stop = min(r1, chr_start[a + 1]);
     if (active && c0 + 3 >= col_lo) {
       const float* p = map + (long long)(r - row0) * ld + c0;   // ld % 4 == 0, ld >= n
-      for (; r + 4 <= r_stop; r += 4, p += 4 * ld) {
-        const float4 v0 = ld_stream4(p), v1 = ld_stream4(p + ld), v2 = ld_stream4(p + 2 * ld), v3 = ld_stream4(p + 3 * ld);
-        accumulate(v0, col_lo); accumulate(v1, col_lo); accumulate(v2, col_lo); accumulate(v3, col_lo);
+      if (c0 >= col_lo && c0 + 3 < n) {
+        // all four columns are inter-chromosome cells of this row range: no per-element tests, 8 rows in flight
+        auto acc4 = [&](const float4& v) {
+          sum[0] += v.x; sum[1] += v.y; sum[2] += v.z; sum[3] += v.w;
+          cnt[0] += (v.x != 0.f); cnt[1] += (v.y != 0.f); cnt[2] += (v.z != 0.f); cnt[3] += (v.w != 0.f);
+          mn[0] = fminf(mn[0], v.x > 0.f ? v.x : INFINITY); mn[1] = fminf(mn[1], v.y > 0.f ? v.y : INFINITY);
+          mn[2] = fminf(mn[2], v.z > 0.f ? v.z : INFINITY); mn[3] = fminf(mn[3], v.w > 0.f ? v.w : INFINITY);
+        };
+        for (; r + 8 <= r_stop; r += 8, p += 8 * ld) {
+          float4 v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = ld_stream4(p + q * ld);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc4(v[q]);
+        }
+        for (; r < r_stop; ++r, p += ld) acc4(ld_stream4(p));
+      } else {
+        for (; r + 4 <= r_stop; r += 4, p += 4 * ld) {
+          const float4 v0 = ld_stream4(p), v1 = ld_stream4(p + ld), v2 = ld_stream4(p + 2 * ld), v3 = ld_stream4(p + 3 * ld);
+          accumulate(v0, col_lo); accumulate(v1, col_lo); accumulate(v2, col_lo); accumulate(v3, col_lo);
+        }
+        for (; r < r_stop; ++r, p += ld) accumulate(ld_stream4(p), col_lo);
       }
-      for (; r < r_stop; ++r, p += ld) accumulate(ld_stream4(p), col_lo);
     } else {
       r = r_stop;
     }

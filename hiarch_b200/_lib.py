@@ -65,6 +65,10 @@ PROTOTYPES = {
     "hia_smooth1d_reflect": (c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, ctypes.c_double, c_i32, c_vp]),
     "hia_gf_pool_scores": (c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hia_template_scores": (c_int, [c_vp, c_i32, c_vp, c_i32, c_int, c_vp, c_vp]),
+    "hia_wavelet_default_levels": (c_i32, [c_i32, c_i32]),
+    "hia_wavelet_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),
+    "hia_wavelet_denoise_db3": (c_int, [c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_i64,
+                                        c_vp]),
     "hia_intra_x_response": (c_int, [c_vp, c_i32, c_i64, c_i32, c_vp, c_vp]),
     "hia_intra_x_workspace_bytes": (c_i64, [c_i32]),
     "hia_intra_x_response_prefix": (c_int, [c_vp, c_i32, c_i64, c_i32, c_vp, c_vp, c_i64, c_vp]),

@@ -1,0 +1,415 @@
+// Wavelet denoise of one dense block: multi-level separable 2-D db3 transform with half-sample
+// symmetric extension, VisuShrink soft threshold (sigma from the median |dd| of the finest level),
+// inverse transform. Replaces skimage.restoration.denoise_wavelet(arr, wavelet='db3',
+// method="VisuShrink") at publish/oe_map/S3_denoise.py:43-47 (the arithmetic is scikit-image +
+// PyWavelets; oracle/wavelet_oracle.py restates it, parity unpinned).
+//
+// All arithmetic is fp64 (the reference's arrays are float64); maps are read / written as fp32 or fp64.
+// Per level ONE kernel each way: a CTA stages a 36 x 36 input tile in shared memory, filters along
+// axis 0 then axis 1 and writes 16 x 16 coefficients of each of the four bands (forward); the inverse
+// stages 18 x 18 coefficients per band (soft-thresholded on the way in), and writes a 32 x 32 tile.
+// The median is an exact radix select on the 63-bit magnitude keys (6 passes of 11 bits).
+#include "hia_common.cuh"
+#include <mutex>
+
+namespace hia {
+namespace {
+
+constexpr int kF = 6;                // db3 filter length
+constexpr int kFwdT = 16;            // forward: coefficients per band per CTA (each way)
+constexpr int kFwdIn = 2 * kFwdT + 4;
+constexpr int kInvT = 32;            // inverse: output samples per CTA (each way)
+constexpr int kInvK = kInvT / 2 + 2; // coefficients per band per CTA (each way)
+constexpr int kBins = 2048;          // 11-bit digits
+constexpr int kPasses = 6;
+
+// dec_lo, dec_hi, rec_lo, rec_hi (closed form of the 3-vanishing-moment Daubechies filter, filled by the host)
+__constant__ double c_filt[4][kF];
+
+struct SelState {
+  unsigned long long prefix;   // key bits decided so far
+  unsigned long long k;        // remaining rank inside the prefix
+  unsigned long long m;        // number of nonzero coefficients
+  unsigned long long cnt_le;   // nonzero keys <= key(k1)
+  unsigned long long next;     // smallest key > key(k1)
+  unsigned int hist[kBins];
+};
+
+__device__ __forceinline__ int sym_index(int i, int n) {
+  // half-sample symmetric extension (... x1 x0 | x0 x1 ...), repeated for signals shorter than the halo
+  const int p = 2 * n;
+  i %= p;
+  if (i < 0) i += p;
+  return i < n ? i : p - 1 - i;
+}
+
+__device__ __forceinline__ int pass_shift(int pass) { return pass < 5 ? 52 - 11 * pass : 0; }
+__device__ __forceinline__ int pass_bits(int pass) { return pass < 5 ? 11 : 8; }
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) dwt2_fwd_kernel(const TIn* __restrict__ in, long long ld, int rows, int cols,
+                                                       double* __restrict__ aa, double* __restrict__ ad,
+                                                       double* __restrict__ da, double* __restrict__ dd,
+                                                       int orows, int ocols) {
+  __shared__ double s_in[kFwdIn][kFwdIn + 1];
+  __shared__ double s_lo[kFwdT][kFwdIn + 1];
+  __shared__ double s_hi[kFwdT][kFwdIn + 1];
+  const int k0r = blockIdx.y * kFwdT, k0c = blockIdx.x * kFwdT;
+  const int r_base = 2 * k0r - 4, c_base = 2 * k0c - 4;       // input index of tile element (0, 0)
+  for (int t = threadIdx.x; t < kFwdIn * kFwdIn; t += 256) {
+    const int tr = t / kFwdIn, tc = t - tr * kFwdIn;
+    const int gr = sym_index(r_base + tr, rows), gc = sym_index(c_base + tc, cols);
+    s_in[tr][tc] = (double)in[(long long)gr * ld + gc];
+  }
+  __syncthreads();
+  // axis 0: c[k] = sum_j f[j] x[2k + 1 - j]  ->  tile row 2 kl + 5 - j
+  for (int t = threadIdx.x; t < kFwdT * kFwdIn; t += 256) {
+    const int kl = t / kFwdIn, tc = t - kl * kFwdIn;
+    double lo = 0.0, hi = 0.0;
+#pragma unroll
+    for (int j = 0; j < kF; ++j) {
+      const double v = s_in[2 * kl + 5 - j][tc];
+      lo += c_filt[0][j] * v;
+      hi += c_filt[1][j] * v;
+    }
+    s_lo[kl][tc] = lo;
+    s_hi[kl][tc] = hi;
+  }
+  __syncthreads();
+  const int kr = threadIdx.x / kFwdT, kc = threadIdx.x % kFwdT;
+  const int gr = k0r + kr, gc = k0c + kc;
+  if (gr < orows && gc < ocols) {
+    double vaa = 0.0, vad = 0.0, vda = 0.0, vdd = 0.0;
+#pragma unroll
+    for (int j = 0; j < kF; ++j) {
+      const double l = s_lo[kr][2 * kc + 5 - j], h = s_hi[kr][2 * kc + 5 - j];
+      vaa += c_filt[0][j] * l;
+      vad += c_filt[1][j] * l;
+      vda += c_filt[0][j] * h;
+      vdd += c_filt[1][j] * h;
+    }
+    const long long o = (long long)gr * ocols + gc;
+    aa[o] = vaa; ad[o] = vad; da[o] = vda; dd[o] = vdd;
+  }
+}
+
+__device__ __forceinline__ double soft(double d, double thr) {
+  // pywt.threshold(d, thr, 'soft') = d * max(1 - thr/|d|, 0); a nan threshold poisons the band
+  if (thr != thr) return thr;
+  const double mag = fabs(d);
+  if (mag <= thr) return 0.0;
+  return d * (1.0 - thr / mag);
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(256) dwt2_inv_kernel(const double* __restrict__ aa, const double* __restrict__ ad,
+                                                       const double* __restrict__ da, const double* __restrict__ dd,
+                                                       int crows, int ccols, int lda /* row stride of aa */,
+                                                       const double* __restrict__ thr_ptr,
+                                                       TOut* __restrict__ out, long long ld_out, int rows, int cols) {
+  __shared__ double s_c[4][kInvK][kInvK + 1];
+  __shared__ double s_lo[kInvK][kInvT + 1];
+  __shared__ double s_hi[kInvK][kInvT + 1];
+  const double thr = *thr_ptr;
+  const int n0r = blockIdx.y * kInvT, n0c = blockIdx.x * kInvT;
+  const int kr0 = n0r / 2, kc0 = n0c / 2;
+  for (int t = threadIdx.x; t < kInvK * kInvK; t += 256) {
+    const int tr = t / kInvK, tc = t - tr * kInvK;
+    const int gr = kr0 + tr, gc = kc0 + tc;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    if (gr < crows && gc < ccols) {
+      const long long o = (long long)gr * ccols + gc;
+      v0 = aa[(long long)gr * lda + gc];
+      v1 = soft(ad[o], thr); v2 = soft(da[o], thr); v3 = soft(dd[o], thr);
+    }
+    s_c[0][tr][tc] = v0; s_c[1][tr][tc] = v1; s_c[2][tr][tc] = v2; s_c[3][tr][tc] = v3;
+  }
+  __syncthreads();
+  // axis 1: x[n] = sum_k a[k] g[n - 2k + 4] + d[k] gh[n - 2k + 4]; k = n/2 .. n/2 + 2, taps 4+par, 2+par, par
+  for (int t = threadIdx.x; t < kInvK * kInvT; t += 256) {
+    const int tr = t / kInvT, nl = t - tr * kInvT;
+    const int p = nl >> 1, par = nl & 1;
+    double lo = 0.0, hi = 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const double g = c_filt[2][4 + par - 2 * q], gh = c_filt[3][4 + par - 2 * q];
+      lo += s_c[0][tr][p + q] * g + s_c[1][tr][p + q] * gh;
+      hi += s_c[2][tr][p + q] * g + s_c[3][tr][p + q] * gh;
+    }
+    s_lo[tr][nl] = lo;
+    s_hi[tr][nl] = hi;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < kInvT * kInvT; t += 256) {
+    const int ml = t / kInvT, nl = t - ml * kInvT;
+    const int gr = n0r + ml, gc = n0c + nl;
+    if (gr >= rows || gc >= cols) continue;
+    const int p = ml >> 1, par = ml & 1;
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      v += s_lo[p + q][nl] * c_filt[2][4 + par - 2 * q] + s_hi[p + q][nl] * c_filt[3][4 + par - 2 * q];
+    out[(long long)gr * ld_out + gc] = (TOut)v;
+  }
+}
+
+__device__ __forceinline__ unsigned long long mag_key(double v) {
+  return (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
+}
+
+__global__ void __launch_bounds__(256) wl_hist_kernel(const double* __restrict__ d, long long n, int pass,
+                                                      SelState* __restrict__ st) {
+  __shared__ unsigned int s_h[kBins];
+  for (int i = threadIdx.x; i < kBins; i += 256) s_h[i] = 0u;
+  __syncthreads();
+  const int shift = pass_shift(pass), bits = pass_bits(pass);
+  const unsigned long long prefix = st->prefix;
+  const unsigned long long hi_mask = pass == 0 ? 0ull : ~((1ull << (shift + bits)) - 1ull);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const unsigned long long key = mag_key(d[i]);
+    if (key == 0ull) continue;                       // skimage drops exact zeros before the median
+    if ((key & hi_mask) != prefix) continue;
+    atomicAdd(&s_h[(unsigned int)(key >> shift) & ((1u << bits) - 1u)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBins; i += 256)
+    if (s_h[i]) atomicAdd(&st->hist[i], s_h[i]);
+}
+
+__global__ void __launch_bounds__(1024) wl_pick_kernel(SelState* __restrict__ st, int pass) {
+  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_total;
+  const int t = threadIdx.x;
+  const unsigned int h0 = st->hist[2 * t], h1 = st->hist[2 * t + 1];
+  unsigned long long v = (unsigned long long)h0 + h1, incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((t & 31) >= o) incl += u;
+  }
+  if ((t & 31) == 31) s_warp[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    unsigned long long w = s_warp[t], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, wi, o);
+      if (t >= o) wi += u;
+    }
+    s_warp[t] = wi - w;                 // exclusive prefix of the warp
+    if (t == 31) s_total = wi;
+  }
+  __syncthreads();
+  const unsigned long long before = s_warp[t >> 5] + incl - v;   // entries in bins < 2t
+  unsigned long long k = st->k;
+  if (pass == 0) {
+    const unsigned long long m = s_total;
+    k = m ? (m - 1) / 2 : 0;
+    if (t == 0) st->m = m;
+  }
+  __syncthreads();
+  if (s_total != 0) {
+    int bin = -1; unsigned long long below = 0;
+    if (k >= before && k < before + h0) { bin = 2 * t; below = before; }
+    else if (k >= before + h0 && k < before + v) { bin = 2 * t + 1; below = before + h0; }
+    if (bin >= 0) {
+      st->prefix |= (unsigned long long)bin << pass_shift(pass);
+      st->k = k - below;
+    }
+  }
+  st->hist[2 * t] = 0u;
+  st->hist[2 * t + 1] = 0u;
+}
+
+__global__ void __launch_bounds__(256) wl_rank_kernel(const double* __restrict__ d, long long n,
+                                                      SelState* __restrict__ st) {
+  const unsigned long long key1 = st->prefix;
+  unsigned long long cnt = 0, nxt = ~0ull;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const unsigned long long key = mag_key(d[i]);
+    if (key == 0ull) continue;
+    if (key <= key1) ++cnt;
+    else if (key < nxt) nxt = key;
+  }
+  cnt = warp_sum(cnt);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long u = __shfl_xor_sync(0xffffffffu, nxt, o);
+    nxt = u < nxt ? u : nxt;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (cnt) atomicAdd(&st->cnt_le, cnt);
+    if (nxt != ~0ull) atomicMin(&st->next, nxt);
+  }
+}
+
+// stats: [0] sigma, [1] threshold, [2] nonzero finest-diagonal coefficients
+__global__ void wl_finish_kernel(const SelState* __restrict__ st, double thr_factor, double* __restrict__ stats) {
+  const unsigned long long m = st->m;
+  double sigma;
+  if (m == 0) {
+    sigma = __longlong_as_double(0x7ff8000000000000ll);       // median of nothing: nan, as numpy gives
+  } else {
+    const double v1 = __longlong_as_double((long long)st->prefix);
+    const unsigned long long k2 = m / 2;
+    const double v2 = (st->cnt_le > k2) ? v1 : __longlong_as_double((long long)st->next);
+    const double med = (m & 1ull) ? v1 : (v1 + v2) * 0.5;
+    sigma = med / 0.6744897501960817;                          // scipy.stats.norm.ppf(0.75)
+  }
+  stats[0] = sigma;
+  stats[1] = sigma * thr_factor;
+  stats[2] = (double)m;
+}
+
+__global__ void wl_reset_kernel(SelState* __restrict__ st) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < kBins) st->hist[t] = 0u;
+  if (t == 0) { st->prefix = 0ull; st->k = 0ull; st->m = 0ull; st->cnt_le = 0ull; st->next = ~0ull; }
+}
+
+struct Plan {
+  int levels;
+  int r[34], c[34];
+  int64_t band_off[34];     // doubles; 4 bands of r[l] x c[l] from here (aa, ad, da, dd)
+  int64_t state_off;        // bytes
+  int64_t bytes;
+};
+
+int coeff_len(int n) { return (n + kF - 1) / 2; }
+
+int max_level(int n) {
+  if (n < kF - 1) return 0;
+  int l = 0;
+  while (((long long)(kF - 1) << (l + 1)) <= n) ++l;      // floor(log2(n / (F - 1)))
+  return l;
+}
+
+int default_levels(int rows, int cols) {
+  const int l = min(max_level(rows), max_level(cols)) - 3;
+  return l < 1 ? 1 : l;
+}
+
+bool make_plan(int rows, int cols, int levels, Plan* p) {
+  if (levels <= 0) levels = default_levels(rows, cols);
+  if (levels > 32) return false;
+  p->levels = levels;
+  p->r[0] = rows; p->c[0] = cols;
+  int64_t off = 0;
+  for (int l = 1; l <= levels; ++l) {
+    p->r[l] = coeff_len(p->r[l - 1]);
+    p->c[l] = coeff_len(p->c[l - 1]);
+    p->band_off[l] = off;
+    off += 4 * (((int64_t)p->r[l] * p->c[l] + 31) / 32 * 32);
+  }
+  p->state_off = off * 8;
+  p->bytes = p->state_off + (int64_t)sizeof(SelState) + 256;
+  return true;
+}
+
+int64_t band_stride(const Plan& p, int l) { return ((int64_t)p.r[l] * p.c[l] + 31) / 32 * 32; }
+
+int upload_filters() {
+  static std::mutex mu;
+  static bool done = false;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done) return HIA_OK;
+  const double s10 = sqrt(10.0), s5 = sqrt(5.0 + 2.0 * s10), den = 16.0 * sqrt(2.0);
+  const double h[kF] = {(1 + s10 + s5) / den, (5 + s10 + 3 * s5) / den, (10 - 2 * s10 + 2 * s5) / den,
+                        (10 - 2 * s10 - 2 * s5) / den, (5 + s10 - 3 * s5) / den, (1 + s10 - s5) / den};
+  double f[4][kF];
+  for (int j = 0; j < kF; ++j) {
+    f[2][j] = h[j];                                   // rec_lo
+    f[0][j] = h[kF - 1 - j];                          // dec_lo
+  }
+  for (int j = 0; j < kF; ++j) {
+    f[1][j] = ((j + 1) & 1 ? -1.0 : 1.0) * f[0][kF - 1 - j];   // dec_hi[j] = (-1)^(j+1) dec_lo[F-1-j]
+  }
+  for (int j = 0; j < kF; ++j) f[3][j] = f[1][kF - 1 - j];      // rec_hi
+  HIA_CUDA(cudaMemcpyToSymbol(c_filt, f, sizeof(f)));
+  done = true;
+  return HIA_OK;
+}
+
+template <typename T>
+int run(const T* in, int64_t ld_in, int rows, int cols, int levels, T* out, int64_t ld_out, double* stats,
+        void* ws, int64_t ws_bytes, cudaStream_t s) {
+  Plan p;
+  if (!make_plan(rows, cols, levels, &p)) return HIA_ERR_BAD_ARG;
+  if (ws_bytes < p.bytes) return HIA_ERR_WORKSPACE;
+  if (!aligned16(ws)) return HIA_ERR_ALIGN;
+  int st_ = upload_filters();
+  if (st_ != HIA_OK) return st_;
+  double* base = reinterpret_cast<double*>(ws);
+  SelState* st = reinterpret_cast<SelState*>(reinterpret_cast<char*>(ws) + p.state_off);
+  auto band = [&](int l, int b) { return base + p.band_off[l] + b * band_stride(p, l); };
+
+  wl_reset_kernel<<<(kBins + 255) / 256, 256, 0, s>>>(st);
+  HIA_LAUNCH_CHECK();
+  for (int l = 1; l <= p.levels; ++l) {
+    dim3 grid((p.c[l] + kFwdT - 1) / kFwdT, (p.r[l] + kFwdT - 1) / kFwdT);
+    if (l == 1)
+      dwt2_fwd_kernel<T><<<grid, 256, 0, s>>>(in, ld_in, rows, cols, band(1, 0), band(1, 1), band(1, 2), band(1, 3),
+                                              p.r[1], p.c[1]);
+    else
+      dwt2_fwd_kernel<double><<<grid, 256, 0, s>>>(band(l - 1, 0), p.c[l - 1], p.r[l - 1], p.c[l - 1], band(l, 0),
+                                                   band(l, 1), band(l, 2), band(l, 3), p.r[l], p.c[l]);
+    HIA_LAUNCH_CHECK();
+  }
+  // sigma: median of the nonzero |dd| of the finest level (exact radix select), threshold = sigma sqrt(2 ln size)
+  const long long nd = (long long)p.r[1] * p.c[1];
+  const long long sel_want = (nd + 256 * 8 - 1) / (256 * 8), sel_cap = (long long)num_sms() * 8;
+  const int sel_grid = (int)(sel_want < sel_cap ? sel_want : sel_cap);
+  for (int pass = 0; pass < kPasses; ++pass) {
+    wl_hist_kernel<<<max(sel_grid, 1), 256, 0, s>>>(band(1, 3), nd, pass, st);
+    HIA_LAUNCH_CHECK();
+    wl_pick_kernel<<<1, 1024, 0, s>>>(st, pass);
+    HIA_LAUNCH_CHECK();
+  }
+  wl_rank_kernel<<<max(sel_grid, 1), 256, 0, s>>>(band(1, 3), nd, st);
+  HIA_LAUNCH_CHECK();
+  const double size = (double)rows * (double)cols;
+  wl_finish_kernel<<<1, 1, 0, s>>>(st, sqrt(2.0 * log(size)), stats);
+  HIA_LAUNCH_CHECK();
+  for (int l = p.levels; l >= 1; --l) {
+    // the level-l bands rebuild the level-(l-1) approximation, trimmed to its forward size
+    const int orows = p.r[l - 1], ocols = p.c[l - 1];
+    dim3 grid((ocols + kInvT - 1) / kInvT, (orows + kInvT - 1) / kInvT);
+    if (l == 1)
+      dwt2_inv_kernel<T><<<grid, 256, 0, s>>>(band(1, 0), band(1, 1), band(1, 2), band(1, 3), p.r[1], p.c[1], p.c[1],
+                                              stats + 1, out, ld_out, rows, cols);
+    else
+      dwt2_inv_kernel<double><<<grid, 256, 0, s>>>(band(l, 0), band(l, 1), band(l, 2), band(l, 3), p.r[l], p.c[l],
+                                                   p.c[l], stats + 1, band(l - 1, 0), p.c[l - 1], orows, ocols);
+    HIA_LAUNCH_CHECK();
+  }
+  return HIA_OK;
+}
+
+}  // namespace
+}  // namespace hia
+
+HIA_API int32_t hia_wavelet_default_levels(int32_t rows, int32_t cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  return hia::default_levels(rows, cols);
+}
+
+HIA_API int64_t hia_wavelet_workspace_bytes(int32_t rows, int32_t cols, int32_t levels) {
+  if (rows <= 0 || cols <= 0) return 0;
+  hia::Plan p;
+  if (!hia::make_plan(rows, cols, levels, &p)) return -1;
+  return p.bytes;
+}
+
+HIA_API int hia_wavelet_denoise_db3(const void* in, int64_t ld_in, int32_t rows, int32_t cols, int32_t elem_bytes,
+                                    int32_t levels, void* out, int64_t ld_out, double* stats, void* ws,
+                                    int64_t ws_bytes, void* stream_) {
+  if (rows < 0 || cols < 0 || (elem_bytes != 4 && elem_bytes != 8)) return HIA_ERR_BAD_ARG;
+  if (rows == 0 || cols == 0) return HIA_OK;
+  if (!in || !out || !stats || !ws || in == out || ld_in < cols || ld_out < cols) return HIA_ERR_BAD_ARG;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  if (elem_bytes == 4)
+    return hia::run<float>(static_cast<const float*>(in), ld_in, rows, cols, levels, static_cast<float*>(out), ld_out,
+                           stats, ws, ws_bytes, s);
+  return hia::run<double>(static_cast<const double*>(in), ld_in, rows, cols, levels, static_cast<double*>(out),
+                          ld_out, stats, ws, ws_bytes, s);
+}

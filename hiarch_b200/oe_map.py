@@ -55,9 +55,15 @@ def norm_de_mtx(input_mtx):
 
 
 def denoise_one_method(sps_mtx, mode='wavelet', sigma=None, spatial_sigma_ratio=None):
-    """S3_denoise.py:38-73, modes 'median' and 'mean'. 'wavelet' (skimage db3 VisuShrink) is
-    third-party, unversioned arithmetic that is absent here: parity unpinned, not implemented."""
+    """S3_denoise.py:38-73, modes 'wavelet', 'median' and 'mean'. 'wavelet' is
+    skimage.restoration.denoise_wavelet(arr, wavelet='db3', method="VisuShrink") (:43-47) on the
+    device (csrc/hia_wavelet.cu); that arithmetic is third-party and unversioned in the reference, so
+    its parity is pinned to oracle/wavelet_oracle.py's written-down definition only. `sigma` is
+    accepted and, as in the reference, not passed on. 'low-pass' / 'bilateral' are unused by the
+    pipeline and not built."""
     d = sps_mtx.to_dense() if isinstance(sps_mtx, SpsHiCMtx) else sps_mtx
+    if mode == 'wavelet':
+        return ArrayHiCMtx(ops.wavelet_denoise_db3(d.dmatrix), copy_mtx_paras=d)
     ratio = .1 if spatial_sigma_ratio is None else spatial_sigma_ratio
     size = int(np.mean(np.array(list(sps_mtx.row_window.chr_lens.values())) * ratio))
     if mode == 'median':
@@ -72,39 +78,38 @@ def denoise_one_method(sps_mtx, mode='wavelet', sigma=None, spatial_sigma_ratio=
         out = ops.alloc_map(d.shape[0], d.dmatrix.device, cols=d.shape[1])
         ops.used_filter(d.dmatrix, size, out, decimals=-1, normalise=False)
     else:
-        raise NotImplementedError(f"denoise mode {mode!r}: parity unpinned / not on the hot path")
+        raise NotImplementedError(f"denoise mode {mode!r}: not used by the pipeline, not built")
     return ArrayHiCMtx(out, copy_mtx_paras=d)
 
 
-class WaveletSkippedWarning(UserWarning):
-    """The wavelet step of the reference's denoise was not applied (see main_denoise)."""
+def used_denoise(sps_mtx, wavelet=None):
+    """S3_denoise.py:76-79: wavelet, then median (size from 1 % of the mean chromosome length)."""
+    wavelet = _resolve_wavelet(wavelet)
+    if wavelet is not None:
+        sps_mtx = wavelet(sps_mtx)
+    return denoise_one_method(sps_mtx, 'median', None, .01)
+
+
+def _native_wavelet(blk):
+    return denoise_one_method(blk, 'wavelet', None, None)
 
 
 def _resolve_wavelet(wavelet):
-    """None -> warn loudly (the output then differs from the reference pipeline's), 'identity' ->
-    the caller opted out explicitly, callable -> applied per block."""
-    if wavelet is None:
-        import warnings
-        msg = ("wavelet denoise (skimage denoise_wavelet db3/VisuShrink, publish/oe_map/S3_denoise.py:43-47) "
-               "is NOT applied: scikit-image/PyWavelets arithmetic is third-party and unpinned. The "
-               "`.de_ode.mtx` written under the reference's name is clip -> median only. Pass "
-               "wavelet=<callable on a block> to apply one, or wavelet='identity' to silence this.")
-        warnings.warn(msg, WaveletSkippedWarning, stacklevel=3)
-        print(f'Warning: {msg}')
-        return None
+    """None / 'db3' -> the reference's step on the device; 'identity' -> skip it knowingly (the
+    fixtures generated before the step existed say wavelet=identity); callable -> applied per block."""
+    if wavelet is None or (isinstance(wavelet, str) and wavelet == 'db3'):
+        return _native_wavelet
     if isinstance(wavelet, str):
         if wavelet != 'identity':
-            raise ValueError(f"wavelet={wavelet!r}: pass a callable or 'identity'")
+            raise ValueError(f"wavelet={wavelet!r}: pass None / 'db3', 'identity' or a callable")
         return None
     return wavelet
 
 
 def main_denoise(sps_map, wavelet=None):
-    """S3_denoise.py:95-107: clip to [p2, p98], then per block wavelet -> median. The reference's
-    wavelet is NOT available (see denoise_one_method): `wavelet` = a callable applied per block
-    (e.g. the same substitute on both sides of a comparison), 'identity' = skip it knowingly,
-    None (default) = skip it with a WaveletSkippedWarning + a 'Warning:' line on stdout. The result
-    carries `.wavelet_applied`."""
+    """S3_denoise.py:95-107: clip to [p2, p98], then per chromosome block wavelet -> median.
+    `wavelet`: None / 'db3' = the reference's db3 VisuShrink step (device kernels), 'identity' =
+    leave it out, callable = applied per block instead. The result carries `.wavelet_applied`."""
     wavelet = _resolve_wavelet(wavelet)
     d = _dense_all(sps_map)
     clipped = tid_off_outliers(d)
@@ -126,7 +131,7 @@ def oe_map_main(sps_mtx, output=None, fig_output=None, centr_loc=None,
     """main_get_oe.py:10-59, the NormDis step on an already parsed map: preprocess_mtx ->
     oe_map_core -> `<output>.ode.mtx` (+ `.window.bed`) -> main_denoise -> norm_de_mtx ->
     `<output>.de_ode.mtx`. The plots (`fig_output`, `centr_loc`) are out of scope and ignored;
-    `wavelet` goes to main_denoise (None = skipped WITH a warning, see there)."""
+    `wavelet` goes to main_denoise (None = the db3 VisuShrink step, see there)."""
     from .preprocess import preprocess_mtx
     pro_mtx = preprocess_mtx(sps_mtx, do_filt_chr_by_name)
     if pro_mtx is None:

@@ -669,6 +669,41 @@ def median_filter_reflect(block, size, out=None):
     return out
 
 
+def wavelet_default_levels(rows, cols):
+    """scikit-image's default number of db3 levels for a rows x cols block."""
+    return int(_lib.load().hia_wavelet_default_levels(int(rows), int(cols)))
+
+
+def wavelet_denoise_db3(block, levels=None, out=None, workspace=None, return_stats=False):
+    """skimage.restoration.denoise_wavelet(block, wavelet='db3', method="VisuShrink") of one dense
+    block (denoise_one_method 'wavelet', publish/oe_map/S3_denoise.py:43-47): multi-level db3
+    transform, soft threshold at sigma sqrt(2 ln size), inverse. fp32 or fp64 block, fp64 inside.
+    `return_stats`: also the device tensor [sigma, threshold, nonzero finest-diagonal count]."""
+    lib = _lib.load()
+    _need_cuda(block)
+    assert block.dim() == 2 and block.dtype in (torch.float32, torch.float64) and (block.numel() == 0 or block.stride(1) == 1)
+    rows, cols = block.shape
+    if out is None:
+        if block.dtype == torch.float32:
+            out = alloc_map(rows, block.device, cols=cols)
+        else:
+            out = torch.empty((rows, cols), dtype=block.dtype, device=block.device)
+    assert out.dtype == block.dtype and out.shape == block.shape
+    stats = torch.zeros(3, dtype=torch.float64, device=block.device)
+    if rows and cols:
+        lv = 0 if levels is None else int(levels)
+        need = lib.hia_wavelet_workspace_bytes(rows, cols, lv)
+        if need < 0:
+            raise _lib.HiaError(f"wavelet_denoise_db3: levels={levels} not supported")
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=block.device)
+        st = lib.hia_wavelet_denoise_db3(_ptr(block), block.stride(0), rows, cols, block.element_size(), lv,
+                                         _ptr(out), out.stride(0), _ptr(stats), _ptr(workspace), workspace.numel(),
+                                         _stream())
+        _lib.check(st, "hia_wavelet_denoise_db3")
+    return (out, stats) if return_stats else out
+
+
 def used_filter(block, size, out, decimals=2, normalise=True, workspace=None):
     """used_filter of GF_S1 on one block: box filter + norm_to_zero_mean, fp64 inside with
     scipy's exact summation order (see csrc/hia_filter64.cu for why)."""

@@ -352,6 +352,26 @@ int hia_template_scores(const double* xs, int32_t n_img, const double* tmpl, int
                         double* scores, void* stream);
 
 
+/* ------------------------------------------------------------------------------------ */
+/* f4: wavelet denoise of one dense block. Replaces                                       */
+/*   skimage.restoration.denoise_wavelet(arr, wavelet='db3', method="VisuShrink")         */
+/*   at publish/oe_map/S3_denoise.py:43-47 (called per chromosome block, :76-79, :95-107) */
+/* ------------------------------------------------------------------------------------ */
+/* Multi-level separable 2-D db3 transform (half-sample symmetric extension, PyWavelets' dwt/idwt
+ * conventions), sigma = median(|dd_finest| != 0) / 0.6745, threshold = sigma sqrt(2 ln(rows cols)),
+ * soft threshold of every detail band, inverse transform cut to rows x cols. fp64 arithmetic.
+ * The arithmetic is third-party and unversioned in the reference: oracle/wavelet_oracle.py writes the
+ * definition down (parity unpinned).
+ * levels <= 0: scikit-image's default, max(min over axes of floor(log2(n / 5)) - 3, 1).
+ * in / out: device, rows x cols, elem_bytes = 4 (fp32) or 8 (fp64), must not overlap.
+ * stats (device, 3 doubles): sigma, threshold, number of nonzero finest-diagonal coefficients. */
+int32_t hia_wavelet_default_levels(int32_t rows, int32_t cols);
+int64_t hia_wavelet_workspace_bytes(int32_t rows, int32_t cols, int32_t levels);
+int hia_wavelet_denoise_db3(const void* in, int64_t ld_in, int32_t rows, int32_t cols, int32_t elem_bytes,
+                            int32_t levels, void* out, int64_t ld_out, double* stats, void* ws,
+                            int64_t ws_bytes, void* stream);
+
+
 /* Row-sharded similarity (the one exchange step of the path): every rank
  * prepares the hi/lo planes of ITS rows (hia_sim_prep_rows; planes are row-major with
  * hia_sim_kpad(k, precision) columns of hia_sim_plane_elem_bytes(precision) bytes: fp32 for

@@ -13,8 +13,11 @@ What the shim does:
      `publish/oe_map/S3_denoise.py:5`: skimage.restoration);
   3. no-ops the unconditional plot calls.
 The wavelet step (`skimage.restoration.denoise_wavelet`, S3_denoise.py:45-47) has no
-implementation here (scikit-image/PyWavelets absent, unpinned) -> the stub is the
-identity; every fixture that crosses that call says so ("wavelet=identity").
+implementation here (scikit-image/PyWavelets absent, unpinned) -> the stub is the identity by
+default and every fixture that crosses that call says so ("wavelet=identity");
+`set_wavelet("db3")` swaps in oracle/wavelet_oracle.py's written-down restatement of the two
+libraries' published algorithm (fixtures then say "wavelet=db3 (oracle/wavelet_oracle.py)": the
+reference's own code around a stand-in for the one call that cannot run here).
 """
 import os
 import sys
@@ -52,6 +55,24 @@ def _stub(name, **attrs):
 _installed = False
 
 
+def _identity_wavelet(arr, **kw):
+    return arr
+
+
+def _oracle_wavelet(arr, **kw):
+    """Stand-in for skimage.restoration.denoise_wavelet, only for the reference's own call."""
+    from oracle import wavelet_oracle
+    if kw != {"wavelet": "db3", "method": "VisuShrink"}:
+        raise NotImplementedError(f"denoise_wavelet stand-in: only the reference's call is restated, got {kw}")
+    return wavelet_oracle.denoise_wavelet_db3_visushrink(arr)
+
+
+def set_wavelet(kind):
+    """'identity' (default) or 'db3': what the stubbed skimage.restoration.denoise_wavelet does."""
+    fn = {"identity": _identity_wavelet, "db3": _oracle_wavelet}[kind]
+    sys.modules["skimage.restoration"].denoise_wavelet = fn
+
+
 def install():
     """Idempotently make the reference importable. Returns the `new_hic_class` module."""
     global _installed
@@ -72,7 +93,7 @@ def install():
         if "skimage" not in sys.modules:
             sk = _stub("skimage")
             rest = _stub("skimage.restoration",
-                         denoise_wavelet=lambda arr, **kw: arr,   # identity (see docstring)
+                         denoise_wavelet=_identity_wavelet,        # see set_wavelet
                          denoise_bilateral=lambda arr, **kw: arr)
             sk.restoration = rest
         _installed = True

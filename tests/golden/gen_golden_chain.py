@@ -8,7 +8,9 @@ exactly as `publish/HiArch/one_click_pipeline.sh:40-169` launches them (same arg
 with the plot calls no-op'd and wavelet = identity (oracle/ref_shim.py: scikit-image is absent and
 unpinned). Every output file is stored: .mtx files as (rows, cols, vals) arrays, the small tables as text.
 
-    python tests/golden/gen_golden_chain.py        -> tests/golden/gchain.npz
+    python tests/golden/gen_golden_chain.py                 -> tests/golden/gchain.npz
+    python tests/golden/gen_golden_chain.py --wavelet db3   -> tests/golden/gchain_db3.npz
+        (the reference's own code with oracle/wavelet_oracle.py standing in for the one absent call)
 
 The input is NOT stored: `hiarch_b200.synth.write_sample(**CASE)` regenerates it at test time.
 """
@@ -39,7 +41,10 @@ def mtx_arrays(path):
 
 
 def main():
+    db3 = sys.argv[1:] == ["--wavelet", "db3"]
+    assert db3 or not sys.argv[1:], sys.argv
     ref_shim.install()
+    ref_shim.set_wavelet("db3" if db3 else "identity")
     import NormDis
     import CorrectMap
     import GF_S1_get_center
@@ -47,7 +52,7 @@ def main():
     from complex.src.main_local import local_io
     CorrectMap.heatmap_plot = lambda *a, **k: None
     np.random.seed(0)                                  # main_local draws from np.random for its plot choice
-    g = {"wavelet": np.array("identity")}
+    g = {"wavelet": np.array("db3 (oracle/wavelet_oracle.py)" if db3 else "identity")}
     with tempfile.TemporaryDirectory() as tmp:
         mtx, bed = synth.write_sample(f"{tmp}/sample", **CASE)
         d = {k: f"{tmp}/result/{k}/mtx" for k in ("normDis", "correctMap", "checkerBoard", "globalFolding_s1",
@@ -92,7 +97,7 @@ def main():
         g["confor.files"] = np.array(confor)
         for f in confor:
             g[f"confor.{f}"] = np.array(open(os.path.join(d["globalFolding_s2"], f)).read())
-    np.savez_compressed(f"{HERE}/gchain.npz", **g)
+    np.savez_compressed(f"{HERE}/gchain_db3.npz" if db3 else f"{HERE}/gchain.npz", **g)
     print({k: getattr(v, "shape", None) for k, v in g.items()})
     print(str(g["log"])[-1500:])
     print(str(g["checkerBoard"]))

@@ -7,7 +7,9 @@ stubs it to the identity; everything else of the step is the reference's own cod
                    -> main_denoise (clip p2/p98, per-block [wavelet=identity ->] median filter)
                    -> norm_de_mtx -> .de_ode.mtx
 
-    python tests/golden/gen_golden_normdis.py        -> tests/golden/gnormdis.npz
+    python tests/golden/gen_golden_normdis.py                 -> tests/golden/gnormdis.npz
+    python tests/golden/gen_golden_normdis.py --wavelet db3   -> tests/golden/gnormdis_db3.npz
+        (the reference's own code with oracle/wavelet_oracle.py standing in for the one absent call)
 
 The input is NOT stored: `hiarch_b200.synth.write_sample(**CASE)` regenerates it at test time.
 """
@@ -32,7 +34,10 @@ CASE = dict(names=["chr1", "chr2", "chr3"], lens=[150, 120, 90], bin_size=100000
 
 
 def main():
+    db3 = sys.argv[1:] == ["--wavelet", "db3"]
+    assert db3 or not sys.argv[1:], sys.argv
     ref_shim.install()
+    ref_shim.set_wavelet("db3" if db3 else "identity")
     from oe_map.main_get_oe import oe_map_io
     from oe_map.S3_denoise import main_denoise
     from oe_map.S2_oe import oe_map_core
@@ -44,7 +49,7 @@ def main():
         log = io.StringIO()
         with contextlib.redirect_stdout(log):
             de = oe_map_io(mtx, out, None, do_filt_chr_by_name=True, counts_must_decrese=True, index_file=bed)
-        g = {"log": np.array(log.getvalue()), "wavelet": np.array("identity")}
+        g = {"log": np.array(log.getvalue()), "wavelet": np.array("db3 (oracle/wavelet_oracle.py)" if db3 else "identity")}
         for tag in ("ode", "de_ode"):
             a = np.loadtxt(f"{out}.{tag}.mtx")
             g[f"{tag}.rows"] = a[:, 0].astype(np.int32)
@@ -62,7 +67,7 @@ def main():
         g["ode.dense"] = np.asarray(ode.to_dense().matrix, dtype=np.float64)
         g["denoised.dense"] = np.asarray(den.matrix, dtype=np.float64)
         g["de_ode.dense"] = np.asarray(de.matrix, dtype=np.float64)
-        np.savez_compressed(f"{HERE}/gnormdis.npz", **g)
+        np.savez_compressed(f"{HERE}/gnormdis_db3.npz" if db3 else f"{HERE}/gnormdis.npz", **g)
         print({k: getattr(v, "shape", None) for k, v in g.items()})
         print(log.getvalue())
 

@@ -163,18 +163,21 @@ def test_hot_path_streaming_matches_blocking_calls():
             assert cos >= 0.9999, (j, cos)
 
 
-def test_norm_dis_step_against_reference_files(golden, tmp_path):
+@pytest.mark.parametrize("case", ["gnormdis", "gnormdis_db3"])
+def test_norm_dis_step_against_reference_files(golden, tmp_path, case):
     """Step 1 of one_click_pipeline.sh (publish/HiArch/NormDis.py): `.mtx` + `.window.bed` in,
     `.ode.mtx` / `.window.bed` / `.de_ode.mtx` out, against the files the real reference wrote for
-    the same input (wavelet = identity on both sides, tests/golden/gen_golden_normdis.py)."""
+    the same input (tests/golden/gen_golden_normdis.py). `gnormdis`: wavelet = identity on both sides;
+    `gnormdis_db3`: the default path (db3 VisuShrink on the device) against the reference run with
+    oracle/wavelet_oracle.py standing in for the absent skimage call."""
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
     from gen_golden_normdis import CASE
     from hiarch_b200 import oe_map
-    g = golden("gnormdis")
+    g = golden(case)
     mtx, bed = synth.write_sample(f"{tmp_path}/s", **CASE)
     out = f"{tmp_path}/res"
-    de = oe_map.norm_dis(mtx, bed, out)
+    de = oe_map.norm_dis(mtx, bed, out, wavelet="identity" if str(g["wavelet"]) == "identity" else None)
     assert de is not None and tuple(de.shape) == g["de_ode.dense"].shape
     assert open(f"{out}.window.bed").read() == str(g["window_bed"])          # bins kept by preprocess_mtx
     assert not os.path.exists(f"{out}.de_window.bed")
@@ -183,8 +186,12 @@ def test_norm_dis_step_against_reference_files(golden, tmp_path):
         assert mine.shape[0] == len(g[f"{tag}.vals"]), tag
         assert np.array_equal(mine[:, 0], g[f"{tag}.rows"]) and np.array_equal(mine[:, 1], g[f"{tag}.cols"]), tag
         assert np.abs(mine[:, 2] - g[f"{tag}.vals"]).max() <= 0.0100001, tag     # one %.2f unit (fp32 storage)
-        assert np.mean(mine[:, 2] != g[f"{tag}.vals"]) < 2e-3, tag
-    assert np.abs(de.matrix - g["de_ode.dense"]).max() <= 2e-5
+        # identity: the median of clipped values has many ties; after the wavelet every cell is a distinct
+        # value and a ~2e-5 storage error lands on the other side of a %.2f boundary for ~0.5 % of them
+        assert np.mean(mine[:, 2] != g[f"{tag}.vals"]) < (2e-3 if case == "gnormdis" or tag == "ode" else 1e-2), tag
+    # fp32 map storage between the stages, amplified by the final z-score (values reach +-10); the wavelet
+    # adds one more stored fp32 map to the chain
+    assert np.abs(de.matrix - g["de_ode.dense"]).max() <= (2e-5 if case == "gnormdis" else 3e-5)
 
 
 @pytest.mark.timeout(180)
@@ -251,11 +258,14 @@ def test_upper_only_mode_is_bit_identical(monkeypatch):
 
 
 @pytest.mark.timeout(600)
-def test_one_click_chain_against_reference_files(golden, tmp_path):
+@pytest.mark.parametrize("case", ["gchain", "gchain_db3"])
+def test_one_click_chain_against_reference_files(golden, tmp_path, case):
     """The whole one_click_pipeline.sh chain (BASELINE.json config C1 shape): the five steps of
     publish/HiArch/one_click_pipeline.sh:40-169 with the script's own arguments, chained through their
     text files, every output compared with the files the REAL reference wrote for the same input
-    (tests/golden/gen_golden_chain.py; wavelet = identity on both sides).
+    (tests/golden/gen_golden_chain.py). `gchain`: wavelet = identity on both sides; `gchain_db3`: the
+    default path (wavelet on the device) against the reference run with oracle/wavelet_oracle.py
+    standing in for the absent skimage call.
 
     Each step reads OUR output of the previous step, so a %.2f cell that rounds to the neighbouring
     0.01 (fp32 map storage, bounded below) travels down the chain; the integer outputs (bins, file
@@ -265,8 +275,8 @@ def test_one_click_chain_against_reference_files(golden, tmp_path):
     from gen_golden_chain import CASE, NAME
     from hiarch_b200 import complex as cx, confor, oe_map
     from hiarch_b200.preprocess import correct_map
-    g = golden("gchain")
-    assert str(g["wavelet"]) == "identity"
+    g = golden(case)
+    wavelet = "identity" if str(g["wavelet"]) == "identity" else None
     mtx, bed = synth.write_sample(f"{tmp_path}/sample", **CASE)
     d = {k: f"{tmp_path}/result/{k}/mtx" for k in ("normDis", "correctMap", "checkerBoard", "globalFolding_s1",
                                                     "globalFolding_s2")}
@@ -278,10 +288,12 @@ def test_one_click_chain_against_reference_files(golden, tmp_path):
         assert mine.shape[0] == len(g[f"{tag}.vals"]), tag
         assert np.array_equal(mine[:, 0], g[f"{tag}.rows"]) and np.array_equal(mine[:, 1], g[f"{tag}.cols"]), tag
         assert np.abs(mine[:, 2] - g[f"{tag}.vals"]).max() <= 0.0100001, tag          # one %.2f unit
-        assert np.mean(mine[:, 2] != g[f"{tag}.vals"]) < flips, tag
+        # with the wavelet every denoised cell is a distinct value: a ~2e-5 storage error crosses a %.2f
+        # boundary for ~0.5 % of them (identity: the median of clipped values has many ties)
+        assert np.mean(mine[:, 2] != g[f"{tag}.vals"]) < (flips if wavelet == "identity" or tag == "ode" else 5 * flips), tag
 
     # step 1: NormDis.py -f -w -o -fo -df True -cmd True
-    oe_map.norm_dis(mtx, bed, f"{d['normDis']}/{NAME}", f"{tmp_path}/fig/{NAME}", "True", "True", wavelet="identity")
+    oe_map.norm_dis(mtx, bed, f"{d['normDis']}/{NAME}", f"{tmp_path}/fig/{NAME}", "True", "True", wavelet=wavelet)
     assert open(f"{d['normDis']}/{NAME}.window.bed").read() == str(g["normDis.window_bed"])
     same_mtx(f"{d['normDis']}/{NAME}.ode.mtx", "ode", 2e-3)
     same_mtx(f"{d['normDis']}/{NAME}.de_ode.mtx", "de_ode", 2e-3)

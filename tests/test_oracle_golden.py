@@ -135,18 +135,27 @@ def test_topk_eig_is_selfconsistent(golden):
     assert np.abs(C @ v - v * w).max() < 1e-9
 
 
-def test_main_denoise_and_normdis_chain(golden):
+@pytest.mark.parametrize("case", ["gnormdis", "gnormdis_db3"])
+def test_main_denoise_and_normdis_chain(golden, case):
     """NormDis after the O/E map (oe_map/main_get_oe.py:40-50): main_denoise (clip, per-block
-    median; wavelet = identity, see tests/golden/gen_golden_normdis.py) -> norm_de_mtx, and the
-    %.2f text the step writes -- the oracle against the REAL reference's output."""
-    g = golden("gnormdis")
-    assert str(g["wavelet"]) == "identity"
+    [wavelet ->] median, see tests/golden/gen_golden_normdis.py) -> norm_de_mtx, and the %.2f text
+    the step writes -- the oracle against the REAL reference's output. `gnormdis`: wavelet = identity;
+    `gnormdis_db3`: the reference ran with oracle/wavelet_oracle.py standing in for the absent
+    skimage call (this pins the composition around the wavelet, not the wavelet's arithmetic)."""
+    g = golden(case)
+    if case == "gnormdis":
+        assert str(g["wavelet"]) == "identity"
+        wavelet = None
+    else:
+        from oracle import wavelet_oracle
+        assert str(g["wavelet"]).startswith("db3")
+        wavelet = wavelet_oracle.denoise_wavelet_db3_visushrink
     lens = [int(x) for x in g["pro.lens"]]
     seps, s = [], 0
     for L in lens:
         seps.append((s, s + L - 1))
         s += L
-    den = O.main_denoise(g["ode.dense"], seps)
+    den = O.main_denoise(g["ode.dense"], seps, wavelet=wavelet)
     assert np.abs(den - g["denoised.dense"]).max() == 0.0
     de = O.norm_de_mtx(den)
     assert np.abs(de - g["de_ode.dense"]).max() < 1e-12

@@ -417,6 +417,9 @@ def run_row_sharded(args, world, rank, local, pk, steps=2):
         if it > 0:
             for key, (i, j) in (("oe_log", (0, 1)), ("similarity", (1, 2)), ("eig", (2, 3)), ("total", (0, 3))):
                 ms[key].append(mx(e[i].elapsed_time(e[j])))
+    eig_phases = {}
+    path.eigen(phases=eig_phases)                            # one more, untimed, with per-phase events
+    barrier()
     ring_stats = path.sim.collect_stats() if path.ring else {}
     oe_phases = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(oe_marks[:-1], oe_marks[1:])}
     err, cnt = path.spot_check_fp64(n_own=16, n_other=64)
@@ -446,7 +449,8 @@ def run_row_sharded(args, world, rank, local, pk, steps=2):
                           "note": "exposed_comm_ms = time the compute stream waited for a plane pull (max over "
                                   "ranks, last timed step); the pulls run on copy engines behind the previous block"},
            "fp64_spot_check": {"entries": cnt, "max_abs_err": err},
-           "eig": {"eigvals": [float(x) for x in w.cpu().numpy()], "cycles": info, "rel_residual_max": eig_res}}
+           "eig": {"eigvals": [float(x) for x in w.cpu().numpy()], "cycles": info, "rel_residual_max": eig_res,
+                   "phases_ms_rank0": {k: (round(v_, 3) if isinstance(v_, float) else v_) for k, v_ in eig_phases.items()}}}
     assert err <= 1e-5, rec
     return rec
 

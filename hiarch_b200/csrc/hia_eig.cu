@@ -14,6 +14,7 @@
 // Panels are stored column-major (each vector contiguous, ld = n).
 #include "hia_common.cuh"
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include <stdlib.h>
 
 namespace hia {
@@ -1324,6 +1325,172 @@ long long carve(unsigned char* base, int n, int b, int steps, EigWs* w) {
   return off + 256;
 }
 
+// The same pass with the matrix streamed by TMA: ONE lane per warp issues a 2-D bulk tensor copy of a
+// 4-row x BOXC-column box of C into the warp's shared-memory ring (cp.async.bulk.tensor, completion on an
+// mbarrier); the edge of the matrix is zero-filled by the copy engine, so the per-lane address / bounds
+// arithmetic of the cp.async version (4 copies x ~7 instructions per lane and iteration, ~25 % of that
+// kernel's instructions) disappears. Why it matters: inside the step the pass runs at the ~1.35 GHz the
+// power-capped SYRK leaves behind, where the cp.async kernel's 63 % issue utilisation (at 1.9 GHz, ncu)
+// becomes the limiter. The warp is its own producer and consumer: the box of iteration it + S - 1 is
+// requested right after the lanes are done with iteration it - 1 (its slot), no empty barrier needed.
+__device__ __forceinline__ uint32_t eig_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ bool eig_mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(eig_smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps after ~4 s instead of hanging the GPU box.
+__device__ __forceinline__ void eig_mbar_wait(uint64_t* bar, uint32_t parity) {
+  unsigned int spins = 0;
+  unsigned long long t0 = 0;
+  while (!eig_mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3fffu) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+
+template <int B, int BOXC, int S>
+__global__ void __launch_bounds__(kSymmWarps * 32, 2)
+symm_panel_tma_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int n, const float* __restrict__ v,
+                      double* __restrict__ y, int row_major) {
+  extern __shared__ __align__(128) unsigned char s_tma_raw[];
+  constexpr int kBoxFloats = kSymmRowsPerWarp * BOXC;
+  constexpr int kRingBytes = kSymmWarps * S * kBoxFloats * (int)sizeof(float);
+  float* s_ring = reinterpret_cast<float*>(s_tma_raw);                          // [warp][stage][4][BOXC]
+  float (*s_v)[kSymmCols] = reinterpret_cast<float (*)[kSymmCols]>(s_tma_raw + kRingBytes);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tma_raw + kRingBytes + (size_t)B * kSymmCols * sizeof(float));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * kSymmCols;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSymmWarps * S; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(eig_smem_u32(&s_bar[i])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int idx = threadIdx.x; idx < B * kSymmCols; idx += blockDim.x) {
+    const int j = idx / kSymmCols, col = idx % kSymmCols;
+    s_v[j][col] = (k0 + col < n) ? v[(long long)j * n + k0 + col] : 0.f;
+  }
+  __syncthreads();
+  float* ring = s_ring + (size_t)warp * S * kBoxFloats;
+  uint64_t* bar = s_bar + warp * S;
+  const int rbase = blockIdx.y * kSymmRowsPerCta + warp * (kSymmRowsPerCta / kSymmWarps);
+  constexpr int kGroups = kSymmRowsPerCta / kSymmWarps / kSymmRowsPerWarp;      // 8 row groups per warp
+  constexpr int kBoxes = kSymmCols / BOXC;                                     // boxes per row group
+  constexpr int kIters = kGroups * kBoxes;
+  auto issue = [&](int it) {
+    if (lane == 0 && it < kIters) {
+      const int g = it / kBoxes, bx = it % kBoxes;
+      const int slot = it % S;
+      const uint32_t b = eig_smem_u32(&bar[slot]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                   :: "r"(b), "r"(kBoxFloats * (int)sizeof(float)) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+          :: "r"(eig_smem_u32(ring + (size_t)slot * kBoxFloats)), "l"(&tmap), "r"(b),
+             "r"(k0 + bx * BOXC), "r"(rbase + g * kSymmRowsPerWarp) : "memory");
+    }
+  };
+#pragma unroll
+  for (int it = 0; it < S - 1; ++it) issue(it);
+  float2 acc[kSymmRowsPerWarp][B];
+  for (int it = 0; it < kIters; ++it) {
+    const int g = it / kBoxes, bx = it % kBoxes;
+    if (bx == 0) {
+#pragma unroll
+      for (int r = 0; r < kSymmRowsPerWarp; ++r)
+#pragma unroll
+        for (int j = 0; j < B; ++j) acc[r][j] = make_float2(0.f, 0.f);
+    }
+    __syncwarp();                                        // every lane is done with the slot of iteration it - 1
+    issue(it + S - 1);
+    eig_mbar_wait(&bar[it % S], (uint32_t)((it / S) & 1));
+    const float* src = ring + (size_t)(it % S) * kBoxFloats + lane * 4;
+#pragma unroll 1
+    for (int sub = 0; sub < BOXC / 128; ++sub) {
+      float4 a[kSymmRowsPerWarp];
+#pragma unroll
+      for (int r = 0; r < kSymmRowsPerWarp; ++r) a[r] = *reinterpret_cast<const float4*>(src + r * BOXC + sub * 128);
+      const int cc = bx * BOXC + sub * 128 + lane * 4;
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const float4 vv = *reinterpret_cast<const float4*>(&s_v[j][cc]);
+#pragma unroll
+        for (int r = 0; r < kSymmRowsPerWarp; ++r) {
+          acc[r][j] = ffma2(make_float2(a[r].x, a[r].y), make_float2(vv.x, vv.y), acc[r][j]);
+          acc[r][j] = ffma2(make_float2(a[r].z, a[r].w), make_float2(vv.z, vv.w), acc[r][j]);
+        }
+      }
+    }
+    if (bx == kBoxes - 1) {
+      const int r0 = rbase + g * kSymmRowsPerWarp;
+      float part[kSymmRowsPerWarp * B];
+#pragma unroll
+      for (int r = 0; r < kSymmRowsPerWarp; ++r)
+#pragma unroll
+        for (int j = 0; j < B; ++j) part[r * B + j] = acc[r][j].x + acc[r][j].y;
+      const float total = lane_transpose_sum<kSymmRowsPerWarp * B>(part, lane);
+      const int idx = lane % (kSymmRowsPerWarp * B), r = idx / B, j = idx % B;
+      if (lane < kSymmRowsPerWarp * B && r0 + r < rows) {
+        double* dstp = row_major ? &y[(long long)(r0 + r) * B + j] : &y[(long long)j * rows + r0 + r];
+        atomicAdd(dstp, (double)total);
+      }
+    }
+  }
+}
+
+typedef CUresult (*PFN_eigEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// rows x n fp32 matrix with row stride ld, boxes of kSymmRowsPerWarp rows x boxc columns, no swizzle, zero fill
+int make_matrix_map(CUtensorMap* map, const float* c, int rows, int n, long long ld, int boxc) {
+  static PFN_eigEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !p) { set_last_cuda_error(e); return HIA_ERR_CUDA; }
+    fn = reinterpret_cast<PFN_eigEncodeTiled>(p);
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)boxc, (cuuint32_t)kSymmRowsPerWarp};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(c), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_cuda_error(cudaErrorInvalidValue); return HIA_ERR_CUDA; }
+  return HIA_OK;
+}
+
+template <int B, int BOXC, int S>
+int launch_symm_tma(const float* c, int rows, int n, long long ld, const float* v, double* y, int row_major,
+                    dim3 grid, cudaStream_t s) {
+  constexpr int smem = kSymmWarps * S * kSymmRowsPerWarp * BOXC * (int)sizeof(float) +
+                       B * kSymmCols * (int)sizeof(float) + kSymmWarps * S * (int)sizeof(uint64_t);
+  static bool attr_set = false;                            // once per process and instantiation
+  if (!attr_set) {
+    HIA_CUDA(cudaFuncSetAttribute(symm_panel_tma_kernel<B, BOXC, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  CUtensorMap map;
+  int st = make_matrix_map(&map, c, rows, n, ld, BOXC);
+  if (st != HIA_OK) return st;
+  symm_panel_tma_kernel<B, BOXC, S><<<grid, kSymmWarps * 32, smem, s>>>(map, rows, n, v, y, row_major);
+  count_launch();
+  return cuda_ok(cudaGetLastError());
+}
+
 template <int B>
 int launch_symm(const float* c, int rows, int n, long long ld, const float* v, double* y, int row_major,
                 cudaStream_t s) {
@@ -1339,6 +1506,12 @@ int launch_symm(const float* c, int rows, int n, long long ld, const float* v, d
   }
   const char* e = getenv("HIA_EIG_ASYNC");                 // read per call: tools time both in one process
   const bool use_async = !(e && atoi(e) == 0) && ((reinterpret_cast<uintptr_t>(c) & 15u) == 0) && (ld & 3) == 0;
+  // TMA boxes of 4 rows x 256 columns, 2 slots per warp (default). Measured inside the step at 30 894 bins
+  // (eigen stage, 8 passes): cp.async ring 8.65 ms, this 7.65 ms; 4 x 128 boxes with 4 slots 8.63 ms; 3 slots
+  // of 4 x 256 (one CTA per SM) 9.97 ms. HIA_EIG_TMA=0 keeps the cp.async ring.
+  const char* et = getenv("HIA_EIG_TMA");
+  if (use_async && !(et && atoi(et) == 0))
+    return launch_symm_tma<B, 256, 2>(c, rows, n, ld, v, y, row_major, grid, s);
   if (use_async)
     symm_panel_async_kernel<B><<<grid, kSymmWarps * 32, smem_async, s>>>(c, rows, n, ld, v, y, row_major);
   else

@@ -292,10 +292,11 @@ class RingSimilarity:
 
 
 def topk_eig_rows(c_rows, n, k=3, block=8, steps=19, tol=1e-6, angle_tol=1e-3, max_restarts=8, seed=0,
-                  group=None):
+                  group=None, phases=None):
     """Top-k eigenpairs of the symmetric n x n matrix whose rows [row0, row0 + rows) this rank
     holds in `c_rows` (row layout of ShardedSimilarity). Returns (eigvals [k] fp64 device,
-    eigvecs [n, k] fp32 device, info) -- identical on every rank."""
+    eigvecs [n, k] fp32 device, info) -- identical on every rank. `phases`: a dict that receives
+    the device time per phase in ms (pass / gather / absorb / check / ritz; bench.py)."""
     lib = _lib.load()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -316,14 +317,25 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=19, tol=1e-6, angle_tol=1e-3, m
     conv = ctypes.c_int32(0)
     s = ops._stream
 
+    marks = [] if phases is not None else None
+
+    def mark(name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
     def matvec():
+        mark("other")
         if rows > 0:
             _lib.check(lib.hia_eig_symm_rows(c_rows.data_ptr(), rows, n, c_rows.stride(0), block, steps,
                                              ws.data_ptr(), y_rows.data_ptr(), s()), "hia_eig_symm_rows")
+        mark("pass")
         if world > 1:
             dist.all_gather_into_tensor(y_full.view(-1), y_rows.view(-1), group=group)
         else:
             y_full.copy_(y_rows)
+        mark("gather")
 
     vote = torch.zeros(1, dtype=torch.int32, device=dev)
 
@@ -347,12 +359,15 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=19, tol=1e-6, angle_tol=1e-3, m
             matvec()
             _lib.check(lib.hia_eig_absorb(n, block, steps, j, y_full.data_ptr(), ws.data_ptr(), s()),
                        "hia_eig_absorb")
+            mark("absorb")
             done = j + 1
             if done >= first_check and (done - first_check) % every == 0 and done < steps:
                 # replicated on every rank; the branch is taken by agreement (see agree())
                 _lib.check(lib.hia_eig_check(n, block, steps, done, k, 0.5 * tol, 0.5 * angle_tol,
                                              ctypes.addressof(conv), None, ws.data_ptr(), s()), "hia_eig_check")
-                if agree(conv.value):
+                ok = agree(conv.value)
+                mark("check")
+                if ok:
                     used, reuse = done, 1
                     break
         _lib.check(lib.hia_eig_ritz(n, block, steps, used, reuse, kk, eigvals.data_ptr(), eigvecs.data_ptr(),
@@ -366,14 +381,21 @@ def topk_eig_rows(c_rows, n, k=3, block=8, steps=19, tol=1e-6, angle_tol=1e-3, m
                 dist.broadcast(t, src=src, group=group)
             _lib.check(lib.hia_eig_set_ritz(n, block, steps, kk, eigvecs.data_ptr(), ws.data_ptr(), s()),
                        "hia_eig_set_ritz")
+        mark("ritz")
         matvec()
         _lib.check(lib.hia_eig_resid(n, block, steps, kk, y_full.data_ptr(), eigvals.data_ptr(),
                                      resid.data_ptr(), ws.data_ptr(), s()), "hia_eig_resid")
         r, lam = resid.cpu().numpy()[:k], eigvals.cpu().numpy()[:k]
+        mark("ritz")
         info.append((float(r.max()), float(abs(lam[0])), used))
         if agree(ops.eig_converged(r, lam, gaps.cpu().numpy()[:k], tol, angle_tol)):
             break
         init, n_init = eigvecs.clone(), kk                  # restart from the whole block of Ritz vectors
+    if marks:
+        torch.cuda.synchronize()
+        for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+            phases[name] = phases.get(name, 0.0) + e0.elapsed_time(e1)
+            phases[f"n_{name}"] = phases.get(f"n_{name}", 0) + 1
     return eigvals[:k], eigvecs[:k].t(), info
 
 
@@ -472,8 +494,8 @@ class RowShardedPath:
             self.sim_rows = self.sim.run(self.oe_rows, out_rows=self._out)
         return self.sim_rows
 
-    def eigen(self, tol=1e-6):
-        return topk_eig_rows(self.sim_rows, self.n, k=self.k_eig, tol=tol, group=self.group)
+    def eigen(self, tol=1e-6, phases=None):
+        return topk_eig_rows(self.sim_rows, self.n, k=self.k_eig, tol=tol, group=self.group, phases=phases)
 
     def run(self, count_rows):
         self.normalise(count_rows)

@@ -6,6 +6,7 @@ evaluation of the full symmetric map. Written from the kernel source: it guards 
 lower triangle of the input is NaN-poisoned and must never reach the output)."""
 import numpy as np
 T = 64
+FAST_TILES = []
 def emulate(map_, n, ld, chr_start, bin_chr, inv_expected, inter_inv, n_chr, only_intra, do_log, fill):
     out=np.full((n,ld),np.nan,dtype=np.float32)
     nt=(n+T-1)//T
@@ -14,6 +15,27 @@ def emulate(map_, n, ld, chr_start, bin_chr, inv_expected, inter_inv, n_chr, onl
             if bj<bi: continue
             tile=np.zeros((T,T+1),dtype=np.float32)
             diag_tile = bi==bj
+            # fast path (CTA-uniform): full tile strictly above the diagonal, rows in one chromosome,
+            # columns in ONE OTHER chromosome: one factor, no per-cell look-ups or edge predicates
+            if bi<bj and bj*T+T<=n:
+                ra,rb=bin_chr[bi*T],bin_chr[bi*T+T-1]; ca,cbl=bin_chr[bj*T],bin_chr[bj*T+T-1]
+                if ra==rb and ca==cbl and ra!=ca:
+                    FAST_TILES.append((bi,bj))
+                    f=np.float32(0) if only_intra else np.float32(inter_inv[ra*n_chr+ca])
+                    for tid in range(256):
+                        tx,ty=tid&15,tid>>4
+                        c0=bj*T+4*tx
+                        for k in range(4):
+                            r=bi*T+ty+16*k
+                            for j in range(4):
+                                x=np.float32(np.float32(map_[r,c0+j])*f)
+                                if do_log: x=np.float32(np.log(np.float32(1)+x)) if x>0 else fill
+                                out[r,c0+j]=x; tile[ty+16*k,4*tx+j]=x
+                    for tid in range(256):
+                        tx,ty=tid&15,tid>>4
+                        for k in range(4):
+                            for j in range(4): out[bj*T+ty+16*k,bi*T+4*tx+j]=tile[4*tx+j,ty+16*k]
+                    continue
             # phase 1
             for tid in range(256):
                 tx,ty=tid&15,tid>>4
@@ -66,7 +88,7 @@ def direct(full, n, chr_start, bin_chr, inv_expected, inter_inv, n_chr, only_int
     return out
 def test_upper_apply_kernel_index_logic():
     rng = np.random.default_rng(0)
-    for lens in ([70,45,20],[33],[31,1,64],[64,64],[130,2,61]):
+    for lens in ([70,45,20],[33],[31,1,64],[64,64],[130,2,61],[64,128,70]):
         n=sum(lens); ld=(n+3)//4*4
         chr_start=np.concatenate([[0],np.cumsum(lens)]).astype(int)
         bin_chr=np.repeat(np.arange(len(lens)),lens)
@@ -83,6 +105,7 @@ def test_upper_apply_kernel_index_logic():
                 ref=direct(full,n,chr_start,bin_chr,inv_expected,inter_inv,C,only_intra,do_log,fill)
                 assert not np.isnan(got).any(), (lens,only_intra,do_log)
                 assert np.array_equal(got,ref), (lens,only_intra,do_log,np.abs(got-ref).max())
+    assert (0, 1) in FAST_TILES and (0, 3) in FAST_TILES       # [64,128,70]: tiles that take the fast path
 
 
 # ---------------------------------------------------------------------------------------------

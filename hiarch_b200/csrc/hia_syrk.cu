@@ -466,6 +466,22 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 template <int PREC> struct PlaneT { typedef float type; };
 template <> struct PlaneT<HIA_PREC_3XF16> { typedef __half type; };
 
+// hi/lo planes of a value that already carries the plane's scale (2^14 for fp16, 1 for tf32)
+template <int PREC>
+__device__ __forceinline__ void split_planes(float xs, typename PlaneT<PREC>::type& h, typename PlaneT<PREC>::type& l) {
+  if constexpr (PREC == HIA_PREC_3XF16) {
+    h = __float2half_rn(xs);
+    l = __float2half_rn(xs - __half2float(h));            // the difference is exact in fp32
+  } else {
+    uint32_t hb, lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(xs));
+    h = __uint_as_float(hb);
+    const float rem = xs - h;                             // exact in fp32
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+    l = __uint_as_float(lb);
+  }
+}
+
 template <int PREC>
 __device__ __forceinline__ void split_hi_lo(float xn, typename PlaneT<PREC>::type& h, typename PlaneT<PREC>::type& l) {
   if constexpr (PREC == HIA_PREC_3XF16) {
@@ -488,33 +504,43 @@ __device__ __forceinline__ void split_hi_lo(float xn, typename PlaneT<PREC>::typ
 // first, which is what an LRU-like L2 still holds.
 constexpr int kPrepThreads = 512;
 
+// Instruction budget (ncu, 30 894 bins: 49 % issue utilisation at ~1.9 GHz, i.e. issue-bound at the ~1.35 GHz
+// the step runs at): the first version converted every cell to fp64 twice (statistics pass, then
+// ((double)x - mean) * inv) -- 64-bit conversions and fp64 adds issue at a fraction of the fp32 rate. Now
+// the statistics are fp32 inside a float4 (x - shift, 4-term sum and sum of squares) and fp64 across
+// float4s (one conversion pair per 4 cells; the per-cell roundings are unbiased and average out, ~1e-9 of
+// the row's spread on the mean), and the unit row is ((x - mean_hi) - mean_lo) * inv in fp32 with the mean
+// split into two floats: 2.4e-7 relative per cell, the size of the hi/lo split's own quantisation, random
+// in sign -- the Pearson sum averages it to ~1e-9 (measured stripe error unchanged). fp16 pairs are
+// converted with the packed 2-wide instructions.
 template <int PREC>
 __global__ void __launch_bounds__(kPrepThreads, 4)
 row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int kpad, int center,
                 typename PlaneT<PREC>::type* __restrict__ hi, typename PlaneT<PREC>::type* __restrict__ lo) {
   typedef typename PlaneT<PREC>::type P;
   __shared__ double s_red[kPrepThreads / 32][2];
-  __shared__ double s_val[2];
+  __shared__ float s_val[3];
   const int r = blockIdx.x;
   if (r >= m) return;
   const float* row = x + (long long)r * ld_x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
   // shift by the first element: keeps sum((x - s)^2) - n (mean - s)^2 well conditioned
-  const double shift = (double)row[0];
+  const float shift = row[0];
   double s1 = 0.0, s2 = 0.0;
   const unsigned long long keep = l2_policy_evict_last();
+  auto one = [&](float v) { const float a = v - shift; s1 += (double)a; s2 += (double)(a * a); };
   if (vec_ok) {
     const int k4 = k >> 2;
     for (int j = tid; j < k4; j += blockDim.x) {
       const float4 v = ld_keep4(row + 4 * j, keep);        // stays in L2 for the second pass
-      const double a = (double)v.x - shift, b = (double)v.y - shift, c = (double)v.z - shift, d = (double)v.w - shift;
-      s1 += (a + b) + (c + d);
-      s2 += (a * a + b * b) + (c * c + d * d);
+      const float a = v.x - shift, b = v.y - shift, c = v.z - shift, d = v.w - shift;
+      s1 += (double)((a + b) + (c + d));
+      s2 += (double)((a * a + b * b) + (c * c + d * d));
     }
-    for (int j = (k4 << 2) + tid; j < k; j += blockDim.x) { const double a = (double)row[j] - shift; s1 += a; s2 += a * a; }
+    for (int j = (k4 << 2) + tid; j < k; j += blockDim.x) one(row[j]);
   } else {
-    for (int j = tid; j < k; j += blockDim.x) { const double a = (double)row[j] - shift; s1 += a; s2 += a * a; }
+    for (int j = tid; j < k; j += blockDim.x) one(row[j]);
   }
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
@@ -524,13 +550,18 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
     double t1 = 0, t2 = 0;
     for (int i = 0; i < kPrepThreads / 32; ++i) { t1 += s_red[i][0]; t2 += s_red[i][1]; }
     // Pearson: centre on the mean; cosine: centre on 0 (= shift back)
-    const double mean_s = center ? t1 / (double)k : -shift;      // mean of (x - shift)
+    const double mean_s = center ? t1 / (double)k : -(double)shift;      // mean of (x - shift)
     const double ss = t2 - 2.0 * mean_s * t1 + (double)k * mean_s * mean_s;   // sum (x - shift - mean_s)^2
-    s_val[0] = mean_s + shift;
-    s_val[1] = 1.0 / sqrt(ss > 0.0 ? ss : 0.0);          // inf for an all-zero row -> NaN, like pdist
+    const double mean = mean_s + (double)shift;
+    const double inv = 1.0 / sqrt(ss > 0.0 ? ss : 0.0);  // inf for an all-zero row -> NaN, like pdist
+    const float mean_hi = (float)mean;
+    s_val[0] = mean_hi;
+    s_val[1] = (float)(mean - (double)mean_hi);
+    s_val[2] = (float)(PREC == HIA_PREC_3XF16 ? inv * (double)kF16Scale : inv);   // the fp16 planes hold 2^14 x
   }
   __syncthreads();
-  const double mean = s_val[0], inv = s_val[1];
+  const float mean_hi = s_val[0], mean_lo = s_val[1], inv = s_val[2];
+  auto unit = [&](float v) { return ((v - mean_hi) - mean_lo) * inv; };
   P* ph = hi + (long long)r * kpad;
   P* pl = lo + (long long)r * kpad;
   // second pass, back to front: 4 cells per thread (128-bit loads; 128-/64-bit plane stores; kpad % 4
@@ -539,27 +570,28 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
     const int n4 = kpad >> 2;
     for (int j4 = n4 - 1 - tid; j4 >= 0; j4 -= blockDim.x) {
       const int j = j4 << 2;
-      float xv[4] = {0.f, 0.f, 0.f, 0.f};
+      float xs[4] = {0.f, 0.f, 0.f, 0.f};
       if (j + 3 < k) {
         const float4 v = ld_last4(row + j);                  // last use: evict first
-        xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
+        xs[0] = unit(v.x); xs[1] = unit(v.y); xs[2] = unit(v.z); xs[3] = unit(v.w);
       } else {
-        for (int e = 0; e < 4; ++e) if (j + e < k) xv[e] = row[j + e];
-      }
-      P h[4], l[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (j + e < k) {
-          split_hi_lo<PREC>((float)(((double)xv[e] - mean) * inv), h[e], l[e]);
-        } else {
-          h[e] = P(0.f); l[e] = P(0.f);
-        }
+        for (int e = 0; e < 4; ++e) if (j + e < k) xs[e] = unit(row[j + e]);   // beyond k: zero padding
       }
       // streaming stores: the planes must not evict the rows that still wait for their second pass
       if constexpr (PREC == HIA_PREC_3XF16) {
-        st_cs_u2(ph + j, *reinterpret_cast<const uint2*>(h));
-        st_cs_u2(pl + j, *reinterpret_cast<const uint2*>(l));
+        const __half2 h01 = __floats2half2_rn(xs[0], xs[1]), h23 = __floats2half2_rn(xs[2], xs[3]);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(xs[0] - f01.x, xs[1] - f01.y);   // the differences are exact in fp32
+        const __half2 l23 = __floats2half2_rn(xs[2] - f23.x, xs[3] - f23.y);
+        uint2 qh, ql;
+        qh.x = *reinterpret_cast<const unsigned int*>(&h01); qh.y = *reinterpret_cast<const unsigned int*>(&h23);
+        ql.x = *reinterpret_cast<const unsigned int*>(&l01); ql.y = *reinterpret_cast<const unsigned int*>(&l23);
+        st_cs_u2(ph + j, qh);
+        st_cs_u2(pl + j, ql);
       } else {
+        P h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_planes<PREC>(xs[e], h[e], l[e]);
         st_cs_f4(ph + j, *reinterpret_cast<const float4*>(h));
         st_cs_f4(pl + j, *reinterpret_cast<const float4*>(l));
       }
@@ -567,7 +599,7 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
   } else {
     for (int j = kpad - 1 - tid; j >= 0; j -= blockDim.x) {
       P h = P(0.f), l = P(0.f);
-      if (j < k) split_hi_lo<PREC>((float)(((double)row[j] - mean) * inv), h, l);
+      if (j < k) split_planes<PREC>(unit(row[j]), h, l);
       ph[j] = h;
       pl[j] = l;
     }

@@ -183,6 +183,8 @@ row_ptr_kernel(const int* __restrict__ rows, long long nnz, int n, long long* __
     } else {
       for (int i = 0; i < 4; ++i) rv[i] = (e0 + i < nnz) ? rows[e0 + i] : 0;
     }
+    // (taking the entry before the group from the neighbouring lane's registers -- a shuffle instead of this
+    //  scalar load -- measured 0.1 ms SLOWER in-step: the load overlaps the 128-bit one, the shuffle waits for it)
     int prev = (e0 > 0) ? rows[e0 - 1] : -1;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -200,6 +202,12 @@ row_ptr_kernel(const int* __restrict__ rows, long long nnz, int n, long long* __
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
+// HIA_FILL_ATOMIC=1: the all-atomic fill for every row (A/B timing; read per call)
+inline bool fill_atomic_only() {
+  const char* e = getenv("HIA_FILL_ATOMIC");
+  return e && atoi(e) == 1;
+}
+
 constexpr int kSegCols = 16384;              // 64 KB of shared memory per CTA, 3 CTAs per SM
 constexpr int kSegThreads = 512;
 
@@ -208,6 +216,91 @@ __device__ __forceinline__ int4 load_cols4(const int* p) { return *reinterpret_c
 __device__ __forceinline__ int4 load_cols4(const unsigned short* p) {
   const uint2 t = *reinterpret_cast<const uint2*>(p);
   return make_int4((int)(t.x & 0xffffu), (int)(t.x >> 16), (int)(t.y & 0xffffu), (int)(t.y >> 16));
+}
+
+// The default fill. One CTA per (row, 16 384-column segment): the segment is built in shared memory and
+// written with 128-bit stores. Entries whose columns increase STRICTLY inside the row (what a sorted COO /
+// canonical CSR holds) hit distinct cells, so they are placed with plain shared-memory stores; every entry
+// is compared with its predecessor on the way, and a row that breaks the order (duplicates, unsorted
+// columns) is redone by the same CTA with shared-memory atomics -- a CTA-local decision, both segment
+// CTAs of a row see the same entries. Why: a shared-memory float atomicAdd is a compare-and-swap loop
+// (~8 instructions + replays); ncu showed the all-atomic kernel (fill_rows_sorted_kernel below, still used
+// for the fused statistics) at 36 % issue utilisation and 44 ... 57 % of DRAM peak, issue-bound at the
+// clock the step runs at. The buffer is shifted by the 16-byte phase of the output segment so that the
+// write-out is aligned 128-bit shared loads + 128-bit global stores.
+template <typename CT>
+__global__ void __launch_bounds__(kSegThreads)
+fill_rows_fast_kernel(const CT* __restrict__ cols, const float* __restrict__ vals,
+                      const long long* __restrict__ row_ptr, const int* __restrict__ flag, int n,
+                      long long ld, int mtx_type, float* __restrict__ out) {
+  extern __shared__ __align__(16) float s_buf[];            // kSegCols + 4 floats
+  if (flag && *flag) return;                               // rows not sorted: the any-order kernels do the work
+  const int segs = (n + kSegCols - 1) / kSegCols;
+  const int r = blockIdx.x / segs;
+  const int c_lo = (mtx_type == HIA_MTX_TRIU) ? r : 0;     // a 'triu' row starts on the diagonal
+  const int seg_lo = c_lo + (blockIdx.x % segs) * kSegCols;
+  if (seg_lo >= n) return;
+  const int seg_n = min(kSegCols, n - seg_lo);
+  const long long e0 = row_ptr[r], e1 = row_ptr[r + 1];    // in flight while the buffer is zeroed
+  const int off = (int)(((long long)r * ld + seg_lo) & 3);  // cell i of the segment lives in s_buf[i + off]
+  float* s_row = s_buf + off;
+  const int nq = (off + seg_n + 3) >> 2;                   // float4 groups of the buffer in use
+  float4* s_q = reinterpret_cast<float4*>(s_buf);
+  for (int i = threadIdx.x; i < nq; i += blockDim.x) s_q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  // the row's entries: scalar head up to a 16-byte boundary, 128-bit body (two groups in flight), scalar tail
+  const long long a0 = min(e1, (e0 + 3) & ~3ll), a1 = max(a0, e1 & ~3ll);
+  bool bad = false;
+  auto put = [&](int prev, int c, float v) {
+    bad |= (c <= prev);
+    c -= seg_lo;
+    if (c >= 0 && c < seg_n) s_row[c] = v;
+  };
+  auto before = [&](long long e) { return e > e0 ? (int)cols[e - 1] : -1; };
+  for (long long e = e0 + threadIdx.x; e < a0; e += blockDim.x) put(before(e), (int)cols[e], vals[e]);
+  const long long ng = (a1 - a0) >> 2;
+  long long g = threadIdx.x;
+  for (; g + blockDim.x < ng; g += 2 * blockDim.x) {
+    const long long g1 = g + blockDim.x;
+    const int4 c0 = load_cols4(cols + a0 + 4 * g);
+    const float4 v0 = *reinterpret_cast<const float4*>(vals + a0 + 4 * g);
+    const int4 c1 = load_cols4(cols + a0 + 4 * g1);
+    const float4 v1 = *reinterpret_cast<const float4*>(vals + a0 + 4 * g1);
+    const int p0 = before(a0 + 4 * g), p1 = before(a0 + 4 * g1);
+    put(p0, c0.x, v0.x); put(c0.x, c0.y, v0.y); put(c0.y, c0.z, v0.z); put(c0.z, c0.w, v0.w);
+    put(p1, c1.x, v1.x); put(c1.x, c1.y, v1.y); put(c1.y, c1.z, v1.z); put(c1.z, c1.w, v1.w);
+  }
+  for (; g < ng; g += blockDim.x) {
+    const int4 c0 = load_cols4(cols + a0 + 4 * g);
+    const float4 v0 = *reinterpret_cast<const float4*>(vals + a0 + 4 * g);
+    const int p0 = before(a0 + 4 * g);
+    put(p0, c0.x, v0.x); put(c0.x, c0.y, v0.y); put(c0.y, c0.z, v0.z); put(c0.z, c0.w, v0.w);
+  }
+  for (long long e = a1 + threadIdx.x; e < e1; e += blockDim.x) put(before(e), (int)cols[e], vals[e]);
+  if (__syncthreads_or(bad)) {
+    // duplicates or unsorted columns in this row: redo the segment with atomics
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) s_q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+      const int c = (int)cols[e] - seg_lo;
+      if (c >= 0 && c < seg_n) atomicAdd(&s_row[c], vals[e]);
+    }
+    __syncthreads();
+  }
+  // write-out: buffer group q <-> cells 4 q - off ... 4 q - off + 3 of the segment (16-byte aligned in `out`)
+  float* dst = out + (long long)r * ld + seg_lo;
+  for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+    const int i0 = 4 * q - off;
+    const float4 v = s_q[q];
+    if (i0 >= 0 && i0 + 3 < seg_n) {
+      *reinterpret_cast<float4*>(dst + i0) = v;
+    } else {
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (i0 + j >= 0 && i0 + j < seg_n) dst[i0 + j] = e[j];
+    }
+  }
 }
 
 // CT = int (COO / CSR with 32-bit columns) or unsigned short (CSR with 16-bit columns, n <= 65 536:
@@ -603,6 +696,8 @@ static int scatter_coo_impl(const int32_t* rows, const int32_t* cols, const floa
                                      kSegCols * (int)sizeof(float))));
       HIA_CUDA((cudaFuncSetAttribute(fill_rows_sorted_kernel<int, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kSegCols * (int)sizeof(float))));
+      HIA_CUDA((cudaFuncSetAttribute(fill_rows_fast_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (kSegCols + 4) * (int)sizeof(float))));
       attr_set = true;
     }
     dim3 grid_f((unsigned)n * ((n + kSegCols - 1) / kSegCols), 1);
@@ -611,9 +706,12 @@ static int scatter_coo_impl(const int32_t* rows, const int32_t* cols, const floa
     if (stats)
       fill_rows_sorted_kernel<int, true><<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(
           cols, vals, row_ptr, flag, n, ld, mtx_type, out, *stats);
-    else
+    else if (fill_atomic_only())
       fill_rows_sorted_kernel<int, false><<<grid_f, kSegThreads, kSegCols * sizeof(float), stream>>>(
           cols, vals, row_ptr, flag, n, ld, mtx_type, out, InterStats{});
+    else
+      fill_rows_fast_kernel<int><<<grid_f, kSegThreads, (kSegCols + 4) * sizeof(float), stream>>>(
+          cols, vals, row_ptr, flag, n, ld, mtx_type, out);
     HIA_LAUNCH_CHECK();
     // (a 4096-row grid of CTAs that only read the flag and exit cost 69 us per call: launch list r1)
     dim3 grid_z((n + threads * 4 - 1) / (threads * 4), min(n, 64));
@@ -716,6 +814,9 @@ static int scatter_csr_impl(const int64_t* row_ptr, const void* cols, int col_by
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
     HIA_CUDA((cudaFuncSetAttribute(fill_rows_sorted_kernel<unsigned short, true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
+    HIA_CUDA((cudaFuncSetAttribute(fill_rows_fast_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 16)));
+    HIA_CUDA((cudaFuncSetAttribute(fill_rows_fast_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   bytes + 16)));
     attr_set = true;
   }
   dim3 grid_f((unsigned)n * ((n + kSegCols - 1) / kSegCols), 1);
@@ -725,12 +826,18 @@ static int scatter_csr_impl(const int64_t* row_ptr, const void* cols, int col_by
   if (col_bytes == 4 && stats)
     fill_rows_sorted_kernel<int, true><<<grid_f, kSegThreads, sh, stream>>>(static_cast<const int*>(cols), vals, rp,
                                                                             nullptr, n, ld, mt, out, *stats);
+  else if (col_bytes == 4 && !fill_atomic_only())
+    fill_rows_fast_kernel<int><<<grid_f, kSegThreads, sh + 16, stream>>>(static_cast<const int*>(cols), vals, rp, nullptr,
+                                                                         n, ld, mt, out);
   else if (col_bytes == 4)
     fill_rows_sorted_kernel<int, false><<<grid_f, kSegThreads, sh, stream>>>(static_cast<const int*>(cols), vals, rp,
                                                                              nullptr, n, ld, mt, out, none);
   else if (stats)
     fill_rows_sorted_kernel<unsigned short, true><<<grid_f, kSegThreads, sh, stream>>>(
         static_cast<const unsigned short*>(cols), vals, rp, nullptr, n, ld, mt, out, *stats);
+  else if (!fill_atomic_only())
+    fill_rows_fast_kernel<unsigned short><<<grid_f, kSegThreads, sh + 16, stream>>>(
+        static_cast<const unsigned short*>(cols), vals, rp, nullptr, n, ld, mt, out);
   else
     fill_rows_sorted_kernel<unsigned short, false><<<grid_f, kSegThreads, sh, stream>>>(
         static_cast<const unsigned short*>(cols), vals, rp, nullptr, n, ld, mt, out, none);

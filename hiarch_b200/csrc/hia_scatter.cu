@@ -186,6 +186,10 @@ row_ptr_kernel(const int* __restrict__ rows, long long nnz, int n, long long* __
     // (taking the entry before the group from the neighbouring lane's registers -- a shuffle instead of this
     //  scalar load -- measured 0.1 ms SLOWER in-step: the load overlaps the 128-bit one, the shuffle waits for it)
     int prev = (e0 > 0) ? rows[e0 - 1] : -1;
+    // the common group: all four entries continue the previous entry's row and none of them is the last entry
+    // -- nothing to record. (A run of one invalid row index starts in a group that takes the slow path: its
+    // first entry differs from its predecessor, or it is entry 0 whose predecessor is -1.)
+    if (e0 + 4 < nnz && prev >= 0 && ((rv[0] ^ prev) | (rv[1] ^ prev) | (rv[2] ^ prev) | (rv[3] ^ prev)) == 0) continue;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const long long e = e0 + i;
@@ -235,10 +239,15 @@ fill_rows_fast_kernel(const CT* __restrict__ cols, const float* __restrict__ val
                       long long ld, int mtx_type, float* __restrict__ out) {
   extern __shared__ __align__(16) float s_buf[];            // kSegCols + 4 floats
   if (flag && *flag) return;                               // rows not sorted: the any-order kernels do the work
+  // (all loops below run on 32-bit indices with the compile-time stride kSegThreads: with blockDim.x and 64-bit
+  //  entry indices the compiler's unrolling computed every trip count by an emulated division -- a third of the
+  //  kernel's instructions for loops of ~8 iterations)
+  constexpr int T = kSegThreads;
+  const int tid = threadIdx.x;
   const int segs = (n + kSegCols - 1) / kSegCols;
   const int r = blockIdx.x / segs;
   const int c_lo = (mtx_type == HIA_MTX_TRIU) ? r : 0;     // a 'triu' row starts on the diagonal
-  const int seg_lo = c_lo + (blockIdx.x % segs) * kSegCols;
+  const int seg_lo = c_lo + (blockIdx.x - r * segs) * kSegCols;
   if (seg_lo >= n) return;
   const int seg_n = min(kSegCols, n - seg_lo);
   const long long e0 = row_ptr[r], e1 = row_ptr[r + 1];    // in flight while the buffer is zeroed
@@ -246,59 +255,65 @@ fill_rows_fast_kernel(const CT* __restrict__ cols, const float* __restrict__ val
   float* s_row = s_buf + off;
   const int nq = (off + seg_n + 3) >> 2;                   // float4 groups of the buffer in use
   float4* s_q = reinterpret_cast<float4*>(s_buf);
-  for (int i = threadIdx.x; i < nq; i += blockDim.x) s_q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < nq; i += T) s_q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  // the row's entries: scalar head up to a 16-byte boundary, 128-bit body (two groups in flight), scalar tail
-  const long long a0 = min(e1, (e0 + 3) & ~3ll), a1 = max(a0, e1 & ~3ll);
+  // the row's entries (a row holds < 2^31 of them): scalar head up to a 16-byte boundary, 128-bit body (two
+  // groups in flight), scalar tail; indices relative to the row's first entry
+  const CT* rc = cols + e0;
+  const float* rv = vals + e0;
+  const int len = (int)(e1 - e0);
+  const int h = min(len, (int)((4 - (e0 & 3)) & 3));       // entries before the first 16-byte aligned one
+  const int ng = (len - h) >> 2;                           // aligned groups of 4
+  const int t0 = h + 4 * ng;                               // first tail entry
   bool bad = false;
   auto put = [&](int prev, int c, float v) {
     bad |= (c <= prev);
     c -= seg_lo;
     if (c >= 0 && c < seg_n) s_row[c] = v;
   };
-  auto before = [&](long long e) { return e > e0 ? (int)cols[e - 1] : -1; };
-  for (long long e = e0 + threadIdx.x; e < a0; e += blockDim.x) put(before(e), (int)cols[e], vals[e]);
-  const long long ng = (a1 - a0) >> 2;
-  long long g = threadIdx.x;
-  for (; g + blockDim.x < ng; g += 2 * blockDim.x) {
-    const long long g1 = g + blockDim.x;
-    const int4 c0 = load_cols4(cols + a0 + 4 * g);
-    const float4 v0 = *reinterpret_cast<const float4*>(vals + a0 + 4 * g);
-    const int4 c1 = load_cols4(cols + a0 + 4 * g1);
-    const float4 v1 = *reinterpret_cast<const float4*>(vals + a0 + 4 * g1);
-    const int p0 = before(a0 + 4 * g), p1 = before(a0 + 4 * g1);
+  auto before = [&](int e) { return e > 0 ? (int)rc[e - 1] : -1; };
+  if (tid < h) put(before(tid), (int)rc[tid], rv[tid]);
+  int g = tid;
+  for (; g + T < ng; g += 2 * T) {
+    const int ea = h + 4 * g, eb = ea + 4 * T;
+    const int4 c0 = load_cols4(rc + ea);
+    const float4 v0 = *reinterpret_cast<const float4*>(rv + ea);
+    const int4 c1 = load_cols4(rc + eb);
+    const float4 v1 = *reinterpret_cast<const float4*>(rv + eb);
+    const int p0 = before(ea), p1 = before(eb);
     put(p0, c0.x, v0.x); put(c0.x, c0.y, v0.y); put(c0.y, c0.z, v0.z); put(c0.z, c0.w, v0.w);
     put(p1, c1.x, v1.x); put(c1.x, c1.y, v1.y); put(c1.y, c1.z, v1.z); put(c1.z, c1.w, v1.w);
   }
-  for (; g < ng; g += blockDim.x) {
-    const int4 c0 = load_cols4(cols + a0 + 4 * g);
-    const float4 v0 = *reinterpret_cast<const float4*>(vals + a0 + 4 * g);
-    const int p0 = before(a0 + 4 * g);
+  if (g < ng) {
+    const int ea = h + 4 * g;
+    const int4 c0 = load_cols4(rc + ea);
+    const float4 v0 = *reinterpret_cast<const float4*>(rv + ea);
+    const int p0 = before(ea);
     put(p0, c0.x, v0.x); put(c0.x, c0.y, v0.y); put(c0.y, c0.z, v0.z); put(c0.z, c0.w, v0.w);
   }
-  for (long long e = a1 + threadIdx.x; e < e1; e += blockDim.x) put(before(e), (int)cols[e], vals[e]);
+  if (t0 + tid < len) put(before(t0 + tid), (int)rc[t0 + tid], rv[t0 + tid]);
   if (__syncthreads_or(bad)) {
     // duplicates or unsorted columns in this row: redo the segment with atomics
-    for (int i = threadIdx.x; i < nq; i += blockDim.x) s_q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < nq; i += T) s_q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-      const int c = (int)cols[e] - seg_lo;
-      if (c >= 0 && c < seg_n) atomicAdd(&s_row[c], vals[e]);
+    for (int e = tid; e < len; e += T) {
+      const int c = (int)rc[e] - seg_lo;
+      if (c >= 0 && c < seg_n) atomicAdd(&s_row[c], rv[e]);
     }
     __syncthreads();
   }
   // write-out: buffer group q <-> cells 4 q - off ... 4 q - off + 3 of the segment (16-byte aligned in `out`)
-  float* dst = out + (long long)r * ld + seg_lo;
-  for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+  float* dst = out + (long long)r * ld + seg_lo - off;
+  for (int q = tid; q < nq; q += T) {
     const int i0 = 4 * q - off;
     const float4 v = s_q[q];
     if (i0 >= 0 && i0 + 3 < seg_n) {
-      *reinterpret_cast<float4*>(dst + i0) = v;
+      *reinterpret_cast<float4*>(dst + 4 * q) = v;
     } else {
       const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (i0 + j >= 0 && i0 + j < seg_n) dst[i0 + j] = e[j];
+        if (i0 + j >= 0 && i0 + j < seg_n) dst[4 * q + j] = e[j];
     }
   }
 }

@@ -532,15 +532,15 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
   auto one = [&](float v) { const float a = v - shift; s1 += (double)a; s2 += (double)(a * a); };
   if (vec_ok) {
     const int k4 = k >> 2;
-    for (int j = tid; j < k4; j += blockDim.x) {
+    for (int j = tid; j < k4; j += kPrepThreads) {
       const float4 v = ld_keep4(row + 4 * j, keep);        // stays in L2 for the second pass
       const float a = v.x - shift, b = v.y - shift, c = v.z - shift, d = v.w - shift;
       s1 += (double)((a + b) + (c + d));
       s2 += (double)((a * a + b * b) + (c * c + d * d));
     }
-    for (int j = (k4 << 2) + tid; j < k; j += blockDim.x) one(row[j]);
+    for (int j = (k4 << 2) + tid; j < k; j += kPrepThreads) one(row[j]);
   } else {
-    for (int j = tid; j < k; j += blockDim.x) one(row[j]);
+    for (int j = tid; j < k; j += kPrepThreads) one(row[j]);
   }
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
@@ -568,7 +568,7 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
   // == 0 and the plane rows are 16-byte aligned by construction)
   if (vec_ok) {
     const int n4 = kpad >> 2;
-    for (int j4 = n4 - 1 - tid; j4 >= 0; j4 -= blockDim.x) {
+    for (int j4 = n4 - 1 - tid; j4 >= 0; j4 -= kPrepThreads) {
       const int j = j4 << 2;
       float xs[4] = {0.f, 0.f, 0.f, 0.f};
       if (j + 3 < k) {
@@ -597,7 +597,7 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
       }
     }
   } else {
-    for (int j = kpad - 1 - tid; j >= 0; j -= blockDim.x) {
+    for (int j = kpad - 1 - tid; j >= 0; j -= kPrepThreads) {
       P h = P(0.f), l = P(0.f);
       if (j < k) split_planes<PREC>(unit(row[j]), h, l);
       ph[j] = h;

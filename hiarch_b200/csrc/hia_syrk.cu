@@ -27,7 +27,8 @@
 // plane bytes. The epilogue rescales by 2^-28 (exact).
 //
 // 3xTF32 error budget: |hi.hi + hi.lo + lo.hi - x.y| <= ~2^-21 |x||y| per product; fp32
-// accumulation over <= k_chunk/8 MMA steps, then RN fp32 adds of <= k/k_chunk partials.
+// accumulation over <= k_chunk/8 MMA steps in TMEM (truncating: the bias grows with the chunk), then
+// an EXACT fixed-point fold of the <= k/k_chunk partials in the epilogue registers (see there).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -46,6 +47,8 @@ __host__ __device__ constexpr int bk_of(int prec) { return prec == HIA_PREC_3XF1
 __host__ __device__ constexpr int elem_bytes(int prec) { return prec == HIA_PREC_3XF16 ? 2 : 4; }
 constexpr float kF16Scale = 16384.f;                         // 2^14
 constexpr float kF16Unscale = 1.f / (16384.f * 16384.f);     // 2^-28
+constexpr float kFixScale = 16384.f * 16384.f;               // tf32 planes are unscaled: partials x 2^28 before the fixed-point fold
+constexpr int kFixNaN = (int)0x80000000;                     // fixed-point marker of a NaN sum
 constexpr int EPI_WARPS = 8;                   // 2 per TMEM lane quarter x 128 columns each
 constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr int TRANS_PAD = 33;
@@ -372,20 +375,39 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     uint32_t chunk_it = 0;
     for (int t = unit; t < num_tiles; t += num_units) {
       const int m0 = tiles[t].m0 + (int)cta_rank * BM, n0 = tiles[t].n0 + half * (BN / 2);
-      float accr[BN / 2];
+      // The chunk partials are folded in FIXED POINT: unit rows give |sum| <= 1, i.e. <= 2^28 in the planes'
+      // 2^14 x 2^14 scale, so an int32 with a resolution of 2^-28 (3.7e-9) holds the running sum and the adds
+      // are exact; each partial is rounded to that grid once (<= 1.9e-9, unbiased). An fp32 running sum
+      // loses up to half an ulp of the SUM per add, and on sparse high-resolution maps the partials of one
+      // cell are nearly equal from chunk to chunk (the rows are mostly one repeated background value), so
+      // those roundings do not average out: 241 folds x 3e-8 = 7e-6 at 25 kb (tools/accuracy_split.py:
+      // fold 3.8e-6 mean / 6.8e-6 max of a 1.1e-5 total at k_chunk 512; 1.6e-5 mean at k_chunk 128).
+      // A NaN partial (all-zero row: every chunk is NaN) is caught on the last chunk and kept as INT_MIN.
+      int accr[BN / 2];
 #pragma unroll
-      for (int j = 0; j < BN / 2; ++j) accr[j] = 0.f;
+      for (int j = 0; j < BN / 2; ++j) accr[j] = 0;
       for (int ch = 0; ch < chunks_per_tile; ++ch, ++chunk_it) {
         const uint32_t buf = chunk_it & 1, tph = (chunk_it >> 1) & 1;
         mbar_wait(&tfull_bar[buf], tph);
         tcgen05_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * (BN / 2);
+        const bool last = ch == chunks_per_tile - 1;
 #pragma unroll
         for (int cg = 0; cg < BN / 64; ++cg) {
           uint32_t v[32];
           tmem_ld32(taddr0 + cg * 32, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) accr[cg * 32 + j] += __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) {
+            const float pv = (PREC == HIA_PREC_3XF16) ? __uint_as_float(v[j]) : __uint_as_float(v[j]) * kFixScale;
+            accr[cg * 32 + j] += __float2int_rn(pv);
+          }
+          if (last) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float pv = __uint_as_float(v[j]);
+              if (pv != pv) accr[cg * 32 + j] = kFixNaN;
+            }
+          }
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -411,7 +433,8 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float raw = (PREC == HIA_PREC_3XF16) ? accr[cg * 32 + j] * kF16Unscale : accr[cg * 32 + j];
+            const int fx = accr[cg * 32 + j];
+            const float raw = (fx == kFixNaN) ? __int_as_float(0x7fc00000) : (float)fx * kF16Unscale;
             float c = fminf(1.f, fmaxf(-1.f, raw));         // |cos| clipped to 1 like scipy
             if (raw != raw) c = raw;                        // NaN stays NaN
             f[j] = (flavour == HIA_SIM_PEARSON) ? c : (1.f - c);

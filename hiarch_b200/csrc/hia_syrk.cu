@@ -548,8 +548,20 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
   const float* row = x + (long long)r * ld_x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
-  // shift by the first element: keeps sum((x - s)^2) - n (mean - s)^2 well conditioned
-  const float shift = row[0];
+  // Shift by an ESTIMATE OF THE MEAN (32 cells spread over the row, warp 0): sum((x - s)^2) - n (mean - s)^2
+  // cancels by a factor ((mean - s) / sigma)^2, and with fp32 squares the rounding of the (repeated)
+  // background value of a sparse row is the same in every cell -- with s = row[0] (a count cell, several sigma
+  // from the mean) that put 1e-6 into the norm of 25 kb rows (tools/accuracy_split.py: representation error
+  // 8e-7 mean / 3.6e-6 max against 6e-9 with fp64 squares).
+  __shared__ float s_shift;
+  if (w == 0) {
+    float v = row[(int)(((long long)lane * k) >> 5)];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_shift = (v == v && fabsf(v) < INFINITY) ? v * (1.f / 32.f) : row[0];
+  }
+  __syncthreads();
+  const float shift = s_shift;
   double s1 = 0.0, s2 = 0.0;
   const unsigned long long keep = l2_policy_evict_last();
   auto one = [&](float v) { const float a = v - shift; s1 += (double)a; s2 += (double)(a * a); };

@@ -47,7 +47,10 @@ __host__ __device__ constexpr int bk_of(int prec) { return prec == HIA_PREC_3XF1
 __host__ __device__ constexpr int elem_bytes(int prec) { return prec == HIA_PREC_3XF16 ? 2 : 4; }
 constexpr float kF16Scale = 16384.f;                         // 2^14
 constexpr float kF16Unscale = 1.f / (16384.f * 16384.f);     // 2^-28
-constexpr float kFixScale = 16384.f * 16384.f;               // tf32 planes are unscaled: partials x 2^28 before the fixed-point fold
+// fixed-point fold of the chunk partials: |sum| <= 1 (unit rows) is held as an int32 in units of 2^-30
+template <int PREC> struct FixScale { static constexpr float value = 1073741824.f; };          // tf32 planes: x 2^30
+template <> struct FixScale<HIA_PREC_3XF16> { static constexpr float value = 4.f; };          // fp16 planes carry 2^28
+constexpr float kFixUnscale = 1.f / 1073741824.f;            // 2^-30
 constexpr int kFixNaN = (int)0x80000000;                     // fixed-point marker of a NaN sum
 constexpr int EPI_WARPS = 8;                   // 2 per TMEM lane quarter x 128 columns each
 constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
@@ -375,13 +378,14 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     uint32_t chunk_it = 0;
     for (int t = unit; t < num_tiles; t += num_units) {
       const int m0 = tiles[t].m0 + (int)cta_rank * BM, n0 = tiles[t].n0 + half * (BN / 2);
-      // The chunk partials are folded in FIXED POINT: unit rows give |sum| <= 1, i.e. <= 2^28 in the planes'
-      // 2^14 x 2^14 scale, so an int32 with a resolution of 2^-28 (3.7e-9) holds the running sum and the adds
-      // are exact; each partial is rounded to that grid once (<= 1.9e-9, unbiased). An fp32 running sum
-      // loses up to half an ulp of the SUM per add, and on sparse high-resolution maps the partials of one
-      // cell are nearly equal from chunk to chunk (the rows are mostly one repeated background value), so
-      // those roundings do not average out: 241 folds x 3e-8 = 7e-6 at 25 kb (tools/accuracy_split.py:
-      // fold 3.8e-6 mean / 6.8e-6 max of a 1.1e-5 total at k_chunk 512; 1.6e-5 mean at k_chunk 128).
+      // The chunk partials are folded in FIXED POINT: unit rows give |sum| <= 1, so an int32 in units of 2^-30
+      // (9.3e-10) holds the running sum and the adds are exact; each partial is rounded to that grid once
+      // (<= 4.7e-10). An fp32 running sum loses up to half an ulp of the SUM (3e-8) per add, and between
+      // neighbouring rows of a sparse high-resolution map that does not average out: the few chunks near the
+      // diagonal carry almost all of the sum, and the hundreds of small, nearly equal background partials
+      // that follow fall below half an ulp of it and are rounded away one after the other
+      // (tools/accuracy_split.py at 25 kb: fold 3.8e-6 mean / 6.8e-6 max of a 1.1e-5 total at k_chunk 512,
+      // 1.6e-5 mean at k_chunk 128 -- a shorter chunk made it worse).
       // A NaN partial (all-zero row: every chunk is NaN) is caught on the last chunk and kept as INT_MIN.
       int accr[BN / 2];
 #pragma unroll
@@ -398,8 +402,7 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
           tmem_ld32(taddr0 + cg * 32, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float pv = (PREC == HIA_PREC_3XF16) ? __uint_as_float(v[j]) : __uint_as_float(v[j]) * kFixScale;
-            accr[cg * 32 + j] += __float2int_rn(pv);
+            accr[cg * 32 + j] += __float2int_rn(__uint_as_float(v[j]) * FixScale<PREC>::value);
           }
           if (last) {
 #pragma unroll
@@ -434,7 +437,7 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int fx = accr[cg * 32 + j];
-            const float raw = (fx == kFixNaN) ? __int_as_float(0x7fc00000) : (float)fx * kF16Unscale;
+            const float raw = (fx == kFixNaN) ? __int_as_float(0x7fc00000) : (float)fx * kFixUnscale;
             float c = fminf(1.f, fmaxf(-1.f, raw));         // |cos| clipped to 1 like scipy
             if (raw != raw) c = raw;                        // NaN stays NaN
             f[j] = (flavour == HIA_SIM_PEARSON) ? c : (1.f - c);

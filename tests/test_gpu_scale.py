@@ -1,7 +1,7 @@
 """GPU parity at the BASELINE.json config sizes (C2: genome-wide 100 kb, 30 894 bins; C4: chr1 at
 10 kb, 24 896 bins) -- the sizes `bench.py` reports on, not the toy sizes of test_gpu_parity.py.
-Row-sharded C5 (123 541 bins) is checked in-run by `bench.py --gpus N` (fp64 spot check asserted)
-and at reduced size by tests/test_gpu_multi.py.
+Row-sharded C5 (123 541 bins) is checked in-run by `bench.py --gpus N` (fp64 spot check recorded), at
+reduced size by tests/test_gpu_multi.py, and at the full ROW LENGTH on one GPU here (a 768-row block).
 
 Oracle comparisons are made on sub-blocks the numpy oracle finishes in seconds:
   C2  O/E+log of the chr21 and chr22 intra blocks and the chr21 x chr22 inter block (<= 1e-5);
@@ -9,6 +9,10 @@ Oracle comparisons are made on sub-blocks the numpy oracle finishes in seconds:
       GPU's own correlation map (|cos| >= 0.9999).
   C4  O/E+log of the whole chr1 block -- the only config where the `dis >= bin_size` lookup quirk of
       ScaledGenomicDistance fires (new_hic_class.py:865-875) -- and `get_local` on a 5 000-bin block.
+  C5  a 768-row block inside chr1 at 25 kb (rows of 123 541 cells): count rows -> O/E + log -> the row
+      prep and the tcgen05 block product of the sharded path (`hia_sim_prep_rows` / `hia_sim_gemm_block`)
+      against torch fp64. Neighbouring rows of one chromosome (|rho| > 0.5 for half the entries) are the
+      hardest entries for the 3-term fp16 split; the budget is 1e-5, measured 3.3e-6.
 """
 import numpy as np
 import pytest
@@ -166,3 +170,48 @@ def test_c4_get_local_on_a_5k_block_against_the_oracle(c4):
     ref = O.get_local(oe.cpu().numpy().astype(np.float64), 5000)
     assert got is not None and ref is not None
     assert abs(got - ref) <= 1e-4 * abs(ref), (got, ref)
+
+
+@pytest.mark.timeout(300)
+def test_c5_row_length_pearson_block_against_fp64():
+    """K = 123 541 (genome-wide 25 kb), 768 neighbouring rows of chr1: the accuracy of the K-chunked
+    tcgen05 accumulation with its fixed-point fold, and of the row prep, on the sparse rows of a
+    high-resolution count map (the first version of either put > 1e-5 into this block)."""
+    from hiarch_b200 import _lib, ops
+    from hiarch_b200.sharded import obs_d_exp_rows
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    res, m, row0 = 25000, 768, 1000
+    lens = [n for _, n in synth.hg38_bins(res)]
+    n = int(sum(lens))
+    layout = ops.GenomeLayout(synth.chr_seps_from_lens(lens), dev)
+    counts, _ = synth.device_count_rows(lens, row0, m, 5, dev)
+    oe, _ = obs_d_exp_rows(counts, layout, res, row0)        # statistics of these rows only: fine for the purpose
+    del counts
+    a = oe.double()
+    a = a - a.mean(dim=1, keepdim=True)
+    a = a / a.norm(dim=1, keepdim=True)
+    ref = (a @ a.t()).clamp(-1.0, 1.0)
+    ref.fill_diagonal_(1.0)
+    del a
+    prec = ops.PREC_3XF16
+    kpad = lib.hia_sim_kpad(n, prec)
+    planes = torch.zeros((2, m, kpad), dtype=torch.float16, device=dev)
+    _lib.check(lib.hia_sim_prep_rows(oe.data_ptr(), m, n, oe.stride(0), ops.SIM_PEARSON, prec, planes[0].data_ptr(),
+                                     planes[1].data_ptr(), ops._stream()), "hia_sim_prep_rows")
+    # the planes alone: exact products in fp64 (22 + 22 bits) against the reference -> the representation error
+    hi, lo = planes[0, :64].double(), planes[1, :64].double()
+    rep = (hi @ hi.t() + hi @ lo.t() + lo @ hi.t()) * 2.0 ** -28
+    assert float((rep - ref[:64, :64]).abs().max()) <= 5e-7
+    ws = torch.empty(lib.hia_sim_gemm_rows_workspace_bytes(m, n), dtype=torch.uint8, device=dev)
+    ld = ops.padded_ld(m)
+    c = torch.zeros((m, ld), dtype=torch.float32, device=dev)
+    _lib.check(lib.hia_sim_gemm_block(planes[0].data_ptr(), planes[1].data_ptr(), m, planes[0].data_ptr(),
+                                      planes[1].data_ptr(), m, prec, n, 0, m, 0, m, 1, c.data_ptr(), ld,
+                                      c.data_ptr(), ld, ops.SIM_PEARSON, 0, ws.data_ptr(), ws.numel(), ops._stream()),
+               "hia_sim_gemm_block")
+    torch.cuda.synchronize()
+    err = (c[:, :m].double() - ref).abs()
+    assert float((ref.abs() > 0.5).double().mean()) > 0.3       # the block IS the hard case
+    assert float(err.max()) <= 6e-6, float(err.max())           # budget 1e-5; measured 3.3e-6
+    assert float(err.mean()) <= 2e-6

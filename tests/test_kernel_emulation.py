@@ -177,3 +177,95 @@ def test_symm_upper_pass_index_logic():
             y = emulate_symm_upper(poisoned, v)
         assert not np.isnan(y).any(), n
         assert np.abs(y - full @ v).max() < 1e-9, n
+
+
+# ---------------------------------------------------------------------------------------------
+# Numerics of the similarity path on SPARSE high-resolution rows (csrc/hia_syrk.cu), emulated in numpy
+# from the kernel source: (1) row_prep_kernel's statistics -- fp32 inside a float4, fp64 across float4s,
+# shifted by a 32-cell mean estimate -- and its fp32 unit row with a two-float mean; (2) the epilogue's
+# fixed-point fold of the K-chunk partials. Both guard regressions that cost > 1e-5 at 25 kb on the GPU
+#  and cannot be seen on the small dense maps of the other tests.
+# ---------------------------------------------------------------------------------------------
+def _sparse_rows(n, seed, first):
+    rng = np.random.default_rng(seed)
+    base = rng.poisson(0.04, n) * (1.0 + rng.random(n))            # shared structure -> |rho| large
+    out = []
+    for _ in range(2):
+        x = np.log1p(base + rng.poisson(0.01, n) * rng.random(n))
+        x[x == 0] = np.log1p(0.0371)                                # the repeated background value
+        x[0] = first                                                # the first cell is a count cell
+        out.append(x.astype(np.float32))
+    return out
+
+
+def _prep_emulated(x, shift_mode):
+    n = x.size
+    f32 = np.float32
+    if shift_mode == "sampled":
+        idx = (np.arange(32, dtype=np.int64) * n) >> 5
+        shift = f32(np.float32(x[idx].astype(np.float32).sum(dtype=np.float32)) * f32(1.0 / 32.0))
+    else:
+        shift = x[0]
+    a = (x - shift).astype(f32)
+    k4 = n // 4
+    g = a[:k4 * 4].reshape(-1, 4)
+    p1 = ((g[:, 0] + g[:, 1]).astype(f32) + (g[:, 2] + g[:, 3]).astype(f32)).astype(f32)
+    sq = (g * g).astype(f32)
+    p2 = ((sq[:, 0] + sq[:, 1]).astype(f32) + (sq[:, 2] + sq[:, 3]).astype(f32)).astype(f32)
+    tail = a[k4 * 4:]
+    t1 = p1.astype(np.float64).sum() + tail.astype(np.float64).sum()
+    t2 = p2.astype(np.float64).sum() + (tail * tail).astype(f32).astype(np.float64).sum()
+    ms = t1 / n
+    ss = t2 - 2.0 * ms * t1 + n * ms * ms
+    mean = ms + float(shift)
+    inv = 1.0 / np.sqrt(ss)
+    mh = f32(mean)
+    ml = f32(mean - float(mh))
+    invs = f32(inv * 16384.0)
+    xs = (((x - mh).astype(f32) - ml).astype(f32) * invs).astype(f32)
+    hi = xs.astype(np.float16)
+    lo = (xs - hi.astype(f32)).astype(f32).astype(np.float16)
+    return hi.astype(np.float64), lo.astype(np.float64)
+
+
+def _exact_unit(x):
+    d = x.astype(np.float64)
+    d = d - d.mean()
+    return d / np.sqrt((d * d).sum())
+
+
+def test_row_prep_numerics_on_sparse_rows():
+    n = 123541
+    worst = {"sampled": 0.0, "first_cell": 0.0}
+    for first in (2.5, 1.9, 3.3, 4.1, 2.2, 2.9):                    # the rounding of (background - shift)^2 is a lottery
+        xa, xb = _sparse_rows(n, 3, first)
+        rho = float(_exact_unit(xa) @ _exact_unit(xb))
+        assert abs(rho) > 0.5
+        for mode in worst:
+            (ha, la), (hb, lb) = _prep_emulated(xa, mode), _prep_emulated(xb, mode)
+            got = float((ha @ hb + ha @ lb + la @ hb) * 2.0 ** -28)  # exact products of the planes
+            worst[mode] = max(worst[mode], abs(got - rho))
+    assert worst["sampled"] <= 2e-7, worst                          # GPU, 25 kb: 2.7e-8 mean / 1.0e-7 max
+    assert worst["first_cell"] >= 3 * worst["sampled"], worst       # what the first version did (GPU: 8e-7 / 3.6e-6)
+
+
+def test_fixed_point_fold_keeps_the_small_partials():
+    """The chunk partials of one cell between neighbouring rows of a sparse 25 kb map (k_chunk 128 ... 512 at
+    K = 123 541): a few chunks near the diagonal carry almost all of the sum, hundreds of small, nearly
+    equal background partials follow. A sequential fp32 fold rounds each of those away (they are below half
+    an ulp of the sum); the int32 fold in units of 2^-30 that the epilogue does keeps them."""
+    rng = np.random.default_rng(0)
+    worst32, worst_fix = 0.0, 0.0
+    for rho, n_chunks, small in ((0.93, 965, 3.7), (0.61, 965, 5.2), (-0.77, 241, -6.3), (0.66, 241, 7.9)):
+        big = np.array([0.2, 0.5, 0.3]) * rho * 2.0 ** 28             # the planes' 2^14 x 2^14 scale
+        part = np.concatenate([big, small * (1.0 + 0.02 * rng.standard_normal(n_chunks - 3))])
+        exact = part.sum() * 2.0 ** -28
+        acc = np.float32(0.0)
+        fx = 0
+        for p in part.astype(np.float32):
+            acc = np.float32(acc + p)
+            fx += int(np.rint(np.float32(p * np.float32(4.0))))      # __float2int_rn(partial * 4): exact integer adds
+        worst32 = max(worst32, abs(float(acc) * 2.0 ** -28 - exact))
+        worst_fix = max(worst_fix, abs(float(np.float32(fx)) * 2.0 ** -30 - exact))
+    assert worst_fix <= 3.5e-7, worst_fix          # <= 1/8 unit of 2^-28 per partial when they all round the same way
+    assert worst32 >= 3e-6, worst32                # the stagnation the first version of the epilogue had

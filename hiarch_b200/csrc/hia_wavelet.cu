@@ -310,9 +310,12 @@ int64_t band_stride(const Plan& p, int l) { return ((int64_t)p.r[l] * p.c[l] + 3
 
 int upload_filters() {
   static std::mutex mu;
-  static bool done = false;
+  static bool done_on[64] = {};                            // __constant__ memory is per device
+  int dev = 0;
+  HIA_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lock(mu);
-  if (done) return HIA_OK;
+  const bool tracked = dev >= 0 && dev < 64;
+  if (tracked && done_on[dev]) return HIA_OK;
   const double s10 = sqrt(10.0), s5 = sqrt(5.0 + 2.0 * s10), den = 16.0 * sqrt(2.0);
   const double h[kF] = {(1 + s10 + s5) / den, (5 + s10 + 3 * s5) / den, (10 - 2 * s10 + 2 * s5) / den,
                         (10 - 2 * s10 - 2 * s5) / den, (5 + s10 - 3 * s5) / den, (1 + s10 - s5) / den};
@@ -326,7 +329,7 @@ int upload_filters() {
   }
   for (int j = 0; j < kF; ++j) f[3][j] = f[1][kF - 1 - j];      // rec_hi
   HIA_CUDA(cudaMemcpyToSymbol(c_filt, f, sizeof(f)));
-  done = true;
+  if (tracked) done_on[dev] = true;
   return HIA_OK;
 }
 

@@ -1125,12 +1125,12 @@ static int launch_gemm(const GemmJob& j, cudaStream_t stream) {
   if (st != HIA_OK) return st;
 
   const int bk = bk_of(j.prec);
-  // measured on B200 (3xTF32): k_chunk 256 -> 1.6e-6 max abs err (1024: 5e-6, unchunked: 1e-4). The
-  // error grows with the number of MMA steps in one TMEM chain; fp16 steps cover twice the K.
-  // (Default 512 for fp16: 3e-7 measured on the 100 kb count map at K = 30 894, 3.8e-6 / 8.0e-6 on sampled
-  //  entries of the 50 / 25 kb count maps (bench.py row_sharded.fp64_spot_check). 256 was NOT better on
-  //  those maps -- 5.5e-6 at 50 kb -- so the error there is not the in-chunk truncation alone.
-  //  HIA_K_CHUNK overrides the default for sweeps.)
+  // The TMEM accumulate truncates, so its bias grows with the length of one chain: K = 20 000 in one chain gave
+  // 1e-4. With the exact fixed-point fold of the chunk partials in the epilogue the error is proportional to
+  // k_chunk and to nothing else -- 3xF16, neighbouring rows of a 25 kb count map (K = 123 541, |rho| ~ 0.67),
+  // max / mean abs error: 1024 -> 6.1e-6 / 1.9e-6, 512 -> 3.0e-6 / 9.2e-7, 256 -> 1.6e-6 / 4.3e-7 (+3.5 %
+  // kernel time), 128 -> 1.0e-6 / 2.7e-7 (epilogue-bound, +44 %); 100 kb (K = 30 894): 2.8e-7 at 512.
+  // HIA_K_CHUNK overrides the default for sweeps (tools/accuracy_probe.py).
   static const int env_chunk = getenv("HIA_K_CHUNK") ? atoi(getenv("HIA_K_CHUNK")) : 0;
   const int k_chunk = j.k_chunk > 0 ? j.k_chunk
                                     : (env_chunk > 0 ? env_chunk : (j.prec == HIA_PREC_3XF16 ? 512 : 256));

@@ -539,12 +539,12 @@ constexpr int kPrepThreads = 512;
 // split into two floats: 2.4e-7 relative per cell, the size of the hi/lo split's own quantisation, random
 // in sign -- the Pearson sum averages it to ~1e-9 (measured stripe error unchanged). fp16 pairs are
 // converted with the packed 2-wide instructions.
-template <int PREC>
-__global__ void __launch_bounds__(kPrepThreads, 4)
+template <int PREC, int THREADS = kPrepThreads>
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS)
 row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int kpad, int center,
                 typename PlaneT<PREC>::type* __restrict__ hi, typename PlaneT<PREC>::type* __restrict__ lo) {
   typedef typename PlaneT<PREC>::type P;
-  __shared__ double s_red[kPrepThreads / 32][2];
+  __shared__ double s_red[THREADS / 32][2];
   __shared__ float s_val[3];
   const int r = blockIdx.x;
   if (r >= m) return;
@@ -570,15 +570,15 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
   auto one = [&](float v) { const float a = v - shift; s1 += (double)a; s2 += (double)(a * a); };
   if (vec_ok) {
     const int k4 = k >> 2;
-    for (int j = tid; j < k4; j += kPrepThreads) {
+    for (int j = tid; j < k4; j += THREADS) {
       const float4 v = ld_keep4(row + 4 * j, keep);        // stays in L2 for the second pass
       const float a = v.x - shift, b = v.y - shift, c = v.z - shift, d = v.w - shift;
       s1 += (double)((a + b) + (c + d));
       s2 += (double)((a * a + b * b) + (c * c + d * d));
     }
-    for (int j = (k4 << 2) + tid; j < k; j += kPrepThreads) one(row[j]);
+    for (int j = (k4 << 2) + tid; j < k; j += THREADS) one(row[j]);
   } else {
-    for (int j = tid; j < k; j += kPrepThreads) one(row[j]);
+    for (int j = tid; j < k; j += THREADS) one(row[j]);
   }
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
@@ -586,7 +586,7 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
   __syncthreads();
   if (tid == 0) {
     double t1 = 0, t2 = 0;
-    for (int i = 0; i < kPrepThreads / 32; ++i) { t1 += s_red[i][0]; t2 += s_red[i][1]; }
+    for (int i = 0; i < THREADS / 32; ++i) { t1 += s_red[i][0]; t2 += s_red[i][1]; }
     // Pearson: centre on the mean; cosine: centre on 0 (= shift back)
     const double mean_s = center ? t1 / (double)k : -(double)shift;      // mean of (x - shift)
     const double ss = t2 - 2.0 * mean_s * t1 + (double)k * mean_s * mean_s;   // sum (x - shift - mean_s)^2
@@ -606,7 +606,7 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
   // == 0 and the plane rows are 16-byte aligned by construction)
   if (vec_ok) {
     const int n4 = kpad >> 2;
-    for (int j4 = n4 - 1 - tid; j4 >= 0; j4 -= kPrepThreads) {
+    for (int j4 = n4 - 1 - tid; j4 >= 0; j4 -= THREADS) {
       const int j = j4 << 2;
       float xs[4] = {0.f, 0.f, 0.f, 0.f};
       if (j + 3 < k) {
@@ -635,7 +635,7 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
       }
     }
   } else {
-    for (int j = kpad - 1 - tid; j >= 0; j -= kPrepThreads) {
+    for (int j = kpad - 1 - tid; j >= 0; j -= THREADS) {
       P h = P(0.f), l = P(0.f);
       if (j < k) split_planes<PREC>(unit(row[j]), h, l);
       ph[j] = h;
@@ -888,7 +888,14 @@ int launch_prep(const float* x, int rows, int k, long long ld_x, int center, voi
     HIA_CUDA(cudaFuncSetAttribute(row_prep_kernel<HIA_PREC_3XF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     HIA_CUDA(cudaFuncSetAttribute(row_prep_kernel<HIA_PREC_3XTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
-  if (prec == HIA_PREC_3XF16)
+  // long rows: 1024-thread CTAs, 2 per SM -- the same threads per SM with half the rows in flight, so more of
+  // the second pass hits L2 (30 894 bins: 1.61 against 1.63 ms in-step; HIA_PREP_THREADS=512 keeps the small CTAs)
+  const char* e_thr = getenv("HIA_PREP_THREADS");
+  const bool big_ctas = e_thr ? atoi(e_thr) == 1024 : k >= 16384;
+  if (prec == HIA_PREC_3XF16 && big_ctas && !pad)
+    row_prep_kernel<HIA_PREC_3XF16, 1024><<<rows, 1024, 0, stream>>>(x, rows, k, ld_x, kpad, center,
+                                                                     static_cast<__half*>(hi), static_cast<__half*>(lo));
+  else if (prec == HIA_PREC_3XF16)
     row_prep_kernel<HIA_PREC_3XF16><<<rows, kPrepThreads, pad, stream>>>(x, rows, k, ld_x, kpad, center,
                                                                static_cast<__half*>(hi), static_cast<__half*>(lo));
   else

@@ -269,3 +269,103 @@ def test_fixed_point_fold_keeps_the_small_partials():
         worst_fix = max(worst_fix, abs(float(np.float32(fx)) * 2.0 ** -30 - exact))
     assert worst_fix <= 3.5e-7, worst_fix          # <= 1/8 unit of 2^-28 per partial when they all round the same way
     assert worst32 >= 3e-6, worst32                # the stagnation the first version of the epilogue had
+
+
+# ---------------------------------------------------------------------------------------------
+# fill_rows_fast_kernel (csrc/hia_scatter.cu): the index logic of one (row, segment) CTA, emulated from the
+# kernel source -- the entries of the row split into a scalar head up to the first 16-byte aligned entry,
+# aligned groups of four and a scalar tail; plain stores while the columns increase strictly, the segment
+# redone with adds otherwise; the segment buffer shifted by the 16-byte phase of the output segment and
+# written out in aligned float4 groups with masked edges. NaN-poisoned output: a cell the kernel must
+# write and does not, or an entry it reads outside its row, shows up.
+# ---------------------------------------------------------------------------------------------
+SEG = 16384
+
+
+def emulate_fill_rows_fast(cols, vals, row_ptr, n, ld, triu, seg=SEG, threads=512):
+    out = np.full((n, ld), np.nan, dtype=np.float32)
+    flat = out.reshape(-1)
+    segs = -(-n // seg)
+    for block in range(n * segs):
+        r = block // segs
+        c_lo = r if triu else 0
+        seg_lo = c_lo + (block - r * segs) * seg
+        if seg_lo >= n:
+            continue
+        seg_n = min(seg, n - seg_lo)
+        e0, e1 = int(row_ptr[r]), int(row_ptr[r + 1])
+        off = (r * ld + seg_lo) & 3
+        nq = (off + seg_n + 3) >> 2
+        buf = np.zeros(4 * nq, dtype=np.float32)
+        rc, rv = cols[e0:e1], vals[e0:e1]
+        length = e1 - e0
+        h = min(length, (4 - (e0 & 3)) & 3)
+        ng = (length - h) >> 2
+        t0 = h + 4 * ng
+        bad = False
+        seen = np.zeros(length, dtype=bool)                     # every entry of the row is visited exactly once
+
+        def put(prev, c, v):
+            nonlocal bad
+            bad |= c <= prev
+            c -= seg_lo
+            if 0 <= c < seg_n:
+                buf[off + c] = v
+
+        def before(e):
+            return int(rc[e - 1]) if e > 0 else -1
+
+        for tid in range(min(threads, 4)):                      # head: tid < h
+            if tid < h:
+                put(before(tid), int(rc[tid]), rv[tid]); seen[tid] = True
+        for g in range(ng):                                     # body (any thread / iteration order: distinct cells)
+            ea = h + 4 * g
+            assert (e0 + ea) % 4 == 0                           # the 128-bit loads are aligned
+            prev = before(ea)
+            for j in range(4):
+                put(prev, int(rc[ea + j]), rv[ea + j]); seen[ea + j] = True
+                prev = int(rc[ea + j])
+        for tid in range(min(threads, 4)):                      # tail: t0 + tid < len
+            if t0 + tid < length:
+                put(before(t0 + tid), int(rc[t0 + tid]), rv[t0 + tid]); seen[t0 + tid] = True
+        assert seen.all() and length - t0 < 4
+        if bad:
+            buf[:] = 0
+            for e in range(length):
+                c = int(rc[e]) - seg_lo
+                if 0 <= c < seg_n:
+                    buf[off + c] += rv[e]
+        base = r * ld + seg_lo - off
+        assert base % 4 == 0                                    # aligned 128-bit stores
+        for q in range(nq):
+            i0 = 4 * q - off
+            for j in range(4):
+                if 0 <= i0 + j < seg_n:
+                    flat[base + 4 * q + j] = buf[4 * q + j]
+    return out
+
+
+def test_fill_rows_fast_index_logic():
+    rng = np.random.default_rng(1)
+    for n, ld, seg in ((37, 40, 16), (64, 64, 16), (50, 52, 64), (33, 36, 8)):
+        for triu in (True, False):
+            dense = np.zeros((n, n), dtype=np.float32)
+            rows_l, cols_l, vals_l = [], [], []
+            for r in range(n):
+                k = int(rng.integers(0, n))
+                cs = np.sort(rng.choice(n, size=k, replace=False)) if r % 5 else rng.integers(0, n, size=k)   # some rows unsorted / with duplicates
+                for c in cs:
+                    v = np.float32(rng.integers(1, 9))
+                    rows_l.append(r); cols_l.append(int(c)); vals_l.append(v)
+                    if not triu or c >= r:
+                        dense[r, c] += v
+            cols = np.array(cols_l, dtype=np.int32); vals = np.array(vals_l, dtype=np.float32)
+            row_ptr = np.searchsorted(np.array(rows_l), np.arange(n + 1)).astype(np.int64)
+            got = emulate_fill_rows_fast(cols, vals, row_ptr, n, ld, triu, seg=seg)
+            lo = np.arange(n)[:, None] > np.arange(n)[None, :]
+            if triu:                                            # a 'triu' row starts on the diagonal: cells left of it are not written
+                assert np.isnan(got[:, :n][lo]).all()
+                assert np.array_equal(got[:, :n][~lo], dense[~lo]), (n, ld, seg)
+            else:
+                assert np.array_equal(got[:, :n], dense), (n, ld, seg)
+            assert np.isnan(got[:, n:]).all()                   # the padding columns are never touched

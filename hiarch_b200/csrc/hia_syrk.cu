@@ -21,10 +21,11 @@
 //   lower triangle is written as the exact mirror, the diagonal as the exact constant.
 //
 // HIA_PREC_3XF16: the same split on kind::f16 -- fp16 has the SAME 11-bit significand as TF32, so
-// hi = fp16(S xn), lo = fp16(S xn - hi) (S = 2^14, exact; |xn| <= 1 keeps hi finite) carry the same
+// hi = fp16(S xn), lo = fp16(S xn - hi) (S = 2^15, exact; |xn| <= 1 keeps hi finite) carry the same
 // 22 bits, the products are exact in fp32, and one MMA instruction covers K = 16 instead of 8 in
 // the same 128 cycles and the same 12 KB of shared-memory operands: half the MMA time, half the
-// plane bytes. The epilogue rescales by 2^-28 (exact).
+// plane bytes. The products carry 2^30 -- the unit of the epilogue's fixed-point fold -- and the epilogue
+// rescales by 2^-30 (exact).
 //
 // 3xTF32 error budget: |hi.hi + hi.lo + lo.hi - x.y| <= ~2^-21 |x||y| per product; fp32
 // accumulation over <= k_chunk/8 MMA steps in TMEM (truncating: the bias grows with the chunk), then
@@ -45,11 +46,10 @@ constexpr int A_BYTES = BM * ROW_BYTES;        // 16 KB
 // elements per k-block: 32 (tf32 planes, fp32 storage) or 64 (fp16 planes)
 __host__ __device__ constexpr int bk_of(int prec) { return prec == HIA_PREC_3XF16 ? 64 : 32; }
 __host__ __device__ constexpr int elem_bytes(int prec) { return prec == HIA_PREC_3XF16 ? 2 : 4; }
-constexpr float kF16Scale = 16384.f;                         // 2^14
-constexpr float kF16Unscale = 1.f / (16384.f * 16384.f);     // 2^-28
+constexpr float kF16Scale = 32768.f;                         // 2^15: products of two planes carry 2^30
 // fixed-point fold of the chunk partials: |sum| <= 1 (unit rows) is held as an int32 in units of 2^-30
 template <int PREC> struct FixScale { static constexpr float value = 1073741824.f; };          // tf32 planes: x 2^30
-template <> struct FixScale<HIA_PREC_3XF16> { static constexpr float value = 4.f; };          // fp16 planes carry 2^28
+template <> struct FixScale<HIA_PREC_3XF16> { static constexpr float value = 1.f; };          // fp16 planes carry 2^30
 constexpr float kFixUnscale = 1.f / 1073741824.f;            // 2^-30
 constexpr int kFixNaN = (int)0x80000000;                     // fixed-point marker of a NaN sum
 constexpr int EPI_WARPS = 8;                   // 2 per TMEM lane quarter x 128 columns each
@@ -402,7 +402,9 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
           tmem_ld32(taddr0 + cg * 32, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            accr[cg * 32 + j] += __float2int_rn(__uint_as_float(v[j]) * FixScale<PREC>::value);
+            accr[cg * 32 + j] += (FixScale<PREC>::value == 1.f)
+                                     ? __float2int_rn(__uint_as_float(v[j]))
+                                     : __float2int_rn(__uint_as_float(v[j]) * FixScale<PREC>::value);
           }
           if (last) {
 #pragma unroll
@@ -488,11 +490,11 @@ syrk_split3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 // ------------------------------------------------------------------ row prologue
 // One CTA per row: fp64 sum and sum of squares in ONE pass (128-bit loads; the row then sits in
 // L1/L2), mean / norm, then the hi/lo planes of the unit row in a second pass
-// (TF32-exact fp32 planes, or fp16 planes of the row scaled by 2^14).
+// (TF32-exact fp32 planes, or fp16 planes of the row scaled by 2^15).
 template <int PREC> struct PlaneT { typedef float type; };
 template <> struct PlaneT<HIA_PREC_3XF16> { typedef __half type; };
 
-// hi/lo planes of a value that already carries the plane's scale (2^14 for fp16, 1 for tf32)
+// hi/lo planes of a value that already carries the plane's scale (2^15 for fp16, 1 for tf32)
 template <int PREC>
 __device__ __forceinline__ void split_planes(float xs, typename PlaneT<PREC>::type& h, typename PlaneT<PREC>::type& l) {
   if constexpr (PREC == HIA_PREC_3XF16) {
@@ -595,7 +597,7 @@ row_prep_kernel(const float* __restrict__ x, int m, int k, long long ld_x, int k
     const float mean_hi = (float)mean;
     s_val[0] = mean_hi;
     s_val[1] = (float)(mean - (double)mean_hi);
-    s_val[2] = (float)(PREC == HIA_PREC_3XF16 ? inv * (double)kF16Scale : inv);   // the fp16 planes hold 2^14 x
+    s_val[2] = (float)(PREC == HIA_PREC_3XF16 ? inv * (double)kF16Scale : inv);   // the fp16 planes hold 2^15 x
   }
   __syncthreads();
   const float mean_hi = s_val[0], mean_lo = s_val[1], inv = s_val[2];

@@ -210,7 +210,7 @@ int hia_log_map(const float* x, float* out, int32_t rows, int32_t cols, int64_t 
 #define HIA_SIM_CORRELATION_DISTANCE 2   /* out = 1 - corr, exact 0 diagonal (pdist 'correlation') */
 #define HIA_PREC_3XTF32 0           /* tcgen05 kind::tf32, hi/lo split, fp32 accumulate    */
 #define HIA_PREC_FP64 1             /* FP64 DMMA (mma.sync m8n8k4), fp64 accumulate        */
-#define HIA_PREC_3XF16 2            /* tcgen05 kind::f16, hi/lo split of the row scaled by 2^14 (fp16 has
+#define HIA_PREC_3XF16 2            /* tcgen05 kind::f16, hi/lo split of the row scaled by 2^15 (fp16 has
                                        TF32's 11-bit significand: same 22 bits, K = 16 per MMA instead of
                                        8 -> half the tensor time and half the plane bytes), fp32 accumulate */
 /* X is m x k (ld_x), out is m x m (ld_out). band_lo/band_hi (in bins, band_hi < 0 = all):

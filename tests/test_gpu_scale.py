@@ -201,7 +201,7 @@ def test_c5_row_length_pearson_block_against_fp64():
                                      planes[1].data_ptr(), ops._stream()), "hia_sim_prep_rows")
     # the planes alone: exact products in fp64 (22 + 22 bits) against the reference -> the representation error
     hi, lo = planes[0, :64].double(), planes[1, :64].double()
-    rep = (hi @ hi.t() + hi @ lo.t() + lo @ hi.t()) * 2.0 ** -28
+    rep = (hi @ hi.t() + hi @ lo.t() + lo @ hi.t()) * 2.0 ** -30
     assert float((rep - ref[:64, :64]).abs().max()) <= 5e-7
     ws = torch.empty(lib.hia_sim_gemm_rows_workspace_bytes(m, n), dtype=torch.uint8, device=dev)
     ld = ops.padded_ld(m)

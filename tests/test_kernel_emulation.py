@@ -221,7 +221,7 @@ def _prep_emulated(x, shift_mode):
     inv = 1.0 / np.sqrt(ss)
     mh = f32(mean)
     ml = f32(mean - float(mh))
-    invs = f32(inv * 16384.0)
+    invs = f32(inv * 32768.0)
     xs = (((x - mh).astype(f32) - ml).astype(f32) * invs).astype(f32)
     hi = xs.astype(np.float16)
     lo = (xs - hi.astype(f32)).astype(f32).astype(np.float16)
@@ -243,7 +243,7 @@ def test_row_prep_numerics_on_sparse_rows():
         assert abs(rho) > 0.5
         for mode in worst:
             (ha, la), (hb, lb) = _prep_emulated(xa, mode), _prep_emulated(xb, mode)
-            got = float((ha @ hb + ha @ lb + la @ hb) * 2.0 ** -28)  # exact products of the planes
+            got = float((ha @ hb + ha @ lb + la @ hb) * 2.0 ** -30)  # exact products of the planes
             worst[mode] = max(worst[mode], abs(got - rho))
     assert worst["sampled"] <= 2e-7, worst                          # GPU, 25 kb: 2.7e-8 mean / 1.0e-7 max
     assert worst["first_cell"] >= 3 * worst["sampled"], worst       # what the first version did (GPU: 8e-7 / 3.6e-6)
@@ -256,18 +256,18 @@ def test_fixed_point_fold_keeps_the_small_partials():
     an ulp of the sum); the int32 fold in units of 2^-30 that the epilogue does keeps them."""
     rng = np.random.default_rng(0)
     worst32, worst_fix = 0.0, 0.0
-    for rho, n_chunks, small in ((0.93, 965, 3.7), (0.61, 965, 5.2), (-0.77, 241, -6.3), (0.66, 241, 7.9)):
-        big = np.array([0.2, 0.5, 0.3]) * rho * 2.0 ** 28             # the planes' 2^14 x 2^14 scale
+    for rho, n_chunks, small in ((0.93, 965, 14.8), (0.61, 965, 20.8), (-0.77, 241, -25.2), (0.66, 241, 31.6)):
+        big = np.array([0.2, 0.5, 0.3]) * rho * 2.0 ** 30             # the planes' 2^15 x 2^15 scale
         part = np.concatenate([big, small * (1.0 + 0.02 * rng.standard_normal(n_chunks - 3))])
-        exact = part.sum() * 2.0 ** -28
+        exact = part.sum() * 2.0 ** -30
         acc = np.float32(0.0)
         fx = 0
         for p in part.astype(np.float32):
             acc = np.float32(acc + p)
-            fx += int(np.rint(np.float32(p * np.float32(4.0))))      # __float2int_rn(partial * 4): exact integer adds
-        worst32 = max(worst32, abs(float(acc) * 2.0 ** -28 - exact))
+            fx += int(np.rint(p))                                    # __float2int_rn(partial): exact integer adds
+        worst32 = max(worst32, abs(float(acc) * 2.0 ** -30 - exact))
         worst_fix = max(worst_fix, abs(float(np.float32(fx)) * 2.0 ** -30 - exact))
-    assert worst_fix <= 3.5e-7, worst_fix          # <= 1/8 unit of 2^-28 per partial when they all round the same way
+    assert worst_fix <= 3.5e-7, worst_fix          # <= half a unit of 2^-30 per partial when they all round the same way
     assert worst32 >= 3e-6, worst32                # the stagnation the first version of the epilogue had
 
 

@@ -52,11 +52,11 @@ def main():
             prod = hi[i] * hi[j] + hi[i] * lo[j] + lo[i] * hi[j]            # exact in fp64 (22 + 22 bits)
             prod = torch.nn.functional.pad(prod, (0, nch * k_chunk - kpad))
             part = prod.view(nch, k_chunk).sum(dim=1).cpu().numpy()          # fp64 partials
-            exact = part.sum() * 2.0 ** -28
+            exact = part.sum() * 2.0 ** -30
             acc = np.float32(0)
             for p in part:
                 acc = np.float32(acc + np.float32(p))
-            fold = float(acc) * 2.0 ** -28
+            fold = float(acc) * 2.0 ** -30
             gpu = float(c[i, j])
             r = float(ref[i, j])
             e_repr.append(exact - r); e_fold.append(fold - exact); e_mma.append(gpu - fold); e_tot.append(gpu - r)

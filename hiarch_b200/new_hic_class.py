@@ -125,10 +125,17 @@ class GenomeIndex:
             ni = (idx[m] - lo) // condense_fold + current
             new_index[m] = ni
             current = int(ni.max()) + 1
-        tmp = pd.DataFrame({'chr': chrs, 'start': df['start'].values, 'end': df['end'].values,
-                            'new_index': new_index})
-        grp = tmp.groupby('new_index')
-        new_df = pd.DataFrame({'chr': grp['chr'].min(), 'start': grp['start'].min(), 'end': grp['end'].max()})
+        # groupby('new_index'): chr min / start min / end max per coarse bin. A coarse bin never spans two
+        # chromosomes (`current` restarts per chromosome), so the min over its equal names is any of them;
+        # done with reduceat on the bins sorted by coarse index (pandas falls back to a per-group Python loop
+        # for the string column: 0.13 s of a 0.6 s NormDis step at 6 895 bins).
+        order = np.argsort(new_index, kind='stable')
+        ni_sorted = new_index[order]
+        first = np.flatnonzero(np.r_[True, ni_sorted[1:] != ni_sorted[:-1]])
+        new_df = pd.DataFrame({'chr': chrs[order][first],
+                               'start': np.minimum.reduceat(df['start'].values[order], first),
+                               'end': np.maximum.reduceat(df['end'].values[order], first)},
+                              index=pd.Index(ni_sorted[first], name='new_index'))
         new_df['index'] = new_df.index
         trans = np.full(int(idx.max()) + 1, -1, dtype=np.int64)
         trans[idx] = new_index

@@ -369,3 +369,95 @@ def test_fill_rows_fast_index_logic():
             else:
                 assert np.array_equal(got[:, :n], dense), (n, ld, seg)
             assert np.isnan(got[:, n:]).all()                   # the padding columns are never touched
+
+
+# ---------------------------------------------------------------------------------------------
+# dwt2_fwd_kernel / dwt2_inv_kernel (csrc/hia_wavelet.cu): the tile index logic, emulated from the kernel
+# source against oracle/wavelet_oracle.py -- forward: a 36 x 36 input tile at (2 k0 - 4) with the symmetric
+# index reflection (repeated for blocks shorter than the halo), tile row 2 kl + 5 - j for tap j; inverse:
+# 18 x 18 coefficients per band from (n0 / 2), taps 4 + par - 2 q for the three coefficients of an output
+# sample, coefficients beyond the band = 0, output cut to the forward size of the level.
+# ---------------------------------------------------------------------------------------------
+def _sym_index(i, n):
+    p = 2 * n
+    i = i % p                                    # the kernel adds p when C's % went negative
+    return i if i < n else p - 1 - i
+
+
+def emulate_dwt2_fwd(x):
+    from oracle import wavelet_oracle as wo
+    rows, cols = x.shape
+    orows, ocols = wo.dwt_len(rows), wo.dwt_len(cols)
+    bands = [np.full((orows, ocols), np.nan) for _ in range(4)]
+    FT, FIN = 16, 36
+    lo, hi = wo.DB3_DEC_LO, wo.DB3_DEC_HI
+    for by in range(-(-orows // FT)):
+        for bx in range(-(-ocols // FT)):
+            k0r, k0c = by * FT, bx * FT
+            tile = np.array([[x[_sym_index(2 * k0r - 4 + tr, rows), _sym_index(2 * k0c - 4 + tc, cols)]
+                              for tc in range(FIN)] for tr in range(FIN)])
+            s_lo = np.zeros((FT, FIN)); s_hi = np.zeros((FT, FIN))
+            for kl in range(FT):
+                for j in range(6):
+                    s_lo[kl] += lo[j] * tile[2 * kl + 5 - j]
+                    s_hi[kl] += hi[j] * tile[2 * kl + 5 - j]
+            for kr in range(FT):
+                for kc in range(FT):
+                    gr, gc = k0r + kr, k0c + kc
+                    if gr < orows and gc < ocols:
+                        l = s_lo[kr, [2 * kc + 5 - j for j in range(6)]]
+                        h = s_hi[kr, [2 * kc + 5 - j for j in range(6)]]
+                        bands[0][gr, gc] = lo @ l; bands[1][gr, gc] = hi @ l
+                        bands[2][gr, gc] = lo @ h; bands[3][gr, gc] = hi @ h
+    return dict(zip(("aa", "ad", "da", "dd"), bands))
+
+
+def emulate_dwt2_inv(c, rows, cols):
+    from oracle import wavelet_oracle as wo
+    crows, ccols = c["aa"].shape
+    out = np.full((rows, cols), np.nan)
+    IT, IK = 32, 18
+    g, gh = wo.DB3_REC_LO, wo.DB3_REC_HI
+    names = ("aa", "ad", "da", "dd")
+    for by in range(-(-rows // IT)):
+        for bx in range(-(-cols // IT)):
+            n0r, n0c = by * IT, bx * IT
+            s = np.zeros((4, IK, IK))
+            for tr in range(IK):
+                for tc in range(IK):
+                    gr, gc = n0r // 2 + tr, n0c // 2 + tc
+                    if gr < crows and gc < ccols:
+                        for b in range(4):
+                            s[b, tr, tc] = c[names[b]][gr, gc]
+            s_lo = np.zeros((IK, IT)); s_hi = np.zeros((IK, IT))
+            for tr in range(IK):
+                for nl in range(IT):
+                    p, par = nl >> 1, nl & 1
+                    for q in range(3):
+                        t = 4 + par - 2 * q
+                        s_lo[tr, nl] += s[0, tr, p + q] * g[t] + s[1, tr, p + q] * gh[t]
+                        s_hi[tr, nl] += s[2, tr, p + q] * g[t] + s[3, tr, p + q] * gh[t]
+            for ml in range(IT):
+                for nl in range(IT):
+                    gr, gc = n0r + ml, n0c + nl
+                    if gr >= rows or gc >= cols:
+                        continue
+                    p, par = ml >> 1, ml & 1
+                    out[gr, gc] = sum(s_lo[p + q, nl] * g[4 + par - 2 * q] + s_hi[p + q, nl] * gh[4 + par - 2 * q]
+                                      for q in range(3))
+    return out
+
+
+def test_wavelet_tile_index_logic():
+    from oracle import wavelet_oracle as wo
+    rng = np.random.default_rng(2)
+    for shape in ((37, 50), (64, 33), (3, 41), (1, 9), (35, 2)):
+        x = rng.standard_normal(shape)
+        got = emulate_dwt2_fwd(x)
+        ref = wo.dwt2(x)
+        for k in ref:
+            assert not np.isnan(got[k]).any(), (shape, k)
+            assert np.abs(got[k] - ref[k]).max() < 1e-12, (shape, k)
+        back = emulate_dwt2_inv(ref, *shape)              # the level's approximation, cut to its forward size
+        assert not np.isnan(back).any(), shape
+        assert np.abs(back - x).max() < 1e-12, shape      # = waverecn's trim + perfect reconstruction

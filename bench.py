@@ -607,6 +607,13 @@ def run_ours(args):
     # comparisons proper live in tests/): a bench line of a wrong result is worthless
     checks = parity_checks(hp, rows, cols, vals, w_h, v_h) if not args.no_checks else None
 
+    # passes over the matrix of one eigen solve (untimed repeat of the last step's solve, same state): every
+    # Lanczos step of a cycle plus its true-residual pass reads the 4 B/cell correlation map once
+    from hiarch_b200 import ops as _ops
+    _, _, eig_info = _ops.topk_eig(hp.sim, k=hp.k_eig, block=hp.eig_block, steps=hp.eig_steps, return_info=True,
+                                   workspace=hp._eig_ws)
+    eig_passes = int(sum(used + 1 for _, _, used in eig_info))
+
     # ---- config C3: 64 samples x 24 per-chromosome maps at 50 kb, sharded by sample over the ranks -----
     c3 = run_c3(args, world, rank, max_over_ranks, barrier) if not args.no_c3 else None
 
@@ -695,6 +702,11 @@ def run_ours(args):
             "similarity_prep": {"bytes": (4 + 2 * plane_elem_bytes) * cells,
                                 "gbs": (4 + 2 * plane_elem_bytes) * cells / prep / 1e6,
                                 "frac": (4 + 2 * plane_elem_bytes) * cells / prep / 1e6 / pk["hbm_gbs"]},
+            "topk_eig": {"passes": eig_passes, "cycles": [list(c) for c in eig_info], "bytes": 4 * cells * eig_passes,
+                         "gbs": 4 * cells * eig_passes / eig_ms / 1e6,
+                         "frac": 4 * cells * eig_passes / eig_ms / 1e6 / pk["hbm_gbs"],
+                         "note": "passes x 4 B/cell over the WHOLE stage time (step kernels, projected solve, "
+                                 "read-backs included); the pass kernel alone: profiles/launches_r2_bench_summary.txt"},
             "all_three": {"bytes": 12 * nnz + (4 + 10 + 4 + 2 * plane_elem_bytes) * cells,
                           "gbs": (12 * nnz + (18 + 2 * plane_elem_bytes) * cells) / (scat + oe_ms + prep) / 1e6,
                           "frac": (12 * nnz + (18 + 2 * plane_elem_bytes) * cells) / (scat + oe_ms + prep) / 1e6
